@@ -1,0 +1,291 @@
+// oracle_cli.cpp -- command-line driver for the CPU ORACLE (test infrastructure, not the product).
+// Accepts the subset of carmel's argv grammar (carmel/src/carmel.cc:929-1066) that the training
+// hot path needs, runs the restated reference algorithm from carmel_oracle.hpp, and can dump
+// per-example trellises / per-iteration history for the parity tests and time E-steps for the
+// CPU baseline in bench.py.
+//
+//   carmel_oracle [-t] [-HJ] [-M n] [-e w] [-X w] [-f w] [-U] [-j|-u] [-:] [-F out] [--train-cascade]
+//                 [--normby=JCN..] [--priors=a,b,..] [--dump-trellis=file] [--history=file]
+//                 [--time-estimate=K] corpus wfst [wfst ...]
+#include "carmel_oracle.hpp"
+#include "gibbs_oracle.hpp"
+#include <chrono>
+#include <sys/resource.h>
+#include <unistd.h>
+
+using namespace orc;
+
+static void write_u32(std::ostream& o, uint32_t v) { o.write((char const*)&v, 4); }
+static void write_f64(std::ostream& o, double v) { o.write((char const*)&v, 8); }
+
+// Binary trellis dump (little endian), one record per kept example:
+//   u32 n_states, u32 n_arcs, u32 fin, f64 weight, then per state (id order): u32 n_out,
+//   then n_out x (u32 dest, u32 arc_id) in the stored list order (reverse of discovery order).
+static void dump_trellis(std::ostream& o, Derivations const& d) {
+  write_u32(o, (uint32_t)d.n_states());
+  write_u32(o, (uint32_t)d.n_arcs());
+  write_u32(o, d.fin);
+  write_f64(o, d.weight);
+  for (auto const& st : d.g) {
+    write_u32(o, (uint32_t)st.size());
+    for (auto const& a : st) {
+      write_u32(o, a.dest);
+      write_u32(o, a.id);
+    }
+  }
+}
+
+static std::vector<std::string> split(std::string const& s, char c) {
+  std::vector<std::string> r;
+  std::string cur;
+  for (char ch : s) {
+    if (ch == c) {
+      r.push_back(cur);
+      cur.clear();
+    } else
+      cur.push_back(ch);
+  }
+  r.push_back(cur);
+  return r;
+}
+
+int real_main(int argc, char** argv) {
+  bool flags[256] = {0};
+  std::map<std::string, std::string> lopt;
+  std::vector<std::string> files;
+  std::vector<char> pending;
+  TrainOpts topt;
+  std::string outfile;
+  NormGroupBy default_group = CONDITIONAL;
+  for (int i = 1; i < argc; ++i) {
+    std::string arg = argv[i];
+    if (!pending.empty()) {
+      char p = pending.front();
+      pending.erase(pending.begin());
+      W w;
+      switch (p) {
+        case 'M': topt.max_iter = (unsigned)atol(arg.c_str()); break;
+        case 'e':
+          parse_weight(arg.c_str(), w);
+          topt.converge_arc_delta = w;
+          break;
+        case 'X':
+          parse_weight(arg.c_str(), w);
+          topt.converge_perplexity_ratio = w;
+          break;
+        case 'f':
+          parse_weight(arg.c_str(), w);
+          topt.smoothFloor = w;
+          break;
+        case 'o':
+          topt.learning_rate_growth_factor = std::max(1., atof(arg.c_str()));
+          break;
+        case 'F': outfile = arg; break;
+        case 'R': break;  // seed: unused (no RNG in the EM path)
+        default: break;
+      }
+      continue;
+    }
+    if (arg.size() > 1 && arg[0] == '-') {
+      if (arg[1] == '-') {
+        auto eq = arg.find('=');
+        std::string k = arg.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+        lopt[k] = eq == std::string::npos ? "" : arg.substr(eq + 1);
+      } else {
+        for (size_t k = 1; k < arg.size(); ++k) {
+          char c = arg[k];
+          flags[(unsigned char)c] = true;
+          if (strchr("MeXfoFR", c)) pending.push_back(c);
+          if (c == 'j') default_group = JOINT;
+          if (c == 'u') default_group = NONE;
+        }
+      }
+    } else
+      files.push_back(arg);
+  }
+  bool trainc = lopt.count("train-cascade") || lopt.count("crp");
+  if (trainc) flags[(unsigned)'t'] = true;
+  if (flags[(unsigned)':']) topt.cache_derivations = true;
+  topt.weight_is_prior_count = flags[(unsigned)'U'];
+  if (!flags[(unsigned)'t'] || files.size() < 2) {
+    std::cerr << "usage: carmel_oracle -t [options] corpus wfst [wfst...]\n";
+    return 1;
+  }
+  std::string corpus_file = files[0];
+  std::vector<std::string> fst_files(files.begin() + 1, files.end());
+  unsigned nChain = (unsigned)fst_files.size();
+  std::vector<std::unique_ptr<WFST>> chain;
+  for (auto const& f : fst_files) {
+    std::unique_ptr<WFST> w(new WFST());
+    if (!w->read_file(f, !flags[(unsigned)'K'])) {
+      std::cerr << "Bad format of transducer file: " << f << "\n";
+      return 2;
+    }
+    if (nChain > 1) w->named = false;  // carmel.cc:1197 unNameStates unless -m
+    chain.push_back(std::move(w));
+  }
+  // normalization methods per transducer: carmel.cc:453-477 set_vector
+  std::vector<NormalizeMethod> methods(nChain);
+  for (auto& m : methods) m.group = default_group;
+  if (lopt.count("normby")) {
+    std::string const& s = lopt["normby"];
+    for (unsigned i = 0; i < nChain; ++i) {
+      char c = i < s.size() ? s[i] : (s.empty() ? 'C' : s.back());
+      methods[i].group = (c == 'j' || c == 'J') ? JOINT : (c == 'c' || c == 'C') ? CONDITIONAL : NONE;
+    }
+  }
+  if (lopt.count("priors")) {
+    auto v = split(lopt["priors"], ',');
+    for (unsigned i = 0; i < nChain; ++i) {
+      std::string const& t = i < v.size() ? v[i] : v.back();
+      W w;
+      parse_weight(t.c_str(), w);
+      methods[i].add_count = w;
+    }
+  }
+  Cascade cascade(trainc && nChain >= 2);
+  if (nChain < 2 && !cascade.trivial) cascade.set_trivial();
+  // carmel.cc:1286-1355: result = chain[0]; minimize (reduce) ; compose left to right
+  WFST* result = chain[0].get();
+  if (!flags[(unsigned)'d']) result->reduce();
+  std::vector<std::unique_ptr<WFST>> composed_keep;
+  cascade.add(result);
+  bool first = true;
+  for (unsigned i = 1; i < nChain && result->valid(); ++i, first = false) {
+    cascade.add(chain[i].get());
+    if (first)
+      cascade.prepare_compose(false, false);
+    else
+      cascade.prepare_compose(true, false);
+    std::unique_ptr<WFST> next = compose(cascade, *result, *chain[i]);
+    std::cerr << "\n\t(" << next->numStates() << " states / " << next->numArcs() << " arcs";
+    if (!next->valid()) {
+      std::cerr << ")\nEmpty or invalid result of composition with transducer \"" << fst_files[i] << "\".\n";
+      return 3;
+    }
+    unsigned st = next->numStates();
+    size_t na = next->numArcs();
+    if (!flags[(unsigned)'d']) next->reduce();
+    if (next->numStates() != st || next->numArcs() != na)
+      std::cerr << " reduce-> " << next->numStates() << "/" << next->numArcs();
+    std::cerr << ")";
+    composed_keep.push_back(std::move(next));
+    result = composed_keep.back().get();
+    cascade.done_composing(result);
+  }
+  if (nChain == 1) cascade.set_composed(result);
+  std::cerr << std::endl;
+  if (!result->valid()) {
+    std::cerr << "invalid transducer\n";
+    return 3;
+  }
+  if (lopt.count("write-composed")) {
+    std::ofstream o(lopt["write-composed"]);
+    result->write(o, true, true, true);
+  }
+  Corpus corpus;
+  {
+    std::ifstream cf(corpus_file);
+    if (!cf) {
+      std::cerr << "File " << corpus_file << " could not be opened for input.\n";
+      return 9;
+    }
+    corpus.read(cf, *result);
+  }
+  if (cascade.trivial) methods.resize(1);
+
+  if (lopt.count("crp")) return gibbs_main(*result, cascade, corpus, methods, topt, lopt, flags, fst_files, chain);
+
+  Trainer tr(*result, cascade, corpus, methods, topt, std::cerr);
+
+  if (lopt.count("dump-trellis")) {  // dump the pruned trellises (before training)
+    std::ofstream o(lopt["dump-trellis"], std::ios::binary);
+    IOIndex io(*result);
+    uint32_t n = 0;
+    std::ostringstream body;
+    for (auto const& e : corpus.examples) {
+      Derivations d;
+      d.in = e.in;
+      d.out = e.out;
+      d.weight = e.weight;
+      if (d.compute(*result, io, tr.arcs)) {
+        dump_trellis(body, d);
+        ++n;
+      }
+    }
+    write_u32(o, n);
+    write_u32(o, (uint32_t)tr.arcs.size());
+    o << body.str();
+  }
+  if (lopt.count("time-estimate")) {  // CPU baseline: time K E-steps (+M-steps) on this corpus
+    unsigned K = (unsigned)atoi(lopt["time-estimate"].c_str());
+    cascade.update();
+    W up;
+    tr.estimate(up);  // warm-up (also drops examples without derivations, builds cache if -:)
+    tr.maximize(1);
+    auto t0 = std::chrono::steady_clock::now();
+    for (unsigned k = 0; k < K; ++k) {
+      cascade.update();
+      tr.estimate(up);
+      tr.maximize(1);
+    }
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("{\"iters\": %u, \"seconds\": %.6f, \"trellis_arcs\": %zu, \"trellis_states\": %zu, \"examples\": %u, "
+                "\"ln_prob\": %.17g, \"cached\": %s}\n",
+                K, dt, tr.total_trellis_arcs, tr.total_trellis_states, corpus.n_pairs, up.w,
+                topt.cache_derivations ? "true" : "false");
+    return 0;
+  }
+
+  tr.train();
+
+  if (lopt.count("history")) {
+    std::ofstream o(lopt["history"]);
+    o.precision(17);
+    for (auto const& h : tr.history) o << h.iter << " " << h.ln_prob << " " << h.ln_weighted_prob << " " << h.max_change << "\n";
+  }
+  bool full = flags[(unsigned)'J'], onearc = flags[(unsigned)'H'];
+  WeightFormat wf;
+  if (flags[(unsigned)'B']) wf.base = WeightFormat::LOG10;
+  else if (flags[(unsigned)'2']) wf.base = WeightFormat::LN;
+  if (flags[(unsigned)'Z']) wf.thresh = WeightFormat::ALWAYS;
+  if (flags[(unsigned)'D']) wf.thresh = WeightFormat::NEVER;
+  if (trainc && !cascade.trivial) {  // cascade.h:23-32 write_trained
+    for (unsigned i = 0; i < nChain; ++i) {
+      std::string ft = fst_files[i] + ".trained";
+      std::cerr << "Writing trained " << fst_files[i] << " to " << ft << std::endl;
+      std::ofstream of(ft);
+      chain[i]->named = true;
+      chain[i]->write(of, full, onearc, false, wf);
+    }
+  } else if (trainc) {
+    std::string ft = fst_files[0] + ".trained";
+    std::ofstream of(ft);
+    result->write(of, full, onearc, false, wf);
+  } else {
+    if (!outfile.empty()) {
+      std::ofstream of(outfile);
+      result->write(of, full, onearc, false, wf);
+    } else
+      result->write(std::cout, full, onearc, false, wf);
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  // the reference's trellis construction is recursive (derivations.h:640-704): give it stack
+  struct rlimit rl;
+  if (getrlimit(RLIMIT_STACK, &rl) == 0 && rl.rlim_cur != RLIM_INFINITY && rl.rlim_cur < (1ull << 30)) {
+    rl.rlim_cur = std::min<rlim_t>(rl.rlim_max, 1ull << 30);
+    if (setrlimit(RLIMIT_STACK, &rl) == 0 && !getenv("ORC_REEXEC")) {
+      setenv("ORC_REEXEC", "1", 1);
+      execv("/proc/self/exe", argv);
+    }
+  }
+  try {
+    return real_main(argc, argv);
+  } catch (std::exception& e) {
+    std::cerr << "ERROR: " << e.what() << "\n";
+    return 11;
+  }
+}
