@@ -1,0 +1,267 @@
+"""ctypes binding of include/carmel_b200.h (the C ABI of the B200-native carmel training path).
+
+This is plumbing for tests, bench.py and the Python driver; the product is the CUDA library.  The
+loader fails loudly when libcarmel_b200.so is missing: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libcarmel_b200.so")
+CLI_PATH = os.path.join(_HERE, "_build", "carmel-b200")
+
+SPACE_LOG, SPACE_SCALED = 0, 1
+NO_GROUP = 0xFFFFFFFF
+LOCKED_GROUP = 0
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV = 0, -1, -2, -3, -4, -5
+
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+
+
+class CmlModel(C.Structure):
+    _fields_ = [
+        ("n_arcs", C.c_uint32), ("chain_off", _u32p), ("chain_param", _u32p), ("arc_prior", _f64p),
+        ("n_params", C.c_uint32), ("param_group", _u32p), ("param_tie", _u32p), ("n_groups", C.c_uint32),
+        ("group_add", _f64p), ("n_ties", C.c_uint32),
+    ]
+
+
+class CmlTrellisBatch(C.Structure):
+    _fields_ = [
+        ("n_ex", C.c_uint64), ("ex_states", _u32p), ("ex_fin", _u32p), ("ex_weight", _f64p),
+        ("arc_off", _u32p), ("arc_dst", _u32p), ("arc_id", _u32p),
+    ]
+
+
+class CmlEstimateResult(C.Structure):
+    _fields_ = [("sum_ln_p", C.c_double), ("sum_w_ln_p", C.c_double), ("n_zero", C.c_uint64)]
+
+
+class CarmelB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"carmel_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libcarmel_b200.so (built by carmel_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            f"{p} not found: build it with `python carmel_b200/build.py` (nvcc, sm_100a). "
+            "carmel_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    vp = C.c_void_p
+    lib.cml_version.restype = C.c_char_p
+    lib.cml_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+    lib.cml_destroy.argtypes = [vp]
+    lib.cml_destroy.restype = None
+    lib.cml_last_error.argtypes = [vp]
+    lib.cml_last_error.restype = C.c_char_p
+    lib.cml_set_stream.argtypes = [vp, vp]
+    lib.cml_synchronize.argtypes = [vp]
+    lib.cml_launch_count.argtypes = [vp]
+    lib.cml_launch_count.restype = C.c_uint64
+    lib.cml_set_model.argtypes = [vp, C.POINTER(CmlModel)]
+    lib.cml_set_params.argtypes = [vp, _f64p]
+    lib.cml_get_params.argtypes = [vp, _f64p]
+    lib.cml_snapshot_params.argtypes = [vp, C.c_int]
+    lib.cml_restore_params.argtypes = [vp, C.c_int]
+    lib.cml_add_trellises.argtypes = [vp, C.POINTER(CmlTrellisBatch)]
+    lib.cml_clear_trellises.argtypes = [vp]
+    lib.cml_trellis_totals.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
+    lib.cml_get_example_layout.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u32p]
+    lib.cml_estimate.argtypes = [vp, C.POINTER(CmlEstimateResult)]
+    lib.cml_estimate_launch.argtypes = [vp]
+    lib.cml_estimate_finish.argtypes = [vp, C.POINTER(CmlEstimateResult)]
+    lib.cml_get_example_logprob.argtypes = [vp, _f64p, C.c_uint64]
+    lib.cml_get_arc_counts.argtypes = [vp, _f64p]
+    lib.cml_reduce_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    lib.cml_use_reduce_buffer.argtypes = [vp, vp, C.c_uint64]
+    lib.cml_maximize.argtypes = [vp, C.c_double, _f64p]
+    lib.cml_normalize_params.argtypes = [vp]
+    lib.cml_exported_symbols.argtypes = [C.POINTER(C.c_size_t)]
+    lib.cml_exported_symbols.restype = C.POINTER(C.c_char_p)
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    lib = load_library()
+    n = C.c_size_t()
+    arr = lib.cml_exported_symbols(C.byref(n))
+    return [arr[i].decode() for i in range(n.value)]
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: np.ndarray | None, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+class Context:
+    """One GPU's training context (cml_ctx).  Mirrors the reference's forward_backward object
+    (carmel/src/train.cc:224-460): estimate(), maximize(), save_best / load_best."""
+
+    def __init__(self, device: int = 0, precision: int = 64, space: int = SPACE_LOG):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.cml_create(C.byref(h), device, precision, space)
+        if rc != 0:
+            raise CarmelB200Error(rc, self.lib.cml_last_error(None).decode())
+        self.h = h
+        self.n_arcs = 0
+        self.n_params = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cml_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CarmelB200Error(rc, self.lib.cml_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.cml_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.cml_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.cml_launch_count(self.h))
+
+    def set_model(self, n_arcs, n_params, param_group, param_tie, n_groups, chain_off=None, chain_param=None,
+                  arc_prior=None, group_add=None, n_ties=0):
+        keep = []
+        m = CmlModel()
+        m.n_arcs, m.n_params, m.n_groups, m.n_ties = int(n_arcs), int(n_params), int(n_groups), int(n_ties)
+
+        def u32(a):
+            if a is None:
+                return None
+            a = _u32(a)
+            keep.append(a)
+            return _ptr(a, _u32p)
+
+        def f64(a):
+            if a is None:
+                return None
+            a = _f64(a)
+            keep.append(a)
+            return _ptr(a, _f64p)
+
+        m.chain_off, m.chain_param = u32(chain_off), u32(chain_param)
+        m.arc_prior, m.group_add = f64(arc_prior), f64(group_add)
+        m.param_group, m.param_tie = u32(param_group), u32(param_tie)
+        self._check(self.lib.cml_set_model(self.h, C.byref(m)))
+        self.n_arcs, self.n_params = int(n_arcs), int(n_params)
+
+    def set_trivial_model(self, n_arcs: int):
+        """arc i == parameter i, one joint group, nothing locked (enough for E-step tests)."""
+        self.set_model(n_arcs, n_arcs, np.zeros(n_arcs, np.uint32), np.full(n_arcs, NO_GROUP, np.uint32), 1)
+
+    def set_params(self, ln_w):
+        a = _f64(ln_w)
+        assert a.size == self.n_params
+        self._check(self.lib.cml_set_params(self.h, _ptr(a, _f64p)))
+
+    def get_params(self) -> np.ndarray:
+        a = np.empty(self.n_params, np.float64)
+        self._check(self.lib.cml_get_params(self.h, _ptr(a, _f64p)))
+        return a
+
+    def snapshot_params(self, slot: int = 0):
+        self._check(self.lib.cml_snapshot_params(self.h, slot))
+
+    def restore_params(self, slot: int = 0):
+        self._check(self.lib.cml_restore_params(self.h, slot))
+
+    def add_trellises(self, ex_states, ex_fin, ex_weight, arc_off, arc_dst, arc_id):
+        b = CmlTrellisBatch()
+        es, ef, ew = _u32(ex_states), _u32(ex_fin), _f64(ex_weight)
+        ao, ad, ai = _u32(arc_off), _u32(arc_dst), _u32(arc_id)
+        b.n_ex = es.size
+        b.ex_states, b.ex_fin, b.ex_weight = _ptr(es, _u32p), _ptr(ef, _u32p), _ptr(ew, _f64p)
+        b.arc_off, b.arc_dst, b.arc_id = _ptr(ao, _u32p), _ptr(ad, _u32p), _ptr(ai, _u32p)
+        self._check(self.lib.cml_add_trellises(self.h, C.byref(b)))
+
+    def clear_trellises(self):
+        self._check(self.lib.cml_clear_trellises(self.h))
+
+    def trellis_totals(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.lib.cml_trellis_totals(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("examples", "states", "arcs", "levels"), (int(x.value) for x in v)))
+
+    def example_layout(self, e: int, n_states: int):
+        nl = C.c_uint32()
+        lev = np.empty(n_states, np.uint32)
+        loc = np.empty(n_states, np.uint32)
+        self._check(self.lib.cml_get_example_layout(self.h, e, C.byref(nl), _ptr(lev, _u32p), _ptr(loc, _u32p)))
+        return int(nl.value), lev, loc
+
+    def estimate(self) -> CmlEstimateResult:
+        r = CmlEstimateResult()
+        self._check(self.lib.cml_estimate(self.h, C.byref(r)))
+        return r
+
+    def estimate_launch(self):
+        self._check(self.lib.cml_estimate_launch(self.h))
+
+    def estimate_finish(self) -> CmlEstimateResult:
+        r = CmlEstimateResult()
+        self._check(self.lib.cml_estimate_finish(self.h, C.byref(r)))
+        return r
+
+    def example_logprob(self, n: int) -> np.ndarray:
+        a = np.empty(n, np.float64)
+        self._check(self.lib.cml_get_example_logprob(self.h, _ptr(a, _f64p), n))
+        return a
+
+    def arc_counts(self) -> np.ndarray:
+        a = np.empty(self.n_arcs, np.float64)
+        self._check(self.lib.cml_get_arc_counts(self.h, _ptr(a, _f64p)))
+        return a
+
+    def reduce_buffer(self) -> tuple[int, int]:
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self.lib.cml_reduce_buffer(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def use_reduce_buffer(self, device_ptr: int | None, n_doubles: int = 0):
+        self._check(self.lib.cml_use_reduce_buffer(self.h, C.c_void_p(device_ptr or 0), n_doubles))
+
+    def maximize(self, rate: float = 1.0) -> float:
+        d = C.c_double()
+        self._check(self.lib.cml_maximize(self.h, rate, C.byref(d)))
+        return float(d.value)
+
+    def normalize_params(self):
+        self._check(self.lib.cml_normalize_params(self.h))

@@ -1,0 +1,75 @@
+"""Build the carmel_b200 native code in-tree.
+
+  libcarmel_b200.so   CUDA kernels + C ABI (include/carmel_b200.h), sm_100a only
+  carmel-b200         host C++ command line (carmel's -t / --train-cascade / --crp grammar)
+
+nvcc cross-compiles without a GPU.  Outputs land in carmel_b200/_build/ (git-ignored, but they
+travel to the GPU box with the gpurun snapshot).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libcarmel_b200.so")
+CLI = os.path.join(OUT, "carmel-b200")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: carmel_b200 cannot be built (there is no CPU fallback)")
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(dirpath: str) -> list[str]:
+    out = []
+    for base, _, files in os.walk(dirpath):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                out.append(os.path.join(base, f))
+    return out
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OUT, exist_ok=True)
+    deps = _sources(CSRC) + [os.path.join(ROOT, "include", "carmel_b200.h"), os.path.abspath(__file__)]
+    if not force and _newer(LIB, deps) and _newer(CLI, deps):
+        return LIB
+    nvcc = _nvcc()
+    cu = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    host = os.path.join(CSRC, "host")
+    host_cpp = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")] if os.path.isdir(host) else []
+    lib_cpp = [f for f in host_cpp if not f.endswith("main.cpp")]
+    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-o", LIB, *cu, *lib_cpp, "-lcudart"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    main = os.path.join(host, "main.cpp")
+    if os.path.exists(main):
+        cmd = ["g++", "-O3", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", CLI, main,
+               "-L", OUT, "-lcarmel_b200", "-Wl,-rpath,$ORIGIN"]
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

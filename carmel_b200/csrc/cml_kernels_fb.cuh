@@ -1,0 +1,399 @@
+// cml_kernels_fb.cuh -- forward / backward / expected-count kernels over layered-CSR trellises.
+//
+// Follows (does not copy) the reference's per-example E-step:
+//   forward   propagate_paths_in_order over the DFS order   graehl/shared/graph.h:391-402,
+//                                                           carmel/src/derivations.h:406-408
+//   backward  same on the reversed graph                    derivations.h:410-412
+//   counts    counts[id] += w*alpha[src]*beta[dst]*exw/P    derivations.h:439-447
+// B200 mapping: one example per thread group (a warp, or a whole CTA for wide lattices); the
+// group walks the example's topological levels in order, every thread owns destination states of
+// the current level and PULLS over that state's incoming arcs (8-byte {src,id} records streamed
+// from HBM exactly once per pass, coalesced along the arc array), state scores alpha/beta live in
+// shared memory for the whole example so they never touch HBM.  Backward and the count
+// accumulation are fused (one pass over the outgoing-arc CSR).
+//
+// Two arithmetic spaces (cml_space):
+//   LOG     scores are natural logs, (+) is an online max-shifted log-sum-exp.  Same semiring as
+//           the reference's logweight (graehl/shared/weight.h:737-801) up to summation order.
+//   SCALED  scores are linear with a per-level power-of-two scale (alpha_hat = alpha * 2^E[level]),
+//           renormalised whenever a level's maximum drifts out of a safe exponent window, so any
+//           length of example keeps full mantissa precision; (+) is one FMA per arc.
+#pragma once
+#include "cml_common.cuh"
+
+namespace cmlk {
+
+template <typename Real>
+struct Num;
+template <>
+struct Num<double> {
+  static __device__ __forceinline__ double ninf() { return -CUDART_INF; }
+  static __device__ __forceinline__ double ex(double x) { return exp(x); }
+  static __device__ __forceinline__ double lg(double x) { return log(x); }
+  static __device__ __forceinline__ int expo(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
+  static constexpr int kBias = 1023;
+  static constexpr int kLo = 1023 - 400;   // renormalise when the level max is below 2^-400
+  static constexpr int kHi = 1023 + 400;
+  static __device__ __forceinline__ double scale2(double x, int k) { return scalbn(x, k); }
+};
+template <>
+struct Num<float> {
+  static __device__ __forceinline__ float ninf() { return -CUDART_INF_F; }
+  static __device__ __forceinline__ float ex(float x) { return __expf(x); }
+  static __device__ __forceinline__ float lg(float x) { return __logf(x); }
+  static __device__ __forceinline__ int expo(float x) { return (__float_as_int(x) >> 23) & 0xff; }
+  static constexpr int kBias = 127;
+  static constexpr int kLo = 127 - 24;  // keep every level's max within 2^-24 .. 2^24
+  static constexpr int kHi = 127 + 24;
+  static __device__ __forceinline__ float scale2(float x, int k) { return scalbnf(x, k); }
+};
+
+struct FbArgs {
+  const CmlExDesc* desc;      // per example
+  const uint32_t* ex_list;    // examples handled by this launch (indices into desc)
+  uint32_t n_list;
+  const uint32_t* lvl_off;
+  const uint32_t* in_off;
+  const uint2* in_arc;        // {src layered index, arc id}
+  const uint32_t* out_off;
+  const uint2* out_arc;       // {dst layered index, arc id}
+  const void* arc_w;          // Real[n_arcs]: ln w (LOG) or w (SCALED)
+  double* counts;             // [n_arcs] linear expected counts (atomicAdd)
+  double* ex_lnp;             // [n_ex in batch] ln P_e
+  void* scratch;              // GLOBAL class: Real alpha/beta slots, 2 per state
+  int* scratch_lvl;           // GLOBAL class, SCALED: E/F per level (2 per level)
+  uint32_t cap_states;        // shared-memory state capacity per group (WARP / CTA classes)
+};
+
+// ---------------------------------------------------------------------------------------------
+// group helpers: a "group" is one warp (CTA == false) or the whole CTA (CTA == true)
+// ---------------------------------------------------------------------------------------------
+template <bool CTA>
+__device__ __forceinline__ void group_sync() {
+  if (CTA)
+    __syncthreads();
+  else
+    __syncwarp();
+}
+
+// max over the group of a per-thread int; smax = 2 ints of shared memory (CTA only), par = parity
+template <bool CTA>
+__device__ __forceinline__ int group_max_and_sync(int v, int* smax, int par) {
+  v = __reduce_max_sync(0xffffffffu, v);
+  if (!CTA) {
+    __syncwarp();
+    return v;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(&smax[par], v);
+  __syncthreads();
+  int r = smax[par];
+  if (threadIdx.x == 0) smax[par ^ 1] = INT_MIN;  // ready for the next level (ordered by the next sync)
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LOG space
+// ---------------------------------------------------------------------------------------------
+template <typename Real, bool CTA>
+__device__ void fb_example_log(const FbArgs& A, const CmlExDesc& d, Real* __restrict__ al, Real* __restrict__ be,
+                               int lane, int G) {
+  const Real* __restrict__ w = (const Real*)A.arc_w;
+  const uint32_t* __restrict__ lvl = A.lvl_off + d.lvl_base;
+  const uint32_t* __restrict__ ioff = A.in_off + d.row_base;
+  const uint32_t* __restrict__ ooff = A.out_off + d.row_base;
+  const uint2* __restrict__ iarc = A.in_arc + d.arc_base;
+  const uint2* __restrict__ oarc = A.out_arc + d.arc_base;
+  const Real NI = Num<Real>::ninf();
+  const uint32_t n = d.n_states, nl = d.n_levels;
+
+  // level 0 (states without predecessors): the start state (layered index 0) has alpha = 1
+  for (uint32_t s = lane; s < lvl[1]; s += G) al[s] = (s == 0) ? Real(0) : NI;
+  group_sync<CTA>();
+  for (uint32_t L = 1; L < nl; ++L) {
+    const uint32_t s1 = lvl[L + 1];
+    for (uint32_t s = lvl[L] + lane; s < s1; s += G) {
+      uint32_t k = ioff[s];
+      const uint32_t k1 = ioff[s + 1];
+      Real m = NI, acc = 0;
+      for (; k < k1; ++k) {
+        const uint2 r = __ldg(&iarc[k]);
+        const Real v = al[r.x] + __ldg(&w[r.y]);
+        if (v > m) {
+          acc = acc * Num<Real>::ex(m - v) + Real(1);
+          m = v;
+        } else if (v > NI) {
+          acc += Num<Real>::ex(v - m);
+        }
+      }
+      al[s] = (m > NI) ? m + Num<Real>::lg(acc) : NI;
+    }
+    group_sync<CTA>();
+  }
+  const Real lnP = al[d.fin];
+  if (lane == 0) A.ex_lnp[d.ex_index] = (double)lnP;
+  if (!(lnP > NI)) return;  // zero-probability example: contributes no counts (uniform branch)
+  const Real cbase = (Real)d.ln_weight - lnP;
+
+  // backward, fused with counts.  beta[fin] = 1; every other state pulls over its outgoing arcs.
+  for (int L = (int)nl - 1; L >= 0; --L) {
+    const uint32_t s1 = lvl[L + 1];
+    for (uint32_t s = lvl[L] + lane; s < s1; s += G) {
+      uint32_t k = ooff[s];
+      const uint32_t k1 = ooff[s + 1];
+      Real m = NI, acc = 0;
+      if (s == d.fin) {
+        m = 0;
+        acc = 1;
+      }
+      const Real as = al[s] + cbase;
+      for (; k < k1; ++k) {
+        const uint2 r = __ldg(&oarc[k]);
+        const Real v = __ldg(&w[r.y]) + be[r.x];
+        if (v > m) {
+          acc = acc * Num<Real>::ex(m - v) + Real(1);
+          m = v;
+        } else if (v > NI) {
+          acc += Num<Real>::ex(v - m);
+        }
+        const Real lc = as + v;
+        if (lc > Real(-700)) {
+          const double c = (double)Num<Real>::ex(lc);
+          if (c > 0) atomicAdd(&A.counts[r.y], c);
+        }
+      }
+      be[s] = (m > NI) ? m + Num<Real>::lg(acc) : NI;
+    }
+    group_sync<CTA>();
+  }
+  (void)n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SCALED space
+// ---------------------------------------------------------------------------------------------
+// alpha_hat[s] = alpha[s] * 2^E[level(s)] ; beta_hat[s] = beta[s] * 2^F[level(s)].
+// lvl_min_src[L] / lvl_max_dst[L] (stored interleaved after the level offsets by the flattener)
+// bound the levels a level's arcs reach, so the common case (no renormalisation inside that
+// window) needs no per-arc exponent work at all.
+template <typename Real, bool CTA>
+__device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __restrict__ al, Real* __restrict__ be,
+                                  int* __restrict__ E, int* __restrict__ F, int* smax, int lane, int G) {
+  const Real* __restrict__ w = (const Real*)A.arc_w;
+  const uint32_t* __restrict__ lvl = A.lvl_off + d.lvl_base;
+  const uint32_t nl = d.n_levels;
+  const uint32_t* __restrict__ lvl_min_src = lvl + (nl + 1);      // [nl]
+  const uint32_t* __restrict__ lvl_max_dst = lvl + (nl + 1) + nl;  // [nl]
+  const uint32_t* __restrict__ ioff = A.in_off + d.row_base;
+  const uint32_t* __restrict__ ooff = A.out_off + d.row_base;
+  const uint2* __restrict__ iarc = A.in_arc + d.arc_base;
+  const uint2* __restrict__ oarc = A.out_arc + d.arc_base;
+
+  auto level_of = [&](uint32_t s) -> uint32_t {  // binary search (slow path only)
+    uint32_t lo = 0, hi = nl;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (lvl[mid] <= s)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    return lo;
+  };
+
+  for (uint32_t s = lane; s < lvl[1]; s += G) al[s] = (s == 0) ? Real(1) : Real(0);
+  if (lane == 0) E[0] = 0;
+  if (CTA && threadIdx.x == 0) smax[0] = smax[1] = INT_MIN;
+  group_sync<CTA>();
+  int par = 0;
+  uint32_t last_event = 0;  // highest level j with E[j] != E[j-1]
+  for (uint32_t L = 1; L < nl; ++L) {
+    const uint32_t s0 = lvl[L], s1 = lvl[L + 1];
+    const int Eprev = E[L - 1];
+    const bool uniform = (last_event <= lvl_min_src[L]);
+    int mx = 0;
+    for (uint32_t s = s0 + lane; s < s1; s += G) {
+      uint32_t k = ioff[s];
+      const uint32_t k1 = ioff[s + 1];
+      Real acc = 0;
+      if (uniform) {
+        for (; k < k1; ++k) {
+          const uint2 r = __ldg(&iarc[k]);
+          acc = fma(al[r.x], __ldg(&w[r.y]), acc);
+        }
+      } else {
+        for (; k < k1; ++k) {
+          const uint2 r = __ldg(&iarc[k]);
+          const int de = Eprev - E[level_of(r.x)];  // bring the source up to the previous level's scale
+          acc += Num<Real>::scale2(al[r.x] * __ldg(&w[r.y]), de);
+        }
+      }
+      al[s] = acc;
+      mx = max(mx, Num<Real>::expo(acc));
+    }
+    mx = group_max_and_sync<CTA>(mx, smax, par);
+    par ^= 1;
+    int shift = 0;
+    if (mx != 0 && (mx < Num<Real>::kLo || mx > Num<Real>::kHi)) shift = Num<Real>::kBias - mx;
+    if (shift != 0) {
+      for (uint32_t s = s0 + lane; s < s1; s += G) al[s] = Num<Real>::scale2(al[s], shift);
+    }
+    if (shift != 0) last_event = L;
+    if (lane == 0) E[L] = Eprev + shift;
+    group_sync<CTA>();
+  }
+  const uint32_t Lfin = level_of(d.fin);
+  const Real afin = al[d.fin];
+  const int Efin = E[Lfin];
+  const double lnP = (afin > 0) ? log((double)afin) - (double)Efin * 0.69314718055994530942 : -CUDART_INF;
+  if (lane == 0) A.ex_lnp[d.ex_index] = lnP;
+  if (!(afin > 0)) return;
+  const double cw = d.weight / (double)afin;
+
+  // backward + counts
+  if (CTA && threadIdx.x == 0) smax[0] = smax[1] = INT_MIN;
+  group_sync<CTA>();
+  par = 0;
+  uint32_t last_event_b = 0xFFFFFFFFu;  // lowest level j with F[j] != F[j+1]
+  for (int L = (int)nl - 1; L >= 0; --L) {
+    const uint32_t s0 = lvl[L], s1 = lvl[L + 1];
+    const bool last = (L == (int)nl - 1);
+    const int Fnext = last ? 0 : F[L + 1];
+    const bool uniform = last || (last_event_b >= lvl_max_dst[L]);
+    // count scale for this level: 2^(Efin - E[L] - Fnext) * exw / alpha_hat[fin]
+    const double cs = scalbn(cw, Efin - E[L] - Fnext);
+    int mx = 0;
+    for (uint32_t s = s0 + lane; s < s1; s += G) {
+      uint32_t k = ooff[s];
+      const uint32_t k1 = ooff[s + 1];
+      Real acc = (s == d.fin) ? Num<Real>::scale2(Real(1), Fnext) : Real(0);
+      const double as = (double)al[s] * cs;
+      if (uniform) {
+        for (; k < k1; ++k) {
+          const uint2 r = __ldg(&oarc[k]);
+          const Real t = __ldg(&w[r.y]) * be[r.x];
+          acc += t;
+          const double c = as * (double)t;
+          if (c > 0) atomicAdd(&A.counts[r.y], c);
+        }
+      } else {
+        for (; k < k1; ++k) {
+          const uint2 r = __ldg(&oarc[k]);
+          const int de = Fnext - F[level_of(r.x)];
+          const Real t = Num<Real>::scale2(__ldg(&w[r.y]) * be[r.x], de);
+          acc += t;
+          const double c = as * (double)t;
+          if (c > 0) atomicAdd(&A.counts[r.y], c);
+        }
+      }
+      be[s] = acc;
+      mx = max(mx, Num<Real>::expo(acc));
+    }
+    mx = group_max_and_sync<CTA>(mx, smax, par);
+    par ^= 1;
+    int shift = 0;
+    if (mx != 0 && (mx < Num<Real>::kLo || mx > Num<Real>::kHi)) shift = Num<Real>::kBias - mx;
+    if (shift != 0) {
+      for (uint32_t s = s0 + lane; s < s1; s += G) be[s] = Num<Real>::scale2(be[s], shift);
+    }
+    if (shift != 0) last_event_b = (uint32_t)L;
+    if (lane == 0) F[L] = Fnext + shift;
+    group_sync<CTA>();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels.  WARP: blockDim = 128 (4 examples per CTA), alpha/beta in shared memory.
+//           CTA : blockDim = 256, one example per CTA, alpha/beta in shared memory.
+//           GLOBAL: blockDim = 256, one example per CTA, alpha/beta in an HBM/L2 scratch.
+// Shared memory per group: cap*2 Reals (+ 2*cap ints of level exponents in SCALED space).
+// ---------------------------------------------------------------------------------------------
+template <typename Real, bool SCALED>
+__global__ void __launch_bounds__(128) k_fb_warp(FbArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t li = blockIdx.x * 4 + warp;
+  if (li >= A.n_list) return;
+  const CmlExDesc d = A.desc[A.ex_list[li]];
+  const size_t per = (size_t)A.cap_states * (2 * sizeof(Real) + (SCALED ? 2 * sizeof(int) : 0));
+  unsigned char* base = smem + per * warp;
+  Real* al = (Real*)base;
+  Real* be = al + A.cap_states;
+  if (SCALED) {
+    int* E = (int*)(be + A.cap_states);
+    int* F = E + A.cap_states;
+    fb_example_scaled<Real, false>(A, d, al, be, E, F, nullptr, lane, 32);
+  } else {
+    fb_example_log<Real, false>(A, d, al, be, lane, 32);
+  }
+}
+
+template <typename Real, bool SCALED, bool GLOBAL>
+__global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int smax[2];
+  const uint32_t li = blockIdx.x;
+  if (li >= A.n_list) return;
+  const CmlExDesc d = A.desc[A.ex_list[li]];
+  Real *al, *be;
+  int *E = nullptr, *F = nullptr;
+  if (GLOBAL) {
+    al = (Real*)A.scratch + 2 * d.scratch_base;
+    be = al + d.n_states;
+    if (SCALED) {
+      E = A.scratch_lvl + 2 * d.scratch_base;  // n_levels <= n_states
+      F = E + d.n_states;
+    }
+  } else {
+    al = (Real*)smem;
+    be = al + A.cap_states;
+    if (SCALED) {
+      E = (int*)(be + A.cap_states);
+      F = E + A.cap_states;
+    }
+  }
+  if (SCALED)
+    fb_example_scaled<Real, true>(A, d, al, be, E, F, smax, threadIdx.x, blockDim.x);
+  else
+    fb_example_log<Real, true>(A, d, al, be, threadIdx.x, blockDim.x);
+}
+
+// Sum of ln P_e, w_e ln P_e and the zero-probability count over a batch (deterministic per block,
+// one atomicAdd triple per block into the reduce buffer's scalar tail).
+__global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const CmlExDesc* __restrict__ desc,
+                                                    uint64_t n, double* __restrict__ scal) {
+  double s0 = 0, s1 = 0, nz = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double lp = ex_lnp[desc[i].ex_index];
+    if (lp > -CUDART_INF) {
+      s0 += lp;
+      s1 += desc[i].weight * lp;
+    } else
+      nz += 1;
+  }
+  for (int o = 16; o; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
+  }
+  __shared__ double sh[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[0][warp] = s0;
+    sh[1][warp] = s1;
+    sh[2][warp] = nz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += sh[0][i];
+      b += sh[1][i];
+      c += sh[2][i];
+    }
+    atomicAdd(&scal[0], a);
+    atomicAdd(&scal[1], b);
+    atomicAdd(&scal[2], c);
+  }
+}
+
+}  // namespace cmlk

@@ -1,0 +1,227 @@
+// cml_kernels_model.cuh -- parameter-table kernels: cascade chain products (K6), chain count
+// distribution (K4) and the normalisation M-step (K5).  All fp64, log domain, so the M-step has the
+// reference's dynamic range (weights like e^-900 survive).
+//
+// Reference semantics restated here:
+//   cascade_parameters::calculate_chain_weights / update   carmel/src/cascade.h:426-433,466-479
+//   for_arcs::prep_new_weights                               carmel/src/train.cc:134-153
+//   cascade_parameters::distribute_counts                    carmel/src/cascade.h:286-325
+//   WFST::normalize (locked '!' and tied '!N' arcs)          carmel/src/fst.cc:86-244
+//   for_arcs::overrelax / max_change                         carmel/src/train.cc:157-182
+#pragma once
+#include "cml_common.cuh"
+
+namespace cmlk {
+
+__device__ __forceinline__ double lse2(double a, double b) {  // ln(e^a + e^b), -inf safe
+  if (!(a > -CUDART_INF)) return b;
+  if (!(b > -CUDART_INF)) return a;
+  const double m = fmax(a, b);
+  return m + log1p(exp(-fabs(a - b)));
+}
+// ln(e^a - e^b) clamped at zero like logweight operator- (weight.h:803-830)
+__device__ __forceinline__ double lsub(double a, double b) {
+  if (!(b > -CUDART_INF)) return a;
+  const double rd = b - a;
+  if (rd >= 0) return -CUDART_INF;
+  if (rd < -36.) return a;
+  return a + log1p(-exp(rd));
+}
+// warp-wide max-shifted log-sum-exp of one value per lane
+__device__ __forceinline__ double warp_lse(double v) {
+  double m = v;
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (!(m > -CUDART_INF)) return -CUDART_INF;
+  double s = (v > -CUDART_INF) ? exp(v - m) : 0.;
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return m + log(s);
+}
+__device__ __forceinline__ double warp_max(double m) {
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+// K6: arc weight = product of its chain's parameters.  out_real = ln w (LOG) or w (SCALED) as Real.
+template <typename Real, bool SCALED>
+__global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
+                              const uint32_t* __restrict__ chain_param, const double* __restrict__ ln_w,
+                              double* __restrict__ arc_lnw, Real* __restrict__ out_real) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_arcs) return;
+  double s;
+  if (chain_off) {
+    s = 0;
+    for (uint32_t k = chain_off[a], e = chain_off[a + 1]; k < e; ++k) s += ln_w[chain_param[k]];
+  } else
+    s = ln_w[a];
+  arc_lnw[a] = s;
+  out_real[a] = SCALED ? (Real)exp(s) : (Real)s;
+}
+
+// K4 + prep_new_weights: accumulate (count + prior) of every arc into each unlocked parameter of
+// its chain.  Trivial cascade: acc[p] = counts[p] + prior[p].
+__global__ void k_param_acc(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
+                            const uint32_t* __restrict__ chain_param, const double* __restrict__ counts,
+                            const double* __restrict__ prior, const uint32_t* __restrict__ param_tie,
+                            double* __restrict__ acc) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_arcs) return;
+  const double v = counts[a] + (prior ? prior[a] : 0.);
+  if (chain_off) {
+    for (uint32_t k = chain_off[a], e = chain_off[a + 1]; k < e; ++k) {
+      const uint32_t p = chain_param[k];
+      if (param_tie[p] != CML_LOCKED_GROUP && v != 0.) atomicAdd(&acc[p], v);
+    }
+  } else
+    acc[a] = v;
+}
+
+// unnormalised new weights u[p]: ln(acc) for trainable parameters, the old weight for locked
+// parameters and for members of NONE-normalised transducers (cascade.h:339-350 save/load_none).
+__global__ void k_unnorm(uint32_t n_params, const double* __restrict__ acc, const double* __restrict__ ln_w,
+                         const uint32_t* __restrict__ param_tie, const uint32_t* __restrict__ param_group,
+                         double* __restrict__ u, double* __restrict__ old) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_params) return;
+  const double w = ln_w[p];
+  old[p] = w;
+  const bool keep = (param_tie[p] == CML_LOCKED_GROUP) || (param_group[p] == CML_NO_GROUP);
+  u[p] = keep ? w : (acc[p] > 0 ? log(acc[p]) : -CUDART_INF);
+}
+
+// normalize pass 1 (fst.cc:115-133): one warp per normalisation group.  Adds the group's additive
+// prior to EVERY member (the reference adds it to locked arcs' stored weight too), then sums.
+__global__ void k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+                            const uint32_t* __restrict__ group_members, const double* __restrict__ group_add,
+                            const uint32_t* __restrict__ param_tie, double* __restrict__ u,
+                            double* __restrict__ gsum, double* __restrict__ glocked) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  const double addc = group_add ? group_add[g] : -CUDART_INF;
+  double s = -CUDART_INF, l = -CUDART_INF;
+  for (uint32_t k = group_off[g] + lane, e = group_off[g + 1]; k < e; k += 32) {
+    const uint32_t p = group_members[k];
+    const double v = lse2(u[p], addc);
+    u[p] = v;
+    if (param_tie[p] == CML_LOCKED_GROUP)
+      l = lse2(l, v);
+    else
+      s = lse2(s, v);
+  }
+  s = warp_lse(s);
+  l = warp_lse(l);
+  if (lane == 0) {
+    gsum[g] = s;
+    glocked[g] = l;
+  }
+}
+
+// tie-group totals (fst.cc:134-152): one warp per tie id.
+__global__ void k_tie_totals(uint32_t n_ties, const uint32_t* __restrict__ tie_off,
+                             const uint32_t* __restrict__ tie_members, const uint32_t* __restrict__ param_group,
+                             const double* __restrict__ u, const double* __restrict__ gsum,
+                             const double* __restrict__ glocked, double* __restrict__ tie_arc_total,
+                             double* __restrict__ tie_state_total, double* __restrict__ tie_max_locked) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= n_ties) return;
+  double at = -CUDART_INF, st = -CUDART_INF, ml = -CUDART_INF;
+  for (uint32_t k = tie_off[t] + lane, e = tie_off[t + 1]; k < e; k += 32) {
+    const uint32_t p = tie_members[k];
+    const uint32_t g = param_group[p];
+    if (g == CML_NO_GROUP) continue;
+    at = lse2(at, u[p]);
+    st = lse2(st, gsum[g]);
+    ml = fmax(ml, glocked[g]);
+  }
+  at = warp_lse(at);
+  st = warp_lse(st);
+  ml = warp_max(ml);
+  if (lane == 0) {
+    tie_arc_total[t] = at;
+    tie_state_total[t] = st;
+    tie_max_locked[t] = ml;
+  }
+}
+
+// normalize pass 2 (fst.cc:160-229): one warp per group; writes the new ln weights.
+__global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+                              const uint32_t* __restrict__ group_members, const uint32_t* __restrict__ param_tie,
+                              const double* __restrict__ u, const double* __restrict__ tie_arc_total,
+                              const double* __restrict__ tie_state_total, const double* __restrict__ tie_max_locked,
+                              double* __restrict__ ln_w) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  double normal_sum = -CUDART_INF, reserved = -CUDART_INF;
+  const uint32_t k0 = group_off[g], k1 = group_off[g + 1];
+  for (uint32_t k = k0 + lane; k < k1; k += 32) {
+    const uint32_t p = group_members[k];
+    const uint32_t tie = param_tie[p];
+    if (tie == CML_NO_GROUP) {
+      normal_sum = lse2(normal_sum, u[p]);
+    } else if (tie == CML_LOCKED_GROUP) {
+      reserved = lse2(reserved, u[p]);
+      ln_w[p] = u[p];
+    } else {
+      const uint32_t t = tie - 1;
+      double groupNorm = tie_state_total[t];
+      const double gmax = tie_max_locked[t];
+      double nw = -CUDART_INF;
+      if (!(gmax > 0.)) {
+        if (gmax > -CUDART_INF) groupNorm -= lsub(0., gmax);
+        const double groupTotal = tie_arc_total[t];
+        if (groupTotal > -CUDART_INF) {
+          nw = groupTotal - groupNorm;
+          reserved = lse2(reserved, nw);
+        }
+      }
+      ln_w[p] = nw;
+    }
+  }
+  normal_sum = warp_lse(normal_sum);
+  reserved = warp_lse(reserved);
+  const double fraction_remain = lsub(0., reserved);
+  const bool give = (fraction_remain > -CUDART_INF) && (normal_sum > -CUDART_INF);
+  for (uint32_t k = k0 + lane; k < k1; k += 32) {
+    const uint32_t p = group_members[k];
+    if (param_tie[p] == CML_NO_GROUP) ln_w[p] = give ? fraction_remain + u[p] - normal_sum : -CUDART_INF;
+  }
+}
+
+// parameters outside every normalisation group keep their unnormalised value (NONE method)
+__global__ void k_copy_ungrouped(uint32_t n_params, const uint32_t* __restrict__ param_group,
+                                 const double* __restrict__ u, double* __restrict__ ln_w) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_params && param_group[p] == CML_NO_GROUP) ln_w[p] = u[p];
+}
+
+// over-relaxation (train.cc:157-171): w <- old * (em/old)^rate for unlocked arcs with old > 0
+__global__ void k_overrelax(uint32_t n_params, double rate, const uint32_t* __restrict__ param_tie,
+                            const double* __restrict__ old, const double* __restrict__ ln_w, double* __restrict__ u) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_params) return;
+  double w = ln_w[p];
+  if (param_tie[p] != CML_LOCKED_GROUP && old[p] > -CUDART_INF) w = old[p] + (w - old[p]) * rate;
+  u[p] = w;
+}
+
+// max |w_new - w_old| over unlocked parameters (train.cc:173-182), linear domain; result as the bit
+// pattern of a non-negative double (monotone under unsigned compare).
+__global__ void k_max_change(uint32_t n_params, const uint32_t* __restrict__ param_tie,
+                             const double* __restrict__ old, const double* __restrict__ ln_w,
+                             unsigned long long* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  double d = 0;
+  if (p < n_params && param_tie[p] != CML_LOCKED_GROUP) {
+    const double a = ln_w[p], b = old[p];
+    const double hi = fmax(a, b), lo = fmin(a, b);
+    const double l = lsub(hi, lo);
+    d = (l > -CUDART_INF) ? exp(l) : 0.;
+  }
+  d = warp_max(d);
+  if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, (unsigned long long)__double_as_longlong(d));
+}
+
+}  // namespace cmlk

@@ -1,0 +1,175 @@
+/* carmel_b200.h -- C ABI of the B200-native training hot path for graehl/carmel.
+ *
+ * The reference (graehl/carmel) has no plugin / FFI surface: carmel and forest-em are single
+ * binaries.  This header is the seam a maintainer would bind if the reference's executor concepts
+ * were moved behind a library: each entry point names the reference interface it replaces
+ * (file:line relative to the reference root).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative cml_status on failure; cml_last_error()
+ *     gives the message.  No exception crosses the boundary.
+ *   - host buffers belong to the caller; device memory belongs to the context.
+ *   - one context per GPU; a context is not thread-safe, different contexts are independent
+ *     (the reference itself is single threaded with static state, forest-em/forest.hpp:86-107).
+ *   - weights cross the boundary as natural logs of non-negative reals (the reference's
+ *     logweight<Real>::weight, graehl/shared/weight.h:131-137); -INFINITY is the zero weight.
+ *   - there is NO CPU fallback: every compute entry point fails with CML_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef CARMEL_B200_H
+#define CARMEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cml_ctx cml_ctx;
+
+enum cml_status {
+  CML_OK = 0,
+  CML_ERR_ARG = -1,    /* bad argument / inconsistent sizes */
+  CML_ERR_CUDA = -2,   /* CUDA runtime error or no usable device */
+  CML_ERR_STATE = -3,  /* call order violated (e.g. estimate before set_model) */
+  CML_ERR_CYCLE = -4,  /* derivation lattice has a cycle (reference only warns: derivations.h:726-728) */
+  CML_ERR_NODERIV = -5 /* no training example had a derivation (train.cc:249-252) */
+};
+
+enum cml_space { CML_SPACE_LOG = 0, CML_SPACE_SCALED = 1 };
+enum cml_norm_group { CML_NORM_CONDITIONAL = 0, CML_NORM_JOINT = 1, CML_NORM_NONE = 2 };
+
+#define CML_NO_GROUP 0xFFFFFFFFu /* graehl/shared/arc.h:43 FSTArc::no_group  */
+#define CML_LOCKED_GROUP 0u      /* graehl/shared/arc.h:44 FSTArc::locked_group */
+
+/* ---- library / context ------------------------------------------------------------------- */
+const char* cml_version(void);
+/* precision: 32 or 64 = sizeof(Real)*8 of the forward/backward state scores (carmel FLOAT_TYPE,
+ * graehl/shared/config.h:98-104; forest-em -U, forest-em-params.cpp:9-19).  Counts, likelihood sums
+ * and the M-step are always fp64. */
+int cml_create(cml_ctx** out, int device, int precision, int space);
+void cml_destroy(cml_ctx* ctx);
+const char* cml_last_error(cml_ctx* ctx); /* ctx may be NULL: error of the last failed cml_create */
+/* run all subsequent work of this context on an existing CUDA stream (cudaStream_t as void*). */
+int cml_set_stream(cml_ctx* ctx, void* cuda_stream);
+int cml_synchronize(cml_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t cml_launch_count(cml_ctx* ctx);
+
+/* ---- model: parameters, cascade chains, normalisation groups ------------------------------ *
+ * Replaces arcs_table<arc_counts> (carmel/src/derivations.h:79-140, train.h:28-40),
+ * cascade_parameters::chains (carmel/src/cascade.h:222-262) and the group structure walked by
+ * WFST::normalize / NormGroupIter (carmel/src/fst.cc:86-244, fst.h:1362-1446).
+ *
+ *   n_arcs      size of the arc table the trellis arc ids index (composed transducer arcs).
+ *   chain_off   [n_arcs+1] CSR into chain_param: the parameters whose product is the arc's weight
+ *               (cascade.h:426-433).  NULL = trivial cascade: arc i is parameter i (n_params==n_arcs).
+ *   arc_prior   [n_arcs] linear prior count added to the arc's expected count before the M-step
+ *               (train.cc:134-153 prior_counts; -f floor, + weight with -U).  NULL = all 0.
+ *   n_params    number of original (cascade member) arcs = trainable or locked parameters.
+ *   param_group [n_params] normalisation group id in [0,n_groups) or CML_NO_GROUP for members of a
+ *               NONE-normalised transducer (weights kept, cascade.h:339-350).
+ *   param_tie   [n_params] CML_NO_GROUP (normal), CML_LOCKED_GROUP (locked '!'), else tie id in
+ *               [1,n_ties] ('!N', wfstio.cc:453-464; ids are made dense and unique per cascade by the caller).
+ *   group_add   [n_groups] ln of the per-group additive prior (--priors, fst.cc:124-125); NULL = zero.
+ */
+typedef struct cml_model {
+  uint32_t n_arcs;
+  const uint32_t* chain_off;
+  const uint32_t* chain_param;
+  const double* arc_prior;
+  uint32_t n_params;
+  const uint32_t* param_group;
+  const uint32_t* param_tie;
+  uint32_t n_groups;
+  const double* group_add;
+  uint32_t n_ties;
+} cml_model;
+int cml_set_model(cml_ctx* ctx, const cml_model* m);
+/* ln weights of the n_params parameters: FSTArc::weight (arc.h:37) */
+int cml_set_params(cml_ctx* ctx, const double* ln_w);
+int cml_get_params(cml_ctx* ctx, double* ln_w);
+/* device-side copies used for save_best / load_best (train.cc:449-457, for_arcs::save_best :184-197) */
+int cml_snapshot_params(cml_ctx* ctx, int slot /*0..3*/);
+int cml_restore_params(cml_ctx* ctx, int slot);
+
+/* ---- trellises ------------------------------------------------------------------------------ *
+ * Replaces derivations::g (carmel/src/derivations.h:170-171) = dynamic_array<GraphState> of
+ * List<GraphArc{src,dest,weight,data=arc id}> (graehl/shared/graph.h:37-121) together with the
+ * per-example DFS order and reversed graph (derivations.h:706-736, graph.cc:41-57).
+ * The caller hands over each example's pruned derivation lattice exactly as the reference holds
+ * it: states in reference id order (DFS pre-order after prune, start = 0), per state its arc list in
+ * stored order (derivations.h:698 push_front => reverse discovery order).  The library flattens
+ * the batch into topologically layered CSR arrays in HBM (states renumbered by (level, id), level =
+ * longest-path depth from the start; incoming- and outgoing-arc CSR per example) and keeps it
+ * resident across iterations like carmel's in-memory derivation cache (-: , cached_derivs.h:104-138).
+ *
+ *   n_ex       examples in this batch (appended to those already resident)
+ *   ex_states  [n_ex] states per example        ex_fin [n_ex] goal state id
+ *   ex_weight  [n_ex] example weight (train.h IOSymSeq::weight)
+ *   arc_off    [sum(ex_states) + n_ex] per example a CSR row-offset array of ex_states+1 entries,
+ *              offsets local to the example's first arc
+ *   arc_dst, arc_id [total arcs] destination state id and arc-table id (GraphArc.dest / .data)
+ * Returns CML_ERR_CYCLE if a lattice has a cycle. */
+typedef struct cml_trellis_batch {
+  uint64_t n_ex;
+  const uint32_t* ex_states;
+  const uint32_t* ex_fin;
+  const double* ex_weight;
+  const uint32_t* arc_off;
+  const uint32_t* arc_dst;
+  const uint32_t* arc_id;
+} cml_trellis_batch;
+int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b);
+int cml_clear_trellises(cml_ctx* ctx);
+int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs, uint64_t* n_levels);
+/* introspection for parity tests: the layered layout of resident example e.
+ *   level_of[ex_states]  level of each reference state id;  local_of[ex_states] its layered index. */
+int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_t* level_of, uint32_t* local_of);
+
+/* ---- E-step ----------------------------------------------------------------------------------- *
+ * Replaces forward_backward::estimate (carmel/src/train.cc:763-773) = cascade.update (cascade.h:466-479),
+ * clear counts, then for every example derivations::collect_counts (derivations.h:432-449:
+ * compute_fb :400-417 + the count loop) and the corpus probability products (train.cc:326-332).
+ *   sum_ln_p    Σ_e ln P_e           (ln of "unweighted_corpus_prob")
+ *   sum_w_ln_p  Σ_e w_e ln P_e       (ln of "weighted_corpus_prob")
+ *   n_zero      examples with P_e == 0 (excluded from both sums)
+ * Expected counts stay on the device (per arc-table id, linear domain). */
+typedef struct cml_estimate_result {
+  double sum_ln_p;
+  double sum_w_ln_p;
+  uint64_t n_zero;
+} cml_estimate_result;
+int cml_estimate(cml_ctx* ctx, cml_estimate_result* out);
+/* asynchronous halves of cml_estimate for multi-GPU use: launch, (all-reduce the reduce buffer), finish */
+int cml_estimate_launch(cml_ctx* ctx);
+int cml_estimate_finish(cml_ctx* ctx, cml_estimate_result* out);
+/* per-example ln P_e of the last estimate (order of insertion), for parity tests */
+int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n);
+/* expected counts per arc-table id (linear) of the last estimate */
+int cml_get_arc_counts(cml_ctx* ctx, double* counts);
+/* The per-iteration reduce buffer: [n_arcs counts | sum_ln_p | sum_w_ln_p | n_zero] as fp64 on the
+ * device.  A multi-GPU driver all-reduces (sum) it between cml_estimate_launch and
+ * cml_estimate_finish (one collective per iteration).  cml_use_reduce_buffer lets the caller own the
+ * memory (e.g. a torch tensor registered with NCCL); pass NULL to go back to the internal one. */
+int cml_reduce_buffer(cml_ctx* ctx, void** device_ptr, uint64_t* n_doubles);
+int cml_use_reduce_buffer(cml_ctx* ctx, void* device_ptr, uint64_t n_doubles);
+
+/* ---- M-step ----------------------------------------------------------------------------------- *
+ * Replaces forward_backward::maximize (carmel/src/train.cc:893-923): prep_new_weights (:134-153),
+ * cascade.distribute_counts (cascade.h:286-325), WFST::normalize per cascade member (fst.cc:86-244),
+ * overrelax (:157-171, rate > 1) + renormalise, max_change (:173-182).
+ *   max_delta  max |w_new - w_old| over unlocked parameters (linear domain), as Weight absdiff. */
+int cml_maximize(cml_ctx* ctx, double rate, double* max_delta);
+/* WFST::normalize of the current parameters only (train.cc:509 initial cascade.normalize) */
+int cml_normalize_params(cml_ctx* ctx);
+
+/* ---- host-side helpers exported for bindings and tests (no GPU needed) ------------------------ */
+/* Every symbol this header declares, for the loader test. */
+const char* const* cml_exported_symbols(size_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARMEL_B200_H */

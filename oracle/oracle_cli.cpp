@@ -217,6 +217,27 @@ int real_main(int argc, char** argv) {
     write_u32(o, (uint32_t)tr.arcs.size());
     o << body.str();
   }
+  if (lopt.count("dump-estimate")) {
+    // one E-step at the initial (normalised) weights: arc-table ln weights, ln counts, per-example ln P
+    std::ofstream o(lopt["dump-estimate"], std::ios::binary);
+    cascade.update();
+    IOIndex io(*result);
+    for (auto& a : tr.arcs.t) a.counts.setZero();
+    std::vector<double> lnp;
+    for (auto const& e : corpus.examples) {
+      Derivations d;
+      d.in = e.in;
+      d.out = e.out;
+      d.weight = e.weight;
+      if (d.compute(*result, io, tr.arcs)) lnp.push_back(d.collect_counts(tr.arcs).w);
+    }
+    write_u32(o, (uint32_t)tr.arcs.size());
+    write_u32(o, (uint32_t)lnp.size());
+    for (auto const& a : tr.arcs.t) write_f64(o, a.arc->weight.w);
+    for (auto const& a : tr.arcs.t) write_f64(o, a.counts.w);
+    for (double v : lnp) write_f64(o, v);
+    return 0;
+  }
   if (lopt.count("time-estimate")) {  // CPU baseline: time K E-steps (+M-steps) on this corpus
     unsigned K = (unsigned)atoi(lopt["time-estimate"].c_str());
     cascade.update();
