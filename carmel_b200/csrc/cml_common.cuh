@@ -43,9 +43,10 @@ struct DevArray {
     if (!count) return cudaSuccess;
     return cudaMalloc((void**)&p, count * sizeof(T));
   }
+  // always allocates at least one element so kernels never see a null table
   cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
-    cudaError_t e = alloc(count);
-    if (e != cudaSuccess || !count) return e;
+    cudaError_t e = alloc(count ? count : 1);
+    if (e != cudaSuccess || !count || !h) return e;
     return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
   }
   void release() {

@@ -214,7 +214,7 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   ctx->n_ties = m->n_ties;
   if (!trivial) {
     CML_CUDA(ctx->chain_off.upload(m->chain_off, m->n_arcs + 1, s));
-    CML_CUDA(ctx->chain_param.upload(m->chain_param, std::max<uint32_t>(1, m->chain_off[m->n_arcs]), s));
+    CML_CUDA(ctx->chain_param.upload(m->chain_param, m->chain_off[m->n_arcs], s));
   } else {
     ctx->chain_off.release();
     ctx->chain_param.release();
@@ -226,9 +226,9 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   CML_CUDA(ctx->param_group.upload(pg.data(), m->n_params, s));
   CML_CUDA(ctx->param_tie.upload(m->param_tie, m->n_params, s));
   CML_CUDA(ctx->group_off.upload(goff.data(), goff.size(), s));
-  CML_CUDA(ctx->group_members.upload(gmem.data(), std::max<size_t>(1, gmem.size()), s));
+  CML_CUDA(ctx->group_members.upload(gmem.data(), gmem.size(), s));
   CML_CUDA(ctx->tie_off.upload(toff.data(), toff.size(), s));
-  CML_CUDA(ctx->tie_members.upload(tmem.data(), std::max<size_t>(1, tmem.size()), s));
+  CML_CUDA(ctx->tie_members.upload(tmem.data(), tmem.size(), s));
   CML_CUDA(ctx->ln_w.alloc(m->n_params));
   for (auto& sn : ctx->snap) CML_CUDA(sn.alloc(m->n_params));
   CML_CUDA(ctx->acc.alloc(m->n_params));
@@ -549,8 +549,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   CML_CUDA(bt->lvl_off.upload(h_lvl.data(), h_lvl.size(), s));
   CML_CUDA(bt->in_off.upload(h_in_off.data(), h_in_off.size(), s));
   CML_CUDA(bt->out_off.upload(h_out_off.data(), h_out_off.size(), s));
-  CML_CUDA(bt->in_arc.upload(h_in.data(), std::max<size_t>(1, h_in.size()), s));
-  CML_CUDA(bt->out_arc.upload(h_out.data(), std::max<size_t>(1, h_out.size()), s));
+  CML_CUDA(bt->in_arc.upload(h_in.data(), h_in.size(), s));
+  CML_CUDA(bt->out_arc.upload(h_out.data(), h_out.size(), s));
   CML_CUDA(bt->ex_list.upload(ex_list.data(), ex_list.size(), s));
   CML_CUDA(bt->ex_lnp.alloc(n_ex));
   if (scratch_states) {

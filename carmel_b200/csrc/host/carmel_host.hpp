@@ -1,0 +1,155 @@
+// carmel_host.hpp -- host-side C++ of carmel_b200: the pieces of carmel that stay on the CPU
+// (file formats, composition, cascade bookkeeping, per-example lattice construction, the EM
+// outer loop) re-designed around flat arrays so that everything numeric is handed to the CUDA
+// library through the C ABI (include/carmel_b200.h).  It mirrors the reference's interfaces for
+// this path (names, argument meaning, log lines) without sharing its data structures:
+//   WFST text format        carmel/src/wfstio.cc:341-506,594-625 ; carmel/doc/FORMATS
+//   corpus format           carmel/src/train.cc:985-1025
+//   reduce                  carmel/src/fst.cc:468-545
+//   composition + chains    carmel/src/compose.cc:163-531 ; carmel/src/cascade.h:489-599
+//   lattice construction    carmel/src/derivations.h:479-704
+//   EM outer loop           carmel/src/train.cc:503-678
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <iosfwd>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "carmel_b200.h"
+
+namespace cb {
+
+static const double kNegInf = -std::numeric_limits<double>::infinity();
+static const uint32_t kNoGroup = CML_NO_GROUP, kLocked = CML_LOCKED_GROUP, kEps = 0;
+
+// ---- weights as natural logs (graehl/shared/weight.h) -------------------------------------------
+struct WeightFormat {
+  enum Base { EXP, LN, LOG10 } base = EXP;
+  enum Thresh { SOMETIMES, ALWAYS, NEVER } thresh = SOMETIMES;
+};
+bool parse_weight(const char* s, double& ln_out);               // weight.h:503-528
+std::string format_weight(double ln_w, WeightFormat const& f = WeightFormat());  // weight.h:467-490
+std::string format_base2(double ln_w);                           // Weight::as_base(2), 6 digits
+double ln_add(double a, double b);                               // weight.h:765-801 (cutoff 36 nats)
+double ln_sub(double a, double b);                               // weight.h:803-830
+
+// ---- alphabet / transducer ----------------------------------------------------------------------
+struct Alphabet {
+  std::vector<std::string> names;
+  std::unordered_map<std::string, uint32_t> idx;
+  Alphabet();
+  uint32_t index_of(std::string const& s);
+  int find(std::string const& s) const;
+};
+
+struct Arc {
+  uint32_t in, out, dest;
+  double ln_w;
+  uint32_t group;  // kNoGroup normal, kLocked '!', else tie id '!N'  (cascade composed arcs: chain id)
+};
+
+enum NormGroupBy { CONDITIONAL = 0, JOINT = 1, NONE = 2 };
+struct NormalizeMethod {
+  NormGroupBy group = CONDITIONAL;
+  double ln_add_count = kNegInf;  // --priors
+};
+
+struct Wfst {
+  std::vector<std::vector<Arc>> states;  // arc order within a state = the reference's list order
+  std::vector<std::string> state_names;
+  std::unordered_map<std::string, uint32_t> state_idx;
+  bool named = true;
+  uint32_t final_state = 0;
+  bool valid = false;
+  std::shared_ptr<Alphabet> alph[2];
+  Wfst();
+  uint32_t num_states() const { return (uint32_t)states.size(); }
+  size_t num_arcs() const;
+  std::string state_name(uint32_t i) const;
+  bool read(std::istream& in, bool always_named = true);
+  bool read_file(std::string const& path, bool always_named = true);
+  void write(std::ostream& os, bool full, bool one_arc_per_line, bool include_zero, WeightFormat const& wf) const;
+  void reduce();
+  // arc table: id = visit order (state 0..n, list order) -- carmel/src/fst.h:1330-1334
+  void arc_offsets(std::vector<uint32_t>& off) const;
+};
+
+struct Example {
+  std::vector<uint32_t> in, out;
+  double weight = 1;
+};
+struct Corpus {
+  std::vector<Example> examples;
+  uint32_t n_pairs = 0;
+  double total_weight = 0, n_input = 0, n_output = 0;
+  void count();
+  void read(std::istream& in, Wfst& x);
+};
+
+// ---- cascade: composed arc -> chain of original parameters (cascade.h) --------------------------
+struct Cascade {
+  bool trivial = true;
+  std::vector<Wfst*> members;               // original transducers, in chain order
+  std::vector<uint32_t> member_param_base;  // first parameter id of each member
+  std::vector<std::vector<uint32_t>> chains;  // chain id -> parameter ids (chain 0 = nil)
+  Wfst* composed = nullptr;
+  uint32_t n_params = 0;
+  // parameter id of (member m, state s, k-th arc)
+  std::vector<std::vector<uint32_t>> member_state_base;
+  void number_members();
+};
+// 3-state epsilon-filter composition (compose.cc:316-498).  With a non-trivial cascade the
+// composed arcs' group field holds the chain id (cascade.h:588-599).
+std::unique_ptr<Wfst> compose(Cascade& c, Wfst& a, Wfst& b, bool a_is_composed, uint32_t a_member, uint32_t b_member,
+                              uint32_t index_threshold = 32);
+
+// ---- per-example derivation lattices (derivations.h) --------------------------------------------
+struct TrellisBatch {  // the C ABI's cml_trellis_batch, owning its storage; reference state order
+  std::vector<uint32_t> ex_states, ex_fin;
+  std::vector<double> ex_weight;
+  std::vector<uint32_t> arc_off, arc_dst, arc_id;
+  std::vector<uint32_t> kept_example;  // index into the corpus of each kept example
+  uint64_t pre_arcs = 0;
+  void clear();
+  void dump(std::ostream& o, uint32_t n_arcs_table) const;
+};
+// Builds the pruned lattice of every example (string x WFST x string), multi-threaded over
+// examples; examples without a derivation are reported in `dropped` and left out.
+void build_trellises(Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
+                     unsigned n_threads = 0);
+
+// ---- training -------------------------------------------------------------------------------------
+struct TrainOpts {
+  uint32_t max_iter = 500;          // -M   (fst.h:1089)
+  double ln_converge_delta;         // -e   (carmel.cc:896) ln(1e-4)
+  double ln_converge_ratio;         // -X   (carmel.cc:897) ln(.999)
+  double ln_smooth_floor = kNegInf; // -f
+  bool weight_is_prior = false;     // -U
+  double rate_growth = 1.;          // -o
+  int precision = 64;               // --float => 32
+  int space = CML_SPACE_LOG;        // --scaled => CML_SPACE_SCALED
+  int device = 0;
+  bool quiet = false;
+  std::string history_file, dump_trellis_file;
+  TrainOpts();
+};
+struct IterRecord {
+  uint32_t iter;
+  double ln_prob, ln_weighted_prob, max_change;
+};
+struct TrainResult {
+  double ln_best_ppx = 0;
+  std::vector<IterRecord> history;
+  uint64_t trellis_arcs = 0, trellis_states = 0, examples = 0;
+};
+// WFST::train (train.cc:503-678) with the E- and M-steps on the GPU.  On return the cascade members
+// (or x itself for a trivial cascade) hold the trained weights.  Throws std::runtime_error.
+TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<NormalizeMethod> const& methods,
+                  TrainOpts const& opt, std::ostream& log);
+
+}  // namespace cb

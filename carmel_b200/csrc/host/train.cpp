@@ -1,0 +1,339 @@
+// train.cpp -- EM outer loop (host) driving the CUDA library through the C ABI.
+//
+// Mirrors WFST::train (carmel/src/train.cc:503-678): convergence tests, best-perplexity bookkeeping,
+// over-relaxation schedule and the exact log lines, with forward_backward::estimate / maximize
+// (train.cc:763-773,893-923) replaced by cml_estimate / cml_maximize.  All per-arc state the reference
+// keeps in arcs_table<arc_counts> (weights, counts, scratch, em_weight, best_weight) lives on the GPU.
+#include <algorithm>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+
+#include "carmel_host.hpp"
+
+namespace cb {
+
+TrainOpts::TrainOpts() : ln_converge_delta(std::log(1e-4)), ln_converge_ratio(std::log(.999)) {}
+
+namespace {
+
+struct Ctx {  // RAII over cml_ctx with exceptions on error
+  cml_ctx* h = nullptr;
+  Ctx(int device, int precision, int space) {
+    if (cml_create(&h, device, precision, space) != CML_OK)
+      throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
+  }
+  ~Ctx() { cml_destroy(h); }
+  void ok(int rc) const {
+    if (rc != CML_OK) throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(h));
+  }
+};
+
+// The device model: parameters = all arcs of the cascade members (or of x) in arc-table order.
+struct ModelArrays {
+  std::vector<uint32_t> chain_off, chain_param, param_group, param_tie;
+  std::vector<double> group_add, ln_w, arc_prior;
+  uint32_t n_groups = 0, n_ties = 0, n_arcs = 0, n_params = 0;
+};
+
+void add_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
+  // normalisation groups: all arcs leaving a state (JOINT) or leaving a state with the same input
+  // symbol (CONDITIONAL); NONE keeps weights (carmel/src/fst.h:1362-1446, cascade.h:339-350)
+  std::unordered_map<uint32_t, uint32_t> tie_ids;  // '!N' ids are local to a transducer
+  for (auto const& st : w.states) {
+    std::unordered_map<uint32_t, uint32_t> by_input;
+    uint32_t joint_group = kNoGroup;
+    for (Arc const& a : st) {
+      uint32_t g = kNoGroup;
+      if (m.group == JOINT) {
+        if (joint_group == kNoGroup) {
+          joint_group = M.n_groups++;
+          M.group_add.push_back(m.ln_add_count);
+        }
+        g = joint_group;
+      } else if (m.group == CONDITIONAL) {
+        auto it = by_input.find(a.in);
+        if (it == by_input.end()) {
+          it = by_input.emplace(a.in, M.n_groups++).first;
+          M.group_add.push_back(m.ln_add_count);
+        }
+        g = it->second;
+      }
+      M.param_group.push_back(g);
+      uint32_t t = a.group;
+      if (t != kNoGroup && t != kLocked) {
+        auto it = tie_ids.find(t);
+        if (it == tie_ids.end()) it = tie_ids.emplace(t, ++M.n_ties).first;
+        t = it->second;
+      }
+      M.param_tie.push_back(t);
+      M.ln_w.push_back(a.ln_w);
+    }
+  }
+}
+
+void print_ppx(std::ostream& log, double ln_corpus_p, Corpus const& c) {  // weight.h:311-329
+  log << "probability=" << format_base2(ln_corpus_p);
+  const double n_symbol = std::max(c.n_output, c.n_input);
+  if (n_symbol) log << " per-output-symbol-perplexity(N=" << n_symbol << ")=" << format_base2(-ln_corpus_p / n_symbol);
+  if (c.n_pairs) log << " per-example-perplexity(N=" << c.n_pairs << ")=" << format_base2(-ln_corpus_p / c.n_pairs);
+}
+
+}  // namespace
+
+TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<NormalizeMethod> const& methods,
+                  TrainOpts const& opt, std::ostream& log) {
+  TrainResult res;
+  const bool using_cascade = !cascade.trivial;
+  std::vector<Wfst*> members = using_cascade ? cascade.members : std::vector<Wfst*>{&x};
+
+  // ---- model tables ----
+  ModelArrays M;
+  for (size_t i = 0; i < members.size(); ++i) add_member(*members[i], i < methods.size() ? methods[i] : NormalizeMethod(), M);
+  M.n_params = (uint32_t)M.ln_w.size();
+  M.n_arcs = (uint32_t)x.num_arcs();
+  if (using_cascade) {
+    M.chain_off.push_back(0);
+    for (auto const& st : x.states)
+      for (Arc const& a : st) {
+        auto const& ch = cascade.chains.at(a.group);
+        M.chain_param.insert(M.chain_param.end(), ch.begin(), ch.end());
+        M.chain_off.push_back((uint32_t)M.chain_param.size());
+      }
+  }
+  Ctx ctx(opt.device, opt.precision, opt.space);
+  cml_model mm{};
+  mm.n_arcs = M.n_arcs;
+  mm.chain_off = using_cascade ? M.chain_off.data() : nullptr;
+  mm.chain_param = using_cascade ? M.chain_param.data() : nullptr;
+  mm.arc_prior = nullptr;
+  mm.n_params = M.n_params;
+  mm.param_group = M.param_group.data();
+  mm.param_tie = M.param_tie.data();
+  mm.n_groups = M.n_groups;
+  mm.group_add = M.group_add.data();
+  mm.n_ties = M.n_ties;
+  ctx.ok(cml_set_model(ctx.h, &mm));
+  ctx.ok(cml_set_params(ctx.h, M.ln_w.data()));
+  ctx.ok(cml_normalize_params(ctx.h));  // train.cc:509 cascade.normalize(methods)
+
+  // prior counts per arc-table entry (train.cc:134-153; derivations.h:96-101): the -f floor, plus
+  // the (normalised) arc weight itself with -U
+  if (opt.ln_smooth_floor > kNegInf || opt.weight_is_prior) {
+    std::vector<double> w(M.n_params);
+    ctx.ok(cml_get_params(ctx.h, w.data()));
+    M.arc_prior.assign(M.n_arcs, opt.ln_smooth_floor > kNegInf ? std::exp(opt.ln_smooth_floor) : 0.);
+    if (opt.weight_is_prior)
+      for (uint32_t a = 0; a < M.n_arcs; ++a) {
+        double lw = 0;
+        if (using_cascade)
+          for (uint32_t k = M.chain_off[a]; k < M.chain_off[a + 1]; ++k) lw += w[M.chain_param[k]];
+        else
+          lw = w[a];
+        M.arc_prior[a] += std::exp(lw);
+      }
+    mm.arc_prior = M.arc_prior.data();
+    ctx.ok(cml_set_model(ctx.h, &mm));
+    ctx.ok(cml_set_params(ctx.h, w.data()));
+  }
+
+  // ---- derivation lattices: built once, resident on the GPU (carmel's -: cache semantics) ----
+  {
+    TrellisBatch tb;
+    std::vector<uint32_t> dropped;
+    build_trellises(x, corpus, tb, dropped);
+    for (uint32_t e : dropped)  // cached_derivs.h:53-57,87-93
+      std::cerr << "No derivations in transducer for input/output #" << e + 1 << ":\n";
+    if (!dropped.empty()) {
+      std::vector<Example> keep;
+      keep.reserve(tb.kept_example.size());
+      for (uint32_t e : tb.kept_example) keep.push_back(std::move(corpus.examples[e]));
+      corpus.examples.swap(keep);
+      corpus.count();
+    }
+    if (corpus.examples.empty()) {
+      std::cerr << "No training example had a derivation - check your models, quotes, manually compose with -i, etc.\n";
+      throw std::runtime_error("No training example had a derivation - aborting training.");
+    }
+    if (!opt.dump_trellis_file.empty()) {
+      std::ofstream o(opt.dump_trellis_file, std::ios::binary);
+      tb.dump(o, M.n_arcs);
+    }
+    cml_trellis_batch b{};
+    b.n_ex = tb.ex_states.size();
+    b.ex_states = tb.ex_states.data();
+    b.ex_fin = tb.ex_fin.data();
+    b.ex_weight = tb.ex_weight.data();
+    b.arc_off = tb.arc_off.data();
+    b.arc_dst = tb.arc_dst.data();
+    b.arc_id = tb.arc_id.data();
+    ctx.ok(cml_add_trellises(ctx.h, &b));
+    res.trellis_arcs = tb.arc_dst.size();
+    res.examples = b.n_ex;
+    for (uint32_t n : tb.ex_states) res.trellis_states += n;
+  }
+
+  auto estimate = [&](double& ln_unweighted) -> double {  // returns ln weighted corpus prob
+    cml_estimate_result r;
+    ctx.ok(cml_estimate(ctx.h, &r));
+    if (r.n_zero) {
+      ln_unweighted = kNegInf;
+      return kNegInf;
+    }
+    ln_unweighted = r.sum_ln_p;
+    return r.sum_w_ln_p;
+  };
+  auto write_back = [&]() {  // device parameters -> transducer arcs
+    std::vector<double> w(M.n_params);
+    ctx.ok(cml_get_params(ctx.h, w.data()));
+    size_t p = 0;
+    for (Wfst* m : members)
+      for (auto& st : m->states)
+        for (Arc& a : st) a.ln_w = w[p++];
+    if (using_cascade) {  // cascade.update(): composed weights = chain products
+      size_t a_id = 0;
+      for (auto& st : x.states)
+        for (Arc& a : st) {
+          double lw = 0;
+          for (uint32_t k = M.chain_off[a_id]; k < M.chain_off[a_id + 1]; ++k) lw += w[M.chain_param[k]];
+          a.ln_w = lw;
+          ++a_id;
+        }
+    }
+  };
+  auto finish = [&]() {
+    if (!opt.history_file.empty()) {
+      std::ofstream o(opt.history_file);
+      o.precision(17);
+      for (auto const& h : res.history) o << h.iter << ' ' << h.ln_prob << ' ' << h.ln_weighted_prob << ' ' << h.max_change << '\n';
+    }
+  };
+
+  double ln_corpus_p = 0;
+  // ---- -M 0 / -M 1: fractional counts only / a single iteration (train.cc:520-538) ----
+  if (opt.max_iter == 0 || opt.max_iter == 1) {
+    const double p = estimate(ln_corpus_p);
+    res.history.push_back({1, ln_corpus_p, p, 0});
+    log << "Corpus ";
+    print_ppx(log, ln_corpus_p, corpus);
+    if (opt.max_iter == 0) {
+      log << "0 iterations specified for training; output weights will be unnormalized fractional counts (except locked arcs).\n";
+      std::vector<double> counts(M.n_arcs);
+      ctx.ok(cml_get_arc_counts(ctx.h, counts.data()));
+      size_t a_id = 0;
+      for (auto& st : x.states)
+        for (Arc& a : st) {
+          const double c = counts[a_id] + (M.arc_prior.empty() ? 0. : M.arc_prior[a_id]);
+          if (a.group != kLocked || using_cascade) a.ln_w = c > 0 ? std::log(c) : kNegInf;
+          ++a_id;
+        }
+    } else {
+      double d;
+      ctx.ok(cml_maximize(ctx.h, 1., &d));
+      write_back();
+    }
+    log << "\n";
+    res.ln_best_ppx = -p / corpus.total_weight;
+    finish();
+    return res;
+  }
+
+  // ---- main loop (train.cc:540-667, single start) ----
+  const double kInf = std::numeric_limits<double>::infinity();
+  double ln_best_ppx = kInf;
+  double growth = opt.rate_growth;
+  if (using_cascade && growth != 1) {
+    std::cerr << "Overrelaxed EM not supported for --train-cascade.  Disabling (growth factor=1)." << std::endl;
+    growth = 1;
+  }
+  bool have_good_weights = false;
+  uint32_t train_iter = 0;
+  double ln_last_change = std::log(10.);
+  double ln_last_ppx = kInf;
+  double learning_rate = 1;
+  bool last_was_reset = false;
+  const int SLOT_BEST = 0, SLOT_EM = 1;
+  for (;;) {
+    const bool first_time = train_iter == 0;
+    ++train_iter;
+    const bool cascade_counts = using_cascade && !first_time;
+    if (~opt.max_iter && train_iter > opt.max_iter && have_good_weights) {
+      log << "Maximum number of iterations (" << opt.max_iter
+          << ") reached before convergence criteria was met - greatest arc weight change was "
+          << format_weight(ln_last_change) << "\n";
+      break;
+    }
+    const double p = estimate(ln_corpus_p);
+    const double ln_new_ppx = -p / corpus.total_weight;  // ppxper(totalEmpiricalWeight)
+    res.history.push_back({train_iter, ln_corpus_p, p, std::exp(ln_last_change)});
+    log << "i=" << train_iter << " (rate=" << learning_rate << "): ";
+    print_ppx(log, ln_corpus_p, corpus);
+    if (ln_new_ppx < ln_best_ppx && (!using_cascade || cascade_counts)) {
+      log << " (new best)";
+      ln_best_ppx = ln_new_ppx;
+      have_good_weights = true;
+      ctx.ok(cml_snapshot_params(ctx.h, SLOT_BEST));  // save_best
+    }
+    double ln_ratio;
+    if (first_time) {
+      log << std::endl;
+      log << "Initial best start point ppx=" << format_base2(ln_new_ppx) << std::endl;
+      ln_ratio = kNegInf;
+    } else {
+      // relative_perplexity_ratio (weight.h:247-249): (new/old)^(1/|ln new|)
+      ln_ratio = (ln_new_ppx - ln_last_ppx) / std::fabs(ln_new_ppx);
+      if (!(ln_new_ppx > kNegInf)) ln_ratio = kNegInf;
+      log << " (relative-perplexity-ratio=" << format_weight(ln_ratio) << ")";
+      if (ln_last_change < 0) log << ", max {d(weight)}=" << format_weight(ln_last_change);
+      log << std::endl;
+    }
+    if (!last_was_reset) {
+      if (ln_ratio >= opt.ln_converge_ratio) {
+        if (learning_rate > 1) {
+          log << "Failed to improve (relaxation rate too high); starting again at learning rate 1" << std::endl;
+          learning_rate = 1;
+          ctx.ok(cml_restore_params(ctx.h, SLOT_EM));  // keep_em_weight
+          last_was_reset = true;
+          continue;
+        }
+        log << "Converged - per-example perplexity ratio exceeds " << format_weight(opt.ln_converge_ratio) << " after "
+            << train_iter << " iterations.\n";
+        if (!have_good_weights)
+          log << "Because of the --train-cascade implementation, we need another iteration even though we've converged.\n";
+        else
+          break;
+      } else {
+        if (learning_rate < 20) learning_rate *= growth;  // MAX_LEARNING_RATE_EXP, config.h:145
+      }
+    } else
+      last_was_reset = false;
+    double max_delta = 10;
+    if (learning_rate > 1.) {
+      // the raw EM weights (rate 1) are needed if the relaxed step fails: compute them first
+      ctx.ok(cml_snapshot_params(ctx.h, 2));
+      ctx.ok(cml_maximize(ctx.h, 1., &max_delta));
+      ctx.ok(cml_snapshot_params(ctx.h, SLOT_EM));
+      ctx.ok(cml_restore_params(ctx.h, 2));
+    }
+    ctx.ok(cml_maximize(ctx.h, learning_rate, &max_delta));
+    if (using_cascade) max_delta = 10;  // train.cc:921-922
+    ln_last_change = max_delta > 0 ? std::log(max_delta) : kNegInf;
+    if (ln_last_change <= opt.ln_converge_delta && have_good_weights) {
+      log << "Converged - maximum weight change less than " << format_weight(opt.ln_converge_delta) << " after "
+          << train_iter << " iterations.\n";
+      break;
+    }
+    ln_last_ppx = ln_new_ppx;
+  }
+  log << "Setting weights to model with lowest per-example-perplexity ( = "
+         "prod[modelprob(example)]^(-1/num_examples) = 2^(-log_2(p_model(corpus))/N) = "
+      << format_base2(ln_best_ppx) << std::endl;
+  ctx.ok(cml_restore_params(ctx.h, SLOT_BEST));  // load_best (+ use_counts_final for cascades)
+  write_back();
+  res.ln_best_ppx = ln_best_ppx;
+  finish();
+  return res;
+}
+
+}  // namespace cb

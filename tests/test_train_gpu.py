@@ -1,0 +1,136 @@
+"""End-to-end EM parity on the GPU through the product command line (host C++ -> C ABI -> CUDA):
+likelihood trajectories against the reference's golden log and the CPU oracle, learned weights
+against the oracle and the reference's *.trained file.
+
+Tolerances (north_star): per-iteration corpus log-likelihood and learned weights within 1e-6
+relative in fp64 modes, 1e-4 in fp32 modes."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (compare_wfst_text, golden, random_wfst, read_history, run, sample_pairs, stage, trajectory_log2)
+
+pytestmark = pytest.mark.gpu
+
+MODES = [([], 1e-6), (["--scaled"], 1e-6), (["--float"], 1e-4), (["--float", "--scaled"], 1e-4)]
+
+
+@pytest.fixture(scope="module")
+def cli(native_lib):
+    from carmel_b200 import CLI_PATH
+    return CLI_PATH
+
+
+def _golden_traj(got, want):
+    assert [i for i, _ in got] == [i for i, _ in want]
+    for (_, g), (_, w) in zip(got, want):
+        assert abs(g - w) <= 1.01e-5 * max(1.0, abs(w)), (g, w)
+
+
+def _history_close(h_got, h_want, rel):
+    assert [h[0] for h in h_got] == [h[0] for h in h_want], (len(h_got), len(h_want))
+    for a, b in zip(h_got, h_want):
+        assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (a, b)
+        assert abs(a[2] - b[2]) <= rel * max(1.0, abs(b[2])), (a, b)
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_epron_jpron(cli, oracle_bin, tmp_path, mode, rel):
+    fst, data = stage(tmp_path, "epron-jpron.fst", "epron-jpron.data")
+    rc, out, err = run(cli, ["-t", *mode, f"--history={tmp_path}/h.p", data, fst])
+    assert rc == 0, err
+    rc, oout, oerr = run(oracle_bin, ["-t", f"--history={tmp_path}/h.o", data, fst])
+    assert rc == 0, oerr
+    if rel <= 1e-6:
+        _golden_traj(trajectory_log2(err), golden()["epron_jpron"]["trajectory_log2"])
+        assert "Converged - maximum weight change less than 0.0001 after 5 iterations." in err
+    _history_close(read_history(f"{tmp_path}/h.p"), read_history(f"{tmp_path}/h.o"), rel)
+    compare_wfst_text(out, oout, rel * 20)
+
+
+@pytest.mark.parametrize("mode,rel", MODES[:2])
+def test_cipher_cascade(cli, oracle_bin, tmp_path, golden_dir, mode, rel):
+    data, wfsa, fst = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    rc, out, err = run(cli, ["--train-cascade", "-HJ", *mode, f"--history={tmp_path}/h.p", data, wfsa, fst])
+    assert rc == 0, err
+    g = golden()["cipher"]
+    assert f"({g['composed_states']} states / {g['composed_arcs']} arcs)" in err
+    _golden_traj(trajectory_log2(err), g["trajectory_log2"])
+    assert "Converged - per-example perplexity ratio exceeds 0.999 after 22 iterations." in err
+    # learned channel against the reference's own trained file (written by the 2010 binary)
+    compare_wfst_text(open(fst + ".trained").read(), open(os.path.join(golden_dir, "cipher.fst.trained")).read(), 1e-5)
+    compare_wfst_text(open(wfsa + ".trained").read(), open(os.path.join(golden_dir, "cipher.wfsa.trained")).read(), 1e-9)
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_tagging_cascade(cli, oracle_bin, tmp_path, mode, rel):
+    data, fsa, fst = stage(tmp_path, "tagging.data", "tagging.fsa", "tagging.fst")
+    rc, out, err = run(cli, ["--train-cascade", "-HJ", *mode, f"--history={tmp_path}/h.p", data, fsa, fst])
+    assert rc == 0, err
+    g = golden()["tagging"]
+    assert f"({g['composed_states']} states / {g['composed_arcs']} arcs)" in err
+    if rel <= 1e-6:
+        _golden_traj(trajectory_log2(err), g["trajectory_log2"])
+        assert "after 9 iterations" in err
+    else:
+        got = trajectory_log2(err)
+        for (_, a), (_, b) in zip(got, g["trajectory_log2"]):
+            assert abs(a - b) <= 1e-4 * abs(b)
+
+
+OPTION_SETS = [
+    [], ["-j"], ["-u", "-M", "3"], ["-f", "0.01"], ["-U"], ["-o", "1.5"], ["--priors=0.1"], ["-j", "--priors=e^-3", "-f", "1e-3"],
+]
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_models_match_oracle(cli, oracle_bin, tmp_path, seed):
+    """M-step semantics (locked '!' and tied '!N' arcs, joint / conditional / no normalisation,
+    --priors, -f, -U, over-relaxation) on seeded random transducers: trajectories and final weights"""
+    rng = np.random.default_rng(20260301 + seed)
+    ns = int(rng.integers(2, 6))
+    fst, ins, outs, arcs = random_wfst(rng, n_states=ns, eps_rate=0.2, lock_rate=0.15, tie_rate=0.2)
+    corpus = sample_pairs(rng, arcs, ns, n_pairs=12, weighted=bool(seed % 3 == 0), ins=ins, outs=outs)
+    f, c = os.path.join(str(tmp_path), "r.fst"), os.path.join(str(tmp_path), "r.data")
+    open(f, "w").write(fst)
+    open(c, "w").write(corpus)
+    opts = OPTION_SETS[seed % len(OPTION_SETS)]
+    args = ["-t", "-M", "12", *opts, c, f]
+    rc, oout, oerr = run(oracle_bin, [*args[:-2], f"--history={tmp_path}/h.o", c, f])
+    assert rc == 0, oerr
+    for mode, rel in MODES[:2]:
+        rc, out, err = run(cli, [*args[:-2], *mode, f"--history={tmp_path}/h.p", c, f])
+        assert rc == 0, err
+        _history_close(read_history(f"{tmp_path}/h.p"), read_history(f"{tmp_path}/h.o"), 1e-6)
+        compare_wfst_text(out, oout, 1e-5)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_cascades_match_oracle(cli, oracle_bin, tmp_path, seed):
+    rng = np.random.default_rng(20260401 + seed)
+    a, ins, mids, _ = random_wfst(rng, n_states=3, n_in=2, n_out=2, eps_rate=0.2, lock_rate=0.1, tie_rate=0.1,
+                                 in_prefix="i", out_prefix="m")
+    b, _, outs, _ = random_wfst(rng, n_states=3, n_in=2, n_out=2, eps_rate=0.2, lock_rate=0.1, tie_rate=0.1,
+                                in_prefix="m", out_prefix="z")
+    lines = []
+    for _ in range(30):
+        li, lo = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        lines.append(" ".join(ins[int(rng.integers(0, 2))] for _ in range(li)))
+        lines.append(" ".join(outs[int(rng.integers(0, 2))] for _ in range(lo)))
+    d = str(tmp_path)
+    for sub in ("o", "p"):
+        os.makedirs(os.path.join(d, sub))
+        open(os.path.join(d, sub, "a.fst"), "w").write(a)
+        open(os.path.join(d, sub, "b.fst"), "w").write(b)
+        open(os.path.join(d, sub, "c.data"), "w").write("\n".join(lines) + "\n")
+    normby = ["--normby=CC", "--normby=JC", "--normby=CN"][seed % 3]
+    args = ["--train-cascade", "-M", "10", normby, "c.data", "a.fst", "b.fst"]
+    rc, _, oerr = run(oracle_bin, [*args[:-3], f"--history={d}/h.o", *args[-3:]], cwd=os.path.join(d, "o"))
+    if rc != 0:
+        pytest.skip("empty composition / no derivations for this seed")
+    rc, _, err = run(cli, [*args[:-3], f"--history={d}/h.p", *args[-3:]], cwd=os.path.join(d, "p"))
+    assert rc == 0, err
+    _history_close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), 1e-6)
+    for n in ("a.fst.trained", "b.fst.trained"):
+        compare_wfst_text(open(os.path.join(d, "p", n)).read(), open(os.path.join(d, "o", n)).read(), 1e-5)
