@@ -43,6 +43,15 @@ class CmlEstimateResult(C.Structure):
     _fields_ = [("sum_ln_p", C.c_double), ("sum_w_ln_p", C.c_double), ("n_zero", C.c_uint64)]
 
 
+class CmlJobInfo(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("examples", "trellis_states", "trellis_arcs", "n_params", "n_arcs",
+                                          "corpus_pairs", "iterations")] + [("ln_best_ppx", C.c_double),
+                                                                            ("last_ln_prob", C.c_double)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
 class CarmelB200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"carmel_b200 error {code}: {msg}")
@@ -92,6 +101,21 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_use_reduce_buffer.argtypes = [vp, vp, C.c_uint64]
     lib.cml_maximize.argtypes = [vp, C.c_double, _f64p]
     lib.cml_normalize_params.argtypes = [vp]
+    lib.cml_last_fb_time_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    lib.cml_reduce_buffer_write.argtypes = [vp, _f64p, C.c_uint64]
+    lib.cml_reduce_buffer_read.argtypes = [vp, _f64p, C.c_uint64]
+    lib.cml_job_open.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p)]
+    lib.cml_job_close.argtypes = [vp]
+    lib.cml_job_close.restype = None
+    lib.cml_job_error.argtypes = [vp]
+    lib.cml_job_error.restype = C.c_char_p
+    lib.cml_job_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    lib.cml_job_prepare.argtypes = [vp]
+    lib.cml_job_context.argtypes = [vp]
+    lib.cml_job_context.restype = vp
+    lib.cml_job_train.argtypes = [vp]
+    lib.cml_job_write.argtypes = [vp]
+    lib.cml_job_stats.argtypes = [vp, C.POINTER(CmlJobInfo)]
     lib.cml_exported_symbols.argtypes = [C.POINTER(C.c_size_t)]
     lib.cml_exported_symbols.restype = C.POINTER(C.c_char_p)
     if path is None:
@@ -258,6 +282,22 @@ class Context:
     def use_reduce_buffer(self, device_ptr: int | None, n_doubles: int = 0):
         self._check(self.lib.cml_use_reduce_buffer(self.h, C.c_void_p(device_ptr or 0), n_doubles))
 
+    def last_fb_time_ms(self) -> tuple[float, int]:
+        ms = C.c_float()
+        nk = C.c_uint32()
+        self._check(self.lib.cml_last_fb_time_ms(self.h, C.byref(ms), C.byref(nk)))
+        return float(ms.value), int(nk.value)
+
+    def set_params_ptr(self, host_ptr: int):
+        """cml_set_params from a raw (e.g. pinned) host pointer"""
+        self._check(self.lib.cml_set_params(self.h, C.cast(C.c_void_p(host_ptr), _f64p)))
+
+    def get_params_ptr(self, host_ptr: int):
+        self._check(self.lib.cml_get_params(self.h, C.cast(C.c_void_p(host_ptr), _f64p)))
+
+    def get_arc_counts_ptr(self, host_ptr: int):
+        self._check(self.lib.cml_get_arc_counts(self.h, C.cast(C.c_void_p(host_ptr), _f64p)))
+
     def maximize(self, rate: float = 1.0) -> float:
         d = C.c_double()
         self._check(self.lib.cml_maximize(self.h, rate, C.byref(d)))
@@ -265,3 +305,64 @@ class Context:
 
     def normalize_params(self):
         self._check(self.lib.cml_normalize_params(self.h))
+
+
+class Job:
+    """One `carmel -t ...` run (cml_job): argv in carmel's grammar.  After prepare() the job's Context
+    (borrowed, owned by the job) can be driven step by step; train() runs the reference's EM loop."""
+
+    def __init__(self, argv: list[str], allreduce=None):
+        self.lib = load_library()
+        args = ["carmel-b200", *argv]
+        arr = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        h = C.c_void_p()
+        rc = self.lib.cml_job_open(C.byref(h), len(args), arr)
+        self.h = h
+        if rc != 0:
+            msg = self.lib.cml_job_error(h).decode()
+            self.close()
+            raise CarmelB200Error(rc, msg)
+        self._cb = None
+        if allreduce is not None:
+            self._cb = ALLREDUCE_FN(lambda user, ptr, n: allreduce(int(ptr), int(n)))
+            self.lib.cml_job_set_allreduce(self.h, self._cb, None)
+        self.ctx = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CarmelB200Error(rc, self.lib.cml_job_error(self.h).decode())
+
+    def prepare(self) -> "Context":
+        self._check(self.lib.cml_job_prepare(self.h))
+        ctx = Context.__new__(Context)
+        ctx.lib = self.lib
+        ctx.h = None  # borrowed: never destroyed from Python
+        ctx._borrowed = C.c_void_p(self.lib.cml_job_context(self.h))
+        info = self.stats()
+        ctx.n_arcs, ctx.n_params = info["n_arcs"], info["n_params"]
+        ctx.h = ctx._borrowed
+        ctx.close = lambda: None
+        self.ctx = ctx
+        return ctx
+
+    def stats(self) -> dict:
+        i = CmlJobInfo()
+        self._check(self.lib.cml_job_stats(self.h, C.byref(i)))
+        return {n: getattr(i, n) for n, _ in CmlJobInfo._fields_}
+
+    def train(self):
+        self._check(self.lib.cml_job_train(self.h))
+
+    def write(self):
+        self._check(self.lib.cml_job_write(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cml_job_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -29,6 +29,11 @@ struct Batch {
   uint32_t cta_cap = 0;  // shared-memory capacity (states) needed by the CTA class
   DevArray<unsigned char> scratch;
   DevArray<int> scratch_lvl;
+  cudaEvent_t ev_fb0 = nullptr, ev_fb1 = nullptr;  // bracket this batch's forward-backward kernels
+  ~Batch() {
+    if (ev_fb0) cudaEventDestroy(ev_fb0);
+    if (ev_fb1) cudaEventDestroy(ev_fb1);
+  }
   // host copies kept for introspection (cml_get_example_layout)
   std::vector<uint64_t> h_state_base;
   std::vector<uint32_t> h_level_of, h_local_of, h_nlevels;
@@ -623,6 +628,11 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
   A.scratch = bt.scratch.p;
   A.scratch_lvl = bt.scratch_lvl.p;
   const size_t per_state = 2 * sizeof(Real) + (SCALED ? 2 * sizeof(int) : 0);
+  if (!bt.ev_fb0) {
+    CML_CUDA(cudaEventCreate(&bt.ev_fb0));
+    CML_CUDA(cudaEventCreate(&bt.ev_fb1));
+  }
+  CML_CUDA(cudaEventRecord(bt.ev_fb0, ctx->stream));
   for (int c = 0; c < NWARPCLS; ++c) {
     const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];
     if (!n) continue;
@@ -659,6 +669,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
       ++ctx->launches;
     }
   }
+  CML_CUDA(cudaEventRecord(bt.ev_fb1, ctx->stream));
   k_reduce_lnp<<<std::min<unsigned>(cdiv(bt.n_ex, 256), 4 * ctx->sm_count), 256, 0, ctx->stream>>>(
       bt.ex_lnp.p, bt.desc.p, bt.n_ex, ctx->reduce + ctx->n_arcs);
   ++ctx->launches;
@@ -722,6 +733,24 @@ extern "C" int cml_estimate(cml_ctx* ctx, cml_estimate_result* out) {
   return cml_estimate_finish(ctx, out);
 }
 
+extern "C" int cml_last_fb_time_ms(cml_ctx* ctx, float* ms, uint32_t* n_kernels) {
+  if (!ctx || !ms) return CML_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  float tot = 0;
+  uint32_t nk = 0;
+  for (auto& bt : ctx->batches) {
+    if (!bt->ev_fb0) continue;
+    float t = 0;
+    CML_CUDA(cudaEventElapsedTime(&t, bt->ev_fb0, bt->ev_fb1));
+    tot += t;
+    for (int c = 0; c < NCLS; ++c) nk += bt->cls_begin[c + 1] > bt->cls_begin[c];
+  }
+  *ms = tot;
+  if (n_kernels) *n_kernels = nk;
+  return CML_OK;
+}
+
 extern "C" int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n) {
   if (!ctx || !ln_p) return CML_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -751,6 +780,25 @@ extern "C" int cml_reduce_buffer(cml_ctx* ctx, void** p, uint64_t* n) {
   CML_REQUIRE(ctx->have_model, CML_ERR_STATE, "cml_set_model first");
   if (p) *p = ctx->reduce;
   if (n) *n = ctx->reduce_n;
+  return CML_OK;
+}
+
+extern "C" int cml_reduce_buffer_write(cml_ctx* ctx, const double* src, uint64_t n) {
+  if (!ctx || !src) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model && n <= ctx->reduce_n, CML_ERR_ARG, "reduce buffer smaller than requested");
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), ctx->stream));
+  CML_CUDA(cudaMemcpyAsync(ctx->reduce, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CML_OK;
+}
+
+extern "C" int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n) {
+  if (!ctx || !dst) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model && n <= ctx->reduce_n, CML_ERR_ARG, "reduce buffer smaller than requested");
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaMemcpyAsync(dst, ctx->reduce, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
   return CML_OK;
 }
 
@@ -845,7 +893,9 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_restore_params", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals",
       "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish",
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_reduce_buffer", "cml_use_reduce_buffer", "cml_maximize",
-      "cml_normalize_params", "cml_exported_symbols"};
+      "cml_normalize_params", "cml_exported_symbols", "cml_reduce_buffer_write", "cml_reduce_buffer_read",
+      "cml_job_open", "cml_job_close", "cml_job_error", "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context",
+      "cml_job_train", "cml_job_write", "cml_job_stats", "cml_last_fb_time_ms"};
   if (n) *n = sizeof(syms) / sizeof(syms[0]);
   return syms;
 }

@@ -133,7 +133,8 @@ struct TrainOpts {
   double rate_growth = 1.;          // -o
   int precision = 64;               // --float => 32
   int space = CML_SPACE_LOG;        // --scaled => CML_SPACE_SCALED
-  int device = 0;
+  int device = 0;                   // --gpu=n
+  int shard_rank = 0, shard_count = 1;  // --shard=r/N : this process trains on block r of N of the corpus
   bool quiet = false;
   std::string history_file, dump_trellis_file;
   TrainOpts();
@@ -145,11 +146,53 @@ struct IterRecord {
 struct TrainResult {
   double ln_best_ppx = 0;
   std::vector<IterRecord> history;
-  uint64_t trellis_arcs = 0, trellis_states = 0, examples = 0;
+  uint64_t trellis_arcs = 0, trellis_states = 0, examples = 0;  // resident on this GPU
 };
-// WFST::train (train.cc:503-678) with the E- and M-steps on the GPU.  On return the cascade members
-// (or x itself for a trivial cascade) hold the trained weights.  Throws std::runtime_error.
-TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<NormalizeMethod> const& methods,
-                  TrainOpts const& opt, std::ostream& log);
+// The device model: parameters = all arcs of the cascade members (or of x) in arc-table order.
+struct ModelArrays {
+  std::vector<uint32_t> chain_off, chain_param, param_group, param_tie;
+  std::vector<double> group_add, ln_w, arc_prior;
+  uint32_t n_groups = 0, n_ties = 0, n_arcs = 0, n_params = 0;
+};
+// sum-all-reduce of n doubles at device_ptr across the ranks of a multi-GPU run (NCCL, supplied by the driver)
+typedef void (*AllReduceFn)(void* user, void* device_ptr, uint64_t n_doubles);
+
+// One training run = the reference's `carmel -t ...` invocation: WFST::train (train.cc:503-678) with the
+// E- and M-steps on the GPU.  After run() the cascade members (or x for a trivial cascade) hold the
+// trained weights.  Methods throw std::runtime_error.
+struct TrainJob {
+  // inputs (filled by open_job or by the caller)
+  std::vector<std::string> fst_files;
+  std::string corpus_file, outfile;
+  std::vector<std::unique_ptr<Wfst>> chain, composed_keep;
+  Wfst* x = nullptr;  // the (composed) transducer being trained
+  Cascade cascade;
+  Corpus corpus;
+  std::vector<NormalizeMethod> methods;
+  TrainOpts opt;
+  bool flags[256] = {false};
+  std::map<std::string, std::string> lopt;
+  bool train_cascade = false;
+  AllReduceFn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  // state
+  cml_ctx* ctx = nullptr;
+  ModelArrays M;
+  std::vector<Wfst*> members;
+  bool using_cascade = false, prepared = false;
+  TrainResult res;
+
+  ~TrainJob();
+  void prepare();
+  double estimate(double& ln_unweighted);
+  TrainResult const& run(std::ostream& log);
+  void write_back();
+  void write_outputs(std::ostream& out);  // trained transducer(s) as carmel writes them
+  void finish();
+  void ok(int rc) const;
+};
+// Parse carmel's argv grammar (carmel.cc:929-1066), read the transducers, reduce / compose them and read the
+// corpus.  Returns carmel's exit code (0 = ready to train); messages go to `err`.
+int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err);
 
 }  // namespace cb

@@ -18,25 +18,6 @@ TrainOpts::TrainOpts() : ln_converge_delta(std::log(1e-4)), ln_converge_ratio(st
 
 namespace {
 
-struct Ctx {  // RAII over cml_ctx with exceptions on error
-  cml_ctx* h = nullptr;
-  Ctx(int device, int precision, int space) {
-    if (cml_create(&h, device, precision, space) != CML_OK)
-      throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
-  }
-  ~Ctx() { cml_destroy(h); }
-  void ok(int rc) const {
-    if (rc != CML_OK) throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(h));
-  }
-};
-
-// The device model: parameters = all arcs of the cascade members (or of x) in arc-table order.
-struct ModelArrays {
-  std::vector<uint32_t> chain_off, chain_param, param_group, param_tie;
-  std::vector<double> group_add, ln_w, arc_prior;
-  uint32_t n_groups = 0, n_ties = 0, n_arcs = 0, n_params = 0;
-};
-
 void add_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
   // normalisation groups: all arcs leaving a state (JOINT) or leaving a state with the same input
   // symbol (CONDITIONAL); NONE keeps weights (carmel/src/fst.h:1362-1446, cascade.h:339-350)
@@ -73,36 +54,49 @@ void add_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
   }
 }
 
+// logweight::root / ppxper keep a zero weight zero (weight.h:435-440, WEIGHT_CORRECT_ZERO): a corpus with a
+// zero-probability example therefore has "perplexity 0", which the reference then treats as the best
+inline bool w_is_zero(double ln) { return !(ln > kNegInf); }
+inline double w_root(double ln, double n) { return w_is_zero(ln) ? ln : ln / n; }
+
 void print_ppx(std::ostream& log, double ln_corpus_p, Corpus const& c) {  // weight.h:311-329
   log << "probability=" << format_base2(ln_corpus_p);
   const double n_symbol = std::max(c.n_output, c.n_input);
-  if (n_symbol) log << " per-output-symbol-perplexity(N=" << n_symbol << ")=" << format_base2(-ln_corpus_p / n_symbol);
-  if (c.n_pairs) log << " per-example-perplexity(N=" << c.n_pairs << ")=" << format_base2(-ln_corpus_p / c.n_pairs);
+  if (n_symbol) log << " per-output-symbol-perplexity(N=" << n_symbol << ")=" << format_base2(w_root(ln_corpus_p, -n_symbol));
+  if (c.n_pairs) log << " per-example-perplexity(N=" << c.n_pairs << ")=" << format_base2(w_root(ln_corpus_p, -(double)c.n_pairs));
 }
 
 }  // namespace
 
-TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<NormalizeMethod> const& methods,
-                  TrainOpts const& opt, std::ostream& log) {
-  TrainResult res;
-  const bool using_cascade = !cascade.trivial;
-  std::vector<Wfst*> members = using_cascade ? cascade.members : std::vector<Wfst*>{&x};
+void TrainJob::ok(int rc) const {
+  if (rc != CML_OK) throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(ctx));
+}
 
-  // ---- model tables ----
-  ModelArrays M;
-  for (size_t i = 0; i < members.size(); ++i) add_member(*members[i], i < methods.size() ? methods[i] : NormalizeMethod(), M);
+TrainJob::~TrainJob() {
+  if (ctx) cml_destroy(ctx);
+}
+
+// Everything up to the first E-step: model tables, initial normalisation, prior counts, derivation
+// lattices (this rank's shard) flattened and resident on the GPU.
+void TrainJob::prepare() {
+  if (prepared) return;
+  using_cascade = !cascade.trivial;
+  members = using_cascade ? cascade.members : std::vector<Wfst*>{x};
+  for (size_t i = 0; i < members.size(); ++i)
+    add_member(*members[i], i < methods.size() ? methods[i] : NormalizeMethod(), M);
   M.n_params = (uint32_t)M.ln_w.size();
-  M.n_arcs = (uint32_t)x.num_arcs();
+  M.n_arcs = (uint32_t)x->num_arcs();
   if (using_cascade) {
     M.chain_off.push_back(0);
-    for (auto const& st : x.states)
+    for (auto const& st : x->states)
       for (Arc const& a : st) {
         auto const& ch = cascade.chains.at(a.group);
         M.chain_param.insert(M.chain_param.end(), ch.begin(), ch.end());
         M.chain_off.push_back((uint32_t)M.chain_param.size());
       }
   }
-  Ctx ctx(opt.device, opt.precision, opt.space);
+  if (cml_create(&ctx, opt.device, opt.precision, opt.space) != CML_OK)
+    throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
   cml_model mm{};
   mm.n_arcs = M.n_arcs;
   mm.chain_off = using_cascade ? M.chain_off.data() : nullptr;
@@ -114,15 +108,15 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
   mm.n_groups = M.n_groups;
   mm.group_add = M.group_add.data();
   mm.n_ties = M.n_ties;
-  ctx.ok(cml_set_model(ctx.h, &mm));
-  ctx.ok(cml_set_params(ctx.h, M.ln_w.data()));
-  ctx.ok(cml_normalize_params(ctx.h));  // train.cc:509 cascade.normalize(methods)
+  ok(cml_set_model(ctx, &mm));
+  ok(cml_set_params(ctx, M.ln_w.data()));
+  ok(cml_normalize_params(ctx));  // train.cc:509 cascade.normalize(methods)
 
   // prior counts per arc-table entry (train.cc:134-153; derivations.h:96-101): the -f floor, plus
   // the (normalised) arc weight itself with -U
   if (opt.ln_smooth_floor > kNegInf || opt.weight_is_prior) {
     std::vector<double> w(M.n_params);
-    ctx.ok(cml_get_params(ctx.h, w.data()));
+    ok(cml_get_params(ctx, w.data()));
     M.arc_prior.assign(M.n_arcs, opt.ln_smooth_floor > kNegInf ? std::exp(opt.ln_smooth_floor) : 0.);
     if (opt.weight_is_prior)
       for (uint32_t a = 0; a < M.n_arcs; ++a) {
@@ -134,25 +128,55 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
         M.arc_prior[a] += std::exp(lw);
       }
     mm.arc_prior = M.arc_prior.data();
-    ctx.ok(cml_set_model(ctx.h, &mm));
-    ctx.ok(cml_set_params(ctx.h, w.data()));
+    ok(cml_set_model(ctx, &mm));
+    ok(cml_set_params(ctx, w.data()));
   }
 
   // ---- derivation lattices: built once, resident on the GPU (carmel's -: cache semantics) ----
+  // With --shard=r/N only a contiguous block of the corpus (balanced by string length) is built and
+  // kept on this GPU; corpus statistics are then made global through the all-reduce hook.
+  size_t e0 = 0, e1 = corpus.examples.size();
+  if (opt.shard_count > 1) {
+    std::vector<double> cost(corpus.examples.size() + 1, 0.);
+    for (size_t e = 0; e < corpus.examples.size(); ++e)
+      cost[e + 1] = cost[e] + 1. + corpus.examples[e].in.size() + corpus.examples[e].out.size();
+    auto cut = [&](int r) {
+      const double target = cost.back() * r / opt.shard_count;
+      return (size_t)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
+    };
+    e0 = opt.shard_rank == 0 ? 0 : std::min(cut(opt.shard_rank), corpus.examples.size());
+    e1 = opt.shard_rank == opt.shard_count - 1 ? corpus.examples.size() : std::min(cut(opt.shard_rank + 1), corpus.examples.size());
+    if (e1 < e0) e1 = e0;
+  }
   {
+    Corpus local;
+    local.examples.assign(std::make_move_iterator(corpus.examples.begin() + e0),
+                          std::make_move_iterator(corpus.examples.begin() + e1));
     TrellisBatch tb;
     std::vector<uint32_t> dropped;
-    build_trellises(x, corpus, tb, dropped);
+    build_trellises(*x, local, tb, dropped);
     for (uint32_t e : dropped)  // cached_derivs.h:53-57,87-93
-      std::cerr << "No derivations in transducer for input/output #" << e + 1 << ":\n";
-    if (!dropped.empty()) {
-      std::vector<Example> keep;
-      keep.reserve(tb.kept_example.size());
-      for (uint32_t e : tb.kept_example) keep.push_back(std::move(corpus.examples[e]));
-      corpus.examples.swap(keep);
-      corpus.count();
+      std::cerr << "No derivations in transducer for input/output #" << e0 + e + 1 << ":\n";
+    std::vector<Example> keep;
+    keep.reserve(tb.kept_example.size());
+    for (uint32_t e : tb.kept_example) keep.push_back(std::move(local.examples[e]));
+    corpus.examples.swap(keep);
+    corpus.count();
+    if (opt.shard_count > 1) {  // global corpus statistics: one small all-reduce
+      if (!allreduce) throw std::runtime_error("--shard needs an all-reduce hook (use the multi-GPU driver)");
+      void* buf;
+      uint64_t nbuf;
+      ok(cml_reduce_buffer(ctx, &buf, &nbuf));
+      double h[4] = {(double)corpus.n_pairs, corpus.total_weight, corpus.n_input, corpus.n_output};
+      ok(cml_reduce_buffer_write(ctx, h, 4));
+      allreduce(allreduce_user, buf, nbuf);
+      ok(cml_reduce_buffer_read(ctx, h, 4));
+      corpus.n_pairs = (uint32_t)(h[0] + .5);
+      corpus.total_weight = h[1];
+      corpus.n_input = h[2];
+      corpus.n_output = h[3];
     }
-    if (corpus.examples.empty()) {
+    if (corpus.n_pairs == 0) {
       std::cerr << "No training example had a derivation - check your models, quotes, manually compose with -i, etc.\n";
       throw std::runtime_error("No training example had a derivation - aborting training.");
     }
@@ -160,56 +184,72 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
       std::ofstream o(opt.dump_trellis_file, std::ios::binary);
       tb.dump(o, M.n_arcs);
     }
-    cml_trellis_batch b{};
-    b.n_ex = tb.ex_states.size();
-    b.ex_states = tb.ex_states.data();
-    b.ex_fin = tb.ex_fin.data();
-    b.ex_weight = tb.ex_weight.data();
-    b.arc_off = tb.arc_off.data();
-    b.arc_dst = tb.arc_dst.data();
-    b.arc_id = tb.arc_id.data();
-    ctx.ok(cml_add_trellises(ctx.h, &b));
+    if (!tb.ex_states.empty()) {
+      cml_trellis_batch b{};
+      b.n_ex = tb.ex_states.size();
+      b.ex_states = tb.ex_states.data();
+      b.ex_fin = tb.ex_fin.data();
+      b.ex_weight = tb.ex_weight.data();
+      b.arc_off = tb.arc_off.data();
+      b.arc_dst = tb.arc_dst.data();
+      b.arc_id = tb.arc_id.data();
+      ok(cml_add_trellises(ctx, &b));
+    }
     res.trellis_arcs = tb.arc_dst.size();
-    res.examples = b.n_ex;
+    res.examples = tb.ex_states.size();
     for (uint32_t n : tb.ex_states) res.trellis_states += n;
   }
+  prepared = true;
+}
 
-  auto estimate = [&](double& ln_unweighted) -> double {  // returns ln weighted corpus prob
-    cml_estimate_result r;
-    ctx.ok(cml_estimate(ctx.h, &r));
-    if (r.n_zero) {
-      ln_unweighted = kNegInf;
-      return kNegInf;
-    }
-    ln_unweighted = r.sum_ln_p;
-    return r.sum_w_ln_p;
-  };
-  auto write_back = [&]() {  // device parameters -> transducer arcs
-    std::vector<double> w(M.n_params);
-    ctx.ok(cml_get_params(ctx.h, w.data()));
-    size_t p = 0;
-    for (Wfst* m : members)
-      for (auto& st : m->states)
-        for (Arc& a : st) a.ln_w = w[p++];
-    if (using_cascade) {  // cascade.update(): composed weights = chain products
-      size_t a_id = 0;
-      for (auto& st : x.states)
-        for (Arc& a : st) {
-          double lw = 0;
-          for (uint32_t k = M.chain_off[a_id]; k < M.chain_off[a_id + 1]; ++k) lw += w[M.chain_param[k]];
-          a.ln_w = lw;
-          ++a_id;
-        }
-    }
-  };
-  auto finish = [&]() {
-    if (!opt.history_file.empty()) {
-      std::ofstream o(opt.history_file);
-      o.precision(17);
-      for (auto const& h : res.history) o << h.iter << ' ' << h.ln_prob << ' ' << h.ln_weighted_prob << ' ' << h.max_change << '\n';
-    }
-  };
+// one E-step over all resident lattices (+ the per-iteration all-reduce when sharded)
+double TrainJob::estimate(double& ln_unweighted) {
+  cml_estimate_result r;
+  ok(cml_estimate_launch(ctx));
+  if (allreduce && opt.shard_count > 1) {
+    void* buf;
+    uint64_t nbuf;
+    ok(cml_reduce_buffer(ctx, &buf, &nbuf));
+    allreduce(allreduce_user, buf, nbuf);
+  }
+  ok(cml_estimate_finish(ctx, &r));
+  if (r.n_zero) {  // some example has probability zero: the corpus probability is zero
+    ln_unweighted = kNegInf;
+    return kNegInf;
+  }
+  ln_unweighted = r.sum_ln_p;
+  return r.sum_w_ln_p;
+}
 
+void TrainJob::write_back() {  // device parameters -> transducer arcs
+  std::vector<double> w(M.n_params);
+  ok(cml_get_params(ctx, w.data()));
+  size_t p = 0;
+  for (Wfst* m : members)
+    for (auto& st : m->states)
+      for (Arc& a : st) a.ln_w = w[p++];
+  if (using_cascade) {  // cascade.update(): composed weights = chain products
+    size_t a_id = 0;
+    for (auto& st : x->states)
+      for (Arc& a : st) {
+        double lw = 0;
+        for (uint32_t k = M.chain_off[a_id]; k < M.chain_off[a_id + 1]; ++k) lw += w[M.chain_param[k]];
+        a.ln_w = lw;
+        ++a_id;
+      }
+  }
+}
+
+void TrainJob::finish() {
+  if (!opt.history_file.empty()) {
+    std::ofstream o(opt.history_file);
+    o.precision(17);
+    for (auto const& h : res.history) o << h.iter << ' ' << h.ln_prob << ' ' << h.ln_weighted_prob << ' ' << h.max_change << '\n';
+  }
+}
+
+TrainResult const& TrainJob::run(std::ostream& log) {
+  prepare();
   double ln_corpus_p = 0;
   // ---- -M 0 / -M 1: fractional counts only / a single iteration (train.cc:520-538) ----
   if (opt.max_iter == 0 || opt.max_iter == 1) {
@@ -220,9 +260,9 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
     if (opt.max_iter == 0) {
       log << "0 iterations specified for training; output weights will be unnormalized fractional counts (except locked arcs).\n";
       std::vector<double> counts(M.n_arcs);
-      ctx.ok(cml_get_arc_counts(ctx.h, counts.data()));
+      ok(cml_get_arc_counts(ctx, counts.data()));
       size_t a_id = 0;
-      for (auto& st : x.states)
+      for (auto& st : x->states)
         for (Arc& a : st) {
           const double c = counts[a_id] + (M.arc_prior.empty() ? 0. : M.arc_prior[a_id]);
           if (a.group != kLocked || using_cascade) a.ln_w = c > 0 ? std::log(c) : kNegInf;
@@ -230,11 +270,11 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
         }
     } else {
       double d;
-      ctx.ok(cml_maximize(ctx.h, 1., &d));
+      ok(cml_maximize(ctx, 1., &d));
       write_back();
     }
     log << "\n";
-    res.ln_best_ppx = -p / corpus.total_weight;
+    res.ln_best_ppx = w_root(p, -corpus.total_weight);
     finish();
     return res;
   }
@@ -264,8 +304,14 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
           << format_weight(ln_last_change) << "\n";
       break;
     }
+    if (~opt.max_iter && train_iter > opt.max_iter + 1) {
+      // the reference would iterate forever here (no iteration was ever accepted as "best"); stop instead
+      std::cerr << "Warning: no iteration produced usable weights after " << opt.max_iter << " iterations; stopping.\n";
+      ok(cml_snapshot_params(ctx, SLOT_BEST));
+      break;
+    }
     const double p = estimate(ln_corpus_p);
-    const double ln_new_ppx = -p / corpus.total_weight;  // ppxper(totalEmpiricalWeight)
+    const double ln_new_ppx = w_root(p, -corpus.total_weight);  // ppxper(totalEmpiricalWeight)
     res.history.push_back({train_iter, ln_corpus_p, p, std::exp(ln_last_change)});
     log << "i=" << train_iter << " (rate=" << learning_rate << "): ";
     print_ppx(log, ln_corpus_p, corpus);
@@ -273,7 +319,7 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
       log << " (new best)";
       ln_best_ppx = ln_new_ppx;
       have_good_weights = true;
-      ctx.ok(cml_snapshot_params(ctx.h, SLOT_BEST));  // save_best
+      ok(cml_snapshot_params(ctx, SLOT_BEST));  // save_best
     }
     double ln_ratio;
     if (first_time) {
@@ -282,8 +328,7 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
       ln_ratio = kNegInf;
     } else {
       // relative_perplexity_ratio (weight.h:247-249): (new/old)^(1/|ln new|)
-      ln_ratio = (ln_new_ppx - ln_last_ppx) / std::fabs(ln_new_ppx);
-      if (!(ln_new_ppx > kNegInf)) ln_ratio = kNegInf;
+      ln_ratio = w_root(ln_new_ppx - ln_last_ppx, std::fabs(ln_new_ppx));
       log << " (relative-perplexity-ratio=" << format_weight(ln_ratio) << ")";
       if (ln_last_change < 0) log << ", max {d(weight)}=" << format_weight(ln_last_change);
       log << std::endl;
@@ -293,7 +338,7 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
         if (learning_rate > 1) {
           log << "Failed to improve (relaxation rate too high); starting again at learning rate 1" << std::endl;
           learning_rate = 1;
-          ctx.ok(cml_restore_params(ctx.h, SLOT_EM));  // keep_em_weight
+          ok(cml_restore_params(ctx, SLOT_EM));  // keep_em_weight
           last_was_reset = true;
           continue;
         }
@@ -311,12 +356,12 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
     double max_delta = 10;
     if (learning_rate > 1.) {
       // the raw EM weights (rate 1) are needed if the relaxed step fails: compute them first
-      ctx.ok(cml_snapshot_params(ctx.h, 2));
-      ctx.ok(cml_maximize(ctx.h, 1., &max_delta));
-      ctx.ok(cml_snapshot_params(ctx.h, SLOT_EM));
-      ctx.ok(cml_restore_params(ctx.h, 2));
+      ok(cml_snapshot_params(ctx, 2));
+      ok(cml_maximize(ctx, 1., &max_delta));
+      ok(cml_snapshot_params(ctx, SLOT_EM));
+      ok(cml_restore_params(ctx, 2));
     }
-    ctx.ok(cml_maximize(ctx.h, learning_rate, &max_delta));
+    ok(cml_maximize(ctx, learning_rate, &max_delta));
     if (using_cascade) max_delta = 10;  // train.cc:921-922
     ln_last_change = max_delta > 0 ? std::log(max_delta) : kNegInf;
     if (ln_last_change <= opt.ln_converge_delta && have_good_weights) {
@@ -329,7 +374,7 @@ TrainResult train(Wfst& x, Cascade& cascade, Corpus& corpus, std::vector<Normali
   log << "Setting weights to model with lowest per-example-perplexity ( = "
          "prod[modelprob(example)]^(-1/num_examples) = 2^(-log_2(p_model(corpus))/N) = "
       << format_base2(ln_best_ppx) << std::endl;
-  ctx.ok(cml_restore_params(ctx.h, SLOT_BEST));  // load_best (+ use_counts_final for cascades)
+  ok(cml_restore_params(ctx, SLOT_BEST));  // load_best (+ use_counts_final for cascades)
   write_back();
   res.ln_best_ppx = ln_best_ppx;
   finish();

@@ -145,6 +145,9 @@ int cml_estimate(cml_ctx* ctx, cml_estimate_result* out);
 /* asynchronous halves of cml_estimate for multi-GPU use: launch, (all-reduce the reduce buffer), finish */
 int cml_estimate_launch(cml_ctx* ctx);
 int cml_estimate_finish(cml_ctx* ctx, cml_estimate_result* out);
+/* device time (CUDA events on the context's stream) spent in the forward-backward-count kernels of the
+ * last cml_estimate_launch, and how many such kernels ran (one per resident example class). */
+int cml_last_fb_time_ms(cml_ctx* ctx, float* ms, uint32_t* n_kernels);
 /* per-example ln P_e of the last estimate (order of insertion), for parity tests */
 int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n);
 /* expected counts per arc-table id (linear) of the last estimate */
@@ -164,6 +167,35 @@ int cml_use_reduce_buffer(cml_ctx* ctx, void* device_ptr, uint64_t n_doubles);
 int cml_maximize(cml_ctx* ctx, double rate, double* max_delta);
 /* WFST::normalize of the current parameters only (train.cc:509 initial cascade.normalize) */
 int cml_normalize_params(cml_ctx* ctx);
+
+/* host access to the first n doubles of the reduce buffer (small control all-reduces) */
+int cml_reduce_buffer_write(cml_ctx* ctx, const double* src, uint64_t n);
+int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n);
+
+/* ---- a whole training run: the `carmel -t ...` / `--train-cascade` invocation ------------------ *
+ * Replaces main()'s -t branch (carmel/src/carmel.cc:1155-1173,1286-1355,1415-1437) and WFST::train
+ * (carmel/src/train.cc:503-678).  argv follows carmel's grammar (carmel.cc:929-1066): bundled flags,
+ * value flags taking the next argument, --key[=value]; first file = pair corpus, then the
+ * transducers (composed left to right).  Extra long options of this implementation: --float
+ * (fp32 scores), --scaled (scaled linear space), --gpu=n, --shard=r/N (this process keeps block r of
+ * N of the corpus on its GPU; needs an all-reduce hook), --history=file, --dump-trellis=file.
+ * Log lines go to stderr in the reference's format (train.cc:587-627). */
+typedef struct cml_job cml_job;
+typedef void (*cml_allreduce_fn)(void* user, void* device_ptr, uint64_t n_doubles); /* in-place fp64 sum */
+typedef struct cml_job_info {
+  uint64_t examples, trellis_states, trellis_arcs; /* resident on this GPU */
+  uint64_t n_params, n_arcs, corpus_pairs, iterations;
+  double ln_best_ppx, last_ln_prob;
+} cml_job_info;
+int cml_job_open(cml_job** out, int argc, const char* const* argv); /* parse, read, reduce, compose */
+void cml_job_close(cml_job* job);
+const char* cml_job_error(cml_job* job);
+int cml_job_set_allreduce(cml_job* job, cml_allreduce_fn fn, void* user);
+int cml_job_prepare(cml_job* job); /* model + lattices onto the GPU; no iteration yet */
+cml_ctx* cml_job_context(cml_job* job); /* valid after cml_job_prepare; owned by the job */
+int cml_job_train(cml_job* job);   /* the EM loop to convergence; trained weights end up in the job */
+int cml_job_write(cml_job* job);   /* stdout / -F file / <input>.trained, as carmel writes them */
+int cml_job_stats(cml_job* job, cml_job_info* info);
 
 /* ---- host-side helpers exported for bindings and tests (no GPU needed) ------------------------ */
 /* Every symbol this header declares, for the loader test. */

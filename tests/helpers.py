@@ -26,7 +26,7 @@ def stage(tmp_path, *names):
     return out
 
 
-def run(binary, args, cwd=None, timeout=600):
+def run(binary, args, cwd=None, timeout=120):
     p = subprocess.run([binary, *args], cwd=cwd, capture_output=True, text=True, timeout=timeout)
     return p.returncode, p.stdout, p.stderr
 
