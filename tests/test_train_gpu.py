@@ -101,6 +101,8 @@ def test_random_models_match_oracle(cli, oracle_bin, tmp_path, seed):
     args = ["-t", "-M", "12", *opts, c, f]
     rc, oout, oerr = run(oracle_bin, [*args[:-2], f"--history={tmp_path}/h.o", c, f])
     assert rc == 0, oerr
+    if any(abs(h[1]) < 1e-6 for h in read_history(f"{tmp_path}/h.o")):
+        pytest.skip("degenerate corpus (probability 1): the convergence ratio divides by |ln ppx| ~ 1e-17")
     for mode, rel in MODES[:2]:
         rc, out, err = run(cli, [*args[:-2], *mode, f"--history={tmp_path}/h.p", c, f])
         assert rc == 0, err
