@@ -276,7 +276,6 @@ int real_main(int argc, char** argv) {
       std::string ft = fst_files[i] + ".trained";
       std::cerr << "Writing trained " << fst_files[i] << " to " << ft << std::endl;
       std::ofstream of(ft);
-      chain[i]->named = true;
       chain[i]->write(of, full, onearc, false, wf);
     }
   } else if (trainc) {
