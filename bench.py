@@ -294,7 +294,8 @@ def main():
     # ---- e2e: host buffers through the C ABI every step
     n_params, n_arcs = info["n_params"], info["n_arcs"]
     h_params = torch.empty(n_params, dtype=torch.float64).pin_memory()
-    h_counts = torch.empty(n_arcs, dtype=torch.float64).pin_memory()
+    n_slots = ctx.count_slots()
+    h_counts = torch.empty(n_slots, dtype=torch.float64).pin_memory()
     ctx.get_params_ptr(h_params.data_ptr())
 
     def e2e_step():
@@ -304,7 +305,7 @@ def main():
             p, n = ctx.reduce_buffer()
             allreduce(p, n)
         ctx.estimate_finish()                             # D2H: likelihood scalars
-        ctx.get_arc_counts_ptr(h_counts.data_ptr())       # D2H: expected counts
+        ctx.get_counts_ptr(h_counts.data_ptr(), n_slots)  # D2H: expected counts (one per count slot)
         ctx.maximize(1.0)
         ctx.get_params_ptr(h_params.data_ptr())           # D2H: new parameters
 
@@ -312,7 +313,7 @@ def main():
         e2e_step()
     ms_e2e = timed(e2e_step, a.steps)
     e2e = {"value": arcs_total * a.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": 8 * n_params,
-           "d2h_bytes_per_step": 8 * n_params + 8 * n_arcs + 24, "ms_per_step": ms_e2e / a.steps,
+           "d2h_bytes_per_step": 8 * n_params + 8 * n_slots + 24, "ms_per_step": ms_e2e / a.steps,
            "lattices": "resident (carmel -: derivation-cache semantics); one-time host build + flatten + upload "
                        f"took {t_build:.2f}s on this rank"}
 
@@ -339,7 +340,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "totals": {"examples": ex_total, "trellis_arcs": arcs_total,
                                              "trellis_states": states_total, "n_params": n_params, "n_arcs": n_arcs},
-                "last_ln_prob": None}
+                "layout": ctx.layout_stats(), "count_slots": n_slots}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

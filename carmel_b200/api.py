@@ -18,6 +18,7 @@ SPACE_LOG, SPACE_SCALED = 0, 1
 NO_GROUP = 0xFFFFFFFF
 LOCKED_GROUP = 0
 
+OPT_ARC_COUNTS, OPT_NO_ELL = 1, 2
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV = 0, -1, -2, -3, -4, -5
 
 _u32p = C.POINTER(C.c_uint32)
@@ -100,6 +101,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_reduce_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.cml_use_reduce_buffer.argtypes = [vp, vp, C.c_uint64]
     lib.cml_maximize.argtypes = [vp, C.c_double, _f64p]
+    lib.cml_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.cml_layout_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
+    lib.cml_count_slots.argtypes = [vp]
+    lib.cml_count_slots.restype = C.c_uint64
+    lib.cml_get_counts.argtypes = [vp, _f64p, C.c_uint64]
     lib.cml_normalize_params.argtypes = [vp]
     lib.cml_last_fb_time_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     lib.cml_reduce_buffer_write.argtypes = [vp, _f64p, C.c_uint64]
@@ -267,6 +273,25 @@ class Context:
         a = np.empty(n, np.float64)
         self._check(self.lib.cml_get_example_logprob(self.h, _ptr(a, _f64p), n))
         return a
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.cml_set_option(self.h, option, value))
+
+    def layout_stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.lib.cml_layout_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("ell_examples", "ell_arcs", "ell_records", "csr_examples"), (int(x.value) for x in v)))
+
+    def count_slots(self) -> int:
+        return int(self.lib.cml_count_slots(self.h))
+
+    def counts(self) -> np.ndarray:
+        a = np.empty(self.count_slots(), np.float64)
+        self._check(self.lib.cml_get_counts(self.h, _ptr(a, _f64p), a.size))
+        return a
+
+    def get_counts_ptr(self, host_ptr: int, n: int):
+        self._check(self.lib.cml_get_counts(self.h, C.cast(C.c_void_p(host_ptr), _f64p), n))
 
     def arc_counts(self) -> np.ndarray:
         a = np.empty(self.n_arcs, np.float64)

@@ -1,35 +1,58 @@
 // cml_device.cu -- C ABI (include/carmel_b200.h) of the B200-native carmel training hot path:
-// context, model tables, trellis flattening into layered CSR, E-step and M-step launches.
-// sm_100a only; there is no CPU fallback (every compute entry point needs the device).
+// context, model tables, trellis flattening (layered CSR + level-sliced ELL), E-step and M-step
+// launches.  sm_100a only; there is no CPU fallback (every compute entry point needs the device).
 #include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <thread>
 
 #include "cml_common.cuh"
+#include "cml_kernels_ell.cuh"
 #include "cml_kernels_fb.cuh"
 #include "cml_kernels_model.cuh"
 
 namespace {
 
-enum ExClass { CLS_WARP0 = 0 /* .. CLS_WARP0+NWARPCLS-1 */, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, NCLS = 8 };
+// ---- example classes ------------------------------------------------------------------------------
+// ELL classes (scaled space only): one example per group of 4/8/16/32 lanes, level-sliced ELL layout.
+// CSR classes (everything else): one example per warp (shared-memory capacity classes), per CTA, or
+// per CTA with alpha/beta in an HBM scratch.
+enum { NELL = 4 };
+static const int kEllG[NELL] = {4, 8, 16, 32};
+enum ExClass { CLS_WARP0 = 0, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, NCLS = 8 };
 static const uint32_t kWarpCaps[NWARPCLS] = {64, 128, 256, 512, 1024, 2048};
+static const uint32_t kPadNone = 0xFFFFFFFFu;
 
 struct Batch {
   uint64_t n_ex = 0, n_states = 0, n_arcs = 0, n_levels = 0;
+  DevArray<double> ex_lnp;
+  DevArray<double> ex_weight;  // for k_reduce_lnp
+  // --- CSR part (v1 kernels)
+  uint64_t csr_ex = 0;
   DevArray<CmlExDesc> desc;
   DevArray<uint32_t> lvl_off, in_off, out_off;
   DevArray<uint2> in_arc, out_arc;
-  DevArray<double> ex_lnp;
-  DevArray<uint32_t> ex_list;  // all classes concatenated
+  DevArray<uint32_t> ex_list;  // all CSR classes concatenated (indices into desc)
   uint32_t cls_begin[NCLS + 1] = {0};
-  uint32_t cta_cap = 0;  // shared-memory capacity (states) needed by the CTA class
+  uint32_t cta_cap = 0;
   DevArray<unsigned char> scratch;
   DevArray<int> scratch_lvl;
+  // --- ELL part (v2 kernel)
+  uint64_t ell_ex = 0, ell_arcs = 0, ell_pad_records = 0;
+  DevArray<cmlk::EllDesc> edesc;
+  DevArray<uint4> lvl_meta;
+  DevArray<uint2> ell_in, ell_out;
+  DevArray<uint32_t> ell_list;
+  uint32_t ell_begin[NELL + 1] = {0};
+  uint32_t ell_ring[NELL] = {0};
+  DevArray<unsigned char> alpha_g;
+  DevArray<int> lvl_exp;
   cudaEvent_t ev_fb0 = nullptr, ev_fb1 = nullptr;  // bracket this batch's forward-backward kernels
+  uint32_t n_fb_kernels = 0;
   ~Batch() {
     if (ev_fb0) cudaEventDestroy(ev_fb0);
     if (ev_fb1) cudaEventDestroy(ev_fb1);
@@ -51,19 +74,24 @@ struct cml_ctx {
   size_t smem_optin = 0;
   std::string err;
   uint64_t launches = 0;
+  int opt_arc_counts = 0;  // CML_OPT_ARC_COUNTS: keep one count slot per arc-table entry
+  int opt_no_ell = 0;      // CML_OPT_NO_ELL: force the CSR kernels (tests)
 
   // model
   bool have_model = false, trivial = true;
-  uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0;
+  uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0, n_slots = 0;
+  bool slots_are_arcs = true;
+  std::vector<uint32_t> h_arc_slot;  // host copy: slot of every arc (kPadNone = contributes to no parameter)
   DevArray<uint32_t> chain_off, chain_param, param_group, param_tie, group_off, group_members, tie_off, tie_members;
-  DevArray<double> arc_prior, group_add;
+  DevArray<uint32_t> arc_slot, slot_off, slot_param;
+  DevArray<double> slot_prior, group_add;
   bool have_prior = false, have_add = false;
   DevArray<double> ln_w, snap[4], arc_lnw, acc, u, old, gsum, glocked, tie_arc, tie_state, tie_maxl;
-  DevArray<unsigned char> arc_w_real;
+  DevArray<unsigned char> arc_w_real, arc_ws;
   DevArray<unsigned long long> maxchg;
   bool have_params = false;
 
-  // reduce buffer: [n_arcs counts | sum_ln_p | sum_w_ln_p | n_zero]
+  // reduce buffer: [n_slots counts | sum_ln_p | sum_w_ln_p | n_zero]
   DevArray<double> reduce_own;
   double* reduce = nullptr;
   uint64_t reduce_n = 0;
@@ -87,7 +115,7 @@ static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b -
 // -------------------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------------------
-extern "C" const char* cml_version(void) { return "carmel_b200 0.1 (sm_100a)"; }
+extern "C" const char* cml_version(void) { return "carmel_b200 0.2 (sm_100a)"; }
 
 extern "C" int cml_create(cml_ctx** out, int device, int precision, int space) {
   if (!out) return CML_ERR_ARG;
@@ -170,6 +198,21 @@ extern "C" int cml_synchronize(cml_ctx* ctx) {
 
 extern "C" uint64_t cml_launch_count(cml_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int cml_set_option(cml_ctx* ctx, int option, int value) {
+  if (!ctx) return CML_ERR_ARG;
+  switch (option) {
+    case CML_OPT_ARC_COUNTS:
+      CML_REQUIRE(!ctx->have_model, CML_ERR_STATE, "CML_OPT_ARC_COUNTS must be set before cml_set_model");
+      ctx->opt_arc_counts = value;
+      return CML_OK;
+    case CML_OPT_NO_ELL:
+      CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "CML_OPT_NO_ELL must be set before cml_add_trellises");
+      ctx->opt_no_ell = value;
+      return CML_OK;
+    default: ctx->err = "unknown option"; return CML_ERR_ARG;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // model
 // -------------------------------------------------------------------------------------------------
@@ -188,6 +231,7 @@ static void build_csr(uint32_t n_keys, const std::vector<uint32_t>& key_of, std:
 extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   if (!ctx || !m) return CML_ERR_ARG;
   cudaSetDevice(ctx->device);
+  CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "cml_set_model after cml_add_trellises: clear the trellises first");
   CML_REQUIRE(m->n_arcs > 0 && m->n_params > 0, CML_ERR_ARG, "empty model");
   CML_REQUIRE(m->param_group && m->param_tie, CML_ERR_ARG, "param_group / param_tie are required");
   const bool trivial = (m->chain_off == nullptr);
@@ -211,21 +255,75 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   build_csr(m->n_groups, pg, goff, gmem);
   build_csr(m->n_ties, tie_key, toff, tmem);
 
+  // Count slots.  The expected count of an arc is only ever used through the UNLOCKED parameters of
+  // its chain (cascade.h:286-325 distribute_counts skips locked arcs), so arcs whose chains have the
+  // same unlocked parameters can share one accumulator: the cipher's 19,683 composed arcs collapse onto
+  // its 729 channel parameters, and arcs with fully locked chains need no accumulator at all.
+  std::vector<uint32_t> arc_slot(m->n_arcs), slot_off, slot_param;
+  std::vector<double> slot_prior;
+  uint32_t n_slots = 0;
+  const bool merge = !trivial && !ctx->opt_arc_counts;
+  if (!merge) {
+    n_slots = m->n_arcs;
+    for (uint32_t a = 0; a < m->n_arcs; ++a) arc_slot[a] = a;
+    if (!trivial) {
+      slot_off.assign(m->chain_off, m->chain_off + m->n_arcs + 1);
+      slot_param.assign(m->chain_param, m->chain_param + m->chain_off[m->n_arcs]);
+    }
+    if (m->arc_prior) slot_prior.assign(m->arc_prior, m->arc_prior + m->n_arcs);
+  } else {
+    std::map<std::vector<uint32_t>, uint32_t> ids;
+    slot_off.push_back(0);
+    std::vector<uint32_t> key;
+    for (uint32_t a = 0; a < m->n_arcs; ++a) {
+      key.clear();
+      for (uint32_t k = m->chain_off[a]; k < m->chain_off[a + 1]; ++k)
+        if (m->param_tie[m->chain_param[k]] != CML_LOCKED_GROUP) key.push_back(m->chain_param[k]);
+      if (key.empty()) {
+        arc_slot[a] = kPadNone;
+        continue;
+      }
+      auto ins = ids.emplace(key, n_slots);
+      if (ins.second) {
+        ++n_slots;
+        slot_param.insert(slot_param.end(), key.begin(), key.end());
+        slot_off.push_back((uint32_t)slot_param.size());
+        slot_prior.push_back(0.);
+      }
+      arc_slot[a] = ins.first->second;
+      if (m->arc_prior) slot_prior[arc_slot[a]] += m->arc_prior[a];
+    }
+    if (n_slots == 0) {  // nothing trainable: keep one dummy slot so buffers are non-empty
+      n_slots = 1;
+      slot_off.push_back(0);
+      slot_prior.push_back(0.);
+    }
+    if (!m->arc_prior) slot_prior.clear();
+  }
+
   cudaStream_t s = ctx->stream;
   ctx->trivial = trivial;
   ctx->n_arcs = m->n_arcs;
   ctx->n_params = m->n_params;
   ctx->n_groups = m->n_groups;
   ctx->n_ties = m->n_ties;
+  ctx->n_slots = n_slots;
+  ctx->slots_are_arcs = !merge;
+  ctx->h_arc_slot = arc_slot;
   if (!trivial) {
     CML_CUDA(ctx->chain_off.upload(m->chain_off, m->n_arcs + 1, s));
     CML_CUDA(ctx->chain_param.upload(m->chain_param, m->chain_off[m->n_arcs], s));
+    CML_CUDA(ctx->slot_off.upload(slot_off.data(), slot_off.size(), s));
+    CML_CUDA(ctx->slot_param.upload(slot_param.data(), slot_param.size(), s));
   } else {
     ctx->chain_off.release();
     ctx->chain_param.release();
+    ctx->slot_off.release();
+    ctx->slot_param.release();
   }
-  ctx->have_prior = m->arc_prior != nullptr;
-  if (ctx->have_prior) CML_CUDA(ctx->arc_prior.upload(m->arc_prior, m->n_arcs, s));
+  CML_CUDA(ctx->arc_slot.upload(arc_slot.data(), arc_slot.size(), s));
+  ctx->have_prior = !slot_prior.empty();
+  if (ctx->have_prior) CML_CUDA(ctx->slot_prior.upload(slot_prior.data(), slot_prior.size(), s));
   ctx->have_add = m->group_add != nullptr && m->n_groups > 0;
   if (ctx->have_add) CML_CUDA(ctx->group_add.upload(m->group_add, m->n_groups, s));
   CML_CUDA(ctx->param_group.upload(pg.data(), m->n_params, s));
@@ -240,16 +338,17 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   CML_CUDA(ctx->u.alloc(m->n_params));
   CML_CUDA(ctx->old.alloc(m->n_params));
   CML_CUDA(ctx->arc_lnw.alloc(m->n_arcs));
-  CML_CUDA(ctx->arc_w_real.alloc((size_t)m->n_arcs * (ctx->precision / 8)));
+  CML_CUDA(ctx->arc_w_real.alloc(((size_t)m->n_arcs + 1) * (ctx->precision / 8)));
+  CML_CUDA(ctx->arc_ws.alloc(((size_t)m->n_arcs + 1) * (ctx->precision == 64 ? 16 : 8)));
   CML_CUDA(ctx->gsum.alloc(std::max<uint32_t>(1, m->n_groups)));
   CML_CUDA(ctx->glocked.alloc(std::max<uint32_t>(1, m->n_groups)));
   CML_CUDA(ctx->tie_arc.alloc(std::max<uint32_t>(1, m->n_ties)));
   CML_CUDA(ctx->tie_state.alloc(std::max<uint32_t>(1, m->n_ties)));
   CML_CUDA(ctx->tie_maxl.alloc(std::max<uint32_t>(1, m->n_ties)));
   CML_CUDA(ctx->maxchg.alloc(1));
-  CML_CUDA(ctx->reduce_own.alloc((size_t)m->n_arcs + 3));
+  CML_CUDA(ctx->reduce_own.alloc((size_t)n_slots + 3));
   ctx->reduce = ctx->reduce_own.p;
-  ctx->reduce_n = (uint64_t)m->n_arcs + 3;
+  ctx->reduce_n = (uint64_t)n_slots + 3;
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
   CML_CUDA(cudaStreamSynchronize(s));  // the host staging vectors go out of scope
   ctx->have_model = true;
@@ -295,20 +394,37 @@ extern "C" int cml_restore_params(cml_ctx* ctx, int slot) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// trellis flattening: reference-order adjacency lists -> topologically layered CSR
+// trellis flattening: reference-order adjacency lists -> layered CSR / level-sliced ELL
 // -------------------------------------------------------------------------------------------------
 namespace {
 
-struct FlatEx {  // per-example sizes discovered in pass 1
+struct FlatEx {  // per-example facts discovered in pass 1
   uint32_t n_levels = 0;
   bool cycle = false;
+  bool ell = false;        // eligible for the ELL kernel
+  uint32_t g_class = 0;    // index into kEllG
+  uint32_t ring_need = 0;  // max index distance of an arc + max level width + 1
+  uint64_t in_pad = 0, out_pad = 0;  // ELL record counts (with padding)
+  uint32_t width = 0;
 };
 
-// pass 1: longest-path levels via Kahn's algorithm; fills level_of[] / local_of[] for the example
-void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* level_of, uint32_t* local_of,
-              FlatEx& fx, std::vector<uint32_t>& indeg, std::vector<uint32_t>& queue, std::vector<uint32_t>& cnt) {
+inline uint32_t pow2ceil(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct Scratch {  // per-thread temporaries
+  std::vector<uint32_t> indeg, queue, cnt, lvl_first, lvl_width, lvl_d, lvl_o, lvl_min, lvl_max, ref_of, icur, ocur, order;
+};
+
+// pass 1: longest-path levels via Kahn's algorithm; level_of[] / local_of[]; ELL eligibility
+void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* level_of, uint32_t* local_of, FlatEx& fx,
+              Scratch& S, bool want_ell) {
+  auto &indeg = S.indeg, &queue = S.queue, &cnt = S.cnt;
   indeg.assign(n, 0);
   for (uint32_t k = 0, e = off[n]; k < e; ++k) ++indeg[dst[k]];
+  S.icur.assign(indeg.begin(), indeg.end());  // keep the in-degrees (indeg is consumed below)
   queue.clear();
   for (uint32_t s = 0; s < n; ++s) {
     level_of[s] = 0;
@@ -331,11 +447,52 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
     fx.cycle = true;
     return;
   }
-  fx.n_levels = maxl + 1;
-  cnt.assign(fx.n_levels + 1, 0);
+  const uint32_t nl = fx.n_levels = maxl + 1;
+  cnt.assign(nl + 1, 0);
   for (uint32_t s = 0; s < n; ++s) ++cnt[level_of[s] + 1];
-  for (uint32_t l = 0; l < fx.n_levels; ++l) cnt[l + 1] += cnt[l];
+  uint32_t width = 0;
+  for (uint32_t l = 0; l < nl; ++l) {
+    width = std::max(width, cnt[l + 1]);
+    cnt[l + 1] += cnt[l];
+  }
+  fx.width = width;
+  S.lvl_first.assign(cnt.begin(), cnt.end());
   for (uint32_t s = 0; s < n; ++s) local_of[s] = cnt[level_of[s]]++;  // stable: (level, reference id)
+  if (!want_ell) return;
+  // ELL eligibility: bounded width / degrees / level spans / ring, modest padding
+  auto &ld = S.lvl_d, &lo = S.lvl_o, &lmin = S.lvl_min, &lmax = S.lvl_max;
+  ld.assign(nl, 0);
+  lo.assign(nl, 0);
+  lmin.assign(nl, 0);
+  lmax.assign(nl, 0);
+  uint32_t maxdist = 0, maxspan = 0;
+  for (uint32_t s = 0; s < n; ++s) {
+    const uint32_t l = level_of[s];
+    ld[l] = std::max(ld[l], S.icur[s]);
+    lo[l] = std::max(lo[l], off[s + 1] - off[s]);
+    for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
+      const uint32_t d = dst[k];
+      maxdist = std::max(maxdist, local_of[d] - local_of[s]);
+      maxspan = std::max(maxspan, level_of[d] - l);
+    }
+  }
+  uint64_t in_pad = 0, out_pad = 0;
+  uint32_t maxdeg = 0;
+  for (uint32_t l = 0; l < nl; ++l) {
+    const uint32_t w = S.lvl_first[l + 1] - S.lvl_first[l];
+    in_pad += (uint64_t)w * ld[l];
+    out_pad += (uint64_t)w * lo[l];
+    maxdeg = std::max(maxdeg, std::max(ld[l], lo[l]));
+  }
+  const uint64_t arcs = off[n];
+  fx.in_pad = in_pad;
+  fx.out_pad = out_pad;
+  fx.ring_need = maxdist + width + 1;
+  uint32_t gc = 0;
+  while (gc + 1 < NELL && (uint32_t)kEllG[gc] < width) ++gc;
+  fx.g_class = gc;
+  fx.ell = width <= (uint32_t)kEllG[gc] * cmlk::kEllMaxRows && width <= 255 && maxdeg <= 255 && maxspan <= 15 &&
+           fx.ring_need <= 4096 && in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
 }
 
 }  // namespace
@@ -350,6 +507,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   const uint64_t n_ex = b->n_ex;
   const int rs = ctx->precision / 8;
   const bool scaled = ctx->space == CML_SPACE_SCALED;
+  const bool want_ell = scaled && !ctx->opt_no_ell;
 
   // prefix sums over the caller's arrays
   std::vector<uint64_t> state_base(n_ex + 1), arc_base(n_ex + 1);
@@ -373,152 +531,253 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   bt->h_level_of.resize(tot_states);
   bt->h_local_of.resize(tot_states);
   bt->h_nlevels.resize(n_ex);
+  std::vector<FlatEx> fx(n_ex);
 
-  // pass 1 (parallel over examples): levels
+  // ---- pass 1 (parallel over examples): levels + ELL eligibility
   const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::atomic<int> bad_cycle{0}, bad_range{0};
-  {
+  auto parallel_for = [&](auto&& body) {
     std::atomic<uint64_t> next{0};
     auto work = [&]() {
-      std::vector<uint32_t> indeg, queue, cnt;
+      Scratch S;
       for (;;) {
         const uint64_t e0 = next.fetch_add(256);
         if (e0 >= n_ex) break;
-        for (uint64_t e = e0; e < std::min(n_ex, e0 + 256); ++e) {
-          const uint32_t n = b->ex_states[e];
-          const uint32_t* off = b->arc_off + state_base[e] + e;
-          const uint32_t* dst = b->arc_dst + arc_base[e];
-          const uint32_t* id = b->arc_id + arc_base[e];
-          bool ok = true;
-          for (uint32_t s = 0; s < n && ok; ++s) ok = off[s] <= off[s + 1];
-          for (uint32_t k = 0; k < off[n] && ok; ++k) ok = dst[k] < n && id[k] < ctx->n_arcs;
-          if (!ok) {
-            bad_range = 1;
-            continue;
-          }
-          FlatEx fx;
-          levelize(n, off, dst, &bt->h_level_of[state_base[e]], &bt->h_local_of[state_base[e]], fx, indeg, queue, cnt);
-          if (fx.cycle) bad_cycle = 1;
-          bt->h_nlevels[e] = fx.n_levels;
-        }
+        for (uint64_t e = e0; e < std::min(n_ex, e0 + 256); ++e) body(e, S);
       }
     };
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
-  }
+  };
+  parallel_for([&](uint64_t e, Scratch& S) {
+    const uint32_t n = b->ex_states[e];
+    const uint32_t* off = b->arc_off + state_base[e] + e;
+    const uint32_t* dst = b->arc_dst + arc_base[e];
+    const uint32_t* id = b->arc_id + arc_base[e];
+    bool ok = true;
+    for (uint32_t s = 0; s < n && ok; ++s) ok = off[s] <= off[s + 1];
+    for (uint32_t k = 0; k < off[n] && ok; ++k) ok = dst[k] < n && id[k] < ctx->n_arcs;
+    if (!ok) {
+      bad_range = 1;
+      return;
+    }
+    levelize(n, off, dst, &bt->h_level_of[state_base[e]], &bt->h_local_of[state_base[e]], fx[e], S, want_ell);
+    if (fx[e].cycle) bad_cycle = 1;
+    bt->h_nlevels[e] = fx[e].n_levels;
+  });
   CML_REQUIRE(!bad_range, CML_ERR_ARG, "trellis arc destination or arc id out of range");
   CML_REQUIRE(!bad_cycle, CML_ERR_CYCLE,
               "derivation lattice has a cycle (the reference warns 'Forward/backward will miss some paths')");
 
-  // layout offsets
-  std::vector<uint64_t> lvl_base(n_ex + 1);
-  lvl_base[0] = 0;
-  for (uint64_t e = 0; e < n_ex; ++e) lvl_base[e + 1] = lvl_base[e] + 3ull * bt->h_nlevels[e] + 1;
+  // ---- layout offsets (serial prefix sums), separately for the CSR and the ELL examples
+  std::vector<uint64_t> c_lvl(n_ex), c_row(n_ex), c_arc(n_ex), e_in(n_ex), e_out(n_ex), e_meta(n_ex), e_state(n_ex);
+  std::vector<uint32_t> slot_of(n_ex);  // index of the example inside its part's descriptor array
+  uint64_t n_c = 0, n_e = 0, cl = 0, cr = 0, ca = 0, ei = 0, eo = 0, em = 0, es = 0;
   bt->n_levels = 0;
-  for (uint64_t e = 0; e < n_ex; ++e) bt->n_levels += bt->h_nlevels[e];
+  for (uint64_t e = 0; e < n_ex; ++e) {
+    const uint32_t n = b->ex_states[e], nl = fx[e].n_levels;
+    bt->n_levels += nl;
+    if (fx[e].ell) {
+      slot_of[e] = (uint32_t)n_e++;
+      e_in[e] = ei;
+      e_out[e] = eo;
+      e_meta[e] = em;
+      e_state[e] = es;
+      ei += fx[e].in_pad;
+      eo += fx[e].out_pad;
+      em += nl;
+      es += n;
+    } else {
+      slot_of[e] = (uint32_t)n_c++;
+      c_lvl[e] = cl;
+      c_row[e] = cr;
+      c_arc[e] = ca;
+      cl += 3ull * nl + 1;
+      cr += n + 1;
+      ca += arc_base[e + 1] - arc_base[e];
+    }
+  }
+  bt->csr_ex = n_c;
+  bt->ell_ex = n_e;
+  bt->ell_pad_records = ei + eo;
 
-  std::vector<CmlExDesc> desc(n_ex);
-  std::vector<uint32_t> h_lvl(lvl_base[n_ex]), h_in_off(tot_states + n_ex), h_out_off(tot_states + n_ex);
-  std::vector<uint2> h_in(tot_arcs), h_out(tot_arcs);
+  std::vector<CmlExDesc> desc(n_c);
+  std::vector<uint32_t> h_lvl(cl), h_in_off(cr), h_out_off(cr);
+  std::vector<uint2> h_in(ca), h_out(ca);
+  std::vector<cmlk::EllDesc> edesc(n_e);
+  std::vector<uint4> h_meta(em);
+  std::vector<uint2> h_ein(ei), h_eout(eo);
+  std::vector<double> h_weight(n_ex);
+  const uint32_t pad_id = ctx->n_arcs;  // zero-weight padding arc
+  const std::vector<uint32_t>& arc_slot = ctx->h_arc_slot;
 
-  // classes
+  // ---- pass 2 (parallel): fill
+  parallel_for([&](uint64_t e, Scratch& S) {
+    const uint32_t n = b->ex_states[e], nl = fx[e].n_levels;
+    const uint32_t* off = b->arc_off + state_base[e] + e;
+    const uint32_t* dst = b->arc_dst + arc_base[e];
+    const uint32_t* id = b->arc_id + arc_base[e];
+    const uint32_t* level_of = &bt->h_level_of[state_base[e]];
+    const uint32_t* local_of = &bt->h_local_of[state_base[e]];
+    const double weight = b->ex_weight ? b->ex_weight[e] : 1.0;
+    h_weight[e] = weight;
+    auto &lfirst = S.lvl_first, &ref_of = S.ref_of;
+    lfirst.assign(nl + 1, 0);
+    for (uint32_t s = 0; s < n; ++s) ++lfirst[level_of[s] + 1];
+    for (uint32_t l = 0; l < nl; ++l) lfirst[l + 1] += lfirst[l];
+    ref_of.resize(n);
+    for (uint32_t s = 0; s < n; ++s) ref_of[local_of[s]] = s;
+    auto &lmin = S.lvl_min, &lmax = S.lvl_max;
+    lmin.resize(nl);
+    lmax.resize(nl);
+    for (uint32_t l = 0; l < nl; ++l) {
+      lmin[l] = l ? l - 1 : 0;
+      lmax[l] = std::min(nl - 1, l + 1);
+    }
+    for (uint32_t s = 0; s < n; ++s)
+      for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
+        const uint32_t ls = level_of[s], ld = level_of[dst[k]];
+        if (ls < lmin[ld]) lmin[ld] = ls;
+        if (ld > lmax[ls]) lmax[ls] = ld;
+      }
+    if (!fx[e].ell) {
+      // ------------------------------------------------ layered CSR
+      uint32_t* lv = &h_lvl[c_lvl[e]];
+      for (uint32_t l = 0; l <= nl; ++l) lv[l] = lfirst[l];
+      for (uint32_t l = 0; l < nl; ++l) {
+        lv[nl + 1 + l] = lmin[l];
+        lv[2 * nl + 1 + l] = lmax[l];
+      }
+      uint32_t* ioff = &h_in_off[c_row[e]];
+      uint32_t* ooff = &h_out_off[c_row[e]];
+      uint2* ia = &h_in[c_arc[e]];
+      uint2* oa = &h_out[c_arc[e]];
+      for (uint32_t s = 0; s <= n; ++s) ioff[s] = ooff[s] = 0;
+      for (uint32_t s = 0; s < n; ++s) {
+        ooff[local_of[s] + 1] = off[s + 1] - off[s];
+        for (uint32_t k = off[s]; k < off[s + 1]; ++k) ++ioff[local_of[dst[k]] + 1];
+      }
+      for (uint32_t s = 0; s < n; ++s) {
+        ioff[s + 1] += ioff[s];
+        ooff[s + 1] += ooff[s];
+      }
+      S.icur.assign(ioff, ioff + n);
+      for (uint32_t j = 0; j < n; ++j) {  // sources in layered order => in-lists sorted by source (stable)
+        const uint32_t s = ref_of[j];
+        uint32_t o = ooff[j];
+        for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
+          const uint32_t dj = local_of[dst[k]];
+          oa[o++] = make_uint2(dj, id[k]);
+          ia[S.icur[dj]++] = make_uint2(j, id[k]);
+        }
+      }
+      CmlExDesc& d = desc[slot_of[e]];
+      d.arc_base = c_arc[e];
+      d.row_base = c_row[e];
+      d.lvl_base = c_lvl[e];
+      d.scratch_base = 0;
+      d.n_states = n;
+      d.n_levels = nl;
+      d.fin = local_of[b->ex_fin[e]];
+      d.ex_index = (uint32_t)e;
+      d.weight = weight;
+      d.ln_weight = weight > 0 ? std::log(weight) : -INFINITY;
+      return;
+    }
+    // -------------------------------------------------- level-sliced ELL
+    auto &ld = S.lvl_d, &lo = S.lvl_o;
+    ld.assign(nl, 0);
+    lo.assign(nl, 0);
+    S.indeg.assign(n, 0);  // in-degree by layered index
+    for (uint32_t s = 0; s < n; ++s) {
+      lo[level_of[s]] = std::max(lo[level_of[s]], off[s + 1] - off[s]);
+      for (uint32_t k = off[s]; k < off[s + 1]; ++k) ++S.indeg[local_of[dst[k]]];
+    }
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint32_t l = level_of[ref_of[j]];
+      ld[l] = std::max(ld[l], S.indeg[j]);
+    }
+    uint4* meta = &h_meta[e_meta[e]];
+    uint2* ein = &h_ein[e_in[e]];
+    uint2* eout = &h_eout[e_out[e]];
+    uint32_t in_off = 0, out_off = 0;
+    for (uint32_t l = 0; l < nl; ++l) {
+      const uint32_t w = lfirst[l + 1] - lfirst[l];
+      meta[l].x = in_off;
+      meta[l].y = out_off;
+      meta[l].z = lfirst[l];
+      meta[l].w = w | (ld[l] << 8) | (lo[l] << 16) | ((l - lmin[l]) << 24) | ((lmax[l] - l) << 28);
+      // padding: zero-weight arc from/to a state that is certainly inside the ring window
+      const uint2 pin = make_uint2(l ? lfirst[l - 1] : 0, pad_id);
+      const uint2 pout = make_uint2(l + 1 < nl ? lfirst[l + 1] : lfirst[l], pad_id);
+      for (uint64_t k = 0; k < (uint64_t)w * ld[l]; ++k) ein[in_off + k] = pin;
+      for (uint64_t k = 0; k < (uint64_t)w * lo[l]; ++k) eout[out_off + k] = pout;
+      in_off += w * ld[l];
+      out_off += w * lo[l];
+    }
+    // outgoing blocks: row = source, columns sorted by destination index
+    S.icur.assign(n, 0);  // next free in-column per destination (layered index)
+    auto& order = S.order;
+    for (uint32_t j = 0; j < n; ++j) {  // sources in layered order => in-columns sorted by source
+      const uint32_t s = ref_of[j], l = level_of[s];
+      const uint32_t w = lfirst[l + 1] - lfirst[l], r = j - lfirst[l];
+      const uint32_t deg = off[s + 1] - off[s];
+      order.resize(deg);
+      for (uint32_t k = 0; k < deg; ++k) order[k] = off[s] + k;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return local_of[dst[x]] < local_of[dst[y]]; });
+      for (uint32_t c = 0; c < deg; ++c) {
+        const uint32_t k = order[c];
+        const uint32_t dj = local_of[dst[k]], dl = level_of[dst[k]];
+        eout[meta[l].y + (uint64_t)c * w + r] = make_uint2(dj, id[k]);
+        const uint32_t dw = lfirst[dl + 1] - lfirst[dl], dr = dj - lfirst[dl];
+        ein[meta[dl].x + (uint64_t)(S.icur[dj]++) * dw + dr] = make_uint2(j, id[k]);
+      }
+    }
+    // aggregate flag: no padding in the level's outgoing block and every column feeds one slot
+    for (uint32_t l = 0; l < nl; ++l) {
+      const uint32_t w = lfirst[l + 1] - lfirst[l], O = lo[l];
+      bool agg = O > 0 && w > 1;
+      for (uint32_t c = 0; c < O && agg; ++c) {
+        const uint2* col = eout + meta[l].y + (uint64_t)c * w;
+        if (col[0].y == pad_id) agg = false;
+        const uint32_t s0 = col[0].y == pad_id ? kPadNone : arc_slot[col[0].y];
+        for (uint32_t r = 1; r < w && agg; ++r) agg = col[r].y != pad_id && arc_slot[col[r].y] == s0;
+      }
+      if (agg) meta[l].z |= 0x80000000u;
+    }
+    cmlk::EllDesc& d = edesc[slot_of[e]];
+    d.in_base = e_in[e];
+    d.out_base = e_out[e];
+    d.meta_base = e_meta[e];
+    d.state_base = e_state[e];
+    d.level_base = e_meta[e];
+    d.n_states = n;
+    d.n_levels = nl;
+    d.fin = local_of[b->ex_fin[e]];
+    d.ex_index = (uint32_t)e;
+    d.weight = weight;
+    d.fin_level = level_of[b->ex_fin[e]];
+    d.pad = 0;
+  });
+
+  // ---- classes (serial; cheap)
   const size_t per_state = 2 * (size_t)rs + (scaled ? 8 : 0);
   const size_t smem_budget = std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : 48 * 1024, 220 * 1024);
   const uint32_t cta_max_states = (uint32_t)((smem_budget - 64) / per_state);
-  std::vector<std::vector<uint32_t>> cls(NCLS);
+  std::vector<std::vector<uint32_t>> cls(NCLS), ecls(NELL);
   uint64_t scratch_states = 0;
-  std::vector<uint32_t> ex_width(n_ex);
-
-  // pass 2 (parallel): fill CSR arrays
-  {
-    std::atomic<uint64_t> next{0};
-    auto work = [&]() {
-      std::vector<uint32_t> ref_of, icur;
-      for (;;) {
-        const uint64_t e0 = next.fetch_add(256);
-        if (e0 >= n_ex) break;
-        for (uint64_t e = e0; e < std::min(n_ex, e0 + 256); ++e) {
-          const uint32_t n = b->ex_states[e], nl = bt->h_nlevels[e];
-          const uint32_t* off = b->arc_off + state_base[e] + e;
-          const uint32_t* dst = b->arc_dst + arc_base[e];
-          const uint32_t* id = b->arc_id + arc_base[e];
-          const uint32_t* level_of = &bt->h_level_of[state_base[e]];
-          const uint32_t* local_of = &bt->h_local_of[state_base[e]];
-          uint32_t* lv = &h_lvl[lvl_base[e]];
-          uint32_t* lmin = lv + nl + 1;
-          uint32_t* lmax = lmin + nl;
-          uint32_t* ioff = &h_in_off[state_base[e] + e];
-          uint32_t* ooff = &h_out_off[state_base[e] + e];
-          uint2* ia = &h_in[arc_base[e]];
-          uint2* oa = &h_out[arc_base[e]];
-          // level offsets
-          for (uint32_t l = 0; l <= nl; ++l) lv[l] = 0;
-          for (uint32_t s = 0; s < n; ++s) ++lv[level_of[s] + 1];
-          uint32_t width = 0;
-          for (uint32_t l = 0; l < nl; ++l) {
-            width = std::max(width, lv[l + 1]);
-            lv[l + 1] += lv[l];
-          }
-          ex_width[e] = width;
-          for (uint32_t l = 0; l < nl; ++l) {
-            lmin[l] = l ? l - 1 : 0;
-            lmax[l] = std::min(nl - 1, l + 1);
-          }
-          // row sizes
-          for (uint32_t s = 0; s <= n; ++s) ioff[s] = ooff[s] = 0;
-          for (uint32_t s = 0; s < n; ++s) {
-            ooff[local_of[s] + 1] = off[s + 1] - off[s];
-            for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
-              ++ioff[local_of[dst[k]] + 1];
-              const uint32_t ls = level_of[s], ld = level_of[dst[k]];
-              if (ls < lmin[ld]) lmin[ld] = ls;
-              if (ld > lmax[ls]) lmax[ls] = ld;
-            }
-          }
-          for (uint32_t s = 0; s < n; ++s) {
-            ioff[s + 1] += ioff[s];
-            ooff[s + 1] += ooff[s];
-          }
-          // fill: outgoing in reference list order; incoming ordered by source layered index
-          // visit sources in layered order so each in-list is sorted by source index (stable)
-          ref_of.resize(n);
-          for (uint32_t s = 0; s < n; ++s) ref_of[local_of[s]] = s;
-          icur.assign(ioff, ioff + n);
-          for (uint32_t j = 0; j < n; ++j) {
-            const uint32_t s = ref_of[j];
-            uint32_t o = ooff[j];
-            for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
-              const uint32_t dj = local_of[dst[k]];
-              oa[o++] = make_uint2(dj, id[k]);
-              ia[icur[dj]++] = make_uint2(j, id[k]);
-            }
-          }
-          CmlExDesc& d = desc[e];
-          d.arc_base = arc_base[e];
-          d.row_base = state_base[e] + e;
-          d.lvl_base = lvl_base[e];
-          d.scratch_base = 0;
-          d.n_states = n;
-          d.n_levels = nl;
-          d.fin = local_of[b->ex_fin[e]];
-          d.ex_index = (uint32_t)e;
-          d.weight = b->ex_weight ? b->ex_weight[e] : 1.0;
-          d.ln_weight = d.weight > 0 ? std::log(d.weight) : -INFINITY;
-        }
-      }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nthr; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
-  }
-  // classify (serial; cheap)
   for (uint64_t e = 0; e < n_ex; ++e) {
-    const uint32_t n = desc[e].n_states;
+    if (fx[e].ell) {
+      ecls[fx[e].g_class].push_back(slot_of[e]);
+      bt->ell_ring[fx[e].g_class] = std::max(bt->ell_ring[fx[e].g_class], pow2ceil(fx[e].ring_need));
+      bt->ell_arcs += arc_base[e + 1] - arc_base[e];
+      continue;
+    }
+    const uint32_t n = b->ex_states[e];
     int c = -1;
-    if (ex_width[e] <= 96) {
+    if (fx[e].width <= 96) {
       for (int i = 0; i < NWARPCLS; ++i)
         if (n <= kWarpCaps[i]) {
           c = CLS_WARP0 + i;
@@ -531,36 +790,51 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         bt->cta_cap = std::max(bt->cta_cap, n);
       } else {
         c = CLS_GLOBAL;
-        desc[e].scratch_base = scratch_states;
+        desc[slot_of[e]].scratch_base = scratch_states;
         scratch_states += n;
       }
     }
-    cls[c].push_back((uint32_t)e);
+    cls[c].push_back(slot_of[e]);
   }
-  std::vector<uint32_t> ex_list;
-  ex_list.reserve(n_ex);
+  std::vector<uint32_t> ex_list, ell_list;
   for (int c = 0; c < NCLS; ++c) {
     bt->cls_begin[c] = (uint32_t)ex_list.size();
-    // longest examples first inside a class: better tail behaviour
-    std::stable_sort(cls[c].begin(), cls[c].end(), [&](uint32_t a, uint32_t b2) {
-      return desc[a].n_levels > desc[b2].n_levels;
-    });
+    std::stable_sort(cls[c].begin(), cls[c].end(), [&](uint32_t x, uint32_t y) { return desc[x].n_levels > desc[y].n_levels; });
     ex_list.insert(ex_list.end(), cls[c].begin(), cls[c].end());
   }
   bt->cls_begin[NCLS] = (uint32_t)ex_list.size();
+  for (int c = 0; c < NELL; ++c) {
+    bt->ell_begin[c] = (uint32_t)ell_list.size();
+    // longest first; neighbours in a warp then have similar level counts (less sub-warp divergence)
+    std::stable_sort(ecls[c].begin(), ecls[c].end(), [&](uint32_t x, uint32_t y) { return edesc[x].n_levels > edesc[y].n_levels; });
+    ell_list.insert(ell_list.end(), ecls[c].begin(), ecls[c].end());
+  }
+  bt->ell_begin[NELL] = (uint32_t)ell_list.size();
 
   cudaStream_t s = ctx->stream;
-  CML_CUDA(bt->desc.upload(desc.data(), n_ex, s));
-  CML_CUDA(bt->lvl_off.upload(h_lvl.data(), h_lvl.size(), s));
-  CML_CUDA(bt->in_off.upload(h_in_off.data(), h_in_off.size(), s));
-  CML_CUDA(bt->out_off.upload(h_out_off.data(), h_out_off.size(), s));
-  CML_CUDA(bt->in_arc.upload(h_in.data(), h_in.size(), s));
-  CML_CUDA(bt->out_arc.upload(h_out.data(), h_out.size(), s));
-  CML_CUDA(bt->ex_list.upload(ex_list.data(), ex_list.size(), s));
   CML_CUDA(bt->ex_lnp.alloc(n_ex));
-  if (scratch_states) {
-    CML_CUDA(bt->scratch.alloc(scratch_states * 2 * rs));
-    if (scaled) CML_CUDA(bt->scratch_lvl.alloc(scratch_states * 2));
+  CML_CUDA(bt->ex_weight.upload(h_weight.data(), n_ex, s));
+  if (n_c) {
+    CML_CUDA(bt->desc.upload(desc.data(), n_c, s));
+    CML_CUDA(bt->lvl_off.upload(h_lvl.data(), h_lvl.size(), s));
+    CML_CUDA(bt->in_off.upload(h_in_off.data(), h_in_off.size(), s));
+    CML_CUDA(bt->out_off.upload(h_out_off.data(), h_out_off.size(), s));
+    CML_CUDA(bt->in_arc.upload(h_in.data(), h_in.size(), s));
+    CML_CUDA(bt->out_arc.upload(h_out.data(), h_out.size(), s));
+    CML_CUDA(bt->ex_list.upload(ex_list.data(), ex_list.size(), s));
+    if (scratch_states) {
+      CML_CUDA(bt->scratch.alloc(scratch_states * 2 * rs));
+      if (scaled) CML_CUDA(bt->scratch_lvl.alloc(scratch_states * 2));
+    }
+  }
+  if (n_e) {
+    CML_CUDA(bt->edesc.upload(edesc.data(), n_e, s));
+    CML_CUDA(bt->lvl_meta.upload(h_meta.data(), h_meta.size(), s));
+    CML_CUDA(bt->ell_in.upload(h_ein.data(), h_ein.size(), s));
+    CML_CUDA(bt->ell_out.upload(h_eout.data(), h_eout.size(), s));
+    CML_CUDA(bt->ell_list.upload(ell_list.data(), ell_list.size(), s));
+    CML_CUDA(bt->alpha_g.alloc(es * rs));
+    CML_CUDA(bt->lvl_exp.alloc(em * 2));
   }
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->batches.push_back(std::move(bt));
@@ -592,6 +866,23 @@ extern "C" int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_stat
   return CML_OK;
 }
 
+extern "C" int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,
+                                uint64_t* csr_examples) {
+  if (!ctx) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0, d = 0;
+  for (auto& bt : ctx->batches) {
+    a += bt->ell_ex;
+    b += bt->ell_arcs;
+    c += bt->ell_pad_records;
+    d += bt->csr_ex;
+  }
+  if (ell_examples) *ell_examples = a;
+  if (ell_arcs) *ell_arcs = b;
+  if (ell_records) *ell_records = c;
+  if (csr_examples) *csr_examples = d;
+  return CML_OK;
+}
+
 extern "C" int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_t* level_of,
                                       uint32_t* local_of) {
   if (!ctx) return CML_ERR_ARG;
@@ -612,66 +903,108 @@ extern "C" int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_leve
 // -------------------------------------------------------------------------------------------------
 // E-step
 // -------------------------------------------------------------------------------------------------
+template <typename Real, int G>
+static int launch_ell_class(cml_ctx* ctx, Batch& bt, cmlk::EllArgs& A, int c) {
+  const uint32_t n = bt.ell_begin[c + 1] - bt.ell_begin[c];
+  if (!n) return CML_OK;
+  A.ex_list = bt.ell_list.p + bt.ell_begin[c];
+  A.n_list = n;
+  A.ring = bt.ell_ring[c];
+  constexpr int GPB = 256 / G;
+  const size_t smem = (size_t)GPB * A.ring * sizeof(Real);
+  auto kern = cmlk::k_fb_ell<Real, G>;
+  if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<cdiv(n, GPB), 256, smem, ctx->stream>>>(A);
+  ++ctx->launches;
+  ++bt.n_fb_kernels;
+  return CML_OK;
+}
+
 template <typename Real, bool SCALED>
 static int launch_fb(cml_ctx* ctx, Batch& bt) {
   using namespace cmlk;
-  FbArgs A;
-  A.desc = bt.desc.p;
-  A.lvl_off = bt.lvl_off.p;
-  A.in_off = bt.in_off.p;
-  A.in_arc = bt.in_arc.p;
-  A.out_off = bt.out_off.p;
-  A.out_arc = bt.out_arc.p;
-  A.arc_w = ctx->arc_w_real.p;
-  A.counts = ctx->reduce;
-  A.ex_lnp = bt.ex_lnp.p;
-  A.scratch = bt.scratch.p;
-  A.scratch_lvl = bt.scratch_lvl.p;
-  const size_t per_state = 2 * sizeof(Real) + (SCALED ? 2 * sizeof(int) : 0);
   if (!bt.ev_fb0) {
     CML_CUDA(cudaEventCreate(&bt.ev_fb0));
     CML_CUDA(cudaEventCreate(&bt.ev_fb1));
   }
+  bt.n_fb_kernels = 0;
   CML_CUDA(cudaEventRecord(bt.ev_fb0, ctx->stream));
-  for (int c = 0; c < NWARPCLS; ++c) {
-    const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];
-    if (!n) continue;
-    A.ex_list = bt.ex_list.p + bt.cls_begin[c];
-    A.n_list = n;
-    A.cap_states = kWarpCaps[c];
-    const size_t smem = 4 * per_state * kWarpCaps[c];
-    auto kern = k_fb_warp<Real, SCALED>;
-    if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(n, 4), 128, smem, ctx->stream>>>(A);
-    ++ctx->launches;
+  if (SCALED && bt.ell_ex) {
+    EllArgs E;
+    E.desc = bt.edesc.p;
+    E.lvl_meta = bt.lvl_meta.p;
+    E.ell_in = bt.ell_in.p;
+    E.ell_out = bt.ell_out.p;
+    E.arc_w = ctx->arc_w_real.p;
+    E.arc_ws = ctx->arc_ws.p;
+    E.counts = ctx->reduce;
+    E.ex_lnp = bt.ex_lnp.p;
+    E.alpha_g = bt.alpha_g.p;
+    E.lvl_exp = bt.lvl_exp.p;
+    int r;
+    if ((r = launch_ell_class<Real, 4>(ctx, bt, E, 0))) return r;
+    if ((r = launch_ell_class<Real, 8>(ctx, bt, E, 1))) return r;
+    if ((r = launch_ell_class<Real, 16>(ctx, bt, E, 2))) return r;
+    if ((r = launch_ell_class<Real, 32>(ctx, bt, E, 3))) return r;
   }
-  {
-    const uint32_t n = bt.cls_begin[CLS_CTA + 1] - bt.cls_begin[CLS_CTA];
-    if (n) {
-      A.ex_list = bt.ex_list.p + bt.cls_begin[CLS_CTA];
+  if (bt.csr_ex) {
+    FbArgs A;
+    A.desc = bt.desc.p;
+    A.lvl_off = bt.lvl_off.p;
+    A.in_off = bt.in_off.p;
+    A.in_arc = bt.in_arc.p;
+    A.out_off = bt.out_off.p;
+    A.out_arc = bt.out_arc.p;
+    A.arc_w = ctx->arc_w_real.p;
+    A.arc_slot = ctx->arc_slot.p;
+    A.counts = ctx->reduce;
+    A.ex_lnp = bt.ex_lnp.p;
+    A.scratch = bt.scratch.p;
+    A.scratch_lvl = bt.scratch_lvl.p;
+    const size_t per_state = 2 * sizeof(Real) + (SCALED ? 2 * sizeof(int) : 0);
+    for (int c = 0; c < NWARPCLS; ++c) {
+      const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];
+      if (!n) continue;
+      A.ex_list = bt.ex_list.p + bt.cls_begin[c];
       A.n_list = n;
-      A.cap_states = bt.cta_cap;
-      const size_t smem = per_state * bt.cta_cap;
-      auto kern = k_fb_cta<Real, SCALED, false>;
-      if (smem > 48 * 1024)
-        CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<n, 256, smem, ctx->stream>>>(A);
+      A.cap_states = kWarpCaps[c];
+      const size_t smem = 4 * per_state * kWarpCaps[c];
+      auto kern = k_fb_warp<Real, SCALED>;
+      if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<cdiv(n, 4), 128, smem, ctx->stream>>>(A);
       ++ctx->launches;
+      ++bt.n_fb_kernels;
     }
-  }
-  {
-    const uint32_t n = bt.cls_begin[CLS_GLOBAL + 1] - bt.cls_begin[CLS_GLOBAL];
-    if (n) {
-      A.ex_list = bt.ex_list.p + bt.cls_begin[CLS_GLOBAL];
-      A.n_list = n;
-      A.cap_states = 0;
-      k_fb_cta<Real, SCALED, true><<<n, 256, 0, ctx->stream>>>(A);
-      ++ctx->launches;
+    {
+      const uint32_t n = bt.cls_begin[CLS_CTA + 1] - bt.cls_begin[CLS_CTA];
+      if (n) {
+        A.ex_list = bt.ex_list.p + bt.cls_begin[CLS_CTA];
+        A.n_list = n;
+        A.cap_states = bt.cta_cap;
+        const size_t smem = per_state * bt.cta_cap;
+        auto kern = k_fb_cta<Real, SCALED, false>;
+        if (smem > 48 * 1024)
+          CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n, 256, smem, ctx->stream>>>(A);
+        ++ctx->launches;
+        ++bt.n_fb_kernels;
+      }
+    }
+    {
+      const uint32_t n = bt.cls_begin[CLS_GLOBAL + 1] - bt.cls_begin[CLS_GLOBAL];
+      if (n) {
+        A.ex_list = bt.ex_list.p + bt.cls_begin[CLS_GLOBAL];
+        A.n_list = n;
+        A.cap_states = 0;
+        k_fb_cta<Real, SCALED, true><<<n, 256, 0, ctx->stream>>>(A);
+        ++ctx->launches;
+        ++bt.n_fb_kernels;
+      }
     }
   }
   CML_CUDA(cudaEventRecord(bt.ev_fb1, ctx->stream));
   k_reduce_lnp<<<std::min<unsigned>(cdiv(bt.n_ex, 256), 4 * ctx->sm_count), 256, 0, ctx->stream>>>(
-      bt.ex_lnp.p, bt.desc.p, bt.n_ex, ctx->reduce + ctx->n_arcs);
+      bt.ex_lnp.p, bt.ex_weight.p, bt.n_ex, ctx->reduce + ctx->n_slots);
   ++ctx->launches;
   CML_CUDA(cudaGetLastError());
   return CML_OK;
@@ -679,9 +1012,9 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
 
 template <typename Real, bool SCALED>
 static int launch_arc_weights(cml_ctx* ctx) {
-  cmlk::k_arc_weights<Real, SCALED><<<cdiv(ctx->n_arcs, 256), 256, 0, ctx->stream>>>(
-      ctx->n_arcs, ctx->trivial ? nullptr : ctx->chain_off.p, ctx->chain_param.p, ctx->ln_w.p, ctx->arc_lnw.p,
-      (Real*)ctx->arc_w_real.p);
+  cmlk::k_arc_weights<Real, SCALED, cmlk::WS<Real>><<<cdiv(ctx->n_arcs + 1, 256), 256, 0, ctx->stream>>>(
+      ctx->n_arcs, ctx->trivial ? nullptr : ctx->chain_off.p, ctx->chain_param.p, ctx->ln_w.p, ctx->arc_slot.p,
+      ctx->arc_lnw.p, (Real*)ctx->arc_w_real.p, (cmlk::WS<Real>*)ctx->arc_ws.p);
   ++ctx->launches;
   CML_CUDA(cudaGetLastError());
   return CML_OK;
@@ -716,7 +1049,7 @@ extern "C" int cml_estimate_finish(cml_ctx* ctx, cml_estimate_result* out) {
   CML_REQUIRE(ctx->estimate_pending, CML_ERR_STATE, "cml_estimate_launch first");
   cudaSetDevice(ctx->device);
   double h[3];
-  CML_CUDA(cudaMemcpyAsync(h, ctx->reduce + ctx->n_arcs, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaMemcpyAsync(h, ctx->reduce + ctx->n_slots, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->estimate_pending = false;
   if (out) {
@@ -744,7 +1077,7 @@ extern "C" int cml_last_fb_time_ms(cml_ctx* ctx, float* ms, uint32_t* n_kernels)
     float t = 0;
     CML_CUDA(cudaEventElapsedTime(&t, bt->ev_fb0, bt->ev_fb1));
     tot += t;
-    for (int c = 0; c < NCLS; ++c) nk += bt->cls_begin[c + 1] > bt->cls_begin[c];
+    nk += bt->n_fb_kernels;
   }
   *ms = tot;
   if (n_kernels) *n_kernels = nk;
@@ -769,11 +1102,25 @@ extern "C" int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n) {
 extern "C" int cml_get_arc_counts(cml_ctx* ctx, double* counts) {
   if (!ctx || !counts) return CML_ERR_ARG;
   CML_REQUIRE(ctx->have_model, CML_ERR_STATE, "cml_set_model first");
+  CML_REQUIRE(ctx->slots_are_arcs, CML_ERR_STATE,
+              "per-arc counts are not kept: counts are accumulated per unlocked-parameter slot "
+              "(set CML_OPT_ARC_COUNTS before cml_set_model, or use cml_get_counts)");
   cudaSetDevice(ctx->device);
   CML_CUDA(cudaMemcpyAsync(counts, ctx->reduce, ctx->n_arcs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   return CML_OK;
 }
+
+extern "C" int cml_get_counts(cml_ctx* ctx, double* counts, uint64_t n) {
+  if (!ctx || !counts) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model && n <= ctx->n_slots, CML_ERR_ARG, "more counts requested than count slots");
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaMemcpyAsync(counts, ctx->reduce, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CML_OK;
+}
+
+extern "C" uint64_t cml_count_slots(cml_ctx* ctx) { return ctx ? ctx->n_slots : 0; }
 
 extern "C" int cml_reduce_buffer(cml_ctx* ctx, void** p, uint64_t* n) {
   if (!ctx) return CML_ERR_ARG;
@@ -809,7 +1156,7 @@ extern "C" int cml_use_reduce_buffer(cml_ctx* ctx, void* p, uint64_t n) {
     ctx->reduce = ctx->reduce_own.p;
     return CML_OK;
   }
-  CML_REQUIRE(n >= ctx->reduce_n, CML_ERR_ARG, "reduce buffer too small (need n_arcs + 3 doubles)");
+  CML_REQUIRE(n >= ctx->reduce_n, CML_ERR_ARG, "reduce buffer too small (need count slots + 3 doubles)");
   ctx->reduce = (double*)p;
   return CML_OK;
 }
@@ -858,10 +1205,10 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   if (!ctx->trivial) CML_CUDA(cudaMemsetAsync(ctx->acc.p, 0, ctx->n_params * sizeof(double), s));
-  k_param_acc<<<cdiv(ctx->n_arcs, 256), 256, 0, s>>>(ctx->n_arcs, ctx->trivial ? nullptr : ctx->chain_off.p,
-                                                     ctx->chain_param.p, ctx->reduce,
-                                                     ctx->have_prior ? ctx->arc_prior.p : nullptr, ctx->param_tie.p,
-                                                     ctx->acc.p);
+  k_param_acc<<<cdiv(ctx->n_slots, 256), 256, 0, s>>>(ctx->n_slots, ctx->trivial ? nullptr : ctx->slot_off.p,
+                                                      ctx->slot_param.p, ctx->reduce,
+                                                      ctx->have_prior ? ctx->slot_prior.p : nullptr, ctx->param_tie.p,
+                                                      ctx->acc.p);
   k_unnorm<<<cdiv(ctx->n_params, 256), 256, 0, s>>>(ctx->n_params, ctx->acc.p, ctx->ln_w.p, ctx->param_tie.p,
                                                    ctx->param_group.p, ctx->u.p, ctx->old.p);
   ctx->launches += 2;
@@ -889,13 +1236,13 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
 extern "C" const char* const* cml_exported_symbols(size_t* n) {
   static const char* const syms[] = {
       "cml_version", "cml_create", "cml_destroy", "cml_last_error", "cml_set_stream", "cml_synchronize",
-      "cml_launch_count", "cml_set_model", "cml_set_params", "cml_get_params", "cml_snapshot_params",
-      "cml_restore_params", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals",
-      "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish",
-      "cml_get_example_logprob", "cml_get_arc_counts", "cml_reduce_buffer", "cml_use_reduce_buffer", "cml_maximize",
-      "cml_normalize_params", "cml_exported_symbols", "cml_reduce_buffer_write", "cml_reduce_buffer_read",
-      "cml_job_open", "cml_job_close", "cml_job_error", "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context",
-      "cml_job_train", "cml_job_write", "cml_job_stats", "cml_last_fb_time_ms"};
+      "cml_launch_count", "cml_set_option", "cml_set_model", "cml_set_params", "cml_get_params", "cml_snapshot_params",
+      "cml_restore_params", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
+      "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
+      "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
+      "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
+      "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",
+      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats"};
   if (n) *n = sizeof(syms) / sizeof(syms[0]);
   return syms;
 }

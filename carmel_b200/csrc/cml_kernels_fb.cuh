@@ -58,7 +58,8 @@ struct FbArgs {
   const uint32_t* out_off;
   const uint2* out_arc;       // {dst layered index, arc id}
   const void* arc_w;          // Real[n_arcs]: ln w (LOG) or w (SCALED)
-  double* counts;             // [n_arcs] linear expected counts (atomicAdd)
+  const uint32_t* arc_slot;   // [n_arcs] count slot of every arc (0xFFFFFFFF: feeds no parameter)
+  double* counts;             // [n_slots] linear expected counts (atomicAdd)
   double* ex_lnp;             // [n_ex in batch] ln P_e
   void* scratch;              // GLOBAL class: Real alpha/beta slots, 2 per state
   int* scratch_lvl;           // GLOBAL class, SCALED: E/F per level (2 per level)
@@ -158,7 +159,8 @@ __device__ void fb_example_log(const FbArgs& A, const CmlExDesc& d, Real* __rest
         const Real lc = as + v;
         if (lc > Real(-700)) {
           const double c = (double)Num<Real>::ex(lc);
-          if (c > 0) atomicAdd(&A.counts[r.y], c);
+          const uint32_t slot = __ldg(&A.arc_slot[r.y]);
+          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
         }
       }
       be[s] = (m > NI) ? m + Num<Real>::lg(acc) : NI;
@@ -273,7 +275,8 @@ __device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __r
           const Real t = __ldg(&w[r.y]) * be[r.x];
           acc += t;
           const double c = as * (double)t;
-          if (c > 0) atomicAdd(&A.counts[r.y], c);
+          const uint32_t slot = __ldg(&A.arc_slot[r.y]);
+          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
         }
       } else {
         for (; k < k1; ++k) {
@@ -282,7 +285,8 @@ __device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __r
           const Real t = Num<Real>::scale2(__ldg(&w[r.y]) * be[r.x], de);
           acc += t;
           const double c = as * (double)t;
-          if (c > 0) atomicAdd(&A.counts[r.y], c);
+          const uint32_t slot = __ldg(&A.arc_slot[r.y]);
+          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
         }
       }
       be[s] = acc;
@@ -359,14 +363,14 @@ __global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
 
 // Sum of ln P_e, w_e ln P_e and the zero-probability count over a batch (deterministic per block,
 // one atomicAdd triple per block into the reduce buffer's scalar tail).
-__global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const CmlExDesc* __restrict__ desc,
+__global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const double* __restrict__ ex_weight,
                                                     uint64_t n, double* __restrict__ scal) {
   double s0 = 0, s1 = 0, nz = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double lp = ex_lnp[desc[i].ex_index];
+    const double lp = ex_lnp[i];
     if (lp > -CUDART_INF) {
       s0 += lp;
-      s1 += desc[i].weight * lp;
+      s1 += ex_weight[i] * lp;
     } else
       nz += 1;
   }

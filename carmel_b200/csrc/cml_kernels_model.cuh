@@ -41,35 +41,59 @@ __device__ __forceinline__ double warp_max(double m) {
   return m;
 }
 
-// K6: arc weight = product of its chain's parameters.  out_real = ln w (LOG) or w (SCALED) as Real.
-template <typename Real, bool SCALED>
+// K6: arc weight = product of its chain's parameters.  out_real = ln w (LOG) or w (SCALED) as Real;
+// out_ws pairs the weight with the arc's count slot (one gather in the backward sweep).  Entry n_arcs
+// is the zero-weight padding arc of the ELL layout.
+template <typename Real>
+struct WSOut;
+template <>
+struct __align__(16) WSOut<double> {
+  double w;
+  uint32_t slot, pad;
+};
+template <>
+struct __align__(8) WSOut<float> {
+  float w;
+  uint32_t slot;
+};
+template <typename Real, bool SCALED, typename WSReal>
 __global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
                               const uint32_t* __restrict__ chain_param, const double* __restrict__ ln_w,
-                              double* __restrict__ arc_lnw, Real* __restrict__ out_real) {
+                              const uint32_t* __restrict__ arc_slot, double* __restrict__ arc_lnw,
+                              Real* __restrict__ out_real, WSReal* __restrict__ out_ws) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_arcs) return;
+  if (a > n_arcs) return;
   double s;
-  if (chain_off) {
-    s = 0;
-    for (uint32_t k = chain_off[a], e = chain_off[a + 1]; k < e; ++k) s += ln_w[chain_param[k]];
-  } else
-    s = ln_w[a];
-  arc_lnw[a] = s;
-  out_real[a] = SCALED ? (Real)exp(s) : (Real)s;
+  uint32_t slot = 0xFFFFFFFFu;
+  if (a == n_arcs) {
+    s = -CUDART_INF;
+  } else {
+    if (chain_off) {
+      s = 0;
+      for (uint32_t k = chain_off[a], e = chain_off[a + 1]; k < e; ++k) s += ln_w[chain_param[k]];
+    } else
+      s = ln_w[a];
+    arc_lnw[a] = s;
+    slot = arc_slot[a];
+  }
+  const Real v = SCALED ? (Real)exp(s) : (Real)s;
+  out_real[a] = v;
+  out_ws[a].w = v;
+  out_ws[a].slot = slot;
 }
 
-// K4 + prep_new_weights: accumulate (count + prior) of every arc into each unlocked parameter of
-// its chain.  Trivial cascade: acc[p] = counts[p] + prior[p].
-__global__ void k_param_acc(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
-                            const uint32_t* __restrict__ chain_param, const double* __restrict__ counts,
+// K4 + prep_new_weights: add (count + prior) of every count slot to each parameter of the slot's
+// (unlocked) chain.  Trivial cascade: slot == arc == parameter, acc[p] = counts[p] + prior[p].
+__global__ void k_param_acc(uint32_t n_slots, const uint32_t* __restrict__ slot_off,
+                            const uint32_t* __restrict__ slot_param, const double* __restrict__ counts,
                             const double* __restrict__ prior, const uint32_t* __restrict__ param_tie,
                             double* __restrict__ acc) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_arcs) return;
+  if (a >= n_slots) return;
   const double v = counts[a] + (prior ? prior[a] : 0.);
-  if (chain_off) {
-    for (uint32_t k = chain_off[a], e = chain_off[a + 1]; k < e; ++k) {
-      const uint32_t p = chain_param[k];
+  if (slot_off) {
+    for (uint32_t k = slot_off[a], e = slot_off[a + 1]; k < e; ++k) {
+      const uint32_t p = slot_param[k];
       if (param_tie[p] != CML_LOCKED_GROUP && v != 0.) atomicAdd(&acc[p], v);
     }
   } else

@@ -136,6 +136,7 @@ struct TrainOpts {
   int device = 0;                   // --gpu=n
   int shard_rank = 0, shard_count = 1;  // --shard=r/N : this process trains on block r of N of the corpus
   bool quiet = false;
+  bool no_ell = false;              // --no-ell : general (layered CSR) kernels only
   std::string history_file, dump_trellis_file;
   TrainOpts();
 };

@@ -88,6 +88,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   topt.weight_is_prior = flags[(unsigned)'U'];
   if (lopt.count("float")) topt.precision = 32;
   if (lopt.count("scaled")) topt.space = CML_SPACE_SCALED;
+  if (lopt.count("no-ell")) topt.no_ell = true;
   if (lopt.count("gpu")) topt.device = std::atoi(lopt["gpu"].c_str());
   if (lopt.count("history")) topt.history_file = lopt["history"];
   if (lopt.count("dump-trellis")) topt.dump_trellis_file = lopt["dump-trellis"];

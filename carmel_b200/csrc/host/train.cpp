@@ -97,6 +97,8 @@ void TrainJob::prepare() {
   }
   if (cml_create(&ctx, opt.device, opt.precision, opt.space) != CML_OK)
     throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
+  if (opt.max_iter == 0) ok(cml_set_option(ctx, CML_OPT_ARC_COUNTS, 1));  // -M 0 writes per-arc fractional counts
+  if (opt.no_ell) ok(cml_set_option(ctx, CML_OPT_NO_ELL, 1));
   cml_model mm{};
   mm.n_arcs = M.n_arcs;
   mm.chain_off = using_cascade ? M.chain_off.data() : nullptr;
@@ -128,7 +130,7 @@ void TrainJob::prepare() {
         M.arc_prior[a] += std::exp(lw);
       }
     mm.arc_prior = M.arc_prior.data();
-    ok(cml_set_model(ctx, &mm));
+    ok(cml_set_model(ctx, &mm));  // (no lattices are resident yet)
     ok(cml_set_params(ctx, w.data()));
   }
 

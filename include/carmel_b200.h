@@ -57,6 +57,15 @@ int cml_synchronize(cml_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t cml_launch_count(cml_ctx* ctx);
 
+/* options (cml_set_option) */
+enum cml_option {
+  CML_OPT_ARC_COUNTS = 1, /* keep one expected-count accumulator per arc-table entry (needed by
+                             cml_get_arc_counts on real cascades); default 0: arcs whose chains have the same
+                             unlocked parameters share an accumulator.  Set before cml_set_model. */
+  CML_OPT_NO_ELL = 2      /* force the layered-CSR kernels (tests).  Set before cml_add_trellises. */
+};
+int cml_set_option(cml_ctx* ctx, int option, int value);
+
 /* ---- model: parameters, cascade chains, normalisation groups ------------------------------ *
  * Replaces arcs_table<arc_counts> (carmel/src/derivations.h:79-140, train.h:28-40),
  * cascade_parameters::chains (carmel/src/cascade.h:222-262) and the group structure walked by
@@ -124,6 +133,10 @@ typedef struct cml_trellis_batch {
 int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b);
 int cml_clear_trellises(cml_ctx* ctx);
 int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs, uint64_t* n_levels);
+/* how the resident lattices are stored: examples / arcs / padded records in the level-sliced ELL layout
+ * (throughput kernel) and examples in the layered-CSR layout (general kernels) */
+int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,
+                     uint64_t* csr_examples);
 /* introspection for parity tests: the layered layout of resident example e.
  *   level_of[ex_states]  level of each reference state id;  local_of[ex_states] its layered index. */
 int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_t* level_of, uint32_t* local_of);
@@ -150,9 +163,12 @@ int cml_estimate_finish(cml_ctx* ctx, cml_estimate_result* out);
 int cml_last_fb_time_ms(cml_ctx* ctx, float* ms, uint32_t* n_kernels);
 /* per-example ln P_e of the last estimate (order of insertion), for parity tests */
 int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n);
-/* expected counts per arc-table id (linear) of the last estimate */
+/* expected counts per arc-table id (linear) of the last estimate.  On a real cascade this needs
+ * CML_OPT_ARC_COUNTS (otherwise counts are kept per unlocked-parameter slot: cml_get_counts). */
 int cml_get_arc_counts(cml_ctx* ctx, double* counts);
-/* The per-iteration reduce buffer: [n_arcs counts | sum_ln_p | sum_w_ln_p | n_zero] as fp64 on the
+uint64_t cml_count_slots(cml_ctx* ctx);
+int cml_get_counts(cml_ctx* ctx, double* counts, uint64_t n);
+/* The per-iteration reduce buffer: [count slots | sum_ln_p | sum_w_ln_p | n_zero] as fp64 on the
  * device.  A multi-GPU driver all-reduces (sum) it between cml_estimate_launch and
  * cml_estimate_finish (one collective per iteration).  cml_use_reduce_buffer lets the caller own the
  * memory (e.g. a torch tensor registered with NCCL); pass NULL to go back to the internal one. */

@@ -34,11 +34,14 @@ def dumps(oracle_bin, tmp_path_factory):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("precision,space,rel", [(64, 0, 1e-6), (64, 1, 1e-6), (32, 0, 1e-4), (32, 1, 1e-4)])
-def test_estep_matches_oracle(native_lib, dumps, name, precision, space, rel):
+@pytest.mark.parametrize("precision,space,rel,no_ell", [(64, 0, 1e-6, 0), (64, 1, 1e-6, 0), (64, 1, 1e-6, 1), (32, 0, 1e-4, 0),
+                                                         (32, 1, 1e-4, 0), (32, 1, 1e-4, 1)])
+def test_estep_matches_oracle(native_lib, dumps, name, precision, space, rel, no_ell):
     import carmel_b200 as cb
     t, e = dumps[name]
     ctx = cb.Context(0, precision, space)
+    if no_ell:
+        ctx.set_option(cb.OPT_NO_ELL, 1)
     ctx.set_trivial_model(t["n_arcs_table"])
     ctx.set_params(e["ln_w"])
     ctx.add_trellises(t["ex_states"], t["ex_fin"], t["ex_weight"], t["arc_off"], t["arc_dst"], t["arc_id"])
