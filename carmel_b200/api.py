@@ -29,7 +29,7 @@ class CmlModel(C.Structure):
     _fields_ = [
         ("n_arcs", C.c_uint32), ("chain_off", _u32p), ("chain_param", _u32p), ("arc_prior", _f64p),
         ("n_params", C.c_uint32), ("param_group", _u32p), ("param_tie", _u32p), ("n_groups", C.c_uint32),
-        ("group_add", _f64p), ("n_ties", C.c_uint32),
+        ("group_add", _f64p), ("n_ties", C.c_uint32), ("arc_locality_key", C.POINTER(C.c_uint64)),
     ]
 
 

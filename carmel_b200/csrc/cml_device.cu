@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 #include "cml_common.cuh"
@@ -21,8 +22,14 @@ namespace {
 // ELL classes (scaled space only): one example per group of 4/8/16/32 lanes, level-sliced ELL layout.
 // CSR classes (everything else): one example per warp (shared-memory capacity classes), per CTA, or
 // per CTA with alpha/beta in an HBM scratch.
-enum { NELL = 4 };
-static const int kEllG[NELL] = {4, 8, 16, 32};
+enum { NELL = 7 };
+struct EllClass {
+  int R, C;  // row-lanes x column-lanes per example: level width <= R, max degree <= C * kEllSlots
+  bool cta;  // R*C == 256: one example per block
+};
+// ordered by group size: an example takes the first class it fits
+static const EllClass kEllCls[NELL] = {{4, 1, false},  {8, 1, false},  {4, 4, false}, {8, 4, false},
+                                       {16, 2, false}, {32, 1, false}, {32, 8, true}};
 enum ExClass { CLS_WARP0 = 0, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, NCLS = 8 };
 static const uint32_t kWarpCaps[NWARPCLS] = {64, 128, 256, 512, 1024, 2048};
 static const uint32_t kPadNone = 0xFFFFFFFFu;
@@ -82,6 +89,15 @@ struct cml_ctx {
   uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0, n_slots = 0;
   bool slots_are_arcs = true;
   std::vector<uint32_t> h_arc_slot;  // host copy: slot of every arc (kPadNone = contributes to no parameter)
+  // internal arc numbering (locality order): weight tables and lattice records use perm[arc id]
+  std::vector<uint32_t> h_perm, h_slot_internal;
+  DevArray<uint32_t> arc_perm;
+  // hot count slots (see CountSink in cml_kernels_fb.cuh): occurrence statistics of the resident lattices
+  std::vector<uint64_t> slot_occ;    // arcs per slot over all resident batches
+  bool hot_dirty = true;             // slot codes must be rebuilt before the next E-step
+  uint32_t n_hot = 0;
+  DevArray<uint32_t> arc_slot_code, hot_slot;
+  DevArray<double> hot_counts;
   DevArray<uint32_t> chain_off, chain_param, param_group, param_tie, group_off, group_members, tie_off, tie_members;
   DevArray<uint32_t> arc_slot, slot_off, slot_param;
   DevArray<double> slot_prior, group_add;
@@ -310,6 +326,20 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   ctx->n_slots = n_slots;
   ctx->slots_are_arcs = !merge;
   ctx->h_arc_slot = arc_slot;
+  ctx->h_perm.resize((size_t)m->n_arcs + 1);
+  {
+    std::vector<uint32_t> order(m->n_arcs);
+    for (uint32_t a = 0; a < m->n_arcs; ++a) order[a] = a;
+    if (m->arc_locality_key)
+      std::stable_sort(order.begin(), order.end(),
+                       [&](uint32_t x, uint32_t y) { return m->arc_locality_key[x] < m->arc_locality_key[y]; });
+    for (uint32_t i = 0; i < m->n_arcs; ++i) ctx->h_perm[order[i]] = i;
+    ctx->h_perm[m->n_arcs] = m->n_arcs;  // the padding arc
+    ctx->h_slot_internal.assign((size_t)m->n_arcs + 1, kPadNone);
+    for (uint32_t a = 0; a < m->n_arcs; ++a) ctx->h_slot_internal[ctx->h_perm[a]] = arc_slot[a];
+  }
+  ctx->slot_occ.assign(n_slots, 0);
+  ctx->hot_dirty = true;
   if (!trivial) {
     CML_CUDA(ctx->chain_off.upload(m->chain_off, m->n_arcs + 1, s));
     CML_CUDA(ctx->chain_param.upload(m->chain_param, m->chain_off[m->n_arcs], s));
@@ -322,6 +352,7 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
     ctx->slot_param.release();
   }
   CML_CUDA(ctx->arc_slot.upload(arc_slot.data(), arc_slot.size(), s));
+  CML_CUDA(ctx->arc_perm.upload(ctx->h_perm.data(), ctx->h_perm.size(), s));
   ctx->have_prior = !slot_prior.empty();
   if (ctx->have_prior) CML_CUDA(ctx->slot_prior.upload(slot_prior.data(), slot_prior.size(), s));
   ctx->have_add = m->group_add != nullptr && m->n_groups > 0;
@@ -415,6 +446,7 @@ inline uint32_t pow2ceil(uint32_t v) {
 }
 
 struct Scratch {  // per-thread temporaries
+  std::vector<uint64_t> occ;
   std::vector<uint32_t> indeg, queue, cnt, lvl_first, lvl_width, lvl_d, lvl_o, lvl_min, lvl_max, ref_of, icur, ocur, order;
 };
 
@@ -488,11 +520,19 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
   fx.in_pad = in_pad;
   fx.out_pad = out_pad;
   fx.ring_need = maxdist + width + 1;
-  uint32_t gc = 0;
-  while (gc + 1 < NELL && (uint32_t)kEllG[gc] < width) ++gc;
-  fx.g_class = gc;
-  fx.ell = width <= (uint32_t)kEllG[gc] * cmlk::kEllMaxRows && width <= 255 && maxdeg <= 255 && maxspan <= 15 &&
-           fx.ring_need <= 4096 && in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
+  // smallest lane group (R x C) whose per-lane record slots hold every level of the example
+  int gc = -1;
+  for (int k = 0; k < NELL && gc < 0; ++k) {
+    bool fits = true;
+    for (uint32_t l = 0; l < nl && fits; ++l) {
+      const uint32_t w = S.lvl_first[l + 1] - S.lvl_first[l], deg = std::max(ld[l], lo[l]);
+      fits = w <= (uint32_t)kEllCls[k].R && deg <= (uint32_t)(kEllCls[k].C * cmlk::kEllSlots);
+    }
+    if (fits) gc = k;
+  }
+  fx.g_class = gc < 0 ? 0 : (uint32_t)gc;
+  fx.ell = gc >= 0 && width <= 255 && maxdeg <= 255 && maxspan <= 15 && fx.ring_need <= 4096 &&
+           in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
 }
 
 }  // namespace
@@ -536,6 +576,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   // ---- pass 1 (parallel over examples): levels + ELL eligibility
   const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::atomic<int> bad_cycle{0}, bad_range{0};
+  std::vector<uint64_t> batch_occ(ctx->n_slots, 0);  // arcs per count slot in this batch
+  std::mutex occ_mutex;
   auto parallel_for = [&](auto&& body) {
     std::atomic<uint64_t> next{0};
     auto work = [&]() {
@@ -544,6 +586,10 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         const uint64_t e0 = next.fetch_add(256);
         if (e0 >= n_ex) break;
         for (uint64_t e = e0; e < std::min(n_ex, e0 + 256); ++e) body(e, S);
+      }
+      if (!S.occ.empty()) {  // merge this thread's slot occurrence counts
+        std::lock_guard<std::mutex> lk(occ_mutex);
+        for (size_t i = 0; i < S.occ.size(); ++i) batch_occ[i] += S.occ[i];
       }
     };
     std::vector<std::thread> th;
@@ -566,6 +612,11 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     levelize(n, off, dst, &bt->h_level_of[state_base[e]], &bt->h_local_of[state_base[e]], fx[e], S, want_ell);
     if (fx[e].cycle) bad_cycle = 1;
     bt->h_nlevels[e] = fx[e].n_levels;
+    if (S.occ.empty()) S.occ.assign(ctx->n_slots, 0);
+    for (uint32_t k = 0; k < off[n]; ++k) {
+      const uint32_t sl = ctx->h_arc_slot[id[k]];
+      if (sl != kPadNone) ++S.occ[sl];
+    }
   });
   CML_REQUIRE(!bad_range, CML_ERR_ARG, "trellis arc destination or arc id out of range");
   CML_REQUIRE(!bad_cycle, CML_ERR_CYCLE,
@@ -611,7 +662,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   std::vector<uint2> h_ein(ei), h_eout(eo);
   std::vector<double> h_weight(n_ex);
   const uint32_t pad_id = ctx->n_arcs;  // zero-weight padding arc
-  const std::vector<uint32_t>& arc_slot = ctx->h_arc_slot;
+  const std::vector<uint32_t>& arc_slot = ctx->h_slot_internal;  // indexed by internal arc id
+  const std::vector<uint32_t>& perm = ctx->h_perm;
 
   // ---- pass 2 (parallel): fill
   parallel_for([&](uint64_t e, Scratch& S) {
@@ -669,8 +721,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         uint32_t o = ooff[j];
         for (uint32_t k = off[s]; k < off[s + 1]; ++k) {
           const uint32_t dj = local_of[dst[k]];
-          oa[o++] = make_uint2(dj, id[k]);
-          ia[S.icur[dj]++] = make_uint2(j, id[k]);
+          oa[o++] = make_uint2(dj, perm[id[k]]);
+          ia[S.icur[dj]++] = make_uint2(j, perm[id[k]]);
         }
       }
       CmlExDesc& d = desc[slot_of[e]];
@@ -730,9 +782,9 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       for (uint32_t c = 0; c < deg; ++c) {
         const uint32_t k = order[c];
         const uint32_t dj = local_of[dst[k]], dl = level_of[dst[k]];
-        eout[meta[l].y + (uint64_t)c * w + r] = make_uint2(dj, id[k]);
+        eout[meta[l].y + (uint64_t)c * w + r] = make_uint2(dj, perm[id[k]]);
         const uint32_t dw = lfirst[dl + 1] - lfirst[dl], dr = dj - lfirst[dl];
-        ein[meta[dl].x + (uint64_t)(S.icur[dj]++) * dw + dr] = make_uint2(j, id[k]);
+        ein[meta[dl].x + (uint64_t)(S.icur[dj]++) * dw + dr] = make_uint2(j, perm[id[k]]);
       }
     }
     // aggregate flag: no padding in the level's outgoing block and every column feeds one slot
@@ -838,6 +890,9 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   }
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->batches.push_back(std::move(bt));
+  if (ctx->slot_occ.size() != ctx->n_slots) ctx->slot_occ.assign(ctx->n_slots, 0);
+  for (size_t i = 0; i < batch_occ.size(); ++i) ctx->slot_occ[i] += batch_occ[i];
+  ctx->hot_dirty = true;
   return CML_OK;
 }
 
@@ -846,6 +901,8 @@ extern "C" int cml_clear_trellises(cml_ctx* ctx) {
   cudaSetDevice(ctx->device);
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->batches.clear();
+  ctx->slot_occ.assign(ctx->n_slots, 0);
+  ctx->hot_dirty = true;
   return CML_OK;
 }
 
@@ -903,18 +960,19 @@ extern "C" int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_leve
 // -------------------------------------------------------------------------------------------------
 // E-step
 // -------------------------------------------------------------------------------------------------
-template <typename Real, int G>
+template <typename Real, int R, int C, bool CTA>
 static int launch_ell_class(cml_ctx* ctx, Batch& bt, cmlk::EllArgs& A, int c) {
   const uint32_t n = bt.ell_begin[c + 1] - bt.ell_begin[c];
   if (!n) return CML_OK;
   A.ex_list = bt.ell_list.p + bt.ell_begin[c];
   A.n_list = n;
   A.ring = bt.ell_ring[c];
-  constexpr int GPB = 256 / G;
-  const size_t smem = (size_t)GPB * A.ring * sizeof(Real);
-  auto kern = cmlk::k_fb_ell<Real, G>;
+  constexpr int GPB = CTA ? 1 : cmlk::kEllThreads / (R * C);
+  const size_t smem = (size_t)cmlk::kEllStages * cmlk::kEllSlots * cmlk::kEllThreads * sizeof(uint2) +
+                      (size_t)GPB * A.ring * sizeof(Real);
+  auto kern = cmlk::k_fb_ell<Real, R, C, CTA>;
   if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<cdiv(n, GPB), 256, smem, ctx->stream>>>(A);
+  kern<<<cdiv(n, GPB), cmlk::kEllThreads, smem, ctx->stream>>>(A);
   ++ctx->launches;
   ++bt.n_fb_kernels;
   return CML_OK;
@@ -937,15 +995,18 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     E.ell_out = bt.ell_out.p;
     E.arc_w = ctx->arc_w_real.p;
     E.arc_ws = ctx->arc_ws.p;
-    E.counts = ctx->reduce;
+    E.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
     E.ex_lnp = bt.ex_lnp.p;
     E.alpha_g = bt.alpha_g.p;
     E.lvl_exp = bt.lvl_exp.p;
     int r;
-    if ((r = launch_ell_class<Real, 4>(ctx, bt, E, 0))) return r;
-    if ((r = launch_ell_class<Real, 8>(ctx, bt, E, 1))) return r;
-    if ((r = launch_ell_class<Real, 16>(ctx, bt, E, 2))) return r;
-    if ((r = launch_ell_class<Real, 32>(ctx, bt, E, 3))) return r;
+    if ((r = launch_ell_class<Real, 4, 1, false>(ctx, bt, E, 0))) return r;   // kEllCls[0]
+    if ((r = launch_ell_class<Real, 8, 1, false>(ctx, bt, E, 1))) return r;   // kEllCls[1]
+    if ((r = launch_ell_class<Real, 4, 4, false>(ctx, bt, E, 2))) return r;   // kEllCls[2]
+    if ((r = launch_ell_class<Real, 8, 4, false>(ctx, bt, E, 3))) return r;   // kEllCls[3]
+    if ((r = launch_ell_class<Real, 16, 2, false>(ctx, bt, E, 4))) return r;  // kEllCls[4]
+    if ((r = launch_ell_class<Real, 32, 1, false>(ctx, bt, E, 5))) return r;  // kEllCls[5]
+    if ((r = launch_ell_class<Real, 32, 8, true>(ctx, bt, E, 6))) return r;   // kEllCls[6]
   }
   if (bt.csr_ex) {
     FbArgs A;
@@ -956,8 +1017,8 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     A.out_off = bt.out_off.p;
     A.out_arc = bt.out_arc.p;
     A.arc_w = ctx->arc_w_real.p;
-    A.arc_slot = ctx->arc_slot.p;
-    A.counts = ctx->reduce;
+    A.arc_slot = ctx->arc_slot_code.p;
+    A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
     A.ex_lnp = bt.ex_lnp.p;
     A.scratch = bt.scratch.p;
     A.scratch_lvl = bt.scratch_lvl.p;
@@ -1013,10 +1074,40 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
 template <typename Real, bool SCALED>
 static int launch_arc_weights(cml_ctx* ctx) {
   cmlk::k_arc_weights<Real, SCALED, cmlk::WS<Real>><<<cdiv(ctx->n_arcs + 1, 256), 256, 0, ctx->stream>>>(
-      ctx->n_arcs, ctx->trivial ? nullptr : ctx->chain_off.p, ctx->chain_param.p, ctx->ln_w.p, ctx->arc_slot.p,
-      ctx->arc_lnw.p, (Real*)ctx->arc_w_real.p, (cmlk::WS<Real>*)ctx->arc_ws.p);
+      ctx->n_arcs, ctx->trivial ? nullptr : ctx->chain_off.p, ctx->chain_param.p, ctx->ln_w.p, ctx->arc_slot_code.p,
+      ctx->arc_perm.p, ctx->arc_lnw.p, (Real*)ctx->arc_w_real.p, (cmlk::WS<Real>*)ctx->arc_ws.p);
   ++ctx->launches;
   CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
+// Slot codes: slots that occur at least kHotMinOcc times in the resident lattices become HOT (replicated
+// accumulators, see CountSink); at most kHotMaxSlots of them, most frequent first.
+static int rebuild_slot_codes(cml_ctx* ctx) {
+  uint64_t kHotMinOcc = 4096;
+  size_t kHotMaxSlots = 32768;
+  if (const char* e = getenv("CML_HOT_MIN_OCC")) kHotMinOcc = (uint64_t)atoll(e);  // tuning knobs (profiling)
+  if (const char* e = getenv("CML_HOT_MAX_SLOTS")) kHotMaxSlots = (size_t)atoll(e);
+  std::vector<uint32_t> hot;
+  for (uint32_t sl = 0; sl < ctx->n_slots && sl < ctx->slot_occ.size(); ++sl)
+    if (ctx->slot_occ[sl] >= kHotMinOcc) hot.push_back(sl);
+  std::sort(hot.begin(), hot.end(), [&](uint32_t a, uint32_t b) {
+    return ctx->slot_occ[a] != ctx->slot_occ[b] ? ctx->slot_occ[a] > ctx->slot_occ[b] : a < b;
+  });
+  if (hot.size() > kHotMaxSlots) hot.resize(kHotMaxSlots);
+  std::vector<uint32_t> hot_index(ctx->n_slots, kPadNone);
+  for (uint32_t h = 0; h < hot.size(); ++h) hot_index[hot[h]] = h;
+  std::vector<uint32_t> code((size_t)ctx->n_arcs + 1, kPadNone);  // indexed by internal arc id
+  for (uint32_t a = 0; a < ctx->n_arcs; ++a) {
+    const uint32_t sl = ctx->h_arc_slot[a];
+    code[ctx->h_perm[a]] = (sl == kPadNone) ? kPadNone : (hot_index[sl] != kPadNone ? (cmlk::kSlotHot | hot_index[sl]) : sl);
+  }
+  ctx->n_hot = (uint32_t)hot.size();
+  CML_CUDA(ctx->arc_slot_code.upload(code.data(), code.size(), ctx->stream));
+  CML_CUDA(ctx->hot_slot.upload(hot.data(), hot.size(), ctx->stream));
+  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * cmlk::kHotCopies)));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->hot_dirty = false;
   return CML_OK;
 }
 
@@ -1025,6 +1116,10 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
   CML_REQUIRE(!ctx->batches.empty(), CML_ERR_NODERIV, "no trellises resident (no training example had a derivation)");
   cudaSetDevice(ctx->device);
+  if (ctx->hot_dirty) {
+    const int rc = rebuild_slot_codes(ctx);
+    if (rc) return rc;
+  }
   const bool sc = ctx->space == CML_SPACE_SCALED;
   int r;
   if (ctx->precision == 64)
@@ -1033,12 +1128,20 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
     r = sc ? launch_arc_weights<float, true>(ctx) : launch_arc_weights<float, false>(ctx);
   if (r) return r;
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), ctx->stream));
+  if (ctx->n_hot)
+    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * cmlk::kHotCopies * sizeof(double), ctx->stream));
   for (auto& bt : ctx->batches) {
     if (ctx->precision == 64)
       r = sc ? launch_fb<double, true>(ctx, *bt) : launch_fb<double, false>(ctx, *bt);
     else
       r = sc ? launch_fb<float, true>(ctx, *bt) : launch_fb<float, false>(ctx, *bt);
     if (r) return r;
+  }
+  if (ctx->n_hot) {
+    cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, ctx->stream>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p,
+                                                                   ctx->reduce);
+    ++ctx->launches;
+    CML_CUDA(cudaGetLastError());
   }
   ctx->estimate_pending = true;
   return CML_OK;

@@ -48,6 +48,39 @@ struct Num<float> {
   static __device__ __forceinline__ float scale2(float x, int k) { return scalbnf(x, k); }
 };
 
+// Expected-count accumulation.  A slot code is either 0xFFFFFFFF (the arc feeds no trainable
+// parameter), a plain slot index into counts[], or 0x80000000|h for a HOT slot: slots that occur many
+// thousand times in the corpus serialise in the L2 atomic unit (measured: ~2.5 ns per RED on one
+// address, 80% of the sweep's time), so they get kHotCopies replicas spread by block index and are folded
+// into counts[] by k_fold_hot afterwards.
+constexpr uint32_t kSlotNone = 0xFFFFFFFFu;
+constexpr uint32_t kSlotHot = 0x80000000u;
+constexpr uint32_t kHotCopies = 64;
+struct CountSink {
+  double* counts;   // [n_slots]
+  double* hot;      // [kHotCopies][n_hot]
+  uint32_t n_hot;
+};
+__device__ __forceinline__ void count_add(const CountSink& S, uint32_t code, double v) {
+#ifdef CML_DEBUG_NO_COUNTS  // profiling experiment: how long is the sweep without its REDs?
+  if (v < 1e300) return;
+#endif
+  if (code & kSlotHot)
+    atomicAdd(S.hot + (size_t)(blockIdx.x & (kHotCopies - 1)) * S.n_hot + (code & 0x7fffffffu), v);
+  else
+    atomicAdd(S.counts + code, v);
+}
+// fold the hot replicas into the count table (one thread per hot slot)
+__global__ void k_fold_hot(uint32_t n_hot, const uint32_t* __restrict__ hot_slot, const double* __restrict__ hot,
+                           double* __restrict__ counts) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hot) return;
+  double s = 0;
+#pragma unroll 8
+  for (uint32_t k = 0; k < kHotCopies; ++k) s += hot[(size_t)k * n_hot + h];
+  if (s != 0.) atomicAdd(&counts[hot_slot[h]], s);
+}
+
 struct FbArgs {
   const CmlExDesc* desc;      // per example
   const uint32_t* ex_list;    // examples handled by this launch (indices into desc)
@@ -58,8 +91,8 @@ struct FbArgs {
   const uint32_t* out_off;
   const uint2* out_arc;       // {dst layered index, arc id}
   const void* arc_w;          // Real[n_arcs]: ln w (LOG) or w (SCALED)
-  const uint32_t* arc_slot;   // [n_arcs] count slot of every arc (0xFFFFFFFF: feeds no parameter)
-  double* counts;             // [n_slots] linear expected counts (atomicAdd)
+  const uint32_t* arc_slot;   // [n_arcs] count slot code of every arc (see CountSink)
+  CountSink sink;             // linear expected counts (fp64 RED)
   double* ex_lnp;             // [n_ex in batch] ln P_e
   void* scratch;              // GLOBAL class: Real alpha/beta slots, 2 per state
   int* scratch_lvl;           // GLOBAL class, SCALED: E/F per level (2 per level)
@@ -160,7 +193,7 @@ __device__ void fb_example_log(const FbArgs& A, const CmlExDesc& d, Real* __rest
         if (lc > Real(-700)) {
           const double c = (double)Num<Real>::ex(lc);
           const uint32_t slot = __ldg(&A.arc_slot[r.y]);
-          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
+          if (c > 0 && slot != kSlotNone) count_add(A.sink, slot, c);
         }
       }
       be[s] = (m > NI) ? m + Num<Real>::lg(acc) : NI;
@@ -276,7 +309,7 @@ __device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __r
           acc += t;
           const double c = as * (double)t;
           const uint32_t slot = __ldg(&A.arc_slot[r.y]);
-          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
+          if (c > 0 && slot != kSlotNone) count_add(A.sink, slot, c);
         }
       } else {
         for (; k < k1; ++k) {
@@ -286,7 +319,7 @@ __device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __r
           acc += t;
           const double c = as * (double)t;
           const uint32_t slot = __ldg(&A.arc_slot[r.y]);
-          if (c > 0 && slot != 0xFFFFFFFFu) atomicAdd(&A.counts[slot], c);
+          if (c > 0 && slot != kSlotNone) count_add(A.sink, slot, c);
         }
       }
       be[s] = acc;

@@ -59,8 +59,8 @@ struct __align__(8) WSOut<float> {
 template <typename Real, bool SCALED, typename WSReal>
 __global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
                               const uint32_t* __restrict__ chain_param, const double* __restrict__ ln_w,
-                              const uint32_t* __restrict__ arc_slot, double* __restrict__ arc_lnw,
-                              Real* __restrict__ out_real, WSReal* __restrict__ out_ws) {
+                              const uint32_t* __restrict__ slot_code, const uint32_t* __restrict__ perm,
+                              double* __restrict__ arc_lnw, Real* __restrict__ out_real, WSReal* __restrict__ out_ws) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a > n_arcs) return;
   double s;
@@ -74,12 +74,13 @@ __global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chai
     } else
       s = ln_w[a];
     arc_lnw[a] = s;
-    slot = arc_slot[a];
   }
+  const uint32_t ia = perm[a];  // internal (locality-ordered) arc id; slot codes are stored in that order
+  slot = (a == n_arcs) ? 0xFFFFFFFFu : slot_code[ia];
   const Real v = SCALED ? (Real)exp(s) : (Real)s;
-  out_real[a] = v;
-  out_ws[a].w = v;
-  out_ws[a].slot = slot;
+  out_real[ia] = v;
+  out_ws[ia].w = v;
+  out_ws[ia].slot = slot;
 }
 
 // K4 + prep_new_weights: add (count + prior) of every count slot to each parameter of the slot's

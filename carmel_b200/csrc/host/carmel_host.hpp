@@ -153,6 +153,7 @@ struct TrainResult {
 struct ModelArrays {
   std::vector<uint32_t> chain_off, chain_param, param_group, param_tie;
   std::vector<double> group_add, ln_w, arc_prior;
+  std::vector<uint64_t> arc_key;
   uint32_t n_groups = 0, n_ties = 0, n_arcs = 0, n_params = 0;
 };
 // sum-all-reduce of n doubles at device_ptr across the ranks of a multi-GPU run (NCCL, supplied by the driver)

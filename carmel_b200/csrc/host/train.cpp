@@ -99,7 +99,19 @@ void TrainJob::prepare() {
     throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
   if (opt.max_iter == 0) ok(cml_set_option(ctx, CML_OPT_ARC_COUNTS, 1));  // -M 0 writes per-arc fractional counts
   if (opt.no_ell) ok(cml_set_option(ctx, CML_OPT_NO_ELL, 1));
+  // locality keys: arcs with the same output symbol, then source state, are laid out together on the GPU,
+  // so the weight gathers of one lattice level (one output position) fall into few cache sectors
+  {
+    uint32_t src = 0;
+    for (auto const& st : x->states) {
+      for (Arc const& a : st)
+        M.arc_key.push_back(((uint64_t)(a.out & 0xFFFFF) << 44) | ((uint64_t)(a.in & 0xFFFFF) << 24) |
+                            ((uint64_t)(src & 0xFFF) << 12) | (uint64_t)(a.dest & 0xFFF));
+      ++src;
+    }
+  }
   cml_model mm{};
+  mm.arc_locality_key = M.arc_key.data();
   mm.n_arcs = M.n_arcs;
   mm.chain_off = using_cascade ? M.chain_off.data() : nullptr;
   mm.chain_param = using_cascade ? M.chain_param.data() : nullptr;

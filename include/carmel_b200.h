@@ -94,6 +94,10 @@ typedef struct cml_model {
   uint32_t n_groups;
   const double* group_add;
   uint32_t n_ties;
+  /* optional [n_arcs]: arcs with nearby keys are used together (e.g. output symbol, then destination, then
+   * source state); the library lays its weight tables out in key order so gathers of one lattice level share
+   * cache sectors.  Must be the same on every rank of a multi-GPU job.  NULL = arc-table order. */
+  const uint64_t* arc_locality_key;
 } cml_model;
 int cml_set_model(cml_ctx* ctx, const cml_model* m);
 /* ln weights of the n_params parameters: FSTArc::weight (arc.h:37) */
