@@ -11,122 +11,10 @@
 #include <mutex>
 #include <thread>
 
-#include "cml_common.cuh"
-#include "cml_kernels_ell.cuh"
-#include "cml_kernels_fb.cuh"
+#include "cml_ctx.cuh"
 #include "cml_kernels_model.cuh"
 
-namespace {
-
-// ---- example classes ------------------------------------------------------------------------------
-// ELL classes (scaled space only): one example per group of 4/8/16/32 lanes, level-sliced ELL layout.
-// CSR classes (everything else): one example per warp (shared-memory capacity classes), per CTA, or
-// per CTA with alpha/beta in an HBM scratch.
-enum { NELL = 7 };
-struct EllClass {
-  int R, C;  // row-lanes x column-lanes per example: level width <= R, max degree <= C * kEllSlots
-  bool cta;  // R*C == 256: one example per block
-};
-// ordered by group size: an example takes the first class it fits
-static const EllClass kEllCls[NELL] = {{4, 1, false},  {8, 1, false},  {4, 4, false}, {8, 4, false},
-                                       {16, 2, false}, {32, 1, false}, {32, 8, true}};
-enum ExClass { CLS_WARP0 = 0, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, NCLS = 8 };
-static const uint32_t kWarpCaps[NWARPCLS] = {64, 128, 256, 512, 1024, 2048};
-static const uint32_t kPadNone = 0xFFFFFFFFu;
-
-struct Batch {
-  uint64_t n_ex = 0, n_states = 0, n_arcs = 0, n_levels = 0;
-  DevArray<double> ex_lnp;
-  DevArray<double> ex_weight;  // for k_reduce_lnp
-  // --- CSR part (v1 kernels)
-  uint64_t csr_ex = 0;
-  DevArray<CmlExDesc> desc;
-  DevArray<uint32_t> lvl_off, in_off, out_off;
-  DevArray<uint2> in_arc, out_arc;
-  DevArray<uint32_t> ex_list;  // all CSR classes concatenated (indices into desc)
-  uint32_t cls_begin[NCLS + 1] = {0};
-  uint32_t cta_cap = 0;
-  DevArray<unsigned char> scratch;
-  DevArray<int> scratch_lvl;
-  // --- ELL part (v2 kernel)
-  uint64_t ell_ex = 0, ell_arcs = 0, ell_pad_records = 0;
-  DevArray<cmlk::EllDesc> edesc;
-  DevArray<uint4> lvl_meta;
-  DevArray<uint2> ell_in, ell_out;
-  DevArray<uint32_t> ell_list;
-  uint32_t ell_begin[NELL + 1] = {0};
-  uint32_t ell_ring[NELL] = {0};
-  DevArray<unsigned char> alpha_g;
-  DevArray<int> lvl_exp;
-  cudaEvent_t ev_fb0 = nullptr, ev_fb1 = nullptr;  // bracket this batch's forward-backward kernels
-  uint32_t n_fb_kernels = 0;
-  ~Batch() {
-    if (ev_fb0) cudaEventDestroy(ev_fb0);
-    if (ev_fb1) cudaEventDestroy(ev_fb1);
-  }
-  // host copies kept for introspection (cml_get_example_layout)
-  std::vector<uint64_t> h_state_base;
-  std::vector<uint32_t> h_level_of, h_local_of, h_nlevels;
-};
-
-}  // namespace
-
-struct cml_ctx {
-  int device = 0;
-  int precision = 64;
-  int space = CML_SPACE_LOG;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = CML_SM_COUNT_FALLBACK;
-  size_t smem_optin = 0;
-  std::string err;
-  uint64_t launches = 0;
-  int opt_arc_counts = 0;  // CML_OPT_ARC_COUNTS: keep one count slot per arc-table entry
-  int opt_no_ell = 0;      // CML_OPT_NO_ELL: force the CSR kernels (tests)
-
-  // model
-  bool have_model = false, trivial = true;
-  uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0, n_slots = 0;
-  bool slots_are_arcs = true;
-  std::vector<uint32_t> h_arc_slot;  // host copy: slot of every arc (kPadNone = contributes to no parameter)
-  // internal arc numbering (locality order): weight tables and lattice records use perm[arc id]
-  std::vector<uint32_t> h_perm, h_slot_internal;
-  DevArray<uint32_t> arc_perm;
-  // hot count slots (see CountSink in cml_kernels_fb.cuh): occurrence statistics of the resident lattices
-  std::vector<uint64_t> slot_occ;    // arcs per slot over all resident batches
-  bool hot_dirty = true;             // slot codes must be rebuilt before the next E-step
-  uint32_t n_hot = 0;
-  DevArray<uint32_t> arc_slot_code, hot_slot;
-  DevArray<double> hot_counts;
-  DevArray<uint32_t> chain_off, chain_param, param_group, param_tie, group_off, group_members, tie_off, tie_members;
-  DevArray<uint32_t> arc_slot, slot_off, slot_param;
-  DevArray<double> slot_prior, group_add;
-  bool have_prior = false, have_add = false;
-  DevArray<double> ln_w, snap[4], arc_lnw, acc, u, old, gsum, glocked, tie_arc, tie_state, tie_maxl;
-  DevArray<unsigned char> arc_w_real, arc_ws;
-  DevArray<unsigned long long> maxchg;
-  bool have_params = false;
-
-  // reduce buffer: [n_slots counts | sum_ln_p | sum_w_ln_p | n_zero]
-  DevArray<double> reduce_own;
-  double* reduce = nullptr;
-  uint64_t reduce_n = 0;
-
-  std::vector<std::unique_ptr<Batch>> batches;
-  bool estimate_pending = false;
-};
-
 static thread_local std::string g_create_err;
-
-#define CML_REQUIRE(cond, code, msg) \
-  do {                               \
-    if (!(cond)) {                   \
-      ctx->err = (msg);              \
-      return (code);                 \
-    }                                \
-  } while (0)
-
-static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // -------------------------------------------------------------------------------------------------
 // context
@@ -1345,7 +1233,8 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
       "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",
-      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats"};
+      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_sweep",
+      "cml_gibbs_sample_capacity", "cml_gibbs_get_samples", "cml_gibbs_get_state"};
   if (n) *n = sizeof(syms) / sizeof(syms[0]);
   return syms;
 }

@@ -112,7 +112,7 @@ __device__ __forceinline__ T row_reduce(T v, unsigned mask, Op op) {
 
 // R row-lanes x C column-lanes per example (level width <= R).  CTA: R*C == 256, one example per block.
 template <typename Real, int R, int C, bool CTA>
-__global__ void __launch_bounds__(kEllThreads) k_fb_ell(EllArgs A) {
+static __global__ void __launch_bounds__(kEllThreads) k_fb_ell(EllArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int smax[3];
   constexpr int G = R * C;

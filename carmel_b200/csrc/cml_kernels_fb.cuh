@@ -71,7 +71,7 @@ __device__ __forceinline__ void count_add(const CountSink& S, uint32_t code, dou
     atomicAdd(S.counts + code, v);
 }
 // fold the hot replicas into the count table (one thread per hot slot)
-__global__ void k_fold_hot(uint32_t n_hot, const uint32_t* __restrict__ hot_slot, const double* __restrict__ hot,
+static __global__ void k_fold_hot(uint32_t n_hot, const uint32_t* __restrict__ hot_slot, const double* __restrict__ hot,
                            double* __restrict__ counts) {
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_hot) return;
@@ -345,7 +345,7 @@ __device__ void fb_example_scaled(const FbArgs& A, const CmlExDesc& d, Real* __r
 // Shared memory per group: cap*2 Reals (+ 2*cap ints of level exponents in SCALED space).
 // ---------------------------------------------------------------------------------------------
 template <typename Real, bool SCALED>
-__global__ void __launch_bounds__(128) k_fb_warp(FbArgs A) {
+static __global__ void __launch_bounds__(128) k_fb_warp(FbArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t li = blockIdx.x * 4 + warp;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(128) k_fb_warp(FbArgs A) {
 }
 
 template <typename Real, bool SCALED, bool GLOBAL>
-__global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
+static __global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int smax[2];
   const uint32_t li = blockIdx.x;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
 
 // Sum of ln P_e, w_e ln P_e and the zero-probability count over a batch (deterministic per block,
 // one atomicAdd triple per block into the reduce buffer's scalar tail).
-__global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const double* __restrict__ ex_weight,
+static __global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const double* __restrict__ ex_weight,
                                                     uint64_t n, double* __restrict__ scal) {
   double s0 = 0, s1 = 0, nz = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {

@@ -57,7 +57,7 @@ struct __align__(8) WSOut<float> {
   uint32_t slot;
 };
 template <typename Real, bool SCALED, typename WSReal>
-__global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
+static __global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chain_off,
                               const uint32_t* __restrict__ chain_param, const double* __restrict__ ln_w,
                               const uint32_t* __restrict__ slot_code, const uint32_t* __restrict__ perm,
                               double* __restrict__ arc_lnw, Real* __restrict__ out_real, WSReal* __restrict__ out_ws) {
@@ -85,7 +85,7 @@ __global__ void k_arc_weights(uint32_t n_arcs, const uint32_t* __restrict__ chai
 
 // K4 + prep_new_weights: add (count + prior) of every count slot to each parameter of the slot's
 // (unlocked) chain.  Trivial cascade: slot == arc == parameter, acc[p] = counts[p] + prior[p].
-__global__ void k_param_acc(uint32_t n_slots, const uint32_t* __restrict__ slot_off,
+static __global__ void k_param_acc(uint32_t n_slots, const uint32_t* __restrict__ slot_off,
                             const uint32_t* __restrict__ slot_param, const double* __restrict__ counts,
                             const double* __restrict__ prior, const uint32_t* __restrict__ param_tie,
                             double* __restrict__ acc) {
@@ -103,7 +103,7 @@ __global__ void k_param_acc(uint32_t n_slots, const uint32_t* __restrict__ slot_
 
 // unnormalised new weights u[p]: ln(acc) for trainable parameters, the old weight for locked
 // parameters and for members of NONE-normalised transducers (cascade.h:339-350 save/load_none).
-__global__ void k_unnorm(uint32_t n_params, const double* __restrict__ acc, const double* __restrict__ ln_w,
+static __global__ void k_unnorm(uint32_t n_params, const double* __restrict__ acc, const double* __restrict__ ln_w,
                          const uint32_t* __restrict__ param_tie, const uint32_t* __restrict__ param_group,
                          double* __restrict__ u, double* __restrict__ old) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,7 +116,7 @@ __global__ void k_unnorm(uint32_t n_params, const double* __restrict__ acc, cons
 
 // normalize pass 1 (fst.cc:115-133): one warp per normalisation group.  Adds the group's additive
 // prior to EVERY member (the reference adds it to locked arcs' stored weight too), then sums.
-__global__ void k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+static __global__ void k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ group_off,
                             const uint32_t* __restrict__ group_members, const double* __restrict__ group_add,
                             const uint32_t* __restrict__ param_tie, double* __restrict__ u,
                             double* __restrict__ gsum, double* __restrict__ glocked) {
@@ -143,7 +143,7 @@ __global__ void k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ grou
 }
 
 // tie-group totals (fst.cc:134-152): one warp per tie id.
-__global__ void k_tie_totals(uint32_t n_ties, const uint32_t* __restrict__ tie_off,
+static __global__ void k_tie_totals(uint32_t n_ties, const uint32_t* __restrict__ tie_off,
                              const uint32_t* __restrict__ tie_members, const uint32_t* __restrict__ param_group,
                              const double* __restrict__ u, const double* __restrict__ gsum,
                              const double* __restrict__ glocked, double* __restrict__ tie_arc_total,
@@ -171,7 +171,7 @@ __global__ void k_tie_totals(uint32_t n_ties, const uint32_t* __restrict__ tie_o
 }
 
 // normalize pass 2 (fst.cc:160-229): one warp per group; writes the new ln weights.
-__global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+static __global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ group_off,
                               const uint32_t* __restrict__ group_members, const uint32_t* __restrict__ param_tie,
                               const double* __restrict__ u, const double* __restrict__ tie_arc_total,
                               const double* __restrict__ tie_state_total, const double* __restrict__ tie_max_locked,
@@ -216,14 +216,14 @@ __global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ gr
 }
 
 // parameters outside every normalisation group keep their unnormalised value (NONE method)
-__global__ void k_copy_ungrouped(uint32_t n_params, const uint32_t* __restrict__ param_group,
+static __global__ void k_copy_ungrouped(uint32_t n_params, const uint32_t* __restrict__ param_group,
                                  const double* __restrict__ u, double* __restrict__ ln_w) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n_params && param_group[p] == CML_NO_GROUP) ln_w[p] = u[p];
 }
 
 // over-relaxation (train.cc:157-171): w <- old * (em/old)^rate for unlocked arcs with old > 0
-__global__ void k_overrelax(uint32_t n_params, double rate, const uint32_t* __restrict__ param_tie,
+static __global__ void k_overrelax(uint32_t n_params, double rate, const uint32_t* __restrict__ param_tie,
                             const double* __restrict__ old, const double* __restrict__ ln_w, double* __restrict__ u) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_params) return;
@@ -234,7 +234,7 @@ __global__ void k_overrelax(uint32_t n_params, double rate, const uint32_t* __re
 
 // max |w_new - w_old| over unlocked parameters (train.cc:173-182), linear domain; result as the bit
 // pattern of a non-negative double (monotone under unsigned compare).
-__global__ void k_max_change(uint32_t n_params, const uint32_t* __restrict__ param_tie,
+static __global__ void k_max_change(uint32_t n_params, const uint32_t* __restrict__ param_tie,
                              const double* __restrict__ old, const double* __restrict__ ln_w,
                              unsigned long long* __restrict__ out) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -156,6 +156,16 @@ struct ModelArrays {
   std::vector<uint64_t> arc_key;
   uint32_t n_groups = 0, n_ties = 0, n_arcs = 0, n_params = 0;
 };
+// --crp options (graehl/shared/gibbs_opts.hpp:34-130, defaults :213-252)
+struct GibbsOpts {
+  bool enabled = false;
+  uint32_t iter = 0, burnin = 0;     // --crp[=n] / -M n ; --burnin=n
+  bool uniform_p0 = false, dirichlet_p0 = false, final_counts = false, exclude_prior = false;
+  double high_temp = 1, low_temp = 1;  // --high-temp= --low-temp=
+  uint64_t seed = 1;                 // --seed= : key of the counter-based uniforms
+  bool batched = false;              // --crp-batched : all blocks in parallel against the previous sweep's counts
+  std::string dump_samples_file;     // --dump-samples=file : final sample, arc-table ids per block
+};
 // sum-all-reduce of n doubles at device_ptr across the ranks of a multi-GPU run (NCCL, supplied by the driver)
 typedef void (*AllReduceFn)(void* user, void* device_ptr, uint64_t n_doubles);
 
@@ -172,6 +182,7 @@ struct TrainJob {
   Corpus corpus;
   std::vector<NormalizeMethod> methods;
   TrainOpts opt;
+  GibbsOpts gopt;
   bool flags[256] = {false};
   std::map<std::string, std::string> lopt;
   bool train_cascade = false;
@@ -187,7 +198,8 @@ struct TrainJob {
   ~TrainJob();
   void prepare();
   double estimate(double& ln_unweighted);
-  TrainResult const& run(std::ostream& log);
+  TrainResult const& run(std::ostream& log);        // EM (WFST::train)
+  TrainResult const& run_gibbs(std::ostream& log);  // --crp (WFST::train_gibbs)
   void write_back();
   void write_outputs(std::ostream& out);  // trained transducer(s) as carmel writes them
   void finish();

@@ -73,12 +73,25 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
     } else
       files.push_back(arg);
   }
-  const bool trainc = lopt.count("train-cascade") > 0;
+  // --crp forces -t and --train-cascade (carmel.cc:255-304 parse_gibbs_opts)
+  const bool crp = lopt.count("crp") > 0;
+  const bool trainc = lopt.count("train-cascade") > 0 || crp;
   job.train_cascade = trainc;
   if (trainc) flags[(unsigned)'t'] = true;
-  if (lopt.count("crp")) {
-    err << "carmel-b200: --crp Gibbs sampling is not available in this build\n";
-    return -11;
+  if (crp) {
+    GibbsOpts& g = job.gopt;
+    g.enabled = true;
+    g.iter = lopt["crp"].empty() ? topt.max_iter : (uint32_t)std::atol(lopt["crp"].c_str());
+    if (lopt.count("burnin")) g.burnin = (uint32_t)std::atol(lopt["burnin"].c_str());
+    g.uniform_p0 = lopt.count("uniform-p0") > 0;
+    g.dirichlet_p0 = lopt.count("dirichlet-p0") > 0;
+    g.final_counts = lopt.count("final-counts") > 0;
+    g.exclude_prior = lopt.count("crp-exclude-prior") > 0;
+    if (lopt.count("high-temp")) g.high_temp = std::atof(lopt["high-temp"].c_str());
+    if (lopt.count("low-temp")) g.low_temp = std::atof(lopt["low-temp"].c_str());
+    if (lopt.count("seed")) g.seed = std::strtoull(lopt["seed"].c_str(), nullptr, 10);
+    g.batched = lopt.count("crp-batched") > 0;
+    if (lopt.count("dump-samples")) g.dump_samples_file = lopt["dump-samples"];
   }
   if (!flags[(unsigned)'t']) {
     err << "carmel-b200 implements carmel's training path only: use -t (or --train-cascade)\n";
@@ -274,7 +287,10 @@ extern "C" int cml_job_stats(cml_job* j, cml_job_info* info) {
 }
 extern "C" int cml_job_train(cml_job* j) {
   return guarded(j, [&]() {
-    j->job.run(std::cerr);
+    if (j->job.gopt.enabled)
+      j->job.run_gibbs(std::cerr);
+    else
+      j->job.run(std::cerr);
     return (int)CML_OK;
   });
 }

@@ -60,7 +60,10 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
-    job.run(std::cerr);
+    if (job.gopt.enabled)
+      job.run_gibbs(std::cerr);
+    else
+      job.run(std::cerr);
     job.write_outputs(std::cout);
     return 0;
   } catch (std::exception& e) {

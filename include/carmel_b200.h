@@ -188,6 +188,43 @@ int cml_maximize(cml_ctx* ctx, double rate, double* max_delta);
 /* WFST::normalize of the current parameters only (train.cc:509 initial cascade.normalize) */
 int cml_normalize_params(cml_ctx* ctx);
 
+/* ---- --crp Gibbs sampling --------------------------------------------------------------------- *
+ * Replaces gibbs_base / gibbs_param (graehl/shared/gibbs.hpp:106-227,229-1079) and carmel_gibbs::
+ * resample_block + derivations::random_path (carmel/src/gibbs.cc:306-371, derivations.h:345-375).
+ * Parameters are the model's n_params (cml_set_model supplies the chains); lattices must be resident in
+ * one batch in the layered-CSR layout (fp64 log-space context), which keeps the reference's per-state arc
+ * order -- the order the sampler walks when it turns a uniform draw into an arc.
+ *   param_norm  [n_params] CRP normalisation group, or CML_NO_GROUP for a fixed probability (locked arc /
+ *               NONE-normalised transducer): then param_prior IS the probability (gibbs.cc:105-120)
+ *   param_prior [n_params] pseudo-count alpha*p0*N (gibbs.hpp:589-597)
+ * Uniform draws are counter based, u(seed, sweep, block, draw): one per visited non-final lattice state in
+ * path order (random.ipp:118), so sequential mode reproduces the CPU restatement derivation by derivation. */
+typedef struct cml_gibbs_model {
+  uint32_t n_params;
+  const uint32_t* param_norm;
+  const double* param_prior;
+  uint32_t n_norms;
+} cml_gibbs_model;
+enum cml_gibbs_mode {
+  CML_GIBBS_SEQUENTIAL = 0, /* exact collapsed sampler: blocks in corpus order, counts updated between blocks */
+  CML_GIBBS_BATCHED = 1     /* all blocks in parallel against the previous sweep's counts */
+};
+typedef struct cml_gibbs_sweep_opts {
+  int mode;
+  double power;          /* 1/temperature (gibbs.hpp:838-839) */
+  uint64_t seed;
+  uint32_t sweep;        /* iteration number: part of the uniform counter */
+  int init_from_params;  /* sample from the current cml_set_params weights (--init-em first sample, gibbs.cc:317-322) */
+  double accumulate_dt;  /* after the sweep add dt * count to the time-averaged counts (delta_sum.hpp:60-84) */
+} cml_gibbs_sweep_opts;
+int cml_gibbs_init(cml_ctx* ctx, const cml_gibbs_model* g); /* counts := priors (restore_p0, gibbs.hpp:618-623) */
+int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o);
+uint64_t cml_gibbs_sample_capacity(cml_ctx* ctx);
+/* current sample: path_len[example], and the arc-table ids of example e's path at path_arcs[base_e ..],
+ * base_e = sum of the lattice level counts of the examples before e */
+int cml_gibbs_get_samples(cml_ctx* ctx, uint32_t* path_len, uint32_t* path_arcs, uint64_t cap);
+int cml_gibbs_get_state(cml_ctx* ctx, double* count, double* cum, double* normsum);
+
 /* host access to the first n doubles of the reduce buffer (small control all-reduces) */
 int cml_reduce_buffer_write(cml_ctx* ctx, const double* src, uint64_t n);
 int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n);

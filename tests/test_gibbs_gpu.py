@@ -1,0 +1,102 @@
+"""`--crp` Gibbs sampling parity on the GPU.
+
+Sequential mode: product and oracle draw the same counter-based uniforms (seed, sweep, block, draw),
+so every sampled derivation must be IDENTICAL arc for arc, the per-sweep cache-model probability must
+agree to 1e-9 relative and the final (time-averaged) weights to 1e-6.  Batched mode is a different
+(parallel, stale-count) sampler: it is checked for self-consistency only (valid paths, finite
+probability, normalised weights)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import _ln_weight, compare_wfst_text, random_wfst, run, sample_pairs, stage
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli(native_lib):
+    from carmel_b200 import CLI_PATH
+    return CLI_PATH
+
+
+def _hist(path):
+    return [(int(r.split()[0]), float(r.split()[1])) for r in open(path) if r.strip()]
+
+
+def _samples(path):
+    return [ln.split() for ln in open(path)]
+
+
+def _both(cli, oracle_bin, tmp_path, args, files, trained):
+    rc, out, err = run(cli, [*args, f"--history={tmp_path}/h.p", f"--dump-samples={tmp_path}/s.p", *files])
+    assert rc == 0, err
+    got_trained = [open(f + ".trained").read() for f in trained]
+    rc, oout, oerr = run(oracle_bin, [*args, f"--history={tmp_path}/h.o", f"--dump-samples={tmp_path}/s.o", *files])
+    assert rc == 0, oerr
+    want_trained = [open(f + ".trained").read() for f in trained]
+    hp, ho = _hist(f"{tmp_path}/h.p"), _hist(f"{tmp_path}/h.o")
+    assert len(hp) == len(ho)
+    for (i, a), (j, b) in zip(hp, ho):
+        assert i == j and abs(a - b) <= 1e-9 * max(1.0, abs(b)), (i, a, b)
+    sp, so = _samples(f"{tmp_path}/s.p"), _samples(f"{tmp_path}/s.o")
+    assert sp == so
+    for g, w in zip(got_trained, want_trained):
+        compare_wfst_text(g, w, 1e-6)
+    return err
+
+
+@pytest.mark.parametrize("extra", [[], ["--burnin=3"], ["--final-counts"], ["--crp-exclude-prior"], ["--uniform-p0"],
+                                   ["--dirichlet-p0"], ["--high-temp=3", "--low-temp=1"]])
+def test_cipher_crp_sequential(cli, oracle_bin, tmp_path, extra):
+    data, wfsa, fst = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    err = _both(cli, oracle_bin, tmp_path, ["--crp", "-M", "8", "--priors=0,1e-2", "--seed=7", "-HJ", *extra],
+                [data, wfsa, fst], [wfsa, fst])
+    assert "Gibbs i=8" in err
+
+
+def test_tagging_crp_sequential(cli, oracle_bin, tmp_path):
+    data, fsa, fst = stage(tmp_path, "tagging.data", "tagging.fsa", "tagging.fst")
+    _both(cli, oracle_bin, tmp_path, ["--crp=5", "--burnin=2", "--priors=0.1,0.01", "--seed=3", "-HJ"], [data, fsa, fst],
+          [fsa, fst])
+
+
+def test_epron_crp_single_transducer(cli, oracle_bin, tmp_path):
+    fst, data = stage(tmp_path, "epron-jpron.fst", "epron-jpron.data")
+    _both(cli, oracle_bin, tmp_path, ["--crp", "-M", "6", "--priors=0.05", "--seed=11"], [data, fst], [fst])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_crp_sequential(cli, oracle_bin, tmp_path, seed):
+    rng = np.random.default_rng(1000 + seed)
+    ns = int(rng.integers(3, 7))
+    text, ins, outs, arcs = random_wfst(rng, n_states=ns, eps_rate=0.15, lock_rate=0.1, tie_rate=0.0)
+    fst = os.path.join(str(tmp_path), "r.fst")
+    open(fst, "w").write(text)
+    data = os.path.join(str(tmp_path), "r.data")
+    open(data, "w").write(sample_pairs(rng, arcs, ns, n_pairs=12, noise=0.0))
+    _both(cli, oracle_bin, tmp_path, ["--crp", "-M", "5", "--priors=0.02", f"--seed={seed}"], [data, fst], [fst])
+
+
+def test_cipher_crp_batched(cli, tmp_path):
+    data, wfsa, fst = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    rc, out, err = run(cli, ["--crp", "-M", "10", "--crp-batched", "--priors=0,1e-2", "--seed=5", "-HJ",
+                             f"--history={tmp_path}/h.p", f"--dump-samples={tmp_path}/s.p", data, wfsa, fst])
+    assert rc == 0, err
+    h = _hist(f"{tmp_path}/h.p")
+    assert len(h) == 11 and all(np.isfinite(v) and v < 0 for _, v in h)
+    # the sampler must move towards better samples than the initial (prior) draw
+    assert max(v for _, v in h[5:]) > h[0][1]
+    # every block sampled a path of the letter count of its line
+    lens = [len(s) for s in _samples(f"{tmp_path}/s.p")]
+    assert all(n > 0 for n in lens)
+    # trained channel rows are normalised
+    rows = {}
+    for m in re.finditer(r'\(0 \(0 ("[^"]*") ("[^"]*") ([^)\s]+)\)\)', open(fst + ".trained").read()):
+        rows[m.group(1)] = rows.get(m.group(1), 0.0) + math.exp(_ln_weight(m.group(3)))
+    assert len(rows) == 27
+    for k, v in rows.items():
+        assert abs(v - 1) < 1e-6, (k, v)
