@@ -7,6 +7,8 @@
 //   carmel_oracle [-t] [-HJ] [-M n] [-e w] [-X w] [-f w] [-U] [-j|-u] [-:] [-F out] [--train-cascade]
 //                 [--normby=JCN..] [--priors=a,b,..] [--dump-trellis=file] [--history=file]
 //                 [--time-estimate=K] corpus wfst [wfst ...]
+#include <functional>
+
 #include "carmel_oracle.hpp"
 #include "gibbs_oracle.hpp"
 #include <chrono>
@@ -216,6 +218,104 @@ int real_main(int argc, char** argv) {
     write_u32(o, n);
     write_u32(o, (uint32_t)tr.arcs.size());
     o << body.str();
+  }
+  if (lopt.count("fem-forest") || lopt.count("fem-norm") || lopt.count("fem-param")) {
+    // forest-em export of the cascade (cascade.h:34-166; carmel.cc:756-830): parameter ids are 1-based
+    // visit order over the cascade members; one forest per example with a derivation.
+    std::vector<WFST*> members;
+    if (cascade.trivial)
+      members.push_back(result);
+    else
+      for (auto& w : chain) members.push_back(w.get());
+    std::unordered_map<Arc const*, unsigned> aid;
+    unsigned next_id = 1;
+    for (WFST* w : members) w->visit_arcs([&](unsigned, Arc& a) { aid.emplace(&a, next_id++); });
+    if (lopt.count("fem-param")) {  // cascade.h:168-181 print_params
+      std::ofstream o(lopt["fem-param"]);
+      for (WFST* w : members) w->visit_arcs([&](unsigned, Arc& a) { o << fmt_weight(a.weight) << "\n"; });
+    }
+    if (lopt.count("fem-norm")) {  // cascade.h:85-117 fem_norms
+      std::ofstream o(lopt["fem-norm"]);
+      o << "(";
+      for (size_t i = 0; i < members.size(); ++i) {
+        o << "\n";
+        NormalizeMethod const& nm = methods[i < methods.size() ? i : methods.size() - 1];
+        if (nm.group == NONE) continue;
+        std::vector<std::vector<Arc*>> groups;
+        members[i]->norm_groups(nm.group, groups);
+        for (auto const& g : groups) {
+          o << '(';
+          for (Arc* a : g) o << ' ' << aid[a];
+          o << " )\n";
+        }
+      }
+      o << ")\n";
+    }
+    if (lopt.count("fem-forest")) {  // cascade.h:119-166 fem_deriv + graph.h:165-194 backrefs
+      std::ofstream o(lopt["fem-forest"]);
+      IOIndex io(*result);
+      for (auto const& e : corpus.examples) {
+        Derivations d;
+        d.in = e.in;
+        d.out = e.out;
+        d.weight = e.weight;
+        if (!d.compute(*result, io, tr.arcs)) continue;
+        struct BR {
+          unsigned uses = 0, id = 0;
+        };
+        std::vector<BR> br(d.g.size());
+        unsigned nextid = 1;
+        std::function<void(unsigned)> use = [&](unsigned s) {
+          if (br[s].uses++ > 0) {
+            br[s].id = nextid++;
+            return;
+          }
+          for (auto const& a : d.g[s]) use(a.dest);
+        };
+        use(0);
+        std::function<void(unsigned)> emit = [&](unsigned s) {
+          BR& b = br[s];
+          const bool backdef = b.uses > 1;
+          if (backdef) {
+            o << "#" << b.id;
+            b.uses = 0;
+          } else if (b.uses == 0) {
+            o << "#" << b.id;
+            return;
+          }
+          auto const& st = d.g[s];
+          const bool ornode = st.size() >= 2;
+          if (ornode) o << "(OR";
+          for (auto const& a : st) {
+            if (ornode) o << " ";
+            Arc* arc = tr.arcs.t[a.id].arc;
+            std::vector<Arc*> p;
+            if (cascade.trivial)
+              p.push_back(arc);
+            else
+              p = cascade.chains[arc->group];
+            const bool mid = a.dest != d.fin;
+            const bool nonleaf1 = backdef || (!p.empty() && (p.size() > 1 || mid));
+            if (nonleaf1) o << "(";
+            bool sp = false;
+            for (Arc* x : p) {
+              if (sp) o << ' ';
+              sp = true;
+              o << aid[x];
+            }
+            if (mid) {
+              if (sp) o << ' ';
+              emit(a.dest);
+            }
+            if (nonleaf1) o << ")";
+          }
+          if (ornode) o << ")";
+        };
+        emit(0);
+        o << "\n";
+      }
+    }
+    return 0;
   }
   if (lopt.count("dump-estimate")) {
     // one E-step at the initial (normalised) weights: arc-table ln weights, ln counts, per-example ln P

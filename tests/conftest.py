@@ -24,6 +24,16 @@ def oracle_bin():
 
 
 @pytest.fixture(scope="session")
+def forest_oracle_bin(oracle_bin):
+    """Path of the forest-em CPU oracle binary (same Makefile as carmel_oracle)."""
+    out = os.path.join(ROOT, "oracle", "_build", "forest_oracle")
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("forest_cli.cpp", "forest_oracle.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    return out
+
+
+@pytest.fixture(scope="session")
 def native_lib():
     """libcarmel_b200.so, (re)built in-tree if sources changed and nvcc is present."""
     from carmel_b200 import build as _b

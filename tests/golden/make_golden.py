@@ -35,6 +35,16 @@ def main():
     for f in ["span.spell.corpus", "span.spell.wfst"]:
         shutil.copyfile(os.path.join(REF, "test", f), os.path.join(HERE, f))
         os.chmod(os.path.join(HERE, f), 0o644)
+    # forest-em: sample INPUTS (forest-em ships no expected outputs) + the parse/print round-trip vectors
+    # of its unit test (forest-em/forest.hpp:1041-1048 test_forests[])
+    fdir = os.path.join(HERE, "forest")
+    os.makedirs(fdir, exist_ok=True)
+    for f in ["forest", "forests", "norm", "norm_and_forests", "best_forest", "best_norm", "best_weights"]:
+        shutil.copyfile(os.path.join(os.path.dirname(REF), "forest-em", "sample", f), os.path.join(fdir, f))
+        os.chmod(os.path.join(fdir, f), 0o644)
+    src = open(os.path.join(os.path.dirname(REF), "forest-em", "forest.hpp")).read()
+    m = re.search(r"test_forests\[\]\s*=\s*\{(.*?)\};", src, re.S)
+    json.dump(re.findall(r'"([^"]*)"', m.group(1)), open(os.path.join(fdir, "test_forests.json"), "w"), indent=1)
     trace = open(os.path.join(TUT, "commands.trace"), errors="replace").read().split("\n")
     runs = []  # every EM run in the log: starts at an "i=1" line
     for ln in trace:
