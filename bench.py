@@ -148,8 +148,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cipher", choices=["cipher", "hmm"])
-    ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
+    ap.add_argument("--workload", default="cipher", choices=["cipher", "hmm", "forest"])
+    ap.add_argument("--precision", type=int, default=None, choices=[32, 64],
+                    help="score precision (default 64 for cipher/hmm like carmel, 32 for forest like forest-em)")
     ap.add_argument("--space", default="scaled", choices=["scaled", "log"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="per-GPU corpus multiplier")
@@ -159,6 +160,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.precision is None:
+        a.precision = 32 if a.workload == "forest" else 64
+    if a.workload == "forest":  # forest-em inside-outside (configs[4]): see bench_forest.py
+        import bench_forest
+        if a.impl == "reference":
+            if rank == 0:
+                bench_forest.reference_arm(a)
+            return
+        return bench_forest.run(a, rank, world, local)
     metric = "em_iteration_trellis_arcs_per_sec"
     unit = "trellis arcs/s"
     wl_name = {"cipher": "configs[1] cipher decipherment: 27x27 channel o 27-state locked bigram LM, "

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libcarmel_b200.so")
 CLI_PATH = os.path.join(_HERE, "_build", "carmel-b200")
+FOREST_CLI_PATH = os.path.join(_HERE, "_build", "forest-em-b200")
 
 SPACE_LOG, SPACE_SCALED = 0, 1
 NO_GROUP = 0xFFFFFFFF

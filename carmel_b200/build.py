@@ -49,25 +49,43 @@ def _sources(dirpath: str) -> list[str]:
     return out
 
 
+FOREST_CLI = os.path.join(OUT, "forest-em-b200")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every source to an object (only when it or a header changed), link the shared library and the
+    two command lines (carmel-b200, forest-em-b200)."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OUT, exist_ok=True)
-    deps = _sources(CSRC) + [os.path.join(ROOT, "include", "carmel_b200.h"), os.path.abspath(__file__)]
-    if not force and _newer(LIB, deps) and _newer(CLI, deps):
+    obj_dir = os.path.join(OUT, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    all_src = _sources(CSRC) + [os.path.join(ROOT, "include", "carmel_b200.h"), os.path.abspath(__file__)]
+    if not force and _newer(LIB, all_src) and _newer(CLI, all_src) and _newer(FOREST_CLI, all_src):
         return LIB
     nvcc = _nvcc()
-    cu = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    headers = [f for f in all_src if f.endswith((".cuh", ".hpp", ".h", ".py"))]
     host = os.path.join(CSRC, "host")
-    host_cpp = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")] if os.path.isdir(host) else []
-    lib_cpp = [f for f in host_cpp if not f.endswith("main.cpp")]
-    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-o", LIB, *cu, *lib_cpp, "-lcudart"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
-    main = os.path.join(host, "main.cpp")
-    if os.path.exists(main):
-        cmd = ["g++", "-O3", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", CLI, main,
-               "-L", OUT, "-lcarmel_b200", "-Wl,-rpath,$ORIGIN"]
-        subprocess.run(cmd, check=True)
+    cu = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    host_cpp = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")]
+    mains = [f for f in host_cpp if f.endswith("main.cpp")]
+    lib_src = cu + [f for f in host_cpp if f not in mains]
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        if force or not _newer(obj, [src] + headers):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", "-I", os.path.join(ROOT, "include"), "-o", obj, src]
+            if verbose and src.endswith(".cu"):
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(lib_src))) as ex:
+        objs = list(ex.map(compile_one, lib_src))
+    subprocess.run([nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *objs, "-lcudart"], check=True)
+    for main, exe in ((os.path.join(host, "main.cpp"), CLI), (os.path.join(host, "forest_main.cpp"), FOREST_CLI)):
+        if os.path.exists(main):
+            subprocess.run(["g++", "-O3", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe, main,
+                            "-L", OUT, "-lcarmel_b200", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

@@ -1,0 +1,983 @@
+// cml_forest.cu -- forest-em's inside-outside E-step and NormalizeGroups M-step on the GPU (sm_100a).
+//
+// Reference path: FForest::inside_rec / compute_norm_outside /
+// visit_inside_norm_outside (forest-em/forest.hpp:326-491,636-697), FForests::estimate / maximize
+// (forest-em/forest-em.hpp:511-572,626-655), NormalizeGroups (graehl/shared/normalize.hpp:123-164).
+//
+// Layout in HBM.  A forest arrives as the reference's pre-order node array.  Here back references are
+// resolved (a shared node is ONE node with several parents), the real nodes are sorted by height
+// (leaves = 0; a parent is strictly higher than its children), and the hyperedges are stored as two
+// CSRs over that order: children (inside pass, ascending height) and parents (outside pass, descending
+// height).  Per node: label u32 (rule id, 0 = OR; bit 31 marks a "hot" rule), child_off u32, par_off u32;
+// per child/parent link: u32 node index (parent links carry the parent's OR flag in bit 31).
+//
+// Arithmetic.  inside[] is a natural log in fp32/fp64 with the reference's log-add (cutoff 16/36 nats,
+// sequential over the OR children in the reference's order).  The outside pass does not keep
+// norm_outside = outside/inside[root] (range of a log) but the posterior gamma[n] = inside[n]*norm_outside[n]
+// in [0, ~1], in linear space: AND parent -> child adds gamma[p]; OR parent -> child adds
+// gamma[p]*exp(inside[c]-inside[p]).  It is a pull over the parent CSR: no atomics, deterministic.
+// counts[rule] += gamma[n] for AND nodes: fp64 RED into an L2-resident table; rules that occur very
+// often are accumulated in 64 replicated slots first (see k_forest_fold) to keep one address from
+// serialising the whole GPU.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <thread>
+
+#include "cml_common.cuh"
+
+namespace {
+
+const uint32_t kHotBit = 0x80000000u;
+const int kHotCopies = 64;
+const int kWarpsPerCta = 4;
+const int kNWarpCls = 6;
+const uint32_t kWarpCaps[kNWarpCls] = {128, 256, 512, 1024, 2048, 4096};  // nodes per forest, shared memory classes
+const int kCtaThreads = 256;
+
+struct __align__(16) ForestDesc {
+  uint64_t node_base;  // first entry in label / child_off / par_off (n_nodes + 1 entries each, own sentinel)
+  uint64_t child_base, par_base;  // first link of this forest in child / par
+  uint64_t lvl_base;   // first entry (n_levels + 1) in lvl_off
+  uint32_t n_nodes, n_levels;
+  uint32_t index;      // forest number within its batch (for ln_inside)
+  uint32_t pad;
+};
+
+template <typename Real>
+struct FNum;
+template <>
+struct FNum<float> {
+  static __device__ __forceinline__ float ninf() { return -CUDART_INF_F; }
+  static __device__ __forceinline__ float cut() { return 16.f; }
+  static __device__ __forceinline__ float ex(float x) { return __expf(x); }
+  static __device__ __forceinline__ float exa(float x) { return expf(x); }
+  static __device__ __forceinline__ float l1p(float x) { return log1pf(x); }
+};
+template <>
+struct FNum<double> {
+  static __device__ __forceinline__ double ninf() { return -CUDART_INF; }
+  static __device__ __forceinline__ double cut() { return 36.; }
+  static __device__ __forceinline__ double ex(double x) { return exp(x); }
+  static __device__ __forceinline__ double exa(double x) { return exp(x); }
+  static __device__ __forceinline__ double l1p(double x) { return log1p(x); }
+};
+// logweight operator+ (graehl/shared/weight.h:765-801)
+template <typename Real>
+__device__ __forceinline__ Real ln_add(Real a, Real b) {
+  if (!(a > FNum<Real>::ninf())) return b;
+  if (!(b > FNum<Real>::ninf())) return a;
+  const Real d = a - b;
+  if (d > FNum<Real>::cut()) return a;
+  if (d < -FNum<Real>::cut()) return b;
+  return d < 0 ? b + FNum<Real>::l1p(FNum<Real>::exa(d)) : a + FNum<Real>::l1p(FNum<Real>::exa(-d));
+}
+
+struct ForestArgs {
+  const ForestDesc* desc;
+  const uint32_t* list;  // forests of this launch (indices into desc)
+  uint32_t n_list;
+  const uint32_t* label;
+  const uint32_t* child_off;
+  const uint32_t* par_off;
+  const uint32_t* child;
+  const uint32_t* par;
+  const uint32_t* lvl_off;
+  const void* lnw;          // Real[rulespace]
+  const uint32_t* hot_index;  // [rulespace] replica row of hot rules
+  double* counts;           // [rulespace]
+  double* hot;              // [kHotCopies][n_hot]
+  uint32_t n_hot;
+  double* ln_inside;        // per forest of the batch
+  void* scratch;            // CTA class: Real[2 * scratch_stride] per block
+  uint64_t scratch_stride;
+  uint32_t cap;             // warp classes: node capacity per warp
+};
+
+template <int NT>
+__device__ __forceinline__ void fsync() {
+  if (NT == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
+// One forest by one group of NT threads.  in_/ga: NT-shared arrays of n_nodes values (shared or global).
+template <typename Real, int NT>
+__device__ void forest_inside_outside(const ForestArgs& A, const ForestDesc& d, Real* __restrict__ in_, Real* __restrict__ ga,
+                                      int lane, uint32_t replica) {
+  const uint32_t* __restrict__ label = A.label + d.node_base;
+  const uint32_t* __restrict__ coff = A.child_off + d.node_base;
+  const uint32_t* __restrict__ poff = A.par_off + d.node_base;
+  const uint32_t* __restrict__ child = A.child + d.child_base;
+  const uint32_t* __restrict__ par = A.par + d.par_base;
+  const uint32_t* __restrict__ lvl = A.lvl_off + d.lvl_base;
+  const Real* __restrict__ lnw = (const Real*)A.lnw;
+  const uint32_t nl = d.n_levels;
+  const Real NI = FNum<Real>::ninf();
+  // ---- inside: ascending height (forest.hpp:636-697) ------------------------------------------------
+  for (uint32_t L = 0; L < nl; ++L) {
+    const uint32_t i1 = __ldg(&lvl[L + 1]);
+    for (uint32_t i = __ldg(&lvl[L]) + lane; i < i1; i += NT) {
+      const uint32_t lab = __ldg(&label[i]) & ~kHotBit;
+      uint32_t c = __ldg(&coff[i]);
+      const uint32_t c1 = __ldg(&coff[i + 1]);
+      Real v;
+      if (lab) {  // AND: rule weight times the children
+        v = __ldg(&lnw[lab]);
+        for (; c < c1; ++c) v += in_[__ldg(&child[c])];
+      } else {    // OR: first child, then fold the rest in order
+        v = in_[__ldg(&child[c])];
+        for (++c; c < c1; ++c) v = ln_add<Real>(v, in_[__ldg(&child[c])]);
+      }
+      in_[i] = v;
+    }
+    fsync<NT>();
+  }
+  const uint32_t root = d.n_nodes - 1;  // the only node of the top level
+  const Real in_root = in_[root];
+  if (lane == 0) A.ln_inside[d.index] = (double)in_root;
+  if (!(in_root > NI)) return;  // zero-probability forest: no counts (forest.hpp:447-451)
+  // ---- outside as posteriors, descending height, pull over parents (forest.hpp:439-491) -------------
+  for (uint32_t L = nl; L-- > 0;) {
+    const uint32_t i1 = __ldg(&lvl[L + 1]);
+    for (uint32_t i = __ldg(&lvl[L]) + lane; i < i1; i += NT) {
+      Real g = i == root ? Real(1) : Real(0);
+      const Real in_i = in_[i];
+      uint32_t k = __ldg(&poff[i]);
+      const uint32_t k1 = __ldg(&poff[i + 1]);
+      for (; k < k1; ++k) {
+        const uint32_t e = __ldg(&par[k]);
+        const uint32_t p = e & ~kHotBit;
+        const Real gp = ga[p];
+        if (e & kHotBit) {  // OR parent: share of this alternative
+          if (in_i > NI && gp > 0) g += gp * FNum<Real>::ex(in_i - in_[p]);
+        } else
+          g += gp;          // AND parent: every child is used whenever the parent is
+      }
+      ga[i] = g;
+      const uint32_t lab = __ldg(&label[i]);
+      if ((lab & ~kHotBit) && g > 0) {
+        if (lab & kHotBit)
+          atomicAdd(A.hot + (size_t)replica * A.n_hot + __ldg(&A.hot_index[lab & ~kHotBit]), (double)g);
+        else
+          atomicAdd(A.counts + lab, (double)g);
+      }
+    }
+    fsync<NT>();
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_forest_warp(ForestArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Real* in_ = (Real*)smem_raw + (size_t)warp * 2 * A.cap;
+  Real* ga = in_ + A.cap;
+  const uint32_t gw = blockIdx.x * kWarpsPerCta + warp, nw = gridDim.x * kWarpsPerCta;
+  for (uint32_t f = gw; f < A.n_list; f += nw) {
+    const ForestDesc d = A.desc[A.list[f]];
+    forest_inside_outside<Real, 32>(A, d, in_, ga, lane, gw & (kHotCopies - 1));
+    __syncwarp();
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kCtaThreads) k_forest_cta(ForestArgs A) {
+  Real* in_ = (Real*)A.scratch + (size_t)blockIdx.x * 2 * A.scratch_stride;
+  Real* ga = in_ + A.scratch_stride;
+  for (uint32_t f = blockIdx.x; f < A.n_list; f += gridDim.x) {
+    const ForestDesc d = A.desc[A.list[f]];
+    forest_inside_outside<Real, kCtaThreads>(A, d, in_, ga, threadIdx.x, blockIdx.x & (kHotCopies - 1));
+    __syncthreads();
+  }
+}
+
+// mark hot rules in the node labels (bit 31); idempotent
+__global__ void k_forest_mark_hot(uint64_t n, uint32_t* __restrict__ label, const uint32_t* __restrict__ hot_index) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t lab = label[i] & ~kHotBit;
+  label[i] = (lab && hot_index[lab] != 0xFFFFFFFFu) ? (lab | kHotBit) : lab;
+}
+__global__ void k_forest_fold(uint32_t n_hot, const uint32_t* __restrict__ hot_rule, const double* __restrict__ hot,
+                              double* __restrict__ counts) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hot) return;
+  double s = 0;
+#pragma unroll 8
+  for (int k = 0; k < kHotCopies; ++k) s += hot[(size_t)k * n_hot + h];
+  if (s != 0.) atomicAdd(&counts[hot_rule[h]], s);
+}
+// sum of ln inside over non-zero forests (forest-em.hpp:519-527): one block, fixed order => deterministic
+__global__ void k_forest_sum(const double* __restrict__ ln_inside, uint64_t n, double* __restrict__ scal) {
+  __shared__ double s_sum[256];
+  __shared__ double s_zero[256];
+  double s = 0, z = 0;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = ln_inside[i];
+    if (v > -CUDART_INF)
+      s += v;
+    else
+      z += 1;
+  }
+  s_sum[threadIdx.x] = s;
+  s_zero[threadIdx.x] = z;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_zero[threadIdx.x] += s_zero[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    scal[0] += s_sum[0];
+    scal[1] += s_zero[0];
+    scal[2] += (double)n;
+  }
+}
+template <typename Real>
+__global__ void k_forest_cast_w(uint64_t n, const double* __restrict__ ln_w, Real* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (Real)ln_w[i];
+}
+// NormalizeGroups::operator()(Group&) (normalize.hpp:123-164): one warp per group.
+// src = counts + prior (linear) or exp(ln_w) when counts == nullptr (normalize in place).
+__global__ void k_forest_norm(uint64_t n_groups, const uint64_t* __restrict__ goff, const uint64_t* __restrict__ gmem,
+                              const double* __restrict__ counts, double prior, double add_k, int zero_mode,
+                              double* __restrict__ ln_w, double* __restrict__ gdiff, uint64_t* __restrict__ gidx) {
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  const uint64_t b = goff[g], e = goff[g + 1];
+  double sum = 0;
+  for (uint64_t k = b + lane; k < e; k += 32) {
+    const uint64_t r = gmem[k];
+    sum += counts ? counts[r] + prior : exp(ln_w[r]);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  double best = -1;
+  uint64_t best_k = ~0ull;
+  if (sum > 0) {
+    const double ln_den = log(sum + add_k);
+    for (uint64_t k = b + lane; k < e; k += 32) {
+      const uint64_t r = gmem[k];
+      const double c = counts ? counts[r] + prior : exp(ln_w[r]);
+      const double prev = ln_w[r];
+      const double nw = c > 0 ? log(c) - ln_den : -CUDART_INF;
+      ln_w[r] = nw;
+      const double diff = fabs(exp(nw) - exp(prev));
+      if (diff > best) {
+        best = diff;
+        best_k = k;
+      }
+    }
+  } else if (zero_mode != CML_FOREST_SKIP) {
+    const double setto = zero_mode == CML_FOREST_UNIFORM ? -log((double)(e - b)) : -CUDART_INF;
+    for (uint64_t k = b + lane; k < e; k += 32) {
+      const uint64_t r = gmem[k];
+      const double diff = fabs(exp(setto) - exp(ln_w[r]));
+      ln_w[r] = setto;
+      if (diff > best) {
+        best = diff;
+        best_k = k;
+      }
+    }
+  }
+  // first maximum in member order (the reference keeps the first strictly larger difference)
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const uint64_t ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob > best || (ob == best && ok < best_k)) {
+      best = ob;
+      best_k = ok;
+    }
+  }
+  if (lane == 0) {
+    gdiff[g] = best;
+    gidx[g] = best_k;
+  }
+}
+// final reduction over groups: largest difference, ties -> first group
+__global__ void k_forest_maxdiff(uint64_t n_groups, const double* __restrict__ gdiff, const uint64_t* __restrict__ gidx,
+                                 const uint64_t* __restrict__ gmem, double* __restrict__ out_diff,
+                                 unsigned long long* __restrict__ out_rule) {
+  __shared__ double s_d[256];
+  __shared__ uint64_t s_g[256];
+  double best = 0;  // maxdiff starts at zero and needs a strictly larger difference (normalize.hpp:258)
+  uint64_t bg = ~0ull;
+  for (uint64_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
+    const double d = gdiff[g];
+    if (d > best || (d == best && d > 0 && g < bg)) {
+      best = d;
+      bg = g;
+    }
+  }
+  s_d[threadIdx.x] = best;
+  s_g[threadIdx.x] = bg;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double d = s_d[threadIdx.x + o];
+      const uint64_t g = s_g[threadIdx.x + o];
+      if (d > s_d[threadIdx.x] || (d == s_d[threadIdx.x] && g < s_g[threadIdx.x])) {
+        s_d[threadIdx.x] = d;
+        s_g[threadIdx.x] = g;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *out_diff = s_d[0];
+    *out_rule = s_g[0] == ~0ull ? 0ull : (unsigned long long)gmem[gidx[s_g[0]]];
+  }
+}
+
+struct ForestBatch {
+  uint64_t n_forests = 0, n_nodes = 0, n_links = 0, n_hyperedges = 0, max_nodes = 0;
+  DevArray<ForestDesc> desc;
+  DevArray<uint32_t> label, child_off, par_off, child, par, lvl_off, list;
+  DevArray<double> ln_inside;
+  uint32_t cls_begin[kNWarpCls + 2] = {0};  // warp classes, then the CTA class
+  DevArray<unsigned char> scratch;
+  uint64_t scratch_stride = 0;
+  uint32_t cta_grid = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint32_t n_kernels = 0;
+  ~ForestBatch() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
+};
+
+}  // namespace
+
+struct cml_forests {
+  int device = 0, precision = 32;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = CML_SM_COUNT_FALLBACK;
+  size_t smem_optin = 0;
+  std::string err;
+  uint64_t launches = 0;
+  bool have_rules = false, have_params = false, hot_dirty = true, pending = false;
+  uint64_t rulespace = 0, n_groups = 0;
+  DevArray<uint64_t> group_off, group_members;
+  DevArray<double> ln_w, reduce, gdiff, out_diff;
+  DevArray<uint64_t> gidx;
+  DevArray<unsigned long long> out_rule;
+  DevArray<unsigned char> w_real;
+  std::vector<uint64_t> rule_occ;
+  DevArray<uint32_t> hot_index, hot_rule;
+  DevArray<double> hot;
+  uint32_t n_hot = 0;
+  std::vector<std::unique_ptr<ForestBatch>> batches;
+};
+
+#define ctx f
+#define F_REQUIRE(cond, code, msg) \
+  do {                             \
+    if (!(cond)) {                 \
+      f->err = (msg);              \
+      return (code);               \
+    }                              \
+  } while (0)
+
+static thread_local std::string g_forest_create_err;
+static inline unsigned f_cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+extern "C" int cml_forests_create(cml_forests** out, int device, int precision) {
+  if (!out || (precision != 32 && precision != 64)) {
+    g_forest_create_err = "cml_forests_create: precision must be 32 or 64";
+    return CML_ERR_ARG;
+  }
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+    g_forest_create_err = "cml_forests_create: no usable CUDA device " + std::to_string(device) +
+                          " (carmel_b200 has no CPU fallback)";
+    return CML_ERR_CUDA;
+  }
+  std::unique_ptr<cml_forests> f(new cml_forests());
+  f->device = device;
+  f->precision = precision;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_forest_create_err = "cml_forests_create: cannot initialise the device";
+    return CML_ERR_CUDA;
+  }
+  f->own_stream = true;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    f->sm_count = prop.multiProcessorCount;
+    f->smem_optin = prop.sharedMemPerBlockOptin;
+  }
+  *out = f.release();
+  return CML_OK;
+}
+extern "C" void cml_forests_destroy(cml_forests* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  cudaStreamSynchronize(f->stream);
+  f->batches.clear();
+  if (f->own_stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+extern "C" const char* cml_forests_last_error(cml_forests* f) { return f ? f->err.c_str() : g_forest_create_err.c_str(); }
+extern "C" int cml_forests_set_stream(cml_forests* f, void* s) {
+  if (!f) return CML_ERR_ARG;
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  if (f->own_stream) cudaStreamDestroy(f->stream);
+  f->stream = (cudaStream_t)s;
+  f->own_stream = false;
+  return CML_OK;
+}
+extern "C" uint64_t cml_forests_launch_count(cml_forests* f) { return f ? f->launches : 0; }
+
+extern "C" int cml_forests_set_rules(cml_forests* f, uint64_t rulespace, uint64_t n_groups, const uint64_t* group_off,
+                                     const uint64_t* group_members) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(rulespace >= 1 && rulespace < 0x7fffffffull, CML_ERR_ARG, "cml_forests_set_rules: rulespace out of range");
+  F_REQUIRE(f->batches.empty(), CML_ERR_STATE, "cml_forests_set_rules: forests already added");
+  F_REQUIRE(n_groups == 0 || (group_off && group_members), CML_ERR_ARG, "cml_forests_set_rules: null groups");
+  std::vector<char> seen(rulespace, 0);
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    F_REQUIRE(group_off[g] <= group_off[g + 1], CML_ERR_ARG, "cml_forests_set_rules: group offsets not monotone");
+    for (uint64_t k = group_off[g]; k < group_off[g + 1]; ++k)
+      F_REQUIRE(group_members[k] < rulespace, CML_ERR_ARG, "cml_forests_set_rules: group member beyond rulespace");
+  }
+  CML_CUDA(cudaSetDevice(f->device));
+  const uint64_t n_mem = n_groups ? group_off[n_groups] : 0;
+  static const uint64_t zero_off[1] = {0};
+  CML_CUDA(f->group_off.upload(n_groups ? group_off : zero_off, n_groups + 1, f->stream));
+  CML_CUDA(f->group_members.upload(group_members, n_mem, f->stream));
+  CML_CUDA(f->ln_w.alloc(rulespace));
+  CML_CUDA(f->w_real.alloc(rulespace * (f->precision == 64 ? 8 : 4)));
+  CML_CUDA(f->reduce.alloc(rulespace + 3));
+  CML_CUDA(cudaMemsetAsync(f->reduce.p, 0, (rulespace + 3) * sizeof(double), f->stream));
+  CML_CUDA(f->gdiff.alloc(std::max<uint64_t>(1, n_groups)));
+  CML_CUDA(f->gidx.alloc(std::max<uint64_t>(1, n_groups)));
+  CML_CUDA(f->out_diff.alloc(1));
+  CML_CUDA(f->out_rule.alloc(1));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  f->rulespace = rulespace;
+  f->n_groups = n_groups;
+  f->rule_occ.assign(rulespace, 0);
+  f->have_rules = true;
+  f->have_params = false;
+  f->hot_dirty = true;
+  return CML_OK;
+}
+extern "C" int cml_forests_set_params(cml_forests* f, const double* ln_w) {
+  if (!f || !ln_w) return CML_ERR_ARG;
+  F_REQUIRE(f->have_rules, CML_ERR_STATE, "cml_forests_set_params before cml_forests_set_rules");
+  CML_CUDA(cudaSetDevice(f->device));
+  CML_CUDA(cudaMemcpyAsync(f->ln_w.p, ln_w, f->rulespace * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  f->have_params = true;
+  return CML_OK;
+}
+extern "C" int cml_forests_get_params(cml_forests* f, double* ln_w) {
+  if (!f || !ln_w) return CML_ERR_ARG;
+  F_REQUIRE(f->have_params, CML_ERR_STATE, "cml_forests_get_params before cml_forests_set_params");
+  CML_CUDA(cudaSetDevice(f->device));
+  CML_CUDA(cudaMemcpyAsync(ln_w, f->ln_w.p, f->rulespace * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  return CML_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side layout: pre-order node arrays -> height-sorted hyperedge CSRs
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct FlatForest {
+  uint32_t n_real = 0, n_levels = 0;
+  uint64_t n_links = 0, n_he = 0;
+  int error = 0;  // 1 malformed, 2 cycle, 3 rule id out of range
+};
+struct ForestScratch {
+  std::vector<uint32_t> height, order, newid, stack, it, cnt;
+  std::vector<char> color;
+};
+// pass 1: validate, heights, counts.  `real_of[i]` for pre-order node i = i or the target of a back reference.
+void forest_pass1(uint32_t n, const uint32_t* next, const uint32_t* label, const uint8_t* backref, uint64_t rulespace,
+                  ForestScratch& S, FlatForest& ff) {
+  ff = FlatForest();
+  if (n == 0 || backref[0] || next[0] != n) {
+    ff.error = 1;
+    return;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (next[i] <= i || next[i] > n) {
+      ff.error = 1;
+      return;
+    }
+    if (backref[i]) {
+      if (label[i] >= n || backref[label[i]] || next[i] != i + 1) {
+        ff.error = 1;
+        return;
+      }
+    } else {
+      if (label[i] >= rulespace) {
+        ff.error = 3;
+        return;
+      }
+      if (label[i] == 0 && next[i] == i + 1) {  // OR without children
+        ff.error = 1;
+        return;
+      }
+    }
+  }
+  // children of real node p: b = p+1; while b < next[p]: (backref ? label[b] : b); b = next[b]
+  S.height.assign(n, 0);
+  S.color.assign(n, 0);
+  S.stack.clear();
+  S.it.assign(n, 0);  // resume position (pre-order index of the next child to look at)
+  S.stack.push_back(0);
+  S.color[0] = 1;
+  S.it[0] = 1;
+  while (!S.stack.empty()) {
+    const uint32_t p = S.stack.back();
+    uint32_t b = S.it[p];
+    if (b < next[p]) {
+      if (next[b] > next[p]) {  // child sticks out of its parent
+        ff.error = 1;
+        return;
+      }
+      S.it[p] = next[b];
+      const uint32_t c = backref[b] ? label[b] : b;
+      ++ff.n_links;
+      if (S.color[c] == 1) {
+        ff.error = 2;
+        return;
+      }
+      if (S.color[c] == 0) {
+        S.color[c] = 1;
+        S.it[c] = c + 1;
+        S.stack.push_back(c);
+      }
+    } else {
+      uint32_t h = 0;
+      for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+        const uint32_t c = backref[q] ? label[q] : q;
+        h = std::max(h, S.height[c] + 1);
+      }
+      S.height[p] = h;
+      S.color[p] = 2;
+      S.stack.pop_back();
+    }
+  }
+  uint32_t n_real = 0, maxh = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (!backref[i]) {
+      if (S.color[i] != 2) {  // a shared definition that is never reached cannot happen in pre-order text
+        ff.error = 1;
+        return;
+      }
+      ++n_real;
+      maxh = std::max(maxh, S.height[i]);
+      if (label[i]) ++ff.n_he;
+    }
+  ff.n_real = n_real;
+  ff.n_levels = maxh + 1;
+}
+}  // namespace
+
+extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
+  if (!f || !b) return CML_ERR_ARG;
+  F_REQUIRE(f->have_rules, CML_ERR_STATE, "cml_forests_add before cml_forests_set_rules");
+  F_REQUIRE(!f->pending, CML_ERR_STATE, "cml_forests_add while an estimate is pending");
+  F_REQUIRE(b->n_forests == 0 || (b->node_off && b->next && b->label && b->backref), CML_ERR_ARG, "cml_forests_add: null array");
+  if (b->n_forests == 0) return CML_OK;
+  const uint64_t nf = b->n_forests;
+  for (uint64_t i = 0; i < nf; ++i) {
+    F_REQUIRE(b->node_off[i] < b->node_off[i + 1], CML_ERR_ARG, "cml_forests_add: empty forest");
+    F_REQUIRE(b->node_off[i + 1] - b->node_off[i] < 0x7fffffffull, CML_ERR_ARG, "cml_forests_add: forest too large");
+  }
+  CML_CUDA(cudaSetDevice(f->device));
+  unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (nf < 64) nt = 1;
+  std::vector<FlatForest> ff(nf);
+  {
+    std::atomic<uint64_t> nextf(0);
+    auto work = [&]() {
+      ForestScratch S;
+      for (;;) {
+        const uint64_t i0 = nextf.fetch_add(64);
+        if (i0 >= nf) break;
+        for (uint64_t i = i0; i < std::min(nf, i0 + 64); ++i) {
+          const uint64_t o = b->node_off[i];
+          forest_pass1((uint32_t)(b->node_off[i + 1] - o), b->next + o, b->label + o, b->backref + o, f->rulespace, S, ff[i]);
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  std::unique_ptr<ForestBatch> bt(new ForestBatch());
+  std::vector<uint64_t> node_base(nf + 1, 0), link_base(nf + 1, 0), lvl_base(nf + 1, 0);
+  for (uint64_t i = 0; i < nf; ++i) {
+    if (ff[i].error) {
+      f->err = "cml_forests_add: forest " + std::to_string(i) +
+               (ff[i].error == 2 ? " has a cyclic back reference" : ff[i].error == 3 ? " uses a rule id beyond rulespace" : " is malformed");
+      return ff[i].error == 2 ? CML_ERR_CYCLE : CML_ERR_ARG;
+    }
+    node_base[i + 1] = node_base[i] + ff[i].n_real + 1;
+    link_base[i + 1] = link_base[i] + ff[i].n_links;
+    lvl_base[i + 1] = lvl_base[i] + ff[i].n_levels + 1;
+    bt->n_nodes += ff[i].n_real;
+    bt->n_links += ff[i].n_links;
+    bt->n_hyperedges += ff[i].n_he;
+    bt->max_nodes = std::max<uint64_t>(bt->max_nodes, ff[i].n_real);
+  }
+  F_REQUIRE(link_base[nf] < 0xffffffffull * 64, CML_ERR_ARG, "cml_forests_add: batch too large");
+  bt->n_forests = nf;
+  std::vector<ForestDesc> desc(nf);
+  std::vector<uint32_t> h_label(node_base[nf]), h_coff(node_base[nf]), h_poff(node_base[nf]), h_child(std::max<uint64_t>(1, link_base[nf])),
+      h_par(std::max<uint64_t>(1, link_base[nf])), h_lvl(lvl_base[nf]);
+  std::vector<std::vector<uint64_t>> occ_parts(nt);
+  {
+    std::atomic<uint64_t> nextf(0);
+    auto work = [&](unsigned tid) {
+      ForestScratch S;
+      std::vector<uint64_t>& occ = occ_parts[tid];
+      occ.assign(f->rulespace, 0);
+      for (;;) {
+        const uint64_t i0 = nextf.fetch_add(64);
+        if (i0 >= nf) break;
+        for (uint64_t fi = i0; fi < std::min(nf, i0 + 64); ++fi) {
+          const uint64_t o = b->node_off[fi];
+          const uint32_t n = (uint32_t)(b->node_off[fi + 1] - o);
+          const uint32_t* next = b->next + o;
+          const uint32_t* label = b->label + o;
+          const uint8_t* backref = b->backref + o;
+          FlatForest fx;
+          forest_pass1(n, next, label, backref, f->rulespace, S, fx);  // recompute heights (cheap, keeps pass 1 memory small)
+          const uint32_t nr = fx.n_real, nl = fx.n_levels;
+          // counting sort by height, stable in pre-order
+          S.cnt.assign(nl + 1, 0);
+          for (uint32_t i = 0; i < n; ++i)
+            if (!backref[i]) ++S.cnt[S.height[i] + 1];
+          for (uint32_t L = 0; L < nl; ++L) S.cnt[L + 1] += S.cnt[L];
+          uint32_t* lvl = h_lvl.data() + lvl_base[fi];
+          for (uint32_t L = 0; L <= nl; ++L) lvl[L] = S.cnt[L];
+          S.newid.assign(n, 0);
+          S.order.assign(nr, 0);
+          for (uint32_t i = 0; i < n; ++i)
+            if (!backref[i]) {
+              const uint32_t id = S.cnt[S.height[i]]++;
+              S.newid[i] = id;
+              S.order[id] = i;
+            }
+          uint32_t* lab = h_label.data() + node_base[fi];
+          uint32_t* coff = h_coff.data() + node_base[fi];
+          uint32_t* poff = h_poff.data() + node_base[fi];
+          uint32_t* child = h_child.data() + link_base[fi];
+          uint32_t* par = h_par.data() + link_base[fi];
+          // children CSR in the new order; parent in-degrees
+          std::fill(poff, poff + nr + 1, 0u);
+          uint32_t nc = 0;
+          for (uint32_t id = 0; id < nr; ++id) {
+            const uint32_t p = S.order[id];
+            lab[id] = label[p];
+            if (label[p]) ++occ[label[p]];
+            coff[id] = nc;
+            for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+              const uint32_t c = S.newid[backref[q] ? label[q] : q];
+              child[nc++] = c;
+              ++poff[c + 1];
+            }
+          }
+          coff[nr] = nc;
+          lab[nr] = 0;
+          for (uint32_t id = 0; id < nr; ++id) poff[id + 1] += poff[id];
+          S.it.assign(nr, 0);
+          for (uint32_t id = 0; id < nr; ++id) {  // parents in increasing internal order => deterministic sums
+            const uint32_t flag = lab[id] ? 0u : kHotBit;
+            for (uint32_t k = coff[id]; k < coff[id + 1]; ++k) {
+              const uint32_t c = child[k];
+              par[poff[c] + S.it[c]++] = id | flag;
+            }
+          }
+          ForestDesc& d = desc[fi];
+          d.node_base = node_base[fi];
+          d.child_base = d.par_base = link_base[fi];
+          d.lvl_base = lvl_base[fi];
+          d.n_nodes = nr;
+          d.n_levels = nl;
+          d.index = (uint32_t)fi;
+          d.pad = 0;
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+  }
+  for (auto const& occ : occ_parts)
+    for (uint64_t r = 0; r < occ.size(); ++r) f->rule_occ[r] += occ[r];
+  // classes: smallest shared-memory capacity that fits, else the CTA class
+  const size_t real_b = f->precision == 64 ? 8 : 4;
+  std::vector<std::vector<uint32_t>> by_cls(kNWarpCls + 1);
+  for (uint64_t i = 0; i < nf; ++i) {
+    int c = kNWarpCls;
+    for (int k = 0; k < kNWarpCls; ++k)
+      if (desc[i].n_nodes <= kWarpCaps[k] && (size_t)kWarpsPerCta * 2 * kWarpCaps[k] * real_b <= f->smem_optin) {
+        c = k;
+        break;
+      }
+    by_cls[c].push_back((uint32_t)i);
+  }
+  std::vector<uint32_t> list;
+  for (int c = 0; c <= kNWarpCls; ++c) {
+    bt->cls_begin[c] = (uint32_t)list.size();
+    // largest first: the tail of a class is then made of short forests
+    std::stable_sort(by_cls[c].begin(), by_cls[c].end(), [&](uint32_t a, uint32_t x) { return desc[a].n_nodes > desc[x].n_nodes; });
+    list.insert(list.end(), by_cls[c].begin(), by_cls[c].end());
+  }
+  bt->cls_begin[kNWarpCls + 1] = (uint32_t)list.size();
+  const uint32_t n_cta = bt->cls_begin[kNWarpCls + 1] - bt->cls_begin[kNWarpCls];
+  if (n_cta) {
+    bt->scratch_stride = (bt->max_nodes + 31) & ~31ull;
+    bt->cta_grid = std::min<uint32_t>(n_cta, 2 * f->sm_count);
+    CML_CUDA(bt->scratch.alloc((size_t)bt->cta_grid * 2 * bt->scratch_stride * real_b));
+  }
+  CML_CUDA(bt->desc.upload(desc.data(), desc.size(), f->stream));
+  CML_CUDA(bt->label.upload(h_label.data(), h_label.size(), f->stream));
+  CML_CUDA(bt->child_off.upload(h_coff.data(), h_coff.size(), f->stream));
+  CML_CUDA(bt->par_off.upload(h_poff.data(), h_poff.size(), f->stream));
+  CML_CUDA(bt->child.upload(h_child.data(), link_base[nf], f->stream));
+  CML_CUDA(bt->par.upload(h_par.data(), link_base[nf], f->stream));
+  CML_CUDA(bt->lvl_off.upload(h_lvl.data(), h_lvl.size(), f->stream));
+  CML_CUDA(bt->list.upload(list.data(), list.size(), f->stream));
+  CML_CUDA(bt->ln_inside.alloc(nf));
+  CML_CUDA(cudaEventCreate(&bt->ev0));
+  CML_CUDA(cudaEventCreate(&bt->ev1));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  f->batches.push_back(std::move(bt));
+  f->hot_dirty = true;
+  return CML_OK;
+}
+
+extern "C" int cml_forests_totals(cml_forests* f, uint64_t* n_forests, uint64_t* n_nodes, uint64_t* n_hyperedges, uint64_t* n_links) {
+  if (!f) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0, d = 0;
+  for (auto const& bt : f->batches) {
+    a += bt->n_forests;
+    b += bt->n_nodes;
+    c += bt->n_hyperedges;
+    d += bt->n_links;
+  }
+  if (n_forests) *n_forests = a;
+  if (n_nodes) *n_nodes = b;
+  if (n_hyperedges) *n_hyperedges = c;
+  if (n_links) *n_links = d;
+  return CML_OK;
+}
+
+static int forest_rebuild_hot(cml_forests* f) {
+  uint64_t min_occ = 4096;
+  uint32_t max_hot = 8192;
+  if (const char* e = getenv("CML_FOREST_HOT_MIN_OCC")) min_occ = std::strtoull(e, nullptr, 10);
+  if (const char* e = getenv("CML_FOREST_HOT_MAX")) max_hot = (uint32_t)std::strtoul(e, nullptr, 10);
+  std::vector<uint32_t> hot_rule;
+  for (uint64_t r = 1; r < f->rulespace; ++r)
+    if (f->rule_occ[r] >= min_occ) hot_rule.push_back((uint32_t)r);
+  if (hot_rule.size() > max_hot) {
+    std::partial_sort(hot_rule.begin(), hot_rule.begin() + max_hot, hot_rule.end(),
+                      [&](uint32_t a, uint32_t b) { return f->rule_occ[a] > f->rule_occ[b] || (f->rule_occ[a] == f->rule_occ[b] && a < b); });
+    hot_rule.resize(max_hot);
+  }
+  std::vector<uint32_t> hot_index(f->rulespace, 0xFFFFFFFFu);
+  for (size_t h = 0; h < hot_rule.size(); ++h) hot_index[hot_rule[h]] = (uint32_t)h;
+  f->n_hot = (uint32_t)hot_rule.size();
+  CML_CUDA(f->hot_index.upload(hot_index.data(), hot_index.size(), f->stream));
+  CML_CUDA(f->hot_rule.upload(hot_rule.data(), hot_rule.size(), f->stream));
+  CML_CUDA(f->hot.alloc(std::max<size_t>(1, (size_t)kHotCopies * f->n_hot)));
+  for (auto& bt : f->batches) {
+    k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
+    ++f->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  f->hot_dirty = false;
+  return CML_OK;
+}
+
+template <typename Real>
+static int forest_launch(cml_forests* f, ForestBatch& bt) {
+  ForestArgs A{};
+  A.desc = bt.desc.p;
+  A.label = bt.label.p;
+  A.child_off = bt.child_off.p;
+  A.par_off = bt.par_off.p;
+  A.child = bt.child.p;
+  A.par = bt.par.p;
+  A.lvl_off = bt.lvl_off.p;
+  A.lnw = f->w_real.p;
+  A.hot_index = f->hot_index.p;
+  A.counts = f->reduce.p;
+  A.hot = f->hot.p;
+  A.n_hot = f->n_hot;
+  A.ln_inside = bt.ln_inside.p;
+  bt.n_kernels = 0;
+  CML_CUDA(cudaEventRecord(bt.ev0, f->stream));
+  for (int c = 0; c < kNWarpCls; ++c) {
+    const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];
+    if (!n) continue;
+    A.list = bt.list.p + bt.cls_begin[c];
+    A.n_list = n;
+    A.cap = kWarpCaps[c];
+    const size_t smem = (size_t)kWarpsPerCta * 2 * A.cap * sizeof(Real);
+    if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(k_forest_warp<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a few forests per warp so the short tail of the (size-sorted) class balances the long head
+    const unsigned grid = std::max(1u, std::min(f_cdiv(n, kWarpsPerCta), (unsigned)f->sm_count * 16u));
+    k_forest_warp<Real><<<grid, kWarpsPerCta * 32, smem, f->stream>>>(A);
+    ++f->launches;
+    ++bt.n_kernels;
+  }
+  {
+    const uint32_t n = bt.cls_begin[kNWarpCls + 1] - bt.cls_begin[kNWarpCls];
+    if (n) {
+      A.list = bt.list.p + bt.cls_begin[kNWarpCls];
+      A.n_list = n;
+      A.scratch = bt.scratch.p;
+      A.scratch_stride = bt.scratch_stride;
+      k_forest_cta<Real><<<bt.cta_grid, kCtaThreads, 0, f->stream>>>(A);
+      ++f->launches;
+      ++bt.n_kernels;
+    }
+  }
+  CML_CUDA(cudaEventRecord(bt.ev1, f->stream));
+  CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
+extern "C" int cml_forests_estimate_launch(cml_forests* f) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(f->have_params, CML_ERR_STATE, "cml_forests_estimate before cml_forests_set_params");
+  CML_CUDA(cudaSetDevice(f->device));
+  if (f->hot_dirty) {
+    const int rc = forest_rebuild_hot(f);
+    if (rc) return rc;
+  }
+  if (f->precision == 64)
+    k_forest_cast_w<double><<<f_cdiv(f->rulespace, 256), 256, 0, f->stream>>>(f->rulespace, f->ln_w.p, (double*)f->w_real.p);
+  else
+    k_forest_cast_w<float><<<f_cdiv(f->rulespace, 256), 256, 0, f->stream>>>(f->rulespace, f->ln_w.p, (float*)f->w_real.p);
+  ++f->launches;
+  CML_CUDA(cudaMemsetAsync(f->reduce.p, 0, (f->rulespace + 3) * sizeof(double), f->stream));
+  if (f->n_hot) CML_CUDA(cudaMemsetAsync(f->hot.p, 0, (size_t)kHotCopies * f->n_hot * sizeof(double), f->stream));
+  for (auto& bt : f->batches) {
+    const int rc = f->precision == 64 ? forest_launch<double>(f, *bt) : forest_launch<float>(f, *bt);
+    if (rc) return rc;
+    k_forest_sum<<<1, 256, 0, f->stream>>>(bt->ln_inside.p, bt->n_forests, f->reduce.p + f->rulespace);
+    ++f->launches;
+  }
+  if (f->n_hot) {
+    k_forest_fold<<<f_cdiv(f->n_hot, 128), 128, 0, f->stream>>>(f->n_hot, f->hot_rule.p, f->hot.p, f->reduce.p);
+    ++f->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  f->pending = true;
+  return CML_OK;
+}
+extern "C" int cml_forests_estimate_finish(cml_forests* f, cml_forest_estimate_result* out) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(f->pending, CML_ERR_STATE, "cml_forests_estimate_finish without a launched estimate");
+  CML_CUDA(cudaSetDevice(f->device));
+  double scal[3];
+  CML_CUDA(cudaMemcpyAsync(scal, f->reduce.p + f->rulespace, sizeof(scal), cudaMemcpyDeviceToHost, f->stream));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  f->pending = false;
+  if (out) {
+    out->sum_ln_p = scal[0];
+    out->n_zero = (uint64_t)(scal[1] + 0.5);
+    out->n_forests = (uint64_t)(scal[2] + 0.5);
+  }
+  return CML_OK;
+}
+extern "C" int cml_forests_estimate(cml_forests* f, cml_forest_estimate_result* out) {
+  const int rc = cml_forests_estimate_launch(f);
+  if (rc) return rc;
+  return cml_forests_estimate_finish(f, out);
+}
+extern "C" int cml_forests_last_time_ms(cml_forests* f, float* ms, uint32_t* n_kernels) {
+  if (!f) return CML_ERR_ARG;
+  float total = 0;
+  uint32_t nk = 0;
+  for (auto& bt : f->batches) {
+    float t = 0;
+    CML_CUDA(cudaEventSynchronize(bt->ev1));
+    CML_CUDA(cudaEventElapsedTime(&t, bt->ev0, bt->ev1));
+    total += t;
+    nk += bt->n_kernels;
+  }
+  if (ms) *ms = total;
+  if (n_kernels) *n_kernels = nk;
+  return CML_OK;
+}
+extern "C" int cml_forests_get_inside(cml_forests* f, double* ln_inside, uint64_t n) {
+  if (!f || !ln_inside) return CML_ERR_ARG;
+  CML_CUDA(cudaSetDevice(f->device));
+  uint64_t o = 0;
+  for (auto& bt : f->batches) {
+    F_REQUIRE(o + bt->n_forests <= n, CML_ERR_ARG, "cml_forests_get_inside: buffer too small");
+    CML_CUDA(cudaMemcpyAsync(ln_inside + o, bt->ln_inside.p, bt->n_forests * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    o += bt->n_forests;
+  }
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  return CML_OK;
+}
+extern "C" int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n) {
+  if (!f || !counts) return CML_ERR_ARG;
+  F_REQUIRE(f->have_rules && n >= f->rulespace, CML_ERR_ARG, "cml_forests_get_counts: buffer too small");
+  CML_CUDA(cudaSetDevice(f->device));
+  CML_CUDA(cudaMemcpyAsync(counts, f->reduce.p, f->rulespace * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  return CML_OK;
+}
+extern "C" int cml_forests_reduce_buffer(cml_forests* f, void** p, uint64_t* n) {
+  if (!f || !p || !n) return CML_ERR_ARG;
+  F_REQUIRE(f->have_rules, CML_ERR_STATE, "cml_forests_reduce_buffer before cml_forests_set_rules");
+  *p = f->reduce.p;
+  *n = f->rulespace + 3;
+  return CML_OK;
+}
+
+static int forest_norm(cml_forests* f, const double* counts, double prior, double add_k, int zero_mode, double* max_delta,
+                       uint64_t* max_index) {
+  CML_CUDA(cudaSetDevice(f->device));
+  if (f->n_groups) {
+    k_forest_norm<<<f_cdiv(f->n_groups * 32, 256), 256, 0, f->stream>>>(f->n_groups, f->group_off.p, f->group_members.p, counts, prior,
+                                                                     add_k, zero_mode, f->ln_w.p, f->gdiff.p, f->gidx.p);
+    ++f->launches;
+  }
+  k_forest_maxdiff<<<1, 256, 0, f->stream>>>(f->n_groups, f->gdiff.p, f->gidx.p, f->group_members.p, f->out_diff.p, f->out_rule.p);
+  ++f->launches;
+  CML_CUDA(cudaGetLastError());
+  double d = 0;
+  unsigned long long r = 0;
+  CML_CUDA(cudaMemcpyAsync(&d, f->out_diff.p, sizeof(d), cudaMemcpyDeviceToHost, f->stream));
+  CML_CUDA(cudaMemcpyAsync(&r, f->out_rule.p, sizeof(r), cudaMemcpyDeviceToHost, f->stream));
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  if (max_delta) *max_delta = d;
+  if (max_index) *max_index = r;
+  return CML_OK;
+}
+extern "C" int cml_forests_maximize(cml_forests* f, const cml_forest_norm_opts* o, double* max_delta, uint64_t* max_index) {
+  if (!f || !o) return CML_ERR_ARG;
+  F_REQUIRE(f->have_params, CML_ERR_STATE, "cml_forests_maximize before cml_forests_set_params");
+  F_REQUIRE(!f->pending, CML_ERR_STATE, "cml_forests_maximize while an estimate is pending");
+  return forest_norm(f, f->reduce.p, o->prior_total, o->add_k, o->zero_mode, max_delta, max_index);
+}
+extern "C" int cml_forests_normalize_params(cml_forests* f) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(f->have_params, CML_ERR_STATE, "cml_forests_normalize_params before cml_forests_set_params");
+  return forest_norm(f, nullptr, 0., 0., CML_FOREST_UNIFORM, nullptr, nullptr);
+}

@@ -1,0 +1,97 @@
+// forest_host.hpp -- host side of the forest-em path: file formats, options and the EM driver
+// (overrelaxed_em), with everything numeric handed to the CUDA library through the C ABI
+// (include/carmel_b200.h, cml_forests_*).  Mirrors, without sharing data structures:
+//   forests  "(OR #1(1 2) #1 (3 4))"     forest-em/forest.hpp:39-46,135-242 (reader), :245-320 (printer)
+//   normalization groups "((1 2) (3 4))"  graehl/shared/normalize.hpp:58-65
+//   parameters, one weight per line       forest-em/forest-em.hpp:190-201,228-250
+//   options                               forest-em/forest-em-params.hpp:69-176
+//   EM driver                             graehl/shared/em.hpp:107-216 ; forest-em/forest-em.hpp:556-655
+#pragma once
+#include <cstdint>
+#include <iosfwd>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "carmel_b200.h"
+
+namespace cb {
+
+// all forests of a corpus in the C ABI's layout (cml_forest_batch): pre-order node arrays, back to back
+struct ForestSet {
+  std::vector<uint64_t> node_off{0};
+  std::vector<uint32_t> next, label;
+  std::vector<uint8_t> backref;
+  uint64_t max_ruleid = 0, max_nodes = 0;
+  uint64_t size() const { return node_off.size() - 1; }
+  uint64_t n_nodes() const { return next.size(); }
+  // parses forests until the end of the buffer; throws std::runtime_error with the forest number on errors
+  void read(const char* begin, const char* end);
+  void print(std::ostream& o, uint64_t f) const;
+};
+
+struct NormGroupsHost {
+  std::vector<uint64_t> off{0}, members;
+  uint64_t max_index = 0;
+  uint64_t size() const { return off.size() - 1; }
+  // parses "((1 2) (3))" and returns the position after the closing paren
+  const char* read(const char* begin, const char* end);
+};
+
+struct ForestOpts {
+  std::string forests_file, normgroups_file, initparam_file, outparam_file, outcounts_file, outinside_file, history_file,
+      print_forests_file;
+  unsigned max_iter = 1000;            // -i  (forest-em-params.hpp:185)
+  double converge_ratio = 1. / 65536;  // -e  (:186)
+  double converge_delta = 0;           // -d  (:187)
+  double prior_counts = 0;             // -p
+  double add_k_smoothing = 0;          // -k
+  bool zero_zerocounts = false;        // -z
+  bool initial_1_params = false;       // -u
+  bool normalize_initial = false;      // -N
+  bool double_precision = false;       // -U
+  bool human_probs = false;            // -H
+  unsigned log_level = 1;              // -L
+  int device = 0;                      // --gpu=n
+  int shard_rank = 0, shard_count = 1;  // --shard=r/N
+  bool parse_only = false;             // --parse-only : read (and --print-forests) without touching the GPU
+};
+
+struct ForestIter {
+  unsigned iter;
+  double avg_logprob, max_delta;
+  uint64_t max_index, n;
+};
+
+typedef void (*ForestAllReduceFn)(void* user, void* device_ptr, uint64_t n_doubles);
+
+struct ForestJob {
+  ForestOpts opt;
+  ForestSet forests;
+  NormGroupsHost groups;
+  std::vector<double> ln_w;  // [rulespace]; index 0 unused
+  bool have_init_params = false;
+  uint64_t rulespace = 0, count_space = 0;
+  uint64_t total_forests = 0;  // whole corpus (all shards)
+  uint64_t shard_begin = 0, shard_end = 0;
+  ForestAllReduceFn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  cml_forests* ctx = nullptr;
+  bool prepared = false, firsttime = true;
+  std::vector<ForestIter> history;
+  double best_alp = 0;
+  uint64_t last_n_zero = 0;
+
+  ~ForestJob();
+  void load();     // read the files named in opt
+  void prepare();  // rules, parameters and this shard's forests onto the GPU
+  double estimate(bool first_time, std::ostream& log, uint64_t* n_used = nullptr);
+  void maximize(std::ostream& log, double& max_delta, uint64_t& max_index);
+  double run(std::ostream& log);  // overrelaxed_em
+  void write_outputs(std::ostream& log);
+  void ok(int rc) const;
+};
+// forest-em's argv (the training subset); returns 0 or forest-em's exit code 1 with the message on `err`
+int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostream& err);
+
+}  // namespace cb

@@ -108,3 +108,155 @@ def head_corpus(src: str, dst: str, n_pairs: int) -> int:
             g.write(b)
             k += 1
     return k
+
+
+# ---------------------------------------------------------------------------------------------------
+# forest-em workload (configs[4]: random binary-branching AND/OR derivation forests)
+# ---------------------------------------------------------------------------------------------------
+def _forest_template(rng, depth: int, share: float):
+    """one random forest shape as pre-order arrays (next, kind, backref target); kind 0 = OR, 1 = AND, 2 = backref.
+    OR fan-out U[2,4]; AND arity {1:.3, 2:.6, 3:.1}; `share` of the children are references to an earlier subforest."""
+    nxt, kind, target = [], [], []
+    shareable = []
+
+    def node_and(d):
+        i = len(nxt)
+        nxt.append(0)
+        kind.append(1)
+        target.append(0)
+        if d > 0 and rng.random() >= 0.12:
+            for _ in range(int(rng.choice([1, 2, 3], p=[0.3, 0.6, 0.1]))):
+                child(d - 1)
+        nxt[i] = len(nxt)
+        return i
+
+    def node_or(d):
+        i = len(nxt)
+        nxt.append(0)
+        kind.append(0)
+        target.append(0)
+        for _ in range(int(rng.integers(2, 5))):
+            node_and(d)
+        nxt[i] = len(nxt)
+        return i
+
+    def child(d):
+        if shareable and rng.random() < share:
+            i = len(nxt)
+            nxt.append(i + 1)
+            kind.append(2)
+            target.append(shareable[int(rng.integers(0, len(shareable)))])
+            return
+        i = node_or(d) if rng.random() < 0.7 else node_and(d)
+        if nxt[i] > i + 1:
+            shareable.append(i)
+
+    node_or(depth)
+    return np.array(nxt, np.uint32), np.array(kind, np.uint8), np.array(target, np.uint32)
+
+
+def make_forests(n_forests: int = 100000, n_rules: int = 1000000, seed: int = 20260105, templates: int = 512,
+                 target_hyperedges: int = 500, zipf: float = 1.0, group_seed: int = 20260105) -> dict:
+    """Synthetic forest corpus in the C ABI's layout (cml_forest_batch) plus normalization groups of size U[2,50]
+    covering every rule.  Shapes come from `templates` random forests (depth 6-12, about `target_hyperedges` AND nodes
+    each); every forest draws its own rule ids, Zipf(`zipf`) over `n_rules`."""
+    rng = np.random.default_rng(seed)
+    shapes = []
+    tries = 0
+    while len(shapes) < templates and tries < 40 * templates:
+        tries += 1
+        t = _forest_template(rng, depth=int(rng.integers(4, 8)), share=0.15)
+        he = int((t[1] == 1).sum())
+        if target_hyperedges * 0.4 <= he <= target_hyperedges * 1.8:
+            shapes.append(t)
+    if not shapes:
+        raise RuntimeError("no forest template of the requested size")
+    pick = rng.integers(0, len(shapes), n_forests)
+    sizes = np.array([len(s[0]) for s in shapes], np.uint64)
+    node_off = np.zeros(n_forests + 1, np.uint64)
+    np.cumsum(sizes[pick], out=node_off[1:])
+    total = int(node_off[-1])
+    nxt = np.empty(total, np.uint32)
+    label = np.empty(total, np.uint32)
+    backref = np.empty(total, np.uint8)
+    # fill template by template (vectorised over the forests that use it)
+    for s, (t_next, t_kind, t_target) in enumerate(shapes):
+        fs = np.nonzero(pick == s)[0]
+        if not len(fs):
+            continue
+        idx = (node_off[fs][:, None] + np.arange(len(t_next), dtype=np.uint64)[None, :]).astype(np.int64)
+        nxt[idx] = t_next[None, :]
+        backref[idx] = (t_kind == 2)[None, :]
+        lab = np.where(t_kind == 2, t_target, 0).astype(np.uint32)
+        label[idx] = lab[None, :]
+    # AND nodes: recover from the templates
+    is_and = np.empty(total, bool)
+    for s, (t_next, t_kind, t_target) in enumerate(shapes):
+        fs = np.nonzero(pick == s)[0]
+        if not len(fs):
+            continue
+        idx = (node_off[fs][:, None] + np.arange(len(t_next), dtype=np.uint64)[None, :]).astype(np.int64)
+        is_and[idx] = (t_kind == 1)[None, :]
+    and_pos = np.nonzero(is_and)[0]
+    ranks = np.arange(1, n_rules + 1, dtype=np.float64) ** -zipf
+    cdf = np.cumsum(ranks / ranks.sum())
+    ids = np.searchsorted(cdf, rng.random(len(and_pos)), side="right").astype(np.uint32)
+    perm = rng.permutation(n_rules).astype(np.uint32)  # frequent rules are scattered over the id space
+    label[and_pos] = 1 + perm[np.minimum(ids, n_rules - 1)]
+    # normalization groups: consecutive runs of a random permutation of the rule ids (own seed: every rank of a
+    # multi-GPU run must see the same groups whatever forests it generated)
+    grng = np.random.default_rng(group_seed)
+    order = 1 + grng.permutation(n_rules).astype(np.uint64)
+    gsz = grng.integers(2, 51, size=n_rules // 2 + 1)
+    goff = np.concatenate([[0], np.cumsum(gsz)])
+    goff = goff[goff < n_rules]
+    goff = np.concatenate([goff, [n_rules]]).astype(np.uint64)
+    return {"node_off": node_off, "next": nxt, "label": label, "backref": backref, "n_rules": n_rules, "rulespace": n_rules + 1,
+            "group_off": goff, "group_members": order, "hyperedges": int(len(and_pos)), "nodes": total,
+            "templates": len(shapes)}
+
+
+def forest_text(fs: dict, f: int) -> str:
+    """forest f of make_forests() in forest-em's text syntax"""
+    b, e = int(fs["node_off"][f]), int(fs["node_off"][f + 1])
+    nxt, label, backref = fs["next"][b:e], fs["label"][b:e], fs["backref"][b:e]
+    n = e - b
+    ids = {}
+    for p in range(n):
+        if backref[p] and int(label[p]) not in ids:
+            ids[int(label[p])] = len(ids) + 1
+    out, ends = [], [n]
+    for p in range(n):
+        while p == ends[-1] and len(ends) > 1:
+            out.append(")")
+            ends.pop()
+        if p:
+            out.append(" ")
+        if p in ids:
+            out.append(f"#{ids[p]}")
+        if backref[p]:
+            out.append(f"#{ids[int(label[p])]}")
+        elif nxt[p] == p + 1:
+            out.append(f"({label[p]})" if p in ids else str(label[p]))
+        else:
+            out.append("(" + (str(label[p]) if label[p] else "OR"))
+            ends.append(int(nxt[p]))
+    out.append(")" * (len(ends) - 1))
+    return "".join(out)
+
+
+def write_forests(fs: dict, outdir: str, n_forests: int | None = None) -> dict:
+    """write the first n forests + the normalization groups as forest-em input files"""
+    os.makedirs(outdir, exist_ok=True)
+    n = len(fs["node_off"]) - 1 if n_forests is None else min(n_forests, len(fs["node_off"]) - 1)
+    with open(os.path.join(outdir, "forests"), "w") as o:
+        for f in range(n):
+            o.write(forest_text(fs, f))
+            o.write("\n")
+    go, gm = fs["group_off"], fs["group_members"]
+    with open(os.path.join(outdir, "norm"), "w") as o:
+        o.write("(")
+        for g in range(len(go) - 1):
+            o.write("(" + " ".join(str(int(x)) for x in gm[int(go[g]):int(go[g + 1])]) + ")\n")
+        o.write(")\n")
+    return {"forests": os.path.join(outdir, "forests"), "norm": os.path.join(outdir, "norm"), "n_forests": n}

@@ -254,6 +254,79 @@ int cml_job_train(cml_job* job);   /* the EM loop to convergence; trained weight
 int cml_job_write(cml_job* job);   /* stdout / -F file / <input>.trained, as carmel writes them */
 int cml_job_stats(cml_job* job, cml_job_info* info);
 
+/* ---- forest-em: inside-outside EM over derivation forests -------------------------------------- *
+ * Replaces FForest::compute_inside / compute_norm_outside / visit_inside_norm_outside
+ * (forest-em/forest.hpp:326-491,636-697), FForests::estimate / maximize (forest-em/forest-em.hpp:
+ * 511-572,626-655) and NormalizeGroups::normalize (graehl/shared/normalize.hpp:123-164,254-267).
+ * Forests cross the boundary in the reference's own representation (forest.hpp:60-76): a pre-order node
+ * array per forest; the library resolves back references, levelises by height and lays the hyperedges
+ * out for the GPU itself.  Rule ids are the reference's 1-based parameter ids (0 is reserved for OR).
+ * Scores are fp32 (forest-em's default) or fp64 (-U) natural logs; expected counts are accumulated
+ * linearly in fp64.  One handle per GPU, not thread-safe per handle. */
+typedef struct cml_forests cml_forests;
+typedef struct cml_forest_batch {
+  uint64_t n_forests;
+  const uint64_t* node_off; /* [n_forests+1] forest f owns nodes [node_off[f], node_off[f+1]) */
+  const uint32_t* next;     /* per node: in-forest index one past its last descendant (ForestNode::next) */
+  const uint32_t* label;    /* rule id (>0), 0 = OR, or the in-forest index of the shared node (back reference) */
+  const uint8_t* backref;   /* per node: 1 = label is a back reference (ForestNode::is_backref) */
+} cml_forest_batch;
+typedef struct cml_forest_estimate_result {
+  double sum_ln_p;     /* sum over non-zero forests of ln inside[root]   (forest-em.hpp:519-527) */
+  uint64_t n_zero;     /* forests with inside[root] == 0 */
+  uint64_t n_forests;  /* forests visited (this GPU) */
+} cml_forest_estimate_result;
+enum cml_forest_zero_mode { CML_FOREST_ZERO = 0, CML_FOREST_SKIP = 1, CML_FOREST_UNIFORM = 2 }; /* normalize.hpp:113 */
+typedef struct cml_forest_norm_opts {
+  double prior_total;   /* added to every rule's count: prior_counts * total_forests (forest-em.hpp:448-449) */
+  double add_k;         /* added to the denominator of non-empty groups (normalize.hpp:133) */
+  int zero_mode;        /* groups whose counts sum to 0 */
+} cml_forest_norm_opts;
+
+int cml_forests_create(cml_forests** out, int device, int precision /* 32 | 64 */);
+void cml_forests_destroy(cml_forests* f);
+const char* cml_forests_last_error(cml_forests* f);
+int cml_forests_set_stream(cml_forests* f, void* cuda_stream);
+uint64_t cml_forests_launch_count(cml_forests* f);
+/* rulespace = 1 + largest rule id; groups = the normalization groups file ((1 2 3) (4 5)) as CSR of rule ids */
+int cml_forests_set_rules(cml_forests* f, uint64_t rulespace, uint64_t n_groups, const uint64_t* group_off,
+                          const uint64_t* group_members);
+int cml_forests_set_params(cml_forests* f, const double* ln_w /* [rulespace] */);
+int cml_forests_get_params(cml_forests* f, double* ln_w);
+int cml_forests_add(cml_forests* f, const cml_forest_batch* b);
+int cml_forests_totals(cml_forests* f, uint64_t* n_forests, uint64_t* n_nodes, uint64_t* n_hyperedges, uint64_t* n_links);
+/* E-step over all resident forests.  Afterwards the reduce buffer holds
+ * [rulespace linear counts (no prior) | sum_ln_p | n_zero | n_forests] for an optional all-reduce. */
+int cml_forests_estimate(cml_forests* f, cml_forest_estimate_result* out);
+int cml_forests_estimate_launch(cml_forests* f);                               /* asynchronous half */
+int cml_forests_estimate_finish(cml_forests* f, cml_forest_estimate_result* out); /* reads the (reduced) buffer */
+int cml_forests_last_time_ms(cml_forests* f, float* ms, uint32_t* n_kernels);  /* inside-outside kernels only */
+int cml_forests_get_inside(cml_forests* f, double* ln_inside, uint64_t n);     /* per forest, in the order added */
+int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n);        /* linear, [rulespace] */
+int cml_forests_reduce_buffer(cml_forests* f, void** device_ptr, uint64_t* n_doubles);
+/* M-step: rule_weights <- normalised (counts + prior_total).  max_delta / max_index as NormalizeGroups
+ * reports them (largest absolute change of a probability and the rule it belongs to). */
+int cml_forests_maximize(cml_forests* f, const cml_forest_norm_opts* o, double* max_delta, uint64_t* max_index);
+int cml_forests_normalize_params(cml_forests* f); /* --normalize-initial: weights normalised in place */
+
+/* A whole forest-em run (forest-em/forest-em-params.cpp:62-148): argv follows forest-em's options
+ * (forest-em-params.hpp:69-176; the training subset).  Extra: --gpu=n, --shard=r/N,
+ * --history=file. */
+typedef struct cml_forest_job cml_forest_job;
+typedef struct cml_forest_job_info {
+  uint64_t forests, nodes, hyperedges, links, rulespace, iterations;
+  double best_avg_logprob;
+} cml_forest_job_info;
+int cml_forest_job_open(cml_forest_job** out, int argc, const char* const* argv);
+void cml_forest_job_close(cml_forest_job* job);
+const char* cml_forest_job_error(cml_forest_job* job);
+int cml_forest_job_set_allreduce(cml_forest_job* job, cml_allreduce_fn fn, void* user);
+int cml_forest_job_prepare(cml_forest_job* job);
+cml_forests* cml_forest_job_context(cml_forest_job* job);
+int cml_forest_job_train(cml_forest_job* job);
+int cml_forest_job_write(cml_forest_job* job);
+int cml_forest_job_stats(cml_forest_job* job, cml_forest_job_info* info);
+
 /* ---- host-side helpers exported for bindings and tests (no GPU needed) ------------------------ */
 /* Every symbol this header declares, for the loader test. */
 const char* const* cml_exported_symbols(size_t* n);

@@ -469,7 +469,7 @@ struct Forests {
       rule_weights.assign(rulespace, W());
       norm_groups.init_uniform(rule_weights);
     }
-    counts.assign(std::max(rulespace, rule_weights.size()), W());
+    counts.assign(rulespace, W());  // forest-em.hpp:362 counts.alloc(rulespace)
     firsttime = true;
     iteration = 0;
   }

@@ -1,0 +1,154 @@
+"""forest-em parity on the GPU through the product command line
+forest-em-b200 (host C++ -> C ABI cml_forests_* -> CUDA) against the CPU oracle and the golden log.
+
+Tolerances (north_star): average log-likelihood per iteration and learned weights within 1e-6 relative with
+-U (fp64 scores), 1e-4 in the default fp32 mode (forest-em's own default precision)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from forest_helpers import parse_ln, random_forest, random_normgroups, read_weights
+from helpers import GOLDEN, golden, run, stage
+
+pytestmark = pytest.mark.gpu
+FDIR = os.path.join(GOLDEN, "forest")
+MODES = [(["-U"], 1e-6), ([], 1e-4)]
+
+
+@pytest.fixture(scope="module")
+def fem(native_lib):
+    from carmel_b200 import FOREST_CLI_PATH
+    return FOREST_CLI_PATH
+
+
+def _hist(path):
+    return [(int(r[0]), float(r[1]), float(r[2]), int(r[3]), int(r[4])) for r in (ln.split() for ln in open(path)) if r]
+
+
+def _close_ln(a, b, rel, floor=-60.0):
+    if a == b:
+        return True
+    if a < floor and b < floor:  # both negligible probabilities / counts
+        return True
+    return abs(math.expm1(a - b)) <= rel if abs(a - b) < 1 else False
+
+
+def _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel, check_index=True):
+    d = str(tmp_path)
+    rc, out, err = run(fem, [*mode, *args, "-o", f"{d}/p.w", "-O", f"{d}/p.c", "-S", f"{d}/p.s", f"--history={d}/p.h"])
+    assert rc == 0, err
+    rc, out, oerr = run(forest_oracle_bin, [*mode, *args, "-o", f"{d}/o.w", "-O", f"{d}/o.c", "-S", f"{d}/o.s", f"--history={d}/o.h"])
+    assert rc == 0, oerr
+    hp, ho = _hist(f"{d}/p.h"), _hist(f"{d}/o.h")
+    assert len(hp) == len(ho), (len(hp), len(ho), err[-2000:])
+    for a, b in zip(hp, ho):
+        assert a[0] == b[0] and a[4] == b[4], (a, b)
+        assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (a, b)
+        assert abs(a[2] - b[2]) <= 20 * rel * max(1.0, abs(b[2])) + 1e-12, (a, b)
+        if check_index and rel <= 1e-6 and b[2] > 1e-3:
+            assert a[3] == b[3], (a, b)
+    # per-forest ln inside: in fp32 both sides carry the rounding of intermediate logs that are much larger in
+    # magnitude than the result (sums over thousands of derivations), so the float-vs-float bound is looser
+    for name, tol in (("w", 20 * rel), ("c", 20 * rel), ("s", rel if rel <= 1e-6 else 10 * rel)):
+        got, want = read_weights(f"{d}/p.{name}"), read_weights(f"{d}/o.{name}")
+        assert len(got) == len(want), (name, len(got), len(want))
+        for i, (a, b) in enumerate(zip(got, want)):
+            if name == "s":
+                assert (a == b) or abs(a - b) <= tol * max(1.0, abs(b)), (name, i, a, b)
+            else:
+                assert _close_ln(a, b, tol), (name, i + 1, a, b)
+    return err
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_sample_forests(fem, forest_oracle_bin, tmp_path, mode, rel):
+    args = ["-f", os.path.join(FDIR, "forests"), "-n", os.path.join(FDIR, "norm"), "-i", "12"]
+    err = _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel)
+    assert "i=12: probability=2^" in err
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_norm_and_forests_one_stream(fem, forest_oracle_bin, tmp_path, mode, rel):
+    both = os.path.join(FDIR, "norm_and_forests")
+    _compare(fem, forest_oracle_bin, tmp_path, ["-f", both, "-n", both, "-i", "8", "-p", "0.1", "-k", "0.5"], mode, rel)
+
+
+def test_best_forest_initparams(fem, forest_oracle_bin, tmp_path):
+    args = ["-f", os.path.join(FDIR, "best_forest"), "-n", os.path.join(FDIR, "best_norm"), "-I", os.path.join(FDIR, "best_weights"),
+            "-i", "6", "-N"]
+    _compare(fem, forest_oracle_bin, tmp_path, args, ["-U"], 1e-6)
+
+
+def _random_corpus(tmp_path, seed, n_forests, n_rules, depth):
+    rng = np.random.default_rng(seed)
+    d = str(tmp_path)
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules, depth=depth) for _ in range(n_forests)) + "\n")
+    open(f"{d}/n", "w").write(random_normgroups(rng, n_rules))
+    return f"{d}/f", f"{d}/n"
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_random_forests(fem, forest_oracle_bin, tmp_path, seed, mode, rel):
+    f, n = _random_corpus(tmp_path, 300 + seed, n_forests=120, n_rules=60, depth=5)
+    extra = [[], ["-z"], ["-p", "0.01"], ["-u"]][seed]
+    # rules outside every normalization group keep weight 0 unless -u: most forests then have zero probability,
+    # which exercises the "0 prob removed" path
+    _compare(fem, forest_oracle_bin, tmp_path, ["-f", f, "-n", n, "-i", "6", *extra], mode, rel, check_index=False)
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_zero_probability_forests(fem, forest_oracle_bin, tmp_path, mode, rel):
+    d = str(tmp_path)
+    # rule 5 is in no normalization group => weight 0 => forests 3 and 5 have no derivation with non-zero probability
+    open(f"{d}/f", "w").write("(1 2 3)\n(OR 3 (4 1))\n(5 5)\n(OR (1 #1(OR 3 4)) (2 #1))\n(OR (5 1) (2 5))\n")
+    open(f"{d}/n", "w").write("((1 2) (3 4))\n")
+    # (two-member groups change by equal and opposite amounts: which member holds the "largest" change is a rounding tie)
+    err = _compare(fem, forest_oracle_bin, tmp_path, ["-f", f"{d}/f", "-n", f"{d}/n", "-i", "5"], mode, rel, check_index=False)
+    assert "N=3 (2 0 prob removed)" in err
+    assert "Warning: 0 probability for forest #3" in err and "Warning: 0 probability for forest #5" in err
+
+
+def test_big_forests_cta_class(fem, forest_oracle_bin, tmp_path):
+    # deep forests exceed the shared-memory classes and take the one-CTA-per-forest kernel
+    rng = np.random.default_rng(77)
+    d = str(tmp_path)
+    n_rules = 200
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules, depth=9, share=0.05) for _ in range(6)) + "\n")
+    ids = list(range(1, n_rules + 1))
+    open(f"{d}/n", "w").write("(" + " ".join("(" + " ".join(map(str, ids[i:i + 8])) + ")" for i in range(0, n_rules, 8)) + ")\n")
+    err = _compare(fem, forest_oracle_bin, tmp_path, ["-f", f"{d}/f", "-n", f"{d}/n", "-i", "4"], ["-U"], 1e-6, check_index=False)
+    assert "N=6" in err
+
+
+def test_cipher_forests_golden_trajectory(fem, oracle_bin, tmp_path):
+    """carmel's cipher cascade exported as forests and trained on the GPU reproduces the reference's golden log"""
+    data, wfsa, fst = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    d = str(tmp_path)
+    rc, out, err = run(oracle_bin, ["--train-cascade", "--normby=NC", "-HJ", f"--fem-forest={d}/c.forest", f"--fem-norm={d}/c.norm",
+                                    f"--fem-param={d}/c.param", data, wfsa, fst])
+    assert rc == 0, err
+    rc, out, err = run(fem, ["-U", "-f", f"{d}/c.forest", "-n", f"{d}/c.norm", "-I", f"{d}/c.param", "-i", "22", "-e", "0",
+                             f"--history={d}/h"])
+    assert rc == 0, err
+    want = golden()["cipher"]["trajectory_log2"]
+    hist = _hist(f"{d}/h")
+    assert len(hist) == len(want) == 22
+    for (it, log2p), h in zip(want, hist):
+        got = h[1] * 10 / math.log(2)
+        assert h[0] == it and abs(got - log2p) <= 1.01e-5 * abs(log2p), (it, got, log2p)
+
+
+def test_errors(fem, tmp_path):
+    d = str(tmp_path)
+    open(f"{d}/bad", "w").write("(OR (1 2) (3 #9))\n")
+    open(f"{d}/n", "w").write("((1 2 3))\n")
+    rc, out, err = run(fem, ["-f", f"{d}/bad", "-n", f"{d}/n", "-i", "2"])
+    assert rc == 1 and "undefined #9" in err
+    open(f"{d}/cyc", "w").write("#1(1 #1 (2 #1 (1 1)))\n")
+    rc, out, err = run(fem, ["-f", f"{d}/cyc", "-n", f"{d}/n", "-i", "2"])
+    assert rc == 1 and "cyclic" in err
+    rc, out, err = run(fem, ["-n", f"{d}/n", "-i", "2"])
+    assert rc == 1 and "Missing forests-file" in err
