@@ -123,6 +123,11 @@ struct TrellisBatch {  // the C ABI's cml_trellis_batch, owning its storage; ref
 void build_trellises(Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
                      unsigned n_threads = 0);
 
+// Multi-GPU sharding of the E-step (examples are independent given the weights: cached_derivs.h:69-75):
+// rank r of n keeps the contiguous block [e0, e1) of the corpus; blocks are balanced by string length
+// (1 + |in| + |out| per example), cover the corpus and do not overlap.
+void shard_range(Corpus const& corpus, int rank, int count, size_t& e0, size_t& e1);
+
 // ---- training -------------------------------------------------------------------------------------
 struct TrainOpts {
   uint32_t max_iter = 500;          // -M   (fst.h:1089)

@@ -253,6 +253,23 @@ void ForestJob::load() {
   total_forests = forests.size();
 }
 
+// this process's block of the corpus: contiguous, balanced by node count, blocks cover the corpus without overlap
+void ForestJob::compute_shard() {
+  shard_begin = 0;
+  shard_end = forests.size();
+  if (opt.shard_count > 1) {
+    const uint64_t total = forests.n_nodes();
+    auto cut = [&](int r) -> uint64_t {
+      if (r <= 0) return 0;
+      if (r >= opt.shard_count) return forests.size();
+      const uint64_t target = total / (uint64_t)opt.shard_count * (uint64_t)r;
+      return (uint64_t)(std::lower_bound(forests.node_off.begin(), forests.node_off.end(), target) - forests.node_off.begin());
+    };
+    shard_begin = std::min(cut(opt.shard_rank), forests.size());
+    shard_end = std::max(shard_begin, std::min(cut(opt.shard_rank + 1), forests.size()));
+  }
+}
+
 // forest-em.hpp:335-381 prepare, :282-306 init_rule_weights
 void ForestJob::prepare() {
   if (prepared) return;
@@ -278,20 +295,7 @@ void ForestJob::prepare() {
   ok(cml_forests_set_rules(ctx, rulespace, groups.size(), groups.off.data(), groups.members.data()));
   ok(cml_forests_set_params(ctx, ln_w.data()));
   if (have_init_params && opt.normalize_initial && groups.size()) ok(cml_forests_normalize_params(ctx));
-  // this process's block of the corpus: contiguous, balanced by node count
-  shard_begin = 0;
-  shard_end = forests.size();
-  if (opt.shard_count > 1) {
-    const uint64_t total = forests.n_nodes();
-    auto cut = [&](int r) -> uint64_t {
-      if (r <= 0) return 0;
-      if (r >= opt.shard_count) return forests.size();
-      const uint64_t target = total / (uint64_t)opt.shard_count * (uint64_t)r;
-      return (uint64_t)(std::lower_bound(forests.node_off.begin(), forests.node_off.end(), target) - forests.node_off.begin());
-    };
-    shard_begin = std::min(cut(opt.shard_rank), forests.size());
-    shard_end = std::max(shard_begin, std::min(cut(opt.shard_rank + 1), forests.size()));
-  }
+  compute_shard();
   if (shard_end > shard_begin) {
     std::vector<uint64_t> off(forests.node_off.begin() + shard_begin, forests.node_off.begin() + shard_end + 1);
     const uint64_t o = off[0];
@@ -453,7 +457,8 @@ void ForestJob::write_outputs(std::ostream& log) {
   }
   if (!opt.print_forests_file.empty()) {
     std::ofstream o(opt.print_forests_file);
-    for (uint64_t f = 0; f < forests.size(); ++f) {
+    if (!prepared) compute_shard();
+    for (uint64_t f = shard_begin; f < shard_end; ++f) {  // with --shard=r/N: this rank's block only
       forests.print(o, f);
       o << "\n";
     }

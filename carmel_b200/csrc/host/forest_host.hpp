@@ -84,6 +84,7 @@ struct ForestJob {
 
   ~ForestJob();
   void load();     // read the files named in opt
+  void compute_shard();  // [shard_begin, shard_end) from opt.shard_rank / opt.shard_count
   void prepare();  // rules, parameters and this shard's forests onto the GPU
   double estimate(bool first_time, std::ostream& log, uint64_t* n_used = nullptr);
   void maximize(std::ostream& log, double& max_delta, uint64_t& max_index);

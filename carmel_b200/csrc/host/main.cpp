@@ -48,6 +48,14 @@ int main(int argc, char** argv) {
     if (job.lopt.count("trellis-only")) {  // host-side lattice construction only (no GPU work): parity tests
       TrellisBatch tb;
       std::vector<uint32_t> dropped;
+      size_t e0, e1;  // with --shard=r/N: this rank's block only (what TrainJob::prepare keeps on its GPU)
+      shard_range(job.corpus, job.opt.shard_rank, job.opt.shard_count, e0, e1);
+      if (job.opt.shard_count > 1) {
+        Corpus local;
+        local.examples.assign(job.corpus.examples.begin() + e0, job.corpus.examples.begin() + e1);
+        job.corpus.examples.swap(local.examples);
+        std::cerr << "Shard " << job.opt.shard_rank << "/" << job.opt.shard_count << ": examples [" << e0 << ", " << e1 << ")\n";
+      }
       build_trellises(*job.x, job.corpus, tb, dropped);
       uint64_t ns = 0;
       for (uint32_t n : tb.ex_states) ns += n;

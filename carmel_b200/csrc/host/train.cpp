@@ -76,6 +76,22 @@ TrainJob::~TrainJob() {
   if (ctx) cml_destroy(ctx);
 }
 
+void shard_range(Corpus const& corpus, int rank, int count, size_t& e0, size_t& e1) {
+  const size_t n = corpus.examples.size();
+  e0 = 0;
+  e1 = n;
+  if (count <= 1) return;
+  std::vector<double> cost(n + 1, 0.);
+  for (size_t e = 0; e < n; ++e) cost[e + 1] = cost[e] + 1. + corpus.examples[e].in.size() + corpus.examples[e].out.size();
+  auto cut = [&](int r) {
+    const double target = cost.back() * r / count;
+    return std::min(n, (size_t)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin()));
+  };
+  e0 = rank == 0 ? 0 : cut(rank);
+  e1 = rank == count - 1 ? n : cut(rank + 1);
+  if (e1 < e0) e1 = e0;
+}
+
 // Everything up to the first E-step: model tables, initial normalisation, prior counts, derivation
 // lattices (this rank's shard) flattened and resident on the GPU.
 void TrainJob::prepare() {
@@ -149,19 +165,8 @@ void TrainJob::prepare() {
   // ---- derivation lattices: built once, resident on the GPU (carmel's -: cache semantics) ----
   // With --shard=r/N only a contiguous block of the corpus (balanced by string length) is built and
   // kept on this GPU; corpus statistics are then made global through the all-reduce hook.
-  size_t e0 = 0, e1 = corpus.examples.size();
-  if (opt.shard_count > 1) {
-    std::vector<double> cost(corpus.examples.size() + 1, 0.);
-    for (size_t e = 0; e < corpus.examples.size(); ++e)
-      cost[e + 1] = cost[e] + 1. + corpus.examples[e].in.size() + corpus.examples[e].out.size();
-    auto cut = [&](int r) {
-      const double target = cost.back() * r / opt.shard_count;
-      return (size_t)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
-    };
-    e0 = opt.shard_rank == 0 ? 0 : std::min(cut(opt.shard_rank), corpus.examples.size());
-    e1 = opt.shard_rank == opt.shard_count - 1 ? corpus.examples.size() : std::min(cut(opt.shard_rank + 1), corpus.examples.size());
-    if (e1 < e0) e1 = e0;
-  }
+  size_t e0, e1;
+  shard_range(corpus, opt.shard_rank, opt.shard_count, e0, e1);
   {
     Corpus local;
     local.examples.assign(std::make_move_iterator(corpus.examples.begin() + e0),
