@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cipher", choices=["cipher", "hmm", "forest"])
+    ap.add_argument("--workload", default="cipher", choices=["cipher", "hmm", "forest", "gibbs"])
     ap.add_argument("--precision", type=int, default=None, choices=[32, 64],
                     help="score precision (default 64 for cipher/hmm like carmel, 32 for forest like forest-em)")
     ap.add_argument("--space", default="scaled", choices=["scaled", "log"])
@@ -169,6 +169,13 @@ def main():
                 bench_forest.reference_arm(a)
             return
         return bench_forest.run(a, rank, world, local)
+    if a.workload == "gibbs":  # --crp Gibbs sampling (configs[3]): see bench_gibbs.py
+        import bench_gibbs
+        if a.impl == "reference":
+            if rank == 0:
+                bench_gibbs.reference_arm(a)
+            return
+        return bench_gibbs.run(a, rank, world, local)
     metric = "em_iteration_trellis_arcs_per_sec"
     unit = "trellis arcs/s"
     wl_name = {"cipher": "configs[1] cipher decipherment: 27x27 channel o 27-state locked bigram LM, "

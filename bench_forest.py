@@ -191,11 +191,17 @@ def run(a, rank, world, local):
         # algorithmic bytes of one E-step: per node label + child_off (inside) and label + par_off (outside), 4 B each;
         # per child/parent link one u32 in each pass; inside/posterior values stay in shared memory
         bytes_step = 16.0 * tot_local["nodes"] + 8.0 * tot_local["links"]
+        lay = F.layout_stats()
+        if lay["tile_forests"]:
+            # thread-per-forest tiles: one u32 op per step in each pass, the label twice, inside[] and gamma[] written once
+            # (their re-reads are L1/L2 hits by construction of the post-order); padding is not counted
+            bytes_step = 4.0 * lay["steps"] + (8.0 + 2.0 * (a.precision // 8)) * tot_local["nodes"]
         kms = sum(m for m, _ in k_ms) / len(k_ms)
         achieved = bytes_step / (kms / 1e3) / 1e9
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": which, "kernel": f"k_forest_warp/k_forest_cta (inside + outside + counts, {k_ms[0][1]} launches)",
+                    "peak_source": which, "kernel": ("k_forest_thread" if lay["tile_forests"] else "k_forest_warp/k_forest_cta") +
+                    f" (inside + outside + counts, {k_ms[0][1]} launch(es) per iteration)",
                     "kernel_ms": kms, "algorithmic_bytes_per_hyperedge": bytes_step / max(1, tot_local["hyperedges"]),
                     "hyperedges_per_launch_set": tot_local["hyperedges"], "kernel_share_of_step": kms / (ms / a.steps)}
         try:
@@ -208,7 +214,8 @@ def run(a, rank, world, local):
                 "dtype": "f64" if a.precision == 64 else "f32", "data": "synthetic", "config": config_of(a, world),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "totals": {"forests": forests_total, "hyperedges": he_total, "nodes": nodes_total, "links": links_total,
-                           "rulespace": rulespace, "avg_ln_p": last[0] / max(1.0, last[2] - last[1])}}
+                           "rulespace": rulespace, "avg_ln_p": last[0] / max(1.0, last[2] - last[1])},
+                "layout": lay}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

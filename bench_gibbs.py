@@ -1,0 +1,193 @@
+"""bench_gibbs.py -- `carmel --crp` Gibbs sampling throughput (samples/s); run as `python bench.py --workload gibbs`.
+
+Workload = BASELINE.json configs[3]: the synthetic cipher model (27x27 channel o locked 27-state
+bigram LM) with a Dirichlet prior alpha=0.01 on the channel, ciphertext in lines of 50 letters; one block = one
+line; one sample = one block resampled once (graehl/shared/gibbs.hpp:844-872).  A step = one sweep over all
+resident blocks in batched mode (all blocks in parallel against the previous sweep's counts, then the count
+deltas are applied); the exact sequential sampler's rate is reported next to it (`sequential`).  The default
+keeps 5000 lines (250k letters) per GPU so that the host lattice build stays short; --scale 4 is C4's 1M letters."""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+ORACLE = os.path.join(ROOT, "oracle", "_build", "carmel_oracle")
+METRIC, UNIT = "gibbs_samples_per_sec", "samples/s"
+
+
+def config_of(a, world):
+    return {"workload": "configs[3] --crp Gibbs on the synthetic cipher (27x27 channel o locked bigram LM, alpha=0.01), "
+                        f"{5000 * a.scale} lines x 50 letters per GPU, batched sweeps",
+            "blocks_per_gpu": 5000 * a.scale, "l2": "lattices 2.9 GB per GPU > 126 MB L2",
+            "parallelism": f"{world} independent replica(s): the exact sampler is sequential over the corpus (SURVEY 8e)"}
+
+
+def cpu_oracle_gibbs(files, n_lines, procs, sweeps=3):
+    """samples/s of the CPU oracle's sequential sampler on the first n_lines, `procs` independent processes"""
+    if not os.path.exists(ORACLE):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    d = tempfile.mkdtemp(prefix="cb200_gcpu_")
+    try:
+        per = max(1, n_lines // procs)
+        shards = []
+        with open(files[0]) as f:
+            for i in range(procs):
+                path = os.path.join(d, f"s{i}.data")
+                k = 0
+                with open(path, "w") as g:
+                    while k < per:
+                        x, y = f.readline(), f.readline()
+                        if not y:
+                            break
+                        g.write(x)
+                        g.write(y)
+                        k += 1
+                if k:
+                    shards.append(path)
+        t0 = time.time()
+        ps = [subprocess.Popen([ORACLE, "--crp", "-M", str(sweeps), "--priors=0,1e-2", "--seed=1", s, *files[1:]],
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d) for s in shards]
+        for p in ps:
+            p.wait()
+        t_all = time.time() - t0
+        # subtract the one-time part (read, compose, lattice build, sweep 0) measured with -M 0
+        t0 = time.time()
+        ps = [subprocess.Popen([ORACLE, "--crp", "-M", "0", "--priors=0,1e-2", "--seed=1", s, *files[1:]],
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d) for s in shards]
+        for p in ps:
+            p.wait()
+        t_base = time.time() - t0
+        secs = max(1e-6, t_all - t_base)
+        n = per * len(shards) * sweeps
+        return {"value": n / secs, "unit": UNIT, "cores": len(shards), "kind": "port",
+                "sample": f"first {per * len(shards)} lines, {sweeps} sequential sweeps (lattices cached), {len(shards)} independent "
+                          f"single-threaded oracle processes; {t_all:.1f}s total, {t_base:.1f}s one-time part subtracted"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def reference_arm(a):
+    from carmel_b200 import synth
+    t0 = time.time()
+    d = tempfile.mkdtemp(prefix="cb200_gref_")
+    try:
+        w = synth.write_cipher(d, n_lines=400, line_len=50)
+        procs = max(1, os.cpu_count() or 1)
+        cb = cpu_oracle_gibbs(w["files"], 25 * procs, procs, sweeps=max(2, min(a.steps, 4)))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(a, a.gpus), "impl": "reference", "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "carmel needs Boost (absent): this arm times the CPU oracle restatement", "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+def run(a, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import carmel_b200 as cb
+    from bench import ClockSampler, FALLBACK_HBM_GBS, measured_peaks
+    from carmel_b200 import synth
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (carmel_b200 has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = tempfile.mkdtemp(prefix=f"cb200_gibbs_{rank}_")
+    w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104 + rank)
+    stream = torch.cuda.Stream()
+    t_build = time.time()
+    job = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", "--priors=0,1e-2", "--seed=1", *w["argv"][1:]])
+    ctx = job.prepare()
+    ctx.set_stream(stream.cuda_stream)
+    t_build = time.time() - t_build
+    info = job.stats()
+    blocks, arcs, states = info["examples"], info["trellis_arcs"], info["trellis_states"]
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sweep = [0]
+
+    def step():
+        ctx.gibbs_sweep(1, sweep[0], seed=1, power=1.0, accumulate_dt=1.0)
+        sweep[0] += 1
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms = timed(step, a.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * blocks * a.steps / (ms / 1e3)
+
+    # e2e: what the host loop of `carmel --crp` does every sweep: read the sampled derivations back (for the cache-model
+    # probability, gibbs.hpp:712-742)
+    cap = ctx.gibbs_sample_capacity()
+    h_len = torch.empty(blocks, dtype=torch.int32).pin_memory()
+    h_arcs = torch.empty(cap, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        step()
+        ctx.gibbs_get_samples_ptr(h_len.data_ptr(), h_arcs.data_ptr(), cap)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    e2e = {"value": world * blocks * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0,
+           "d2h_bytes_per_step": 4 * (blocks + cap), "ms_per_step": ms_e2e / a.steps,
+           "lattices": f"resident; one-time host build + upload took {t_build:.2f}s on this rank"}
+    # the exact sequential sampler on the same blocks (one CTA walks the corpus)
+    n_seq = max(1, min(2, a.steps))
+    ms_seq = timed(lambda: ctx.gibbs_sweep(0, 100000 + sweep[0], seed=1, power=1.0, accumulate_dt=0.0), n_seq)
+    if rank == 0:
+        peaks, which = measured_peaks()
+        # per sample one backward sweep over the block's lattice (8 B/arc record + the state scores written and
+        # read once) + the sampled path (16 B per visited state)
+        bytes_step = 8.0 * arcs + 2.0 * 8 * states + 16.0 * 51 * blocks
+        achieved = bytes_step / (ms / a.steps / 1e3) / 1e9
+        peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": which, "kernel": "k_gibbs (backward filter + forward sample per block) + k_gibbs_apply",
+                    "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks)}
+        try:
+            procs = max(1, os.cpu_count() or 1)
+            cpu = cpu_oracle_gibbs(w["files"], 25 * procs, procs)
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config_of(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks,
+                "sequential": {"value": blocks * n_seq / (ms_seq / 1e3), "unit": UNIT, "ms_per_sweep": ms_seq / n_seq,
+                               "note": "exact collapsed sampler, identical derivations to the CPU oracle (tests/test_gibbs_gpu.py)"},
+                "totals": {"blocks": blocks, "trellis_arcs": arcs, "trellis_states": states}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+    job.close()
+    shutil.rmtree(d, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()

@@ -45,6 +45,11 @@ class CmlEstimateResult(C.Structure):
     _fields_ = [("sum_ln_p", C.c_double), ("sum_w_ln_p", C.c_double), ("n_zero", C.c_uint64)]
 
 
+class CmlGibbsSweepOpts(C.Structure):
+    _fields_ = [("mode", C.c_int), ("power", C.c_double), ("seed", C.c_uint64), ("sweep", C.c_uint32),
+                ("init_from_params", C.c_int), ("accumulate_dt", C.c_double)]
+
+
 class CmlJobInfo(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("examples", "trellis_states", "trellis_arcs", "n_params", "n_arcs",
                                           "corpus_pairs", "iterations")] + [("ln_best_ppx", C.c_double),
@@ -111,6 +116,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_last_fb_time_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     lib.cml_reduce_buffer_write.argtypes = [vp, _f64p, C.c_uint64]
     lib.cml_reduce_buffer_read.argtypes = [vp, _f64p, C.c_uint64]
+    lib.cml_gibbs_sweep.argtypes = [vp, C.POINTER(CmlGibbsSweepOpts)]
+    lib.cml_gibbs_sample_capacity.argtypes = [vp]
+    lib.cml_gibbs_sample_capacity.restype = C.c_uint64
+    lib.cml_gibbs_get_samples.argtypes = [vp, _u32p, _u32p, C.c_uint64]
     lib.cml_job_open.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_char_p)]
     lib.cml_job_close.argtypes = [vp]
     lib.cml_job_close.restype = None
@@ -331,6 +340,19 @@ class Context:
 
     def normalize_params(self):
         self._check(self.lib.cml_normalize_params(self.h))
+
+    # ---- --crp Gibbs sampling (cml_gibbs_*) ----
+    def gibbs_sweep(self, mode: int, sweep: int, seed: int = 1, power: float = 1.0, accumulate_dt: float = 0.0,
+                    init_from_params: bool = False):
+        """one sweep over all blocks; mode 0 = sequential (exact collapsed sampler), 1 = batched"""
+        o = CmlGibbsSweepOpts(mode, power, seed, sweep, int(init_from_params), accumulate_dt)
+        self._check(self.lib.cml_gibbs_sweep(self.h, C.byref(o)))
+
+    def gibbs_sample_capacity(self) -> int:
+        return int(self.lib.cml_gibbs_sample_capacity(self.h))
+
+    def gibbs_get_samples_ptr(self, len_ptr: int, arcs_ptr: int, cap: int):
+        self._check(self.lib.cml_gibbs_get_samples(self.h, C.cast(len_ptr, _u32p), C.cast(arcs_ptr, _u32p), cap))
 
 
 class Job:

@@ -106,9 +106,10 @@ struct cml_ctx {
   // --crp Gibbs sampling state (cml_gibbs.cu)
   bool have_gibbs = false;
   uint32_t g_norms = 0;
-  DevArray<uint32_t> g_param_norm, g_arc_orig, g_sample[2], g_sample_len[2];
-  DevArray<double> g_prior, g_count, g_cum, g_normsum, g_lnp, g_beta;
+  DevArray<uint32_t> g_param_norm, g_arc_orig, g_sample[2], g_sample_len[2], g_au_off, g_au_param;
+  DevArray<double> g_prior, g_count, g_cum, g_normsum, g_lnp, g_beta, g_tbl;
   DevArray<uint64_t> g_sample_base, g_beta_base;
+  DevArray<uint2> g_arc_pg;
   std::vector<uint64_t> h_sample_base;
   uint64_t g_sample_cap = 0;
   int g_cur = 0;  // which sample buffer holds the current sample

@@ -195,6 +195,141 @@ __global__ void __launch_bounds__(kCtaThreads) k_forest_cta(ForestArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Thread-per-forest kernel (the throughput path for corpora of many small forests).
+//
+// 32 forests of similar size form a tile, one forest per lane of a warp; every array of the tile is stored
+// transposed ([row][lane]) so that the warp's loads of its 32 sequential streams coalesce into one 128-byte
+// line per row.  Nodes are numbered in DFS post-order (children before parents, the root last), and the two
+// passes are flattened into streams of one-link "steps":
+//   inside  ops: child index | FIRST (first step of a node: load its label, start the product / sum)
+//                            | LAST  (store inside[node], advance)          -- leaves take one step with no child
+//   outside ops: parent index | OR flag | FIRST | LAST, nodes in reverse post-order (the root first, one step)
+// so all lanes run the same trip count (steps of the largest forest of the tile; the rest is padded with NOPs)
+// with no synchronisation at all.  inside[] / gamma[] of the tile live in HBM/L2, transposed like the rest:
+// the values a lane reads were written by the same lane a few rows earlier (post-order locality).
+// ---------------------------------------------------------------------------------------------------
+const uint32_t kOpFirst = 0x80000000u, kOpLast = 0x40000000u, kOpOr = 0x20000000u, kOpIdx = 0x1fffffffu, kOpNop = 0xffffffffu;
+struct __align__(16) TileDesc {
+  uint64_t ops_in_base, ops_out_base, row_base;  // element offsets (already multiplied by 32) into t_ops_in / t_ops_out / rows
+  uint32_t steps_in, steps_out;
+  uint32_t n_nodes[32];
+  uint32_t forest[32];  // forest number within the batch, 0xffffffff = empty lane
+};
+struct TileArgs {
+  const TileDesc* tiles;
+  uint32_t n_tiles;
+  const uint32_t* ops_in;
+  const uint32_t* ops_out;
+  const uint32_t* label;  // [row][lane]
+  void* in_;              // Real [row][lane]
+  void* ga;
+  const void* lnw;
+  const uint32_t* hot_index;
+  double* counts;
+  double* hot;
+  uint32_t n_hot;
+  double* ln_inside;
+};
+template <typename Real>
+__device__ __forceinline__ Real ln_add_fast(Real a, Real b);
+template <>
+__device__ __forceinline__ double ln_add_fast<double>(double a, double b) {
+  return ln_add<double>(a, b);
+}
+template <>
+__device__ __forceinline__ float ln_add_fast<float>(float a, float b) {  // same cutoff semantics, hardware exp/log
+  if (!(a > -CUDART_INF_F)) return b;
+  if (!(b > -CUDART_INF_F)) return a;
+  const float hi = fmaxf(a, b), d = -fabsf(a - b);
+  if (d < -16.f) return hi;
+  return hi + __logf(1.f + __expf(d));
+}
+const int kTileWarps = 4;
+template <typename Real>
+__global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * kTileWarps + (threadIdx.x >> 5);
+  if (t >= A.n_tiles) return;
+  const TileDesc* __restrict__ T = A.tiles + t;
+  const uint32_t* __restrict__ oi = A.ops_in + T->ops_in_base + lane;
+  const uint32_t* __restrict__ oo = A.ops_out + T->ops_out_base + lane;
+  const uint32_t* __restrict__ lab_ = A.label + T->row_base + lane;
+  Real* __restrict__ in_ = (Real*)A.in_ + T->row_base + lane;
+  Real* __restrict__ ga = (Real*)A.ga + T->row_base + lane;
+  const Real* __restrict__ lnw = (const Real*)A.lnw;
+  const Real NI = FNum<Real>::ninf();
+  const uint32_t n = T->n_nodes[lane];
+  const uint32_t fidx = T->forest[lane];
+  const uint32_t replica = t & (kHotCopies - 1);
+  // ---- inside
+  uint32_t jn = 0;
+  Real v = NI;
+  bool isand = false;
+  const uint32_t si = T->steps_in;
+  uint32_t op = si ? __ldg(oi) : kOpNop;
+  for (uint32_t s = 0; s < si; ++s) {
+    const uint32_t nop = s + 1 < si ? __ldg(oi + (size_t)(s + 1) * 32) : kOpNop;  // next step's op: independent of the values
+    if (op != kOpNop) {
+      if (op & kOpFirst) {
+        const uint32_t lab = __ldg(lab_ + (size_t)jn * 32) & ~kHotBit;
+        isand = lab != 0;
+        v = isand ? __ldg(&lnw[lab]) : NI;
+      }
+      const uint32_t c = op & kOpIdx;
+      if (c != kOpIdx) {
+        const Real x = in_[(size_t)c * 32];
+        v = isand ? v + x : ln_add_fast<Real>(v, x);
+      }
+      if (op & kOpLast) {
+        in_[(size_t)jn * 32] = v;
+        ++jn;
+      }
+    }
+    op = nop;
+  }
+  if (fidx == 0xffffffffu) return;
+  const Real in_root = v;  // the root is the last node of the post-order
+  A.ln_inside[fidx] = (double)in_root;
+  const bool live = in_root > NI;  // zero-probability forests collect no counts (forest.hpp:447-451)
+  // ---- outside as posteriors: reverse post-order
+  jn = n - 1;
+  Real g = 0, in_i = NI;
+  const uint32_t so = T->steps_out;
+  op = so ? __ldg(oo) : kOpNop;
+  for (uint32_t s = 0; s < so; ++s) {
+    const uint32_t nop = s + 1 < so ? __ldg(oo + (size_t)(s + 1) * 32) : kOpNop;
+    if (op != kOpNop && live) {
+      if (op & kOpFirst) {
+        g = 0;
+        in_i = in_[(size_t)jn * 32];
+      }
+      const uint32_t p = op & kOpIdx;
+      if (p == kOpIdx)
+        g = 1;  // the root
+      else {
+        const Real gp = ga[(size_t)p * 32];
+        if (op & kOpOr) {
+          if (in_i > NI && gp > 0) g += gp * FNum<Real>::ex(in_i - in_[(size_t)p * 32]);
+        } else
+          g += gp;
+      }
+      if (op & kOpLast) {
+        ga[(size_t)jn * 32] = g;
+        const uint32_t lab = __ldg(lab_ + (size_t)jn * 32);
+        if ((lab & ~kHotBit) && g > 0) {
+          if (lab & kHotBit)
+            atomicAdd(A.hot + (size_t)replica * A.n_hot + __ldg(&A.hot_index[lab & ~kHotBit]), (double)g);
+          else
+            atomicAdd(A.counts + lab, (double)g);
+        }
+        --jn;
+      }
+    }
+    op = nop;
+  }
+}
+
 // mark hot rules in the node labels (bit 31); idempotent
 __global__ void k_forest_mark_hot(uint64_t n, uint32_t* __restrict__ label, const uint32_t* __restrict__ hot_index) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,11 +347,15 @@ __global__ void k_forest_fold(uint32_t n_hot, const uint32_t* __restrict__ hot_r
   if (s != 0.) atomicAdd(&counts[hot_rule[h]], s);
 }
 // sum of ln inside over non-zero forests (forest-em.hpp:519-527): one block, fixed order => deterministic
-__global__ void k_forest_sum(const double* __restrict__ ln_inside, uint64_t n, double* __restrict__ scal) {
+// stage 1: kSumBlocks blocks, block b sums the fixed slice b of the forests into partial[2b..2b+1]
+const int kSumBlocks = 128;
+__global__ void k_forest_sum_partial(const double* __restrict__ ln_inside, uint64_t n, double* __restrict__ partial) {
   __shared__ double s_sum[256];
   __shared__ double s_zero[256];
+  const uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const uint64_t b = blockIdx.x * per, e = b + per < n ? b + per : n;
   double s = 0, z = 0;
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
     const double v = ln_inside[i];
     if (v > -CUDART_INF)
       s += v;
@@ -234,9 +373,33 @@ __global__ void k_forest_sum(const double* __restrict__ ln_inside, uint64_t n, d
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = s_sum[0];
+    partial[2 * blockIdx.x + 1] = s_zero[0];
+  }
+}
+// stage 2 (one block): fold the partials (pairs: sum, zeros) in a fixed order
+__global__ void k_forest_sum(const double* __restrict__ ln_inside, uint64_t n, double* __restrict__ scal, uint64_t n_forests) {
+  __shared__ double s_sum[256];
+  __shared__ double s_zero[256];
+  double s = 0, z = 0;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    s += ln_inside[2 * i];
+    z += ln_inside[2 * i + 1];
+  }
+  s_sum[threadIdx.x] = s;
+  s_zero[threadIdx.x] = z;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_zero[threadIdx.x] += s_zero[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
     scal[0] += s_sum[0];
     scal[1] += s_zero[0];
-    scal[2] += (double)n;
+    scal[2] += (double)n_forests;
   }
 }
 template <typename Real>
@@ -345,6 +508,12 @@ struct ForestBatch {
   DevArray<unsigned char> scratch;
   uint64_t scratch_stride = 0;
   uint32_t cta_grid = 0;
+  // thread-per-forest tiles
+  uint32_t n_tiles = 0;
+  uint64_t t_forests = 0, t_steps = 0, t_rows = 0;  // forests in tiles; real (unpadded) steps; padded rows * 32
+  DevArray<TileDesc> tiles;
+  DevArray<uint32_t> t_ops_in, t_ops_out, t_label;
+  DevArray<unsigned char> t_in, t_ga;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_kernels = 0;
   ~ForestBatch() {
@@ -364,9 +533,10 @@ struct cml_forests {
   std::string err;
   uint64_t launches = 0;
   bool have_rules = false, have_params = false, hot_dirty = true, pending = false;
+  int layout = CML_FOREST_LAYOUT_AUTO;
   uint64_t rulespace = 0, n_groups = 0;
   DevArray<uint64_t> group_off, group_members;
-  DevArray<double> ln_w, reduce, gdiff, out_diff;
+  DevArray<double> ln_w, reduce, gdiff, out_diff, sum_partial;
   DevArray<uint64_t> gidx;
   DevArray<unsigned long long> out_rule;
   DevArray<unsigned char> w_real;
@@ -435,6 +605,30 @@ extern "C" int cml_forests_set_stream(cml_forests* f, void* s) {
   return CML_OK;
 }
 extern "C" uint64_t cml_forests_launch_count(cml_forests* f) { return f ? f->launches : 0; }
+extern "C" int cml_forests_set_layout(cml_forests* f, int layout) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(layout >= CML_FOREST_LAYOUT_AUTO && layout <= CML_FOREST_LAYOUT_THREAD, CML_ERR_ARG, "cml_forests_set_layout: unknown layout");
+  f->layout = layout;
+  return CML_OK;
+}
+extern "C" int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, uint64_t* tiles, uint64_t* steps, uint64_t* padded_steps,
+                                        uint64_t* padded_rows) {
+  if (!f) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0, d = 0, e = 0;
+  for (auto const& bt : f->batches) {
+    a += bt->t_forests;
+    b += bt->n_tiles;
+    c += bt->t_steps;
+    d += bt->t_ops_in.n * (bt->n_tiles ? 1 : 0) + bt->t_ops_out.n * (bt->n_tiles ? 1 : 0);
+    e += bt->t_rows;
+  }
+  if (tile_forests) *tile_forests = a;
+  if (tiles) *tiles = b;
+  if (steps) *steps = c;
+  if (padded_steps) *padded_steps = d;
+  if (padded_rows) *padded_rows = e;
+  return CML_OK;
+}
 
 extern "C" int cml_forests_set_rules(cml_forests* f, uint64_t rulespace, uint64_t n_groups, const uint64_t* group_off,
                                      const uint64_t* group_members) {
@@ -493,12 +687,12 @@ extern "C" int cml_forests_get_params(cml_forests* f, double* ln_w) {
 // ---------------------------------------------------------------------------------------------------
 namespace {
 struct FlatForest {
-  uint32_t n_real = 0, n_levels = 0;
+  uint32_t n_real = 0, n_levels = 0, n_leaves = 0;
   uint64_t n_links = 0, n_he = 0;
   int error = 0;  // 1 malformed, 2 cycle, 3 rule id out of range
 };
 struct ForestScratch {
-  std::vector<uint32_t> height, order, newid, stack, it, cnt;
+  std::vector<uint32_t> height, order, newid, stack, it, cnt, post;
   std::vector<char> color;
 };
 // pass 1: validate, heights, counts.  `real_of[i]` for pre-order node i = i or the target of a back reference.
@@ -534,6 +728,7 @@ void forest_pass1(uint32_t n, const uint32_t* next, const uint32_t* label, const
   S.height.assign(n, 0);
   S.color.assign(n, 0);
   S.stack.clear();
+  S.post.clear();     // DFS post-order of the real nodes (children before parents, the root last)
   S.it.assign(n, 0);  // resume position (pre-order index of the next child to look at)
   S.stack.push_back(0);
   S.color[0] = 1;
@@ -566,6 +761,8 @@ void forest_pass1(uint32_t n, const uint32_t* next, const uint32_t* label, const
       }
       S.height[p] = h;
       S.color[p] = 2;
+      S.post.push_back(p);
+      if (next[p] == p + 1) ++ff.n_leaves;
       S.stack.pop_back();
     }
   }
@@ -626,19 +823,76 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
                (ff[i].error == 2 ? " has a cyclic back reference" : ff[i].error == 3 ? " uses a rule id beyond rulespace" : " is malformed");
       return ff[i].error == 2 ? CML_ERR_CYCLE : CML_ERR_ARG;
     }
-    node_base[i + 1] = node_base[i] + ff[i].n_real + 1;
-    link_base[i + 1] = link_base[i] + ff[i].n_links;
-    lvl_base[i + 1] = lvl_base[i] + ff[i].n_levels + 1;
     bt->n_nodes += ff[i].n_real;
     bt->n_links += ff[i].n_links;
     bt->n_hyperedges += ff[i].n_he;
     bt->max_nodes = std::max<uint64_t>(bt->max_nodes, ff[i].n_real);
   }
-  F_REQUIRE(link_base[nf] < 0xffffffffull * 64, CML_ERR_ARG, "cml_forests_add: batch too large");
+  // layout family per forest: thread-per-forest tiles for corpora of many small forests, else warp / CTA per forest
+  std::vector<char> in_tile(nf, 0);
+  {
+    uint64_t min_forests = 8192, max_nodes = 16384;
+    if (const char* e = getenv("CML_FOREST_TILE_MIN_FORESTS")) min_forests = std::strtoull(e, nullptr, 10);
+    if (const char* e = getenv("CML_FOREST_TILE_MAX_NODES")) max_nodes = std::strtoull(e, nullptr, 10);
+    uint64_t cand = 0;
+    for (uint64_t i = 0; i < nf; ++i) cand += ff[i].n_real <= max_nodes;
+    const bool use = f->layout == CML_FOREST_LAYOUT_THREAD || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests);
+    if (use)
+      for (uint64_t i = 0; i < nf; ++i) in_tile[i] = ff[i].n_real <= max_nodes || f->layout == CML_FOREST_LAYOUT_THREAD;
+  }
+  for (uint64_t i = 0; i < nf; ++i) {
+    const bool g = !in_tile[i];
+    node_base[i + 1] = node_base[i] + (g ? ff[i].n_real + 1 : 0);
+    link_base[i + 1] = link_base[i] + (g ? ff[i].n_links : 0);
+    lvl_base[i + 1] = lvl_base[i] + (g ? ff[i].n_levels + 1 : 0);
+  }
   bt->n_forests = nf;
   std::vector<ForestDesc> desc(nf);
   std::vector<uint32_t> h_label(node_base[nf]), h_coff(node_base[nf]), h_poff(node_base[nf]), h_child(std::max<uint64_t>(1, link_base[nf])),
       h_par(std::max<uint64_t>(1, link_base[nf])), h_lvl(lvl_base[nf]);
+  // tiles: 32 forests of similar step count per warp; all streams of a tile padded to its longest forest
+  std::vector<uint32_t> tile_of(nf, 0);  // tile * 32 + lane
+  std::vector<TileDesc> tiles;
+  std::vector<uint32_t> h_ops_in, h_ops_out, h_tlabel;
+  {
+    std::vector<uint32_t> tl;
+    for (uint64_t i = 0; i < nf; ++i)
+      if (in_tile[i]) tl.push_back((uint32_t)i);
+    auto steps_in = [&](uint32_t i) { return ff[i].n_links + ff[i].n_leaves; };
+    std::stable_sort(tl.begin(), tl.end(), [&](uint32_t a, uint32_t x) { return steps_in(a) > steps_in(x); });
+    tiles.resize((tl.size() + 31) / 32);
+    uint64_t in_base = 0, out_base = 0, row_base = 0;
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      TileDesc& T = tiles[t];
+      std::memset(&T, 0, sizeof(T));
+      uint64_t si = 0, so = 0, rows = 0;
+      for (int l = 0; l < 32; ++l) {
+        T.forest[l] = 0xffffffffu;
+        const size_t k = t * 32 + l;
+        if (k >= tl.size()) continue;
+        const uint32_t i = tl[k];
+        tile_of[i] = (uint32_t)k;
+        si = std::max<uint64_t>(si, steps_in(i));
+        so = std::max<uint64_t>(so, ff[i].n_links + 1);
+        rows = std::max<uint64_t>(rows, ff[i].n_real);
+        bt->t_steps += steps_in(i) + ff[i].n_links + 1;
+      }
+      T.ops_in_base = in_base;
+      T.ops_out_base = out_base;
+      T.row_base = row_base;
+      T.steps_in = (uint32_t)si;
+      T.steps_out = (uint32_t)so;
+      in_base += si * 32;
+      out_base += so * 32;
+      row_base += rows * 32;
+    }
+    bt->n_tiles = (uint32_t)tiles.size();
+    bt->t_forests = tl.size();
+    bt->t_rows = row_base;
+    h_ops_in.assign(in_base, kOpNop);
+    h_ops_out.assign(out_base, kOpNop);
+    h_tlabel.assign(row_base, 0u);
+  }
   std::vector<std::vector<uint64_t>> occ_parts(nt);
   {
     std::atomic<uint64_t> nextf(0);
@@ -658,6 +912,57 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
           FlatForest fx;
           forest_pass1(n, next, label, backref, f->rulespace, S, fx);  // recompute heights (cheap, keeps pass 1 memory small)
           const uint32_t nr = fx.n_real, nl = fx.n_levels;
+          if (in_tile[fi]) {  // thread-per-forest tile: post-order numbering, transposed step streams
+            const uint32_t t = tile_of[fi] >> 5, l = tile_of[fi] & 31;
+            TileDesc& T = tiles[t];
+            T.n_nodes[l] = nr;
+            T.forest[l] = (uint32_t)fi;
+            S.newid.assign(n, 0);
+            for (uint32_t j = 0; j < nr; ++j) S.newid[S.post[j]] = j;
+            uint32_t* oi = h_ops_in.data() + T.ops_in_base + l;
+            uint32_t* oo = h_ops_out.data() + T.ops_out_base + l;
+            uint32_t* lb = h_tlabel.data() + T.row_base + l;
+            S.cnt.assign(nr + 1, 0);  // parent in-degrees -> offsets
+            uint32_t s = 0;
+            for (uint32_t j = 0; j < nr; ++j) {
+              const uint32_t p = S.post[j];
+              lb[(size_t)j * 32] = label[p];
+              if (label[p]) ++occ[label[p]];
+              if (next[p] == p + 1) {
+                oi[(size_t)s++ * 32] = kOpFirst | kOpLast | kOpIdx;
+                continue;
+              }
+              bool first = true;
+              for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+                const uint32_t c = S.newid[backref[q] ? label[q] : q];
+                ++S.cnt[c + 1];
+                oi[(size_t)s++ * 32] = c | (first ? kOpFirst : 0u) | (next[q] >= next[p] ? kOpLast : 0u);
+                first = false;
+              }
+            }
+            for (uint32_t j = 0; j < nr; ++j) S.cnt[j + 1] += S.cnt[j];
+            S.order.assign(S.cnt[nr] ? S.cnt[nr] : 1, 0);
+            S.it.assign(nr, 0);
+            for (uint32_t j = 0; j < nr; ++j) {  // parents in increasing post-order position => deterministic sums
+              const uint32_t p = S.post[j];
+              const uint32_t flag = label[p] ? 0u : kOpOr;
+              for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+                const uint32_t c = S.newid[backref[q] ? label[q] : q];
+                S.order[S.cnt[c] + S.it[c]++] = j | flag;
+              }
+            }
+            s = 0;
+            for (uint32_t j = nr; j-- > 0;) {
+              const uint32_t k0 = S.cnt[j], k1 = S.cnt[j + 1];
+              if (k0 == k1) {
+                oo[(size_t)s++ * 32] = kOpFirst | kOpLast | kOpIdx;  // the root
+                continue;
+              }
+              for (uint32_t k = k0; k < k1; ++k)
+                oo[(size_t)s++ * 32] = S.order[k] | (k == k0 ? kOpFirst : 0u) | (k + 1 == k1 ? kOpLast : 0u);
+            }
+            continue;
+          }
           // counting sort by height, stable in pre-order
           S.cnt.assign(nl + 1, 0);
           for (uint32_t i = 0; i < n; ++i)
@@ -725,6 +1030,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
   const size_t real_b = f->precision == 64 ? 8 : 4;
   std::vector<std::vector<uint32_t>> by_cls(kNWarpCls + 1);
   for (uint64_t i = 0; i < nf; ++i) {
+    if (in_tile[i]) continue;
     int c = kNWarpCls;
     for (int k = 0; k < kNWarpCls; ++k)
       if (desc[i].n_nodes <= kWarpCaps[k] && (size_t)kWarpsPerCta * 2 * kWarpCaps[k] * real_b <= f->smem_optin) {
@@ -755,6 +1061,14 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
   CML_CUDA(bt->par.upload(h_par.data(), link_base[nf], f->stream));
   CML_CUDA(bt->lvl_off.upload(h_lvl.data(), h_lvl.size(), f->stream));
   CML_CUDA(bt->list.upload(list.data(), list.size(), f->stream));
+  if (bt->n_tiles) {
+    CML_CUDA(bt->tiles.upload(tiles.data(), tiles.size(), f->stream));
+    CML_CUDA(bt->t_ops_in.upload(h_ops_in.data(), h_ops_in.size(), f->stream));
+    CML_CUDA(bt->t_ops_out.upload(h_ops_out.data(), h_ops_out.size(), f->stream));
+    CML_CUDA(bt->t_label.upload(h_tlabel.data(), h_tlabel.size(), f->stream));
+    CML_CUDA(bt->t_in.alloc(bt->t_rows * real_b));
+    CML_CUDA(bt->t_ga.alloc(bt->t_rows * real_b));
+  }
   CML_CUDA(bt->ln_inside.alloc(nf));
   CML_CUDA(cudaEventCreate(&bt->ev0));
   CML_CUDA(cudaEventCreate(&bt->ev1));
@@ -802,6 +1116,10 @@ static int forest_rebuild_hot(cml_forests* f) {
   for (auto& bt : f->batches) {
     k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
     ++f->launches;
+    if (bt->n_tiles) {
+      k_forest_mark_hot<<<f_cdiv(bt->t_label.n, 256), 256, 0, f->stream>>>(bt->t_label.n, bt->t_label.p, f->hot_index.p);
+      ++f->launches;
+    }
   }
   CML_CUDA(cudaGetLastError());
   CML_CUDA(cudaStreamSynchronize(f->stream));
@@ -827,6 +1145,25 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
   A.ln_inside = bt.ln_inside.p;
   bt.n_kernels = 0;
   CML_CUDA(cudaEventRecord(bt.ev0, f->stream));
+  if (bt.n_tiles) {
+    TileArgs T{};
+    T.tiles = bt.tiles.p;
+    T.n_tiles = bt.n_tiles;
+    T.ops_in = bt.t_ops_in.p;
+    T.ops_out = bt.t_ops_out.p;
+    T.label = bt.t_label.p;
+    T.in_ = bt.t_in.p;
+    T.ga = bt.t_ga.p;
+    T.lnw = f->w_real.p;
+    T.hot_index = f->hot_index.p;
+    T.counts = f->reduce.p;
+    T.hot = f->hot.p;
+    T.n_hot = f->n_hot;
+    T.ln_inside = bt.ln_inside.p;
+    k_forest_thread<Real><<<f_cdiv(bt.n_tiles, kTileWarps), kTileWarps * 32, 0, f->stream>>>(T);
+    ++f->launches;
+    ++bt.n_kernels;
+  }
   for (int c = 0; c < kNWarpCls; ++c) {
     const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];
     if (!n) continue;
@@ -876,8 +1213,10 @@ extern "C" int cml_forests_estimate_launch(cml_forests* f) {
   for (auto& bt : f->batches) {
     const int rc = f->precision == 64 ? forest_launch<double>(f, *bt) : forest_launch<float>(f, *bt);
     if (rc) return rc;
-    k_forest_sum<<<1, 256, 0, f->stream>>>(bt->ln_inside.p, bt->n_forests, f->reduce.p + f->rulespace);
-    ++f->launches;
+    if (!f->sum_partial.p) CML_CUDA(f->sum_partial.alloc(2 * kSumBlocks));
+    k_forest_sum_partial<<<kSumBlocks, 256, 0, f->stream>>>(bt->ln_inside.p, bt->n_forests, f->sum_partial.p);
+    k_forest_sum<<<1, 256, 0, f->stream>>>(f->sum_partial.p, kSumBlocks, f->reduce.p + f->rulespace, bt->n_forests);
+    f->launches += 2;
   }
   if (f->n_hot) {
     k_forest_fold<<<f_cdiv(f->n_hot, 128), 128, 0, f->stream>>>(f->n_hot, f->hot_rule.p, f->hot.p, f->reduce.p);

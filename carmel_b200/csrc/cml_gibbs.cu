@@ -13,8 +13,10 @@
 // Modes
 //   sequential (exact): ONE CTA walks the blocks in corpus order; every block sees the counts that include
 //     the blocks sampled before it in this sweep, exactly like the reference (latency bound by design).
-//   batched: one CTA per block, all blocks sampled against the counts of the previous sweep (the
-//     reference's --include-self flavour of staleness), count deltas applied afterwards with fp64 REDs.
+//   batched: one WARP per block, all blocks sampled in parallel against the counts of the previous sweep minus
+//     the block's own previous sample (a synchronous version of "remove block, resample, add block"); the count
+//     deltas are applied afterwards with fp64 REDs.  Not sample-identical to the sequential sampler by
+//     construction; reported as final-perplexity agreement (tests/test_gibbs_gpu.py).
 #include <algorithm>
 #include <cmath>
 
@@ -49,7 +51,10 @@ struct GibbsArgs {
   double* count;
   double* normsum;
   const double* arc_lnw;       // per internal arc id (batched mode / initial sample from EM weights), may be NULL
-  double* beta;                // scratch: one double per lattice state
+  const uint32_t* au_off;      // per internal arc id: its parameters that have a CRP normalisation group (CSR)
+  const uint32_t* au_param;
+  const uint2* arc_pg;         // per internal arc id: {the one adjustable parameter, its group}; x = ~0 none, ~0-1 several (use the CSR)
+  double* beta;               // scratch: one double per lattice state
   const uint64_t* beta_base;
   const uint64_t* sample_base;
   const uint32_t* old_sample;  // arc-table ids of the previous sample
@@ -93,92 +98,286 @@ __device__ void add_sample_counts(const GibbsArgs& A, const uint32_t* arcs, uint
   }
 }
 
-// one block (example): backward filter over the layered CSR (log space), then forward sample by thread 0
-__device__ void sample_block(const GibbsArgs& A, uint32_t e) {
+// ---------------------------------------------------------------------------------------------------
+// One block (example) by a group of NT threads (NT = 32: a warp, batched mode; NT = blockDim: the CTA of the
+// sequential mode).  Backward filter over the layered CSR in log space, then a forward sample.
+//   backward, per level: phase 1 -- threads over the level's ARCS (coalesced 8-byte records, independent
+//   gathers of the arc's ln probability and beta[dst]) stage v = ln w + beta[dst] in shared memory;
+//   phase 2 -- threads over the level's STATES fold their contiguous run of staged values (online LSE, arcs in
+//   the stored order).  Levels with more arcs than the stage are processed in chunks.
+//   forward: the first warp evaluates the current state's arcs in parallel, lane 0 then replays the
+//   reference's three sequential loops (sum, psum, running choice; derivations.h:318-337, random.ipp:111-127)
+//   on the staged values, so the selected arc -- and the rounding that selects it -- is the sequential one.
+// ---------------------------------------------------------------------------------------------------
+// Batched mode, "remove the block before resampling it" (gibbs.hpp:844-859): every block is sampled against the
+// previous sweep's counts MINUS its own previous sample.  The subtraction is kept per block in two small shared
+// hash tables (parameter -> ln(1 - own/count), normalisation group -> -ln(1 - own/normsum)) and added to the frozen
+// per-arc table entry of every arc whose adjustable parameters they touch.
+const int kOwnCap = 128;  // entries per table (power of two); a block with more distinct parameters keeps the rest unadjusted
+struct OwnTables {
+  uint32_t* kp;
+  double* vp;
+  uint32_t* kg;
+  double* vg;
+};
+__device__ __forceinline__ uint32_t own_hash(uint32_t key) { return (key * 2654435761u) >> 25; }  // 7 bits
+__device__ __forceinline__ int own_find(const uint32_t* keys, uint32_t key) {
+  uint32_t i = own_hash(key);
+  for (int probe = 0; probe < kOwnCap; ++probe, i = (i + 1) & (kOwnCap - 1)) {
+    const uint32_t k = keys[i];
+    if (k == key) return (int)i;
+    if (k == 0xFFFFFFFFu) return -1;
+  }
+  return -1;
+}
+__device__ __forceinline__ void own_add(uint32_t* keys, double* vals, uint32_t key, double d) {
+  uint32_t i = own_hash(key);
+  for (int probe = 0; probe < kOwnCap - 8; ++probe, i = (i + 1) & (kOwnCap - 1)) {  // keep a few slots free: finds terminate
+    const uint32_t prev = atomicCAS(&keys[i], 0xFFFFFFFFu, key);
+    if (prev == 0xFFFFFFFFu || prev == key) {
+      atomicAdd(&vals[i], d);
+      return;
+    }
+  }
+}
+__device__ void own_build(const GibbsArgs& A, uint32_t e, int lane, const OwnTables& T) {
+  for (int i = lane; i < kOwnCap; i += 32) {
+    T.kp[i] = 0xFFFFFFFFu;
+    T.kg[i] = 0xFFFFFFFFu;
+    T.vp[i] = 0;
+    T.vg[i] = 0;
+  }
+  __syncwarp();
+  const uint32_t* arcs = A.old_sample + A.sample_base[e];
+  const uint32_t n = A.old_len[e];
+  const double wt = A.desc[e].weight;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t a = arcs[i];
+    const uint32_t k0 = A.chain_off ? A.chain_off[a] : a, k1 = A.chain_off ? A.chain_off[a + 1] : a + 1;
+    for (uint32_t k = k0; k < k1; ++k) {
+      const uint32_t p = A.chain_off ? A.chain_param[k] : k;
+      const uint32_t g = A.param_norm[p];
+      if (g == CML_NO_GROUP) continue;
+      own_add(T.kp, T.vp, p, wt);
+      own_add(T.kg, T.vg, g, wt);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < kOwnCap; i += 32) {
+    if (T.kp[i] != 0xFFFFFFFFu) {
+      const double r = 1. - T.vp[i] / A.count[T.kp[i]];
+      T.vp[i] = r > 0 ? log(r) : -CUDART_INF;
+    }
+    if (T.kg[i] != 0xFFFFFFFFu) {
+      const double r = 1. - T.vg[i] / A.normsum[T.kg[i]];
+      T.vg[i] = r > 0 ? -log(r) : 0.;
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ double own_correction(const GibbsArgs& A, const OwnTables* T, uint32_t internal_id) {
+  if (!T) return 0.;
+  double c = 0;
+  const uint2 pg = __ldg(&A.arc_pg[internal_id]);  // the common cases in one load: no / exactly one adjustable parameter
+  if (pg.x == 0xFFFFFFFFu) return 0.;
+  if (pg.x != 0xFFFFFFFEu) {
+    const int ig = own_find(T->kg, pg.y);
+    if (ig < 0) return 0.;
+    c = T->vg[ig];
+    const int ip = own_find(T->kp, pg.x);
+    return ip >= 0 ? c + T->vp[ip] : c;
+  }
+  for (uint32_t k = A.au_off[internal_id], k1 = A.au_off[internal_id + 1]; k < k1; ++k) {
+    const uint32_t p = A.au_param[k];
+    const int ig = own_find(T->kg, A.param_norm[p]);
+    if (ig < 0) continue;
+    c += T->vg[ig];
+    const int ip = own_find(T->kp, p);
+    if (ip >= 0) c += T->vp[ip];
+  }
+  return c;
+}
+
+template <int NT>
+__device__ __forceinline__ void gsync() {
+  if (NT == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+template <int NT>
+__device__ void sample_block(const GibbsArgs& A, uint32_t e, int tid, double* __restrict__ stage, uint32_t cap,
+                             const OwnTables* own = nullptr) {
   const CmlExDesc d = A.desc[e];
-  const uint32_t* lvl = A.lvl_off + d.lvl_base;
-  const uint32_t* ooff = A.out_off + d.row_base;
-  const uint2* oarc = A.out_arc + d.arc_base;
+  const uint32_t* __restrict__ lvl = A.lvl_off + d.lvl_base;
+  const uint32_t* __restrict__ ooff = A.out_off + d.row_base;
+  const uint2* __restrict__ oarc = A.out_arc + d.arc_base;
   double* be = A.beta + A.beta_base[e];
   const double NI = -CUDART_INF;
   const int nl = (int)d.n_levels;
+  const int nt = NT == 32 ? 32 : (int)blockDim.x;
   for (int L = nl - 1; L >= 0; --L) {
-    for (uint32_t s = lvl[L] + threadIdx.x; s < lvl[L + 1]; s += blockDim.x) {
+    const uint32_t s0 = lvl[L], s1 = lvl[L + 1];
+    for (uint32_t st0 = s0; st0 < s1; st0 += nt) {  // a tile of nt states and the arcs that leave them
+      const uint32_t st1 = min(st0 + (uint32_t)nt, s1);
+      const uint32_t t0 = ooff[st0], t1 = ooff[st1];
+      const uint32_t s = st0 + tid;
+      uint32_t r0 = 0, r1 = 0;
       double m = NI, acc = 0;
-      if (s == d.fin) {
-        m = 0;
-        acc = 1;
+      if (s < st1) {
+        r0 = ooff[s];
+        r1 = ooff[s + 1];
+        if (s == d.fin) {
+          m = 0;
+          acc = 1;
+        }
       }
-      for (uint32_t k = ooff[s]; k < ooff[s + 1]; ++k) {
-        const uint2 r = oarc[k];
-        const double v = arc_lnprob(A, r.y) + be[r.x];
-        if (v > m) {
-          acc = acc * exp(m - v) + 1.;
-          m = v;
-        } else if (v > NI)
-          acc += exp(v - m);
+      for (uint32_t c0 = t0; c0 < t1; c0 += cap) {
+        const uint32_t c1 = min(c0 + cap, t1);
+#pragma unroll 4
+        for (uint32_t k = c0 + tid; k < c1; k += nt) {
+          const uint2 r = oarc[k];
+          stage[k - c0] = arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x];
+        }
+        gsync<NT>();
+        for (uint32_t k = max(r0, c0), ke = min(r1, c1); k < ke; ++k) {
+          const double v = stage[k - c0];
+          if (v > m) {
+            acc = acc * exp(m - v) + 1.;
+            m = v;
+          } else if (v > NI)
+            acc += exp(v - m);
+        }
+        gsync<NT>();
       }
-      be[s] = (m > NI) ? m + log(acc) : NI;
+      if (s < st1) be[s] = (m > NI) ? m + log(acc) : NI;
     }
-    __syncthreads();
+    gsync<NT>();
   }
-  if (threadIdx.x == 0) {
+  if (tid < 32) {  // forward sample by the first warp
+    const int lane = tid;
     uint32_t* out = A.new_sample + A.sample_base[e];
     uint32_t n = 0, s = 0, draw = 0;  // the start state has layered index 0
     while (s != d.fin) {
       const uint32_t k0 = ooff[s], k1 = ooff[s + 1];
       if (k0 == k1) break;  // cannot happen on a pruned lattice
-      // global_normalize: nw = (w*beta)^power ; p = nw / sum
-      double m = NI;
-      for (uint32_t k = k0; k < k1; ++k) {
-        const uint2 r = oarc[k];
-        m = fmax(m, A.power * (arc_lnprob(A, r.y) + be[r.x]));
-      }
-      double sum = 0;
-      for (uint32_t k = k0; k < k1; ++k) {
-        const uint2 r = oarc[k];
-        const double v = A.power * (arc_lnprob(A, r.y) + be[r.x]);
-        if (v > NI) sum += exp(v - m);
-      }
-      // choose_p: psum = sum of normalised p (~1); choice = psum * u; first arc where the running
-      // remainder goes negative (or the last arc)
-      double psum = 0;
-      for (uint32_t k = k0; k < k1; ++k) {
-        const uint2 r = oarc[k];
-        const double v = A.power * (arc_lnprob(A, r.y) + be[r.x]);
-        psum += (v > NI && sum > 0) ? exp(v - m) / sum : 0.;
-      }
-      double choice = psum * gibbs_uniform(A.seed, A.sweep, d.ex_index, draw++);
+      const uint32_t deg = k1 - k0;
       uint32_t pick = k1 - 1;
-      for (uint32_t k = k0; k < k1; ++k) {
-        const uint2 r = oarc[k];
-        const double v = A.power * (arc_lnprob(A, r.y) + be[r.x]);
-        choice -= (v > NI && sum > 0) ? exp(v - m) / sum : 0.;
-        if (choice < 0) {
-          pick = k;
-          break;
+      if (deg <= cap) {
+        // global_normalize: nw = (w*beta)^power ; p = nw / sum -- values staged once, loops replayed by lane 0
+        for (uint32_t j = lane; j < deg; j += 32) {
+          const uint2 r = oarc[k0 + j];
+          stage[j] = A.power * (arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          double m = NI;
+          for (uint32_t j = 0; j < deg; ++j) m = fmax(m, stage[j]);
+          double sum = 0;
+          for (uint32_t j = 0; j < deg; ++j) {
+            const double v = stage[j];
+            const double ex = v > NI ? exp(v - m) : 0.;
+            stage[j] = ex;
+            sum += ex;
+          }
+          double psum = 0;
+          for (uint32_t j = 0; j < deg; ++j) {
+            const double pj = sum > 0 ? stage[j] / sum : 0.;
+            stage[j] = pj;
+            psum += pj;
+          }
+          double choice = psum * gibbs_uniform(A.seed, A.sweep, d.ex_index, draw);
+          for (uint32_t j = 0; j < deg; ++j) {
+            choice -= stage[j];
+            if (choice < 0) {
+              pick = k0 + j;
+              break;
+            }
+          }
+        }
+      } else if (lane == 0) {  // very wide state: recompute per pass (no staging)
+        double m = NI;
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint2 r = oarc[k];
+          m = fmax(m, A.power * (arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x]));
+        }
+        double sum = 0;
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint2 r = oarc[k];
+          const double v = A.power * (arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x]);
+          if (v > NI) sum += exp(v - m);
+        }
+        double psum = 0;
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint2 r = oarc[k];
+          const double v = A.power * (arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x]);
+          psum += (v > NI && sum > 0) ? exp(v - m) / sum : 0.;
+        }
+        double choice = psum * gibbs_uniform(A.seed, A.sweep, d.ex_index, draw);
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint2 r = oarc[k];
+          const double v = A.power * (arc_lnprob(A, r.y) + own_correction(A, own, r.y) + be[r.x]);
+          choice -= (v > NI && sum > 0) ? exp(v - m) / sum : 0.;
+          if (choice < 0) {
+            pick = k;
+            break;
+          }
         }
       }
-      out[n++] = A.arc_orig[oarc[pick].y];
-      s = oarc[pick].x;
+      ++draw;
+      pick = __shfl_sync(0xffffffffu, pick, 0);
+      const uint2 pr = oarc[pick];
+      if (lane == 0) out[n] = A.arc_orig[pr.y];
+      ++n;
+      s = pr.x;
+      __syncwarp();
     }
-    A.new_len[e] = n;
+    if (lane == 0) A.new_len[e] = n;
   }
-  __syncthreads();
+  gsync<NT>();
 }
 
-__global__ void __launch_bounds__(128) k_gibbs(GibbsArgs A) {
-  if (A.sequential) {  // one CTA, blocks in corpus order, counts updated in place between blocks
-    for (uint32_t e = 0; e < A.n_ex; ++e) {
-      const double wt = A.desc[e].weight;
-      if (threadIdx.x == 0) add_sample_counts(A, A.old_sample + A.sample_base[e], A.old_len[e], -wt, false);
-      __syncthreads();
-      sample_block(A, e);
-      if (threadIdx.x == 0) add_sample_counts(A, A.new_sample + A.sample_base[e], A.new_len[e], wt, false);
+const int kGibbsStage = 384;       // staged arc values per warp (batched mode): 3 KB (+3 KB of own-sample tables => 37 warps/SM)
+const int kGibbsWarps = 4;
+const int kGibbsSeqThreads = 1024;
+const int kGibbsSeqStage = 4096;   // sequential mode: one CTA, 32 KB stage
+
+// batched mode: one warp per block, every block against the frozen per-arc table of this sweep
+__global__ void __launch_bounds__(kGibbsWarps * 32) k_gibbs_batched(GibbsArgs A) {
+  __shared__ double stage_all[kGibbsWarps * kGibbsStage];
+  __shared__ double own_v[kGibbsWarps * 2 * kOwnCap];
+  __shared__ uint32_t own_k[kGibbsWarps * 2 * kOwnCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* stage = stage_all + warp * kGibbsStage;
+  OwnTables T;
+  T.kp = own_k + warp * 2 * kOwnCap;
+  T.kg = T.kp + kOwnCap;
+  T.vp = own_v + warp * 2 * kOwnCap;
+  T.vg = T.vp + kOwnCap;
+  for (uint32_t e = blockIdx.x * kGibbsWarps + warp; e < A.n_ex; e += gridDim.x * kGibbsWarps) {
+    const bool excl = A.au_off != nullptr && A.old_len[e] != 0;
+    if (excl) own_build(A, e, lane, T);
+    sample_block<32>(A, e, lane, stage, kGibbsStage, excl ? &T : nullptr);
+  }
+}
+
+// sequential (exact) mode: one CTA walks the blocks in corpus order; counts updated in place between blocks and the
+// per-arc ln-probability table rebuilt from them (all threads) before every block
+__global__ void __launch_bounds__(kGibbsSeqThreads) k_gibbs_sequential(GibbsArgs A, double* __restrict__ tbl, uint32_t n_tbl) {
+  __shared__ double stage[kGibbsSeqStage];
+  GibbsArgs B = A;
+  B.arc_lnw = tbl;
+  for (uint32_t e = 0; e < A.n_ex; ++e) {
+    const double wt = A.desc[e].weight;
+    if (threadIdx.x == 0) add_sample_counts(A, A.old_sample + A.sample_base[e], A.old_len[e], -wt, false);
+    __syncthreads();
+    if (!A.arc_lnw) {
+      for (uint32_t a = threadIdx.x; a < n_tbl; a += blockDim.x) tbl[a] = arc_lnprob(A, a);
       __syncthreads();
     }
-  } else {
-    for (uint32_t e = blockIdx.x; e < A.n_ex; e += gridDim.x) sample_block(A, e);
+    sample_block<kGibbsSeqThreads>(A.arc_lnw ? A : B, e, (int)threadIdx.x, stage, kGibbsSeqStage);
+    if (threadIdx.x == 0) add_sample_counts(A, A.new_sample + A.sample_base[e], A.new_len[e], wt, false);
+    __syncthreads();
   }
 }
 
@@ -235,6 +434,42 @@ extern "C" int cml_gibbs_init(cml_ctx* ctx, const cml_gibbs_model* g) {
   std::vector<uint32_t> orig((size_t)ctx->n_arcs + 1);
   for (uint32_t a = 0; a <= ctx->n_arcs; ++a) orig[ctx->h_perm[a]] = a;
   CML_CUDA(ctx->g_arc_orig.upload(orig.data(), orig.size(), s));
+  {  // per internal arc: the parameters of its chain that have a CRP group (what removing a block can change)
+    std::vector<uint32_t> coff, cpar;
+    if (!ctx->trivial) {
+      coff.resize((size_t)ctx->n_arcs + 1);
+      CML_CUDA(cudaMemcpyAsync(coff.data(), ctx->chain_off.p, coff.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CML_CUDA(cudaStreamSynchronize(s));
+      cpar.resize(coff[ctx->n_arcs]);
+      if (!cpar.empty()) CML_CUDA(cudaMemcpyAsync(cpar.data(), ctx->chain_param.p, cpar.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CML_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<uint32_t> au_off((size_t)ctx->n_arcs + 2, 0), au_param;
+    for (uint32_t i = 0; i <= ctx->n_arcs; ++i) {  // i = internal id (n_arcs = the padding arc: empty)
+      if (i < ctx->n_arcs) {
+        const uint32_t a = orig[i];
+        const uint32_t k0 = ctx->trivial ? a : coff[a], k1 = ctx->trivial ? a + 1 : coff[a + 1];
+        for (uint32_t k = k0; k < k1; ++k) {
+          const uint32_t p = ctx->trivial ? k : cpar[k];
+          if (g->param_norm[p] != CML_NO_GROUP) au_param.push_back(p);
+        }
+      }
+      au_off[i + 1] = (uint32_t)au_param.size();
+    }
+    std::vector<uint2> pg((size_t)ctx->n_arcs + 1);
+    for (uint32_t i = 0; i <= ctx->n_arcs; ++i) {
+      const uint32_t n = au_off[i + 1] - au_off[i];
+      if (n == 0)
+        pg[i] = make_uint2(0xFFFFFFFFu, 0u);
+      else if (n == 1)
+        pg[i] = make_uint2(au_param[au_off[i]], g->param_norm[au_param[au_off[i]]]);
+      else
+        pg[i] = make_uint2(0xFFFFFFFEu, 0u);
+    }
+    CML_CUDA(ctx->g_arc_pg.upload(pg.data(), pg.size(), s));
+    CML_CUDA(ctx->g_au_off.upload(au_off.data(), au_off.size(), s));
+    CML_CUDA(ctx->g_au_param.upload(au_param.data(), au_param.size(), s));
+  }
   // per-example bases: sample slots (n_levels each) and beta scratch (n_states each)
   std::vector<uint64_t> sbase(bt.n_ex + 1, 0), bbase(bt.n_ex + 1, 0);
   for (uint64_t e = 0; e < bt.n_ex; ++e) {
@@ -277,6 +512,9 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
   A.count = ctx->g_count.p;
   A.normsum = ctx->g_normsum.p;
   A.arc_lnw = nullptr;
+  A.au_off = o->init_from_params ? nullptr : ctx->g_au_off.p;  // no own-block removal when sampling from fixed EM weights
+  A.au_param = ctx->g_au_param.p;
+  A.arc_pg = ctx->g_arc_pg.p;
   A.beta = ctx->g_beta.p;
   A.beta_base = ctx->g_beta_base.p;
   A.sample_base = ctx->g_sample_base.p;
@@ -311,10 +549,11 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
     A.arc_lnw = (const double*)ctx->arc_w_real.p;
   }
   if (A.sequential) {
-    k_gibbs<<<1, 128, 0, s>>>(A);
+    if (ctx->g_tbl.n < (size_t)ctx->n_arcs + 1) CML_CUDA(ctx->g_tbl.alloc((size_t)ctx->n_arcs + 1));
+    k_gibbs_sequential<<<1, kGibbsSeqThreads, 0, s>>>(A, ctx->g_tbl.p, ctx->n_arcs);
     ++ctx->launches;
   } else {
-    k_gibbs<<<std::min<unsigned>(A.n_ex, 148 * 16), 128, 0, s>>>(A);
+    k_gibbs_batched<<<std::max(1u, std::min<unsigned>(cdiv(A.n_ex, kGibbsWarps), (unsigned)ctx->sm_count * 16u)), kGibbsWarps * 32, 0, s>>>(A);
     k_gibbs_apply<<<cdiv(A.n_ex, 128), 128, 0, s>>>(A);
     ctx->launches += 2;
   }

@@ -205,6 +205,12 @@ struct TrainJob {
   double estimate(double& ln_unweighted);
   TrainResult const& run(std::ostream& log);        // EM (WFST::train)
   TrainResult const& run_gibbs(std::ostream& log);  // --crp (WFST::train_gibbs)
+  void prepare_gibbs();  // lattices + CRP parameters on the GPU, counts = priors; no sweep yet
+  bool gibbs_prepared = false;
+  std::vector<uint32_t> g_norm;  // CRP normalisation group of every parameter (kNoGroup = fixed probability)
+  std::vector<double> g_prior;   // pseudo-count (or the fixed probability)
+  std::vector<uint64_t> g_base;  // sample slot base of every resident example
+  uint32_t g_n_norms = 0;
   void write_back();
   void write_outputs(std::ostream& out);  // trained transducer(s) as carmel writes them
   void finish();

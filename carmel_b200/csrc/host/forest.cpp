@@ -292,6 +292,7 @@ void ForestJob::prepare() {
   }
   if (cml_forests_create(&ctx, opt.device, opt.double_precision ? 64 : 32) != CML_OK)
     throw std::runtime_error(std::string("GPU library: ") + cml_forests_last_error(nullptr));
+  ok(cml_forests_set_layout(ctx, opt.layout));
   ok(cml_forests_set_rules(ctx, rulespace, groups.size(), groups.off.data(), groups.members.data()));
   ok(cml_forests_set_params(ctx, ln_w.data()));
   if (have_init_params && opt.normalize_initial && groups.size()) ok(cml_forests_normalize_params(ctx));
@@ -491,6 +492,11 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
         if (key == "history") { a.history_file = val; continue; }
         if (key == "print-forests") { a.print_forests_file = val; continue; }
         if (key == "parse-only") { a.parse_only = true; continue; }
+        if (key == "layout") {
+          if (val != "auto" && val != "group" && val != "thread") throw std::runtime_error("--layout=auto|group|thread");
+          a.layout = val == "group" ? CML_FOREST_LAYOUT_GROUP : val == "thread" ? CML_FOREST_LAYOUT_THREAD : CML_FOREST_LAYOUT_AUTO;
+          continue;
+        }
         if (key == "gpu") { a.device = std::atoi(val.c_str()); continue; }
         if (key == "shard") {
           const size_t sl = val.find('/');

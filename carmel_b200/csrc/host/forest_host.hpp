@@ -54,7 +54,8 @@ struct ForestOpts {
   unsigned log_level = 1;              // -L
   int device = 0;                      // --gpu=n
   int shard_rank = 0, shard_count = 1;  // --shard=r/N
-  bool parse_only = false;             // --parse-only : read (and --print-forests) without touching the GPU
+  int layout = CML_FOREST_LAYOUT_AUTO;  // --layout=auto|group|thread (device layout family, see cml_forests_set_layout)
+  bool parse_only = false;            // --parse-only : read (and --print-forests) without touching the GPU
 };
 
 struct ForestIter {

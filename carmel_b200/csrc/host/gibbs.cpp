@@ -61,7 +61,9 @@ void add_gibbs_params(Wfst const& w, NormalizeMethod const& nm, bool uniform_p0,
 
 }  // namespace
 
-TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
+// everything up to the first sweep: lattices resident, CRP parameters defined, counts = priors
+void TrainJob::prepare_gibbs() {
+  if (gibbs_prepared) return;
   GibbsOpts& g = gopt;
   for (auto& m : methods)  // gibbs.cc:390-397
     if (!(m.ln_add_count > kNegInf)) {
@@ -75,9 +77,12 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
   opt.no_ell = true;
   prepare();
 
-  std::vector<uint32_t> norm;
-  std::vector<double> prior;
-  uint32_t n_norms = 0;
+  std::vector<uint32_t>& norm = g_norm;
+  std::vector<double>& prior = g_prior;
+  uint32_t& n_norms = g_n_norms;
+  norm.clear();
+  prior.clear();
+  n_norms = 0;
   for (size_t i = 0; i < members.size(); ++i)
     add_gibbs_params(*members[i], i < methods.size() ? methods[i] : NormalizeMethod(), g.uniform_p0, g.dirichlet_p0, n_norms,
                      norm, prior);
@@ -88,16 +93,25 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
   gm.param_prior = prior.data();
   gm.n_norms = n_norms;
   ok(cml_gibbs_init(ctx, &gm));
-
-  const uint64_t cap = cml_gibbs_sample_capacity(ctx);
-  std::vector<uint32_t> path_len(res.examples), path_arcs(cap);
   // sample slot bases (= prefix sums of lattice level counts) are recomputed from the layout
-  std::vector<uint64_t> base(res.examples + 1, 0);
+  g_base.assign(res.examples + 1, 0);
   for (uint64_t e = 0; e < res.examples; ++e) {
     uint32_t nl = 0;
     ok(cml_get_example_layout(ctx, e, &nl, nullptr, nullptr));
-    base[e + 1] = base[e] + nl;
+    g_base[e + 1] = g_base[e] + nl;
   }
+  gibbs_prepared = true;
+}
+
+TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
+  prepare_gibbs();
+  GibbsOpts& g = gopt;
+  std::vector<uint32_t> const& norm = g_norm;
+  std::vector<double> const& prior = g_prior;
+  const uint32_t n_norms = g_n_norms;
+  std::vector<uint64_t> const& base = g_base;
+  const uint64_t cap = cml_gibbs_sample_capacity(ctx);
+  std::vector<uint32_t> path_len(res.examples), path_arcs(cap);
   auto time_of = [&](uint32_t it) { return it > g.burnin ? (double)it - (double)g.burnin : 0.; };
   std::vector<double> ccount(M.n_params), csum(std::max<uint32_t>(1, n_norms));
   const double n_sym = corpus.n_output;

@@ -267,7 +267,10 @@ extern "C" int cml_job_set_allreduce(cml_job* j, cml_allreduce_fn fn, void* user
 }
 extern "C" int cml_job_prepare(cml_job* j) {
   return guarded(j, [&]() {
-    j->job.prepare();
+    if (j->job.gopt.enabled)
+      j->job.prepare_gibbs();  // --crp: also defines the CRP parameters (counts = priors)
+    else
+      j->job.prepare();
     return (int)CML_OK;
   });
 }

@@ -47,6 +47,8 @@ def _lib():
         lib.cml_forests_last_error.argtypes = [_vp]
         lib.cml_forests_last_error.restype = C.c_char_p
         lib.cml_forests_set_stream.argtypes = [_vp, _vp]
+        lib.cml_forests_set_layout.argtypes = [_vp, C.c_int]
+        lib.cml_forests_layout_stats.argtypes = [_vp] + [_u64p] * 5
         lib.cml_forests_launch_count.argtypes = [_vp]
         lib.cml_forests_launch_count.restype = C.c_uint64
         lib.cml_forests_set_rules.argtypes = [_vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
@@ -115,6 +117,15 @@ class Forests:
 
     def set_stream(self, cuda_stream: int):
         self._ok(self.lib.cml_forests_set_stream(self.h, _vp(cuda_stream)))
+
+    def set_layout(self, layout: int):
+        """0 auto, 1 warp/CTA per forest, 2 thread per forest"""
+        self._ok(self.lib.cml_forests_set_layout(self.h, layout))
+
+    def layout_stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(5)]
+        self._ok(self.lib.cml_forests_layout_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("tile_forests", "tiles", "steps", "padded_steps", "padded_rows"), (x.value for x in v)))
 
     def set_rules(self, rulespace: int, group_off, group_members):
         go, gm = _arr(group_off, np.uint64), _arr(group_members, np.uint64)

@@ -287,6 +287,14 @@ int cml_forests_create(cml_forests** out, int device, int precision /* 32 | 64 *
 void cml_forests_destroy(cml_forests* f);
 const char* cml_forests_last_error(cml_forests* f);
 int cml_forests_set_stream(cml_forests* f, void* cuda_stream);
+/* Device layout of the forests added afterwards.  AUTO: corpora of many small forests use one thread per forest
+ * (32 forests per warp, transposed streams); few or large forests use one warp / one CTA per forest with
+ * height-levelised CSRs.  The other two values force one family (tests, measurements). */
+enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1, CML_FOREST_LAYOUT_THREAD = 2 };
+int cml_forests_set_layout(cml_forests* f, int layout);
+/* thread-per-forest tiles resident: forests in tiles, tiles, real steps, padded steps, padded value rows x 32 */
+int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, uint64_t* tiles, uint64_t* steps, uint64_t* padded_steps,
+                             uint64_t* padded_rows);
 uint64_t cml_forests_launch_count(cml_forests* f);
 /* rulespace = 1 + largest rule id; groups = the normalization groups file ((1 2 3) (4 5)) as CSR of rule ids */
 int cml_forests_set_rules(cml_forests* f, uint64_t rulespace, uint64_t n_groups, const uint64_t* group_off,

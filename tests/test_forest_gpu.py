@@ -35,30 +35,35 @@ def _close_ln(a, b, rel, floor=-60.0):
     return abs(math.expm1(a - b)) <= rel if abs(a - b) < 1 else False
 
 
-def _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel, check_index=True):
+def _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel, check_index=True, layouts=("group", "thread")):
+    """product (every device layout family) against the oracle: history, weights, counts, per-forest inside"""
     d = str(tmp_path)
-    rc, out, err = run(fem, [*mode, *args, "-o", f"{d}/p.w", "-O", f"{d}/p.c", "-S", f"{d}/p.s", f"--history={d}/p.h"])
-    assert rc == 0, err
     rc, out, oerr = run(forest_oracle_bin, [*mode, *args, "-o", f"{d}/o.w", "-O", f"{d}/o.c", "-S", f"{d}/o.s", f"--history={d}/o.h"])
     assert rc == 0, oerr
-    hp, ho = _hist(f"{d}/p.h"), _hist(f"{d}/o.h")
-    assert len(hp) == len(ho), (len(hp), len(ho), err[-2000:])
-    for a, b in zip(hp, ho):
-        assert a[0] == b[0] and a[4] == b[4], (a, b)
-        assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (a, b)
-        assert abs(a[2] - b[2]) <= 20 * rel * max(1.0, abs(b[2])) + 1e-12, (a, b)
-        if check_index and rel <= 1e-6 and b[2] > 1e-3:
-            assert a[3] == b[3], (a, b)
-    # per-forest ln inside: in fp32 both sides carry the rounding of intermediate logs that are much larger in
-    # magnitude than the result (sums over thousands of derivations), so the float-vs-float bound is looser
-    for name, tol in (("w", 20 * rel), ("c", 20 * rel), ("s", rel if rel <= 1e-6 else 10 * rel)):
-        got, want = read_weights(f"{d}/p.{name}"), read_weights(f"{d}/o.{name}")
-        assert len(got) == len(want), (name, len(got), len(want))
-        for i, (a, b) in enumerate(zip(got, want)):
-            if name == "s":
-                assert (a == b) or abs(a - b) <= tol * max(1.0, abs(b)), (name, i, a, b)
-            else:
-                assert _close_ln(a, b, tol), (name, i + 1, a, b)
+    ho = _hist(f"{d}/o.h")
+    err = ""
+    for layout in layouts:
+        rc, out, err = run(fem, [*mode, *args, f"--layout={layout}", "-o", f"{d}/p.w", "-O", f"{d}/p.c", "-S", f"{d}/p.s",
+                                 f"--history={d}/p.h"])
+        assert rc == 0, err
+        hp = _hist(f"{d}/p.h")
+        assert len(hp) == len(ho), (layout, len(hp), len(ho), err[-2000:])
+        for a, b in zip(hp, ho):
+            assert a[0] == b[0] and a[4] == b[4], (layout, a, b)
+            assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (layout, a, b)
+            assert abs(a[2] - b[2]) <= 20 * rel * max(1.0, abs(b[2])) + 1e-12, (layout, a, b)
+            if check_index and rel <= 1e-6 and b[2] > 1e-3:
+                assert a[3] == b[3], (layout, a, b)
+        # per-forest ln inside: in fp32 both sides carry the rounding of intermediate logs that are much larger in
+        # magnitude than the result (sums over thousands of derivations), so the float-vs-float bound is looser
+        for name, tol in (("w", 20 * rel), ("c", 20 * rel), ("s", rel if rel <= 1e-6 else 10 * rel)):
+            got, want = read_weights(f"{d}/p.{name}"), read_weights(f"{d}/o.{name}")
+            assert len(got) == len(want), (layout, name, len(got), len(want))
+            for i, (a, b) in enumerate(zip(got, want)):
+                if name == "s":
+                    assert (a == b) or abs(a - b) <= tol * max(1.0, abs(b)), (layout, name, i, a, b)
+                else:
+                    assert _close_ln(a, b, tol), (layout, name, i + 1, a, b)
     return err
 
 
@@ -130,15 +135,16 @@ def test_cipher_forests_golden_trajectory(fem, oracle_bin, tmp_path):
     rc, out, err = run(oracle_bin, ["--train-cascade", "--normby=NC", "-HJ", f"--fem-forest={d}/c.forest", f"--fem-norm={d}/c.norm",
                                     f"--fem-param={d}/c.param", data, wfsa, fst])
     assert rc == 0, err
-    rc, out, err = run(fem, ["-U", "-f", f"{d}/c.forest", "-n", f"{d}/c.norm", "-I", f"{d}/c.param", "-i", "22", "-e", "0",
-                             f"--history={d}/h"])
-    assert rc == 0, err
     want = golden()["cipher"]["trajectory_log2"]
-    hist = _hist(f"{d}/h")
-    assert len(hist) == len(want) == 22
-    for (it, log2p), h in zip(want, hist):
-        got = h[1] * 10 / math.log(2)
-        assert h[0] == it and abs(got - log2p) <= 1.01e-5 * abs(log2p), (it, got, log2p)
+    for layout in ("group", "thread"):
+        rc, out, err = run(fem, ["-U", "-f", f"{d}/c.forest", "-n", f"{d}/c.norm", "-I", f"{d}/c.param", "-i", "22", "-e", "0",
+                                 f"--layout={layout}", f"--history={d}/h"])
+        assert rc == 0, err
+        hist = _hist(f"{d}/h")
+        assert len(hist) == len(want) == 22
+        for (it, log2p), h in zip(want, hist):
+            got = h[1] * 10 / math.log(2)
+            assert h[0] == it and abs(got - log2p) <= 1.01e-5 * abs(log2p), (layout, it, got, log2p)
 
 
 def test_errors(fem, tmp_path):
