@@ -20,7 +20,7 @@ NO_GROUP = 0xFFFFFFFF
 LOCKED_GROUP = 0
 
 OPT_ARC_COUNTS, OPT_NO_ELL = 1, 2
-OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV, ERR_NOT_DENSE = 0, -1, -2, -3, -4, -5, -6
 
 _u32p = C.POINTER(C.c_uint32)
 _f64p = C.POINTER(C.c_double)
@@ -39,6 +39,15 @@ class CmlTrellisBatch(C.Structure):
         ("n_ex", C.c_uint64), ("ex_states", _u32p), ("ex_fin", _u32p), ("ex_weight", _f64p),
         ("arc_off", _u32p), ("arc_dst", _u32p), ("arc_id", _u32p),
     ]
+
+
+class CmlDenseView(C.Structure):
+    _fields_ = [("n_states", C.c_uint32), ("n_symbols", C.c_uint32), ("start", C.c_uint32), ("final_state", C.c_uint32),
+                ("arc_src", _u32p), ("arc_dst", _u32p), ("arc_sym", _u32p)]
+
+
+class CmlSequenceBatch(C.Structure):
+    _fields_ = [("n_seq", C.c_uint64), ("seq_off", C.POINTER(C.c_uint64)), ("sym", _u32p), ("seq_weight", _f64p)]
 
 
 class CmlEstimateResult(C.Structure):
@@ -97,6 +106,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_restore_params.argtypes = [vp, C.c_int]
     lib.cml_add_trellises.argtypes = [vp, C.POINTER(CmlTrellisBatch)]
     lib.cml_clear_trellises.argtypes = [vp]
+    lib.cml_add_sequences.argtypes = [vp, C.POINTER(CmlDenseView), C.POINTER(CmlSequenceBatch)]
+    lib.cml_dense_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _u32p, _u32p]
     lib.cml_trellis_totals.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_get_example_layout.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u32p]
     lib.cml_estimate.argtypes = [vp, C.POINTER(CmlEstimateResult)]
@@ -253,6 +264,30 @@ class Context:
 
     def clear_trellises(self):
         self._check(self.lib.cml_clear_trellises(self.h))
+
+    def add_sequences(self, n_states, n_symbols, start, final_state, arc_src, arc_dst, arc_sym, seqs, weights=None):
+        """dense-state view (cml_add_sequences): seqs = list of symbol-id sequences.  Raises CarmelB200Error with
+        code ERR_NOT_DENSE when the arc table has no transition x emission factorisation."""
+        v, b = CmlDenseView(), CmlSequenceBatch()
+        a_s, a_d, a_y = _u32(arc_src), _u32(arc_dst), _u32(arc_sym)
+        v.n_states, v.n_symbols, v.start, v.final_state = n_states, n_symbols, start, final_state
+        v.arc_src, v.arc_dst, v.arc_sym = _ptr(a_s, _u32p), _ptr(a_d, _u32p), _ptr(a_y, _u32p)
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        off[1:] = np.cumsum([len(q) for q in seqs])
+        sym = _u32(np.concatenate([np.asarray(q, np.uint32) for q in seqs]) if len(seqs) else np.zeros(0, np.uint32))
+        if sym.size == 0:
+            sym = np.zeros(1, np.uint32)
+        w = _f64(weights if weights is not None else np.ones(len(seqs)))
+        b.n_seq = len(seqs)
+        b.seq_off = off.ctypes.data_as(C.POINTER(C.c_uint64))
+        b.sym, b.seq_weight = _ptr(sym, _u32p), _ptr(w, _f64p)
+        self._check(self.lib.cml_add_sequences(self.h, C.byref(v), C.byref(b)))
+
+    def dense_stats(self) -> dict:
+        a, b_ = C.c_uint64(), C.c_uint64()
+        c, d = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.cml_dense_stats(self.h, C.byref(a), C.byref(b_), C.byref(c), C.byref(d)))
+        return dict(sequences=int(a.value), positions=int(b_.value), t_slots=int(c.value), e_slots=int(d.value))
 
     def trellis_totals(self) -> dict:
         v = [C.c_uint64() for _ in range(4)]

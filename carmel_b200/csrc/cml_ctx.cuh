@@ -7,6 +7,7 @@
 #include "cml_common.cuh"
 #include "cml_kernels_ell.cuh"
 #include "cml_kernels_fb.cuh"
+#include "cml_kernels_lane.cuh"
 
 // ---- example classes ------------------------------------------------------------------------------
 // ELL classes (scaled space only): one example per group of 4/8/16/32 lanes, level-sliced ELL layout.
@@ -48,6 +49,15 @@ struct Batch {
   uint32_t ell_ring[NELL] = {0};
   DevArray<unsigned char> alpha_g;
   DevArray<int> lvl_exp;
+  // --- lane part (k_fb_lane: one lattice per lane, tiles of 32)
+  uint64_t lane_ex = 0, lane_arcs = 0, lane_records = 0;
+  uint32_t lane_tiles = 0;
+  DevArray<cmlk::LaneTile> ltile;
+  DevArray<uint2> lane_fw, lane_bw;
+  DevArray<uint32_t> lane_exidx, lane_fin, lane_nlev;
+  DevArray<double> lane_weight;
+  DevArray<unsigned char> lane_alpha;
+  DevArray<int> lane_lvle;
   cudaEvent_t ev_fb0 = nullptr, ev_fb1 = nullptr;  // bracket this batch's forward-backward kernels
   uint32_t n_fb_kernels = 0;
   ~Batch() {
@@ -57,6 +67,27 @@ struct Batch {
   // host copies kept for introspection (cml_get_example_layout)
   std::vector<uint64_t> h_state_base;
   std::vector<uint32_t> h_level_of, h_local_of, h_nlevels;
+};
+
+// Dense-state sequences (cml_add_sequences, cml_dense.cu): w(i -> j, o) = T[i][j] * E[j][o].
+struct DenseState {
+  uint32_t S = 0, n_sym = 0, start = 0, fin = 0;
+  uint64_t n_seq = 0, n_pos = 0;
+  uint32_t n_t_slots = 0, n_e_slots = 0;
+  uint32_t n_cells = 0;  // 32*32 T cells then n_sym*32 E cells (symbol major)
+  DevArray<uint32_t> cell_off, cell_param, cell_slot;
+  DevArray<unsigned char> cell_exists;
+  DevArray<unsigned char> tables;  // Real T[32][32] then Real Et[n_sym][32]
+  DevArray<uint64_t> seq_off;
+  DevArray<uint16_t> sym;
+  DevArray<double> seq_weight, ex_lnp;
+  DevArray<unsigned char> alpha_g;  // Real[(n_pos + n_seq)][32]
+  DevArray<int> exp_g;              // cumulative power-of-two exponent of every alpha row
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ~DenseState() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
 };
 
 struct cml_ctx {
@@ -71,6 +102,8 @@ struct cml_ctx {
   uint64_t launches = 0;
   int opt_arc_counts = 0;  // CML_OPT_ARC_COUNTS: keep one count slot per arc-table entry
   int opt_no_ell = 0;      // CML_OPT_NO_ELL: force the CSR kernels (tests)
+  int opt_lane_min = 16384;  // CML_OPT_LANE_MIN: eligible lattices needed before the lane kernel is used (0 = never)
+  int opt_no_counts = 0;     // CML_OPT_NO_COUNTS: profiling only, the sweeps skip their count REDs (lane kernel)
 
   // model
   bool have_model = false, trivial = true;
@@ -102,6 +135,10 @@ struct cml_ctx {
 
   std::vector<std::unique_ptr<Batch>> batches;
   bool estimate_pending = false;
+  // host copies of the chains (the dense-state factorisation needs them)
+  std::vector<uint32_t> h_chain_off, h_chain_param, h_param_tie;
+  std::vector<double> h_arc_prior;
+  std::unique_ptr<DenseState> dense;  // non-null: the E-step runs over dense-state sequences
 
   // --crp Gibbs sampling state (cml_gibbs.cu)
   bool have_gibbs = false;
@@ -114,6 +151,8 @@ struct cml_ctx {
   uint64_t g_sample_cap = 0;
   int g_cur = 0;  // which sample buffer holds the current sample
 };
+
+int cml_dense_estimate_launch(cml_ctx* ctx);  // cml_dense.cu
 
 #define CML_REQUIRE(cond, code, msg) \
   do {                               \

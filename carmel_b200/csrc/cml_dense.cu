@@ -1,0 +1,546 @@
+// cml_dense.cu -- the dense-state E-step (K7): forward / backward / expected counts over position-synchronous
+// lattices that are never materialised.
+//
+// Reference semantics (restated, not copied): the same per-example computation as the lattice kernels --
+//   derivations::compute / derive      carmel/src/derivations.h:479-513,640-704   (lattice state = (position, WFST state))
+//   compute_fb                         carmel/src/derivations.h:400-417
+//   collect_counts                     carmel/src/derivations.h:432-449
+//   cascade_parameters chains          carmel/src/cascade.h:426-433 (arc weight = product of its chain)
+// -- for a transducer whose every arc consumes exactly one observed symbol.  Then the lattice of a sequence
+// o_1..o_n has the states (t, s) and between positions t-1 and t exactly the arcs (i -> j, o_t); when the chain
+// of every arc splits into a part that depends on (i, j) only and a part that depends on (j, o) only,
+//     w(i -> j, o) = T[i][j] * E[j][o],
+// one position step of a BATCH of sequences is the dense product  alpha_t = (alpha_{t-1} . T) o E[:, o_t]
+// ([batch x S] . [S x S], then the emission column of each row's observed symbol).  Lattice states the
+// reference would prune (unreachable or dead) simply carry alpha = 0 or beta = 0, so likelihoods and expected
+// counts are those of the pruned lattice.
+//
+// B200 mapping.  S <= 32: one lane per WFST state, one warp per sequence (a warp walks several sequences, a CTA
+// has 8 warps).  T lives in registers (a column per lane in the forward sweep, a row per lane in the backward
+// sweep); the state vector of the current position is exchanged through a 2 x 32 shared-memory buffer read back
+// as 128-bit broadcasts, so a position step costs 32 FMAs + 8 LDS.128 + one redux.sync per lane and touches HBM
+// only for the alpha row (written once, read once) and 2 bytes of symbol.  Scores are linear and renormalised by
+// an exact power of two EVERY step (redux.sync.max on the bit patterns), exponents accumulated per row.
+// Expected counts: gamma_t(j) goes to the E cell (j, o_t), xi_t(i, j) to the T cell (i, j) (kept only when some
+// transition parameter is trainable: 32 more FMAs per step on the same shared-memory reads).  Small alphabets
+// keep per-warp private gamma tables in shared memory (no atomics in the sweep, one RED per cell and CTA at the
+// end); large alphabets issue fp64 REDs on the cell's count slot directly.
+//
+// The M-step is the lattice path's (cml_maximize): cml_add_sequences re-declares the count slots as the
+// trainable T / E cells with their parameter chains.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "cml_ctx.cuh"
+#include "cml_kernels_model.cuh"
+
+namespace {
+
+constexpr int kDW = 8;    // warps per CTA
+constexpr int kDS = 32;   // padded state count (lanes)
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+template <typename Real>
+struct DN;
+template <>
+struct DN<float> {
+  static __device__ __forceinline__ int bits(float x) { return __float_as_int(x); }  // monotone for x >= 0
+  static __device__ __forceinline__ int expo(int b) { return min(max(((b >> 23) & 0xff) - 127, -126), 126); }
+  static __device__ __forceinline__ float pow2(int k) { return __int_as_float((127 + k) << 23); }
+};
+template <>
+struct DN<double> {
+  static __device__ __forceinline__ int bits(double x) { return __double2hiint(x); }
+  static __device__ __forceinline__ int expo(int b) { return min(max(((b >> 20) & 0x7ff) - 1023, -1022), 1022); }
+  static __device__ __forceinline__ double pow2(int k) { return __hiloint2double((1023 + k) << 20, 0); }
+};
+// 2^k as a double for any k (0 below the normal range: such a posterior is < 1e-308)
+__device__ __forceinline__ double pow2d(int k) {
+  if (k < -1022) return 0.;
+  return __hiloint2double((1023 + min(k, 1023)) << 20, 0);
+}
+// renormalise a warp's state vector by the power of two of its largest entry
+template <typename Real>
+__device__ __forceinline__ void renorm(Real& a, int& E) {
+  const int mx = __reduce_max_sync(0xffffffffu, DN<Real>::bits(a));
+  if (mx > 0) {
+    const int e = DN<Real>::expo(mx);
+    a *= DN<Real>::pow2(-e);
+    E += e;
+  }
+}
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+  const double2 q0 = *reinterpret_cast<const double2*>(p), q1 = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+}
+
+struct DenseArgs {
+  const uint64_t* seq_off;
+  const uint16_t* sym;
+  const double* seq_weight;
+  uint32_t n_seq, n_sym, start, fin;
+  const void* T;             // Real T[32][32] (row = source state), zero padded
+  const void* Et;            // Real Et[n_sym][32] (E[j][o] at o*32+j), zero padded
+  const uint32_t* cell_slot; // [1024 T cells | n_sym*32 E cells]: count slot or kNone
+  double* counts;            // the reduce buffer's count slots
+  double* ex_lnp;
+  void* alpha_g;
+  int* exp_g;
+};
+
+// K6 for the dense view: T / E cell value = product of the cell's parameter chain (0 for absent cells)
+template <typename Real>
+__global__ void k_dense_tables(uint32_t n_cells, const uint32_t* __restrict__ cell_off,
+                               const uint32_t* __restrict__ cell_param, const unsigned char* __restrict__ exists,
+                               const double* __restrict__ ln_w, Real* __restrict__ out) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  double s = -CUDART_INF;
+  if (exists[c]) {
+    s = 0;
+    for (uint32_t k = cell_off[c], e = cell_off[c + 1]; k < e; ++k) s += ln_w[cell_param[k]];
+  }
+  out[c] = (Real)exp(s);
+}
+
+// shared memory: Real buf[kDW][2][32] | Real Ts[32][32] | Real Tt[32][32] | (GSM: Real Es[n_sym][32]) |
+//                (GSM: double gam[kDW][n_sym][32]) | (XI: double xis[32][32], transposed)
+template <typename Real>
+static size_t dense_smem(uint32_t n_sym, bool xi, bool gsm) {
+  size_t b = (size_t)kDW * 64 * sizeof(Real) + 2 * 1024 * sizeof(Real);
+  if (gsm) b += (size_t)n_sym * 32 * sizeof(Real);
+  b = (b + 15) & ~(size_t)15;
+  if (gsm) b += (size_t)kDW * n_sym * 32 * sizeof(double);
+  if (xi) b += 1024 * sizeof(double);
+  return b;
+}
+
+template <typename Real, bool XI, bool GSM>
+__global__ void __launch_bounds__(kDW * 32) k_fb_dense(DenseArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_sym = A.n_sym;
+  Real* buf = reinterpret_cast<Real*>(smem) + w * 64;
+  Real* Ts = reinterpret_cast<Real*>(smem) + kDW * 64;
+  Real* Tt = Ts + 1024;
+  size_t off = ((size_t)kDW * 64 + 2048) * sizeof(Real);
+  const Real* Et = reinterpret_cast<const Real*>(A.Et);
+  if (GSM) {
+    Real* Es = reinterpret_cast<Real*>(smem + off);
+    for (uint32_t i = threadIdx.x; i < n_sym * 32; i += blockDim.x) Es[i] = Et[i];
+    Et = Es;
+    off += (size_t)n_sym * 32 * sizeof(Real);
+  }
+  off = (off + 15) & ~(size_t)15;
+  double* gam_all = reinterpret_cast<double*>(smem + off);
+  double* gam = gam_all + (size_t)w * n_sym * 32;
+  if (GSM) {
+    for (uint32_t i = threadIdx.x; i < kDW * n_sym * 32; i += blockDim.x) gam_all[i] = 0.;
+    off += (size_t)kDW * n_sym * 32 * sizeof(double);
+  }
+  double* xis = reinterpret_cast<double*>(smem + off);
+  {
+    const Real* Tg = reinterpret_cast<const Real*>(A.T);
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) {
+      const Real v = Tg[i];
+      Ts[i] = v;
+      Tt[(i & 31) * 32 + (i >> 5)] = v;
+      if (XI) xis[i] = 0.;
+    }
+  }
+  __syncthreads();
+  const uint32_t* __restrict__ e_slot = A.cell_slot + 1024;
+  Real* __restrict__ ag = reinterpret_cast<Real*>(A.alpha_g);
+
+  for (uint64_t e = (uint64_t)blockIdx.x * kDW + w; e < A.n_seq; e += (uint64_t)gridDim.x * kDW) {
+    const uint64_t base = A.seq_off[e];
+    const uint32_t n = (uint32_t)(A.seq_off[e + 1] - base);
+    const uint64_t r0 = base + e;  // first alpha row of this sequence (n + 1 rows)
+    const uint16_t* __restrict__ sy = A.sym + base;
+    // ---------------------------------------------------------------- forward
+    Real a = (lane == (int)A.start) ? Real(1) : Real(0);
+    int Ea = 0;
+    ag[r0 * 32 + lane] = a;
+    if (lane == 0) A.exp_g[r0] = 0;
+    {
+      Real Tcol[32];  // T[i][lane]
+#pragma unroll
+      for (int i = 0; i < 32; ++i) Tcol[i] = Ts[i * 32 + lane];
+      uint32_t symv = ((uint32_t)lane < n) ? sy[lane] : 0u;
+      uint32_t symn = (32u + lane < n) ? sy[32 + lane] : 0u;
+      Real ev = Et[__shfl_sync(0xffffffffu, symv, 0) * 32 + lane];
+      int p = 0;
+      for (uint32_t t = 0; t < n; ++t) {
+        buf[p * 32 + lane] = a;
+        __syncwarp();
+        // emission column of the next step (off the critical path)
+        Real evn = 0;
+        if (t + 1 < n) {
+          if (((t + 1) & 31) == 0) {
+            symv = symn;
+            symn = (t + 33 + lane < n) ? sy[t + 33 + lane] : 0u;
+          }
+          evn = Et[__shfl_sync(0xffffffffu, symv, (t + 1) & 31) * 32 + lane];
+        }
+        Real acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          Real v[4];
+          ld4(buf + p * 32 + i, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] = fma(v[k], Tcol[i + k], acc[k]);
+        }
+        a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * ev;
+        renorm<Real>(a, Ea);
+        ag[(r0 + t + 1) * 32 + lane] = a;
+        if (lane == 0) A.exp_g[r0 + t + 1] = Ea;
+        ev = evn;
+        p ^= 1;
+      }
+    }
+    const Real afin = __shfl_sync(0xffffffffu, a, A.fin);
+    const int EaN = Ea;
+    if (lane == 0)
+      A.ex_lnp[e] = (afin > 0) ? log((double)afin) + (double)EaN * 0.69314718055994530942 : -CUDART_INF;
+    if (!(afin > 0)) continue;  // zero-probability sequence: no counts (warp-uniform)
+    const double cw = A.seq_weight[e] / (double)afin;
+    __syncwarp();
+    // ---------------------------------------------------------------- backward + counts
+    {
+      Real Trow[32];  // T[lane][j]
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Trow[j] = Tt[j * 32 + lane];
+      Real xi[XI ? 32 : 1];
+      if (XI) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xi[j] = 0;
+      }
+      Real b = (lane == (int)A.fin) ? Real(1) : Real(0);
+      int Eb = 0;
+      Real a1 = a;  // alpha row n
+      int Ea1 = EaN;
+      // symbols in reverse: reverse index u = n-1-t
+      uint32_t symv = ((uint32_t)lane < n) ? sy[n - 1 - lane] : 0u;
+      uint32_t symn = (32u + lane < n) ? sy[n - 33 - lane] : 0u;
+      uint32_t o = __shfl_sync(0xffffffffu, symv, 0);
+      Real ev = Et[o * 32 + lane];
+      int p = 0;
+      for (uint32_t u = 0; u < n; ++u) {
+        const uint32_t t = n - 1 - u;
+        // alpha row t and its exponent (needed at the end of this step and in the next one)
+        const Real a0 = ag[(r0 + t) * 32 + lane];
+        const int Ea0 = A.exp_g[r0 + t];
+        const Real bt = b * ev;  // E[j][o_t] * beta_{t+1}[j]
+        // posterior of lattice state (t+1, lane) -> E cell (lane, o_t)
+        const double gamma = (double)a1 * (double)b * (cw * pow2d(Ea1 + Eb - EaN));
+        if (GSM) {
+          gam[o * 32 + lane] += gamma;
+        } else if (gamma > 0) {
+          const uint32_t sl = e_slot[o * 32 + lane];
+          if (sl != kNone) atomicAdd(A.counts + sl, gamma);
+        }
+        buf[p * 32 + lane] = bt;
+        __syncwarp();
+        Real evn = 0;
+        uint32_t on = 0;
+        if (u + 1 < n) {
+          if (((u + 1) & 31) == 0) {
+            symv = symn;
+            symn = (u + 33 + lane < n) ? sy[n - 1 - (u + 33 + lane)] : 0u;
+          }
+          on = __shfl_sync(0xffffffffu, symv, (u + 1) & 31);
+          evn = Et[on * 32 + lane];
+        }
+        Real x0 = 0;
+        if (XI) x0 = (Real)((double)a0 * (cw * pow2d(Ea0 + Eb - EaN)));
+        Real acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          Real v[4];
+          ld4(buf + p * 32 + j, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[k] = fma(v[k], Trow[j + k], acc[k]);
+            if (XI) xi[j + k] = fma(x0, v[k], xi[j + k]);
+          }
+        }
+        b = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        renorm<Real>(b, Eb);
+        a1 = a0;
+        Ea1 = Ea0;
+        ev = evn;
+        o = on;
+        p ^= 1;
+        if (XI && ((u & 255) == 255 || u + 1 == n)) {  // fold the xi partial sums (fp64, per CTA)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double v = (double)xi[j] * (double)Trow[j];
+            if (v != 0.) atomicAdd(&xis[j * 32 + lane], v);
+            xi[j] = 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (GSM) {
+    for (uint32_t c = threadIdx.x; c < n_sym * 32; c += blockDim.x) {
+      const uint32_t sl = e_slot[c];
+      if (sl == kNone) continue;
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < kDW; ++k) s += gam_all[(size_t)k * n_sym * 32 + c];
+      if (s != 0.) atomicAdd(A.counts + sl, s);
+    }
+  }
+  if (XI) {
+    for (uint32_t c = threadIdx.x; c < 1024; c += blockDim.x) {  // c = j*32 + i (transposed)
+      const uint32_t sl = A.cell_slot[(c & 31) * 32 + (c >> 5)];
+      const double s = xis[c];
+      if (sl != kNone && s != 0.) atomicAdd(A.counts + sl, s);
+    }
+  }
+}
+
+template <typename Real>
+int launch_dense(cml_ctx* ctx) {
+  DenseState& D = *ctx->dense;
+  cudaStream_t s = ctx->stream;
+  k_dense_tables<Real><<<cdiv(D.n_cells, 256), 256, 0, s>>>(D.n_cells, D.cell_off.p, D.cell_param.p, D.cell_exists.p,
+                                                           ctx->ln_w.p, reinterpret_cast<Real*>(D.tables.p));
+  ++ctx->launches;
+  CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
+  DenseArgs A;
+  A.seq_off = D.seq_off.p;
+  A.sym = D.sym.p;
+  A.seq_weight = D.seq_weight.p;
+  A.n_seq = (uint32_t)D.n_seq;
+  A.n_sym = D.n_sym;
+  A.start = D.start;
+  A.fin = D.fin;
+  A.T = D.tables.p;
+  A.Et = D.tables.p + 1024 * sizeof(Real);
+  A.cell_slot = D.cell_slot.p;
+  A.counts = ctx->reduce;
+  A.ex_lnp = D.ex_lnp.p;
+  A.alpha_g = D.alpha_g.p;
+  A.exp_g = D.exp_g.p;
+  const bool xi = D.n_t_slots > 0;
+  const bool gsm = dense_smem<Real>(D.n_sym, xi, true) <= 100 * 1024;
+  const size_t smem = dense_smem<Real>(D.n_sym, xi, gsm);
+  void (*kern)(DenseArgs) = xi ? (gsm ? k_fb_dense<Real, true, true> : k_fb_dense<Real, true, false>)
+                               : (gsm ? k_fb_dense<Real, false, true> : k_fb_dense<Real, false, false>);
+  CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDW * 32, smem));
+  const unsigned grid = std::max(1u, std::min<unsigned>(cdiv(D.n_seq, kDW), (unsigned)(std::max(per_sm, 1) * ctx->sm_count)));
+  if (!D.ev0) {
+    CML_CUDA(cudaEventCreate(&D.ev0));
+    CML_CUDA(cudaEventCreate(&D.ev1));
+  }
+  CML_CUDA(cudaEventRecord(D.ev0, s));
+  kern<<<grid, kDW * 32, smem, s>>>(A);
+  ++ctx->launches;
+  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (D.n_seq) {
+    cmlk::k_reduce_lnp<<<std::min<unsigned>(cdiv(D.n_seq, 256), 4 * ctx->sm_count), 256, 0, s>>>(
+        D.ex_lnp.p, D.seq_weight.p, D.n_seq, ctx->reduce + ctx->n_slots);
+    ++ctx->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
+// multiset helpers on sorted vectors
+std::vector<uint32_t> ms_intersect(const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) {
+  std::vector<uint32_t> r;
+  std::set_intersection(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(r));
+  return r;
+}
+std::vector<uint32_t> ms_minus(const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) {
+  std::vector<uint32_t> r;
+  std::set_difference(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(r));
+  return r;
+}
+
+}  // namespace
+
+int cml_dense_estimate_launch(cml_ctx* ctx) {
+  return ctx->precision == 64 ? launch_dense<double>(ctx) : launch_dense<float>(ctx);
+}
+
+extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b) {
+  if (!ctx || !v || !b) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model, CML_ERR_STATE, "cml_set_model first");
+  CML_REQUIRE(ctx->batches.empty() && !ctx->dense, CML_ERR_STATE,
+              "cml_add_sequences needs a context without resident lattices or sequences (cml_set_model resets it)");
+  CML_REQUIRE(ctx->space == CML_SPACE_SCALED, CML_ERR_STATE, "dense-state sequences need a CML_SPACE_SCALED context");
+  CML_REQUIRE(v->arc_src && v->arc_dst && v->arc_sym && b->seq_off && (b->sym || b->seq_off[b->n_seq] == 0),
+              CML_ERR_ARG, "null array");
+  CML_REQUIRE(b->n_seq < 0xFFFFFFFFull, CML_ERR_ARG, "too many sequences");
+  CML_REQUIRE(v->n_symbols > 0 && v->n_symbols <= 65535, CML_ERR_ARG, "n_symbols must be in 1..65535");
+  CML_REQUIRE(v->start < v->n_states && v->final_state < v->n_states, CML_ERR_ARG, "start / final state out of range");
+  const uint32_t S = v->n_states, V = v->n_symbols, nA = ctx->n_arcs;
+  if (S > kDS) {
+    ctx->err = "dense-state path needs n_states <= 32";
+    return CML_ERR_NOT_DENSE;
+  }
+  for (uint32_t a = 0; a < nA; ++a)
+    CML_REQUIRE(v->arc_src[a] < S && v->arc_dst[a] < S && v->arc_sym[a] < V, CML_ERR_ARG, "arc triple out of range");
+  const uint64_t n_pos = b->seq_off[b->n_seq];
+  for (uint64_t e = 0; e < b->n_seq; ++e)
+    CML_REQUIRE(b->seq_off[e] <= b->seq_off[e + 1] && b->seq_off[e + 1] - b->seq_off[e] < 0x7FFFFFFFull, CML_ERR_ARG,
+                "seq_off not monotone");
+  for (uint64_t i = 0; i < n_pos; ++i) CML_REQUIRE(b->sym[i] < V, CML_ERR_ARG, "sequence symbol out of range");
+
+  // ---- factorisation: chain(a) = A(i,j) + B(j,o) as multisets of parameter ids --------------------------------
+  auto chain_of = [&](uint32_t a) {
+    std::vector<uint32_t> c;
+    if (ctx->trivial)
+      c.push_back(a);
+    else
+      c.assign(ctx->h_chain_param.begin() + ctx->h_chain_off[a], ctx->h_chain_param.begin() + ctx->h_chain_off[a + 1]);
+    std::sort(c.begin(), c.end());
+    return c;
+  };
+  const uint32_t nT = kDS * kDS, nE = V * kDS, n_cells = nT + nE;
+  auto tcell = [&](uint32_t a) { return v->arc_src[a] * kDS + v->arc_dst[a]; };
+  auto ecell = [&](uint32_t a) { return nT + v->arc_sym[a] * kDS + v->arc_dst[a]; };
+  std::vector<std::vector<uint32_t>> cell_chain(n_cells);
+  std::vector<unsigned char> exists(n_cells, 0);
+  std::vector<std::vector<uint32_t>> chains(nA);
+  {
+    std::map<uint64_t, uint32_t> seen;  // (i, j, o) must be unique
+    for (uint32_t a = 0; a < nA; ++a) {
+      chains[a] = chain_of(a);
+      const uint64_t key = ((uint64_t)tcell(a) << 32) | v->arc_sym[a];
+      if (!seen.emplace(key, a).second) {
+        ctx->err = "parallel arcs with the same (source, destination, symbol): no dense view";
+        return CML_ERR_NOT_DENSE;
+      }
+    }
+  }
+  for (uint32_t a = 0; a < nA; ++a) {  // B(j,o) = intersection over the sources i
+    const uint32_t c = ecell(a);
+    cell_chain[c] = exists[c] ? ms_intersect(cell_chain[c], chains[a]) : chains[a];
+    exists[c] = 1;
+  }
+  std::vector<std::vector<uint32_t>> rest(nA);
+  for (uint32_t a = 0; a < nA; ++a) {  // A(i,j) = intersection over the symbols o of what B leaves
+    rest[a] = ms_minus(chains[a], cell_chain[ecell(a)]);
+    const uint32_t c = tcell(a);
+    cell_chain[c] = exists[c] ? ms_intersect(cell_chain[c], rest[a]) : rest[a];
+    exists[c] = 1;
+  }
+  for (uint32_t a = 0; a < nA; ++a)
+    if (rest[a] != cell_chain[tcell(a)]) {
+      ctx->err = "arc chains do not factor into (source,destination) x (destination,symbol) parts";
+      return CML_ERR_NOT_DENSE;
+    }
+  {  // completeness: every (i,j) x (j,o) combination must be an arc, or the dense product would invent arcs
+    std::vector<uint32_t> n_in(S, 0), n_o(S, 0);
+    for (uint32_t i = 0; i < S; ++i)
+      for (uint32_t j = 0; j < S; ++j) n_in[j] += exists[i * kDS + j];
+    for (uint32_t o = 0; o < V; ++o)
+      for (uint32_t j = 0; j < S; ++j) n_o[j] += exists[nT + o * kDS + j];
+    uint64_t tot = 0;
+    for (uint32_t j = 0; j < S; ++j) tot += (uint64_t)n_in[j] * n_o[j];
+    if (tot != nA) {
+      ctx->err = "the arc table is not the full product of its transition and emission supports";
+      return CML_ERR_NOT_DENSE;
+    }
+  }
+
+  // ---- count slots := trainable cells; priors of an arc are shared out to the cells of its parameters -----------
+  std::vector<uint32_t> cell_off(n_cells + 1, 0), cell_param, cell_slot(n_cells, kNone), slot_off{0}, slot_param;
+  std::vector<double> slot_prior;
+  uint32_t n_slots = 0, n_t_slots = 0, n_e_slots = 0;
+  for (uint32_t c = 0; c < n_cells; ++c) {
+    cell_param.insert(cell_param.end(), cell_chain[c].begin(), cell_chain[c].end());
+    cell_off[c + 1] = (uint32_t)cell_param.size();
+    if (!exists[c]) continue;
+    std::vector<uint32_t> un;
+    for (uint32_t p : cell_chain[c])
+      if (ctx->h_param_tie[p] != CML_LOCKED_GROUP) un.push_back(p);
+    if (un.empty()) continue;
+    cell_slot[c] = n_slots++;
+    (c < nT ? n_t_slots : n_e_slots)++;
+    slot_param.insert(slot_param.end(), un.begin(), un.end());
+    slot_off.push_back((uint32_t)slot_param.size());
+    slot_prior.push_back(0.);
+  }
+  const bool have_prior = !ctx->h_arc_prior.empty();
+  if (have_prior)
+    for (uint32_t a = 0; a < nA; ++a) {
+      if (cell_slot[tcell(a)] != kNone) slot_prior[cell_slot[tcell(a)]] += ctx->h_arc_prior[a];
+      if (cell_slot[ecell(a)] != kNone) slot_prior[cell_slot[ecell(a)]] += ctx->h_arc_prior[a];
+    }
+  if (n_slots == 0) {
+    n_slots = 1;
+    slot_off.push_back(0);
+    slot_prior.push_back(0.);
+  }
+
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  std::unique_ptr<DenseState> D(new DenseState());
+  D->S = S;
+  D->n_sym = V;
+  D->start = v->start;
+  D->fin = v->final_state;
+  D->n_seq = b->n_seq;
+  D->n_pos = n_pos;
+  D->n_cells = n_cells;
+  D->n_t_slots = n_t_slots;
+  D->n_e_slots = n_e_slots;
+  const size_t rs = ctx->precision / 8;
+  std::vector<uint16_t> sym16(std::max<uint64_t>(1, n_pos));
+  for (uint64_t i = 0; i < n_pos; ++i) sym16[i] = (uint16_t)b->sym[i];
+  std::vector<double> wts(std::max<uint64_t>(1, b->n_seq), 1.);
+  if (b->seq_weight) std::copy(b->seq_weight, b->seq_weight + b->n_seq, wts.begin());
+  CML_CUDA(D->cell_off.upload(cell_off.data(), cell_off.size(), s));
+  CML_CUDA(D->cell_param.upload(cell_param.data(), cell_param.size(), s));
+  CML_CUDA(D->cell_slot.upload(cell_slot.data(), cell_slot.size(), s));
+  CML_CUDA(D->cell_exists.upload(exists.data(), exists.size(), s));
+  CML_CUDA(D->tables.alloc((size_t)n_cells * rs));
+  CML_CUDA(D->seq_off.upload(b->seq_off, b->n_seq + 1, s));
+  CML_CUDA(D->sym.upload(sym16.data(), sym16.size(), s));
+  CML_CUDA(D->seq_weight.upload(wts.data(), wts.size(), s));
+  CML_CUDA(D->ex_lnp.alloc(std::max<uint64_t>(1, b->n_seq)));
+  CML_CUDA(D->alpha_g.alloc((size_t)(n_pos + b->n_seq) * kDS * rs));
+  CML_CUDA(D->exp_g.alloc((size_t)(n_pos + b->n_seq)));
+  // the M-step's view of the count slots
+  CML_CUDA(ctx->slot_off.upload(slot_off.data(), slot_off.size(), s));
+  CML_CUDA(ctx->slot_param.upload(slot_param.data(), slot_param.size(), s));
+  ctx->have_prior = have_prior;
+  if (have_prior) CML_CUDA(ctx->slot_prior.upload(slot_prior.data(), slot_prior.size(), s));
+  CML_CUDA(ctx->reduce_own.alloc((size_t)n_slots + 3));
+  ctx->reduce = ctx->reduce_own.p;
+  ctx->reduce_n = (uint64_t)n_slots + 3;
+  CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  ctx->n_slots = n_slots;
+  ctx->slots_are_arcs = false;
+  ctx->n_hot = 0;
+  ctx->slot_occ.assign(n_slots, 0);
+  ctx->dense = std::move(D);
+  return CML_OK;
+}
+
+extern "C" int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positions, uint32_t* n_t_slots,
+                               uint32_t* n_e_slots) {
+  if (!ctx) return CML_ERR_ARG;
+  const DenseState* D = ctx->dense.get();
+  if (n_seq) *n_seq = D ? D->n_seq : 0;
+  if (n_positions) *n_positions = D ? D->n_pos : 0;
+  if (n_t_slots) *n_t_slots = D ? D->n_t_slots : 0;
+  if (n_e_slots) *n_e_slots = D ? D->n_e_slots : 0;
+  return CML_OK;
+}

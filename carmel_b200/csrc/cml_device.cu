@@ -113,6 +113,13 @@ extern "C" int cml_set_option(cml_ctx* ctx, int option, int value) {
       CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "CML_OPT_NO_ELL must be set before cml_add_trellises");
       ctx->opt_no_ell = value;
       return CML_OK;
+    case CML_OPT_LANE_MIN:
+      CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "CML_OPT_LANE_MIN must be set before cml_add_trellises");
+      ctx->opt_lane_min = value;
+      return CML_OK;
+    case CML_OPT_NO_COUNTS:
+      ctx->opt_no_counts = value;
+      return CML_OK;
     default: ctx->err = "unknown option"; return CML_ERR_ARG;
   }
 }
@@ -206,6 +213,19 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   }
 
   cudaStream_t s = ctx->stream;
+  ctx->dense.reset();
+  ctx->h_param_tie.assign(m->param_tie, m->param_tie + m->n_params);
+  if (!trivial) {
+    ctx->h_chain_off.assign(m->chain_off, m->chain_off + m->n_arcs + 1);
+    ctx->h_chain_param.assign(m->chain_param, m->chain_param + m->chain_off[m->n_arcs]);
+  } else {
+    ctx->h_chain_off.clear();
+    ctx->h_chain_param.clear();
+  }
+  if (m->arc_prior)
+    ctx->h_arc_prior.assign(m->arc_prior, m->arc_prior + m->n_arcs);
+  else
+    ctx->h_arc_prior.clear();
   ctx->trivial = trivial;
   ctx->n_arcs = m->n_arcs;
   ctx->n_params = m->n_params;
@@ -325,6 +345,8 @@ struct FlatEx {  // per-example facts discovered in pass 1
   uint32_t ring_need = 0;  // max index distance of an arc + max level width + 1
   uint64_t in_pad = 0, out_pad = 0;  // ELL record counts (with padding)
   uint32_t width = 0;
+  bool lane_ok = false;    // narrow, every arc spans exactly one level: eligible for the lane-per-lattice kernel
+  bool lane = false;       // ... and chosen for it
 };
 
 inline uint32_t pow2ceil(uint32_t v) {
@@ -419,6 +441,7 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
     if (fits) gc = k;
   }
   fx.g_class = gc < 0 ? 0 : (uint32_t)gc;
+  fx.lane_ok = maxspan <= 1 && 2 * width <= (uint32_t)cmlk::kLaneRing && n < (1u << 30);
   fx.ell = gc >= 0 && width <= 255 && maxdeg <= 255 && maxspan <= 15 && fx.ring_need <= 4096 &&
            in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
 }
@@ -426,6 +449,10 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
 }  // namespace
 
 extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
+  if (ctx && ctx->dense) {
+    ctx->err = "dense-state sequences are resident (cml_add_sequences): call cml_set_model before adding lattices";
+    return CML_ERR_STATE;
+  }
   if (!ctx || !b) return CML_ERR_ARG;
   CML_REQUIRE(ctx->have_model, CML_ERR_STATE, "cml_set_model first");
   CML_REQUIRE(b->n_ex > 0, CML_ERR_ARG, "empty batch");
@@ -510,6 +537,20 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   CML_REQUIRE(!bad_cycle, CML_ERR_CYCLE,
               "derivation lattice has a cycle (the reference warns 'Forward/backward will miss some paths')");
 
+  // ---- lane-per-lattice layout for corpora of many narrow lattices (cml_kernels_lane.cuh)
+  std::vector<uint32_t> lane_list;
+  if (want_ell && ctx->opt_lane_min > 0) {
+    for (uint64_t e = 0; e < n_ex; ++e)
+      if (fx[e].lane_ok) lane_list.push_back((uint32_t)e);
+    if (lane_list.size() >= (size_t)ctx->opt_lane_min)
+      for (uint32_t e : lane_list) {
+        fx[e].lane = true;
+        fx[e].ell = false;
+      }
+    else
+      lane_list.clear();
+  }
+
   // ---- layout offsets (serial prefix sums), separately for the CSR and the ELL examples
   std::vector<uint64_t> c_lvl(n_ex), c_row(n_ex), c_arc(n_ex), e_in(n_ex), e_out(n_ex), e_meta(n_ex), e_state(n_ex);
   std::vector<uint32_t> slot_of(n_ex);  // index of the example inside its part's descriptor array
@@ -518,6 +559,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   for (uint64_t e = 0; e < n_ex; ++e) {
     const uint32_t n = b->ex_states[e], nl = fx[e].n_levels;
     bt->n_levels += nl;
+    if (fx[e].lane) continue;
     if (fx[e].ell) {
       slot_of[e] = (uint32_t)n_e++;
       e_in[e] = ei;
@@ -563,6 +605,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     const uint32_t* local_of = &bt->h_local_of[state_base[e]];
     const double weight = b->ex_weight ? b->ex_weight[e] : 1.0;
     h_weight[e] = weight;
+    if (fx[e].lane) return;  // laid out per tile below
     auto &lfirst = S.lvl_first, &ref_of = S.ref_of;
     lfirst.assign(nl + 1, 0);
     for (uint32_t s = 0; s < n; ++s) ++lfirst[level_of[s] + 1];
@@ -709,6 +752,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   std::vector<std::vector<uint32_t>> cls(NCLS), ecls(NELL);
   uint64_t scratch_states = 0;
   for (uint64_t e = 0; e < n_ex; ++e) {
+    if (fx[e].lane) continue;
     if (fx[e].ell) {
       ecls[fx[e].g_class].push_back(slot_of[e]);
       bt->ell_ring[fx[e].g_class] = std::max(bt->ell_ring[fx[e].g_class], pow2ceil(fx[e].ring_need));
@@ -751,6 +795,151 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   }
   bt->ell_begin[NELL] = (uint32_t)ell_list.size();
 
+  // ---- lane tiles: 32 lattices of similar size per tile, streams aligned by state ordinal
+  std::vector<cmlk::LaneTile> h_tile;
+  std::vector<uint2> h_lfw, h_lbw;
+  std::vector<uint32_t> h_lex, h_lfin, h_lnlev;
+  std::vector<double> h_lweight;
+  uint64_t lane_states = 0, lane_levels = 0;
+  if (!lane_list.empty()) {
+    constexpr uint32_t U = cmlk::kLaneU;
+    std::stable_sort(lane_list.begin(), lane_list.end(), [&](uint32_t x, uint32_t y) {
+      return b->ex_states[x] != b->ex_states[y] ? b->ex_states[x] > b->ex_states[y]
+                                                 : arc_base[x + 1] - arc_base[x] > arc_base[y + 1] - arc_base[y];
+    });
+    const uint32_t n_tiles = (uint32_t)((lane_list.size() + 31) / 32);
+    h_tile.resize(n_tiles);
+    h_lex.assign((size_t)n_tiles * 32, 0xFFFFFFFFu);
+    h_lfin.assign((size_t)n_tiles * 32, 0xFFFFFFFFu);
+    h_lnlev.assign((size_t)n_tiles * 32, 1);
+    h_lweight.assign((size_t)n_tiles * 32, 0.);
+    std::vector<std::vector<uint32_t>> rin(n_tiles), rout(n_tiles);  // rows per state ordinal (tile maxima)
+    auto tile_for = [&](auto&& body) {
+      std::atomic<uint32_t> next{0};
+      auto work = [&]() {
+        for (;;) {
+          const uint32_t t = next.fetch_add(1);
+          if (t >= n_tiles) break;
+          body(t);
+        }
+      };
+      std::vector<std::thread> th;
+      for (unsigned k = 1; k < nthr; ++k) th.emplace_back(work);
+      work();
+      for (auto& k : th) k.join();
+    };
+    // phase A: per-ordinal maxima of the in / out degrees
+    tile_for([&](uint32_t t) {
+      uint32_t nmax = 0, nlmax = 0;
+      for (uint32_t l = 0; l < 32 && (size_t)t * 32 + l < lane_list.size(); ++l) {
+        const uint32_t e = lane_list[(size_t)t * 32 + l];
+        nmax = std::max(nmax, b->ex_states[e]);
+        nlmax = std::max(nlmax, fx[e].n_levels);
+      }
+      auto &ri = rin[t], &ro = rout[t];
+      ri.assign(nmax, 0);
+      ro.assign(nmax, 0);
+      std::vector<uint32_t> ind;
+      for (uint32_t l = 0; l < 32 && (size_t)t * 32 + l < lane_list.size(); ++l) {
+        const uint32_t e = lane_list[(size_t)t * 32 + l], n = b->ex_states[e];
+        const uint32_t* off = b->arc_off + state_base[e] + e;
+        const uint32_t* dst = b->arc_dst + arc_base[e];
+        const uint32_t* local_of = &bt->h_local_of[state_base[e]];
+        ind.assign(n, 0);
+        for (uint32_t sr = 0; sr < n; ++sr) {
+          ro[local_of[sr]] = std::max(ro[local_of[sr]], off[sr + 1] - off[sr]);
+          for (uint32_t k = off[sr]; k < off[sr + 1]; ++k) ++ind[local_of[dst[k]]];
+        }
+        for (uint32_t j = 0; j < n; ++j) ri[j] = std::max(ri[j], ind[j]);
+      }
+      uint64_t rf = 0, rb = 0;
+      for (uint32_t j = 0; j < nmax; ++j) {
+        if (j) rf += (ri[j] = std::max(1u, ri[j]));
+        rb += (ro[j] = std::max(1u, ro[j]));
+      }
+      cmlk::LaneTile& T = h_tile[t];
+      T.rows_f = (uint32_t)((rf + U - 1) / U * U);
+      T.rows_b = (uint32_t)((rb + U - 1) / U * U);
+      T.n_states = nmax;
+      T.n_levels = nlmax;
+    });
+    uint64_t fo = 0, bo = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+      cmlk::LaneTile& T = h_tile[t];
+      T.fw_base = fo * 32;
+      T.bw_base = bo * 32;
+      T.st_base = lane_states * 32;
+      T.lv_base = lane_levels * 32;
+      fo += T.rows_f;
+      bo += T.rows_b;
+      lane_states += T.n_states;
+      lane_levels += T.n_levels;
+    }
+    const uint2 padrec = make_uint2(0u, pad_id);
+    h_lfw.assign((size_t)(fo + 2 * U) * 32, padrec);  // + the prefetch tail
+    h_lbw.assign((size_t)(bo + 2 * U) * 32, padrec);
+    // phase B: fill
+    tile_for([&](uint32_t t) {
+      const cmlk::LaneTile& T = h_tile[t];
+      const auto &ri = rin[t], &ro = rout[t];
+      std::vector<uint32_t> rowf(T.n_states + 1, 0), rowb(T.n_states + 1, 0);  // first row of every ordinal
+      for (uint32_t j = 1; j < T.n_states; ++j) rowf[j + 1] = rowf[j] + ri[j];
+      {
+        uint32_t r = 0;
+        for (uint32_t j = T.n_states; j-- > 0;) {
+          rowb[j] = r;
+          r += ro[j];
+        }
+      }
+      uint2* fwp = &h_lfw[T.fw_base];
+      uint2* bwp = &h_lbw[T.bw_base];
+      // the LAST flag closes every ordinal in every lane (also in padding / empty lanes)
+      for (uint32_t l = 0; l < 32; ++l) {
+        for (uint32_t j = 1; j < T.n_states; ++j) fwp[(size_t)(rowf[j] + ri[j] - 1) * 32 + l].x |= cmlk::kLaneLast;
+        for (uint32_t j = 0; j < T.n_states; ++j) bwp[(size_t)(rowb[j] + ro[j] - 1) * 32 + l].x |= cmlk::kLaneLast;
+      }
+      std::vector<uint32_t> cur, lfirst;
+      for (uint32_t l = 0; l < 32 && (size_t)t * 32 + l < lane_list.size(); ++l) {
+        const uint32_t e = lane_list[(size_t)t * 32 + l], n = b->ex_states[e], nl = fx[e].n_levels;
+        const uint32_t* off = b->arc_off + state_base[e] + e;
+        const uint32_t* dst = b->arc_dst + arc_base[e];
+        const uint32_t* id = b->arc_id + arc_base[e];
+        const uint32_t* level_of = &bt->h_level_of[state_base[e]];
+        const uint32_t* local_of = &bt->h_local_of[state_base[e]];
+        const size_t li = (size_t)t * 32 + l;
+        h_lex[li] = e;
+        h_lfin[li] = local_of[b->ex_fin[e]];
+        h_lnlev[li] = nl;
+        h_lweight[li] = b->ex_weight ? b->ex_weight[e] : 1.0;
+        lfirst.assign(nl + 1, 0);
+        for (uint32_t sr = 0; sr < n; ++sr) ++lfirst[level_of[sr] + 1];
+        for (uint32_t L = 0; L < nl; ++L) lfirst[L + 1] += lfirst[L];
+        cur.assign(n, 0);
+        for (uint32_t sr = 0; sr < n; ++sr) {
+          const uint32_t j = local_of[sr];
+          for (uint32_t k = off[sr]; k < off[sr + 1]; ++k) {
+            const uint32_t dj = local_of[dst[k]], ia = perm[id[k]];
+            uint2& f = fwp[(size_t)(rowf[dj] + cur[dj]++) * 32 + l];
+            f.x = (f.x & cmlk::kLaneLast) | j;
+            f.y = ia;
+            uint2& g = bwp[(size_t)(rowb[j] + (k - off[sr])) * 32 + l];
+            g.x = (g.x & cmlk::kLaneLast) | dj;
+            g.y = ia;
+          }
+        }
+        for (uint32_t L = 0; L < nl; ++L) {
+          const uint32_t hi = lfirst[L + 1] - 1, lo = lfirst[L];  // last / first state of the level
+          if (hi >= 1) fwp[(size_t)(rowf[hi] + ri[hi] - 1) * 32 + l].x |= cmlk::kLaneLevelEnd;
+          bwp[(size_t)(rowb[lo] + ro[lo] - 1) * 32 + l].x |= cmlk::kLaneLevelEnd;
+        }
+      }
+    });
+    bt->lane_ex = lane_list.size();
+    bt->lane_tiles = n_tiles;
+    bt->lane_records = (fo + bo) * 32;
+    for (uint32_t e : lane_list) bt->lane_arcs += arc_base[e + 1] - arc_base[e];
+  }
+
   cudaStream_t s = ctx->stream;
   CML_CUDA(bt->ex_lnp.alloc(n_ex));
   CML_CUDA(bt->ex_weight.upload(h_weight.data(), n_ex, s));
@@ -775,6 +964,17 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     CML_CUDA(bt->ell_list.upload(ell_list.data(), ell_list.size(), s));
     CML_CUDA(bt->alpha_g.alloc(es * rs));
     CML_CUDA(bt->lvl_exp.alloc(em * 2));
+  }
+  if (bt->lane_tiles) {
+    CML_CUDA(bt->ltile.upload(h_tile.data(), h_tile.size(), s));
+    CML_CUDA(bt->lane_fw.upload(h_lfw.data(), h_lfw.size(), s));
+    CML_CUDA(bt->lane_bw.upload(h_lbw.data(), h_lbw.size(), s));
+    CML_CUDA(bt->lane_exidx.upload(h_lex.data(), h_lex.size(), s));
+    CML_CUDA(bt->lane_fin.upload(h_lfin.data(), h_lfin.size(), s));
+    CML_CUDA(bt->lane_nlev.upload(h_lnlev.data(), h_lnlev.size(), s));
+    CML_CUDA(bt->lane_weight.upload(h_lweight.data(), h_lweight.size(), s));
+    CML_CUDA(bt->lane_alpha.alloc(lane_states * 32 * rs));
+    CML_CUDA(bt->lane_lvle.alloc(lane_levels * 32));
   }
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->batches.push_back(std::move(bt));
@@ -808,6 +1008,23 @@ extern "C" int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_stat
   if (n_states) *n_states = b;
   if (n_arcs) *n_arcs = c;
   if (n_levels) *n_levels = d;
+  return CML_OK;
+}
+
+extern "C" int cml_lane_stats(cml_ctx* ctx, uint64_t* lane_examples, uint64_t* lane_arcs, uint64_t* lane_records,
+                              uint64_t* tiles) {
+  if (!ctx) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0, d = 0;
+  for (auto& bt : ctx->batches) {
+    a += bt->lane_ex;
+    b += bt->lane_arcs;
+    c += bt->lane_records;
+    d += bt->lane_tiles;
+  }
+  if (lane_examples) *lane_examples = a;
+  if (lane_arcs) *lane_arcs = b;
+  if (lane_records) *lane_records = c;
+  if (tiles) *tiles = d;
   return CML_OK;
 }
 
@@ -895,6 +1112,28 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     if ((r = launch_ell_class<Real, 16, 2, false>(ctx, bt, E, 4))) return r;  // kEllCls[4]
     if ((r = launch_ell_class<Real, 32, 1, false>(ctx, bt, E, 5))) return r;  // kEllCls[5]
     if ((r = launch_ell_class<Real, 32, 8, true>(ctx, bt, E, 6))) return r;   // kEllCls[6]
+  }
+  if (SCALED && bt.lane_tiles) {
+    LaneArgs L;
+    L.tile = bt.ltile.p;
+    L.n_tiles = bt.lane_tiles;
+    L.fw = bt.lane_fw.p;
+    L.bw = bt.lane_bw.p;
+    L.ex = bt.lane_exidx.p;
+    L.fin = bt.lane_fin.p;
+    L.nlev = bt.lane_nlev.p;
+    L.weight = bt.lane_weight.p;
+    L.arc_w = ctx->arc_w_real.p;
+    L.arc_ws = ctx->arc_ws.p;
+    L.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    L.ex_lnp = bt.ex_lnp.p;
+    L.alpha = bt.lane_alpha.p;
+    L.lvle = bt.lane_lvle.p;
+    L.no_counts = ctx->opt_no_counts;
+    const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real);
+    k_fb_lane<Real><<<cdiv(bt.lane_tiles, kLaneWarps), kLaneWarps * 32, smem, ctx->stream>>>(L);
+    ++ctx->launches;
+    ++bt.n_fb_kernels;
   }
   if (bt.csr_ex) {
     FbArgs A;
@@ -1002,8 +1241,15 @@ static int rebuild_slot_codes(cml_ctx* ctx) {
 extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   if (!ctx) return CML_ERR_ARG;
   CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
-  CML_REQUIRE(!ctx->batches.empty(), CML_ERR_NODERIV, "no trellises resident (no training example had a derivation)");
+  CML_REQUIRE(!ctx->batches.empty() || ctx->dense, CML_ERR_NODERIV,
+              "no trellises resident (no training example had a derivation)");
   cudaSetDevice(ctx->device);
+  if (ctx->dense) {
+    const int rc = cml_dense_estimate_launch(ctx);
+    if (rc) return rc;
+    ctx->estimate_pending = true;
+    return CML_OK;
+  }
   if (ctx->hot_dirty) {
     const int rc = rebuild_slot_codes(ctx);
     if (rc) return rc;
@@ -1063,6 +1309,10 @@ extern "C" int cml_last_fb_time_ms(cml_ctx* ctx, float* ms, uint32_t* n_kernels)
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   float tot = 0;
   uint32_t nk = 0;
+  if (ctx->dense && ctx->dense->ev0) {
+    CML_CUDA(cudaEventElapsedTime(&tot, ctx->dense->ev0, ctx->dense->ev1));
+    nk = 1;
+  }
   for (auto& bt : ctx->batches) {
     if (!bt->ev_fb0) continue;
     float t = 0;
@@ -1079,6 +1329,11 @@ extern "C" int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n) {
   if (!ctx || !ln_p) return CML_ERR_ARG;
   cudaSetDevice(ctx->device);
   uint64_t done = 0;
+  if (ctx->dense) {
+    const uint64_t k = std::min<uint64_t>(ctx->dense->n_seq, n);
+    CML_CUDA(cudaMemcpyAsync(ln_p, ctx->dense->ex_lnp.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    done = k;
+  }
   for (auto& bt : ctx->batches) {
     if (done >= n) break;
     const uint64_t k = std::min<uint64_t>(bt->n_ex, n - done);
@@ -1093,7 +1348,7 @@ extern "C" int cml_get_example_logprob(cml_ctx* ctx, double* ln_p, uint64_t n) {
 extern "C" int cml_get_arc_counts(cml_ctx* ctx, double* counts) {
   if (!ctx || !counts) return CML_ERR_ARG;
   CML_REQUIRE(ctx->have_model, CML_ERR_STATE, "cml_set_model first");
-  CML_REQUIRE(ctx->slots_are_arcs, CML_ERR_STATE,
+  CML_REQUIRE(ctx->slots_are_arcs && !ctx->dense, CML_ERR_STATE,
               "per-arc counts are not kept: counts are accumulated per unlocked-parameter slot "
               "(set CML_OPT_ARC_COUNTS before cml_set_model, or use cml_get_counts)");
   cudaSetDevice(ctx->device);
@@ -1195,8 +1450,9 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
   CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
-  if (!ctx->trivial) CML_CUDA(cudaMemsetAsync(ctx->acc.p, 0, ctx->n_params * sizeof(double), s));
-  k_param_acc<<<cdiv(ctx->n_slots, 256), 256, 0, s>>>(ctx->n_slots, ctx->trivial ? nullptr : ctx->slot_off.p,
+  const bool slots_are_params = ctx->trivial && !ctx->dense;  // dense mode: slots are T / E cells with chains
+  if (!slots_are_params) CML_CUDA(cudaMemsetAsync(ctx->acc.p, 0, ctx->n_params * sizeof(double), s));
+  k_param_acc<<<cdiv(ctx->n_slots, 256), 256, 0, s>>>(ctx->n_slots, slots_are_params ? nullptr : ctx->slot_off.p,
                                                       ctx->slot_param.p, ctx->reduce,
                                                       ctx->have_prior ? ctx->slot_prior.p : nullptr, ctx->param_tie.p,
                                                       ctx->acc.p);
@@ -1228,8 +1484,8 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
   static const char* const syms[] = {
       "cml_version", "cml_create", "cml_destroy", "cml_last_error", "cml_set_stream", "cml_synchronize",
       "cml_launch_count", "cml_set_option", "cml_set_model", "cml_set_params", "cml_get_params", "cml_snapshot_params",
-      "cml_restore_params", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
-      "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
+      "cml_restore_params", "cml_add_sequences", "cml_dense_stats", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
+      "cml_lane_stats", "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
       "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",

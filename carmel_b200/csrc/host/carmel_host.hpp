@@ -142,6 +142,7 @@ struct TrainOpts {
   int shard_rank = 0, shard_count = 1;  // --shard=r/N : this process trains on block r of N of the corpus
   bool quiet = false;
   bool no_ell = false;              // --no-ell : general (layered CSR) kernels only
+  int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
   TrainOpts();
 };
@@ -153,6 +154,7 @@ struct TrainResult {
   double ln_best_ppx = 0;
   std::vector<IterRecord> history;
   uint64_t trellis_arcs = 0, trellis_states = 0, examples = 0;  // resident on this GPU
+  bool dense = false;  // the E-step runs on the dense-state view (no lattices materialised)
 };
 // The device model: parameters = all arcs of the cascade members (or of x) in arc-table order.
 struct ModelArrays {
@@ -202,6 +204,7 @@ struct TrainJob {
 
   ~TrainJob();
   void prepare();
+  bool try_dense(int tape, Corpus const& local, std::vector<uint32_t>& kept, std::vector<uint32_t>& dropped);
   double estimate(double& ln_unweighted);
   TrainResult const& run(std::ostream& log);        // EM (WFST::train)
   TrainResult const& run_gibbs(std::ostream& log);  // --crp (WFST::train_gibbs)

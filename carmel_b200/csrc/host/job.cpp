@@ -102,6 +102,8 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   if (lopt.count("float")) topt.precision = 32;
   if (lopt.count("scaled")) topt.space = CML_SPACE_SCALED;
   if (lopt.count("no-ell")) topt.no_ell = true;
+  if (lopt.count("no-dense")) topt.dense = -1;
+  if (lopt.count("dense")) topt.dense = 1;
   if (lopt.count("gpu")) topt.device = std::atoi(lopt["gpu"].c_str());
   if (lopt.count("history")) topt.history_file = lopt["history"];
   if (lopt.count("dump-trellis")) topt.dump_trellis_file = lopt["dump-trellis"];

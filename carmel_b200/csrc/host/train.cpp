@@ -92,6 +92,129 @@ void shard_range(Corpus const& corpus, int rank, int count, size_t& e0, size_t& 
   if (e1 < e0) e1 = e0;
 }
 
+// The dense-state view of this shard: symbol sequences + the arc table's (source, destination, symbol) triples.
+// Examples without a derivation are found by a reachability pass over the supports (bit masks, S <= 32) and
+// dropped like the lattice builder drops them; the same pass counts the states and arcs the reference's pruned
+// lattices would have (derivations.h:572-629), which is what the throughput figures are quoted in.
+// Returns false (nothing changed) when the library finds no transition x emission factorisation.
+bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& kept, std::vector<uint32_t>& dropped) {
+  const uint32_t S = x->num_states();
+  std::unordered_map<uint32_t, uint32_t> sym_id;
+  std::vector<uint32_t> a_src, a_dst, a_sym;
+  for (uint32_t s = 0; s < S; ++s)
+    for (Arc const& a : x->states[s]) {
+      const uint32_t sy = tape ? a.out : a.in;
+      auto it = sym_id.find(sy);
+      if (it == sym_id.end()) it = sym_id.emplace(sy, (uint32_t)sym_id.size()).first;
+      a_src.push_back(s);
+      a_dst.push_back(a.dest);
+      a_sym.push_back(it->second);
+    }
+  const uint32_t V = (uint32_t)sym_id.size();
+  if (V == 0 || V > 65535) return false;
+  std::vector<uint32_t> adj((size_t)V * S, 0), radj((size_t)V * S, 0);  // [symbol][state] -> successor / predecessor masks
+  for (size_t a = 0; a < a_src.size(); ++a) {
+    adj[(size_t)a_sym[a] * S + a_src[a]] |= 1u << a_dst[a];
+    radj[(size_t)a_sym[a] * S + a_dst[a]] |= 1u << a_src[a];
+  }
+  const uint32_t fin = x->final_state;
+  std::vector<uint64_t> seq_off{0};
+  std::vector<uint32_t> syms;
+  std::vector<double> wts;
+  std::vector<uint32_t> fwd, cur;
+  uint64_t n_states = 0, n_arcs = 0;
+  for (uint32_t e = 0; e < local.examples.size(); ++e) {
+    std::vector<uint32_t> const& str = tape ? local.examples[e].out : local.examples[e].in;
+    const size_t n = str.size();
+    cur.resize(n);
+    bool known = true;
+    for (size_t t = 0; t < n && known; ++t) {
+      auto it = sym_id.find(str[t]);
+      known = it != sym_id.end();
+      if (known) cur[t] = it->second;
+    }
+    bool alive = known;
+    if (alive) {
+      fwd.assign(n + 1, 0);
+      fwd[0] = 1u;
+      for (size_t t = 0; t < n; ++t) {
+        uint32_t m = fwd[t], nx = 0;
+        const uint32_t* row = &adj[(size_t)cur[t] * S];
+        while (m) {
+          const int i = __builtin_ctz(m);
+          m &= m - 1;
+          nx |= row[i];
+        }
+        fwd[t + 1] = nx;
+      }
+      alive = (fwd[n] >> fin) & 1u;
+    }
+    if (!alive) {
+      dropped.push_back(e);
+      continue;
+    }
+    // co-reachability; live_t = fwd_t & bwd_t, arcs between consecutive live sets
+    uint32_t live_next = 1u << fin;
+    uint64_t st = 1, ar = 0;
+    for (size_t t = n; t-- > 0;) {
+      uint32_t m = live_next, pv = 0;
+      const uint32_t* rrow = &radj[(size_t)cur[t] * S];
+      while (m) {
+        const int j = __builtin_ctz(m);
+        m &= m - 1;
+        pv |= rrow[j];
+      }
+      const uint32_t live = pv & fwd[t];
+      const uint32_t* row = &adj[(size_t)cur[t] * S];
+      m = live;
+      while (m) {
+        const int i = __builtin_ctz(m);
+        m &= m - 1;
+        ar += __builtin_popcount(row[i] & live_next);
+      }
+      st += __builtin_popcount(live);
+      live_next = live;
+    }
+    n_states += st;
+    n_arcs += ar;
+    kept.push_back(e);
+    syms.insert(syms.end(), cur.begin(), cur.end());
+    seq_off.push_back(syms.size());
+    wts.push_back(local.examples[e].weight);
+  }
+  cml_dense_view v{};
+  v.n_states = S;
+  v.n_symbols = V;
+  v.start = 0;
+  v.final_state = fin;
+  v.arc_src = a_src.data();
+  v.arc_dst = a_dst.data();
+  v.arc_sym = a_sym.data();
+  cml_sequence_batch b{};
+  b.n_seq = wts.size();
+  b.seq_off = seq_off.data();
+  b.sym = syms.data();
+  b.seq_weight = wts.data();
+  const int rc = cml_add_sequences(ctx, &v, &b);
+  if (rc == CML_ERR_NOT_DENSE) {
+    if (!opt.quiet && !flags[(unsigned)'q']) std::cerr << "dense-state view not applicable (" << cml_last_error(ctx) << "); using lattices\n";
+    kept.clear();
+    dropped.clear();
+    return false;
+  }
+  ok(rc);
+  uint32_t nt = 0, ne = 0;
+  ok(cml_dense_stats(ctx, nullptr, nullptr, &nt, &ne));
+  if (!opt.quiet && !flags[(unsigned)'q'])
+    std::cerr << "dense-state path: " << S << " states x " << V << " symbols, " << nt << " trainable transition cells, "
+              << ne << " trainable emission cells\n";
+  res.trellis_arcs = n_arcs;
+  res.trellis_states = n_states;
+  res.examples = wts.size();
+  res.dense = true;
+  return true;
+}
+
 // Everything up to the first E-step: model tables, initial normalisation, prior counts, derivation
 // lattices (this rank's shard) flattened and resident on the GPU.
 void TrainJob::prepare() {
@@ -165,6 +288,24 @@ void TrainJob::prepare() {
   // ---- derivation lattices: built once, resident on the GPU (carmel's -: cache semantics) ----
   // With --shard=r/N only a contiguous block of the corpus (balanced by string length) is built and
   // kept on this GPU; corpus statistics are then made global through the all-reduce hook.
+  // Dense-state view (cml_add_sequences): every arc consumes one symbol of one tape and the other tape of
+  // every pair is empty -> lattice states are (position, state) and nothing needs to be materialised.  The
+  // decision is made on the WHOLE corpus and the model, so every rank of a sharded run takes the same path.
+  int dense_tape = -1;  // 0: symbols on the input tape, 1: on the output tape
+  if (opt.dense >= 0 && opt.space == CML_SPACE_SCALED && opt.max_iter != 0 && opt.dump_trellis_file.empty() &&
+      x->num_states() <= 32) {
+    bool in_only = true, out_only = true;
+    for (auto const& st : x->states)
+      for (Arc const& a : st) {
+        in_only = in_only && a.in != kEps && a.out == kEps;
+        out_only = out_only && a.out != kEps && a.in == kEps;
+      }
+    for (Example const& ex : corpus.examples) {
+      in_only = in_only && ex.out.empty();
+      out_only = out_only && ex.in.empty();
+    }
+    dense_tape = out_only ? 1 : in_only ? 0 : -1;
+  }
   size_t e0, e1;
   shard_range(corpus, opt.shard_rank, opt.shard_count, e0, e1);
   {
@@ -172,13 +313,21 @@ void TrainJob::prepare() {
     local.examples.assign(std::make_move_iterator(corpus.examples.begin() + e0),
                           std::make_move_iterator(corpus.examples.begin() + e1));
     TrellisBatch tb;
-    std::vector<uint32_t> dropped;
-    build_trellises(*x, local, tb, dropped);
+    std::vector<uint32_t> dropped, kept;
+    bool dense_done = false;
+    if (dense_tape >= 0) dense_done = try_dense(dense_tape, local, kept, dropped);
+    if (opt.dense > 0 && !dense_done)
+      throw std::runtime_error(std::string("--dense: no dense-state view of this model / corpus") +
+                               (ctx ? std::string(": ") + cml_last_error(ctx) : std::string()));
+    if (!dense_done) {
+      build_trellises(*x, local, tb, dropped);
+      kept = tb.kept_example;
+    }
     for (uint32_t e : dropped)  // cached_derivs.h:53-57,87-93
       std::cerr << "No derivations in transducer for input/output #" << e0 + e + 1 << ":\n";
     std::vector<Example> keep;
-    keep.reserve(tb.kept_example.size());
-    for (uint32_t e : tb.kept_example) keep.push_back(std::move(local.examples[e]));
+    keep.reserve(kept.size());
+    for (uint32_t e : kept) keep.push_back(std::move(local.examples[e]));
     corpus.examples.swap(keep);
     corpus.count();
     if (opt.shard_count > 1) {  // global corpus statistics: one small all-reduce
@@ -203,20 +352,22 @@ void TrainJob::prepare() {
       std::ofstream o(opt.dump_trellis_file, std::ios::binary);
       tb.dump(o, M.n_arcs);
     }
-    if (!tb.ex_states.empty()) {
-      cml_trellis_batch b{};
-      b.n_ex = tb.ex_states.size();
-      b.ex_states = tb.ex_states.data();
-      b.ex_fin = tb.ex_fin.data();
-      b.ex_weight = tb.ex_weight.data();
-      b.arc_off = tb.arc_off.data();
-      b.arc_dst = tb.arc_dst.data();
-      b.arc_id = tb.arc_id.data();
-      ok(cml_add_trellises(ctx, &b));
+    if (!dense_done) {
+      if (!tb.ex_states.empty()) {
+        cml_trellis_batch b{};
+        b.n_ex = tb.ex_states.size();
+        b.ex_states = tb.ex_states.data();
+        b.ex_fin = tb.ex_fin.data();
+        b.ex_weight = tb.ex_weight.data();
+        b.arc_off = tb.arc_off.data();
+        b.arc_dst = tb.arc_dst.data();
+        b.arc_id = tb.arc_id.data();
+        ok(cml_add_trellises(ctx, &b));
+      }
+      res.trellis_arcs = tb.arc_dst.size();
+      res.examples = tb.ex_states.size();
+      for (uint32_t n : tb.ex_states) res.trellis_states += n;
     }
-    res.trellis_arcs = tb.arc_dst.size();
-    res.examples = tb.ex_states.size();
-    for (uint32_t n : tb.ex_states) res.trellis_states += n;
   }
   prepared = true;
 }

@@ -34,7 +34,9 @@ enum cml_status {
   CML_ERR_CUDA = -2,   /* CUDA runtime error or no usable device */
   CML_ERR_STATE = -3,  /* call order violated (e.g. estimate before set_model) */
   CML_ERR_CYCLE = -4,  /* derivation lattice has a cycle (reference only warns: derivations.h:726-728) */
-  CML_ERR_NODERIV = -5 /* no training example had a derivation (train.cc:249-252) */
+  CML_ERR_NODERIV = -5, /* no training example had a derivation (train.cc:249-252) */
+  CML_ERR_NOT_DENSE = -6 /* cml_add_sequences: the arc table has no transition x emission factorisation
+                            (or too many states); nothing was changed, use cml_add_trellises instead */
 };
 
 enum cml_space { CML_SPACE_LOG = 0, CML_SPACE_SCALED = 1 };
@@ -62,7 +64,10 @@ enum cml_option {
   CML_OPT_ARC_COUNTS = 1, /* keep one expected-count accumulator per arc-table entry (needed by
                              cml_get_arc_counts on real cascades); default 0: arcs whose chains have the same
                              unlocked parameters share an accumulator.  Set before cml_set_model. */
-  CML_OPT_NO_ELL = 2      /* force the layered-CSR kernels (tests).  Set before cml_add_trellises. */
+  CML_OPT_NO_ELL = 2,     /* force the layered-CSR kernels (tests).  Set before cml_add_trellises. */
+  CML_OPT_LANE_MIN = 3,   /* the lane-per-lattice kernel (narrow lattices, tiles of 32) is used when a batch has at
+                             least this many eligible lattices; default 16384, 0 = never.  Before cml_add_trellises. */
+  CML_OPT_NO_COUNTS = 4   /* profiling only: the lane kernel skips its expected-count REDs */
 };
 int cml_set_option(cml_ctx* ctx, int option, int value);
 
@@ -141,9 +146,45 @@ int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_
  * (throughput kernel) and examples in the layered-CSR layout (general kernels) */
 int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,
                      uint64_t* csr_examples);
+/* lattices / arcs / padded records (both sweeps) resident in the lane-per-lattice layout, and its tiles */
+int cml_lane_stats(cml_ctx* ctx, uint64_t* lane_examples, uint64_t* lane_arcs, uint64_t* lane_records, uint64_t* tiles);
 /* introspection for parity tests: the layered layout of resident example e.
  *   level_of[ex_states]  level of each reference state id;  local_of[ex_states] its layered index. */
 int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_t* level_of, uint32_t* local_of);
+
+/* ---- dense-state sequences (position-synchronous lattices) ------------------------------------ *
+ * The same derivations::g lattices (carmel/src/derivations.h:479-513,640-704) for the special case where
+ * every arc of the trained transducer consumes exactly one symbol of ONE tape and nothing of the other
+ * (e.g. a letter-bigram LM composed with a substitution channel, trained on (empty input, ciphertext)
+ * pairs): lattice state (t, s) exists for every position t and transducer state s, so the lattice is never
+ * materialised.  The caller gives the arc table's (source, destination, symbol) triples and the observed
+ * symbol sequences; the library checks that the cascade chains factor as
+ *     w(i -> j, o) = T[i][j] * E[j][o]      (chain = parameters depending on (i,j) + parameters depending on (j,o))
+ * and then runs forward/backward as one S x S transition product per position followed by the emission
+ * column of the observed symbol (each position step of a batch of sequences is a dense [batch x S] * [S x S]
+ * product).  Expected counts are accumulated per T cell (xi) and per E cell (gamma) and handed to the same
+ * M-step; likelihoods and learned weights equal the lattice path's (unreachable / dead lattice states carry
+ * alpha = 0 or beta = 0).  Needs a CML_SPACE_SCALED context, n_states <= 32, no lattices resident.
+ * After success the count slots (cml_count_slots, cml_get_counts, the reduce buffer) are the trainable T / E
+ * cells and stay so until the next cml_set_model; per-arc counts are not available.
+ * Returns CML_ERR_NOT_DENSE (context unchanged) when the arc table does not factor. */
+typedef struct cml_dense_view {
+  uint32_t n_states;        /* states of the trained transducer */
+  uint32_t n_symbols;       /* observed alphabet: sequence symbols are ids in [0, n_symbols) */
+  uint32_t start, final_state;
+  const uint32_t* arc_src;  /* [n_arcs] per arc-table id */
+  const uint32_t* arc_dst;
+  const uint32_t* arc_sym;  /* the symbol the arc consumes */
+} cml_dense_view;
+typedef struct cml_sequence_batch {
+  uint64_t n_seq;
+  const uint64_t* seq_off;  /* [n_seq+1] sequence e owns sym[seq_off[e] .. seq_off[e+1]) */
+  const uint32_t* sym;
+  const double* seq_weight; /* [n_seq] example weight */
+} cml_sequence_batch;
+int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b);
+/* resident dense sequences: count, positions (sum of lengths), and whether T cells are trainable (xi kept) */
+int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positions, uint32_t* n_t_slots, uint32_t* n_e_slots);
 
 /* ---- E-step ----------------------------------------------------------------------------------- *
  * Replaces forward_backward::estimate (carmel/src/train.cc:763-773) = cascade.update (cascade.h:466-479),
