@@ -263,6 +263,8 @@ def main():
         # the job's context must run on our stream before lattices are uploaded
         ctx = job.prepare()
         ctx.set_stream(stream.cuda_stream)
+        if os.environ.get("CML_BENCH_NO_COUNTS"):  # profiling experiment only: the sweep without its count REDs
+            ctx.set_option(cb.OPT_NO_COUNTS, 1)
         t_build = time.time() - t_build
         info = job.stats()
         dense = ctx.dense_stats()
@@ -397,7 +399,7 @@ def main():
                                    f"{n_k} launch(es) per iteration)", "kernel_ms": k_ms,
                                    "algorithmic_bytes_per_arc": bytes_per_arc, "arcs_per_launch_set": arcs_local,
                                    "kernel_share_of_step": k_ms / (ms / a.steps)}
-                res["layout"] = ctx.layout_stats()
+                res["layout"] = {**ctx.layout_stats(), **ctx.lane_stats()}
         job.close()
         return res
 

@@ -19,7 +19,7 @@ SPACE_LOG, SPACE_SCALED = 0, 1
 NO_GROUP = 0xFFFFFFFF
 LOCKED_GROUP = 0
 
-OPT_ARC_COUNTS, OPT_NO_ELL = 1, 2
+OPT_ARC_COUNTS, OPT_NO_ELL, OPT_LANE_MIN, OPT_NO_COUNTS = 1, 2, 3, 4
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV, ERR_NOT_DENSE = 0, -1, -2, -3, -4, -5, -6
 
 _u32p = C.POINTER(C.c_uint32)
@@ -120,6 +120,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_maximize.argtypes = [vp, C.c_double, _f64p]
     lib.cml_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.cml_layout_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
+    lib.cml_lane_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_count_slots.argtypes = [vp]
     lib.cml_count_slots.restype = C.c_uint64
     lib.cml_get_counts.argtypes = [vp, _f64p, C.c_uint64]
@@ -326,6 +327,11 @@ class Context:
         v = [C.c_uint64() for _ in range(4)]
         self._check(self.lib.cml_layout_stats(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("ell_examples", "ell_arcs", "ell_records", "csr_examples"), (int(x.value) for x in v)))
+
+    def lane_stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.lib.cml_lane_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("lane_examples", "lane_arcs", "lane_records", "tiles"), (int(x.value) for x in v)))
 
     def count_slots(self) -> int:
         return int(self.lib.cml_count_slots(self.h))

@@ -142,6 +142,7 @@ struct TrainOpts {
   int shard_rank = 0, shard_count = 1;  // --shard=r/N : this process trains on block r of N of the corpus
   bool quiet = false;
   bool no_ell = false;              // --no-ell : general (layered CSR) kernels only
+  int lane_min = -1;                // --lane-min=n / --no-lane : CML_OPT_LANE_MIN (-1 = library default)
   int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
   TrainOpts();

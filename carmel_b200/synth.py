@@ -55,7 +55,7 @@ def write_cipher(outdir: str, n_lines: int = 2000, line_len: int = 50, seed: int
 
 
 def write_hmm(outdir: str, n_sent: int = 125000, n_tags: int = 32, vocab: int = 5000, tags_per_word: int = 4,
-              seed: int = 20260103) -> dict:
+              seed: int = 20260103, len_range: tuple = (10, 41)) -> dict:
     rng = np.random.default_rng(seed)
     os.makedirs(outdir, exist_ok=True)
     fsa, fst, data = (os.path.join(outdir, f) for f in ("tags.fsa", "lexicon.fst", "sentences.data"))
@@ -79,7 +79,7 @@ def write_hmm(outdir: str, n_sent: int = 125000, n_tags: int = 32, vocab: int = 
                 f.write(f"(0 (0 {_q(tags[t])} {_q(words[w])} 1))\n")
     zipf = 1.0 / np.arange(1, vocab + 1) ** 1.1
     zipf /= zipf.sum()
-    lens = rng.integers(10, 41, size=n_sent)
+    lens = rng.integers(len_range[0], len_range[1], size=n_sent)
     toks = rng.choice(vocab, size=int(lens.sum()), p=zipf)
     with open(data, "w") as f:
         pos = 0
