@@ -70,8 +70,17 @@ struct Batch {
 };
 
 // Dense-state sequences (cml_add_sequences, cml_dense.cu): w(i -> j, o) = T[i][j] * E[j][o].
+struct SparseTile {     // sparse-emission kernel: 32 sequences of similar length
+  uint64_t sym_base;    // symbol t of lane l at sym[sym_base + t*32 + l]
+  uint64_t row_base;    // alpha rows: alpha[((row_base + t) * K + c) * 32 + l], exps[(row_base + t) * 32 + l]
+  uint32_t n_max, pad;
+};
 struct DenseState {
   uint32_t S = 0, n_sym = 0, start = 0, fin = 0;
+  uint32_t SP = 32, nT = 1024, K = 0;  // padded state count (row stride of T); sparse kernel: emission row width (4 / 8)
+  bool sparse = false;      // lane-per-sequence sparse-emission kernel instead of the warp-per-sequence dense one
+  int has_phi = 0;          // epsilon arcs into the final state = final weights
+  uint32_t n_tiles = 0;
   uint64_t n_seq = 0, n_pos = 0;
   uint32_t n_t_slots = 0, n_e_slots = 0;
   uint32_t n_cells = 0;  // 32*32 T cells then n_sym*32 E cells (symbol major)
@@ -83,6 +92,11 @@ struct DenseState {
   DevArray<double> seq_weight, ex_lnp;
   DevArray<unsigned char> alpha_g;  // Real[(n_pos + n_seq)][32]
   DevArray<int> exp_g;              // cumulative power-of-two exponent of every alpha row
+  // sparse kernel: tiles of 32 sequences, per-lane facts, emission rows
+  DevArray<SparseTile> stile;
+  DevArray<uint32_t> lane_len, lane_seq, e_code;
+  DevArray<double> lane_weight;
+  DevArray<unsigned char> e_state;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ~DenseState() {
     if (ev0) cudaEventDestroy(ev0);
@@ -107,7 +121,7 @@ struct cml_ctx {
 
   // model
   bool have_model = false, trivial = true;
-  uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0, n_slots = 0;
+  uint32_t n_arcs = 0, n_params = 0, n_groups = 0, n_ties = 0, n_slots = 0, max_group_size = 0;
   bool slots_are_arcs = true;
   std::vector<uint32_t> h_arc_slot;  // host copy: slot of every arc (kPadNone = contributes to no parameter)
   // internal arc numbering (locality order): weight tables and lattice records use perm[arc id]

@@ -358,6 +358,357 @@ int launch_dense(cml_ctx* ctx) {
   return CML_OK;
 }
 
+// =====================================================================================================
+// Sparse-emission variant (k_fb_sparse): HMM / tagging style models where a symbol is emitted by only a few
+// states (a word has <= 8 possible tags) and sequences are many and short.  One sequence per LANE (tiles of
+// 32 sequences of similar length, symbol streams stored transposed sym[t][lane]); a lane keeps the alpha values
+// of the <= K active states of the current position in registers, the transition matrix T (S <= 64) and the
+// final weights live in shared memory, the emission row of a symbol is ONE gather of K values.  A position
+// costs K*K shared-memory reads + FMAs and touches HBM for the symbol, K alpha values (written once, read once)
+// and an exponent -- the lattice (K*K 16-byte arc records per position) is never streamed.
+// epsilon arcs into a final state without outgoing arcs are final weights phi[s] (tagging.fsa style).
+// =====================================================================================================
+constexpr int kSW = 8;       // warps per CTA (sparse kernel)
+constexpr int kSXi = 4;      // transition-count tables per CTA when they fit: one per pair of warps
+struct SparseArgs {
+  const SparseTile* tile;
+  uint32_t n_tiles;
+  const uint16_t* sym;
+  const uint32_t* len;        // [tile*32+lane]
+  const uint32_t* seq;        // [tile*32+lane] sequence index (0xFFFFFFFF = empty lane)
+  const double* weight;       // [tile*32+lane]
+  uint32_t S, SP, start, fin;
+  const void* T;              // Real[SP*SP]
+  const void* Ev;             // Real[n_sym*K]
+  const void* Phi;            // Real[SP] final weights of the epsilon arcs (0 where absent)
+  const unsigned char* e_state;  // [n_sym*K] state of every emission entry (SP-1, the zero state, for padding)
+  const uint32_t* e_code;     // [n_sym*K] count-slot code of every emission entry (CountSink codes)
+  const uint32_t* t_slot;     // [SP*SP] slot or kNone
+  const uint32_t* f_slot;     // [SP]
+  cmlk::CountSink sink;
+  double* ex_lnp;
+  void* alpha;
+  int* exps;
+  int has_phi;                // epsilon final arcs exist (otherwise P = alpha_n[fin])
+  uint32_t xi_tables;         // shared-memory transition-count tables per CTA: kSW (one per warp) or 1
+};
+
+template <typename Real, int K>
+struct RowVec {
+  Real v[K];
+};
+template <typename Real, int K>
+__device__ __forceinline__ void load_row(const Real* p, Real (&v)[K]) {  // K consecutive Reals, 16-byte aligned
+  if (sizeof(Real) * K % 16 == 0) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 raw[sizeof(Real) * K / 16];
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(Real) * K / 16); ++i) raw[i] = __ldg(q + i);
+    memcpy(v, raw, sizeof(Real) * K);
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = __ldg(p + i);
+  }
+}
+template <int K>
+__device__ __forceinline__ void load_states(const unsigned char* p, uint32_t (&st)[K]) {
+  if (K == 4) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+#pragma unroll
+    for (int i = 0; i < K; ++i) st[i] = (w >> (8 * i)) & 0xff;
+  } else {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+#pragma unroll
+    for (int i = 0; i < K; ++i) st[i] = ((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xff;
+  }
+}
+template <typename Real, int K>
+__device__ __forceinline__ void lane_renorm(Real (&a)[K], int& E) {
+  int mx = 0;
+#pragma unroll
+  for (int c = 0; c < K; ++c) mx = max(mx, DN<Real>::bits(a[c]));
+  if (mx > 0) {
+    const int e = DN<Real>::expo(mx);
+    const Real f = DN<Real>::pow2(-e);
+#pragma unroll
+    for (int c = 0; c < K; ++c) a[c] *= f;
+    E += e;
+  }
+}
+
+
+template <typename Real, int K, bool XI>
+__global__ void __launch_bounds__(kSW * 32) k_fb_sparse(SparseArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t SP = A.SP;
+  Real* Ts = reinterpret_cast<Real*>(smem);
+  Real* Ph = Ts + SP * SP;
+  // expected transition counts: a few tables per CTA when they fit (fp64 shared-memory atomics are CAS loops on
+  // sm_100a; with one CTA-wide table they were 75% of the kernel: profiles/r1e_hmm_k_fb_sparse_f64.txt)
+  double* xis_all = reinterpret_cast<double*>(smem + (((size_t)SP * SP + SP) * sizeof(Real) + 15) / 16 * 16);
+  const uint32_t n_xi = XI ? A.xi_tables : 0;
+  double* phc = xis_all + (size_t)n_xi * SP * SP;
+  double* xis = xis_all + (size_t)(n_xi > 1 ? ((threadIdx.x >> 5) % n_xi) : 0) * SP * SP;
+  // per-lane staging columns of the xi update (private to the lane: no synchronisation)
+  Real* xst = reinterpret_cast<Real*>(phc + SP) + (size_t)(threadIdx.x >> 5) * 2 * K * 32 + (threadIdx.x & 31);
+  Real* bst = xst + K * 32;
+  for (uint32_t i = threadIdx.x; i < SP * SP; i += blockDim.x) Ts[i] = reinterpret_cast<const Real*>(A.T)[i];
+  for (uint32_t i = threadIdx.x; i < n_xi * SP * SP; i += blockDim.x) xis_all[i] = 0.;
+  for (uint32_t i = threadIdx.x; i < SP; i += blockDim.x) {
+    Ph[i] = reinterpret_cast<const Real*>(A.Phi)[i];
+    phc[i] = 0.;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile = blockIdx.x * kSW + (threadIdx.x >> 5);
+  if (tile < A.n_tiles) {
+    const SparseTile T = A.tile[tile];
+    const uint32_t li = tile * 32 + lane;
+    const uint32_t n = A.len[li], seq = A.seq[li];
+    const bool live = seq != 0xFFFFFFFFu;
+    const uint16_t* __restrict__ sy = A.sym + T.sym_base + lane;
+    Real* __restrict__ ag = reinterpret_cast<Real*>(A.alpha) + T.row_base * K * 32 + lane;
+    int* __restrict__ ex = A.exps + T.row_base * 32 + lane;
+    const Real* __restrict__ Ev = reinterpret_cast<const Real*>(A.Ev);
+    // ------------------------------------------------------------ forward
+    Real a[K];
+    uint32_t st[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      a[c] = 0;
+      st[c] = SP - 1;  // the padding state: its row and column of T and its final weight are zero
+    }
+    a[0] = live ? Real(1) : Real(0);
+    st[0] = A.start;
+    int Ea = 0;
+#pragma unroll
+    for (int c = 0; c < K; ++c) ag[(size_t)c * 32] = a[c];
+    ex[0] = 0;
+    uint32_t o_next = T.n_max ? sy[0] : 0;
+    for (uint32_t t = 0; t < T.n_max; ++t) {
+      const uint32_t o = o_next;
+      if (t + 1 < T.n_max) o_next = sy[(size_t)(t + 1) * 32];
+      if (t < n) {
+        uint32_t es[K];
+        Real ev[K], nw[K];
+        load_states<K>(A.e_state + (size_t)o * K, es);
+        load_row<Real, K>(Ev + (size_t)o * K, ev);
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          Real acc = 0;
+#pragma unroll
+          for (int d = 0; d < K; ++d) acc = fma(a[d], Ts[st[d] * SP + es[c]], acc);
+          nw[c] = acc * ev[c];
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          a[c] = nw[c];
+          st[c] = es[c];
+        }
+        lane_renorm<Real, K>(a, Ea);
+#pragma unroll
+        for (int c = 0; c < K; ++c) ag[((size_t)(t + 1) * K + c) * 32] = a[c];
+        ex[(size_t)(t + 1) * 32] = Ea;
+      }
+    }
+    // probability: final weights of the active states (or the final state itself)
+    Real b[K];
+    Real pfin = 0;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      b[c] = A.has_phi ? Ph[st[c]] : (st[c] == A.fin ? Real(1) : Real(0));
+      pfin = fma(a[c], b[c], pfin);
+    }
+    const int EaN = Ea;
+    if (live) A.ex_lnp[seq] = (pfin > 0) ? log((double)pfin) + (double)EaN * 0.69314718055994530942 : -CUDART_INF;
+    const double cw = (live && pfin > 0) ? A.weight[li] / (double)pfin : 0.;
+    // ------------------------------------------------------------ backward + counts
+    if (cw > 0) {
+      if (A.has_phi) {  // counts of the epsilon final arcs: gamma_n(s) * phi[s] / P
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const double g = (double)a[c] * (double)b[c] * cw;
+          if (g > 0) atomicAdd(&phc[st[c]], g);
+        }
+      }
+      int Eb = 0;
+      Real a1[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) a1[c] = a[c];
+      int Ea1 = EaN;
+      // emission row of the symbol that leads INTO position t+1 = the active states of position t+1
+      uint32_t es[K];
+      Real ev[K];
+      uint32_t o = n ? sy[(size_t)(n - 1) * 32] : 0;
+#pragma unroll
+      for (int c = 0; c < K; ++c) es[c] = st[c];
+      if (n) load_row<Real, K>(Ev + (size_t)o * K, ev);
+      for (uint32_t t = n; t-- > 0;) {
+        // active states of position t: emission row of symbol t-1 (or the start state)
+        uint32_t ps[K];
+        uint32_t op = 0;
+        if (t > 0) {
+          op = sy[(size_t)(t - 1) * 32];
+          load_states<K>(A.e_state + (size_t)op * K, ps);
+        } else {
+#pragma unroll
+          for (int c = 0; c < K; ++c) ps[c] = SP - 1;
+          ps[0] = A.start;
+        }
+        Real a0[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) a0[c] = ag[((size_t)t * K + c) * 32];
+        const int Ea0 = ex[(size_t)t * 32];
+        // gamma of position t+1 -> emission cells of symbol o
+        uint32_t code[K];
+        {
+          const uint4* q = reinterpret_cast<const uint4*>(A.e_code + (size_t)o * K);
+          uint4 r0 = __ldg(q);
+          code[0] = r0.x; code[1] = r0.y; code[2] = r0.z; code[3] = r0.w;
+          if (K == 8) {
+            uint4 r1 = __ldg(q + 1);
+            code[4 % K] = r1.x; code[5 % K] = r1.y; code[6 % K] = r1.z; code[7 % K] = r1.w;
+          }
+        }
+        const double g1 = cw * pow2d(Ea1 + Eb - EaN);
+        Real bt[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const double gamma = (double)a1[c] * (double)b[c] * g1;
+          if (gamma > 0 && code[c] != kNone) cmlk::count_add(A.sink, code[c], gamma);
+          bt[c] = b[c] * ev[c];
+        }
+        const double g0 = cw * pow2d(Ea0 + Eb - EaN);
+        Real nb[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+          Real acc = 0;
+#pragma unroll
+          for (int c = 0; c < K; ++c) acc = fma(Ts[ps[d] * SP + es[c]], bt[c], acc);
+          nb[d] = acc;
+        }
+        if (XI) {
+          // xi_t(i,j) = alpha_t[i] T[i][j] E[j][o] beta_{t+1}[j] / P for the K x K active pairs.  The lanes of a warp
+          // share the warp's count table, and frequent tags sit at the same list position in most lanes, so the pairs
+          // are visited in a lane-rotated order: simultaneous updates of one cell (a CAS retry each) become rare.
+          uint64_t pp = 0, ee = 0;
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            xst[c * 32] = (Real)((double)a0[c] * g0);
+            bst[c * 32] = bt[c];
+            pp |= (uint64_t)ps[c] << (8 * c);
+            ee |= (uint64_t)es[c] << (8 * c);
+          }
+#pragma unroll 4
+          for (int k = 0; k < K * K; ++k) {
+            const int idx = (k + lane) & (K * K - 1);
+            const int d = idx / K, c = idx % K;
+            const uint32_t cell = (uint32_t)((pp >> (8 * d)) & 0xff) * SP + (uint32_t)((ee >> (8 * c)) & 0xff);
+            const double xv = (double)xst[d * 32] * (double)Ts[cell] * (double)bst[c * 32];
+            if (xv > 0) atomicAdd(&xis[cell], xv);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          b[c] = nb[c];
+          a1[c] = a0[c];
+          es[c] = ps[c];
+        }
+        lane_renorm<Real, K>(b, Eb);
+        Ea1 = Ea0;
+        o = op;
+        if (t > 0) load_row<Real, K>(Ev + (size_t)o * K, ev);
+      }
+    }
+  }
+  __syncthreads();
+  if (XI)
+    for (uint32_t c = threadIdx.x; c < SP * SP; c += blockDim.x) {
+      const uint32_t sl = A.t_slot[c];
+      if (sl == kNone) continue;
+      double v = 0;
+      for (uint32_t k = 0; k < n_xi; ++k) v += xis_all[(size_t)k * SP * SP + c];
+      if (v != 0.) atomicAdd(A.sink.counts + sl, v);
+    }
+  for (uint32_t c = threadIdx.x; c < SP; c += blockDim.x) {
+    const uint32_t sl = A.f_slot[c];
+    if (sl != kNone && phc[c] != 0.) atomicAdd(A.sink.counts + sl, phc[c]);
+  }
+}
+
+template <typename Real>
+static size_t sparse_smem(uint32_t SP, uint32_t xi_tables, uint32_t K) {
+  size_t b = (((size_t)SP * SP + SP) * sizeof(Real) + 15) / 16 * 16;
+  b += ((size_t)xi_tables * SP * SP + SP) * sizeof(double);
+  if (xi_tables) b += (size_t)kSW * 2 * K * 32 * sizeof(Real);
+  return b;
+}
+
+template <typename Real>
+int launch_sparse(cml_ctx* ctx) {
+  DenseState& D = *ctx->dense;
+  cudaStream_t s = ctx->stream;
+  k_dense_tables<Real><<<cdiv(D.n_cells, 256), 256, 0, s>>>(D.n_cells, D.cell_off.p, D.cell_param.p, D.cell_exists.p,
+                                                           ctx->ln_w.p, reinterpret_cast<Real*>(D.tables.p));
+  ++ctx->launches;
+  CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
+  if (ctx->n_hot)
+    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * cmlk::kHotCopies * sizeof(double), s));
+  const size_t rs = sizeof(Real);
+  const uint32_t SP = D.SP, K = D.K;
+  SparseArgs A;
+  A.tile = D.stile.p;
+  A.n_tiles = D.n_tiles;
+  A.sym = D.sym.p;
+  A.len = D.lane_len.p;
+  A.seq = D.lane_seq.p;
+  A.weight = D.lane_weight.p;
+  A.S = D.S;
+  A.SP = SP;
+  A.start = D.start;
+  A.fin = D.fin;
+  A.T = D.tables.p;
+  A.Ev = D.tables.p + (size_t)D.nT * rs;
+  A.Phi = D.tables.p + ((size_t)D.nT + (size_t)D.n_sym * K) * rs;
+  A.e_state = D.e_state.p;
+  A.e_code = D.e_code.p;
+  A.t_slot = D.cell_slot.p;
+  A.f_slot = D.cell_slot.p + (size_t)D.nT + (size_t)D.n_sym * K;
+  A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+  A.ex_lnp = D.ex_lnp.p;
+  A.alpha = D.alpha_g.p;
+  A.exps = D.exp_g.p;
+  A.has_phi = D.has_phi;
+  const bool xi = D.n_t_slots > 0;
+  A.xi_tables = !xi ? 0u : (sparse_smem<Real>(SP, kSXi, K) <= 72 * 1024 ? (uint32_t)kSXi : 1u);
+  const size_t smem = sparse_smem<Real>(SP, A.xi_tables, K);
+  void (*kern)(SparseArgs) =
+      K == 4 ? (xi ? k_fb_sparse<Real, 4, true> : k_fb_sparse<Real, 4, false>)
+             : (xi ? k_fb_sparse<Real, 8, true> : k_fb_sparse<Real, 8, false>);
+  CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!D.ev0) {
+    CML_CUDA(cudaEventCreate(&D.ev0));
+    CML_CUDA(cudaEventCreate(&D.ev1));
+  }
+  CML_CUDA(cudaEventRecord(D.ev0, s));
+  if (D.n_tiles) {
+    kern<<<cdiv(D.n_tiles, kSW), kSW * 32, smem, s>>>(A);
+    ++ctx->launches;
+  }
+  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (ctx->n_hot) {
+    cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, s>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p, ctx->reduce);
+    ++ctx->launches;
+  }
+  if (D.n_seq) {
+    cmlk::k_reduce_lnp<<<std::min<unsigned>(cdiv(D.n_seq, 256), 4 * ctx->sm_count), 256, 0, s>>>(
+        D.ex_lnp.p, D.seq_weight.p, D.n_seq, ctx->reduce + ctx->n_slots);
+    ++ctx->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
 // multiset helpers on sorted vectors
 std::vector<uint32_t> ms_intersect(const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) {
   std::vector<uint32_t> r;
@@ -373,6 +724,7 @@ std::vector<uint32_t> ms_minus(const std::vector<uint32_t>& a, const std::vector
 }  // namespace
 
 int cml_dense_estimate_launch(cml_ctx* ctx) {
+  if (ctx->dense->sparse) return ctx->precision == 64 ? launch_sparse<double>(ctx) : launch_sparse<float>(ctx);
   return ctx->precision == 64 ? launch_dense<double>(ctx) : launch_dense<float>(ctx);
 }
 
@@ -388,17 +740,57 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   CML_REQUIRE(v->n_symbols > 0 && v->n_symbols <= 65535, CML_ERR_ARG, "n_symbols must be in 1..65535");
   CML_REQUIRE(v->start < v->n_states && v->final_state < v->n_states, CML_ERR_ARG, "start / final state out of range");
   const uint32_t S = v->n_states, V = v->n_symbols, nA = ctx->n_arcs;
-  if (S > kDS) {
-    ctx->err = "dense-state path needs n_states <= 32";
+  if (S > 64) {
+    ctx->err = "dense-state path needs n_states <= 64";
     return CML_ERR_NOT_DENSE;
   }
-  for (uint32_t a = 0; a < nA; ++a)
-    CML_REQUIRE(v->arc_src[a] < S && v->arc_dst[a] < S && v->arc_sym[a] < V, CML_ERR_ARG, "arc triple out of range");
+  bool has_phi = false;
+  for (uint32_t a = 0; a < nA; ++a) {
+    CML_REQUIRE(v->arc_src[a] < S && v->arc_dst[a] < S && (v->arc_sym[a] < V || v->arc_sym[a] == CML_DENSE_EPS),
+                CML_ERR_ARG, "arc triple out of range");
+    if (v->arc_sym[a] == CML_DENSE_EPS) has_phi = true;
+  }
+  if (has_phi)  // epsilon arcs are final weights: only into the final state, which must be a sink
+    for (uint32_t a = 0; a < nA; ++a) {
+      const bool eps = v->arc_sym[a] == CML_DENSE_EPS;
+      if ((eps && v->arc_dst[a] != v->final_state) || v->arc_src[a] == v->final_state ||
+          (!eps && v->arc_dst[a] == v->final_state)) {
+        ctx->err = "epsilon arcs are only supported as final weights (into a final state that is reached by nothing else "
+                   "and has no outgoing arcs)";
+        return CML_ERR_NOT_DENSE;
+      }
+    }
   const uint64_t n_pos = b->seq_off[b->n_seq];
   for (uint64_t e = 0; e < b->n_seq; ++e)
     CML_REQUIRE(b->seq_off[e] <= b->seq_off[e + 1] && b->seq_off[e + 1] - b->seq_off[e] < 0x7FFFFFFFull, CML_ERR_ARG,
                 "seq_off not monotone");
   for (uint64_t i = 0; i < n_pos; ++i) CML_REQUIRE(b->sym[i] < V, CML_ERR_ARG, "sequence symbol out of range");
+
+  // ---- which kernel: emission rows of <= 8 states -> lane-per-sequence sparse kernel; else the warp-per-sequence
+  //      dense kernel (S <= 32, no final weights)
+  std::vector<std::vector<uint32_t>> allowed(V);  // states that can emit a symbol, ascending
+  {
+    std::vector<uint64_t> mask(V, 0);
+    for (uint32_t a = 0; a < nA; ++a)
+      if (v->arc_sym[a] != CML_DENSE_EPS) mask[v->arc_sym[a]] |= 1ull << v->arc_dst[a];
+    for (uint32_t o = 0; o < V; ++o)
+      for (uint32_t j = 0; j < S; ++j)
+        if ((mask[o] >> j) & 1) allowed[o].push_back(j);
+  }
+  uint32_t kmax = 1;
+  for (auto const& al : allowed) kmax = std::max<uint32_t>(kmax, (uint32_t)al.size());
+  const bool can_dense = S <= (uint32_t)kDS && !has_phi;
+  const bool can_sparse = kmax <= 8 && S <= 63;  // (one spare state index is the zero padding state)
+  uint64_t sparse_min = 4096;
+  if (const char* e = getenv("CML_SPARSE_MIN_SEQ")) sparse_min = (uint64_t)atoll(e);
+  const bool sparse = can_sparse && (!can_dense || (b->n_seq >= sparse_min && 4 * kmax <= S));
+  if (!sparse && !can_dense) {
+    ctx->err = "no dense-state kernel for this shape (more than 32 states or final weights, and symbols emitted by more "
+               "than 8 states)";
+    return CML_ERR_NOT_DENSE;
+  }
+  const uint32_t K = sparse ? (kmax <= 4 ? 4u : 8u) : 0u;
+  const uint32_t SP = sparse ? S + 1 : (uint32_t)kDS;  // sparse: row stride of T; index S is the zero padding state
 
   // ---- factorisation: chain(a) = A(i,j) + B(j,o) as multisets of parameter ids --------------------------------
   auto chain_of = [&](uint32_t a) {
@@ -410,9 +802,17 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
     std::sort(c.begin(), c.end());
     return c;
   };
-  const uint32_t nT = kDS * kDS, nE = V * kDS, n_cells = nT + nE;
-  auto tcell = [&](uint32_t a) { return v->arc_src[a] * kDS + v->arc_dst[a]; };
-  auto ecell = [&](uint32_t a) { return nT + v->arc_sym[a] * kDS + v->arc_dst[a]; };
+  const uint32_t nT = (SP * SP + 3u) & ~3u;  // (keeps the emission table 16-byte aligned behind T)
+  const uint32_t nE = sparse ? V * K : V * (uint32_t)kDS, nF = sparse ? SP : 0, n_cells = nT + nE + nF;
+  auto is_eps = [&](uint32_t a) { return v->arc_sym[a] == CML_DENSE_EPS; };
+  auto tcell = [&](uint32_t a) { return v->arc_src[a] * SP + v->arc_dst[a]; };
+  auto ecell = [&](uint32_t a) {
+    const uint32_t o = v->arc_sym[a], j = v->arc_dst[a];
+    if (!sparse) return nT + o * (uint32_t)kDS + j;
+    const auto& al = allowed[o];
+    return nT + o * K + (uint32_t)(std::lower_bound(al.begin(), al.end(), j) - al.begin());
+  };
+  auto fcell = [&](uint32_t a) { return nT + nE + v->arc_src[a]; };
   std::vector<std::vector<uint32_t>> cell_chain(n_cells);
   std::vector<unsigned char> exists(n_cells, 0);
   std::vector<std::vector<uint32_t>> chains(nA);
@@ -427,32 +827,40 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
       }
     }
   }
-  for (uint32_t a = 0; a < nA; ++a) {  // B(j,o) = intersection over the sources i
-    const uint32_t c = ecell(a);
+  uint32_t n_sym_arcs = 0;
+  for (uint32_t a = 0; a < nA; ++a) {
+    if (is_eps(a)) {  // a final weight is its own cell
+      cell_chain[fcell(a)] = chains[a];
+      exists[fcell(a)] = 1;
+      continue;
+    }
+    ++n_sym_arcs;
+    const uint32_t c = ecell(a);  // B(j,o) = intersection over the sources i
     cell_chain[c] = exists[c] ? ms_intersect(cell_chain[c], chains[a]) : chains[a];
     exists[c] = 1;
   }
   std::vector<std::vector<uint32_t>> rest(nA);
   for (uint32_t a = 0; a < nA; ++a) {  // A(i,j) = intersection over the symbols o of what B leaves
+    if (is_eps(a)) continue;
     rest[a] = ms_minus(chains[a], cell_chain[ecell(a)]);
     const uint32_t c = tcell(a);
     cell_chain[c] = exists[c] ? ms_intersect(cell_chain[c], rest[a]) : rest[a];
     exists[c] = 1;
   }
   for (uint32_t a = 0; a < nA; ++a)
-    if (rest[a] != cell_chain[tcell(a)]) {
+    if (!is_eps(a) && rest[a] != cell_chain[tcell(a)]) {
       ctx->err = "arc chains do not factor into (source,destination) x (destination,symbol) parts";
       return CML_ERR_NOT_DENSE;
     }
   {  // completeness: every (i,j) x (j,o) combination must be an arc, or the dense product would invent arcs
     std::vector<uint32_t> n_in(S, 0), n_o(S, 0);
     for (uint32_t i = 0; i < S; ++i)
-      for (uint32_t j = 0; j < S; ++j) n_in[j] += exists[i * kDS + j];
+      for (uint32_t j = 0; j < S; ++j) n_in[j] += exists[i * SP + j];
     for (uint32_t o = 0; o < V; ++o)
-      for (uint32_t j = 0; j < S; ++j) n_o[j] += exists[nT + o * kDS + j];
+      for (uint32_t j : allowed[o]) ++n_o[j];
     uint64_t tot = 0;
     for (uint32_t j = 0; j < S; ++j) tot += (uint64_t)n_in[j] * n_o[j];
-    if (tot != nA) {
+    if (tot != n_sym_arcs) {
       ctx->err = "the arc table is not the full product of its transition and emission supports";
       return CML_ERR_NOT_DENSE;
     }
@@ -479,6 +887,10 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   const bool have_prior = !ctx->h_arc_prior.empty();
   if (have_prior)
     for (uint32_t a = 0; a < nA; ++a) {
+      if (is_eps(a)) {
+        if (cell_slot[fcell(a)] != kNone) slot_prior[cell_slot[fcell(a)]] += ctx->h_arc_prior[a];
+        continue;
+      }
       if (cell_slot[tcell(a)] != kNone) slot_prior[cell_slot[tcell(a)]] += ctx->h_arc_prior[a];
       if (cell_slot[ecell(a)] != kNone) slot_prior[cell_slot[ecell(a)]] += ctx->h_arc_prior[a];
     }
@@ -492,6 +904,11 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   cudaStream_t s = ctx->stream;
   std::unique_ptr<DenseState> D(new DenseState());
   D->S = S;
+  D->SP = SP;
+  D->nT = nT;
+  D->K = K;
+  D->sparse = sparse;
+  D->has_phi = has_phi ? 1 : 0;
   D->n_sym = V;
   D->start = v->start;
   D->fin = v->final_state;
@@ -501,8 +918,6 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   D->n_t_slots = n_t_slots;
   D->n_e_slots = n_e_slots;
   const size_t rs = ctx->precision / 8;
-  std::vector<uint16_t> sym16(std::max<uint64_t>(1, n_pos));
-  for (uint64_t i = 0; i < n_pos; ++i) sym16[i] = (uint16_t)b->sym[i];
   std::vector<double> wts(std::max<uint64_t>(1, b->n_seq), 1.);
   if (b->seq_weight) std::copy(b->seq_weight, b->seq_weight + b->n_seq, wts.begin());
   CML_CUDA(D->cell_off.upload(cell_off.data(), cell_off.size(), s));
@@ -510,12 +925,76 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   CML_CUDA(D->cell_slot.upload(cell_slot.data(), cell_slot.size(), s));
   CML_CUDA(D->cell_exists.upload(exists.data(), exists.size(), s));
   CML_CUDA(D->tables.alloc((size_t)n_cells * rs));
-  CML_CUDA(D->seq_off.upload(b->seq_off, b->n_seq + 1, s));
-  CML_CUDA(D->sym.upload(sym16.data(), sym16.size(), s));
   CML_CUDA(D->seq_weight.upload(wts.data(), wts.size(), s));
   CML_CUDA(D->ex_lnp.alloc(std::max<uint64_t>(1, b->n_seq)));
-  CML_CUDA(D->alpha_g.alloc((size_t)(n_pos + b->n_seq) * kDS * rs));
-  CML_CUDA(D->exp_g.alloc((size_t)(n_pos + b->n_seq)));
+  std::vector<uint32_t> hot, e_code;
+  if (!sparse) {
+    std::vector<uint16_t> sym16(std::max<uint64_t>(1, n_pos));
+    for (uint64_t i = 0; i < n_pos; ++i) sym16[i] = (uint16_t)b->sym[i];
+    CML_CUDA(D->seq_off.upload(b->seq_off, b->n_seq + 1, s));
+    CML_CUDA(D->sym.upload(sym16.data(), sym16.size(), s));
+    CML_CUDA(D->alpha_g.alloc((size_t)(n_pos + b->n_seq) * kDS * rs));
+    CML_CUDA(D->exp_g.alloc((size_t)(n_pos + b->n_seq)));
+  } else {
+    // tiles of 32 sequences of similar length, symbols transposed
+    std::vector<uint32_t> order(b->n_seq);
+    for (uint32_t e = 0; e < b->n_seq; ++e) order[e] = e;
+    auto len_of = [&](uint32_t e) { return (uint32_t)(b->seq_off[e + 1] - b->seq_off[e]); };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return len_of(x) > len_of(y); });
+    const uint32_t n_tiles = (uint32_t)((b->n_seq + 31) / 32);
+    std::vector<SparseTile> tiles(n_tiles);
+    std::vector<uint32_t> l_len((size_t)n_tiles * 32, 0), l_seq((size_t)n_tiles * 32, 0xFFFFFFFFu);
+    std::vector<double> l_w((size_t)n_tiles * 32, 0.);
+    uint64_t sym_rows = 0, a_rows = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+      const uint32_t nmax = len_of(order[(size_t)t * 32]);
+      tiles[t].sym_base = sym_rows * 32;
+      tiles[t].row_base = a_rows;
+      tiles[t].n_max = nmax;
+      tiles[t].pad = 0;
+      sym_rows += nmax;
+      a_rows += nmax + 1;
+    }
+    std::vector<uint16_t> symt(std::max<uint64_t>(1, sym_rows * 32), 0);
+    for (uint32_t t = 0; t < n_tiles; ++t)
+      for (uint32_t l = 0; l < 32 && (size_t)t * 32 + l < b->n_seq; ++l) {
+        const uint32_t e = order[(size_t)t * 32 + l], n = len_of(e);
+        l_len[(size_t)t * 32 + l] = n;
+        l_seq[(size_t)t * 32 + l] = e;
+        l_w[(size_t)t * 32 + l] = wts[e];
+        for (uint32_t k = 0; k < n; ++k) symt[tiles[t].sym_base + (size_t)k * 32 + l] = (uint16_t)b->sym[b->seq_off[e] + k];
+      }
+    D->n_tiles = n_tiles;
+    CML_CUDA(D->stile.upload(tiles.data(), tiles.size(), s));
+    CML_CUDA(D->sym.upload(symt.data(), symt.size(), s));
+    CML_CUDA(D->lane_len.upload(l_len.data(), l_len.size(), s));
+    CML_CUDA(D->lane_seq.upload(l_seq.data(), l_seq.size(), s));
+    CML_CUDA(D->lane_weight.upload(l_w.data(), l_w.size(), s));
+    CML_CUDA(D->alpha_g.alloc(std::max<uint64_t>(1, a_rows) * K * 32 * rs));
+    CML_CUDA(D->exp_g.alloc(std::max<uint64_t>(1, a_rows) * 32));
+    // emission rows: state ids, count-slot codes (hot slots replicated: CountSink)
+    std::vector<unsigned char> e_state((size_t)V * K, (unsigned char)(SP - 1));  // padding -> the zero state
+    for (uint32_t o = 0; o < V; ++o)
+      for (size_t c = 0; c < allowed[o].size(); ++c) e_state[(size_t)o * K + c] = (unsigned char)allowed[o][c];
+    std::vector<uint64_t> sym_occ(V, 0), slot_occ(n_slots, 0);
+    for (uint64_t i = 0; i < n_pos; ++i) ++sym_occ[b->sym[i]];
+    for (uint32_t o = 0; o < V; ++o)
+      for (uint32_t c = 0; c < K; ++c)
+        if (cell_slot[nT + o * K + c] != kNone) slot_occ[cell_slot[nT + o * K + c]] += sym_occ[o];
+    std::vector<uint32_t> hot_index(n_slots, kNone);
+    for (uint32_t sl = 0; sl < n_slots; ++sl)
+      if (slot_occ[sl] >= 4096) {
+        hot_index[sl] = (uint32_t)hot.size();
+        hot.push_back(sl);
+      }
+    e_code.assign((size_t)V * K, kNone);
+    for (size_t c = 0; c < e_code.size(); ++c) {
+      const uint32_t sl = cell_slot[nT + c];
+      if (sl != kNone) e_code[c] = hot_index[sl] != kNone ? (cmlk::kSlotHot | hot_index[sl]) : sl;
+    }
+    CML_CUDA(D->e_state.upload(e_state.data(), e_state.size(), s));
+    CML_CUDA(D->e_code.upload(e_code.data(), e_code.size(), s));
+  }
   // the M-step's view of the count slots
   CML_CUDA(ctx->slot_off.upload(slot_off.data(), slot_off.size(), s));
   CML_CUDA(ctx->slot_param.upload(slot_param.data(), slot_param.size(), s));
@@ -525,10 +1004,13 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   ctx->reduce = ctx->reduce_own.p;
   ctx->reduce_n = (uint64_t)n_slots + 3;
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
+  ctx->n_hot = (uint32_t)hot.size();
+  CML_CUDA(ctx->hot_slot.upload(hot.data(), hot.size(), s));
+  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * cmlk::kHotCopies)));
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->n_slots = n_slots;
   ctx->slots_are_arcs = false;
-  ctx->n_hot = 0;
+  ctx->hot_dirty = false;
   ctx->slot_occ.assign(n_slots, 0);
   ctx->dense = std::move(D);
   return CML_OK;
@@ -542,5 +1024,13 @@ extern "C" int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positi
   if (n_positions) *n_positions = D ? D->n_pos : 0;
   if (n_t_slots) *n_t_slots = D ? D->n_t_slots : 0;
   if (n_e_slots) *n_e_slots = D ? D->n_e_slots : 0;
+  return CML_OK;
+}
+
+extern "C" int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k) {
+  if (!ctx) return CML_ERR_ARG;
+  const DenseState* D = ctx->dense.get();
+  if (sparse) *sparse = D ? (D->sparse ? 1 : 0) : -1;
+  if (k) *k = D ? D->K : 0;
   return CML_OK;
 }

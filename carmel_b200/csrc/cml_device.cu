@@ -165,6 +165,8 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   std::vector<uint32_t> goff, gmem, toff, tmem;
   build_csr(m->n_groups, pg, goff, gmem);
   build_csr(m->n_ties, tie_key, toff, tmem);
+  ctx->max_group_size = 0;
+  for (uint32_t g = 0; g < m->n_groups; ++g) ctx->max_group_size = std::max(ctx->max_group_size, goff[g + 1] - goff[g]);
 
   // Count slots.  The expected count of an arc is only ever used through the UNLOCKED parameters of
   // its chain (cascade.h:286-325 distribute_counts skips locked arcs), so arcs whose chains have the
@@ -1414,9 +1416,14 @@ static int run_normalize(cml_ctx* ctx) {  // u -> ln_w
   using namespace cmlk;
   cudaStream_t s = ctx->stream;
   if (ctx->n_groups) {
-    k_norm_sums<<<cdiv((uint64_t)ctx->n_groups * 32, 256), 256, 0, s>>>(
-        ctx->n_groups, ctx->group_off.p, ctx->group_members.p, ctx->have_add ? ctx->group_add.p : nullptr,
-        ctx->param_tie.p, ctx->u.p, ctx->gsum.p, ctx->glocked.p);
+    // a warp per group, or a block per group when some group is large (its members are summed serially per thread)
+    const bool big = ctx->max_group_size > 512;
+    const unsigned grid = big ? ctx->n_groups : cdiv((uint64_t)ctx->n_groups * 32, 256);
+    auto sums = big ? k_norm_sums<256> : k_norm_sums<32>;
+    auto assign = big ? k_norm_assign<256> : k_norm_assign<32>;
+    sums<<<grid, 256, 0, s>>>(ctx->n_groups, ctx->group_off.p, ctx->group_members.p,
+                              ctx->have_add ? ctx->group_add.p : nullptr, ctx->param_tie.p, ctx->u.p, ctx->gsum.p,
+                              ctx->glocked.p);
     ++ctx->launches;
     if (ctx->n_ties) {
       k_tie_totals<<<cdiv((uint64_t)ctx->n_ties * 32, 256), 256, 0, s>>>(
@@ -1424,9 +1431,8 @@ static int run_normalize(cml_ctx* ctx) {  // u -> ln_w
           ctx->tie_arc.p, ctx->tie_state.p, ctx->tie_maxl.p);
       ++ctx->launches;
     }
-    k_norm_assign<<<cdiv((uint64_t)ctx->n_groups * 32, 256), 256, 0, s>>>(
-        ctx->n_groups, ctx->group_off.p, ctx->group_members.p, ctx->param_tie.p, ctx->u.p, ctx->tie_arc.p,
-        ctx->tie_state.p, ctx->tie_maxl.p, ctx->ln_w.p);
+    assign<<<grid, 256, 0, s>>>(ctx->n_groups, ctx->group_off.p, ctx->group_members.p, ctx->param_tie.p, ctx->u.p,
+                                ctx->tie_arc.p, ctx->tie_state.p, ctx->tie_maxl.p, ctx->ln_w.p);
     ++ctx->launches;
   }
   k_copy_ungrouped<<<cdiv(ctx->n_params, 256), 256, 0, s>>>(ctx->n_params, ctx->param_group.p, ctx->u.p, ctx->ln_w.p);
@@ -1484,7 +1490,7 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
   static const char* const syms[] = {
       "cml_version", "cml_create", "cml_destroy", "cml_last_error", "cml_set_stream", "cml_synchronize",
       "cml_launch_count", "cml_set_option", "cml_set_model", "cml_set_params", "cml_get_params", "cml_snapshot_params",
-      "cml_restore_params", "cml_add_sequences", "cml_dense_stats", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
+      "cml_restore_params", "cml_add_sequences", "cml_dense_stats", "cml_dense_kernel", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
       "cml_lane_stats", "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
       "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",

@@ -114,29 +114,49 @@ static __global__ void k_unnorm(uint32_t n_params, const double* __restrict__ ac
   u[p] = keep ? w : (acc[p] > 0 ? log(acc[p]) : -CUDART_INF);
 }
 
-// normalize pass 1 (fst.cc:115-133): one warp per normalisation group.  Adds the group's additive
+// log-sum-exp / max over the TPG threads that share one normalisation group (TPG = 32: a warp; TPG = 256: the block)
+template <int TPG>
+__device__ __forceinline__ double group_lse(double v, double* sh) {
+  v = warp_lse(v);
+  if (TPG == 32) return v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // (sh may still be read from a previous call)
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = -CUDART_INF;
+#pragma unroll
+  for (int k = 0; k < TPG / 32; ++k) r = lse2(r, sh[k]);
+  return r;
+}
+
+// normalize pass 1 (fst.cc:115-133): TPG threads per normalisation group (a warp, or a whole block when some group
+// has thousands of members: a lexicon's conditional group of one frequent tag).  Adds the group's additive
 // prior to EVERY member (the reference adds it to locked arcs' stored weight too), then sums.
-static __global__ void k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+template <int TPG>
+static __global__ void __launch_bounds__(256) k_norm_sums(uint32_t n_groups, const uint32_t* __restrict__ group_off,
                             const uint32_t* __restrict__ group_members, const double* __restrict__ group_add,
                             const uint32_t* __restrict__ param_tie, double* __restrict__ u,
                             double* __restrict__ gsum, double* __restrict__ glocked) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
-  const double addc = group_add ? group_add[g] : -CUDART_INF;
+  __shared__ double sh[8];
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / TPG;
+  const int t = threadIdx.x % TPG;
+  const bool live = g < n_groups;  // (TPG == 256: block-uniform)
+  if (TPG == 32 && !live) return;
+  const double addc = (live && group_add) ? group_add[g] : -CUDART_INF;
   double s = -CUDART_INF, l = -CUDART_INF;
-  for (uint32_t k = group_off[g] + lane, e = group_off[g + 1]; k < e; k += 32) {
-    const uint32_t p = group_members[k];
-    const double v = lse2(u[p], addc);
-    u[p] = v;
-    if (param_tie[p] == CML_LOCKED_GROUP)
-      l = lse2(l, v);
-    else
-      s = lse2(s, v);
-  }
-  s = warp_lse(s);
-  l = warp_lse(l);
-  if (lane == 0) {
+  if (live)
+    for (uint32_t k = group_off[g] + t, e = group_off[g + 1]; k < e; k += TPG) {
+      const uint32_t p = group_members[k];
+      const double v = lse2(u[p], addc);
+      u[p] = v;
+      if (param_tie[p] == CML_LOCKED_GROUP)
+        l = lse2(l, v);
+      else
+        s = lse2(s, v);
+    }
+  s = group_lse<TPG>(s, sh);
+  l = group_lse<TPG>(l, sh);
+  if (live && t == 0) {
     gsum[g] = s;
     glocked[g] = l;
   }
@@ -170,18 +190,21 @@ static __global__ void k_tie_totals(uint32_t n_ties, const uint32_t* __restrict_
   }
 }
 
-// normalize pass 2 (fst.cc:160-229): one warp per group; writes the new ln weights.
-static __global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ group_off,
+// normalize pass 2 (fst.cc:160-229): TPG threads per group; writes the new ln weights.
+template <int TPG>
+static __global__ void __launch_bounds__(256) k_norm_assign(uint32_t n_groups, const uint32_t* __restrict__ group_off,
                               const uint32_t* __restrict__ group_members, const uint32_t* __restrict__ param_tie,
                               const double* __restrict__ u, const double* __restrict__ tie_arc_total,
                               const double* __restrict__ tie_state_total, const double* __restrict__ tie_max_locked,
                               double* __restrict__ ln_w) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= n_groups) return;
+  __shared__ double sh[8];
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / TPG;
+  const int t = threadIdx.x % TPG;
+  const bool live = g < n_groups;
+  if (TPG == 32 && !live) return;
   double normal_sum = -CUDART_INF, reserved = -CUDART_INF;
-  const uint32_t k0 = group_off[g], k1 = group_off[g + 1];
-  for (uint32_t k = k0 + lane; k < k1; k += 32) {
+  const uint32_t k0 = live ? group_off[g] : 0, k1 = live ? group_off[g + 1] : 0;
+  for (uint32_t k = k0 + t; k < k1; k += TPG) {
     const uint32_t p = group_members[k];
     const uint32_t tie = param_tie[p];
     if (tie == CML_NO_GROUP) {
@@ -190,13 +213,13 @@ static __global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restri
       reserved = lse2(reserved, u[p]);
       ln_w[p] = u[p];
     } else {
-      const uint32_t t = tie - 1;
-      double groupNorm = tie_state_total[t];
-      const double gmax = tie_max_locked[t];
+      const uint32_t ti = tie - 1;
+      double groupNorm = tie_state_total[ti];
+      const double gmax = tie_max_locked[ti];
       double nw = -CUDART_INF;
       if (!(gmax > 0.)) {
         if (gmax > -CUDART_INF) groupNorm -= lsub(0., gmax);
-        const double groupTotal = tie_arc_total[t];
+        const double groupTotal = tie_arc_total[ti];
         if (groupTotal > -CUDART_INF) {
           nw = groupTotal - groupNorm;
           reserved = lse2(reserved, nw);
@@ -205,11 +228,11 @@ static __global__ void k_norm_assign(uint32_t n_groups, const uint32_t* __restri
       ln_w[p] = nw;
     }
   }
-  normal_sum = warp_lse(normal_sum);
-  reserved = warp_lse(reserved);
+  normal_sum = group_lse<TPG>(normal_sum, sh);
+  reserved = group_lse<TPG>(reserved, sh);
   const double fraction_remain = lsub(0., reserved);
   const bool give = (fraction_remain > -CUDART_INF) && (normal_sum > -CUDART_INF);
-  for (uint32_t k = k0 + lane; k < k1; k += 32) {
+  for (uint32_t k = k0 + t; k < k1; k += TPG) {
     const uint32_t p = group_members[k];
     if (param_tie[p] == CML_NO_GROUP) ln_w[p] = give ? fraction_remain + u[p] - normal_sum : -CUDART_INF;
   }

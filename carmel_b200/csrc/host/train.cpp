@@ -101,27 +101,36 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
   const uint32_t S = x->num_states();
   std::unordered_map<uint32_t, uint32_t> sym_id;
   std::vector<uint32_t> a_src, a_dst, a_sym;
+  const uint32_t fin = x->final_state;
+  uint64_t phi_mask = 0;  // states with an epsilon arc into the final state (final weights)
   for (uint32_t s = 0; s < S; ++s)
     for (Arc const& a : x->states[s]) {
       const uint32_t sy = tape ? a.out : a.in;
-      auto it = sym_id.find(sy);
-      if (it == sym_id.end()) it = sym_id.emplace(sy, (uint32_t)sym_id.size()).first;
+      uint32_t id = CML_DENSE_EPS;
+      if (sy != kEps) {
+        auto it = sym_id.find(sy);
+        if (it == sym_id.end()) it = sym_id.emplace(sy, (uint32_t)sym_id.size()).first;
+        id = it->second;
+      } else
+        phi_mask |= 1ull << s;
       a_src.push_back(s);
       a_dst.push_back(a.dest);
-      a_sym.push_back(it->second);
+      a_sym.push_back(id);
     }
   const uint32_t V = (uint32_t)sym_id.size();
   if (V == 0 || V > 65535) return false;
-  std::vector<uint32_t> adj((size_t)V * S, 0), radj((size_t)V * S, 0);  // [symbol][state] -> successor / predecessor masks
+  std::vector<uint64_t> adj((size_t)V * S, 0), radj((size_t)V * S, 0);  // [symbol][state] -> successor / predecessor masks
   for (size_t a = 0; a < a_src.size(); ++a) {
-    adj[(size_t)a_sym[a] * S + a_src[a]] |= 1u << a_dst[a];
-    radj[(size_t)a_sym[a] * S + a_dst[a]] |= 1u << a_src[a];
+    if (a_sym[a] == CML_DENSE_EPS) continue;
+    adj[(size_t)a_sym[a] * S + a_src[a]] |= 1ull << a_dst[a];
+    radj[(size_t)a_sym[a] * S + a_dst[a]] |= 1ull << a_src[a];
   }
-  const uint32_t fin = x->final_state;
+  const uint64_t goal_mask = phi_mask ? phi_mask : (1ull << fin);  // lattice states of the last position that reach the goal
   std::vector<uint64_t> seq_off{0};
   std::vector<uint32_t> syms;
   std::vector<double> wts;
-  std::vector<uint32_t> fwd, cur;
+  std::vector<uint64_t> fwd;
+  std::vector<uint32_t> cur;
   uint64_t n_states = 0, n_arcs = 0;
   for (uint32_t e = 0; e < local.examples.size(); ++e) {
     std::vector<uint32_t> const& str = tape ? local.examples[e].out : local.examples[e].in;
@@ -136,43 +145,47 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
     bool alive = known;
     if (alive) {
       fwd.assign(n + 1, 0);
-      fwd[0] = 1u;
+      fwd[0] = 1ull;
       for (size_t t = 0; t < n; ++t) {
-        uint32_t m = fwd[t], nx = 0;
-        const uint32_t* row = &adj[(size_t)cur[t] * S];
+        uint64_t m = fwd[t], nx = 0;
+        const uint64_t* row = &adj[(size_t)cur[t] * S];
         while (m) {
-          const int i = __builtin_ctz(m);
+          const int i = __builtin_ctzll(m);
           m &= m - 1;
           nx |= row[i];
         }
         fwd[t + 1] = nx;
       }
-      alive = (fwd[n] >> fin) & 1u;
+      alive = (fwd[n] & goal_mask) != 0;
     }
     if (!alive) {
       dropped.push_back(e);
       continue;
     }
     // co-reachability; live_t = fwd_t & bwd_t, arcs between consecutive live sets
-    uint32_t live_next = 1u << fin;
-    uint64_t st = 1, ar = 0;
+    uint64_t live_next = fwd[n] & goal_mask;
+    uint64_t st = __builtin_popcountll(live_next), ar = 0;
+    if (phi_mask) {  // the epsilon arcs of the last position and the final state itself
+      ar += st;
+      st += 1;
+    }
     for (size_t t = n; t-- > 0;) {
-      uint32_t m = live_next, pv = 0;
-      const uint32_t* rrow = &radj[(size_t)cur[t] * S];
+      uint64_t m = live_next, pv = 0;
+      const uint64_t* rrow = &radj[(size_t)cur[t] * S];
       while (m) {
-        const int j = __builtin_ctz(m);
+        const int j = __builtin_ctzll(m);
         m &= m - 1;
         pv |= rrow[j];
       }
-      const uint32_t live = pv & fwd[t];
-      const uint32_t* row = &adj[(size_t)cur[t] * S];
+      const uint64_t live = pv & fwd[t];
+      const uint64_t* row = &adj[(size_t)cur[t] * S];
       m = live;
       while (m) {
-        const int i = __builtin_ctz(m);
+        const int i = __builtin_ctzll(m);
         m &= m - 1;
-        ar += __builtin_popcount(row[i] & live_next);
+        ar += __builtin_popcountll(row[i] & live_next);
       }
-      st += __builtin_popcount(live);
+      st += __builtin_popcountll(live);
       live_next = live;
     }
     n_states += st;
@@ -203,11 +216,16 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
     return false;
   }
   ok(rc);
-  uint32_t nt = 0, ne = 0;
+  uint32_t nt = 0, ne = 0, kk = 0;
+  int sparse = 0;
   ok(cml_dense_stats(ctx, nullptr, nullptr, &nt, &ne));
-  if (!opt.quiet && !flags[(unsigned)'q'])
+  ok(cml_dense_kernel(ctx, &sparse, &kk));
+  if (!opt.quiet && !flags[(unsigned)'q']) {
     std::cerr << "dense-state path: " << S << " states x " << V << " symbols, " << nt << " trainable transition cells, "
-              << ne << " trainable emission cells\n";
+              << ne << " trainable emission cells";
+    if (sparse) std::cerr << " (sparse emission rows of " << kk << ", one sequence per lane)";
+    std::cerr << "\n";
+  }
   res.trellis_arcs = n_arcs;
   res.trellis_states = n_states;
   res.examples = wts.size();
@@ -294,12 +312,14 @@ void TrainJob::prepare() {
   // decision is made on the WHOLE corpus and the model, so every rank of a sharded run takes the same path.
   int dense_tape = -1;  // 0: symbols on the input tape, 1: on the output tape
   if (opt.dense >= 0 && opt.space == CML_SPACE_SCALED && opt.max_iter != 0 && opt.dump_trellis_file.empty() &&
-      x->num_states() <= 32) {
+      x->num_states() <= 64) {
+    // every arc consumes one symbol of one tape; *e*:*e* arcs are candidates for final weights (the library checks)
     bool in_only = true, out_only = true;
     for (auto const& st : x->states)
       for (Arc const& a : st) {
-        in_only = in_only && a.in != kEps && a.out == kEps;
-        out_only = out_only && a.out != kEps && a.in == kEps;
+        const bool eps = a.in == kEps && a.out == kEps;
+        in_only = in_only && (eps || (a.in != kEps && a.out == kEps));
+        out_only = out_only && (eps || (a.out != kEps && a.in == kEps));
       }
     for (Example const& ex : corpus.examples) {
       in_only = in_only && ex.out.empty();

@@ -164,10 +164,15 @@ int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_
  * column of the observed symbol (each position step of a batch of sequences is a dense [batch x S] * [S x S]
  * product).  Expected counts are accumulated per T cell (xi) and per E cell (gamma) and handed to the same
  * M-step; likelihoods and learned weights equal the lattice path's (unreachable / dead lattice states carry
- * alpha = 0 or beta = 0).  Needs a CML_SPACE_SCALED context, n_states <= 32, no lattices resident.
+ * alpha = 0 or beta = 0).  Needs a CML_SPACE_SCALED context and no lattices resident.  Two kernels:
+ *   dense   one warp per sequence, all n_states <= 32 states live at every position (cipher: 27 x 27 per letter)
+ *   sparse  one lane per sequence, every symbol emitted by <= 8 states, n_states <= 64, optional final weights
+ *           (HMM tagging: a word has a handful of tags); chosen for batches of >= 4096 sequences.
  * After success the count slots (cml_count_slots, cml_get_counts, the reduce buffer) are the trainable T / E
  * cells and stay so until the next cml_set_model; per-arc counts are not available.
  * Returns CML_ERR_NOT_DENSE (context unchanged) when the arc table does not factor. */
+#define CML_DENSE_EPS 0xFFFFFFFFu /* arc_sym of an arc that consumes nothing: allowed only as a FINAL WEIGHT, i.e. into a
+                                     final state that nothing else reaches and that has no outgoing arcs (tagging.fsa) */
 typedef struct cml_dense_view {
   uint32_t n_states;        /* states of the trained transducer */
   uint32_t n_symbols;       /* observed alphabet: sequence symbols are ids in [0, n_symbols) */
@@ -183,6 +188,8 @@ typedef struct cml_sequence_batch {
   const double* seq_weight; /* [n_seq] example weight */
 } cml_sequence_batch;
 int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b);
+/* which kernel the resident sequences use: *sparse = 1 sparse-emission, 0 dense, -1 none; *k = emission row width */
+int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k);
 /* resident dense sequences: count, positions (sum of lengths), and whether T cells are trainable (xi kept) */
 int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positions, uint32_t* n_t_slots, uint32_t* n_e_slots);
 

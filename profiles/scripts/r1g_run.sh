@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests/test_sparse_gpu.py -x -q 2>&1 | tail -5) > gpurun_out/r1g_tests.log
+timeout 300 python bench.py --workload hmm --no-sparse-leg > gpurun_out/r1g_bench_hmm.json 2> gpurun_out/r1g_bench_hmm.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fb_sparse --launch-skip 3 --launch-count 1 -f -o gpurun_out/r1g_hmm_sparse python bench.py --workload hmm --steps 1 --warmup 3 --no-sparse-leg > gpurun_out/r1g_ncu_hmm.log 2>&1
+cat gpurun_out/r1g_tests.log; head -c 1800 gpurun_out/r1g_bench_hmm.json; tail -3 gpurun_out/r1g_bench_hmm.err
