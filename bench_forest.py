@@ -193,9 +193,10 @@ def run(a, rank, world, local):
         bytes_step = 16.0 * tot_local["nodes"] + 8.0 * tot_local["links"]
         lay = F.layout_stats()
         if lay["tile_forests"]:
-            # thread-per-forest tiles: one u32 op per step in each pass, the label twice, inside[] and gamma[] written once
-            # (their re-reads are L1/L2 hits by construction of the post-order); padding is not counted
-            bytes_step = 4.0 * lay["steps"] + (8.0 + 2.0 * (a.precision // 8)) * tot_local["nodes"]
+            # thread-per-forest tiles: one u32 word per node header and per link in each pass (rule ids ride in the
+            # headers), inside[] and gamma[] written once (tree children / tree parents are read back from the
+            # per-lane shared-memory stacks, the rest are L1/L2 hits by post-order locality); padding is not counted
+            bytes_step = 4.0 * lay["steps"] + 2.0 * (a.precision // 8) * tot_local["nodes"]
         kms = sum(m for m, _ in k_ms) / len(k_ms)
         achieved = bytes_step / (kms / 1e3) / 1e9
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))

@@ -198,21 +198,32 @@ __global__ void __launch_bounds__(kCtaThreads) k_forest_cta(ForestArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // Thread-per-forest kernel (the throughput path for corpora of many small forests).
 //
-// 32 forests of similar size form a tile, one forest per lane of a warp; every array of the tile is stored
-// transposed ([row][lane]) so that the warp's loads of its 32 sequential streams coalesce into one 128-byte
-// line per row.  Nodes are numbered in DFS post-order (children before parents, the root last), and the two
-// passes are flattened into streams of one-link "steps":
-//   inside  ops: child index | FIRST (first step of a node: load its label, start the product / sum)
-//                            | LAST  (store inside[node], advance)          -- leaves take one step with no child
-//   outside ops: parent index | OR flag | FIRST | LAST, nodes in reverse post-order (the root first, one step)
-// so all lanes run the same trip count (steps of the largest forest of the tile; the rest is padded with NOPs)
-// with no synchronisation at all.  inside[] / gamma[] of the tile live in HBM/L2, transposed like the rest:
-// the values a lane reads were written by the same lane a few rows earlier (post-order locality).
+// 32 forests of similar size form a tile, one forest per lane of a warp; the two passes are flattened into
+// streams of 32-bit words stored transposed ([row][lane]), so the warp's loads of its 32 sequential streams
+// coalesce into one 128-byte line per row.  Nodes are numbered in DFS post-order (children before parents, the
+// root last).  Per node a HEADER word (rule id, flags), then one word per link:
+//   inside  stream: children;  a tree child (defined inside its parent) was completed just before and sits on
+//                   top of the lane's VALUE STACK in shared memory: POP.  Only children reached through a back
+//                   reference (shared sub-forests) are read from the global inside[] array.
+//   outside stream: nodes in reverse post-order (= a pre-order walk), parents;  the tree parent is an ancestor on
+//                   the current root-to-node path and sits in the lane's PATH STACK (gamma, inside) at depth-1:
+//                   TREE.  Only the other parents of a shared node are read from the global gamma[] / inside[].
+// (profiles/r1i_k_forest_thread_f32.txt: with every value read from global memory the kernel ran at 21 warps per SM
+// with 31 cycles of long-scoreboard stall per issue -- one dependent, uncoalesced load per link.)
+// Streams are prefetched three 8-row chunks ahead; the rule weight of a header two chunks ahead.  All lanes run the
+// same trip count (rows of the largest forest of the tile; the rest is NOP padding) with no synchronisation.
+// A forest whose text order is not a proper tree walk, or whose stacks would be deeper than the caps, simply
+// carries no POP / TREE / PUSH flags and reads everything from global memory.
 // ---------------------------------------------------------------------------------------------------
-const uint32_t kOpFirst = 0x80000000u, kOpLast = 0x40000000u, kOpOr = 0x20000000u, kOpIdx = 0x1fffffffu, kOpNop = 0xffffffffu;
+const uint32_t kOpNop = 0xffffffffu;
+const uint32_t kHdr = 0x80000000u, kOpLast = 0x40000000u;
+const uint32_t kHdrPush = 0x20000000u, kHdrDepthShift = 23, kHdrHot = 1u << 22, kHdrLabel = (1u << 22) - 1;
+const uint32_t kLinkPop = 0x20000000u, kLinkIdxIn = 0x1fffffffu;                       // inside links
+const uint32_t kLinkOr = 0x20000000u, kLinkTree = 0x10000000u, kLinkIdxOut = 0x0fffffffu;  // outside links
+const int kStackCap = 64, kDepthCap = 63, kTileU = 8, kTileAhead = 4;  // rows per chunk; chunk buffers (three chunks of stream in flight)
 struct __align__(16) TileDesc {
   uint64_t ops_in_base, ops_out_base, row_base;  // element offsets (already multiplied by 32) into t_ops_in / t_ops_out / rows
-  uint32_t steps_in, steps_out;
+  uint32_t steps_in, steps_out;                  // multiples of kTileU
   uint32_t n_nodes[32];
   uint32_t forest[32];  // forest number within the batch, 0xffffffff = empty lane
 };
@@ -221,7 +232,6 @@ struct TileArgs {
   uint32_t n_tiles;
   const uint32_t* ops_in;
   const uint32_t* ops_out;
-  const uint32_t* label;  // [row][lane]
   void* in_;              // Real [row][lane]
   void* ga;
   const void* lnw;
@@ -230,6 +240,7 @@ struct TileArgs {
   double* hot;
   uint32_t n_hot;
   double* ln_inside;
+  uint32_t stack_rows;    // shared-memory rows per lane: >= value-stack depth and >= 2 * (path depth + 1), even
 };
 template <typename Real>
 __device__ __forceinline__ Real ln_add_fast(Real a, Real b);
@@ -248,13 +259,17 @@ __device__ __forceinline__ float ln_add_fast<float>(float a, float b) {  // same
 const int kTileWarps = 4;
 template <typename Real>
 __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t t = blockIdx.x * kTileWarps + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char smem_ft[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * kTileWarps + wib;
   if (t >= A.n_tiles) return;
+  // per-lane columns: value stack (inside pass), then reused as the gamma / inside path stacks (outside pass)
+  Real* stk = reinterpret_cast<Real*>(smem_ft) + (size_t)wib * A.stack_rows * 32 + lane;
+  Real* gstk = stk;
+  Real* istk = stk + (size_t)(A.stack_rows / 2) * 32;
   const TileDesc* __restrict__ T = A.tiles + t;
   const uint32_t* __restrict__ oi = A.ops_in + T->ops_in_base + lane;
   const uint32_t* __restrict__ oo = A.ops_out + T->ops_out_base + lane;
-  const uint32_t* __restrict__ lab_ = A.label + T->row_base + lane;
   Real* __restrict__ in_ = (Real*)A.in_ + T->row_base + lane;
   Real* __restrict__ ga = (Real*)A.ga + T->row_base + lane;
   const Real* __restrict__ lnw = (const Real*)A.lnw;
@@ -262,72 +277,161 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
   const uint32_t n = T->n_nodes[lane];
   const uint32_t fidx = T->forest[lane];
   const uint32_t replica = t & (kHotCopies - 1);
+  auto hdr_weight = [&](uint32_t op) -> Real {  // rule weight of a header word (0 = OR / not a header: unused)
+    const uint32_t lab = op & kHdrLabel;
+    return ((op & kHdr) && op != kOpNop && lab) ? __ldg(&lnw[lab]) : NI;
+  };
   // ---- inside
-  uint32_t jn = 0;
+  uint32_t jn = 0, sp = 0;
   Real v = NI;
-  bool isand = false;
-  const uint32_t si = T->steps_in;
-  uint32_t op = si ? __ldg(oi) : kOpNop;
-  for (uint32_t s = 0; s < si; ++s) {
-    const uint32_t nop = s + 1 < si ? __ldg(oi + (size_t)(s + 1) * 32) : kOpNop;  // next step's op: independent of the values
-    if (op != kOpNop) {
-      if (op & kOpFirst) {
-        const uint32_t lab = __ldg(lab_ + (size_t)jn * 32) & ~kHotBit;
-        isand = lab != 0;
-        v = isand ? __ldg(&lnw[lab]) : NI;
+  bool isand = false, push = false;
+  {
+    // the stream is prefetched three 8-row chunks ahead, the rule weights of its headers two chunks ahead.
+    // (Four buffers used round robin without register moves were SLOWER: 32 inlined copies of the row body thrash
+    // the instruction cache -- profiles/r1l: 3.5 cycles of no-instruction stall per issue.)
+    const uint32_t si = T->steps_in;  // multiple of kTileU
+    uint32_t a0[kTileU], a1[kTileU], a2[kTileU], a3[kTileU];
+    Real wa[kTileU], wb[kTileU], wc[kTileU];
+    auto load = [&](uint32_t (&a)[kTileU], uint32_t row) {
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) a[k] = __ldg(oi + (size_t)(row + k) * 32);
+    };
+    auto weights = [&](const uint32_t (&a)[kTileU], Real (&w)[kTileU]) {
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) w[k] = hdr_weight(a[k]);
+    };
+    auto process = [&](const uint32_t (&a)[kTileU], const Real (&w)[kTileU]) {
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) {
+        const uint32_t op = a[k];
+        if (op == kOpNop) continue;
+        if (op & kHdr) {
+          isand = (op & kHdrLabel) != 0;
+          push = (op & kHdrPush) != 0;
+          v = w[k];
+        } else {
+          Real x;
+          if (op & kLinkPop)
+            x = stk[(size_t)(--sp) * 32];
+          else
+            x = in_[(size_t)(op & kLinkIdxIn) * 32];
+          v = isand ? v + x : ln_add_fast<Real>(v, x);
+        }
+        if (op & kOpLast) {
+          in_[(size_t)jn * 32] = v;
+          if (push) stk[(size_t)(sp++) * 32] = v;
+          ++jn;
+        }
       }
-      const uint32_t c = op & kOpIdx;
-      if (c != kOpIdx) {
-        const Real x = in_[(size_t)c * 32];
-        v = isand ? v + x : ln_add_fast<Real>(v, x);
-      }
-      if (op & kOpLast) {
-        in_[(size_t)jn * 32] = v;
-        ++jn;
+    };
+    load(a0, 0);
+    load(a1, kTileU);
+    load(a2, 2 * kTileU);
+    weights(a0, wa);
+    weights(a1, wb);
+    for (uint32_t s = 0; s < si; s += kTileU) {
+      load(a3, s + 3 * kTileU);  // (padded tail)
+      weights(a2, wc);
+      process(a0, wa);
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) {
+        a0[k] = a1[k];
+        a1[k] = a2[k];
+        a2[k] = a3[k];
+        wa[k] = wb[k];
+        wb[k] = wc[k];
       }
     }
-    op = nop;
   }
   if (fidx == 0xffffffffu) return;
   const Real in_root = v;  // the root is the last node of the post-order
   A.ln_inside[fidx] = (double)in_root;
-  const bool live = in_root > NI;  // zero-probability forests collect no counts (forest.hpp:447-451)
+  if (!(in_root > NI)) return;  // zero-probability forests collect no counts (forest.hpp:447-451)
   // ---- outside as posteriors: reverse post-order
-  jn = n - 1;
-  Real g = 0, in_i = NI;
-  const uint32_t so = T->steps_out;
-  op = so ? __ldg(oo) : kOpNop;
-  for (uint32_t s = 0; s < so; ++s) {
-    const uint32_t nop = s + 1 < so ? __ldg(oo + (size_t)(s + 1) * 32) : kOpNop;
-    if (op != kOpNop && live) {
-      if (op & kOpFirst) {
-        g = 0;
-        in_i = in_[(size_t)jn * 32];
-      }
-      const uint32_t p = op & kOpIdx;
-      if (p == kOpIdx)
-        g = 1;  // the root
-      else {
-        const Real gp = ga[(size_t)p * 32];
-        if (op & kOpOr) {
-          if (in_i > NI && gp > 0) g += gp * FNum<Real>::ex(in_i - in_[(size_t)p * 32]);
-        } else
-          g += gp;
-      }
-      if (op & kOpLast) {
-        ga[(size_t)jn * 32] = g;
-        const uint32_t lab = __ldg(lab_ + (size_t)jn * 32);
-        if ((lab & ~kHotBit) && g > 0) {
-          if (lab & kHotBit)
-            atomicAdd(A.hot + (size_t)replica * A.n_hot + __ldg(&A.hot_index[lab & ~kHotBit]), (double)g);
-          else
-            atomicAdd(A.counts + lab, (double)g);
+  {
+    jn = n - 1;
+    Real g = 0;
+    uint32_t hdr = 0;
+    Real in_i = in_[(size_t)jn * 32];
+    Real in_n1 = n >= 2 ? in_[(size_t)(jn - 1) * 32] : NI;  // inside of the next two nodes, prefetched
+    Real in_n2 = n >= 3 ? in_[(size_t)(jn - 2) * 32] : NI;
+    const uint32_t so = T->steps_out;  // multiple of kTileU
+    uint32_t hidx = 0;
+    uint32_t a0[kTileU], a1[kTileU], a2[kTileU], a3[kTileU];
+    auto load = [&](uint32_t (&a)[kTileU], uint32_t row) {
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) a[k] = __ldg(oo + (size_t)(row + k) * 32);
+    };
+    auto process = [&](const uint32_t (&a)[kTileU]) {
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) {
+        const uint32_t op = a[k];
+        if (op == kOpNop) continue;
+        if (op & kHdr) {
+          hdr = op;
+          g = (op & kOpLast) ? Real(1) : Real(0);  // a header that is also LAST has no parents: the root
+          if (op & kHdrHot) hidx = __ldg(&A.hot_index[op & kHdrLabel]);  // (ready by the time the node is complete)
+        } else {
+          Real gp, inp;
+          if (op & kLinkTree) {
+            const uint32_t d = ((hdr >> kHdrDepthShift) & 63u) - 1u;
+            gp = gstk[(size_t)d * 32];
+            inp = istk[(size_t)d * 32];
+          } else {
+            const uint32_t p = op & kLinkIdxOut;
+            gp = ga[(size_t)p * 32];
+            inp = (op & kLinkOr) ? in_[(size_t)p * 32] : Real(0);
+          }
+          if (op & kLinkOr) {
+            if (in_i > NI && gp > 0) g += gp * FNum<Real>::ex(in_i - inp);
+          } else
+            g += gp;
         }
-        --jn;
+        if (op & kOpLast) {
+          if (hdr & kHdrPush) {  // an internal node: its children will ask for it
+            const uint32_t d = (hdr >> kHdrDepthShift) & 63u;
+            gstk[(size_t)d * 32] = g;
+            istk[(size_t)d * 32] = in_i;
+            ga[(size_t)jn * 32] = g;
+          }
+          const uint32_t lab = hdr & kHdrLabel;
+          if (lab && g > 0) {
+            if (hdr & kHdrHot)
+              atomicAdd(A.hot + (size_t)replica * A.n_hot + hidx, (double)g);
+            else
+              atomicAdd(A.counts + lab, (double)g);
+          }
+          --jn;
+          in_i = in_n1;
+          in_n1 = in_n2;
+          in_n2 = (jn >= 2 && jn != 0xffffffffu) ? in_[(size_t)(jn - 2) * 32] : NI;
+        }
+      }
+    };
+    load(a0, 0);
+    load(a1, kTileU);
+    load(a2, 2 * kTileU);
+    for (uint32_t s = 0; s < so; s += kTileU) {
+      load(a3, s + 3 * kTileU);  // (padded tail)
+      process(a0);
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) {
+        a0[k] = a1[k];
+        a1[k] = a2[k];
+        a2[k] = a3[k];
       }
     }
-    op = nop;
   }
+}
+
+// mark hot rules in the headers of the outside streams (bit 22); idempotent
+__global__ void k_forest_mark_hot_ops(uint64_t n, uint32_t* __restrict__ ops, const uint32_t* __restrict__ hot_index) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t op = ops[i];
+  if (op == kOpNop || !(op & kHdr)) return;
+  const uint32_t lab = op & kHdrLabel;
+  ops[i] = (lab && hot_index[lab] != 0xFFFFFFFFu) ? (op | kHdrHot) : (op & ~kHdrHot);
 }
 
 // mark hot rules in the node labels (bit 31); idempotent
@@ -512,7 +616,8 @@ struct ForestBatch {
   uint32_t n_tiles = 0;
   uint64_t t_forests = 0, t_steps = 0, t_rows = 0;  // forests in tiles; real (unpadded) steps; padded rows * 32
   DevArray<TileDesc> tiles;
-  DevArray<uint32_t> t_ops_in, t_ops_out, t_label;
+  DevArray<uint32_t> t_ops_in, t_ops_out;
+  uint32_t t_stack_rows = 2;  // shared-memory rows per lane for the value / path stacks
   DevArray<unsigned char> t_in, t_ga;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_kernels = 0;
@@ -692,7 +797,7 @@ struct FlatForest {
   int error = 0;  // 1 malformed, 2 cycle, 3 rule id out of range
 };
 struct ForestScratch {
-  std::vector<uint32_t> height, order, newid, stack, it, cnt, post;
+  std::vector<uint32_t> height, order, newid, stack, it, cnt, post, tpar, depth, sim, kids;
   std::vector<char> color;
 };
 // pass 1: validate, heights, counts.  `real_of[i]` for pre-order node i = i or the target of a back reference.
@@ -836,7 +941,9 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     if (const char* e = getenv("CML_FOREST_TILE_MAX_NODES")) max_nodes = std::strtoull(e, nullptr, 10);
     uint64_t cand = 0;
     for (uint64_t i = 0; i < nf; ++i) cand += ff[i].n_real <= max_nodes;
-    const bool use = f->layout == CML_FOREST_LAYOUT_THREAD || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests);
+    const bool labels_fit = f->rulespace <= (uint64_t)kHdrLabel + 1;  // the stream headers carry 22-bit rule ids
+    const bool use = labels_fit &&
+                     (f->layout == CML_FOREST_LAYOUT_THREAD || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests));
     if (use)
       for (uint64_t i = 0; i < nf; ++i) in_tile[i] = ff[i].n_real <= max_nodes || f->layout == CML_FOREST_LAYOUT_THREAD;
   }
@@ -853,12 +960,12 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
   // tiles: 32 forests of similar step count per warp; all streams of a tile padded to its longest forest
   std::vector<uint32_t> tile_of(nf, 0);  // tile * 32 + lane
   std::vector<TileDesc> tiles;
-  std::vector<uint32_t> h_ops_in, h_ops_out, h_tlabel;
+  std::vector<uint32_t> h_ops_in, h_ops_out;
   {
     std::vector<uint32_t> tl;
     for (uint64_t i = 0; i < nf; ++i)
       if (in_tile[i]) tl.push_back((uint32_t)i);
-    auto steps_in = [&](uint32_t i) { return ff[i].n_links + ff[i].n_leaves; };
+    auto steps_in = [&](uint32_t i) { return ff[i].n_links + ff[i].n_real; };  // one header per node + one word per link
     std::stable_sort(tl.begin(), tl.end(), [&](uint32_t a, uint32_t x) { return steps_in(a) > steps_in(x); });
     tiles.resize((tl.size() + 31) / 32);
     uint64_t in_base = 0, out_base = 0, row_base = 0;
@@ -873,10 +980,12 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
         const uint32_t i = tl[k];
         tile_of[i] = (uint32_t)k;
         si = std::max<uint64_t>(si, steps_in(i));
-        so = std::max<uint64_t>(so, ff[i].n_links + 1);
+        so = std::max<uint64_t>(so, steps_in(i));
         rows = std::max<uint64_t>(rows, ff[i].n_real);
-        bt->t_steps += steps_in(i) + ff[i].n_links + 1;
+        bt->t_steps += 2 * (uint64_t)steps_in(i);
       }
+      si = (si + kTileU - 1) / kTileU * kTileU;
+      so = (so + kTileU - 1) / kTileU * kTileU;
       T.ops_in_base = in_base;
       T.ops_out_base = out_base;
       T.row_base = row_base;
@@ -889,10 +998,11 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     bt->n_tiles = (uint32_t)tiles.size();
     bt->t_forests = tl.size();
     bt->t_rows = row_base;
-    h_ops_in.assign(in_base, kOpNop);
-    h_ops_out.assign(out_base, kOpNop);
-    h_tlabel.assign(row_base, 0u);
+    h_ops_in.assign(in_base + (size_t)kTileAhead * kTileU * 32, kOpNop);  // + the prefetch tail
+    h_ops_out.assign(out_base + (size_t)kTileAhead * kTileU * 32, kOpNop);
   }
+  const bool no_stack = getenv("CML_FOREST_NO_STACK") != nullptr;  // tests / profiling: every value from global memory
+  std::atomic<uint32_t> tile_stack_rows(2);  // shared-memory rows per lane the tile kernel needs (value / path stacks)
   std::vector<std::vector<uint64_t>> occ_parts(nt);
   {
     std::atomic<uint64_t> nextf(0);
@@ -921,45 +1031,91 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
             for (uint32_t j = 0; j < nr; ++j) S.newid[S.post[j]] = j;
             uint32_t* oi = h_ops_in.data() + T.ops_in_base + l;
             uint32_t* oo = h_ops_out.data() + T.ops_out_base + l;
-            uint32_t* lb = h_tlabel.data() + T.row_base + l;
+            // tree parent (the node a child is DEFINED in) and depth along tree parents; pre-order: parents first
+            S.tpar.assign(n, 0xffffffffu);
+            S.depth.assign(n, 0);
+            uint32_t max_depth = 0;
+            for (uint32_t p = 0; p < n; ++p) {
+              if (backref[p]) continue;
+              if (S.tpar[p] != 0xffffffffu) S.depth[p] = S.depth[S.tpar[p]] + 1;
+              max_depth = std::max(max_depth, S.depth[p]);
+              for (uint32_t q = p + 1; q < next[p]; q = next[q])
+                if (!backref[q]) S.tpar[q] = p;
+            }
+            // stack mode: the post-order must be a proper walk of the tree children (simulate the value stack)
+            bool stack_ok = max_depth <= (uint32_t)kDepthCap && !no_stack;
+            uint32_t max_sp = 0;
+            if (stack_ok) {
+              S.sim.clear();
+              for (uint32_t j = 0; j < nr && stack_ok; ++j) {
+                const uint32_t p = S.post[j];
+                S.kids.clear();
+                for (uint32_t q = p + 1; q < next[p]; q = next[q])
+                  if (!backref[q]) S.kids.push_back(q);
+                for (size_t k = S.kids.size(); k-- > 0 && stack_ok;) {
+                  if (S.sim.empty() || S.sim.back() != S.kids[k])
+                    stack_ok = false;
+                  else
+                    S.sim.pop_back();
+                }
+                S.sim.push_back(p);
+                max_sp = std::max<uint32_t>(max_sp, (uint32_t)S.sim.size());
+              }
+              if (max_sp > (uint32_t)kStackCap) stack_ok = false;
+            }
+            if (stack_ok) {
+              uint32_t need = std::max(max_sp, 2 * (max_depth + 1));
+              need += need & 1;
+              uint32_t cur = tile_stack_rows.load();
+              while (cur < need && !tile_stack_rows.compare_exchange_weak(cur, need)) {
+              }
+            }
             S.cnt.assign(nr + 1, 0);  // parent in-degrees -> offsets
             uint32_t s = 0;
             for (uint32_t j = 0; j < nr; ++j) {
               const uint32_t p = S.post[j];
-              lb[(size_t)j * 32] = label[p];
               if (label[p]) ++occ[label[p]];
-              if (next[p] == p + 1) {
-                oi[(size_t)s++ * 32] = kOpFirst | kOpLast | kOpIdx;
-                continue;
-              }
-              bool first = true;
+              const bool leaf = next[p] == p + 1;
+              oi[(size_t)s++ * 32] = kHdr | (leaf ? kOpLast : 0u) | (stack_ok ? kHdrPush : 0u) | label[p];
+              if (leaf) continue;
+              // links: children behind back references first (global reads), then the tree children, last defined
+              // first (they are popped off the value stack)
+              S.kids.clear();
+              uint32_t n_links = 0;
               for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
-                const uint32_t c = S.newid[backref[q] ? label[q] : q];
-                ++S.cnt[c + 1];
-                oi[(size_t)s++ * 32] = c | (first ? kOpFirst : 0u) | (next[q] >= next[p] ? kOpLast : 0u);
-                first = false;
+                ++n_links;
+                ++S.cnt[S.newid[backref[q] ? label[q] : q] + 1];
+                if (!backref[q] && stack_ok) S.kids.push_back(q);
               }
+              uint32_t done = 0;
+              for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+                if (!backref[q] && stack_ok) continue;
+                const uint32_t c = S.newid[backref[q] ? label[q] : q];
+                oi[(size_t)s++ * 32] = c | (++done == n_links ? kOpLast : 0u);
+              }
+              for (size_t k = S.kids.size(); k-- > 0;)
+                oi[(size_t)s++ * 32] = kLinkPop | (++done == n_links ? kOpLast : 0u);
             }
             for (uint32_t j = 0; j < nr; ++j) S.cnt[j + 1] += S.cnt[j];
             S.order.assign(S.cnt[nr] ? S.cnt[nr] : 1, 0);
             S.it.assign(nr, 0);
             for (uint32_t j = 0; j < nr; ++j) {  // parents in increasing post-order position => deterministic sums
               const uint32_t p = S.post[j];
-              const uint32_t flag = label[p] ? 0u : kOpOr;
+              const uint32_t flag = label[p] ? 0u : kLinkOr;
               for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
                 const uint32_t c = S.newid[backref[q] ? label[q] : q];
-                S.order[S.cnt[c] + S.it[c]++] = j | flag;
+                const uint32_t tree = (!backref[q] && stack_ok) ? kLinkTree : 0u;
+                S.order[S.cnt[c] + S.it[c]++] = j | flag | tree;
               }
             }
             s = 0;
             for (uint32_t j = nr; j-- > 0;) {
+              const uint32_t p = S.post[j];
               const uint32_t k0 = S.cnt[j], k1 = S.cnt[j + 1];
-              if (k0 == k1) {
-                oo[(size_t)s++ * 32] = kOpFirst | kOpLast | kOpIdx;  // the root
-                continue;
-              }
-              for (uint32_t k = k0; k < k1; ++k)
-                oo[(size_t)s++ * 32] = S.order[k] | (k == k0 ? kOpFirst : 0u) | (k + 1 == k1 ? kOpLast : 0u);
+              const bool internal = next[p] != p + 1;
+              oo[(size_t)s++ * 32] = kHdr | (k0 == k1 ? kOpLast : 0u) | (internal ? kHdrPush : 0u) |
+                                     ((stack_ok ? S.depth[p] : 0u) << kHdrDepthShift) | label[p];
+              for (uint32_t k = k0; k < k1; ++k) oo[(size_t)s++ * 32] = S.order[k] | (k + 1 == k1 ? kOpLast : 0u);
             }
             continue;
           }
@@ -1065,7 +1221,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     CML_CUDA(bt->tiles.upload(tiles.data(), tiles.size(), f->stream));
     CML_CUDA(bt->t_ops_in.upload(h_ops_in.data(), h_ops_in.size(), f->stream));
     CML_CUDA(bt->t_ops_out.upload(h_ops_out.data(), h_ops_out.size(), f->stream));
-    CML_CUDA(bt->t_label.upload(h_tlabel.data(), h_tlabel.size(), f->stream));
+    bt->t_stack_rows = tile_stack_rows.load();
     CML_CUDA(bt->t_in.alloc(bt->t_rows * real_b));
     CML_CUDA(bt->t_ga.alloc(bt->t_rows * real_b));
   }
@@ -1117,7 +1273,8 @@ static int forest_rebuild_hot(cml_forests* f) {
     k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
     ++f->launches;
     if (bt->n_tiles) {
-      k_forest_mark_hot<<<f_cdiv(bt->t_label.n, 256), 256, 0, f->stream>>>(bt->t_label.n, bt->t_label.p, f->hot_index.p);
+      k_forest_mark_hot_ops<<<f_cdiv(bt->t_ops_out.n, 256), 256, 0, f->stream>>>(bt->t_ops_out.n, bt->t_ops_out.p,
+                                                                               f->hot_index.p);
       ++f->launches;
     }
   }
@@ -1151,7 +1308,6 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     T.n_tiles = bt.n_tiles;
     T.ops_in = bt.t_ops_in.p;
     T.ops_out = bt.t_ops_out.p;
-    T.label = bt.t_label.p;
     T.in_ = bt.t_in.p;
     T.ga = bt.t_ga.p;
     T.lnw = f->w_real.p;
@@ -1160,7 +1316,11 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     T.hot = f->hot.p;
     T.n_hot = f->n_hot;
     T.ln_inside = bt.ln_inside.p;
-    k_forest_thread<Real><<<f_cdiv(bt.n_tiles, kTileWarps), kTileWarps * 32, 0, f->stream>>>(T);
+    T.stack_rows = bt.t_stack_rows;
+    const size_t tsmem = (size_t)kTileWarps * bt.t_stack_rows * 32 * sizeof(Real);
+    if (tsmem > 48 * 1024)
+      CML_CUDA(cudaFuncSetAttribute(k_forest_thread<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    k_forest_thread<Real><<<f_cdiv(bt.n_tiles, kTileWarps), kTileWarps * 32, tsmem, f->stream>>>(T);
     ++f->launches;
     ++bt.n_kernels;
   }

@@ -105,6 +105,29 @@ def test_random_forests(fem, forest_oracle_bin, tmp_path, seed, mode, rel):
 
 
 @pytest.mark.parametrize("mode,rel", MODES)
+def test_random_forests_thread_layout_without_stacks(fem, forest_oracle_bin, tmp_path, monkeypatch, mode, rel):
+    """the thread-per-forest kernel reads tree children / tree parents from per-lane shared-memory stacks; with
+    CML_FOREST_NO_STACK every value comes from the global arrays (the path forests in non-tree text order take)"""
+    monkeypatch.setenv("CML_FOREST_NO_STACK", "1")
+    f, n = _random_corpus(tmp_path, 311, n_forests=150, n_rules=50, depth=6)
+    _compare(fem, forest_oracle_bin, tmp_path, ["-f", f, "-n", n, "-i", "5", "-u"], mode, rel, check_index=False,
+             layouts=("thread",))
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
+def test_deep_random_forests_thread_layout(fem, forest_oracle_bin, tmp_path, mode, rel):
+    """deeper forests with many shared sub-forests: value stack and path stack several levels deep, back-reference
+    links mixed with stack links"""
+    rng = np.random.default_rng(912)
+    d = str(tmp_path)
+    n_rules = 80
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules, depth=8, share=0.3) for _ in range(64)) + "\n")
+    open(f"{d}/n", "w").write(random_normgroups(rng, n_rules))
+    _compare(fem, forest_oracle_bin, tmp_path, ["-f", f"{d}/f", "-n", f"{d}/n", "-i", "4", "-u"], mode, rel,
+             check_index=False, layouts=("thread",))
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
 def test_zero_probability_forests(fem, forest_oracle_bin, tmp_path, mode, rel):
     d = str(tmp_path)
     # rule 5 is in no normalization group => weight 0 => forests 3 and 5 have no derivation with non-zero probability
