@@ -103,29 +103,68 @@ def run(a, rank, world, local):
     d = tempfile.mkdtemp(prefix=f"cb200_gibbs_{rank}_")
     w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104 + rank)
     stream = torch.cuda.Stream()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    no_dense = bool(getattr(a, "no_dense", False))
+
+    def timed(fn, steps, flush=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        if not flush:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record()
+                for _ in range(steps):
+                    fn()
+                e1.record()
+            torch.cuda.synchronize()
+            total = e0.elapsed_time(e1)
+        else:  # working set fits in L2: flush it between steps, every step has its own event pair
+            for _ in range(steps):
+                with torch.cuda.stream(stream):
+                    flush_buf.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                torch.cuda.synchronize()
+                total += e0.elapsed_time(e1)
+        ms = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # the same corpus on the lattice sampler (k_gibbs_batched), for the record beside the dense-state sampler
+    lattice_leg = None
+    if not no_dense:
+        job0 = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", "--no-dense", "--priors=0,1e-2",
+                       "--seed=1", *w["argv"][1:]])
+        ctx0 = job0.prepare()
+        ctx0.set_stream(stream.cuda_stream)
+        k0 = [0]
+
+        def step0():
+            ctx0.gibbs_sweep(1, k0[0], seed=1, power=1.0, accumulate_dt=1.0)
+            k0[0] += 1
+
+        for _ in range(a.warmup):
+            step0()
+        n0 = max(2, min(a.steps, 5))
+        ms0 = timed(step0, n0)
+        lattice_leg = {"value": world * job0.stats()["examples"] * n0 / (ms0 / 1e3), "unit": UNIT, "ms_per_step": ms0 / n0,
+                       "note": "same corpus with --no-dense: k_gibbs_batched walks the materialised lattices"}
+        job0.close()
+
     t_build = time.time()
-    job = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", "--priors=0,1e-2", "--seed=1", *w["argv"][1:]])
+    job = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", *(["--no-dense"] if no_dense else []),
+                  "--priors=0,1e-2", "--seed=1", *w["argv"][1:]])
     ctx = job.prepare()
     ctx.set_stream(stream.cuda_stream)
     t_build = time.time() - t_build
     info = job.stats()
     blocks, arcs, states = info["examples"], info["trellis_arcs"], info["trellis_states"]
-
-    def timed(fn, steps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record()
-            for _ in range(steps):
-                fn()
-            e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    is_dense = bool(info.get("dense", 0))
 
     sweep = [0]
 
@@ -139,7 +178,7 @@ def run(a, rank, world, local):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    ms = timed(step, a.steps)
+    ms = timed(step, a.steps, flush=is_dense)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * blocks * a.steps / (ms / 1e3)
@@ -155,7 +194,7 @@ def run(a, rank, world, local):
         ctx.gibbs_get_samples_ptr(h_len.data_ptr(), h_arcs.data_ptr(), cap)
 
     e2e_step()
-    ms_e2e = timed(e2e_step, a.steps)
+    ms_e2e = timed(e2e_step, a.steps, flush=is_dense)
     e2e = {"value": world * blocks * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0,
            "d2h_bytes_per_step": 4 * (blocks + cap), "ms_per_step": ms_e2e / a.steps,
            "lattices": f"resident; one-time host build + upload took {t_build:.2f}s on this rank"}
@@ -166,12 +205,31 @@ def run(a, rank, world, local):
         peaks, which = measured_peaks()
         # per sample one backward sweep over the block's lattice (8 B/arc record + the state scores written and
         # read once) + the sampled path (16 B per visited state)
-        bytes_step = 8.0 * arcs + 2.0 * 8 * states + 16.0 * 51 * blocks
-        achieved = bytes_step / (ms / a.steps / 1e3) / 1e9
+        lattice_bytes = 8.0 * arcs + 2.0 * 8 * states + 16.0 * 51 * blocks
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": which, "kernel": "k_gibbs (backward filter + forward sample per block) + k_gibbs_apply",
-                    "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks)}
+        if is_dense:
+            # dense-state sampler: per position the symbol (twice), one beta row of 32 doubles written and read, the
+            # sampled arc id; the 187 KB probability table and the own-sample tables live in L2 / shared memory
+            positions = 50.0 * blocks
+            bytes_step = positions * (2 * 2 + 2 * 32 * 8 + 4)
+            achieved = bytes_step / (ms / a.steps / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": which,
+                        "kernel": "k_gibbs_dense_table + k_gibbs_dense (dense-state backward filter + forward sample, one "
+                                  "warp per block) + k_gibbs_apply",
+                        "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks),
+                        "lattice_equivalent": {"algorithmic_bytes": lattice_bytes,
+                                               "achieved_gbs": lattice_bytes / (ms / a.steps / 1e3) / 1e9,
+                                               "frac_of_hbm_peak": lattice_bytes / (ms / a.steps / 1e3) / 1e9 / peak,
+                                               "note": "what the same samples cost as a sweep over 8-byte lattice records "
+                                                       "(SURVEY 8d); this kernel does not read them"}}
+        else:
+            bytes_step = lattice_bytes
+            achieved = bytes_step / (ms / a.steps / 1e3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": which,
+                        "kernel": "k_gibbs (backward filter + forward sample per block) + k_gibbs_apply",
+                        "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks)}
         try:
             procs = max(1, os.cpu_count() or 1)
             cpu = cpu_oracle_gibbs(w["files"], 25 * procs, procs)
@@ -183,7 +241,13 @@ def run(a, rank, world, local):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "sequential": {"value": blocks * n_seq / (ms_seq / 1e3), "unit": UNIT, "ms_per_sweep": ms_seq / n_seq,
                                "note": "exact collapsed sampler, identical derivations to the CPU oracle (tests/test_gibbs_gpu.py)"},
-                "totals": {"blocks": blocks, "trellis_arcs": arcs, "trellis_states": states}}
+                "totals": {"blocks": blocks, "trellis_arcs": arcs, "trellis_states": states},
+                "sampler": "dense-state (cml_gibbs_attach_dense)" if is_dense else "lattice"}
+        if lattice_leg is not None:
+            line["lattice_path"] = lattice_leg
+        if is_dense:
+            line["config"]["l2"] = ("dense-state working set (symbols, beta rows, probability table) fits in L2: L2 flushed "
+                                    "(256 MB write) between timed sweeps, each sweep timed with its own CUDA-event pair")
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

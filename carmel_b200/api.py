@@ -62,7 +62,8 @@ class CmlGibbsSweepOpts(C.Structure):
 class CmlJobInfo(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("examples", "trellis_states", "trellis_arcs", "n_params", "n_arcs",
                                           "corpus_pairs", "iterations")] + [("ln_best_ppx", C.c_double),
-                                                                            ("last_ln_prob", C.c_double)]
+                                                                            ("last_ln_prob", C.c_double),
+                                                                            ("dense", C.c_uint64)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)
@@ -109,6 +110,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_add_sequences.argtypes = [vp, C.POINTER(CmlDenseView), C.POINTER(CmlSequenceBatch)]
     lib.cml_dense_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _u32p, _u32p]
     lib.cml_dense_kernel.argtypes = [vp, C.POINTER(C.c_int), _u32p]
+    lib.cml_gibbs_attach_dense.argtypes = [vp, C.POINTER(CmlDenseView), C.POINTER(CmlSequenceBatch)]
     lib.cml_trellis_totals.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_get_example_layout.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u32p]
     lib.cml_estimate.argtypes = [vp, C.POINTER(CmlEstimateResult)]

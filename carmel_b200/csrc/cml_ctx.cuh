@@ -164,6 +164,13 @@ struct cml_ctx {
   std::vector<uint64_t> h_sample_base;
   uint64_t g_sample_cap = 0;
   int g_cur = 0;  // which sample buffer holds the current sample
+  // dense-state batched sampler (cml_gibbs_attach_dense)
+  bool gd_attached = false;
+  uint32_t gd_S = 0, gd_V = 0, gd_start = 0, gd_fin = 0;
+  DevArray<uint32_t> gd_arc, gd_rep;   // [(o*S+j)*32+i] internal arc id; [o*S+j] an arc that carries the (j,o) CRP parameters
+  DevArray<uint64_t> gd_seq_off;
+  DevArray<uint16_t> gd_sym;
+  DevArray<double> gd_W, gd_beta;      // per-sweep dense probability table; beta rows [(positions + sequences)][32]
 };
 
 int cml_dense_estimate_launch(cml_ctx* ctx);  // cml_dense.cu

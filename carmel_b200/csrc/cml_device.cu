@@ -1495,7 +1495,7 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
       "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",
-      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_sweep",
+      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_attach_dense", "cml_gibbs_sweep",
       "cml_gibbs_sample_capacity", "cml_gibbs_get_samples", "cml_gibbs_get_state", "cml_forests_create", "cml_forests_destroy",
       "cml_forests_last_error", "cml_forests_set_stream", "cml_forests_set_layout", "cml_forests_layout_stats",
       "cml_forests_launch_count", "cml_forests_set_rules",

@@ -381,6 +381,115 @@ __global__ void __launch_bounds__(kGibbsSeqThreads) k_gibbs_sequential(GibbsArgs
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Dense-state batched sampler (cml_gibbs_attach_dense): position-synchronous lattices are never walked.
+// One warp per block, lane = WFST state.  Backward filter in scaled linear space: beta_t[i] = sum_j W[o_t][j][i] *
+// c_t[j] * beta_{t+1}[j] with W the per-sweep dense table of arc probabilities (stored [symbol][destination][source]
+// so a lane's reads are coalesced) and c_t[j] the block's own-sample correction of the (j, o_t) parameters; the vector
+// is renormalised by a power of two every step (only ratios matter to the sampler).  Forward: from state s, lane j
+// holds (W[o_t][j][s] c_t[j] beta_{t+1}[j])^power, one warp scan turns the uniform draw into the successor state.
+// ---------------------------------------------------------------------------------------------------
+struct DenseGibbs {
+  uint32_t S, V, start, fin;
+  const uint32_t* arc;   // [(o*S+j)*32+i] internal arc id or 0xFFFFFFFF
+  const uint32_t* rep;   // [o*S+j] internal id of an arc whose adjustable parameters are those of (j,o), or 0xFFFFFFFF
+  const uint64_t* seq_off;
+  const uint16_t* sym;
+  const double* W;       // [(o*S+j)*32+i] linear probability (0 where there is no arc)
+  double* beta;          // rows of 32
+};
+__global__ void k_gibbs_dense_table(uint32_t n, const uint32_t* __restrict__ arc, const double* __restrict__ arc_lnw,
+                                    double* __restrict__ W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t a = arc[i];
+  W[i] = a == 0xFFFFFFFFu ? 0. : exp(arc_lnw[a]);
+}
+__global__ void __launch_bounds__(kGibbsWarps * 32) k_gibbs_dense(GibbsArgs A, DenseGibbs G) {
+  __shared__ double stage_all[kGibbsWarps * 32];
+  __shared__ double own_v[kGibbsWarps * 2 * kOwnCap];
+  __shared__ uint32_t own_k[kGibbsWarps * 2 * kOwnCap];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* stage = stage_all + warp * 32;
+  OwnTables T;
+  T.kp = own_k + warp * 2 * kOwnCap;
+  T.kg = T.kp + kOwnCap;
+  T.vp = own_v + warp * 2 * kOwnCap;
+  T.vg = T.vp + kOwnCap;
+  const uint32_t S = G.S;
+  for (uint32_t e = blockIdx.x * kGibbsWarps + warp; e < A.n_ex; e += gridDim.x * kGibbsWarps) {
+    const bool excl = A.au_off != nullptr && A.old_len[e] != 0;
+    if (excl) own_build(A, e, lane, T);
+    const uint64_t base = G.seq_off[e];
+    const uint32_t n = (uint32_t)(G.seq_off[e + 1] - base);
+    const uint16_t* __restrict__ sy = G.sym + base;
+    double* __restrict__ be = G.beta + (base + e) * 32 + lane;
+    auto corr = [&](uint32_t o) -> double {  // multiplicative own-sample correction of the (lane, o) parameters
+      if (!excl || (uint32_t)lane >= S) return 1.;
+      const uint32_t r = __ldg(&G.rep[o * S + lane]);
+      return r == 0xFFFFFFFFu ? 1. : exp(own_correction(A, &T, r));
+    };
+    // ---- backward filter
+    double b = (lane == (int)G.fin) ? 1. : 0.;
+    be[(size_t)n * 32] = b;
+    for (uint32_t t = n; t-- > 0;) {
+      const uint32_t o = sy[t];
+      stage[lane] = b * corr(o);
+      __syncwarp();
+      const double* __restrict__ Wo = G.W + (size_t)o * S * 32 + lane;
+      double acc0 = 0, acc1 = 0;
+      uint32_t j = 0;
+      for (; j + 1 < S; j += 2) {
+        acc0 = fma(__ldg(Wo + (size_t)j * 32), stage[j], acc0);
+        acc1 = fma(__ldg(Wo + (size_t)(j + 1) * 32), stage[j + 1], acc1);
+      }
+      if (j < S) acc0 = fma(__ldg(Wo + (size_t)j * 32), stage[j], acc0);
+      b = acc0 + acc1;
+      const int mx = __reduce_max_sync(0xffffffffu, __double2hiint(b));
+      if (mx > 0) {
+        const int ex = min(max(((mx >> 20) & 0x7ff) - 1023, -1022), 1022);
+        b *= __hiloint2double((1023 - ex) << 20, 0);
+      }
+      be[(size_t)t * 32] = b;
+      __syncwarp();
+    }
+    // ---- forward sample
+    uint32_t* out = A.new_sample + A.sample_base[e];
+    uint32_t s = G.start;
+    const uint32_t ex_index = A.desc[e].ex_index;
+    for (uint32_t t = 0; t < n; ++t) {
+      const uint32_t o = sy[t];
+      double v = 0;
+      if ((uint32_t)lane < S) v = __ldg(G.W + ((size_t)o * S + lane) * 32 + s) * corr(o) * be[(size_t)(t + 1) * 32];
+      if (A.power != 1. && v > 0) v = exp(A.power * log(v));
+      double m = v;
+      for (int k = 16; k; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+      double p = m > 0 ? v / m : 0.;
+      double sum = p;
+      for (int k = 16; k; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+      p = sum > 0 ? p / sum : 0.;
+      double cum = p;  // inclusive scan over the lanes (destination states in ascending order)
+      for (int k = 1; k < 32; k <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, cum, k);
+        if (lane >= k) cum += up;
+      }
+      const double psum = __shfl_sync(0xffffffffu, cum, 31);
+      const double choice = psum * gibbs_uniform(A.seed, A.sweep, ex_index, t);
+      const unsigned hit = __ballot_sync(0xffffffffu, p > 0 && choice - cum < 0);
+      const unsigned any = __ballot_sync(0xffffffffu, p > 0);
+      uint32_t pick = hit ? (uint32_t)(__ffs(hit) - 1) : (any ? (uint32_t)(31 - __clz(any)) : 0u);
+      if (lane == 0) {
+        const uint32_t a = __ldg(&G.arc[((size_t)o * S + pick) * 32 + s]);
+        out[t] = a == 0xFFFFFFFFu ? 0u : A.arc_orig[a];
+      }
+      s = pick;
+    }
+    if (lane == 0) A.new_len[e] = n;
+    __syncwarp();
+  }
+}
+
 // batched mode: apply (new - old) sample counts of every block
 __global__ void k_gibbs_apply(GibbsArgs A) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,6 +661,23 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
     if (ctx->g_tbl.n < (size_t)ctx->n_arcs + 1) CML_CUDA(ctx->g_tbl.alloc((size_t)ctx->n_arcs + 1));
     k_gibbs_sequential<<<1, kGibbsSeqThreads, 0, s>>>(A, ctx->g_tbl.p, ctx->n_arcs);
     ++ctx->launches;
+  } else if (ctx->gd_attached) {
+    DenseGibbs G;
+    G.S = ctx->gd_S;
+    G.V = ctx->gd_V;
+    G.start = ctx->gd_start;
+    G.fin = ctx->gd_fin;
+    G.arc = ctx->gd_arc.p;
+    G.rep = ctx->gd_rep.p;
+    G.seq_off = ctx->gd_seq_off.p;
+    G.sym = ctx->gd_sym.p;
+    G.W = ctx->gd_W.p;
+    G.beta = ctx->gd_beta.p;
+    const uint32_t nt = ctx->gd_V * ctx->gd_S * 32;
+    k_gibbs_dense_table<<<cdiv(nt, 256), 256, 0, s>>>(nt, ctx->gd_arc.p, A.arc_lnw, ctx->gd_W.p);
+    k_gibbs_dense<<<std::max(1u, std::min<unsigned>(cdiv(A.n_ex, kGibbsWarps), (unsigned)ctx->sm_count * 16u)), kGibbsWarps * 32, 0, s>>>(A, G);
+    k_gibbs_apply<<<cdiv(A.n_ex, 128), 128, 0, s>>>(A);
+    ctx->launches += 3;
   } else {
     k_gibbs_batched<<<std::max(1u, std::min<unsigned>(cdiv(A.n_ex, kGibbsWarps), (unsigned)ctx->sm_count * 16u)), kGibbsWarps * 32, 0, s>>>(A);
     k_gibbs_apply<<<cdiv(A.n_ex, 128), 128, 0, s>>>(A);
@@ -564,6 +690,82 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
   CML_CUDA(cudaGetLastError());
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->g_cur ^= 1;
+  return CML_OK;
+}
+
+
+extern "C" int cml_gibbs_attach_dense(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b) {
+  if (!ctx || !v || !b) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_gibbs, CML_ERR_STATE, "cml_gibbs_init first");
+  CML_REQUIRE(v->arc_src && v->arc_dst && v->arc_sym && b->seq_off, CML_ERR_ARG, "null array");
+  Batch& bt = *ctx->batches[0];
+  CML_REQUIRE(b->n_seq == bt.n_ex, CML_ERR_ARG, "one sequence per resident lattice, in the same order");
+  const uint32_t S = v->n_states, V = v->n_symbols, nA = ctx->n_arcs;
+  if (S > 32 || V == 0 || V > 65535) {
+    ctx->err = "dense-state sampler needs n_states <= 32";
+    return CML_ERR_NOT_DENSE;
+  }
+  CML_REQUIRE(v->start < S && v->final_state < S, CML_ERR_ARG, "start / final state out of range");
+  for (uint64_t e = 0; e < b->n_seq; ++e) {
+    const uint64_t n = b->seq_off[e + 1] - b->seq_off[e];
+    if (n + 1 != bt.h_nlevels[e]) {
+      ctx->err = "a lattice is not position-synchronous (levels != symbols + 1)";
+      return CML_ERR_NOT_DENSE;
+    }
+  }
+  const uint64_t n_pos = b->seq_off[b->n_seq];
+  for (uint64_t i = 0; i < n_pos; ++i) CML_REQUIRE(b->sym[i] < V, CML_ERR_ARG, "sequence symbol out of range");
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  // per-arc adjustable (CRP) parameters, by internal id
+  std::vector<uint32_t> au_off((size_t)nA + 2), au_param;
+  CML_CUDA(cudaMemcpyAsync(au_off.data(), ctx->g_au_off.p, au_off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  au_param.resize(au_off[nA + 1]);
+  if (!au_param.empty())
+    CML_CUDA(cudaMemcpyAsync(au_param.data(), ctx->g_au_param.p, au_param.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  std::vector<uint32_t> arc((size_t)V * S * 32, 0xFFFFFFFFu), rep((size_t)V * S, 0xFFFFFFFFu);
+  for (uint32_t a = 0; a < nA; ++a) {
+    const uint32_t i = v->arc_src[a], j = v->arc_dst[a], o = v->arc_sym[a];
+    if (i >= S || j >= S || o >= V) {
+      ctx->err = "epsilon arcs / out-of-range arc triples: no dense-state sampler";
+      return CML_ERR_NOT_DENSE;
+    }
+    uint32_t& slot = arc[((size_t)o * S + j) * 32 + i];
+    if (slot != 0xFFFFFFFFu) {
+      ctx->err = "parallel arcs with the same (source, destination, symbol)";
+      return CML_ERR_NOT_DENSE;
+    }
+    const uint32_t ia = ctx->h_perm[a];
+    slot = ia;
+    uint32_t& r = rep[(size_t)o * S + j];
+    if (r == 0xFFFFFFFFu)
+      r = ia;
+    else {  // the adjustable parameters must be a function of (destination, symbol)
+      const uint32_t n0 = au_off[r + 1] - au_off[r], n1 = au_off[ia + 1] - au_off[ia];
+      bool same = n0 == n1;
+      for (uint32_t k = 0; k < n0 && same; ++k) same = au_param[au_off[r] + k] == au_param[au_off[ia] + k];
+      if (!same) {
+        ctx->err = "an arc's CRP parameters depend on its source state: no dense-state sampler";
+        return CML_ERR_NOT_DENSE;
+      }
+    }
+  }
+  std::vector<uint16_t> sym16(std::max<uint64_t>(1, n_pos));
+  for (uint64_t i = 0; i < n_pos; ++i) sym16[i] = (uint16_t)b->sym[i];
+  CML_CUDA(ctx->gd_arc.upload(arc.data(), arc.size(), s));
+  CML_CUDA(ctx->gd_rep.upload(rep.data(), rep.size(), s));
+  CML_CUDA(ctx->gd_seq_off.upload(b->seq_off, b->n_seq + 1, s));
+  CML_CUDA(ctx->gd_sym.upload(sym16.data(), sym16.size(), s));
+  CML_CUDA(ctx->gd_W.alloc(arc.size()));
+  CML_CUDA(ctx->gd_beta.alloc((size_t)(n_pos + b->n_seq) * 32));
+  CML_CUDA(cudaStreamSynchronize(s));
+  ctx->gd_S = S;
+  ctx->gd_V = V;
+  ctx->gd_start = v->start;
+  ctx->gd_fin = v->final_state;
+  ctx->gd_attached = true;
   return CML_OK;
 }
 

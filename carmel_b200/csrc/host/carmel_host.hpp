@@ -209,7 +209,8 @@ struct TrainJob {
   double estimate(double& ln_unweighted);
   TrainResult const& run(std::ostream& log);        // EM (WFST::train)
   TrainResult const& run_gibbs(std::ostream& log);  // --crp (WFST::train_gibbs)
-  void prepare_gibbs();  // lattices + CRP parameters on the GPU, counts = priors; no sweep yet
+  void prepare_gibbs();
+  void attach_dense_sampler();  // batched --crp on position-synchronous lattices: cml_gibbs_attach_dense  // lattices + CRP parameters on the GPU, counts = priors; no sweep yet
   bool gibbs_prepared = false;
   std::vector<uint32_t> g_norm;  // CRP normalisation group of every parameter (kNoGroup = fixed probability)
   std::vector<double> g_prior;   // pseudo-count (or the fixed probability)

@@ -100,7 +100,70 @@ void TrainJob::prepare_gibbs() {
     ok(cml_get_example_layout(ctx, e, &nl, nullptr, nullptr));
     g_base[e + 1] = g_base[e] + nl;
   }
+  if (g.batched && opt.dense >= 0) attach_dense_sampler();
   gibbs_prepared = true;
+}
+
+// Batched sweeps on position-synchronous lattices (every arc consumes one symbol of one tape, the other tape of every
+// pair empty) can use the dense-state sampler: hand the library the arc triples and the strings of the resident
+// examples.  Anything else (or CML_ERR_NOT_DENSE) keeps the lattice sampler.
+void TrainJob::attach_dense_sampler() {
+  const uint32_t S = x->num_states();
+  if (S > 32 || corpus.examples.size() != res.examples) return;
+  bool in_only = true, out_only = true;
+  for (auto const& st : x->states)
+    for (Arc const& a : st) {
+      in_only = in_only && a.in != kEps && a.out == kEps;
+      out_only = out_only && a.out != kEps && a.in == kEps;
+    }
+  for (Example const& ex : corpus.examples) {
+    in_only = in_only && ex.out.empty();
+    out_only = out_only && ex.in.empty();
+  }
+  if (!in_only && !out_only) return;
+  const int tape = out_only ? 1 : 0;
+  std::unordered_map<uint32_t, uint32_t> sym_id;
+  std::vector<uint32_t> a_src, a_dst, a_sym;
+  for (uint32_t s = 0; s < S; ++s)
+    for (Arc const& a : x->states[s]) {
+      const uint32_t sy = tape ? a.out : a.in;
+      auto it = sym_id.find(sy);
+      if (it == sym_id.end()) it = sym_id.emplace(sy, (uint32_t)sym_id.size()).first;
+      a_src.push_back(s);
+      a_dst.push_back(a.dest);
+      a_sym.push_back(it->second);
+    }
+  std::vector<uint64_t> seq_off{0};
+  std::vector<uint32_t> syms;
+  for (Example const& ex : corpus.examples) {
+    for (uint32_t sy : (tape ? ex.out : ex.in)) {
+      auto it = sym_id.find(sy);
+      if (it == sym_id.end()) return;  // (cannot happen: the example has a derivation)
+      syms.push_back(it->second);
+    }
+    seq_off.push_back(syms.size());
+  }
+  cml_dense_view v{};
+  v.n_states = S;
+  v.n_symbols = (uint32_t)sym_id.size();
+  v.start = 0;
+  v.final_state = x->final_state;
+  v.arc_src = a_src.data();
+  v.arc_dst = a_dst.data();
+  v.arc_sym = a_sym.data();
+  cml_sequence_batch b{};
+  b.n_seq = corpus.examples.size();
+  b.seq_off = seq_off.data();
+  b.sym = syms.data();
+  b.seq_weight = nullptr;
+  const int rc = cml_gibbs_attach_dense(ctx, &v, &b);
+  if (rc == CML_ERR_NOT_DENSE) {
+    if (!flags[(unsigned)'q']) std::cerr << "dense-state sampler not applicable (" << cml_last_error(ctx) << "); sampling on lattices\n";
+    return;
+  }
+  ok(rc);
+  res.dense = true;
+  if (!flags[(unsigned)'q']) std::cerr << "dense-state sampler: " << S << " states x " << v.n_symbols << " symbols\n";
 }
 
 TrainResult const& TrainJob::run_gibbs(std::ostream& log) {

@@ -290,6 +290,7 @@ extern "C" int cml_job_stats(cml_job* j, cml_job_info* info) {
   info->iterations = j->job.res.history.size();
   info->ln_best_ppx = j->job.res.ln_best_ppx;
   info->last_ln_prob = j->job.res.history.empty() ? 0. : j->job.res.history.back().ln_prob;
+  info->dense = j->job.res.dense ? 1 : 0;
   return CML_OK;
 }
 extern "C" int cml_job_train(cml_job* j) {

@@ -266,6 +266,14 @@ typedef struct cml_gibbs_sweep_opts {
   double accumulate_dt;  /* after the sweep add dt * count to the time-averaged counts (delta_sum.hpp:60-84) */
 } cml_gibbs_sweep_opts;
 int cml_gibbs_init(cml_ctx* ctx, const cml_gibbs_model* g); /* counts := priors (restore_p0, gibbs.hpp:618-623) */
+/* Optional dense-state sampler for CML_GIBBS_BATCHED sweeps (after cml_gibbs_init): the same view / sequences as
+ * cml_add_sequences (n_states <= 32, no epsilon arcs), one sequence per resident lattice in the same order.  The
+ * backward filter then runs as one S x S product per position over a per-sweep dense table of arc probabilities
+ * and the forward sample picks the successor state with one warp-wide scan -- the lattices are only used by the
+ * sequential mode.  Samples have the same format (arc-table ids) and the same distribution; they are not the
+ * lattice sampler's derivations for equal uniforms (arcs are visited in destination-state order).
+ * Returns CML_ERR_NOT_DENSE (nothing changed) when an arc's CRP parameters depend on its source state. */
+int cml_gibbs_attach_dense(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b);
 int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o);
 uint64_t cml_gibbs_sample_capacity(cml_ctx* ctx);
 /* current sample: path_len[example], and the arc-table ids of example e's path at path_arcs[base_e ..],
@@ -291,6 +299,7 @@ typedef struct cml_job_info {
   uint64_t examples, trellis_states, trellis_arcs; /* resident on this GPU */
   uint64_t n_params, n_arcs, corpus_pairs, iterations;
   double ln_best_ppx, last_ln_prob;
+  uint64_t dense; /* 1: the E-step / batched sampler runs on the dense-state view (no lattice walked) */
 } cml_job_info;
 int cml_job_open(cml_job** out, int argc, const char* const* argv); /* parse, read, reduce, compose */
 void cml_job_close(cml_job* job);

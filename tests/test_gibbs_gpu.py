@@ -131,3 +131,62 @@ def test_cipher_crp_batched(cli, tmp_path):
     assert len(rows) == 27
     for k, v in rows.items():
         assert abs(v - 1) < 1e-6, (k, v)
+
+
+def _sample_histogram(native_lib, files, extra, n_draws):
+    """n_draws independent samples of every block from FIXED weights (init_from_params: the sampler ignores the counts),
+    as a histogram over the sampled arc-id tuples of block 0"""
+    import ctypes as C
+    import carmel_b200 as cb
+    job = cb.Job(["--crp", "--crp-batched", "--priors=0,1e-2", "-q", *extra, *files])
+    ctx = job.prepare()
+    st = job.stats()
+    cap = ctx.gibbs_sample_capacity()
+    lens = np.zeros(st["examples"], np.uint32)
+    arcs = np.zeros(cap, np.uint32)
+    hist = {}
+    for k in range(n_draws):
+        ctx.gibbs_sweep(1, k, seed=123, power=1.0, init_from_params=True)
+        ctx.gibbs_get_samples_ptr(lens.ctypes.data, arcs.ctypes.data, cap)
+        key = tuple(int(v) for v in arcs[:lens[0]])
+        hist[key] = hist.get(key, 0) + 1
+    dense = st["dense"]
+    job.close()
+    return hist, dense
+
+
+def test_dense_state_sampler_draws_from_the_lattice_samplers_distribution(native_lib, tmp_path):
+    """cml_gibbs_attach_dense (batched sweeps on position-synchronous lattices) samples the same posterior over
+    derivations as the lattice sampler: with fixed weights every sweep is an independent draw, so the two histograms
+    over derivations of one short block must agree (two-sample chi-square on the frequent derivations)"""
+    rng = np.random.default_rng(4)
+    LET, CIP = ["_", "A", "B", "C"], ["_", "a", "b", "c", "d"]
+    d = str(tmp_path)
+    q = lambda s_: '"' + s_ + '"'
+    lm = rng.dirichlet(np.full(4, 0.7), size=4)
+    with open(f"{d}/lm.wfsa", "w") as f:
+        f.write("_\n")
+        for a in range(4):
+            for b in range(4):
+                f.write(f"({LET[a]} ({LET[b]} *e* {q(LET[b])} {lm[a, b]:.12g}!))\n")
+    with open(f"{d}/ch.fst", "w") as f:
+        f.write("0\n")
+        for a in range(4):
+            for b in range(5):
+                f.write(f"(0 (0 {q(LET[a])} {q(CIP[b])} {rng.uniform(0.1, 1):.6g}))\n")
+    with open(f"{d}/c.data", "w") as f:
+        f.write("\n" + " ".join(q(c) for c in ["a", "c", "b", "d", "_"]) + "\n")
+        f.write("\n" + " ".join(q(c) for c in ["b", "_"]) + "\n")
+    files = [f"{d}/c.data", f"{d}/lm.wfsa", f"{d}/ch.fst"]
+    n = 6000
+    hd, dense_d = _sample_histogram(native_lib, files, [], n)
+    hl, dense_l = _sample_histogram(native_lib, files, ["--no-dense"], n)
+    assert dense_d == 1 and dense_l == 0
+    assert all(len(k) == 5 for k in hd) and all(len(k) == 5 for k in hl)
+    keys = [k for k in set(hd) | set(hl) if hd.get(k, 0) + hl.get(k, 0) >= 40]
+    assert len(keys) >= 8
+    chi2 = sum((hd.get(k, 0) - hl.get(k, 0)) ** 2 / (hd.get(k, 0) + hl.get(k, 0)) for k in keys)
+    # chi-square with len(keys)-1 degrees of freedom: mean df, sd sqrt(2 df); 6 sd is a comfortable bound
+    assert chi2 <= len(keys) + 6 * math.sqrt(2 * len(keys)), (chi2, len(keys))
+    # and the derivations themselves are the same set (no derivation one sampler can draw and the other cannot)
+    assert {k for k in hd if hd[k] >= 40} == {k for k in hl if hl[k] >= 40}
