@@ -394,12 +394,12 @@ def main():
                 res["layout"] = dense
             elif is_dense:
                 res["totals"]["positions"] = pos_total
-                S = 32  # lanes: the padded state count the kernel computes on
+                S = dense["n_states"]  # useful flops (S x S mat-vecs); the kernel computes on 32 padded lanes
                 products = 3 if dense["t_slots"] else 2  # alpha, beta (+ xi when transitions are trainable)
                 flops = 2.0 * products * S * S * dense["positions"]
                 tf32_peak = float(peaks.get("bf16_tflops", 1665.0)) / 2.0
                 ach = flops / (k_ms / 1e3) / 1e12
-                hbm_bytes = dense["positions"] * (2.0 * S * rs + 8 + 2 + 2)  # alpha row written + read, exponents, symbol twice
+                hbm_bytes = dense["positions"] * (2.0 * 32 * rs + 8 + 2 + 2)  # alpha row written + read, exponents, symbol twice
                 res["roofline"] = {
                     "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                     "traffic": None, "peak_source": f"{which} bf16 dense peak / 2 (TF32 rate; no TF32 entry in MEASURED_PEAKS.json)",

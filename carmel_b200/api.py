@@ -109,7 +109,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_clear_trellises.argtypes = [vp]
     lib.cml_add_sequences.argtypes = [vp, C.POINTER(CmlDenseView), C.POINTER(CmlSequenceBatch)]
     lib.cml_dense_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _u32p, _u32p]
-    lib.cml_dense_kernel.argtypes = [vp, C.POINTER(C.c_int), _u32p]
+    lib.cml_dense_kernel.argtypes = [vp, C.POINTER(C.c_int), _u32p, _u32p]
     lib.cml_gibbs_attach_dense.argtypes = [vp, C.POINTER(CmlDenseView), C.POINTER(CmlSequenceBatch)]
     lib.cml_trellis_totals.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_get_example_layout.argtypes = [vp, C.c_uint64, _u32p, _u32p, _u32p]
@@ -291,10 +291,10 @@ class Context:
         a, b_ = C.c_uint64(), C.c_uint64()
         c, d = C.c_uint32(), C.c_uint32()
         self._check(self.lib.cml_dense_stats(self.h, C.byref(a), C.byref(b_), C.byref(c), C.byref(d)))
-        sp, k = C.c_int(), C.c_uint32()
-        self._check(self.lib.cml_dense_kernel(self.h, C.byref(sp), C.byref(k)))
+        sp, k, ns = C.c_int(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.cml_dense_kernel(self.h, C.byref(sp), C.byref(k), C.byref(ns)))
         return dict(sequences=int(a.value), positions=int(b_.value), t_slots=int(c.value), e_slots=int(d.value),
-                    kernel={1: "sparse", 0: "dense", -1: None}[int(sp.value)], k=int(k.value))
+                    kernel={1: "sparse", 0: "dense", -1: None}[int(sp.value)], k=int(k.value), n_states=int(ns.value))
 
     def trellis_totals(self) -> dict:
         v = [C.c_uint64() for _ in range(4)]

@@ -15,6 +15,9 @@
 // reference would prune (unreachable or dead) simply carry alpha = 0 or beta = 0, so likelihoods and expected
 // counts are those of the pruned lattice.
 //
+// (A variant with a PAIR of warps per sequence -- forward and backward recurrences concurrently, counts in a
+// position-parallel pass -- was measured and dropped: 126 registers per thread cap the SM at 16 warps either way, so
+// twice the warps per sequence meant half the resident sequences: 69 us against 59 us.)
 // B200 mapping.  S <= 32: one lane per WFST state, one warp per sequence (a warp walks several sequences, a CTA
 // has 8 warps).  T lives in registers (a column per lane in the forward sweep, a row per lane in the backward
 // sweep); the state vector of the current position is exchanged through a 2 x 32 shared-memory buffer read back
@@ -1027,10 +1030,11 @@ extern "C" int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positi
   return CML_OK;
 }
 
-extern "C" int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k) {
+extern "C" int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k, uint32_t* n_states) {
   if (!ctx) return CML_ERR_ARG;
   const DenseState* D = ctx->dense.get();
   if (sparse) *sparse = D ? (D->sparse ? 1 : 0) : -1;
   if (k) *k = D ? D->K : 0;
+  if (n_states) *n_states = D ? D->S : 0;
   return CML_OK;
 }

@@ -1457,6 +1457,38 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   const bool slots_are_params = ctx->trivial && !ctx->dense;  // dense mode: slots are T / E cells with chains
+  if (rate <= 1. && ctx->n_ties == 0 && ctx->n_params <= 8192 && ctx->n_slots <= 16384 && ctx->max_group_size <= 256 &&
+      !getenv("CML_NO_FUSED_MSTEP")) {
+    // small model: the whole M-step in one launch (see k_mstep_fused)
+    MstepArgs M;
+    M.n_slots = ctx->n_slots;
+    M.n_params = ctx->n_params;
+    M.n_groups = ctx->n_groups;
+    M.slot_off = slots_are_params ? nullptr : ctx->slot_off.p;
+    M.slot_param = ctx->slot_param.p;
+    M.counts = ctx->reduce;
+    M.prior = ctx->have_prior ? ctx->slot_prior.p : nullptr;
+    M.param_tie = ctx->param_tie.p;
+    M.param_group = ctx->param_group.p;
+    M.group_off = ctx->group_off.p;
+    M.group_members = ctx->group_members.p;
+    M.group_add = ctx->have_add ? ctx->group_add.p : nullptr;
+    M.acc = ctx->acc.p;
+    M.u = ctx->u.p;
+    M.old = ctx->old.p;
+    M.ln_w = ctx->ln_w.p;
+    M.gsum = ctx->gsum.p;
+    M.glocked = ctx->glocked.p;
+    M.maxchg = ctx->maxchg.p;
+    k_mstep_fused<<<1, 1024, 0, s>>>(M);
+    ++ctx->launches;
+    CML_CUDA(cudaGetLastError());
+    unsigned long long bits = 0;
+    CML_CUDA(cudaMemcpyAsync(&bits, ctx->maxchg.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
+    CML_CUDA(cudaStreamSynchronize(s));
+    if (max_delta) std::memcpy(max_delta, &bits, sizeof(double));
+    return CML_OK;
+  }
   if (!slots_are_params) CML_CUDA(cudaMemsetAsync(ctx->acc.p, 0, ctx->n_params * sizeof(double), s));
   k_param_acc<<<cdiv(ctx->n_slots, 256), 256, 0, s>>>(ctx->n_slots, slots_are_params ? nullptr : ctx->slot_off.p,
                                                       ctx->slot_param.p, ctx->reduce,

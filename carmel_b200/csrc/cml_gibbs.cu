@@ -407,7 +407,7 @@ __global__ void k_gibbs_dense_table(uint32_t n, const uint32_t* __restrict__ arc
   W[i] = a == 0xFFFFFFFFu ? 0. : exp(arc_lnw[a]);
 }
 __global__ void __launch_bounds__(kGibbsWarps * 32) k_gibbs_dense(GibbsArgs A, DenseGibbs G) {
-  __shared__ double stage_all[kGibbsWarps * 32];
+  __shared__ __align__(16) double stage_all[kGibbsWarps * 32];
   __shared__ double own_v[kGibbsWarps * 2 * kOwnCap];
   __shared__ uint32_t own_k[kGibbsWarps * 2 * kOwnCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -432,26 +432,32 @@ __global__ void __launch_bounds__(kGibbsWarps * 32) k_gibbs_dense(GibbsArgs A, D
     };
     // ---- backward filter
     double b = (lane == (int)G.fin) ? 1. : 0.;
-    be[(size_t)n * 32] = b;
     for (uint32_t t = n; t-- > 0;) {
       const uint32_t o = sy[t];
-      stage[lane] = b * corr(o);
+      const double cb = b * corr(o);  // what the forward pass needs of position t+1: correction x beta
+      stage[lane] = cb;
+      be[(size_t)(t + 1) * 32] = cb;
       __syncwarp();
       const double* __restrict__ Wo = G.W + (size_t)o * S * 32 + lane;
-      double acc0 = 0, acc1 = 0;
+      double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
       uint32_t j = 0;
-      for (; j + 1 < S; j += 2) {
-        acc0 = fma(__ldg(Wo + (size_t)j * 32), stage[j], acc0);
-        acc1 = fma(__ldg(Wo + (size_t)(j + 1) * 32), stage[j + 1], acc1);
+      for (; j + 3 < S; j += 4) {
+        const double2 s01 = *reinterpret_cast<const double2*>(stage + j);
+        const double2 s23 = *reinterpret_cast<const double2*>(stage + j + 2);
+        acc0 = fma(__ldg(Wo + (size_t)j * 32), s01.x, acc0);
+        acc1 = fma(__ldg(Wo + (size_t)(j + 1) * 32), s01.y, acc1);
+        acc2 = fma(__ldg(Wo + (size_t)(j + 2) * 32), s23.x, acc2);
+        acc3 = fma(__ldg(Wo + (size_t)(j + 3) * 32), s23.y, acc3);
       }
-      if (j < S) acc0 = fma(__ldg(Wo + (size_t)j * 32), stage[j], acc0);
+      for (; j < S; ++j) acc0 = fma(__ldg(Wo + (size_t)j * 32), stage[j], acc0);
+      acc0 += acc2;
+      acc1 += acc3;
       b = acc0 + acc1;
       const int mx = __reduce_max_sync(0xffffffffu, __double2hiint(b));
       if (mx > 0) {
         const int ex = min(max(((mx >> 20) & 0x7ff) - 1023, -1022), 1022);
         b *= __hiloint2double((1023 - ex) << 20, 0);
       }
-      be[(size_t)t * 32] = b;
       __syncwarp();
     }
     // ---- forward sample
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(kGibbsWarps * 32) k_gibbs_dense(GibbsArgs A, D
     for (uint32_t t = 0; t < n; ++t) {
       const uint32_t o = sy[t];
       double v = 0;
-      if ((uint32_t)lane < S) v = __ldg(G.W + ((size_t)o * S + lane) * 32 + s) * corr(o) * be[(size_t)(t + 1) * 32];
+      if ((uint32_t)lane < S) v = __ldg(G.W + ((size_t)o * S + lane) * 32 + s) * be[(size_t)(t + 1) * 32];
       if (A.power != 1. && v > 0) v = exp(A.power * log(v));
       double m = v;
       for (int k = 16; k; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));

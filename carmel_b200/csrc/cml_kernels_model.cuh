@@ -272,4 +272,100 @@ static __global__ void k_max_change(uint32_t n_params, const uint32_t* __restric
   if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, (unsigned long long)__double_as_longlong(d));
 }
 
+
+// The whole M-step of a SMALL model in one launch (one CTA): K4 + prep_new_weights + normalize + max_change, the
+// phases of the kernels above separated by block barriers.  Used when there are no tie groups and the tables fit
+// one CTA's patience (a few 10^4 parameters): the EM iteration of such models is launch bound (the cipher's
+// dense-state E-step takes 57 us, six M-step launches cost 35 us more).
+struct MstepArgs {
+  uint32_t n_slots, n_params, n_groups;
+  const uint32_t* slot_off;     // NULL: slot == parameter
+  const uint32_t* slot_param;
+  const double* counts;
+  const double* prior;          // per slot or NULL
+  const uint32_t* param_tie;
+  const uint32_t* param_group;
+  const uint32_t* group_off;
+  const uint32_t* group_members;
+  const double* group_add;      // or NULL
+  double* acc;
+  double* u;
+  double* old;
+  double* ln_w;
+  double* gsum;
+  double* glocked;
+  unsigned long long* maxchg;
+};
+static __global__ void __launch_bounds__(1024) k_mstep_fused(MstepArgs A) {
+  __shared__ unsigned long long smax;
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31;
+  const uint32_t warp = tid >> 5, nw = nt >> 5;
+  if (tid == 0) smax = 0ull;
+  if (A.slot_off)
+    for (uint32_t p = tid; p < A.n_params; p += nt) A.acc[p] = 0.;
+  __syncthreads();
+  for (uint32_t a = tid; a < A.n_slots; a += nt) {  // k_param_acc
+    const double v = A.counts[a] + (A.prior ? A.prior[a] : 0.);
+    if (A.slot_off) {
+      for (uint32_t k = A.slot_off[a], e = A.slot_off[a + 1]; k < e; ++k) {
+        const uint32_t p = A.slot_param[k];
+        if (A.param_tie[p] != CML_LOCKED_GROUP && v != 0.) atomicAdd(&A.acc[p], v);
+      }
+    } else
+      A.acc[a] = v;
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < A.n_params; p += nt) {  // k_unnorm
+    const double w = A.ln_w[p];
+    A.old[p] = w;
+    const bool keep = (A.param_tie[p] == CML_LOCKED_GROUP) || (A.param_group[p] == CML_NO_GROUP);
+    A.u[p] = keep ? w : (A.acc[p] > 0 ? log(A.acc[p]) : -CUDART_INF);
+  }
+  __syncthreads();
+  for (uint32_t g = warp; g < A.n_groups; g += nw) {  // k_norm_sums + k_norm_assign (no ties), a warp per group
+    const double addc = A.group_add ? A.group_add[g] : -CUDART_INF;
+    const uint32_t k0 = A.group_off[g], k1 = A.group_off[g + 1];
+    double normal_sum = -CUDART_INF, reserved = -CUDART_INF;
+    for (uint32_t k = k0 + lane; k < k1; k += 32) {
+      const uint32_t p = A.group_members[k];
+      const double v = lse2(A.u[p], addc);
+      A.u[p] = v;
+      if (A.param_tie[p] == CML_LOCKED_GROUP) {
+        reserved = lse2(reserved, v);
+        A.ln_w[p] = v;
+      } else
+        normal_sum = lse2(normal_sum, v);
+    }
+    normal_sum = warp_lse(normal_sum);
+    reserved = warp_lse(reserved);
+    if (lane == 0) {
+      A.gsum[g] = normal_sum;
+      A.glocked[g] = reserved;
+    }
+    const double fraction_remain = lsub(0., reserved);
+    const bool give = (fraction_remain > -CUDART_INF) && (normal_sum > -CUDART_INF);
+    __syncwarp();
+    for (uint32_t k = k0 + lane; k < k1; k += 32) {
+      const uint32_t p = A.group_members[k];
+      if (A.param_tie[p] != CML_LOCKED_GROUP) A.ln_w[p] = give ? fraction_remain + A.u[p] - normal_sum : -CUDART_INF;
+    }
+  }
+  __syncthreads();
+  double d = 0;
+  for (uint32_t p = tid; p < A.n_params; p += nt) {  // k_copy_ungrouped + k_max_change
+    if (A.param_group[p] == CML_NO_GROUP) A.ln_w[p] = A.u[p];
+    if (A.param_tie[p] != CML_LOCKED_GROUP) {
+      const double a = A.ln_w[p], b = A.old[p];
+      const double hi = fmax(a, b), lo = fmin(a, b);
+      const double l = lsub(hi, lo);
+      d = fmax(d, (l > -CUDART_INF) ? exp(l) : 0.);
+    }
+  }
+  d = warp_max(d);
+  if (lane == 0 && d > 0) atomicMax(&smax, (unsigned long long)__double_as_longlong(d));
+  __syncthreads();
+  if (tid == 0) *A.maxchg = smax;
+}
+
 }  // namespace cmlk

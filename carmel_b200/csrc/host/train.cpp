@@ -219,7 +219,7 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
   uint32_t nt = 0, ne = 0, kk = 0;
   int sparse = 0;
   ok(cml_dense_stats(ctx, nullptr, nullptr, &nt, &ne));
-  ok(cml_dense_kernel(ctx, &sparse, &kk));
+  ok(cml_dense_kernel(ctx, &sparse, &kk, nullptr));
   if (!opt.quiet && !flags[(unsigned)'q']) {
     std::cerr << "dense-state path: " << S << " states x " << V << " symbols, " << nt << " trainable transition cells, "
               << ne << " trainable emission cells";

@@ -188,8 +188,9 @@ typedef struct cml_sequence_batch {
   const double* seq_weight; /* [n_seq] example weight */
 } cml_sequence_batch;
 int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b);
-/* which kernel the resident sequences use: *sparse = 1 sparse-emission, 0 dense, -1 none; *k = emission row width */
-int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k);
+/* which kernel the resident sequences use: *sparse = 1 sparse-emission, 0 dense, -1 none; *k = emission row width;
+ * *n_states = states of the dense view */
+int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k, uint32_t* n_states);
 /* resident dense sequences: count, positions (sum of lengths), and whether T cells are trainable (xi kept) */
 int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positions, uint32_t* n_t_slots, uint32_t* n_e_slots);
 

@@ -1,6 +1,7 @@
 """Parity of the lane-per-lattice E-step kernel (k_fb_lane: tiles of 32 narrow lattices, streams aligned by state
 ordinal) against the CPU oracle and against the group kernels (--no-lane) on the same inputs.  The kernel is
-normally used for batches of >= 16384 eligible lattices; the tests force it with --lane-min=1.
+normally used for batches of >= 16384 eligible lattices; the tests force it with --lane-min=1 (and --no-dense: the
+HMM cascades here also have a dense-state view, which the product would otherwise prefer).
 
 Tolerances (north_star): 1e-6 relative in fp64, 1e-4 in fp32."""
 import os
@@ -47,9 +48,10 @@ def test_lane_hmm_matches_oracle(cli, oracle_bin, tmp_path, case, mode, rel):
     args = ["--train-cascade", "-HJ", "-M", "5"]
     rc, _, oerr = run(oracle_bin, [*args, f"--history={d}/h.o", *files["o"]], timeout=600)
     assert rc == 0, oerr
-    rc, _, err = run(cli, [*args, *mode, "--lane-min=1", f"--history={d}/h.p", *files["p"]])
+    rc, _, err = run(cli, [*args, *mode, "--no-dense", "--lane-min=1", f"--history={d}/h.p", *files["p"]])
     assert rc == 0, err
-    rc, _, gerr = run(cli, [*args, *mode, "--no-lane", f"--history={d}/h.g", *files["g"]])
+    assert "dense-state path" not in err
+    rc, _, gerr = run(cli, [*args, *mode, "--no-dense", "--no-lane", f"--history={d}/h.g", *files["g"]])
     assert rc == 0, gerr
     _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), rel)
     _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.g"), rel)
@@ -65,7 +67,7 @@ def test_lane_layout_is_used_and_equals_group_estep(native_lib, tmp_path):
     w = synth.write_hmm(str(tmp_path), n_sent=200, n_tags=7, vocab=60, tags_per_word=3, seed=5, len_range=(1, 50))
     out = {}
     for name, extra in (("lane", ["--lane-min=1"]), ("group", ["--no-lane"])):
-        job = cb.Job(["--scaled", "-q", *extra, *w["argv"]])
+        job = cb.Job(["--scaled", "--no-dense", "-q", *extra, *w["argv"]])
         ctx = job.prepare()
         st = job.stats()
         ls = ctx.lane_stats()
@@ -101,7 +103,7 @@ def test_lane_random_models_match_oracle(cli, oracle_bin, tmp_path, seed):
     assert rc == 0, oerr
     if any(abs(h[1]) < 1e-6 for h in read_history(f"{tmp_path}/h.o")):
         pytest.skip("degenerate corpus (probability 1)")
-    rc, out, err = run(cli, [*args, "--scaled", "--lane-min=1", f"--history={tmp_path}/h.p", c, f])
+    rc, out, err = run(cli, [*args, "--scaled", "--no-dense", "--lane-min=1", f"--history={tmp_path}/h.p", c, f])
     assert rc == 0, err
     _close(read_history(f"{tmp_path}/h.p"), read_history(f"{tmp_path}/h.o"), 1e-6)
     compare_wfst_text(out, oout, 1e-5)
