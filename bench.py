@@ -39,6 +39,15 @@ ORACLE = os.path.join(ROOT, "oracle", "_build", "carmel_oracle")
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+def measured_traffic(kernel):
+    """dram bytes per launch of a kernel from the committed ncu captures (profiles/traffic.json), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+        return float(t["bytes"]) if t else None  # bytes per launch (source file named in profiles/traffic.json)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -380,7 +389,8 @@ def main():
                 peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
                 lattice_bytes = (16.0 + 2.0 * rs * (states_local / max(1, arcs_local))) * arcs_local
                 res["roofline"] = {
-                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": measured_traffic("k_fb_sparse") if a.workload == "hmm" and a.precision == 64 and a.scale == 1 else None,
                     "peak_source": which,
                     "kernel": "k_fb_sparse (forward + backward + counts, one sequence per lane, lattices never "
                               "materialised; 1 launch per iteration)",
@@ -402,7 +412,8 @@ def main():
                 hbm_bytes = dense["positions"] * (2.0 * 32 * rs + 8 + 2 + 2)  # alpha row written + read, exponents, symbol twice
                 res["roofline"] = {
                     "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                    "traffic": None, "peak_source": f"{which} bf16 dense peak / 2 (TF32 rate; no TF32 entry in MEASURED_PEAKS.json)",
+                    "traffic": measured_traffic("k_fb_dense") if a.workload == "cipher" and a.precision == 64 and a.scale == 1 else None,
+                    "peak_source": f"{which} bf16 dense peak / 2 (TF32 rate; no TF32 entry in MEASURED_PEAKS.json)",
                     "kernel": "k_fb_dense (forward + backward + counts over never-materialised lattices, 1 launch per iteration)",
                     "kernel_ms": k_ms, "flops_per_position": 2.0 * products * S * S, "positions_per_launch": dense["positions"],
                     "kernel_share_of_step": k_ms / (ms / a.steps),
@@ -417,7 +428,9 @@ def main():
                 achieved = bytes_per_arc * arcs_local / (k_ms / 1e3) / 1e9
                 peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
                 res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                   "traffic": None, "peak_source": which, "kernel": "k_fb_* (forward + backward + counts, "
+                                   "traffic": (measured_traffic("k_fb_lane" if a.workload == "hmm" else "k_fb_ell_cipher")
+                                               if a.precision == 64 and a.scale == 1 else None),
+                                   "peak_source": which, "kernel": "k_fb_* (forward + backward + counts, "
                                    f"{n_k} launch(es) per iteration)", "kernel_ms": k_ms,
                                    "algorithmic_bytes_per_arc": bytes_per_arc, "arcs_per_launch_set": arcs_local,
                                    "kernel_share_of_step": k_ms / (ms / a.steps)}

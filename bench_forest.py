@@ -200,7 +200,9 @@ def run(a, rank, world, local):
         kms = sum(m for m, _ in k_ms) / len(k_ms)
         achieved = bytes_step / (kms / 1e3) / 1e9
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        from bench import measured_traffic
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": measured_traffic("k_forest_thread") if lay["tile_forests"] and a.precision == 32 and a.scale == 1 else None,
                     "peak_source": which, "kernel": ("k_forest_thread" if lay["tile_forests"] else "k_forest_warp/k_forest_cta") +
                     f" (inside + outside + counts, {k_ms[0][1]} launch(es) per iteration)",
                     "kernel_ms": kms, "algorithmic_bytes_per_hyperedge": bytes_step / max(1, tot_local["hyperedges"]),

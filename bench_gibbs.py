@@ -213,8 +213,9 @@ def run(a, rank, world, local):
             positions = 50.0 * blocks
             bytes_step = positions * (2 * 2 + 2 * 32 * 8 + 4)
             achieved = bytes_step / (ms / a.steps / 1e3) / 1e9
+            from bench import measured_traffic
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": which,
+                        "traffic": measured_traffic("k_gibbs_dense") if a.scale == 1 else None, "peak_source": which,
                         "kernel": "k_gibbs_dense_table + k_gibbs_dense (dense-state backward filter + forward sample, one "
                                   "warp per block) + k_gibbs_apply",
                         "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks),
