@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kCtaThreads) k_forest_cta(ForestArgs A) {
 //                   TREE.  Only the other parents of a shared node are read from the global gamma[] / inside[].
 // (profiles/r1i_k_forest_thread_f32.txt: with every value read from global memory the kernel ran at 21 warps per SM
 // with 31 cycles of long-scoreboard stall per issue -- one dependent, uncoalesced load per link.)
-// Streams are prefetched three 8-row chunks ahead; the rule weight of a header two chunks ahead.  All lanes run the
+// Streams run through a per-warp cp.async ring in shared memory, two 8-row chunks ahead; rule weights one chunk ahead.  All lanes run the
 // same trip count (rows of the largest forest of the tile; the rest is NOP padding) with no synchronisation.
 // A forest whose text order is not a proper tree walk, or whose stacks would be deeper than the caps, simply
 // carries no POP / TREE / PUSH flags and reads everything from global memory.
@@ -218,14 +218,17 @@ __global__ void __launch_bounds__(kCtaThreads) k_forest_cta(ForestArgs A) {
 const uint32_t kOpNop = 0xffffffffu;
 const uint32_t kHdr = 0x80000000u, kOpLast = 0x40000000u;
 const uint32_t kHdrPush = 0x20000000u, kHdrDepthShift = 23, kHdrHot = 1u << 22, kHdrLabel = (1u << 22) - 1;
+const uint32_t kHdrNparShift = 22;  // inside headers only: 7 bits (depth and hot are outside-stream fields)
 const uint32_t kLinkPop = 0x20000000u, kLinkIdxIn = 0x1fffffffu;                       // inside links
 const uint32_t kLinkOr = 0x20000000u, kLinkTree = 0x10000000u, kLinkIdxOut = 0x0fffffffu;  // outside links
-const int kStackCap = 64, kDepthCap = 63, kTileU = 8, kTileAhead = 4;  // rows per chunk; chunk buffers (three chunks of stream in flight)
+const int kStackCap = 64, kDepthCap = 63, kTileU = 8, kTileStages = 3;  // rows per chunk; chunks in the cp.async ring (shared memory decides the resident warps)
+const int kTileAhead = kTileStages + 1;  // chunks of NOP padding behind the streams (prefetch runs past the end)
 struct __align__(16) TileDesc {
   uint64_t ops_in_base, ops_out_base, row_base;  // element offsets (already multiplied by 32) into t_ops_in / t_ops_out / rows
   uint32_t steps_in, steps_out;                  // multiples of kTileU
   uint32_t n_nodes[32];
   uint32_t forest[32];  // forest number within the batch, 0xffffffff = empty lane
+  uint32_t rows_out[32];  // words of the lane's outside stream (nodes + links)
 };
 struct TileArgs {
   const TileDesc* tiles;
@@ -234,6 +237,7 @@ struct TileArgs {
   const uint32_t* ops_out;
   void* in_;              // Real [row][lane]
   void* ga;
+  void* vout;             // Real [outside stream row][lane]: inside[node] at the row of the node's outside header
   const void* lnw;
   const uint32_t* hot_index;
   double* counts;
@@ -257,6 +261,18 @@ __device__ __forceinline__ float ln_add_fast<float>(float a, float b) {  // same
   return hi + __logf(1.f + __expf(d));
 }
 const int kTileWarps = 4;
+__device__ __forceinline__ void f_cp_async4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void f_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int BYTES>
+__device__ __forceinline__ void f_cp_async_n(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_dst), "l"(gsrc), "n"(BYTES) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void f_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 template <typename Real>
 __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
   extern __shared__ __align__(16) unsigned char smem_ft[];
@@ -267,6 +283,16 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
   Real* stk = reinterpret_cast<Real*>(smem_ft) + (size_t)wib * A.stack_rows * 32 + lane;
   Real* gstk = stk;
   Real* istk = stk + (size_t)(A.stack_rows / 2) * 32;
+  // the stream ring of this warp: kTileStages chunks of kTileU rows of 32 words, behind all the stacks
+  uint32_t* ring_w = reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(smem_ft) + (size_t)kTileWarps * A.stack_rows * 32) +
+                     (size_t)wib * kTileStages * kTileU * 32 + lane;
+  const uint32_t sring = (uint32_t)__cvta_generic_to_shared(ring_w);
+  // ... and the ring of inside values that travels with the outside stream (same rows)
+  Real* vring = reinterpret_cast<Real*>(reinterpret_cast<uint32_t*>(reinterpret_cast<Real*>(smem_ft) +
+                                                                      (size_t)kTileWarps * A.stack_rows * 32) +
+                                         (size_t)kTileWarps * kTileStages * kTileU * 32) +
+                (size_t)wib * kTileStages * kTileU * 32 + lane;
+  const uint32_t svring = (uint32_t)__cvta_generic_to_shared(vring);
   const TileDesc* __restrict__ T = A.tiles + t;
   const uint32_t* __restrict__ oi = A.ops_in + T->ops_in_base + lane;
   const uint32_t* __restrict__ oo = A.ops_out + T->ops_out_base + lane;
@@ -282,19 +308,30 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
     return ((op & kHdr) && op != kOpNop && lab) ? __ldg(&lnw[lab]) : NI;
   };
   // ---- inside
-  uint32_t jn = 0, sp = 0;
+  uint32_t jn = 0, sp = 0, cum = 0;
+  const uint32_t rows_out = T->rows_out[lane] & 0x7fffffffu;
+  const bool use_vout = (T->rows_out[lane] >> 31) == 0;  // (a node with > 127 parents: read inside[] directly instead)
+  Real* __restrict__ vo = (Real*)A.vout + T->ops_out_base + lane;
   Real v = NI;
   bool isand = false, push = false;
   {
-    // the stream is prefetched three 8-row chunks ahead, the rule weights of its headers two chunks ahead.
-    // (Four buffers used round robin without register moves were SLOWER: 32 inlined copies of the row body thrash
-    // the instruction cache -- profiles/r1l: 3.5 cycles of no-instruction stall per issue.)
-    const uint32_t si = T->steps_in;  // multiple of kTileU
-    uint32_t a0[kTileU], a1[kTileU], a2[kTileU], a3[kTileU];
-    Real wa[kTileU], wb[kTileU], wc[kTileU];
-    auto load = [&](uint32_t (&a)[kTileU], uint32_t row) {
+    // The stream goes through a per-warp cp.async ring in shared memory, kTileStages - 1 chunks (of 8 rows) ahead:
+    // register-staged prefetch stopped helping beyond one chunk because the loads share scoreboards and a rotating
+    // move waits for the newest one (profiles/r1k, r1l).  A lane copies and later reads only its own words, so
+    // cp.async.wait_group is all the synchronisation needed.  Rule weights of a chunk's headers are gathered one
+    // chunk before its turn, into two register sets used alternately (the loop body handles two chunks).
+    const uint32_t si = T->steps_in;  // multiple of 2 * kTileU
+    auto issue = [&](uint32_t row) {  // queue chunk `row / kTileU` of the stream (rows past the end are NOP padding)
+      const uint32_t st = (row / kTileU) % kTileStages;
 #pragma unroll
-      for (int k = 0; k < kTileU; ++k) a[k] = __ldg(oi + (size_t)(row + k) * 32);
+      for (int k = 0; k < kTileU; ++k)
+        f_cp_async4(sring + (uint32_t)((st * kTileU + k) * 32) * 4u, oi + (size_t)(row + k) * 32);
+      f_cp_async_commit();
+    };
+    auto ops_of = [&](uint32_t row, uint32_t (&a)[kTileU]) {
+      const uint32_t st = (row / kTileU) % kTileStages;
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) a[k] = ring_w[(st * kTileU + k) * 32];
     };
     auto weights = [&](const uint32_t (&a)[kTileU], Real (&w)[kTileU]) {
 #pragma unroll
@@ -308,6 +345,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
         if (op & kHdr) {
           isand = (op & kHdrLabel) != 0;
           push = (op & kHdrPush) != 0;
+          cum += 1u + ((op >> kHdrNparShift) & 127u);  // words of this node in the outside stream: header + parents
           v = w[k];
         } else {
           Real x;
@@ -319,29 +357,34 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
         }
         if (op & kOpLast) {
           in_[(size_t)jn * 32] = v;
+          // the outside pass walks the nodes backwards: leave inside[node] where its stream will pass (the row of
+          // the node's outside header), so that pass reads it through its prefetch ring and not with a dependent load
+          if (use_vout) vo[(size_t)(rows_out - cum) * 32] = v;
           if (push) stk[(size_t)(sp++) * 32] = v;
           ++jn;
         }
       }
     };
-    load(a0, 0);
-    load(a1, kTileU);
-    load(a2, 2 * kTileU);
-    weights(a0, wa);
-    weights(a1, wb);
-    for (uint32_t s = 0; s < si; s += kTileU) {
-      load(a3, s + 3 * kTileU);  // (padded tail)
-      weights(a2, wc);
-      process(a0, wa);
+    uint32_t oa[kTileU], ob[kTileU];
+    Real wa[kTileU], wb[kTileU];
 #pragma unroll
-      for (int k = 0; k < kTileU; ++k) {
-        a0[k] = a1[k];
-        a1[k] = a2[k];
-        a2[k] = a3[k];
-        wa[k] = wb[k];
-        wb[k] = wc[k];
-      }
+    for (int st = 0; st < kTileStages - 1; ++st) issue(st * kTileU);
+    f_cp_async_wait<kTileStages - 2>();  // chunk 0 has landed
+    ops_of(0, oa);
+    weights(oa, wa);
+    for (uint32_t s = 0; s < si; s += 2 * kTileU) {
+      issue(s + (kTileStages - 1) * kTileU);
+      f_cp_async_wait<kTileStages - 2>();  // chunk s/8 + 1 has landed
+      ops_of(s + kTileU, ob);
+      weights(ob, wb);
+      process(oa, wa);
+      issue(s + kTileStages * kTileU);
+      f_cp_async_wait<kTileStages - 2>();  // chunk s/8 + 2
+      ops_of(s + 2 * kTileU, oa);
+      weights(oa, wa);
+      process(ob, wb);
     }
+    f_cp_async_wait<0>();
   }
   if (fidx == 0xffffffffu) return;
   const Real in_root = v;  // the root is the last node of the post-order
@@ -352,23 +395,35 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
     jn = n - 1;
     Real g = 0;
     uint32_t hdr = 0;
-    Real in_i = in_[(size_t)jn * 32];
-    Real in_n1 = n >= 2 ? in_[(size_t)(jn - 1) * 32] : NI;  // inside of the next two nodes, prefetched
-    Real in_n2 = n >= 3 ? in_[(size_t)(jn - 2) * 32] : NI;
+    Real in_i = NI;
     const uint32_t so = T->steps_out;  // multiple of kTileU
     uint32_t hidx = 0;
-    uint32_t a0[kTileU], a1[kTileU], a2[kTileU], a3[kTileU];
-    auto load = [&](uint32_t (&a)[kTileU], uint32_t row) {
+    auto issue = [&](uint32_t row) {  // the op stream and, row for row, the inside values the inside pass left
+      const uint32_t st = (row / kTileU) % kTileStages;
 #pragma unroll
-      for (int k = 0; k < kTileU; ++k) a[k] = __ldg(oo + (size_t)(row + k) * 32);
+      for (int k = 0; k < kTileU; ++k) {
+        f_cp_async4(sring + (uint32_t)((st * kTileU + k) * 32) * 4u, oo + (size_t)(row + k) * 32);
+        f_cp_async_n<sizeof(Real)>(svring + (uint32_t)((st * kTileU + k) * 32) * (uint32_t)sizeof(Real),
+                                   vo + (size_t)(row + k) * 32);
+      }
+      f_cp_async_commit();
     };
-    auto process = [&](const uint32_t (&a)[kTileU]) {
+    auto ops_of = [&](uint32_t row, uint32_t (&a)[kTileU], Real (&val)[kTileU]) {
+      const uint32_t st = (row / kTileU) % kTileStages;
+#pragma unroll
+      for (int k = 0; k < kTileU; ++k) {
+        a[k] = ring_w[(st * kTileU + k) * 32];
+        val[k] = vring[(st * kTileU + k) * 32];
+      }
+    };
+    auto process = [&](const uint32_t (&a)[kTileU], const Real (&val)[kTileU]) {
 #pragma unroll
       for (int k = 0; k < kTileU; ++k) {
         const uint32_t op = a[k];
         if (op == kOpNop) continue;
         if (op & kHdr) {
           hdr = op;
+          in_i = use_vout ? val[k] : in_[(size_t)jn * 32];
           g = (op & kOpLast) ? Real(1) : Real(0);  // a header that is also LAST has no parents: the root
           if (op & kHdrHot) hidx = __ldg(&A.hot_index[op & kHdrLabel]);  // (ready by the time the node is complete)
         } else {
@@ -402,25 +457,20 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
               atomicAdd(A.counts + lab, (double)g);
           }
           --jn;
-          in_i = in_n1;
-          in_n1 = in_n2;
-          in_n2 = (jn >= 2 && jn != 0xffffffffu) ? in_[(size_t)(jn - 2) * 32] : NI;
         }
       }
     };
-    load(a0, 0);
-    load(a1, kTileU);
-    load(a2, 2 * kTileU);
-    for (uint32_t s = 0; s < so; s += kTileU) {
-      load(a3, s + 3 * kTileU);  // (padded tail)
-      process(a0);
+    uint32_t oa[kTileU];
+    Real va[kTileU];
 #pragma unroll
-      for (int k = 0; k < kTileU; ++k) {
-        a0[k] = a1[k];
-        a1[k] = a2[k];
-        a2[k] = a3[k];
-      }
+    for (int st = 0; st < kTileStages - 1; ++st) issue(st * kTileU);
+    for (uint32_t s = 0; s < so; s += kTileU) {
+      issue(s + (kTileStages - 1) * kTileU);   // (padded tail)
+      f_cp_async_wait<kTileStages - 1>();  // chunk s/8 has landed
+      ops_of(s, oa, va);
+      process(oa, va);
     }
+    f_cp_async_wait<0>();
   }
 }
 
@@ -618,7 +668,7 @@ struct ForestBatch {
   DevArray<TileDesc> tiles;
   DevArray<uint32_t> t_ops_in, t_ops_out;
   uint32_t t_stack_rows = 2;  // shared-memory rows per lane for the value / path stacks
-  DevArray<unsigned char> t_in, t_ga;
+  DevArray<unsigned char> t_in, t_ga, t_vout;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_kernels = 0;
   ~ForestBatch() {
@@ -797,7 +847,7 @@ struct FlatForest {
   int error = 0;  // 1 malformed, 2 cycle, 3 rule id out of range
 };
 struct ForestScratch {
-  std::vector<uint32_t> height, order, newid, stack, it, cnt, post, tpar, depth, sim, kids;
+  std::vector<uint32_t> height, order, newid, stack, it, cnt, post, tpar, depth, sim, kids, npar;
   std::vector<char> color;
 };
 // pass 1: validate, heights, counts.  `real_of[i]` for pre-order node i = i or the target of a back reference.
@@ -984,7 +1034,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
         rows = std::max<uint64_t>(rows, ff[i].n_real);
         bt->t_steps += 2 * (uint64_t)steps_in(i);
       }
-      si = (si + kTileU - 1) / kTileU * kTileU;
+      si = (si + 2 * kTileU - 1) / (2 * kTileU) * (2 * kTileU);
       so = (so + kTileU - 1) / kTileU * kTileU;
       T.ops_in_base = in_base;
       T.ops_out_base = out_base;
@@ -1026,6 +1076,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
             const uint32_t t = tile_of[fi] >> 5, l = tile_of[fi] & 31;
             TileDesc& T = tiles[t];
             T.n_nodes[l] = nr;
+            T.rows_out[l] = fx.n_links + nr;
             T.forest[l] = (uint32_t)fi;
             S.newid.assign(n, 0);
             for (uint32_t j = 0; j < nr; ++j) S.newid[S.post[j]] = j;
@@ -1070,13 +1121,24 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
               while (cur < need && !tile_stack_rows.compare_exchange_weak(cur, need)) {
               }
             }
+            // parents per node: the inside header carries the count (7 bits) so the inside pass knows where the
+            // node's header sits in the OUTSIDE stream (it leaves inside[node] there for the outside pass's prefetch)
+            S.npar.assign(nr, 0);
+            uint32_t max_par = 0;
+            for (uint32_t j = 0; j < nr; ++j) {
+              const uint32_t p = S.post[j];
+              for (uint32_t q = p + 1; q < next[p]; q = next[q]) max_par = std::max(max_par, ++S.npar[S.newid[backref[q] ? label[q] : q]]);
+            }
+            const bool use_vout = max_par <= 127;
+            if (!use_vout) T.rows_out[l] |= 0x80000000u;
             S.cnt.assign(nr + 1, 0);  // parent in-degrees -> offsets
             uint32_t s = 0;
             for (uint32_t j = 0; j < nr; ++j) {
               const uint32_t p = S.post[j];
               if (label[p]) ++occ[label[p]];
               const bool leaf = next[p] == p + 1;
-              oi[(size_t)s++ * 32] = kHdr | (leaf ? kOpLast : 0u) | (stack_ok ? kHdrPush : 0u) | label[p];
+              oi[(size_t)s++ * 32] = kHdr | (leaf ? kOpLast : 0u) | (stack_ok ? kHdrPush : 0u) |
+                                     ((use_vout ? S.npar[j] : 0u) << kHdrNparShift) | label[p];
               if (leaf) continue;
               // links: children behind back references first (global reads), then the tree children, last defined
               // first (they are popped off the value stack)
@@ -1224,6 +1286,8 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     bt->t_stack_rows = tile_stack_rows.load();
     CML_CUDA(bt->t_in.alloc(bt->t_rows * real_b));
     CML_CUDA(bt->t_ga.alloc(bt->t_rows * real_b));
+    CML_CUDA(bt->t_vout.alloc(h_ops_out.size() * real_b));  // one value slot per outside stream word
+    CML_CUDA(cudaMemsetAsync(bt->t_vout.p, 0, h_ops_out.size() * real_b, f->stream));
   }
   CML_CUDA(bt->ln_inside.alloc(nf));
   CML_CUDA(cudaEventCreate(&bt->ev0));
@@ -1317,7 +1381,9 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     T.n_hot = f->n_hot;
     T.ln_inside = bt.ln_inside.p;
     T.stack_rows = bt.t_stack_rows;
-    const size_t tsmem = (size_t)kTileWarps * bt.t_stack_rows * 32 * sizeof(Real);
+    const size_t tsmem = (size_t)kTileWarps * bt.t_stack_rows * 32 * sizeof(Real) +
+                         (size_t)kTileWarps * kTileStages * kTileU * 32 * (sizeof(uint32_t) + sizeof(Real));
+    T.vout = bt.t_vout.p;
     if (tsmem > 48 * 1024)
       CML_CUDA(cudaFuncSetAttribute(k_forest_thread<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     k_forest_thread<Real><<<f_cdiv(bt.n_tiles, kTileWarps), kTileWarps * 32, tsmem, f->stream>>>(T);

@@ -196,3 +196,25 @@ def test_not_dense_falls_back(cli, oracle_bin, tmp_path):
     compare_wfst_text(out, oout, 1e-5)
     rc, _, err = run(cli, ["-t", "-M", "6", "--scaled", "--dense", c, f])
     assert rc != 0 and "no dense-state view" in err
+
+
+@pytest.mark.parametrize("mode,rel", [(["--scaled"], 1e-6), (["--float", "--scaled"], 1e-4)])
+def test_synthetic_27_state_cipher_all_paths(cli, oracle_bin, tmp_path, mode, rel):
+    """the bench's cipher model at a small size: dense-state kernel, and with --no-dense the 32x8 one-CTA-per-lattice
+    class of the level-sliced ELL kernel (27-state x 27-arc levels, aggregated count columns), both against the oracle"""
+    from carmel_b200 import synth
+    d = str(tmp_path)
+    files = {sub: synth.write_cipher(os.path.join(d, sub), n_lines=24, line_len=14, seed=77)["files"] for sub in ("o", "p", "l")}
+    args = ["--train-cascade", "-HJ", "-M", "5"]
+    rc, _, oerr = run(oracle_bin, [*args, f"--history={d}/h.o", *files["o"]], timeout=600)
+    assert rc == 0, oerr
+    rc, _, err = run(cli, [*args, *mode, "--dense", f"--history={d}/h.p", *files["p"]])
+    assert rc == 0, err
+    rc, _, lerr = run(cli, [*args, *mode, "--no-dense", f"--history={d}/h.l", *files["l"]])
+    assert rc == 0, lerr
+    _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), rel)
+    _close(read_history(f"{d}/h.l"), read_history(f"{d}/h.o"), rel)
+    for sub in ("p", "l"):
+        compare_wfst_text(open(os.path.join(d, sub, "channel.fst.trained")).read(),
+                          open(os.path.join(d, "o", "channel.fst.trained")).read(), rel * 20,
+                          ln_floor=-690.0 if rel <= 1e-6 else -60.0)
