@@ -683,7 +683,9 @@ int launch_sparse(cml_ctx* ctx) {
   A.exps = D.exp_g.p;
   A.has_phi = D.has_phi;
   const bool xi = D.n_t_slots > 0;
-  A.xi_tables = !xi ? 0u : (sparse_smem<Real>(SP, kSXi, K) <= 72 * 1024 ? (uint32_t)kSXi : 1u);
+  uint32_t want_xi = kSXi;
+  if (const char* e = getenv("CML_SPARSE_XI_TABLES")) want_xi = std::max(1, std::min(8, atoi(e)));  // tuning knob
+  A.xi_tables = !xi ? 0u : (sparse_smem<Real>(SP, want_xi, K) <= 72 * 1024 ? want_xi : 1u);
   const size_t smem = sparse_smem<Real>(SP, A.xi_tables, K);
   void (*kern)(SparseArgs) =
       K == 4 ? (xi ? k_fb_sparse<Real, 4, true> : k_fb_sparse<Real, 4, false>)

@@ -218,3 +218,18 @@ def test_synthetic_27_state_cipher_all_paths(cli, oracle_bin, tmp_path, mode, re
         compare_wfst_text(open(os.path.join(d, sub, "channel.fst.trained")).read(),
                           open(os.path.join(d, "o", "channel.fst.trained")).read(), rel * 20,
                           ln_floor=-690.0 if rel <= 1e-6 else -60.0)
+
+
+def test_dense_long_lines(cli, oracle_bin, tmp_path):
+    """SURVEY 8(d) C2 also names the one-long-line variant of the cipher corpus: two 3,000-letter lines (alpha / beta are
+    renormalised thousands of times; the likelihood is ~2^-14000), dense-state kernel against the oracle's lattices"""
+    from carmel_b200 import synth
+    d = str(tmp_path)
+    files = {sub: synth.write_cipher(os.path.join(d, sub), n_lines=2, line_len=3000, seed=5)["files"] for sub in ("o", "p")}
+    args = ["--train-cascade", "-HJ", "-M", "3"]
+    rc, _, oerr = run(oracle_bin, [*args, f"--history={d}/h.o", *files["o"]], timeout=900)
+    assert rc == 0, oerr
+    for mode, rel in ((["--scaled"], 1e-6), (["--float", "--scaled"], 1e-4)):
+        rc, _, err = run(cli, [*args, *mode, "--dense", f"--history={d}/h.p", *files["p"]])
+        assert rc == 0, err
+        _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), rel)
