@@ -146,10 +146,8 @@ def test_dense_zero_probability_sequence(native_lib):
     ctx = cb.Context(0, 64, cb.SPACE_SCALED)
     grp = np.asarray([0, 0, 1, 1, 2, 2, 3, 3], np.uint32)
     ctx.set_model(len(arcs), 8, grp, np.full(8, cb.NO_GROUP, np.uint32), 4, chain_off=chain_off, chain_param=chain)
-    w = np.log(np.asarray([0.5, 0.5, 0.5, 0.5, 1.0, 0.0, 0.3, 0.7]))  # E[0][1] = 0
     with np.errstate(divide="ignore"):
-        ctx.set_params(np.log(np.asarray([0.5, 0.5, 0.5, 0.5, 1.0, 0.0, 0.3, 0.7])))
-    del w
+        ctx.set_params(np.log(np.asarray([0.5, 0.5, 0.5, 0.5, 1.0, 0.0, 0.3, 0.7])))  # E[0][1] = 0
     src, dst, sym = (np.asarray([a[k] for a in arcs], np.uint32) for k in range(3))
     seqs = [[0, 0, 0], [1, 1, 0], [], [1, 0]]  # final state 0: [1,1,0] must end in state 0 emitting 0: fine
     ctx.add_sequences(2, 2, 0, 0, src, dst, sym, seqs)
