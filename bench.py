@@ -379,7 +379,7 @@ def main():
             rs = a.precision // 8
             k_ms = sum(m for m, _ in fb_ms) / len(fb_ms)
             n_k = fb_ms[0][1]
-            if is_dense and dense["kernel"] == "sparse":
+            if is_dense and dense["kernel"] == "sparse":  # (dense / dense_tc: the elif below)
                 # sparse-emission kernel: per position one symbol, K alpha values written + read, one exponent written +
                 # read; emission rows / transition matrix come from L2 / shared memory
                 res["totals"]["positions"] = pos_total
@@ -414,12 +414,17 @@ def main():
                     "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
                     "traffic": measured_traffic("k_fb_dense") if a.workload == "cipher" and a.precision == 64 and a.scale == 1 else None,
                     "peak_source": f"{which} bf16 dense peak / 2 (TF32 rate; no TF32 entry in MEASURED_PEAKS.json)",
-                    "kernel": "k_fb_dense (forward + backward + counts over never-materialised lattices, 1 launch per iteration)",
+                    "kernel": ("k_dense_tc<fwd> + k_dense_tc<bwd> + k_dense_tc_counts (3xTF32 mma.sync sweeps, 16 sequences per "
+                               "warp; 3 launches per iteration)" if dense["kernel"] == "dense_tc" else
+                               "k_fb_dense (forward + backward + counts over never-materialised lattices, 1 launch per iteration)"),
                     "kernel_ms": k_ms, "flops_per_position": 2.0 * products * S * S, "positions_per_launch": dense["positions"],
                     "kernel_share_of_step": k_ms / (ms / a.steps),
-                    "note": "CUDA-core FMA kernel (fp32/fp64), one warp per sequence: the step is a serial chain of "
-                            "line_len dependent 32x32 products, latency bound at this corpus size (0.4 GFLOP per iteration); "
-                            "reported against the tensor peak as SURVEY 8(d) asks for the dense case",
+                    "note": ("tensor-core path: each position step of 16 sequences is a [16x32].[32x32] product in 3xTF32"
+                             if dense["kernel"] == "dense_tc" else
+                             "CUDA-core FMA kernel (fp32/fp64), one warp per sequence: the step is a serial chain of "
+                             "line_len dependent 32x32 products, latency bound at this corpus size (0.3 GFLOP per iteration); "
+                             "reported against the tensor peak as SURVEY 8(d) asks for the dense case; fp32 corpora of >= 16,384 "
+                             "sequences take the 3xTF32 tensor-core kernels (k_dense_tc)"),
                     "hbm_equivalent": {"algorithmic_bytes": hbm_bytes, "achieved_gbs": hbm_bytes / (k_ms / 1e3) / 1e9,
                                        "peak_gbs": float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))}}
                 res["layout"] = dense

@@ -294,7 +294,7 @@ class Context:
         sp, k, ns = C.c_int(), C.c_uint32(), C.c_uint32()
         self._check(self.lib.cml_dense_kernel(self.h, C.byref(sp), C.byref(k), C.byref(ns)))
         return dict(sequences=int(a.value), positions=int(b_.value), t_slots=int(c.value), e_slots=int(d.value),
-                    kernel={1: "sparse", 0: "dense", -1: None}[int(sp.value)], k=int(k.value), n_states=int(ns.value))
+                    kernel={1: "sparse", 0: "dense", 2: "dense_tc", -1: None}[int(sp.value)], k=int(k.value), n_states=int(ns.value))
 
     def trellis_totals(self) -> dict:
         v = [C.c_uint64() for _ in range(4)]

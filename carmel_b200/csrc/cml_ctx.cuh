@@ -92,6 +92,13 @@ struct DenseState {
   DevArray<double> seq_weight, ex_lnp;
   DevArray<unsigned char> alpha_g;  // Real[(n_pos + n_seq)][32]
   DevArray<int> exp_g;              // cumulative power-of-two exponent of every alpha row
+  // tensor-core sweeps (k_dense_tc): groups of 16 sequences, beta rows, per-sequence alpha_n[final]
+  bool tc = false;
+  uint32_t tc_groups = 0;
+  DevArray<uint32_t> tc_order;
+  DevArray<unsigned char> beta_g;
+  DevArray<int> bexp_g, tc_ean;
+  DevArray<double> tc_afin;
   // sparse kernel: tiles of 32 sequences, per-lane facts, emission rows
   DevArray<SparseTile> stile;
   DevArray<uint32_t> lane_len, lane_seq, e_code;

@@ -312,6 +312,312 @@ __global__ void __launch_bounds__(kDW * 32) k_fb_dense(DenseArgs A) {
   }
 }
 
+// =====================================================================================================
+// Tensor-core variant of the dense-state sweep for LARGE batches in fp32 mode (north_star: the position step of a
+// batch of sequences as a dense GEMM in 3xTF32).  One warp carries 16 sequences (the M dimension of
+// mma.sync.m16n8k8): per position  C[16 x 32] = A[16 x 32] . T[32 x 32]  as 4 x 4 tiles of m16n8k8 TF32 MMAs, each
+// product issued three times (A_hi T_hi + A_lo T_hi + A_hi T_lo, fp32 accumulate) so the result keeps fp32
+// accuracy; the 16 x 32 state matrix goes through a padded shared-memory tile between the accumulator layout and
+// the A-operand layout; emission columns, per-row power-of-two renormalisation and the row stores stay in
+// registers.  Forward and backward are two launches of the same kernel (B operand = T or T^T, emission applied
+// after / before the product); the expected counts are a third, position-parallel launch (one warp per sequence,
+// the pair's private gamma table) -- 16 sequences per warp would collide on the count cells.
+// Used for fp32 contexts with a locked transition model (no xi) and >= 16,384 sequences (CML_DENSE_TC=1 forces it):
+// with the 2,000 lines of the bench corpus there would be 125 warps for 148 SMs.  This is the legacy warp-level MMA
+// path, not tcgen05: a 16-row tile per warp keeps the serial chain of a sequence inside one warp's registers, where
+// a 128-row tcgen05 tile would need a TMEM -> register -> shared-memory round trip per position.
+// =====================================================================================================
+struct TcArgs {
+  const uint64_t* seq_off;
+  const uint16_t* sym;
+  const double* seq_weight;
+  uint32_t n_seq, n_groups, n_sym, start, fin;
+  const uint32_t* order;  // [n_groups * 16] sequence of every row (longest first), 0xFFFFFFFF = empty row
+  const float* T;         // [32][32]
+  const float* Et;        // [n_sym][32]
+  float* rows;            // alpha_g (forward) / beta_g (backward)
+  int* exps;              // exp_g / bexp_g
+  const float* arows;     // counts: alpha rows
+  const int* aexps;
+  double* ex_lnp;
+  double* afin_g;         // per sequence: alpha_n[fin] (renormalised) and its exponent
+  int* ean_g;
+  const uint32_t* cell_slot;
+  double* counts;
+};
+constexpr int kTcWarps = 4, kTcStride = 36;  // row stride of the shared state tile (conflict-free fragment loads)
+
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kTcWarps * 32) k_dense_tc(TcArgs A) {
+  extern __shared__ __align__(16) float smem_tc[];
+  float* Es = smem_tc;
+  for (uint32_t i = threadIdx.x; i < A.n_sym * 32; i += blockDim.x) Es[i] = A.Et[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t grp = blockIdx.x * kTcWarps + warp;
+  if (grp >= A.n_groups) return;
+  float* X = smem_tc + A.n_sym * 32 + warp * 16 * kTcStride;
+  const int g = lane >> 2, tq = lane & 3;
+  const unsigned qmask = 0xFu << (lane & ~3);  // the quad that shares this lane's two rows
+  // this lane's rows: g and g + 8
+  uint32_t e[2], n[2];
+  uint64_t base[2], r0[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    e[h] = A.order[grp * 16 + g + 8 * h];
+    const bool ok = e[h] != 0xFFFFFFFFu;
+    base[h] = ok ? A.seq_off[e[h]] : 0;
+    n[h] = ok ? (uint32_t)(A.seq_off[e[h] + 1] - base[h]) : 0u;
+    r0[h] = base[h] + (ok ? e[h] : 0);
+  }
+  const uint32_t nmax = __shfl_sync(0xffffffffu, n[0], 0);  // row 0 of the group is its longest sequence
+  // B operand: T (forward: B[k][n] = T[k][n]) or T^T (backward: B[k = j][n = i] = T[i][j]), split once
+  uint32_t bh[4][4][2], bl[4][4][2];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int k0 = 8 * kt + tq, k1 = k0 + 4, nn = 8 * nt + g;
+      const float v0 = BWD ? A.T[nn * 32 + k0] : A.T[k0 * 32 + nn];
+      const float v1 = BWD ? A.T[nn * 32 + k1] : A.T[k1 * 32 + nn];
+      tf32_split(v0, bh[kt][nt][0], bl[kt][nt][0]);
+      tf32_split(v1, bh[kt][nt][1], bl[kt][nt][1]);
+    }
+  int E[2] = {0, 0};  // cumulative exponent of each row
+  // one-hot start (forward) / final (backward) rows, in the accumulator layout: cols 8nt + 2tq, +1
+  auto put_onehot = [&](int h, uint32_t hot, uint64_t hbm_row) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint32_t c0 = 8 * nt + 2 * tq;
+      const float2 v = make_float2(c0 == hot ? 1.f : 0.f, c0 + 1 == hot ? 1.f : 0.f);
+      *reinterpret_cast<float2*>(&X[(g + 8 * h) * kTcStride + c0]) = v;
+      if (e[h] != 0xFFFFFFFFu) *reinterpret_cast<float2*>(&A.rows[hbm_row * 32 + c0]) = v;
+    }
+    if (e[h] != 0xFFFFFFFFu && tq == 0) A.exps[hbm_row] = 0;
+    E[h] = 0;
+  };
+  if (!BWD) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      put_onehot(h, A.start, r0[h]);
+      if (e[h] != 0xFFFFFFFFu && n[h] == 0 && tq == 0) {  // empty sequence: P = [start == final]
+        A.ex_lnp[e[h]] = A.start == A.fin ? 0. : -CUDART_INF;
+        A.afin_g[e[h]] = A.start == A.fin ? 1. : 0.;
+        A.ean_g[e[h]] = 0;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // rows shorter than the group start later; clear them, start the longest now
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) *reinterpret_cast<float2*>(&X[(g + 8 * h) * kTcStride + 8 * nt + 2 * tq]) = make_float2(0.f, 0.f);
+      if (n[h] == nmax || n[h] == 0) put_onehot(h, A.fin, r0[h] + n[h]);
+    }
+  }
+  __syncwarp();
+  for (uint32_t s = 0; s < nmax; ++s) {
+    const uint32_t t = BWD ? nmax - 1 - s : s;  // link between positions t and t+1, symbol o_t
+    uint32_t o[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) o[h] = t < n[h] ? A.sym[base[h] + t] : 0u;
+    if (BWD) {  // rows whose sequence ends at t+1 start here with beta = one-hot(final)
+      bool any = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (n[h] == t + 1 && n[h] != nmax) {
+          put_onehot(h, A.fin, r0[h] + n[h]);
+          any = true;
+        }
+      if (__any_sync(0xffffffffu, any)) __syncwarp();
+    }
+    // A operand from the shared state tile (backward: times the emission column of each row's symbol)
+    uint32_t ah[4][4], al[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int k0 = 8 * kt + tq, k1 = k0 + 4;
+      float a0 = X[g * kTcStride + k0], a1 = X[(g + 8) * kTcStride + k0];
+      float a2 = X[g * kTcStride + k1], a3 = X[(g + 8) * kTcStride + k1];
+      if (BWD) {
+        a0 *= Es[o[0] * 32 + k0];
+        a1 *= Es[o[1] * 32 + k0];
+        a2 *= Es[o[0] * 32 + k1];
+        a3 *= Es[o[1] * 32 + k1];
+      }
+      tf32_split(a0, ah[kt][0], al[kt][0]);
+      tf32_split(a1, ah[kt][1], al[kt][1]);
+      tf32_split(a2, ah[kt][2], al[kt][2]);
+      tf32_split(a3, ah[kt][3], al[kt][3]);
+    }
+    __syncwarp();  // everybody has read the tile: it can be overwritten below
+    float c[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c[nt][k] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        mma_tf32(c[nt], al[kt], bh[kt][nt]);
+        mma_tf32(c[nt], ah[kt], bl[kt][nt]);
+        mma_tf32(c[nt], ah[kt], bh[kt][nt]);
+      }
+    }
+    // epilogue per row: (forward: emission column), power-of-two renormalisation, stores
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        v[2 * nt] = c[nt][2 * h];
+        v[2 * nt + 1] = c[nt][2 * h + 1];
+        if (!BWD) {
+          const float2 ev = *reinterpret_cast<const float2*>(&Es[o[h] * 32 + 8 * nt + 2 * tq]);
+          v[2 * nt] *= ev.x;
+          v[2 * nt + 1] *= ev.y;
+        }
+      }
+      int mx = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx = max(mx, __float_as_int(v[k]));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      if (mx > 0) {
+        const int ex = DN<float>::expo(mx);
+        const float f = DN<float>::pow2(-ex);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= f;
+        E[h] += ex;
+      }
+      const bool active = e[h] != 0xFFFFFFFFu && t < n[h];  // this row really has a position t
+      const uint64_t hrow = r0[h] + (BWD ? t : t + 1);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 w2 = make_float2(v[2 * nt], v[2 * nt + 1]);
+        *reinterpret_cast<float2*>(&X[(g + 8 * h) * kTcStride + 8 * nt + 2 * tq]) = w2;
+        if (active) *reinterpret_cast<float2*>(&A.rows[hrow * 32 + 8 * nt + 2 * tq]) = w2;
+      }
+      if (active && tq == 0) A.exps[hrow] = E[h];
+      if (!BWD && e[h] != 0xFFFFFFFFu && t + 1 == n[h]) {  // the row's last position: P = alpha_n[final] (quad-uniform branch)
+        const int ft = A.fin >> 3, fc = A.fin & 7;
+        float mine = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          if (nt == ft) mine = (fc & 1) ? v[2 * nt + 1] : v[2 * nt];
+        const float afin = __shfl_sync(qmask, mine, (lane & ~3) | (fc >> 1));
+        if (tq == 0) {
+          A.ex_lnp[e[h]] = (afin > 0) ? log((double)afin) + (double)E[h] * 0.69314718055994530942 : -CUDART_INF;
+          A.afin_g[e[h]] = (double)afin;
+          A.ean_g[e[h]] = E[h];
+        }
+      }
+    }
+    __syncwarp();  // the new tile is complete before the next step's fragment loads
+  }
+}
+
+// expected counts of the tensor-core sweeps: position-parallel, one warp per sequence, lane = state
+__global__ void __launch_bounds__(kDW * 32) k_dense_tc_counts(TcArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_tcc[];
+  double* gam_all = reinterpret_cast<double*>(smem_tcc);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_sym = A.n_sym;
+  for (uint32_t i = threadIdx.x; i < kDW * n_sym * 32; i += blockDim.x) gam_all[i] = 0.;
+  __syncthreads();
+  double* gam = gam_all + (size_t)w * n_sym * 32;
+  for (uint64_t e = (uint64_t)blockIdx.x * kDW + w; e < A.n_seq; e += (uint64_t)gridDim.x * kDW) {
+    const double afin = A.afin_g[e];
+    if (!(afin > 0)) continue;
+    const int EaN = A.ean_g[e];
+    const double cw = A.seq_weight[e] / afin;
+    const uint64_t base = A.seq_off[e];
+    const uint32_t n = (uint32_t)(A.seq_off[e + 1] - base);
+    const uint64_t r0 = base + e;
+#pragma unroll 2
+    for (uint32_t t = 0; t < n; ++t) {
+      const uint32_t o = A.sym[base + t];
+      const float a1 = A.arows[(r0 + t + 1) * 32 + lane], b1 = A.rows[(r0 + t + 1) * 32 + lane];
+      const int de = A.aexps[r0 + t + 1] + A.exps[r0 + t + 1] - EaN;
+      gam[o * 32 + lane] += (double)a1 * (double)b1 * (cw * pow2d(de));
+    }
+  }
+  __syncthreads();
+  const uint32_t* __restrict__ e_slot = A.cell_slot + 1024;
+  for (uint32_t c = threadIdx.x; c < n_sym * 32; c += blockDim.x) {
+    const uint32_t sl = e_slot[c];
+    if (sl == kNone) continue;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < kDW; ++k) s += gam_all[(size_t)k * n_sym * 32 + c];
+    if (s != 0.) atomicAdd(A.counts + sl, s);
+  }
+}
+
+static int launch_dense_tc(cml_ctx* ctx) {
+  DenseState& D = *ctx->dense;
+  cudaStream_t s = ctx->stream;
+  k_dense_tables<float><<<cdiv(D.n_cells, 256), 256, 0, s>>>(D.n_cells, D.cell_off.p, D.cell_param.p, D.cell_exists.p,
+                                                            ctx->ln_w.p, reinterpret_cast<float*>(D.tables.p));
+  ++ctx->launches;
+  CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
+  TcArgs A;
+  A.seq_off = D.seq_off.p;
+  A.sym = D.sym.p;
+  A.seq_weight = D.seq_weight.p;
+  A.n_seq = (uint32_t)D.n_seq;
+  A.n_groups = D.tc_groups;
+  A.n_sym = D.n_sym;
+  A.start = D.start;
+  A.fin = D.fin;
+  A.order = D.tc_order.p;
+  A.T = reinterpret_cast<const float*>(D.tables.p);
+  A.Et = A.T + 1024;
+  A.ex_lnp = D.ex_lnp.p;
+  A.afin_g = D.tc_afin.p;
+  A.ean_g = D.tc_ean.p;
+  A.cell_slot = D.cell_slot.p;
+  A.counts = ctx->reduce;
+  A.arows = reinterpret_cast<const float*>(D.alpha_g.p);
+  A.aexps = D.exp_g.p;
+  const size_t smem = ((size_t)D.n_sym * 32 + (size_t)kTcWarps * 16 * kTcStride) * sizeof(float);
+  const size_t csmem = (size_t)kDW * D.n_sym * 32 * sizeof(double);
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+  if (!D.ev0) {
+    CML_CUDA(cudaEventCreate(&D.ev0));
+    CML_CUDA(cudaEventCreate(&D.ev1));
+  }
+  CML_CUDA(cudaEventRecord(D.ev0, s));
+  if (D.tc_groups) {
+    A.rows = reinterpret_cast<float*>(D.alpha_g.p);
+    A.exps = D.exp_g.p;
+    k_dense_tc<false><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem, s>>>(A);
+    A.rows = reinterpret_cast<float*>(D.beta_g.p);
+    A.exps = D.bexp_g.p;
+    k_dense_tc<true><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem, s>>>(A);
+    k_dense_tc_counts<<<std::max(1u, std::min<unsigned>(cdiv(D.n_seq, kDW), 4u * ctx->sm_count)), kDW * 32, csmem, s>>>(A);
+    ctx->launches += 3;
+  }
+  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (D.n_seq) {
+    cmlk::k_reduce_lnp<<<std::min<unsigned>(cdiv(D.n_seq, 256), 4 * ctx->sm_count), 256, 0, s>>>(
+        D.ex_lnp.p, D.seq_weight.p, D.n_seq, ctx->reduce + ctx->n_slots);
+    ++ctx->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
 template <typename Real>
 int launch_dense(cml_ctx* ctx) {
   DenseState& D = *ctx->dense;
@@ -729,6 +1035,7 @@ std::vector<uint32_t> ms_minus(const std::vector<uint32_t>& a, const std::vector
 }  // namespace
 
 int cml_dense_estimate_launch(cml_ctx* ctx) {
+  if (ctx->dense->tc) return launch_dense_tc(ctx);
   if (ctx->dense->sparse) return ctx->precision == 64 ? launch_sparse<double>(ctx) : launch_sparse<float>(ctx);
   return ctx->precision == 64 ? launch_dense<double>(ctx) : launch_dense<float>(ctx);
 }
@@ -940,6 +1247,25 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
     CML_CUDA(D->sym.upload(sym16.data(), sym16.size(), s));
     CML_CUDA(D->alpha_g.alloc((size_t)(n_pos + b->n_seq) * kDS * rs));
     CML_CUDA(D->exp_g.alloc((size_t)(n_pos + b->n_seq)));
+    // tensor-core sweeps (3xTF32): fp32, locked transitions, small alphabet, many sequences
+    uint64_t tc_min = 16384;
+    if (const char* ev = getenv("CML_DENSE_TC")) tc_min = atoi(ev) > 0 ? 0 : ~0ull;
+    if (ctx->precision == 32 && n_t_slots == 0 && b->n_seq >= tc_min && b->n_seq > 0 &&
+        (size_t)kDW * V * 32 * sizeof(double) <= 100 * 1024) {
+      std::vector<uint32_t> order(b->n_seq);
+      for (uint32_t e = 0; e < b->n_seq; ++e) order[e] = e;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return b->seq_off[x + 1] - b->seq_off[x] > b->seq_off[y + 1] - b->seq_off[y];
+      });
+      D->tc_groups = (uint32_t)((b->n_seq + 15) / 16);
+      order.resize((size_t)D->tc_groups * 16, 0xFFFFFFFFu);
+      CML_CUDA(D->tc_order.upload(order.data(), order.size(), s));
+      CML_CUDA(D->beta_g.alloc((size_t)(n_pos + b->n_seq) * kDS * rs));
+      CML_CUDA(D->bexp_g.alloc((size_t)(n_pos + b->n_seq)));
+      CML_CUDA(D->tc_afin.alloc(b->n_seq));
+      CML_CUDA(D->tc_ean.alloc(b->n_seq));
+      D->tc = true;
+    }
   } else {
     // tiles of 32 sequences of similar length, symbols transposed
     std::vector<uint32_t> order(b->n_seq);
@@ -1035,7 +1361,7 @@ extern "C" int cml_dense_stats(cml_ctx* ctx, uint64_t* n_seq, uint64_t* n_positi
 extern "C" int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k, uint32_t* n_states) {
   if (!ctx) return CML_ERR_ARG;
   const DenseState* D = ctx->dense.get();
-  if (sparse) *sparse = D ? (D->sparse ? 1 : 0) : -1;
+  if (sparse) *sparse = D ? (D->sparse ? 1 : (D->tc ? 2 : 0)) : -1;
   if (k) *k = D ? D->K : 0;
   if (n_states) *n_states = D ? D->S : 0;
   return CML_OK;

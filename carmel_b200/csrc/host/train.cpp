@@ -223,7 +223,8 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
   if (!opt.quiet && !flags[(unsigned)'q']) {
     std::cerr << "dense-state path: " << S << " states x " << V << " symbols, " << nt << " trainable transition cells, "
               << ne << " trainable emission cells";
-    if (sparse) std::cerr << " (sparse emission rows of " << kk << ", one sequence per lane)";
+    if (sparse == 1) std::cerr << " (sparse emission rows of " << kk << ", one sequence per lane)";
+    if (sparse == 2) std::cerr << " (3xTF32 tensor-core sweeps, 16 sequences per warp)";
     std::cerr << "\n";
   }
   res.trellis_arcs = n_arcs;

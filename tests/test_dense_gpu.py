@@ -231,3 +231,26 @@ def test_dense_long_lines(cli, oracle_bin, tmp_path):
         rc, _, err = run(cli, [*args, *mode, "--dense", f"--history={d}/h.p", *files["p"]])
         assert rc == 0, err
         _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), rel)
+
+
+def test_tensor_core_sweeps_match_oracle(cli, oracle_bin, tmp_path, monkeypatch):
+    """k_dense_tc (3xTF32 mma.sync, 16 sequences per warp; normally for >= 16,384 sequences, forced here with
+    CML_DENSE_TC=1): fp32 trajectory and weights against the oracle on ragged lines (rows of a 16-sequence group
+    start and end at different positions), a partly filled last group, and a zero-length-free corpus"""
+    monkeypatch.setenv("CML_DENSE_TC", "1")
+    d = str(tmp_path)
+    rng = np.random.default_rng(99)
+    files = {}
+    for sub in ("o", "p"):
+        os.makedirs(os.path.join(d, sub))
+        files[sub] = write_small_cipher(os.path.join(d, sub), np.random.default_rng(99), n_lines=53, lens=(1, 70), weighted=True)
+    del rng
+    args = ["--train-cascade", "-HJ", "-M", "6"]
+    rc, _, oerr = run(oracle_bin, [*args, f"--history={d}/h.o", *files["o"]])
+    assert rc == 0, oerr
+    rc, _, err = run(cli, [*args, "--float", "--scaled", "--dense", f"--history={d}/h.p", *files["p"]])
+    assert rc == 0, err
+    assert "3xTF32 tensor-core sweeps" in err, err
+    _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), 1e-4)
+    compare_wfst_text(open(os.path.join(d, "p", "channel.fst.trained")).read(),
+                      open(os.path.join(d, "o", "channel.fst.trained")).read(), 2e-3, ln_floor=-60.0)
