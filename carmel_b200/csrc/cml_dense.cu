@@ -542,12 +542,23 @@ __global__ void __launch_bounds__(kDW * 32) k_dense_tc_counts(TcArgs A) {
     const uint64_t base = A.seq_off[e];
     const uint32_t n = (uint32_t)(A.seq_off[e + 1] - base);
     const uint64_t r0 = base + e;
-#pragma unroll 2
-    for (uint32_t t = 0; t < n; ++t) {
-      const uint32_t o = A.sym[base + t];
-      const float a1 = A.arows[(r0 + t + 1) * 32 + lane], b1 = A.rows[(r0 + t + 1) * 32 + lane];
-      const int de = A.aexps[r0 + t + 1] + A.exps[r0 + t + 1] - EaN;
-      gam[o * 32 + lane] += (double)a1 * (double)b1 * (cw * pow2d(de));
+    // four positions per round: all loads first (the kernel is a pure stream of alpha / beta rows), then the
+    // dependent shared-memory updates
+    for (uint32_t t0 = 0; t0 < n; t0 += 4) {
+      float a1[4], b1[4];
+      int de[4];
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t t = min(t0 + k, n - 1);
+        o[k] = A.sym[base + t];
+        a1[k] = A.arows[(r0 + t + 1) * 32 + lane];
+        b1[k] = A.rows[(r0 + t + 1) * 32 + lane];
+        de[k] = A.aexps[r0 + t + 1] + A.exps[r0 + t + 1] - EaN;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t0 + k < n) gam[o[k] * 32 + lane] += (double)a1[k] * (double)b1[k] * (cw * pow2d(de[k]));
     }
   }
   __syncthreads();
