@@ -358,16 +358,26 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <bool BWD>
+// XI (backward launch only): the transition counts on the tensor cores as well.  xi[i][j] = T[i][j] * sum over
+// sequences b and positions t of (alpha_t[b][i] * scale_b) * betatilde_{t+1}[b][j] is, per position, the product
+// [32 x 16] . [16 x 32] (K = the 16 sequences of the warp): 2 x 4 output tiles x 2 k-steps of m16n8k8, in 3xTF32,
+// accumulated in 32 fp32 registers per lane and folded into an fp64 table every 64 positions -- no atomics per
+// position at all (the FMA kernels pay one shared-memory CAS loop or 32 register FMAs per lane for this).
+template <bool BWD, bool XI>
 __global__ void __launch_bounds__(kTcWarps * 32) k_dense_tc(TcArgs A) {
   extern __shared__ __align__(16) float smem_tc[];
+  __shared__ double xis[XI ? 1024 : 1];
   float* Es = smem_tc;
   for (uint32_t i = threadIdx.x; i < A.n_sym * 32; i += blockDim.x) Es[i] = A.Et[i];
+  if (XI)
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) xis[i] = 0.;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t grp = blockIdx.x * kTcWarps + warp;
-  if (grp >= A.n_groups) return;
-  float* X = smem_tc + A.n_sym * 32 + warp * 16 * kTcStride;
+  if (grp < A.n_groups) {
+  float* X = smem_tc + A.n_sym * 32 + warp * (XI ? 3 : 1) * 16 * kTcStride;
+  float* Y = X + 16 * kTcStride;  // XI: alpha_t rows, scaled     [sequence][state]
+  float* Z = Y + 16 * kTcStride;  // XI: betatilde_{t+1} rows      [sequence][state]
   const int g = lane >> 2, tq = lane & 3;
   const unsigned qmask = 0xFu << (lane & ~3);  // the quad that shares this lane's two rows
   // this lane's rows: g and g + 8
@@ -382,6 +392,37 @@ __global__ void __launch_bounds__(kTcWarps * 32) k_dense_tc(TcArgs A) {
     r0[h] = base[h] + (ok ? e[h] : 0);
   }
   const uint32_t nmax = __shfl_sync(0xffffffffu, n[0], 0);  // row 0 of the group is its longest sequence
+  double cwr[2] = {0., 0.};  // XI: weight / P of this lane's rows, and the exponent of P
+  int eanr[2] = {0, 0};
+  float cxi[2][4][4];        // XI: accumulators of the 2 x 4 output tiles
+  if (XI) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (e[h] != 0xFFFFFFFFu) {
+        const double af = A.afin_g[e[h]];
+        cwr[h] = af > 0 ? A.seq_weight[e[h]] / af : 0.;
+        eanr[h] = A.ean_g[e[h]];
+      }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cxi[mt][nt][k] = 0.f;
+  }
+  auto fold_xi = [&]() {  // accumulators -> the CTA's fp64 table (times T), then cleared
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 16 * mt + g + 8 * (k >> 1), j = 8 * nt + 2 * tq + (k & 1);
+          const double v = (double)cxi[mt][nt][k] * (double)A.T[i * 32 + j];
+          if (v != 0.) atomicAdd(&xis[XI ? i * 32 + j : 0], v);
+          cxi[mt][nt][k] = 0.f;
+        }
+  };
   // B operand: T (forward: B[k][n] = T[k][n]) or T^T (backward: B[k = j][n = i] = T[i][j]), split once
   uint32_t bh[4][4][2], bl[4][4][2];
 #pragma unroll
@@ -440,6 +481,57 @@ __global__ void __launch_bounds__(kTcWarps * 32) k_dense_tc(TcArgs A) {
           any = true;
         }
       if (__any_sync(0xffffffffu, any)) __syncwarp();
+    }
+    if (BWD && XI) {
+      // stage betatilde_{t+1} (this lane's elements of the state tile times the emission column) and the scaled
+      // alpha_t rows, then one [32 x 16] . [16 x 32] product into the xi accumulators
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool on = e[h] != 0xFFFFFFFFu && t < n[h] && cwr[h] > 0.;
+        float sc = 0.f;
+        if (on) sc = (float)(cwr[h] * pow2d(A.aexps[r0[h] + t] + E[h] - eanr[h]));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c0 = 8 * nt + 2 * tq;
+          const float2 xv = *reinterpret_cast<const float2*>(&X[(g + 8 * h) * kTcStride + c0]);
+          const float2 ev = *reinterpret_cast<const float2*>(&Es[o[h] * 32 + c0]);
+          *reinterpret_cast<float2*>(&Z[(g + 8 * h) * kTcStride + c0]) = on ? make_float2(xv.x * ev.x, xv.y * ev.y) : make_float2(0.f, 0.f);
+          float2 av = make_float2(0.f, 0.f);
+          if (on) {
+            av = *reinterpret_cast<const float2*>(&A.arows[(r0[h] + t) * 32 + c0]);
+            av.x *= sc;
+            av.y *= sc;
+          }
+          *reinterpret_cast<float2*>(&Y[(g + 8 * h) * kTcStride + c0]) = av;
+        }
+      }
+      __syncwarp();
+      uint32_t zh[2][4][2], zl[2][4][2];  // B' = betatilde: [k = sequence][n = j]
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          tf32_split(Z[(8 * ks + tq) * kTcStride + 8 * nt + g], zh[ks][nt][0], zl[ks][nt][0]);
+          tf32_split(Z[(8 * ks + tq + 4) * kTcStride + 8 * nt + g], zh[ks][nt][1], zl[ks][nt][1]);
+        }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t yh[4], yl[4];  // A' = alpha^T: [m = i][k = sequence]
+          tf32_split(Y[(8 * ks + tq) * kTcStride + 16 * mt + g], yh[0], yl[0]);
+          tf32_split(Y[(8 * ks + tq) * kTcStride + 16 * mt + g + 8], yh[1], yl[1]);
+          tf32_split(Y[(8 * ks + tq + 4) * kTcStride + 16 * mt + g], yh[2], yl[2]);
+          tf32_split(Y[(8 * ks + tq + 4) * kTcStride + 16 * mt + g + 8], yh[3], yl[3]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            mma_tf32(cxi[mt][nt], yl, zh[ks][nt]);
+            mma_tf32(cxi[mt][nt], yh, zl[ks][nt]);
+            mma_tf32(cxi[mt][nt], yh, zh[ks][nt]);
+          }
+        }
+      if ((s & 63) == 63) fold_xi();
+      __syncwarp();
     }
     // A operand from the shared state tile (backward: times the emission column of each row's symbol)
     uint32_t ah[4][4], al[4][4];
@@ -523,6 +615,16 @@ __global__ void __launch_bounds__(kTcWarps * 32) k_dense_tc(TcArgs A) {
     }
     __syncwarp();  // the new tile is complete before the next step's fragment loads
   }
+  if (BWD && XI) fold_xi();
+  }  // grp < n_groups
+  if (BWD && XI) {
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < 1024; c += blockDim.x) {
+      const uint32_t sl = A.cell_slot[c];
+      const double v = xis[XI ? c : 0];
+      if (sl != kNone && v != 0.) atomicAdd(A.counts + sl, v);
+    }
+  }
 }
 
 // expected counts of the tensor-core sweeps: position-parallel, one warp per sequence, lane = state
@@ -599,10 +701,13 @@ static int launch_dense_tc(cml_ctx* ctx) {
   A.counts = ctx->reduce;
   A.arows = reinterpret_cast<const float*>(D.alpha_g.p);
   A.aexps = D.exp_g.p;
+  const bool xi = D.n_t_slots > 0;
   const size_t smem = ((size_t)D.n_sym * 32 + (size_t)kTcWarps * 16 * kTcStride) * sizeof(float);
+  const size_t smem_b = ((size_t)D.n_sym * 32 + (size_t)kTcWarps * (xi ? 3 : 1) * 16 * kTcStride) * sizeof(float);
   const size_t csmem = (size_t)kDW * D.n_sym * 32 * sizeof(double);
-  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  CML_CUDA(cudaFuncSetAttribute(k_dense_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   CML_CUDA(cudaFuncSetAttribute(k_dense_tc_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
   if (!D.ev0) {
     CML_CUDA(cudaEventCreate(&D.ev0));
@@ -612,10 +717,13 @@ static int launch_dense_tc(cml_ctx* ctx) {
   if (D.tc_groups) {
     A.rows = reinterpret_cast<float*>(D.alpha_g.p);
     A.exps = D.exp_g.p;
-    k_dense_tc<false><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem, s>>>(A);
+    k_dense_tc<false, false><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem, s>>>(A);
     A.rows = reinterpret_cast<float*>(D.beta_g.p);
     A.exps = D.bexp_g.p;
-    k_dense_tc<true><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem, s>>>(A);
+    if (xi)
+      k_dense_tc<true, true><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem_b, s>>>(A);
+    else
+      k_dense_tc<true, false><<<cdiv(D.tc_groups, kTcWarps), kTcWarps * 32, smem_b, s>>>(A);
     k_dense_tc_counts<<<std::max(1u, std::min<unsigned>(cdiv(D.n_seq, kDW), 4u * ctx->sm_count)), kDW * 32, csmem, s>>>(A);
     ctx->launches += 3;
   }
@@ -1261,7 +1369,7 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
     // tensor-core sweeps (3xTF32): fp32, locked transitions, small alphabet, many sequences
     uint64_t tc_min = 16384;
     if (const char* ev = getenv("CML_DENSE_TC")) tc_min = atoi(ev) > 0 ? 0 : ~0ull;
-    if (ctx->precision == 32 && n_t_slots == 0 && b->n_seq >= tc_min && b->n_seq > 0 &&
+    if (ctx->precision == 32 && b->n_seq >= tc_min && b->n_seq > 0 &&
         (size_t)kDW * V * 32 * sizeof(double) <= 100 * 1024) {
       std::vector<uint32_t> order(b->n_seq);
       for (uint32_t e = 0; e < b->n_seq; ++e) order[e] = e;

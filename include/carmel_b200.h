@@ -166,8 +166,8 @@ int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_
  * M-step; likelihoods and learned weights equal the lattice path's (unreachable / dead lattice states carry
  * alpha = 0 or beta = 0).  Needs a CML_SPACE_SCALED context and no lattices resident.  Two kernels:
  *   dense   one warp per sequence, all n_states <= 32 states live at every position (cipher: 27 x 27 per letter);
- *           fp32 contexts with >= 16,384 sequences and no trainable transition run the position step of 16
- *           sequences at a time as 3xTF32 tensor-core products (k_dense_tc)
+ *           fp32 contexts with >= 16,384 sequences run the position step of 16 sequences at a time as 3xTF32
+ *           tensor-core products (k_dense_tc), the transition counts included
  *   sparse  one lane per sequence, every symbol emitted by <= 8 states, n_states <= 64, optional final weights
  *           (HMM tagging: a word has a handful of tags); chosen for batches of >= 4096 sequences.
  * After success the count slots (cml_count_slots, cml_get_counts, the reduce buffer) are the trainable T / E
@@ -191,7 +191,7 @@ typedef struct cml_sequence_batch {
 } cml_sequence_batch;
 int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b);
 /* which kernel the resident sequences use: *sparse = 1 sparse-emission, 0 dense (FMA), 2 dense on the tensor cores
- * (3xTF32, fp32 contexts with >= 16,384 sequences and a locked transition model), -1 none; *k = emission row width;
+ * (3xTF32, fp32 contexts with >= 16,384 sequences), -1 none; *k = emission row width;
  * *n_states = states of the dense view */
 int cml_dense_kernel(cml_ctx* ctx, int* sparse, uint32_t* k, uint32_t* n_states);
 /* resident dense sequences: count, positions (sum of lengths), and whether T cells are trainable (xi kept) */

@@ -233,17 +233,20 @@ def test_dense_long_lines(cli, oracle_bin, tmp_path):
         _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), rel)
 
 
-def test_tensor_core_sweeps_match_oracle(cli, oracle_bin, tmp_path, monkeypatch):
+@pytest.mark.parametrize("lock_lm", [True, False])
+def test_tensor_core_sweeps_match_oracle(cli, oracle_bin, tmp_path, monkeypatch, lock_lm):
     """k_dense_tc (3xTF32 mma.sync, 16 sequences per warp; normally for >= 16,384 sequences, forced here with
     CML_DENSE_TC=1): fp32 trajectory and weights against the oracle on ragged lines (rows of a 16-sequence group
-    start and end at different positions), a partly filled last group, and a zero-length-free corpus"""
+    start and end at different positions) and a partly filled last group; lock_lm=False adds the transition counts
+    xi as a third tensor-core product per position ([32 x 16] . [16 x 32], K = the warp's 16 sequences)"""
     monkeypatch.setenv("CML_DENSE_TC", "1")
     d = str(tmp_path)
     rng = np.random.default_rng(99)
     files = {}
     for sub in ("o", "p"):
         os.makedirs(os.path.join(d, sub))
-        files[sub] = write_small_cipher(os.path.join(d, sub), np.random.default_rng(99), n_lines=53, lens=(1, 70), weighted=True)
+        files[sub] = write_small_cipher(os.path.join(d, sub), np.random.default_rng(99), n_lines=53, lens=(1, 70), weighted=True,
+                                        lock_lm=lock_lm)
     del rng
     args = ["--train-cascade", "-HJ", "-M", "6"]
     rc, _, oerr = run(oracle_bin, [*args, f"--history={d}/h.o", *files["o"]])
@@ -252,5 +255,6 @@ def test_tensor_core_sweeps_match_oracle(cli, oracle_bin, tmp_path, monkeypatch)
     assert rc == 0, err
     assert "3xTF32 tensor-core sweeps" in err, err
     _close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), 1e-4)
-    compare_wfst_text(open(os.path.join(d, "p", "channel.fst.trained")).read(),
-                      open(os.path.join(d, "o", "channel.fst.trained")).read(), 2e-3, ln_floor=-60.0)
+    for name in ("channel.fst.trained", "lm.wfsa.trained"):
+        compare_wfst_text(open(os.path.join(d, "p", name)).read(), open(os.path.join(d, "o", name)).read(), 2e-3,
+                          ln_floor=-60.0)
