@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="cipher: force the lattice (sparse) path")
     ap.add_argument("--no-sparse-leg", action="store_true", help="skip the extra lattice-path measurement")
+    ap.add_argument("--unlock-lm", action="store_true",
+                    help="cipher: make the bigram LM trainable too (transition counts xi are then part of the E-step)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -234,6 +236,11 @@ def main():
     if rank == 0:
         shutil.rmtree(shared, ignore_errors=True)
         w = make_workload(a.workload, a.scale * world, shared)
+        if a.unlock_lm and a.workload == "cipher":
+            lm = w["files"][1]
+            txt = open(lm).read().replace("!))", "))")
+            open(lm, "w").write(txt)
+            config["workload"] += " (LM unlocked: transitions trainable)"
         json.dump(w, open(os.path.join(shared, "workload.json"), "w"))
     if world > 1:
         dist.barrier()

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kDW * 32) k_fb_dense(DenseArgs A) {
 // registers.  Forward and backward are two launches of the same kernel (B operand = T or T^T, emission applied
 // after / before the product); the expected counts are a third, position-parallel launch (one warp per sequence,
 // the pair's private gamma table) -- 16 sequences per warp would collide on the count cells.
-// Used for fp32 contexts with a locked transition model (no xi) and >= 16,384 sequences (CML_DENSE_TC=1 forces it):
+// Used for fp32 contexts with >= 16,384 sequences (CML_DENSE_TC=1 forces it, =0 forbids it):
 // with the 2,000 lines of the bench corpus there would be 125 warps for 148 SMs.  This is the legacy warp-level MMA
 // path, not tcgen05: a 16-row tile per warp keeps the serial chain of a sequence inside one warp's registers, where
 // a 128-row tcgen05 tile would need a TMEM -> register -> shared-memory round trip per position.
