@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(kSW * 32) k_fb_sparse(SparseArgs A) {
     }
   }
   __syncthreads();
-  if (XI)
+  if constexpr (XI)
     for (uint32_t c = threadIdx.x; c < SP * SP; c += blockDim.x) {
       const uint32_t sl = A.t_slot[c];
       if (sl == kNone) continue;
