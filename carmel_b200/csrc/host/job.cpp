@@ -79,6 +79,17 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   job.train_cascade = trainc;
   if (trainc) flags[(unsigned)'t'] = true;
   if (crp) {
+    // Options of carmel's sampler (carmel.cc:268-302) that change what is sampled and that this path does not
+    // build: refuse them instead of training something else under the same command line.
+    static const char* const not_built[] = {"expectation", "random-start", "include-self", "crp-restarts",
+                                            "crp-argmax-final", "crp-argmax-sum", "init-em", "em-p0",
+                                            "init-from-p0", "prior-inference-stddev", "prior-inference-global",
+                                            "prior-inference-restart-fresh"};
+    for (const char* k : not_built)
+      if (lopt.count(k)) {
+        err << "carmel-b200: --" << k << " is not implemented on the --crp path\n";
+        return -11;
+      }
     GibbsOpts& g = job.gopt;
     g.enabled = true;
     g.iter = lopt["crp"].empty() ? topt.max_iter : (uint32_t)std::atol(lopt["crp"].c_str());

@@ -83,3 +83,14 @@ def test_random_cascades_bit_exact(oracle_bin, cli, tmp_path, seed):
     rc, _, err2 = run(cli, ["--train-cascade", c, fa, fb, "--trellis-only", f"--dump-trellis={tmp_path}/p"])
     assert rc == 0, err2
     assert filecmp.cmp(f"{tmp_path}/o", f"{tmp_path}/p", shallow=False)
+
+
+@pytest.mark.parametrize("opt", ["--expectation", "--random-start", "--crp-restarts=2", "--init-em=3",
+                                 "--crp-argmax-final", "--prior-inference-stddev=0.1"])
+def test_unbuilt_sampler_options_are_refused(cli, tmp_path, opt):
+    """Sampler options of the reference (carmel.cc:268-302) that change what is sampled and that this
+    path does not build must fail loudly, before any training, rather than be ignored."""
+    paths = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    rc, _, err = run(cli, ["--crp=2", opt, *paths])
+    assert rc != 0
+    assert "not implemented on the --crp path" in err
