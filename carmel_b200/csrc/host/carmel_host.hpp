@@ -16,6 +16,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <random>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -145,7 +146,19 @@ struct TrainOpts {
   int lane_min = -1;                // --lane-min=n / --no-lane : CML_OPT_LANE_MIN (-1 = library default)
   int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
+  uint32_t ran_restarts = 0;        // -! n : additional random starts (train.cc:553-667)
+  uint32_t final_restart = 0;       // --final-restart=N : restart index at which the tolerance reaches its final value
+  double ln_restart_tolerance = kNegInf, ln_final_restart_tolerance = kNegInf;  // --restart-tolerance= --final-restart-tolerance= (none: accept all)
+  uint64_t seed = 1;                // -R seed : the restarts' generator (the reference seeds boost's lagged Fibonacci; draws differ)
   TrainOpts();
+};
+// WFST::random_restart_acceptor (fst.h:999-1044): a further start must be, after its first iteration, within a
+// tolerance of the first start's first iteration
+struct RestartAcceptor {
+  double ln_best_start = 0, ln_tolerance, ln_final_tolerance, n;
+  RestartAcceptor(double final_at_n, double ln_tol, double ln_final_tol);
+  double ln_likelihood_ratio(uint32_t i) const;
+  bool accept(double ln_this_start, uint32_t restart_i, std::ostream& o);
 };
 struct IterRecord {
   uint32_t iter;
@@ -217,6 +230,7 @@ struct TrainJob {
   std::vector<uint64_t> g_base;  // sample slot base of every resident example
   uint32_t g_n_norms = 0;
   void write_back();
+  void random_restart(std::mt19937_64& rng);
   void write_outputs(std::ostream& out);  // trained transducer(s) as carmel writes them
   void finish();
   void ok(int rc) const;

@@ -50,7 +50,9 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
           break;
         case 'o': topt.rate_growth = std::max(1., std::atof(arg.c_str())); break;
         case 'F': job.outfile = arg; break;
-        default: break;  // -R seed etc.: accepted, unused on this path
+        case '!': topt.ran_restarts = (uint32_t)std::atol(arg.c_str()); break;
+        case 'R': topt.seed = std::strtoull(arg.c_str(), nullptr, 10); break;
+        default: break;  // accepted, unused on this path
       }
       continue;
     }
@@ -110,6 +112,13 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   }
   if (files.size() < 2) return -9;
   topt.weight_is_prior = flags[(unsigned)'U'];
+  {
+    double w = 0;
+    if (lopt.count("restart-tolerance") && parse_weight(lopt["restart-tolerance"].c_str(), w)) topt.ln_restart_tolerance = w;
+    if (lopt.count("final-restart-tolerance") && parse_weight(lopt["final-restart-tolerance"].c_str(), w))
+      topt.ln_final_restart_tolerance = w;
+    if (lopt.count("final-restart")) topt.final_restart = (uint32_t)std::atol(lopt["final-restart"].c_str());
+  }
   if (lopt.count("float")) topt.precision = 32;
   if (lopt.count("scaled")) topt.space = CML_SPACE_SCALED;
   if (lopt.count("no-ell")) topt.no_ell = true;

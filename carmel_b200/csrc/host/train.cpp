@@ -432,6 +432,54 @@ void TrainJob::write_back() {  // device parameters -> transducer arcs
   }
 }
 
+// cascade.random_restart (cascade.h:398-411): WFST::randomSet on every member that is normalised (state.h:84-102:
+// locked arcs keep their weight, the arcs of a tie group share one draw), then normalize
+void TrainJob::random_restart(std::mt19937_64& rng) {
+  std::vector<double> w(M.n_params);
+  ok(cml_get_params(ctx, w.data()));
+  std::unordered_map<uint32_t, double> tied;
+  std::uniform_real_distribution<double> u01(0., 1.);
+  for (uint32_t p = 0; p < M.n_params; ++p) {
+    if (M.param_group[p] == kNoGroup || M.param_tie[p] == kLocked) continue;
+    if (M.param_tie[p] == kNoGroup) {
+      w[p] = std::log(1. - u01(rng));  // (0,1]
+      continue;
+    }
+    auto it = tied.find(M.param_tie[p]);
+    if (it == tied.end()) it = tied.emplace(M.param_tie[p], std::log(1. - u01(rng))).first;
+    w[p] = it->second;
+  }
+  ok(cml_set_params(ctx, w.data()));
+  ok(cml_normalize_params(ctx));
+}
+
+// WFST::random_restart_acceptor (fst.h:999-1044).  All quantities are natural logs; +inf = accept anything.
+RestartAcceptor::RestartAcceptor(double final_at_n, double ln_tol, double ln_final_tol)
+    : ln_tolerance(ln_tol), ln_final_tolerance(ln_final_tol), n(final_at_n) {
+  const double inf = std::numeric_limits<double>::infinity();
+  if (!(ln_tolerance > kNegInf)) ln_tolerance = inf;  // a zero tolerance means none was given
+  if (!(ln_final_tolerance > kNegInf)) ln_final_tolerance = ln_tolerance;
+}
+double RestartAcceptor::ln_likelihood_ratio(uint32_t i) const {
+  if (i >= n) return ln_final_tolerance;
+  if (std::isinf(ln_tolerance)) return ln_tolerance;
+  return ln_tolerance + (ln_final_tolerance - ln_tolerance) * ((i - 1) / (n - 1));
+}
+bool RestartAcceptor::accept(double ln_this_start, uint32_t restart_i, std::ostream& o) {
+  if (restart_i == 0) {
+    ln_best_start = ln_this_start;
+    o << "Initial best start point ppx=" << format_base2(ln_this_start) << std::endl;
+    return true;
+  }
+  const double lr = ln_likelihood_ratio(restart_i);
+  const double ppr = w_root(ln_this_start - ln_best_start, std::fabs(ln_this_start));  // relative_perplexity_ratio
+  const bool r = lr > ppr;
+  o << "For restart " << restart_i << ", " << (r ? "accepting" : "rejecting") << " worse random start of "
+    << format_base2(ln_this_start) << " compared to " << format_base2(ln_best_start) << " with relative ppx ratio="
+    << format_weight(ppr) << " compared to target of " << format_weight(lr) << std::endl;
+  return r;
+}
+
 void TrainJob::finish() {
   if (!opt.history_file.empty()) {
     std::ofstream o(opt.history_file);
@@ -480,12 +528,19 @@ TrainResult const& TrainJob::run(std::ostream& log) {
     growth = 1;
   }
   bool have_good_weights = false;
+  const int SLOT_BEST = 0, SLOT_EM = 1;
+  // random restarts (-! n, train.cc:553-667 outer loop): every further start draws the unlocked parameters
+  // uniformly on (0,1], renormalises, and trains again; the best iteration of any start is kept
+  uint32_t ran_restarts = opt.ran_restarts;
+  RestartAcceptor ra(opt.final_restart ? opt.final_restart : opt.ran_restarts, opt.ln_restart_tolerance,
+                     opt.ln_final_restart_tolerance);
+  std::mt19937_64 restart_rng(opt.seed);
+  for (uint32_t restart_no = 0;; ++restart_no) {
   uint32_t train_iter = 0;
   double ln_last_change = std::log(10.);
   double ln_last_ppx = kInf;
   double learning_rate = 1;
   bool last_was_reset = false;
-  const int SLOT_BEST = 0, SLOT_EM = 1;
   for (;;) {
     const bool first_time = train_iter == 0;
     ++train_iter;
@@ -516,7 +571,10 @@ TrainResult const& TrainJob::run(std::ostream& log) {
     double ln_ratio;
     if (first_time) {
       log << std::endl;
-      log << "Initial best start point ppx=" << format_base2(ln_new_ppx) << std::endl;
+      if (!ra.accept(ln_new_ppx, restart_no, log)) {
+        log << "Random start was insufficiently promising; trying another." << std::endl;
+        break;  // to the next random restart
+      }
       ln_ratio = kNegInf;
     } else {
       // relative_perplexity_ratio (weight.h:247-249): (new/old)^(1/|ln new|)
@@ -562,6 +620,11 @@ TrainResult const& TrainJob::run(std::ostream& log) {
       break;
     }
     ln_last_ppx = ln_new_ppx;
+  }
+  if (ran_restarts == 0) break;
+  --ran_restarts;
+  random_restart(restart_rng);
+  log << "\nRandom restart - " << ran_restarts << " remaining.\n";
   }
   log << "Setting weights to model with lowest per-example-perplexity ( = "
          "prod[modelprob(example)]^(-1/num_examples) = 2^(-log_2(p_model(corpus))/N) = "

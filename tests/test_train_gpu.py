@@ -138,3 +138,42 @@ def test_random_cascades_match_oracle(cli, oracle_bin, tmp_path, seed):
     _history_close(read_history(f"{d}/h.p"), read_history(f"{d}/h.o"), 1e-6)
     for n in ("a.fst.trained", "b.fst.trained"):
         compare_wfst_text(open(os.path.join(d, "p", n)).read(), open(os.path.join(d, "o", n)).read(), 1e-5)
+
+
+def test_cluster_random_restarts(cli, tmp_path):
+    """`carmel -t -HJ -! n cluster.data cluster.fsa` (tutorial `commands:13`, golden log `commands.trace:109-`):
+    the first start is RNG-free and stops on the uniform saddle after 2 iterations (2^-258374, 2^-233284);
+    every random restart then escapes it (the golden log's restarts reach 2^-218162 ... 2^-224000), and the
+    weights kept are those of the best iteration of any start.  The draws themselves differ from the
+    reference's generator, so the restarts are checked through those properties, and for determinism under -R."""
+    data, fsa = stage(tmp_path, "cluster.data", "cluster.fsa")
+    rc, out, err = run(cli, ["-t", "-HJ", "-!", "3", "-R", "7", "-M", "40", data, fsa], timeout=600)
+    assert rc == 0, err
+    traj = trajectory_log2(err)
+    starts = [k for k, (i, _) in enumerate(traj) if i == 1]
+    assert len(starts) == 4
+    first = traj[:starts[1]]
+    _golden_traj(first, golden()["cluster_first_start"]["trajectory_log2"])
+    assert "Converged - maximum weight change less than 0.0001 after 2 iterations." in err
+    for n in (2, 1, 0):
+        assert f"Random restart - {n} remaining." in err
+    for r in (1, 2, 3):
+        assert f"For restart {r}, accepting worse random start of 2^" in err
+    best = first[-1][1]
+    for a, b in zip(starts[1:], starts[2:] + [len(traj)]):
+        run_ = [p for _, p in traj[a:b]]
+        assert all(y >= x - 1e-6 * abs(x) for x, y in zip(run_, run_[1:]))  # EM never lowers the likelihood
+        assert run_[-1] > first[-1][1] + 1000  # the restart left the saddle
+        best = max(best, run_[-1])
+    # the kept model is the best iteration of any start: 2^(-log2 p / N), N = 1121 examples
+    import re
+    m = re.search(r"2\^\(-log_2\(p_model\(corpus\)\)/N\) = 2\^([0-9.]+)", err)
+    n_ex = sum(1 for k, ln in enumerate(open(data)) if k % 2 == 0)
+    assert m and abs(float(m.group(1)) * n_ex + best) <= 1e-4 * abs(best)
+    # same seed -> same draws, same run; another seed -> other draws
+    rc, out2, err2 = run(cli, ["-t", "-HJ", "-!", "3", "-R", "7", "-M", "40", data, fsa], timeout=600)
+    assert rc == 0
+    _golden_traj(trajectory_log2(err2), traj)  # (count accumulation order on the GPU moves the last few ulps only)
+    compare_wfst_text(out2, out, 1e-6)
+    rc, _, err3 = run(cli, ["-t", "-HJ", "-!", "1", "-R", "8", "-M", "3", data, fsa], timeout=600)
+    assert rc == 0 and trajectory_log2(err3)[2][1] != traj[2][1]
