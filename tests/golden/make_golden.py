@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 TUT = os.path.join(REF, "carmel-tutorial")
 
 INPUTS = ["epron-jpron.fst", "epron-jpron.data", "cipher.wfsa", "cipher.fst", "cipher.data", "tagging.fsa",
-          "tagging.fst", "tagging.data", "cluster.fsa", "cluster.data"]
+          "tagging.fst", "tagging.data", "cluster.fsa", "cluster.data", "cat.fsa", "spellout.fst"]
 TRAINED = ["cipher.fst.trained", "cipher.wfsa.trained"]
 
 
@@ -53,10 +53,12 @@ def main():
                 runs.append([])
             runs[-1].append([it, v])
 
-    def run_starting(v0):
+    def run_starting(v0, nth=0):
         for r in runs:
             if abs(r[0][1] - v0) < 1e-9 * abs(v0):
-                return r
+                if nth == 0:
+                    return r
+                nth -= 1
         raise KeyError(v0)
     g = {
         "source": "carmel/carmel-tutorial/commands.trace (line numbers 1-based)",
@@ -69,6 +71,9 @@ def main():
         "cipher": {"lines": "6905-6950", "trajectory_log2": run_starting(-2245.63),
                    "composed_states": 57, "composed_arcs": 11511, "converged_at": 22},
         "cluster_first_start": {"lines": "112-114", "trajectory_log2": run_starting(-258374)[:2]},
+        # `--train-cascade -HJ -! 100 cluster.data cat.fsa spellout.fst`: the RNG-free first start
+        "cat_spellout_first_start": {"lines": "641-649", "trajectory_log2": run_starting(-258374, 1)[:3],
+                                     "composed_states": 4, "composed_arcs": 316, "converged_at": 3},
     }
     json.dump(g, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
     print({k: (len(v["trajectory_log2"]) if isinstance(v, dict) else v) for k, v in g.items()})

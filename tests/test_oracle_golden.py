@@ -67,3 +67,16 @@ def test_cluster_first_start(oracle_bin, tmp_path):
     rc, out, err = run(oracle_bin, ["-t", "-M", "2", data, fsa])
     assert rc == 0, err
     _check_traj(trajectory_log2(err)[:2], golden()["cluster_first_start"]["trajectory_log2"])
+
+
+def test_cat_spellout_cascade_first_start(oracle_bin, tmp_path):
+    """`--train-cascade -HJ cluster.data cat.fsa spellout.fst` (golden log `commands.trace:641-649`): the
+    composition is 4 states / 316 arcs, the uniform start sits on a saddle, and the cascade needs its third
+    iteration before it may stop."""
+    data, cat, spell = stage(tmp_path, "cluster.data", "cat.fsa", "spellout.fst")
+    rc, out, err = run(oracle_bin, ["--train-cascade", "-HJ", data, cat, spell])
+    assert rc == 0, err
+    g = golden()["cat_spellout_first_start"]
+    assert f"({g['composed_states']} states / {g['composed_arcs']} arcs)" in err
+    _check_traj(trajectory_log2(err), g["trajectory_log2"])
+    assert "Converged - per-example perplexity ratio exceeds 0.999 after 3 iterations." in err

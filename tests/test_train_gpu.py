@@ -177,3 +177,37 @@ def test_cluster_random_restarts(cli, tmp_path):
     compare_wfst_text(out2, out, 1e-6)
     rc, _, err3 = run(cli, ["-t", "-HJ", "-!", "1", "-R", "8", "-M", "3", data, fsa], timeout=600)
     assert rc == 0 and trajectory_log2(err3)[2][1] != traj[2][1]
+
+
+def test_cat_spellout_cascade_restarts(cli, tmp_path):
+    """`carmel --train-cascade -HJ -! n cluster.data cat.fsa spellout.fst` (tutorial `commands:14`, golden log
+    `commands.trace:641-`): first start = the golden three iterations (a cascade cannot stop before its third),
+    restarts leave the saddle (golden restart 1: 2^-264791 -> 2^-230800 -> 2^-228829 ...), and both members are
+    written from the best iteration of any start."""
+    data, cat, spell = stage(tmp_path, "cluster.data", "cat.fsa", "spellout.fst")
+    rc, out, err = run(cli, ["--train-cascade", "-HJ", "-!", "2", "-R", "5", "-M", "30", data, cat, spell], timeout=600)
+    assert rc == 0, err
+    g = golden()["cat_spellout_first_start"]
+    assert f"({g['composed_states']} states / {g['composed_arcs']} arcs)" in err
+    traj = trajectory_log2(err)
+    starts = [k for k, (i, _) in enumerate(traj) if i == 1]
+    assert len(starts) == 3
+    _golden_traj(traj[:starts[1]], g["trajectory_log2"])
+    assert "Converged - per-example perplexity ratio exceeds 0.999 after 3 iterations." in err
+    best = traj[starts[1] - 1][1]
+    for a, b in zip(starts[1:], starts[2:] + [len(traj)]):
+        run_ = [p for _, p in traj[a:b]]
+        assert all(y >= x - 1e-6 * abs(x) for x, y in zip(run_, run_[1:]))
+        assert run_[-1] > best + 1000
+    finals = [traj[b - 1][1] for b in starts[1:] + [len(traj)]]
+    import re
+    m = re.search(r"2\^\(-log_2\(p_model\(corpus\)\)/N\) = 2\^([0-9.]+)", err)
+    assert m and abs(float(m.group(1)) * 1121 + max(finals)) <= 1e-4 * abs(max(finals))
+    # the written members are normalised models of the kept start: retraining from them for one iteration
+    # reproduces (at least) the kept likelihood
+    for f in (cat, spell):
+        assert os.path.exists(f + ".trained")
+    rc, _, err2 = run(cli, ["--train-cascade", "-HJ", "-M", "1", data, cat + ".trained", spell + ".trained"], timeout=600)
+    assert rc == 0, err2
+    m2 = re.search(r"probability=2\^(-?[0-9.e+-]+)", err2)
+    assert m2 and float(m2.group(1)) >= max(finals) - 1e-4 * abs(max(finals))
