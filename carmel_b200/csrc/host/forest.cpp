@@ -365,15 +365,39 @@ std::string fmt_delta(double d, uint64_t idx) {  // em.hpp:60-67
 }
 }  // namespace
 
-// graehl/shared/em.hpp:107-216 overrelaxed_em as forest-em calls it (growth factor 1, no random restarts)
+// forests::randomize (forest-em.hpp:393-399) = NormalizeGroups::init_random (normalize.hpp:212-238): every member of
+// a normalisation group gets a uniform draw on (0,1], divided by the group's sum; rules in no group keep their weight
+void ForestJob::randomize(std::mt19937_64& rng) {
+  ok(cml_forests_get_params(ctx, ln_w.data()));
+  std::uniform_real_distribution<double> u01(0., 1.);
+  for (uint64_t g = 0; g < groups.size(); ++g) {
+    double sum = 0;
+    for (uint64_t k = groups.off[g]; k < groups.off[g + 1]; ++k) {
+      const double v = 1. - u01(rng);
+      ln_w[groups.members[k]] = v;
+      sum += v;
+    }
+    for (uint64_t k = groups.off[g]; k < groups.off[g + 1]; ++k) ln_w[groups.members[k]] = std::log(ln_w[groups.members[k]] / sum);
+  }
+  ok(cml_forests_set_params(ctx, ln_w.data()));
+}
+
+// graehl/shared/em.hpp:107-216 overrelaxed_em as forest-em calls it (growth factor 1)
 double ForestJob::run(std::ostream& logs) {
   if (opt.parse_only) return 0;
   prepare();
   best_alp = -HUGE_VAL;
   if (opt.max_iter == 0) return best_alp;
   const double rel_eps = opt.converge_ratio;
-  bool very_first_time = true, first_time = true;
+  bool very_first_time = true;
   const double N = (double)total_forests;
+  // random restarts (-r n): best-weights bookkeeping exists only then (forest-em.hpp:363-365,660-672)
+  unsigned ran_restarts = opt.random_restarts;
+  const bool save_best_enable = ran_restarts > 0;
+  std::vector<double> best_w;
+  std::mt19937_64 rng(opt.random_seed);
+  for (;;) {
+  bool first_time = true;
   unsigned train_iter = 0;
   double max_delta = 0, last_alp = -HUGE_VAL;
   uint64_t max_index = 0;
@@ -391,6 +415,10 @@ double ForestJob::run(std::ostream& logs) {
     if (new_alp > best_alp || very_first_time) {
       logs << " (new best)";
       best_alp = new_alp;
+      if (save_best_enable) {  // save_best: the parameters this estimate was made with
+        best_w.resize(ln_w.size());
+        ok(cml_forests_get_params(ctx, best_w.data()));
+      }
     }
     very_first_time = false;
     const double dpp = new_alp - last_alp;
@@ -415,9 +443,18 @@ double ForestJob::run(std::ostream& logs) {
     }
     last_alp = new_alp;
   }
+  if (ran_restarts == 0) break;
+  --ran_restarts;
+  logs << "\nRandom restart - " << ran_restarts << " remaining.\n";
+  randomize(rng);
+  }
   logs << "\nSetting weights to model with best ";
   print_alp(logs, N, best_alp);
   logs << std::endl;
+  if (save_best_enable && !best_w.empty()) {  // restore_best
+    ok(cml_forests_set_params(ctx, best_w.data()));
+    logs << std::endl;
+  }
   return best_alp;
 }
 
@@ -474,7 +511,8 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
       {"prior-counts-per", 'p'},  {"add-k-smoothing", 'k'},      {"zero-zerocounts", 'z'}, {"initial-1-params", 'u'},
       {"normalize-initial", 'N'}, {"use-double-precision", 'U'}, {"human-probs", 'H'},     {"log-level", 'L'},
       {"out-per-forest-inside-sum", 'S'}, {"max-forest-nodes", 'm'}, {"max-normgroup-size", 'M'}, {"prealloc-params", 'P'},
-      {"tempfile-prefix", 't'},   {"forest-tick-period", 'T'},   {"watch-period", 'W'},    {"random-seed", 's'}};
+      {"tempfile-prefix", 't'},   {"forest-tick-period", 'T'},   {"watch-period", 'W'},    {"random-seed", 's'},
+      {"random-restarts", 'r'}};
   ForestOpts& a = job.opt;
   try {
     for (int i = 1; i < argc; ++i) {
@@ -535,7 +573,9 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
         case 'p': a.prior_counts = std::atof(need().c_str()); break;
         case 'k': a.add_k_smoothing = std::atof(need().c_str()); break;
         case 'L': a.log_level = (unsigned)std::atol(need().c_str()); break;
-        case 'm': case 'M': case 'P': case 't': case 'T': case 'W': case 's': need(); break;  // sizing / cosmetic: accepted, unused
+        case 'r': a.random_restarts = (unsigned)std::atol(need().c_str()); break;
+        case 's': a.random_seed = std::strtoull(need().c_str(), nullptr, 10); break;
+        case 'm': case 'M': case 'P': case 't': case 'T': case 'W': need(); break;  // sizing / cosmetic: accepted, unused
         case 'z': a.zero_zerocounts = true; break;
         case 'u': a.initial_1_params = true; break;
         case 'N': a.normalize_initial = true; break;

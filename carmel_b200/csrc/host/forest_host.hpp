@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <iosfwd>
 #include <map>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,8 @@ struct ForestOpts {
   bool double_precision = false;       // -U
   bool human_probs = false;            // -H
   unsigned log_level = 1;              // -L
+  unsigned random_restarts = 0;        // -r  (forest-em-params.hpp:103): further starts from random parameters
+  uint64_t random_seed = 1;            // -s  : the restarts' generator (draws differ from the reference's)
   int device = 0;                      // --gpu=n
   int shard_rank = 0, shard_count = 1;  // --shard=r/N
   int layout = CML_FOREST_LAYOUT_AUTO;  // --layout=auto|group|thread (device layout family, see cml_forests_set_layout)
@@ -90,6 +93,7 @@ struct ForestJob {
   double estimate(bool first_time, std::ostream& log, uint64_t* n_used = nullptr);
   void maximize(std::ostream& log, double& max_delta, uint64_t& max_index);
   double run(std::ostream& log);  // overrelaxed_em
+  void randomize(std::mt19937_64& rng);
   void write_outputs(std::ostream& log);
   void ok(int rc) const;
 };

@@ -181,3 +181,47 @@ def test_errors(fem, tmp_path):
     assert rc == 1 and "cyclic" in err
     rc, out, err = run(fem, ["-n", f"{d}/n", "-i", "2"])
     assert rc == 1 and "Missing forests-file" in err
+
+
+def test_random_restarts(fem, tmp_path):
+    """forest-em -r n (forest-em-params.hpp:103, em.hpp:114-214, forest-em.hpp:393-399,660-672): the first start
+    is the run without -r; every further start draws each normalisation group's members uniformly on (0,1] and
+    normalises them; the parameters written are those of the best iteration of any start.  The draws differ from
+    the reference's generator, so the restarts are checked through these properties."""
+    d = str(tmp_path)
+    rng = np.random.default_rng(77)
+    f, n = f"{d}/f", f"{d}/n"
+    open(f, "w").write("\n".join(random_forest(rng, 40, depth=5) for _ in range(200)) + "\n")
+    open(n, "w").write(random_normgroups(rng, 40, leave_out=0))  # every rule is in a group: all starts are normalised
+    args = ["-U", "-f", f, "-n", n, "-i", "10"]
+    rc, _, err0 = run(fem, [*args, "-o", f"{d}/w0", f"--history={d}/h0"])
+    assert rc == 0, err0
+    rc, _, err = run(fem, [*args, "-r", "3", "-s", "11", "-o", f"{d}/w", f"--history={d}/h"])
+    assert rc == 0, err
+    h0, h = _hist(f"{d}/h0"), _hist(f"{d}/h")
+    starts = [k for k, row in enumerate(h) if row[0] == 1] + [len(h)]
+    assert len(starts) == 5
+    for n_left in (2, 1, 0):
+        assert f"Random restart - {n_left} remaining." in err
+    assert len(h0) == starts[1]
+    for a, b in zip(h0, h[:starts[1]]):
+        assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * abs(a[1])
+    firsts = set()
+    for a, b in zip(starts, starts[1:]):
+        alps = [row[1] for row in h[a:b]]
+        assert all(y >= x - 1e-9 * abs(x) for x, y in zip(alps, alps[1:]))  # EM never lowers the likelihood
+        firsts.add(round(alps[0], 9))
+    assert len(firsts) == 4  # four different starting points
+    best = max(row[1] for row in h)
+    # the written parameters are the best iteration's: one more estimate from them gives that likelihood
+    rc, _, err1 = run(fem, ["-U", "-f", f, "-n", n, "-I", f"{d}/w", "-i", "1", f"--history={d}/h1"])
+    assert rc == 0, err1
+    assert abs(_hist(f"{d}/h1")[0][1] - best) <= 1e-8 * abs(best)
+    # same seed: same draws; another seed: other draws
+    rc, _, err2 = run(fem, [*args, "-r", "3", "-s", "11", f"--history={d}/h2"])
+    assert rc == 0, err2
+    h2 = _hist(f"{d}/h2")
+    assert len(h2) == len(h) and all(abs(a[1] - b[1]) <= 1e-9 * abs(a[1]) for a, b in zip(h, h2))
+    rc, _, err3 = run(fem, [*args, "-r", "1", "-s", "12", f"--history={d}/h3"])
+    assert rc == 0, err3
+    assert abs(_hist(f"{d}/h3")[starts[1]][1] - h[starts[1]][1]) > 1e-9
