@@ -19,7 +19,7 @@ SPACE_LOG, SPACE_SCALED = 0, 1
 NO_GROUP = 0xFFFFFFFF
 LOCKED_GROUP = 0
 
-OPT_ARC_COUNTS, OPT_NO_ELL, OPT_LANE_MIN, OPT_NO_COUNTS = 1, 2, 3, 4
+OPT_ARC_COUNTS, OPT_NO_ELL, OPT_LANE_MIN, OPT_NO_COUNTS, OPT_NO_FACTOR, OPT_NO_WIDE = 1, 2, 3, 4, 5, 6
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CYCLE, ERR_NODERIV, ERR_NOT_DENSE = 0, -1, -2, -3, -4, -5, -6
 
 _u32p = C.POINTER(C.c_uint32)
@@ -124,6 +124,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.cml_layout_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_lane_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
+    lib.cml_wide_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 5
     lib.cml_count_slots.argtypes = [vp]
     lib.cml_count_slots.restype = C.c_uint64
     lib.cml_get_counts.argtypes = [vp, _f64p, C.c_uint64]
@@ -338,6 +339,12 @@ class Context:
         v = [C.c_uint64() for _ in range(4)]
         self._check(self.lib.cml_lane_stats(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("lane_examples", "lane_arcs", "lane_records", "tiles"), (int(x.value) for x in v)))
+
+    def wide_stats(self) -> dict:
+        v = [C.c_uint64() for _ in range(5)]
+        self._check(self.lib.cml_wide_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("wide_examples", "wide_arcs", "wide_records", "arc_classes", "state_classes"),
+                        (int(x.value) for x in v)))
 
     def count_slots(self) -> int:
         return int(self.lib.cml_count_slots(self.h))

@@ -8,6 +8,7 @@
 #include "cml_kernels_ell.cuh"
 #include "cml_kernels_fb.cuh"
 #include "cml_kernels_lane.cuh"
+#include "cml_kernels_wide.cuh"
 
 // ---- example classes ------------------------------------------------------------------------------
 // ELL classes (scaled space only): one example per group of 4/8/16/32 lanes, level-sliced ELL layout.
@@ -49,6 +50,12 @@ struct Batch {
   uint32_t ell_ring[NELL] = {0};
   DevArray<unsigned char> alpha_g;
   DevArray<int> lvl_exp;
+  // --- wide part (k_fb_wide: one lattice per warp, lane = state of the level; shares edesc / lvl_meta / ell_in /
+  //     ell_out / alpha_g / lvl_exp with the ELL part, records carry arc-CLASS ids, states carry a state class)
+  uint64_t wide_ex = 0, wide_arcs = 0, wide_records = 0;
+  DevArray<uint32_t> wide_list;      // indices into edesc, longest first
+  DevArray<uint32_t> ell_vcls;       // [ELL state slot] state class (v id) of the wide examples' states
+  uint32_t wide_ring = 0;
   // --- lane part (k_fb_lane: one lattice per lane, tiles of 32)
   uint64_t lane_ex = 0, lane_arcs = 0, lane_records = 0;
   uint32_t lane_tiles = 0;
@@ -58,6 +65,7 @@ struct Batch {
   DevArray<double> lane_weight;
   DevArray<unsigned char> lane_alpha;
   DevArray<int> lane_lvle;
+  DevArray<uint32_t> lane_vcls;      // [state ordinal][lane] state class (v id), same indexing as lane_alpha
   cudaEvent_t ev_fb0 = nullptr, ev_fb1 = nullptr;  // bracket this batch's forward-backward kernels
   uint32_t n_fb_kernels = 0;
   ~Batch() {
@@ -125,6 +133,8 @@ struct cml_ctx {
   int opt_no_ell = 0;      // CML_OPT_NO_ELL: force the CSR kernels (tests)
   int opt_lane_min = 16384;  // CML_OPT_LANE_MIN: eligible lattices needed before the lane kernel is used (0 = never)
   int opt_no_counts = 0;     // CML_OPT_NO_COUNTS: profiling only, the sweeps skip their count REDs (lane kernel)
+  int opt_no_factor = 0;     // CML_OPT_NO_FACTOR: keep per-arc weight records (no arc classes; round-1 kernels)
+  int opt_no_wide = 0;       // CML_OPT_NO_WIDE: wide lattices stay on the k_fb_ell classes
 
   // model
   bool have_model = false, trivial = true;
@@ -160,6 +170,22 @@ struct cml_ctx {
   std::vector<uint32_t> h_chain_off, h_chain_param, h_param_tie;
   std::vector<double> h_arc_prior;
   std::unique_ptr<DenseState> dense;  // non-null: the E-step runs over dense-state sequences
+
+  // ---- factored arc weights (wide / lane kernels; see "arc classes" in cml_device.cu) ----------------------
+  // model level (same on every rank): class = a multiset of parameters; every arc has a full class (its chain),
+  // and, when its chain has >= 2 parameters, a state part (the last parameter) and a rest part.
+  bool factored = false;
+  std::vector<uint32_t> cls_off, cls_param;     // class -> parameters (CSR)
+  std::vector<uint32_t> cls_slot;               // class -> count slot (kPadNone: nothing trainable)
+  std::vector<uint32_t> arc_fcls, arc_ucls, arc_vcls;  // per arc-table entry (arc_vcls = kPadNone: no state part)
+  // context level (append-only as batches arrive): classes referenced by lattice ARC records (a ids) and by
+  // lattice STATES (v ids)
+  std::vector<uint32_t> a_of_cls, v_of_cls, a_list, v_list;
+  std::vector<uint64_t> a_occ, v_occ;           // occurrences in the resident lattices (hot-slot statistics)
+  bool cls_dirty = true;                        // device tables must be rebuilt
+  int any_a_slot = 0;                           // some arc class has a count slot
+  DevArray<uint32_t> a_off, a_param, a_slot, v_off, v_param, v_slot;
+  DevArray<unsigned char> a_w, v_w;             // Real[n + 1] linear weights (last = 0 / 1 padding entry)
 
   // --crp Gibbs sampling state (cml_gibbs.cu)
   bool have_gibbs = false;

@@ -10,6 +10,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "cml_ctx.cuh"
 #include "cml_kernels_model.cuh"
@@ -120,6 +121,14 @@ extern "C" int cml_set_option(cml_ctx* ctx, int option, int value) {
     case CML_OPT_NO_COUNTS:
       ctx->opt_no_counts = value;
       return CML_OK;
+    case CML_OPT_NO_FACTOR:
+      CML_REQUIRE(!ctx->have_model, CML_ERR_STATE, "CML_OPT_NO_FACTOR must be set before cml_set_model");
+      ctx->opt_no_factor = value;
+      return CML_OK;
+    case CML_OPT_NO_WIDE:
+      CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "CML_OPT_NO_WIDE must be set before cml_add_trellises");
+      ctx->opt_no_wide = value;
+      return CML_OK;
     default: ctx->err = "unknown option"; return CML_ERR_ARG;
   }
 }
@@ -212,6 +221,93 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
       slot_prior.push_back(0.);
     }
     if (!m->arc_prior) slot_prior.clear();
+  }
+
+  // Arc classes (factored arc weights, SCALED-space wide / lane kernels).  A class is a multiset of parameters;
+  // its weight is their product and its count slot is the slot of its unlocked parameters.  Every arc gets a FULL
+  // class (its whole chain) and, when the chain has two or more parameters, a STATE part (the chain's last
+  // parameter: for LM o channel cascades the channel arc) and a REST part.  When all arcs entering a lattice state
+  // have the same state part, the flattener stores it once per state and the arc records carry the rest part:
+  // alpha[dst] = V[state part] * sum alpha[src] * U[rest part], and the expected count of the state part is the
+  // state posterior (one accumulation per state instead of one per arc; cascade.h:286-325 adds an arc's count
+  // to every parameter of its chain, so the per-parameter totals are unchanged).  Class ids and slots depend on
+  // the model only, so every rank of a multi-GPU job builds the same reduce buffer.
+  {
+    ctx->factored = !ctx->opt_no_factor;
+    ctx->cls_off.assign(1, 0);
+    ctx->cls_param.clear();
+    ctx->cls_slot.clear();
+    ctx->arc_fcls.assign(m->n_arcs, kPadNone);
+    ctx->arc_ucls.assign(m->n_arcs, kPadNone);
+    ctx->arc_vcls.assign(m->n_arcs, kPadNone);
+    {
+      if (!merge || !ctx->factored) {  // class a = arc a with the arc's own slot, no state parts
+        ctx->factored = false;
+        for (uint32_t a = 0; a < m->n_arcs; ++a) {
+          if (trivial)
+            ctx->cls_param.push_back(a);
+          else
+            ctx->cls_param.insert(ctx->cls_param.end(), m->chain_param + m->chain_off[a],
+                                  m->chain_param + m->chain_off[a + 1]);
+          ctx->cls_off.push_back((uint32_t)ctx->cls_param.size());
+          ctx->cls_slot.push_back(arc_slot[a]);
+          ctx->arc_fcls[a] = ctx->arc_ucls[a] = a;
+        }
+      } else {
+        std::unordered_map<std::string, uint32_t> cls_ids;
+        std::map<std::vector<uint32_t>, uint32_t> slot_ids;  // unlocked parameter set -> slot (existing slots first)
+        for (uint32_t sl = 0; sl + 1 < slot_off.size(); ++sl)
+          if (slot_off[sl + 1] > slot_off[sl]) {
+            std::vector<uint32_t> k(slot_param.begin() + slot_off[sl], slot_param.begin() + slot_off[sl + 1]);
+            std::sort(k.begin(), k.end());
+            slot_ids.emplace(std::move(k), sl);
+          }
+        std::vector<uint32_t> key, ukey;
+        auto intern = [&](const uint32_t* p, size_t n) -> uint32_t {
+          key.assign(p, p + n);
+          std::sort(key.begin(), key.end());
+          std::string k((const char*)key.data(), key.size() * sizeof(uint32_t));
+          auto ins = cls_ids.emplace(std::move(k), (uint32_t)ctx->cls_slot.size());
+          if (!ins.second) return ins.first->second;
+          ctx->cls_param.insert(ctx->cls_param.end(), key.begin(), key.end());
+          ctx->cls_off.push_back((uint32_t)ctx->cls_param.size());
+          ukey.clear();
+          for (uint32_t q : key)
+            if (m->param_tie[q] != CML_LOCKED_GROUP) ukey.push_back(q);
+          uint32_t sl = kPadNone;
+          if (!ukey.empty()) {
+            auto it = slot_ids.find(ukey);  // (keys: sorted unlocked parameter sets)
+            if (it == slot_ids.end()) {
+              sl = n_slots++;
+              slot_ids.emplace(ukey, sl);
+              slot_param.insert(slot_param.end(), ukey.begin(), ukey.end());
+              slot_off.push_back((uint32_t)slot_param.size());
+              if (!slot_prior.empty()) slot_prior.push_back(0.);
+            } else
+              sl = it->second;
+          }
+          ctx->cls_slot.push_back(sl);
+          return ins.first->second;
+        };
+        for (uint32_t a = 0; a < m->n_arcs; ++a) {
+          const uint32_t* c = m->chain_param + m->chain_off[a];
+          const size_t n = m->chain_off[a + 1] - m->chain_off[a];
+          ctx->arc_fcls[a] = intern(c, n);
+          if (n >= 2) {
+            ctx->arc_vcls[a] = intern(c + n - 1, 1);
+            ctx->arc_ucls[a] = intern(c, n - 1);
+          } else
+            ctx->arc_ucls[a] = ctx->arc_fcls[a];
+        }
+      }
+    }
+    ctx->a_of_cls.assign(ctx->cls_slot.size(), kPadNone);
+    ctx->v_of_cls.assign(ctx->cls_slot.size(), kPadNone);
+    ctx->a_list.clear();
+    ctx->v_list.clear();
+    ctx->a_occ.clear();
+    ctx->v_occ.clear();
+    ctx->cls_dirty = true;
   }
 
   cudaStream_t s = ctx->stream;
@@ -349,6 +445,8 @@ struct FlatEx {  // per-example facts discovered in pass 1
   uint32_t width = 0;
   bool lane_ok = false;    // narrow, every arc spans exactly one level: eligible for the lane-per-lattice kernel
   bool lane = false;       // ... and chosen for it
+  bool wide_ok = false;    // levels of 9..32 states, degrees <= 255: eligible for the warp-per-lattice kernel
+  bool wide = false;       // ... and chosen for it (laid out like an ELL example, records carry arc classes)
 };
 
 inline uint32_t pow2ceil(uint32_t v) {
@@ -360,6 +458,7 @@ inline uint32_t pow2ceil(uint32_t v) {
 struct Scratch {  // per-thread temporaries
   std::vector<uint64_t> occ;
   std::vector<uint32_t> indeg, queue, cnt, lvl_first, lvl_width, lvl_d, lvl_o, lvl_min, lvl_max, ref_of, icur, ocur, order;
+  std::vector<uint32_t> vstate, occ_a, occ_v;  // factored records: state part per state; class occurrence counts
 };
 
 // pass 1: longest-path levels via Kahn's algorithm; level_of[] / local_of[]; ELL eligibility
@@ -446,6 +545,25 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
   fx.lane_ok = maxspan <= 1 && 2 * width <= (uint32_t)cmlk::kLaneRing && n < (1u << 30);
   fx.ell = gc >= 0 && width <= 255 && maxdeg <= 255 && maxspan <= 15 && fx.ring_need <= 4096 &&
            in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
+  fx.wide_ok = width > 8 && width <= 32 && maxdeg <= 255 && maxspan <= 15 && fx.ring_need <= 4096 &&
+               in_pad <= arcs + arcs / 2 + 64 && out_pad <= arcs + arcs / 2 + 64;
+}
+
+// State part of every lattice state (factored records): the common arc_vcls of its incoming arcs, or kPadNone.
+// vs[] is indexed by the caller's state ids.
+void state_parts(uint32_t n, const uint32_t* off, const uint32_t* dst, const uint32_t* id,
+                 const std::vector<uint32_t>& arc_vcls, std::vector<uint32_t>& vs) {
+  constexpr uint32_t kUnset = 0xFFFFFFFEu;
+  vs.assign(n, kUnset);
+  for (uint32_t k = 0, e = off[n]; k < e; ++k) {
+    const uint32_t d = dst[k], v = arc_vcls[id[k]];
+    if (vs[d] == kUnset)
+      vs[d] = v;
+    else if (vs[d] != v)
+      vs[d] = kPadNone;
+  }
+  for (uint32_t s = 0; s < n; ++s)
+    if (vs[s] == kUnset) vs[s] = kPadNone;
 }
 
 }  // namespace
@@ -494,6 +612,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::atomic<int> bad_cycle{0}, bad_range{0};
   std::vector<uint64_t> batch_occ(ctx->n_slots, 0);  // arcs per count slot in this batch
+  const size_t n_cls = ctx->cls_slot.size();
+  std::vector<uint64_t> batch_occ_a(n_cls, 0), batch_occ_v(n_cls, 0);  // class occurrences (wide / lane examples)
   std::mutex occ_mutex;
   auto parallel_for = [&](auto&& body) {
     std::atomic<uint64_t> next{0};
@@ -504,9 +624,11 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         if (e0 >= n_ex) break;
         for (uint64_t e = e0; e < std::min(n_ex, e0 + 256); ++e) body(e, S);
       }
-      if (!S.occ.empty()) {  // merge this thread's slot occurrence counts
+      if (!S.occ.empty() || !S.occ_a.empty()) {  // merge this thread's occurrence counts
         std::lock_guard<std::mutex> lk(occ_mutex);
         for (size_t i = 0; i < S.occ.size(); ++i) batch_occ[i] += S.occ[i];
+        for (size_t i = 0; i < S.occ_a.size(); ++i) batch_occ_a[i] += S.occ_a[i];
+        for (size_t i = 0; i < S.occ_v.size(); ++i) batch_occ_v[i] += S.occ_v[i];
       }
     };
     std::vector<std::thread> th;
@@ -529,11 +651,6 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     levelize(n, off, dst, &bt->h_level_of[state_base[e]], &bt->h_local_of[state_base[e]], fx[e], S, want_ell);
     if (fx[e].cycle) bad_cycle = 1;
     bt->h_nlevels[e] = fx[e].n_levels;
-    if (S.occ.empty()) S.occ.assign(ctx->n_slots, 0);
-    for (uint32_t k = 0; k < off[n]; ++k) {
-      const uint32_t sl = ctx->h_arc_slot[id[k]];
-      if (sl != kPadNone) ++S.occ[sl];
-    }
   });
   CML_REQUIRE(!bad_range, CML_ERR_ARG, "trellis arc destination or arc id out of range");
   CML_REQUIRE(!bad_cycle, CML_ERR_CYCLE,
@@ -553,6 +670,69 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       lane_list.clear();
   }
 
+  // ---- warp-per-lattice layout for wide lattices (cml_kernels_wide.cuh): laid out like ELL examples
+  if (want_ell && !ctx->opt_no_wide)
+    for (uint64_t e = 0; e < n_ex; ++e)
+      if (!fx[e].lane && fx[e].wide_ok) {
+        fx[e].wide = true;
+        fx[e].ell = true;
+      }
+
+  // ---- pass 1b (parallel): occurrence counts -- per arc slot for the arc-id layouts, per arc class / state part for
+  //      the class layouts (wide, lane)
+  parallel_for([&](uint64_t e, Scratch& S) {
+    const uint32_t n = b->ex_states[e];
+    const uint32_t* off = b->arc_off + state_base[e] + e;
+    const uint32_t* dst = b->arc_dst + arc_base[e];
+    const uint32_t* id = b->arc_id + arc_base[e];
+    if (!(fx[e].wide || fx[e].lane)) {
+      if (S.occ.empty()) S.occ.assign(ctx->n_slots, 0);
+      for (uint32_t k = 0; k < off[n]; ++k) {
+        const uint32_t sl = ctx->h_arc_slot[id[k]];
+        if (sl != kPadNone) ++S.occ[sl];
+      }
+      return;
+    }
+    if (S.occ_a.empty()) {
+      S.occ_a.assign(n_cls, 0);
+      S.occ_v.assign(n_cls, 0);
+    }
+    state_parts(n, off, dst, id, ctx->arc_vcls, S.vstate);
+    for (uint32_t k = 0; k < off[n]; ++k)
+      ++S.occ_a[S.vstate[dst[k]] != kPadNone ? ctx->arc_ucls[id[k]] : ctx->arc_fcls[id[k]]];
+    for (uint32_t st = 0; st < n; ++st)
+      if (S.vstate[st] != kPadNone) ++S.occ_v[S.vstate[st]];
+  });
+  // new classes get the next arc-class / state-class ids (id 0 of either table is the padding / "no class" entry)
+  if (ctx->a_list.empty()) {
+    ctx->a_list.push_back(kPadNone);
+    ctx->v_list.push_back(kPadNone);
+    ctx->a_occ.push_back(0);
+    ctx->v_occ.push_back(0);
+  }
+  for (size_t c = 0; c < n_cls; ++c) {
+    if (batch_occ_a[c]) {
+      if (ctx->a_of_cls[c] == kPadNone) {
+        ctx->a_of_cls[c] = (uint32_t)ctx->a_list.size();
+        ctx->a_list.push_back((uint32_t)c);
+        ctx->a_occ.push_back(0);
+        ctx->cls_dirty = true;
+      }
+      ctx->a_occ[ctx->a_of_cls[c]] += batch_occ_a[c];
+      if (ctx->cls_slot[c] != kPadNone) batch_occ[ctx->cls_slot[c]] += batch_occ_a[c];
+    }
+    if (batch_occ_v[c]) {
+      if (ctx->v_of_cls[c] == kPadNone) {
+        ctx->v_of_cls[c] = (uint32_t)ctx->v_list.size();
+        ctx->v_list.push_back((uint32_t)c);
+        ctx->v_occ.push_back(0);
+        ctx->cls_dirty = true;
+      }
+      ctx->v_occ[ctx->v_of_cls[c]] += batch_occ_v[c];
+      if (ctx->cls_slot[c] != kPadNone) batch_occ[ctx->cls_slot[c]] += batch_occ_v[c];
+    }
+  }
+
   // ---- layout offsets (serial prefix sums), separately for the CSR and the ELL examples
   std::vector<uint64_t> c_lvl(n_ex), c_row(n_ex), c_arc(n_ex), e_in(n_ex), e_out(n_ex), e_meta(n_ex), e_state(n_ex);
   std::vector<uint32_t> slot_of(n_ex);  // index of the example inside its part's descriptor array
@@ -564,6 +744,12 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     if (fx[e].lane) continue;
     if (fx[e].ell) {
       slot_of[e] = (uint32_t)n_e++;
+      if (fx[e].wide) {  // 16-byte aligned streams (bulk copies), padded to a whole number of 16-byte units
+        ei = (ei + 1) & ~1ull;
+        eo = (eo + 1) & ~1ull;
+        fx[e].in_pad = (fx[e].in_pad + 1) & ~1ull;
+        fx[e].out_pad = (fx[e].out_pad + 1) & ~1ull;
+      }
       e_in[e] = ei;
       e_out[e] = eo;
       e_meta[e] = em;
@@ -592,6 +778,12 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   std::vector<cmlk::EllDesc> edesc(n_e);
   std::vector<uint4> h_meta(em);
   std::vector<uint2> h_ein(ei), h_eout(eo);
+  std::vector<uint32_t> h_evcls;
+  {
+    bool any_wide = false;
+    for (uint64_t e = 0; e < n_ex && !any_wide; ++e) any_wide = fx[e].wide;
+    if (any_wide) h_evcls.assign(es, 0u);
+  }
   std::vector<double> h_weight(n_ex);
   const uint32_t pad_id = ctx->n_arcs;  // zero-weight padding arc
   const std::vector<uint32_t>& arc_slot = ctx->h_slot_internal;  // indexed by internal arc id
@@ -671,7 +863,18 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       d.ln_weight = weight > 0 ? std::log(weight) : -INFINITY;
       return;
     }
-    // -------------------------------------------------- level-sliced ELL
+    // -------------------------------------------------- level-sliced ELL (wide examples: records carry arc classes)
+    const bool wide = fx[e].wide;
+    const uint32_t pad_rec = wide ? 0u : pad_id;
+    if (wide) {
+      state_parts(n, off, dst, id, ctx->arc_vcls, S.vstate);
+      uint32_t* vc = &h_evcls[e_state[e]];
+      for (uint32_t sr = 0; sr < n; ++sr) vc[local_of[sr]] = S.vstate[sr] == kPadNone ? 0u : ctx->v_of_cls[S.vstate[sr]];
+    }
+    auto rec_id = [&](uint32_t k) -> uint32_t {  // second word of arc k's record
+      if (!wide) return perm[id[k]];
+      return ctx->a_of_cls[S.vstate[dst[k]] != kPadNone ? ctx->arc_ucls[id[k]] : ctx->arc_fcls[id[k]]];
+    };
     auto &ld = S.lvl_d, &lo = S.lvl_o;
     ld.assign(nl, 0);
     lo.assign(nl, 0);
@@ -695,8 +898,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       meta[l].z = lfirst[l];
       meta[l].w = w | (ld[l] << 8) | (lo[l] << 16) | ((l - lmin[l]) << 24) | ((lmax[l] - l) << 28);
       // padding: zero-weight arc from/to a state that is certainly inside the ring window
-      const uint2 pin = make_uint2(l ? lfirst[l - 1] : 0, pad_id);
-      const uint2 pout = make_uint2(l + 1 < nl ? lfirst[l + 1] : lfirst[l], pad_id);
+      const uint2 pin = make_uint2(l ? lfirst[l - 1] : 0, pad_rec);
+      const uint2 pout = make_uint2(l + 1 < nl ? lfirst[l + 1] : lfirst[l], pad_rec);
       for (uint64_t k = 0; k < (uint64_t)w * ld[l]; ++k) ein[in_off + k] = pin;
       for (uint64_t k = 0; k < (uint64_t)w * lo[l]; ++k) eout[out_off + k] = pout;
       in_off += w * ld[l];
@@ -715,13 +918,14 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       for (uint32_t c = 0; c < deg; ++c) {
         const uint32_t k = order[c];
         const uint32_t dj = local_of[dst[k]], dl = level_of[dst[k]];
-        eout[meta[l].y + (uint64_t)c * w + r] = make_uint2(dj, perm[id[k]]);
+        const uint32_t rid = rec_id(k);
+        eout[meta[l].y + (uint64_t)c * w + r] = make_uint2(dj, rid);
         const uint32_t dw = lfirst[dl + 1] - lfirst[dl], dr = dj - lfirst[dl];
-        ein[meta[dl].x + (uint64_t)(S.icur[dj]++) * dw + dr] = make_uint2(j, perm[id[k]]);
+        ein[meta[dl].x + (uint64_t)(S.icur[dj]++) * dw + dr] = make_uint2(j, rid);
       }
     }
     // aggregate flag: no padding in the level's outgoing block and every column feeds one slot
-    for (uint32_t l = 0; l < nl; ++l) {
+    for (uint32_t l = 0; l < nl && !wide; ++l) {
       const uint32_t w = lfirst[l + 1] - lfirst[l], O = lo[l];
       bool agg = O > 0 && w > 1;
       for (uint32_t c = 0; c < O && agg; ++c) {
@@ -745,6 +949,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     d.weight = weight;
     d.fin_level = level_of[b->ex_fin[e]];
     d.pad = 0;
+    d.in_len = (uint32_t)fx[e].in_pad;
+    d.out_len = (uint32_t)fx[e].out_pad;
   });
 
   // ---- classes (serial; cheap)
@@ -752,9 +958,17 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   const size_t smem_budget = std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : 48 * 1024, 220 * 1024);
   const uint32_t cta_max_states = (uint32_t)((smem_budget - 64) / per_state);
   std::vector<std::vector<uint32_t>> cls(NCLS), ecls(NELL);
+  std::vector<uint32_t> wide_list;
   uint64_t scratch_states = 0;
   for (uint64_t e = 0; e < n_ex; ++e) {
     if (fx[e].lane) continue;
+    if (fx[e].wide) {
+      wide_list.push_back(slot_of[e]);
+      bt->wide_ring = std::max(bt->wide_ring, pow2ceil(fx[e].ring_need));
+      bt->wide_arcs += arc_base[e + 1] - arc_base[e];
+      bt->wide_records += fx[e].in_pad + fx[e].out_pad;
+      continue;
+    }
     if (fx[e].ell) {
       ecls[fx[e].g_class].push_back(slot_of[e]);
       bt->ell_ring[fx[e].g_class] = std::max(bt->ell_ring[fx[e].g_class], pow2ceil(fx[e].ring_need));
@@ -796,11 +1010,14 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     ell_list.insert(ell_list.end(), ecls[c].begin(), ecls[c].end());
   }
   bt->ell_begin[NELL] = (uint32_t)ell_list.size();
+  // wide examples: most records first (a persistent warp takes every n-th entry of the list)
+  std::stable_sort(wide_list.begin(), wide_list.end(), [&](uint32_t x, uint32_t y) { return edesc[x].n_states > edesc[y].n_states; });
+  bt->wide_ex = wide_list.size();
 
   // ---- lane tiles: 32 lattices of similar size per tile, streams aligned by state ordinal
   std::vector<cmlk::LaneTile> h_tile;
   std::vector<uint2> h_lfw, h_lbw;
-  std::vector<uint32_t> h_lex, h_lfin, h_lnlev;
+  std::vector<uint32_t> h_lex, h_lfin, h_lnlev, h_lvcls;
   std::vector<double> h_lweight;
   uint64_t lane_states = 0, lane_levels = 0;
   if (!lane_list.empty()) {
@@ -877,9 +1094,10 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       lane_states += T.n_states;
       lane_levels += T.n_levels;
     }
-    const uint2 padrec = make_uint2(0u, pad_id);
+    const uint2 padrec = make_uint2(0u, 0u);  // arc class 0: the zero-weight padding class
     h_lfw.assign((size_t)(fo + 2 * U) * 32, padrec);  // + the prefetch tail
     h_lbw.assign((size_t)(bo + 2 * U) * 32, padrec);
+    h_lvcls.assign((size_t)(lane_states + 2) * 32, 0u);  // state class 0: no state part (+ the prefetch tail)
     // phase B: fill
     tile_for([&](uint32_t t) {
       const cmlk::LaneTile& T = h_tile[t];
@@ -900,7 +1118,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         for (uint32_t j = 1; j < T.n_states; ++j) fwp[(size_t)(rowf[j] + ri[j] - 1) * 32 + l].x |= cmlk::kLaneLast;
         for (uint32_t j = 0; j < T.n_states; ++j) bwp[(size_t)(rowb[j] + ro[j] - 1) * 32 + l].x |= cmlk::kLaneLast;
       }
-      std::vector<uint32_t> cur, lfirst;
+      std::vector<uint32_t> cur, lfirst, vstate;
       for (uint32_t l = 0; l < 32 && (size_t)t * 32 + l < lane_list.size(); ++l) {
         const uint32_t e = lane_list[(size_t)t * 32 + l], n = b->ex_states[e], nl = fx[e].n_levels;
         const uint32_t* off = b->arc_off + state_base[e] + e;
@@ -917,10 +1135,14 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         for (uint32_t sr = 0; sr < n; ++sr) ++lfirst[level_of[sr] + 1];
         for (uint32_t L = 0; L < nl; ++L) lfirst[L + 1] += lfirst[L];
         cur.assign(n, 0);
+        state_parts(n, off, dst, id, ctx->arc_vcls, vstate);
+        for (uint32_t sr = 0; sr < n; ++sr)
+          h_lvcls[T.st_base + (size_t)local_of[sr] * 32 + l] = vstate[sr] == kPadNone ? 0u : ctx->v_of_cls[vstate[sr]];
         for (uint32_t sr = 0; sr < n; ++sr) {
           const uint32_t j = local_of[sr];
           for (uint32_t k = off[sr]; k < off[sr + 1]; ++k) {
-            const uint32_t dj = local_of[dst[k]], ia = perm[id[k]];
+            const uint32_t dj = local_of[dst[k]];
+            const uint32_t ia = ctx->a_of_cls[vstate[dst[k]] != kPadNone ? ctx->arc_ucls[id[k]] : ctx->arc_fcls[id[k]]];
             uint2& f = fwp[(size_t)(rowf[dj] + cur[dj]++) * 32 + l];
             f.x = (f.x & cmlk::kLaneLast) | j;
             f.y = ia;
@@ -964,6 +1186,10 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     CML_CUDA(bt->ell_in.upload(h_ein.data(), h_ein.size(), s));
     CML_CUDA(bt->ell_out.upload(h_eout.data(), h_eout.size(), s));
     CML_CUDA(bt->ell_list.upload(ell_list.data(), ell_list.size(), s));
+    if (bt->wide_ex) {
+      CML_CUDA(bt->wide_list.upload(wide_list.data(), wide_list.size(), s));
+      CML_CUDA(bt->ell_vcls.upload(h_evcls.data(), h_evcls.size(), s));
+    }
     CML_CUDA(bt->alpha_g.alloc(es * rs));
     CML_CUDA(bt->lvl_exp.alloc(em * 2));
   }
@@ -975,6 +1201,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     CML_CUDA(bt->lane_fin.upload(h_lfin.data(), h_lfin.size(), s));
     CML_CUDA(bt->lane_nlev.upload(h_lnlev.data(), h_lnlev.size(), s));
     CML_CUDA(bt->lane_weight.upload(h_lweight.data(), h_lweight.size(), s));
+    CML_CUDA(bt->lane_vcls.upload(h_lvcls.data(), h_lvcls.size(), s));
     CML_CUDA(bt->lane_alpha.alloc(lane_states * 32 * rs));
     CML_CUDA(bt->lane_lvle.alloc(lane_levels * 32));
   }
@@ -1030,14 +1257,31 @@ extern "C" int cml_lane_stats(cml_ctx* ctx, uint64_t* lane_examples, uint64_t* l
   return CML_OK;
 }
 
+extern "C" int cml_wide_stats(cml_ctx* ctx, uint64_t* wide_examples, uint64_t* wide_arcs, uint64_t* wide_records,
+                              uint64_t* arc_classes, uint64_t* state_classes) {
+  if (!ctx) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0;
+  for (auto& bt : ctx->batches) {
+    a += bt->wide_ex;
+    b += bt->wide_arcs;
+    c += bt->wide_records;
+  }
+  if (wide_examples) *wide_examples = a;
+  if (wide_arcs) *wide_arcs = b;
+  if (wide_records) *wide_records = c;
+  if (arc_classes) *arc_classes = ctx->a_list.empty() ? 0 : ctx->a_list.size() - 1;
+  if (state_classes) *state_classes = ctx->v_list.empty() ? 0 : ctx->v_list.size() - 1;
+  return CML_OK;
+}
+
 extern "C" int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,
                                 uint64_t* csr_examples) {
   if (!ctx) return CML_ERR_ARG;
   uint64_t a = 0, b = 0, c = 0, d = 0;
   for (auto& bt : ctx->batches) {
-    a += bt->ell_ex;
+    a += bt->ell_ex - bt->wide_ex;
     b += bt->ell_arcs;
-    c += bt->ell_pad_records;
+    c += bt->ell_pad_records - bt->wide_records;
     d += bt->csr_ex;
   }
   if (ell_examples) *ell_examples = a;
@@ -1115,6 +1359,59 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     if ((r = launch_ell_class<Real, 32, 1, false>(ctx, bt, E, 5))) return r;  // kEllCls[5]
     if ((r = launch_ell_class<Real, 32, 8, true>(ctx, bt, E, 6))) return r;   // kEllCls[6]
   }
+  if (SCALED && bt.wide_ex) {
+    WideArgs Wd;
+    Wd.desc = bt.edesc.p;
+    Wd.ex_list = bt.wide_list.p;
+    Wd.n_list = (uint32_t)bt.wide_ex;
+    Wd.lvl_meta = bt.lvl_meta.p;
+    Wd.ell_in = bt.ell_in.p;
+    Wd.ell_out = bt.ell_out.p;
+    Wd.st_vcls = bt.ell_vcls.p;
+    Wd.a_w = ctx->a_w.p;
+    Wd.a_slot = ctx->a_slot.p;
+    Wd.v_w = ctx->v_w.p;
+    Wd.v_slot = ctx->v_slot.p;
+    Wd.n_a = (uint32_t)ctx->a_list.size();
+    Wd.n_v = (uint32_t)ctx->v_list.size();
+    Wd.any_a_slot = ctx->any_a_slot;
+    Wd.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    Wd.ex_lnp = bt.ex_lnp.p;
+    Wd.alpha_g = bt.alpha_g.p;
+    Wd.lvl_exp = bt.lvl_exp.p;
+    Wd.ring = std::max<uint32_t>(16, bt.wide_ring);
+    Wd.no_counts = ctx->opt_no_counts;
+    // persistent warps, one CTA per SM: as many warps as shared memory allows (<= 16), trimmed so that the lattices
+    // divide evenly over the warps (2,000 cipher lines on 148 SMs: 14 warps per CTA, one lattice per warp)
+    const size_t budget = std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : 48 * 1024, 220 * 1024);
+    size_t tbl = (((size_t)(Wd.n_a + Wd.n_v) * (sizeof(Real) + 4)) + 127) & ~(size_t)127;
+    const size_t per_warp = 64 + (size_t)kWideStages * kWideChunkBytes + (size_t)Wd.ring * sizeof(Real);
+    const bool tblsm = tbl + 4 * per_warp <= budget && tbl <= 96 * 1024;
+    if (!tblsm) tbl = 0;
+    int wmax = (int)std::min<size_t>(16, (budget - tbl) / per_warp);
+    CML_REQUIRE(wmax >= 1, CML_ERR_ARG, "wide lattice ring does not fit in shared memory");
+    const uint64_t sm = (uint64_t)ctx->sm_count;
+    int wpc = wmax;
+    {
+      double best = -1;
+      for (int w = wmax; w >= std::max(1, wmax / 2); --w) {
+        const uint64_t slots = sm * (uint64_t)w, waves = (Wd.n_list + slots - 1) / slots;
+        const double util = (double)Wd.n_list / (double)(waves * slots) * (0.75 + 0.25 * w / wmax);
+        if (util > best) {
+          best = util;
+          wpc = w;
+        }
+      }
+    }
+    Wd.warps_per_cta = (uint32_t)wpc;
+    const unsigned grid = (unsigned)std::min<uint64_t>(sm, (Wd.n_list + wpc - 1) / wpc);
+    const size_t smem = tbl + (size_t)wpc * per_warp;
+    auto kern = tblsm ? k_fb_wide<Real, true> : k_fb_wide<Real, false>;
+    if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, wpc * 32, smem, ctx->stream>>>(Wd);
+    ++ctx->launches;
+    ++bt.n_fb_kernels;
+  }
   if (SCALED && bt.lane_tiles) {
     LaneArgs L;
     L.tile = bt.ltile.p;
@@ -1125,15 +1422,28 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     L.fin = bt.lane_fin.p;
     L.nlev = bt.lane_nlev.p;
     L.weight = bt.lane_weight.p;
-    L.arc_w = ctx->arc_w_real.p;
-    L.arc_ws = ctx->arc_ws.p;
+    L.vcls = bt.lane_vcls.p;
+    L.a_w = ctx->a_w.p;
+    L.a_slot = ctx->a_slot.p;
+    L.v_w = ctx->v_w.p;
+    L.v_slot = ctx->v_slot.p;
+    L.n_a = (uint32_t)ctx->a_list.size();
+    L.n_v = (uint32_t)ctx->v_list.size();
     L.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
     L.ex_lnp = bt.ex_lnp.p;
     L.alpha = bt.lane_alpha.p;
     L.lvle = bt.lane_lvle.p;
     L.no_counts = ctx->opt_no_counts;
-    const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real);
-    k_fb_lane<Real><<<cdiv(bt.lane_tiles, kLaneWarps), kLaneWarps * 32, smem, ctx->stream>>>(L);
+    // class tables in shared memory when they are small (HMM: the 1k transition classes yes, the 20k emission
+    // classes no: those are gathered once per state)
+    const size_t tbl_a = (((size_t)L.n_a * (sizeof(Real) + 4)) + 15) & ~(size_t)15;
+    const size_t tbl_v = (size_t)L.n_v * (sizeof(Real) + 4);
+    const bool ta = tbl_a <= 40 * 1024, tv = tbl_v <= 24 * 1024;
+    const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real) + (ta ? tbl_a : 0) + (tv ? tbl_v : 0);
+    auto kern = ta ? (tv ? k_fb_lane<Real, true, true> : k_fb_lane<Real, true, false>)
+                   : (tv ? k_fb_lane<Real, false, true> : k_fb_lane<Real, false, false>);
+    if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<cdiv(bt.lane_tiles, kLaneWarps), kLaneWarps * 32, smem, ctx->stream>>>(L);
     ++ctx->launches;
     ++bt.n_fb_kernels;
   }
@@ -1232,6 +1542,41 @@ static int rebuild_slot_codes(cml_ctx* ctx) {
     code[ctx->h_perm[a]] = (sl == kPadNone) ? kPadNone : (hot_index[sl] != kPadNone ? (cmlk::kSlotHot | hot_index[sl]) : sl);
   }
   ctx->n_hot = (uint32_t)hot.size();
+  // arc-class / state-class tables of the wide and lane kernels (ids are append-only; entry 0 = padding / no class)
+  if (ctx->a_list.size() > 1 || ctx->v_list.size() > 1) {
+    auto build = [&](const std::vector<uint32_t>& list, std::vector<uint32_t>& off, std::vector<uint32_t>& par,
+                     std::vector<uint32_t>& slc) {
+      off.assign(1, 0);
+      par.clear();
+      slc.clear();
+      for (uint32_t i = 0; i < list.size(); ++i) {
+        uint32_t sl = kPadNone;
+        if (i) {
+          const uint32_t c = list[i];
+          par.insert(par.end(), ctx->cls_param.begin() + ctx->cls_off[c], ctx->cls_param.begin() + ctx->cls_off[c + 1]);
+          sl = ctx->cls_slot[c];
+        }
+        off.push_back((uint32_t)par.size());
+        slc.push_back(sl == kPadNone ? kPadNone : (hot_index[sl] != kPadNone ? (cmlk::kSlotHot | hot_index[sl]) : sl));
+      }
+    };
+    std::vector<uint32_t> off, par, slc;
+    build(ctx->a_list, off, par, slc);
+    CML_CUDA(ctx->a_off.upload(off.data(), off.size(), ctx->stream));
+    CML_CUDA(ctx->a_param.upload(par.data(), par.size(), ctx->stream));
+    CML_CUDA(ctx->a_slot.upload(slc.data(), slc.size(), ctx->stream));
+    ctx->any_a_slot = 0;
+    for (uint32_t c : slc) ctx->any_a_slot |= (c != kPadNone);
+    CML_CUDA(cudaStreamSynchronize(ctx->stream));
+    build(ctx->v_list, off, par, slc);
+    CML_CUDA(ctx->v_off.upload(off.data(), off.size(), ctx->stream));
+    CML_CUDA(ctx->v_param.upload(par.data(), par.size(), ctx->stream));
+    CML_CUDA(ctx->v_slot.upload(slc.data(), slc.size(), ctx->stream));
+    CML_CUDA(cudaStreamSynchronize(ctx->stream));
+    CML_CUDA(ctx->a_w.alloc(ctx->a_list.size() * (ctx->precision / 8)));
+    CML_CUDA(ctx->v_w.alloc(ctx->v_list.size() * (ctx->precision / 8)));
+  }
+  ctx->cls_dirty = false;
   CML_CUDA(ctx->arc_slot_code.upload(code.data(), code.size(), ctx->stream));
   CML_CUDA(ctx->hot_slot.upload(hot.data(), hot.size(), ctx->stream));
   CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * cmlk::kHotCopies)));
@@ -1252,7 +1597,7 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
     ctx->estimate_pending = true;
     return CML_OK;
   }
-  if (ctx->hot_dirty) {
+  if (ctx->hot_dirty || ctx->cls_dirty) {
     const int rc = rebuild_slot_codes(ctx);
     if (rc) return rc;
   }
@@ -1263,6 +1608,22 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   else
     r = sc ? launch_arc_weights<float, true>(ctx) : launch_arc_weights<float, false>(ctx);
   if (r) return r;
+  if (ctx->a_list.size() > 1 || ctx->v_list.size() > 1) {
+    const uint32_t na = (uint32_t)ctx->a_list.size(), nv = (uint32_t)ctx->v_list.size();
+    if (ctx->precision == 64) {
+      cmlk::k_class_weights<double><<<cdiv(na, 256), 256, 0, ctx->stream>>>(na, ctx->a_off.p, ctx->a_param.p, ctx->ln_w.p, 0.,
+                                                                            (double*)ctx->a_w.p);
+      cmlk::k_class_weights<double><<<cdiv(nv, 256), 256, 0, ctx->stream>>>(nv, ctx->v_off.p, ctx->v_param.p, ctx->ln_w.p, 1.,
+                                                                            (double*)ctx->v_w.p);
+    } else {
+      cmlk::k_class_weights<float><<<cdiv(na, 256), 256, 0, ctx->stream>>>(na, ctx->a_off.p, ctx->a_param.p, ctx->ln_w.p, 0.f,
+                                                                           (float*)ctx->a_w.p);
+      cmlk::k_class_weights<float><<<cdiv(nv, 256), 256, 0, ctx->stream>>>(nv, ctx->v_off.p, ctx->v_param.p, ctx->ln_w.p, 1.f,
+                                                                           (float*)ctx->v_w.p);
+    }
+    ctx->launches += 2;
+    CML_CUDA(cudaGetLastError());
+  }
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), ctx->stream));
   if (ctx->n_hot)
     CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * cmlk::kHotCopies * sizeof(double), ctx->stream));
@@ -1523,7 +1884,7 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_version", "cml_create", "cml_destroy", "cml_last_error", "cml_set_stream", "cml_synchronize",
       "cml_launch_count", "cml_set_option", "cml_set_model", "cml_set_params", "cml_get_params", "cml_snapshot_params",
       "cml_restore_params", "cml_add_sequences", "cml_dense_stats", "cml_dense_kernel", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
-      "cml_lane_stats", "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
+      "cml_lane_stats", "cml_wide_stats", "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
       "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",

@@ -39,6 +39,7 @@ struct __align__(16) EllDesc {
   uint32_t n_states, n_levels, fin, ex_index;
   double weight;
   uint32_t fin_level, pad;
+  uint32_t in_len, out_len;  // records of the example's incoming / outgoing stream (wide kernel: bulk-copy bounds)
 };
 
 // per-level meta (uint4):

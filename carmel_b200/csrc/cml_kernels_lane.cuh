@@ -43,8 +43,12 @@ struct LaneArgs {
   const uint32_t* fin;    // [tile*32+lane] layered index of the goal state (0xFFFFFFFF for empty lanes)
   const uint32_t* nlev;   // [tile*32+lane] levels of the lane's lattice
   const double* weight;   // [tile*32+lane]
-  const void* arc_w;      // Real[n_arcs+1]
-  const void* arc_ws;     // WS<Real>[n_arcs+1]
+  const uint32_t* vcls;   // [state ordinal][lane] state class id (0 = none), indexed like alpha
+  const void* a_w;        // Real[n_a]: arc class weights (entry 0 = 0: padding)
+  const uint32_t* a_slot; // [n_a] count slot codes
+  const void* v_w;        // Real[n_v]: state class weights (entry 0 = 1: no state part)
+  const uint32_t* v_slot;
+  uint32_t n_a, n_v;
   CountSink sink;
   double* ex_lnp;
   void* alpha;            // Real
@@ -57,11 +61,41 @@ constexpr int kLaneRing = 16;  // ring entries per lane: two levels of width <= 
 constexpr int kLaneU = 4;      // rows per software-pipeline chunk
 constexpr int kLaneWarps = 8;
 
-template <typename Real>
+// TA / TV: the arc-class / state-class tables (weight + slot code) are staged in shared memory.  Arc weights are
+// FACTORED (cml_device.cu "arc classes"): w(arc) = U[record's class] * V[class of the destination state]; the state
+// part's expected count is the state posterior, accumulated once per state.
+template <typename Real, bool TA, bool TV>
 static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) {
   extern __shared__ __align__(16) unsigned char smem_lane[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * kLaneWarps + wib;
+  const Real* __restrict__ w = reinterpret_cast<const Real*>(A.a_w);
+  const uint32_t* __restrict__ wsl = A.a_slot;
+  const Real* __restrict__ vwt = reinterpret_cast<const Real*>(A.v_w);
+  const uint32_t* __restrict__ vsl = A.v_slot;
+  unsigned char* sp = smem_lane + (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real);
+  if (TA) {
+    Real* s_w = reinterpret_cast<Real*>(sp);
+    uint32_t* s_sl = reinterpret_cast<uint32_t*>(s_w + A.n_a);
+    for (uint32_t i = threadIdx.x; i < A.n_a; i += blockDim.x) {
+      s_w[i] = w[i];
+      s_sl[i] = wsl[i];
+    }
+    w = s_w;
+    wsl = s_sl;
+    sp += (((size_t)A.n_a * (sizeof(Real) + 4)) + 15) & ~(size_t)15;
+  }
+  if (TV) {
+    Real* s_w = reinterpret_cast<Real*>(sp);
+    uint32_t* s_sl = reinterpret_cast<uint32_t*>(s_w + A.n_v);
+    for (uint32_t i = threadIdx.x; i < A.n_v; i += blockDim.x) {
+      s_w[i] = vwt[i];
+      s_sl[i] = vsl[i];
+    }
+    vwt = s_w;
+    vsl = s_sl;
+  }
+  if (TA || TV) __syncthreads();
   if (tile >= A.n_tiles) return;
   Real* ring = reinterpret_cast<Real*>(smem_lane) + (size_t)wib * kLaneRing * 32 + lane;
 #pragma unroll
@@ -69,9 +103,8 @@ static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) 
   const LaneTile T = A.tile[tile];
   const uint32_t li = tile * 32 + lane;
   const uint32_t ex = A.ex[li], fin = A.fin[li];
-  const Real* __restrict__ w = reinterpret_cast<const Real*>(A.arc_w);
-  const WS<Real>* __restrict__ ws = reinterpret_cast<const WS<Real>*>(A.arc_ws);
   Real* __restrict__ ag = reinterpret_cast<Real*>(A.alpha) + T.st_base + lane;
+  const uint32_t* __restrict__ vcl = A.vcls + T.st_base + lane;
   int* __restrict__ lve = A.lvle + T.lv_base + lane;
 
   // ================================================================ forward
@@ -92,14 +125,17 @@ static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) 
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) r0[k] = fw[(size_t)k * 32];
 #pragma unroll
-    for (int k = 0; k < kLaneU; ++k) w0[k] = __ldg(&w[r0[k].y]);
+    for (int k = 0; k < kLaneU; ++k) w0[k] = w[r0[k].y];
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) r1[k] = fw[(size_t)(kLaneU + k) * 32];
+    // state parts: class of state s+1 two closes ahead, its weight one close ahead (the array has a padded tail)
+    uint32_t vc_next = vcl[(size_t)2 * 32];
+    Real vw_cur = vwt[vcl[(size_t)1 * 32]];
     for (uint32_t r = 0; r < R; r += kLaneU) {
       Real w1[kLaneU];
       uint2 r2[kLaneU];
 #pragma unroll
-      for (int k = 0; k < kLaneU; ++k) w1[k] = __ldg(&w[r1[k].y]);
+      for (int k = 0; k < kLaneU; ++k) w1[k] = w[r1[k].y];
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) r2[k] = fw[(size_t)(r + 2 * kLaneU + k) * 32];  // (the array has a padded tail)
 #pragma unroll
@@ -107,7 +143,9 @@ static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) 
         const uint32_t x = r0[k].x;
         acc = fma(ring[(x & (kLaneRing - 1)) * 32], w0[k], acc);
         if (x & kLaneLast) {  // warp-uniform: the row closes state ordinal s
-          const Real a = acc * pend;
+          const Real a = acc * pend * vw_cur;
+          vw_cur = vwt[vc_next];
+          vc_next = vcl[(size_t)min(s + 2, T.n_states + 1) * 32];
           acc = 0;
           ring[(s & (kLaneRing - 1)) * 32] = a;
           ag[(size_t)s * 32] = a;
@@ -154,32 +192,56 @@ static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) 
     Real a_next = s >= 1 ? ag[(size_t)(s - 1) * 32] : Real(0);
     double as = (double)a_cur * cwE;
     uint2 r0[kLaneU], r1[kLaneU];
-    WS<Real> e0[kLaneU];
+    Real e0[kLaneU];
+    uint32_t q0[kLaneU];
     const uint32_t R = T.rows_b;
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) r0[k] = bw[(size_t)k * 32];
 #pragma unroll
-    for (int k = 0; k < kLaneU; ++k) e0[k] = ws[r0[k].y];
+    for (int k = 0; k < kLaneU; ++k) {
+      e0[k] = w[r0[k].y];
+      q0[k] = wsl[r0[k].y];
+    }
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) r1[k] = bw[(size_t)(kLaneU + k) * 32];
+    // state parts: class of state s-1 two closes ahead, weight / slot of the closing state one close ahead
+    uint32_t vc_next = s >= 1 ? vcl[(size_t)(s - 1) * 32] : 0u;
+    Real vw_cur;
+    uint32_t vs_cur;
+    {
+      const uint32_t vc = vcl[(size_t)s * 32];
+      vw_cur = vwt[vc];
+      vs_cur = vsl[vc];
+    }
     for (uint32_t r = 0; r < R; r += kLaneU) {
-      WS<Real> e1[kLaneU];
+      Real e1[kLaneU];
+      uint32_t q1[kLaneU];
       uint2 r2[kLaneU];
 #pragma unroll
-      for (int k = 0; k < kLaneU; ++k) e1[k] = ws[r1[k].y];
+      for (int k = 0; k < kLaneU; ++k) {
+        e1[k] = w[r1[k].y];
+        q1[k] = wsl[r1[k].y];
+      }
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) r2[k] = bw[(size_t)(r + 2 * kLaneU + k) * 32];
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) {
         const uint32_t x = r0[k].x;
-        const Real tt = e0[k].w * ring[(x & (kLaneRing - 1)) * 32];
+        const Real tt = e0[k] * ring[(x & (kLaneRing - 1)) * 32];
         bacc += tt;
         const double cval = as * (double)tt;
-        if (cval > 0 && e0[k].slot != kSlotNone && !A.no_counts) count_add(A.sink, e0[k].slot, cval);
+        if (cval > 0 && q0[k] != kSlotNone && !A.no_counts) count_add(A.sink, q0[k], cval);
         if (x & kLaneLast) {  // warp-uniform
           const Real b = (s == fin) ? Real(1) : bacc * pendb;
+          {  // the state part: its expected count is the state posterior; predecessors see V * beta
+            const double g = (s == fin) ? as : as * (double)bacc;
+            if (vs_cur != kSlotNone && g > 0 && !A.no_counts) count_add(A.sink, vs_cur, g);
+          }
           bacc = 0;
-          ring[(s & (kLaneRing - 1)) * 32] = b;
+          ring[(s & (kLaneRing - 1)) * 32] = b * vw_cur;
+          vw_cur = vwt[vc_next];
+          vs_cur = vsl[vc_next];
+          vc_next = (s >= 2 && s != 0xFFFFFFFFu) ? vcl[(size_t)(s - 2) * 32] : 0u;
           mxe = max(mxe, Num<Real>::expo(b));
           if (x & kLaneLevelEnd) {  // per lane: the lane's level `lvl` is complete (its lowest state was s)
             int shift = 0;
@@ -203,6 +265,7 @@ static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) 
       for (int k = 0; k < kLaneU; ++k) {
         r0[k] = r1[k];
         e0[k] = e1[k];
+        q0[k] = q1[k];
         r1[k] = r2[k];
       }
     }

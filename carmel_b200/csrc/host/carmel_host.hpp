@@ -144,6 +144,8 @@ struct TrainOpts {
   bool quiet = false;
   bool no_ell = false;              // --no-ell : general (layered CSR) kernels only
   int lane_min = -1;                // --lane-min=n / --no-lane : CML_OPT_LANE_MIN (-1 = library default)
+  bool no_factor = false;           // --no-factor : one weight-table entry per arc (CML_OPT_NO_FACTOR)
+  bool no_wide = false;             // --no-wide : wide lattices stay on the k_fb_ell classes (CML_OPT_NO_WIDE)
   int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
   uint32_t ran_restarts = 0;        // -! n : additional random starts (train.cc:553-667)

@@ -125,6 +125,8 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   if (lopt.count("no-dense")) topt.dense = -1;
   if (lopt.count("lane-min")) topt.lane_min = std::atoi(lopt["lane-min"].c_str());
   if (lopt.count("no-lane")) topt.lane_min = 0;
+  if (lopt.count("no-factor")) topt.no_factor = true;
+  if (lopt.count("no-wide")) topt.no_wide = true;
   if (lopt.count("dense")) topt.dense = 1;
   if (lopt.count("gpu")) topt.device = std::atoi(lopt["gpu"].c_str());
   if (lopt.count("history")) topt.history_file = lopt["history"];

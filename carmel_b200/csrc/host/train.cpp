@@ -258,6 +258,8 @@ void TrainJob::prepare() {
   if (opt.max_iter == 0) ok(cml_set_option(ctx, CML_OPT_ARC_COUNTS, 1));  // -M 0 writes per-arc fractional counts
   if (opt.no_ell) ok(cml_set_option(ctx, CML_OPT_NO_ELL, 1));
   if (opt.lane_min >= 0) ok(cml_set_option(ctx, CML_OPT_LANE_MIN, opt.lane_min));
+  if (opt.no_factor) ok(cml_set_option(ctx, CML_OPT_NO_FACTOR, 1));
+  if (opt.no_wide) ok(cml_set_option(ctx, CML_OPT_NO_WIDE, 1));
   // locality keys: arcs with the same output symbol, then source state, are laid out together on the GPU,
   // so the weight gathers of one lattice level (one output position) fall into few cache sectors
   {

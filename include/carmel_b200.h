@@ -67,7 +67,11 @@ enum cml_option {
   CML_OPT_NO_ELL = 2,     /* force the layered-CSR kernels (tests).  Set before cml_add_trellises. */
   CML_OPT_LANE_MIN = 3,   /* the lane-per-lattice kernel (narrow lattices, tiles of 32) is used when a batch has at
                              least this many eligible lattices; default 16384, 0 = never.  Before cml_add_trellises. */
-  CML_OPT_NO_COUNTS = 4   /* profiling only: the lane kernel skips its expected-count REDs */
+  CML_OPT_NO_COUNTS = 4,  /* profiling only: the wide / lane kernels skip their expected-count REDs */
+  CML_OPT_NO_FACTOR = 5,  /* keep one weight-table entry per arc: no arc classes / state parts.
+                             Set before cml_set_model. */
+  CML_OPT_NO_WIDE = 6     /* lattices with levels of 9..32 states stay on the k_fb_ell classes instead of the
+                             warp-per-lattice kernel (tests).  Set before cml_add_trellises. */
 };
 int cml_set_option(cml_ctx* ctx, int option, int value);
 
@@ -148,6 +152,10 @@ int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, u
                      uint64_t* csr_examples);
 /* lattices / arcs / padded records (both sweeps) resident in the lane-per-lattice layout, and its tiles */
 int cml_lane_stats(cml_ctx* ctx, uint64_t* lane_examples, uint64_t* lane_arcs, uint64_t* lane_records, uint64_t* tiles);
+/* lattices on the warp-per-lattice kernel (levels of 9..32 states), their arcs and stored records (with padding), and
+ * the number of arc classes / state classes the resident wide and lane lattices reference (factored arc weights) */
+int cml_wide_stats(cml_ctx* ctx, uint64_t* wide_examples, uint64_t* wide_arcs, uint64_t* wide_records,
+                   uint64_t* arc_classes, uint64_t* state_classes);
 /* introspection for parity tests: the layered layout of resident example e.
  *   level_of[ex_states]  level of each reference state id;  local_of[ex_states] its layered index. */
 int cml_get_example_layout(cml_ctx* ctx, uint64_t e, uint32_t* n_levels, uint32_t* level_of, uint32_t* local_of);
