@@ -58,7 +58,7 @@ struct Batch {
   uint32_t wide_ring = 0;
   // --- lane part (k_fb_lane: one lattice per lane, tiles of 32)
   uint64_t lane_ex = 0, lane_arcs = 0, lane_records = 0;
-  uint32_t lane_tiles = 0;
+  uint32_t lane_tiles = 0, lane_ring = 16;
   DevArray<cmlk::LaneTile> ltile;
   DevArray<uint2> lane_fw, lane_bw;
   DevArray<uint32_t> lane_exidx, lane_fin, lane_nlev;

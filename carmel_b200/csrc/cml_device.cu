@@ -1158,6 +1158,11 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
         }
       }
     });
+    {
+      uint32_t wmax = 0;
+      for (uint32_t e : lane_list) wmax = std::max(wmax, fx[e].width);
+      bt->lane_ring = 2 * wmax <= 8 ? 8 : (uint32_t)cmlk::kLaneRing;
+    }
     bt->lane_ex = lane_list.size();
     bt->lane_tiles = n_tiles;
     bt->lane_records = (fo + bo) * 32;
@@ -1381,14 +1386,21 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     Wd.lvl_exp = bt.lvl_exp.p;
     Wd.ring = std::max<uint32_t>(16, bt.wide_ring);
     Wd.no_counts = ctx->opt_no_counts;
+    Wd.l2_prefetch = 0;
+    Wd.generic_addr = 0;
+    if (const char* e = getenv("CML_WIDE_PF")) Wd.l2_prefetch = atoi(e);      // tuning knobs (profiling)
+    if (const char* e = getenv("CML_WIDE_GA")) Wd.generic_addr = atoi(e);
     // persistent warps, one CTA per SM: as many warps as shared memory allows (<= 16), trimmed so that the lattices
     // divide evenly over the warps (2,000 cipher lines on 148 SMs: 14 warps per CTA, one lattice per warp)
     const size_t budget = std::min<size_t>(ctx->smem_optin ? ctx->smem_optin : 48 * 1024, 220 * 1024);
+    // layout (cml_kernels_wide.cuh): 8 KB alignment slack | chunk buffers | mbarriers | ring alignment slack | rings | tables
     size_t tbl = (((size_t)(Wd.n_a + Wd.n_v) * (sizeof(Real) + 4)) + 127) & ~(size_t)127;
-    const size_t per_warp = 64 + (size_t)kWideStages * kWideChunkBytes + (size_t)Wd.ring * sizeof(Real);
-    const bool tblsm = tbl + 4 * per_warp <= budget && tbl <= 96 * 1024;
+    const size_t ring_bytes = (size_t)Wd.ring * sizeof(Real);
+    const size_t per_warp = 64 + (size_t)kWideStages * kWideChunkBytes + ring_bytes;
+    const size_t slack = (size_t)kWideStages * kWideChunkBytes + ring_bytes;
+    const bool tblsm = tbl + slack + 4 * per_warp <= budget && tbl <= 96 * 1024;
     if (!tblsm) tbl = 0;
-    int wmax = (int)std::min<size_t>(16, (budget - tbl) / per_warp);
+    int wmax = (int)std::min<size_t>(16, (budget - tbl - slack) / per_warp);
     CML_REQUIRE(wmax >= 1, CML_ERR_ARG, "wide lattice ring does not fit in shared memory");
     const uint64_t sm = (uint64_t)ctx->sm_count;
     int wpc = wmax;
@@ -1403,11 +1415,13 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
         }
       }
     }
+    if (const char* e = getenv("CML_WIDE_WPC")) wpc = std::max(1, std::min(wmax, atoi(e)));
     Wd.warps_per_cta = (uint32_t)wpc;
     const unsigned grid = (unsigned)std::min<uint64_t>(sm, (Wd.n_list + wpc - 1) / wpc);
-    const size_t smem = tbl + (size_t)wpc * per_warp;
+    const size_t smem = tbl + slack + (size_t)wpc * per_warp;
     auto kern = tblsm ? k_fb_wide<Real, true> : k_fb_wide<Real, false>;
     if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<grid, wpc * 32, smem, ctx->stream>>>(Wd);
     ++ctx->launches;
     ++bt.n_fb_kernels;
@@ -1443,6 +1457,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     auto kern = ta ? (tv ? k_fb_lane<Real, true, true> : k_fb_lane<Real, true, false>)
                    : (tv ? k_fb_lane<Real, false, true> : k_fb_lane<Real, false, false>);
     if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<cdiv(bt.lane_tiles, kLaneWarps), kLaneWarps * 32, smem, ctx->stream>>>(L);
     ++ctx->launches;
     ++bt.n_fb_kernels;

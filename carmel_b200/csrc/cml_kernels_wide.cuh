@@ -28,6 +28,7 @@ namespace cmlk {
 constexpr int kWideStages = 4;          // chunks in flight per warp
 constexpr uint32_t kWideChunkRec = 256; // records per chunk (2 KB)
 constexpr uint32_t kWideChunkBytes = kWideChunkRec * 8;
+constexpr int kWidePrefetch = 12;       // chunks ahead of the sweep that are requested into L2
 
 struct WideArgs {
   const EllDesc* desc;
@@ -50,6 +51,8 @@ struct WideArgs {
   uint32_t ring;             // ring entries per warp (power of two)
   uint32_t warps_per_cta;
   int no_counts;
+  int l2_prefetch;           // chunks ahead of the sweep requested into L2 (0 = off)
+  int generic_addr;          // experiment: generic-pointer addressing in the inner loops
 };
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA 8.x; SASS: SYNCS.*, UBLKCP) --------------------------------------
@@ -77,89 +80,145 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// One warp's view of a record stream that arrives in chunks.  Chunk c of the current stream has global sequence number
-// seq0 + c (or seq0 + (n_chunks-1-c) when the stream is consumed backwards); sequence number q lives in slot q % stages
-// and completes phase (q / stages) & 1 of that slot's mbarrier.
+// One warp's view of a record stream that arrives in 2 KB chunks.  Chunk c of a stream always lives in slot c % stages
+// (so record idx sits at byte ((idx mod stages*256) * 8) of the buffer, whichever way the stream is consumed); every
+// issued chunk is waited for exactly once, so a slot's mbarrier phase parity is one bit that flips at each wait.
+// All fields are warp-uniform.
 struct WidePipe {
   uint32_t bar0, buf0;       // shared-memory addresses: mbarriers (8 B each), chunk buffers
-  uint32_t seq;              // sequence number of the next chunk to issue (monotone over the warp's lifetime)
-  uint32_t seq0;             // sequence number of the current stream's first consumed chunk
+  uint32_t wpar;             // bit s: parity to wait for on slot s
   const uint2* src;          // current stream
   uint32_t n_rec, n_chunks;  // records (even), chunks
-  uint32_t issued, waited, freed;  // counts in consumption order
-  bool reverse;
+  uint32_t issued, waited, freed;  // chunk counts in consumption order
+  // forward: records < wait_lim are readable; chunk `freed` may be refilled once the window starts at >= free_lim.
+  // reverse: records >= wait_lim are readable; the oldest chunk may be refilled once the window ends below free_lim.
+  uint32_t wait_lim, free_lim;
+  uint32_t pf;               // L2 prefetch distance in chunks (0 = off)
 };
 
-__device__ __forceinline__ uint32_t wide_chunk_of(const WidePipe& P, uint32_t ord) {  // consumption ordinal -> chunk index
-  return P.reverse ? P.n_chunks - 1 - ord : ord;
-}
-__device__ __forceinline__ void wide_issue(WidePipe& P, int lane) {  // issue consumption ordinal P.issued
-  if (lane == 0) {
-    const uint32_t c = wide_chunk_of(P, P.issued);
+template <bool REV, int ST = kWideStages>
+__device__ __forceinline__ void wide_issue(WidePipe& P, bool leader) {  // issue the next chunk in consumption order
+  if (leader) {
+    const uint32_t c = REV ? P.n_chunks - 1 - P.issued : P.issued;
     const uint32_t first = c * kWideChunkRec;
     const uint32_t bytes = min(kWideChunkRec, P.n_rec - first) * 8u;
-    const uint32_t slot = P.seq % kWideStages;
+    const uint32_t slot = c % ST;
     const uint32_t bar = P.bar0 + slot * 8u;
     fence_proxy_async();  // the slot's previous contents were read through the generic proxy
     mbar_expect_tx(bar, bytes);
     bulk_g2s(P.buf0 + slot * kWideChunkBytes, P.src + first, bytes, bar);
+    // pull the chunk kWidePrefetch positions further along the sweep into L2: the shared-memory ring only covers the
+    // L2 latency, the DRAM latency is covered here (no shared memory needed for the bytes in flight)
+    const uint32_t ahead = P.issued + P.pf;
+    if (P.pf && ahead < P.n_chunks) {
+      const uint32_t ca = REV ? P.n_chunks - 1 - ahead : ahead;
+      bulk_prefetch_l2(P.src + ca * kWideChunkRec, min(kWideChunkRec, P.n_rec - ca * kWideChunkRec) * 8u);
+    }
   }
-  ++P.seq;
   ++P.issued;
 }
-__device__ __forceinline__ void wide_open(WidePipe& P, const uint2* src, uint32_t n_rec, bool reverse, int lane) {
+template <bool REV, int ST = kWideStages>
+__device__ __forceinline__ void wide_open(WidePipe& P, const uint2* src, uint32_t n_rec, bool leader) {
   P.src = src;
   P.n_rec = n_rec;
   P.n_chunks = (n_rec + kWideChunkRec - 1) / kWideChunkRec;
-  P.reverse = reverse;
-  P.seq0 = P.seq;
   P.issued = P.waited = P.freed = 0;
-  __syncwarp();  // every lane is done with the previous stream's buffers
-  while (P.issued < P.n_chunks && P.issued < (uint32_t)kWideStages) wide_issue(P, lane);
+  P.wait_lim = REV ? P.n_chunks * kWideChunkRec : 0u;
+  P.free_lim = REV ? (P.n_chunks ? (P.n_chunks - 1) * kWideChunkRec : 0u) : kWideChunkRec;
+  __syncwarp();  // every lane is done with the previous stream's buffers (all of its chunks have been waited for)
+  if (leader)  // L2 prefetch of the chunks between the shared-memory ring and the steady-state prefetch distance
+    for (uint32_t a = ST; a < P.n_chunks && a < P.pf; ++a) {
+      const uint32_t ca = REV ? P.n_chunks - 1 - a : a;
+      bulk_prefetch_l2(src + ca * kWideChunkRec, min(kWideChunkRec, n_rec - ca * kWideChunkRec) * 8u);
+    }
+  while (P.issued < P.n_chunks && P.issued < (uint32_t)ST) wide_issue<REV, ST>(P, leader);
 }
-// make records [lo, hi] (stream indices, lo <= hi) readable; chunks wholly behind the window are refilled.
-__device__ __forceinline__ void wide_need(WidePipe& P, uint32_t lo, uint32_t hi, int lane) {
-  uint32_t o_first, o_last;  // consumption ordinals of the first / last chunk the window touches
-  if (!P.reverse) {
-    o_first = lo / kWideChunkRec;
-    o_last = hi / kWideChunkRec;
+// make records [lo, hi] (lo <= hi, at most two chunks) readable; chunks wholly behind the window are refilled.
+// The common case (window inside the chunks already waited for) costs two compares.
+template <bool REV, int ST = kWideStages>
+__device__ __forceinline__ void wide_need(WidePipe& P, uint32_t lo, uint32_t hi, bool leader) {
+  if (!REV) {
+    if (lo >= P.free_lim) {
+      __syncwarp();  // all lanes have consumed the chunks before the window
+      do {
+        ++P.freed;
+        P.free_lim += kWideChunkRec;
+        if (P.issued < P.n_chunks) wide_issue<REV, ST>(P, leader);
+      } while (lo >= P.free_lim);
+    }
+    while (hi >= P.wait_lim) {
+      const uint32_t slot = P.waited % ST;
+      mbar_wait(P.bar0 + slot * 8u, (P.wpar >> slot) & 1u);
+      P.wpar ^= 1u << slot;
+      ++P.waited;
+      P.wait_lim += kWideChunkRec;
+    }
   } else {
-    o_first = P.n_chunks - 1 - hi / kWideChunkRec;
-    o_last = P.n_chunks - 1 - lo / kWideChunkRec;
-  }
-  if (P.freed < o_first) {
-    __syncwarp();  // all lanes have consumed the chunks before the window
-    while (P.freed < o_first) {
-      ++P.freed;
-      if (P.issued < P.n_chunks) wide_issue(P, lane);
+    if (hi < P.free_lim) {
+      __syncwarp();
+      do {
+        ++P.freed;
+        P.free_lim -= kWideChunkRec;  // (reaches 0 with the last chunk: `hi < 0` never holds again)
+        if (P.issued < P.n_chunks) wide_issue<REV, ST>(P, leader);
+      } while (hi < P.free_lim);
+    }
+    while (lo < P.wait_lim) {
+      const uint32_t slot = (P.n_chunks - 1 - P.waited) % ST;
+      mbar_wait(P.bar0 + slot * 8u, (P.wpar >> slot) & 1u);
+      P.wpar ^= 1u << slot;
+      ++P.waited;
+      P.wait_lim -= kWideChunkRec;
     }
   }
-  while (P.waited <= o_last) {
-    const uint32_t q = P.seq0 + P.waited;
-    mbar_wait(P.bar0 + (q % kWideStages) * 8u, (q / kWideStages) & 1u);
-    ++P.waited;
-  }
 }
+// shared-memory accessors on 32-bit shared addresses (no generic-address conversion in the inner loops)
+template <typename Real>
+__device__ __forceinline__ Real lds_real(uint32_t a);
+template <>
+__device__ __forceinline__ double lds_real<double>(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
+template <>
+__device__ __forceinline__ float lds_real<float>(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
+  return v;
+}
+template <int ST = kWideStages>
 __device__ __forceinline__ uint2 wide_rec(const WidePipe& P, uint32_t idx) {  // record idx of the current stream
-  const uint32_t c = idx / kWideChunkRec;
-  const uint32_t q = P.seq0 + (P.reverse ? P.n_chunks - 1 - c : c);
-  return lds_u2(P.buf0 + (q % kWideStages) * kWideChunkBytes + (idx % kWideChunkRec) * 8u);
+  return lds_u2(P.buf0 + ((idx & (ST * kWideChunkRec - 1)) << 3));
 }
 
 template <typename Real, bool TBL>  // TBL: both class tables staged in shared memory
 static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
   extern __shared__ __align__(128) unsigned char smem_wide[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  // ---- shared memory: [class tables] | per warp: mbarriers (64 B) | chunk buffers | ring
-  size_t tbl_bytes = 0;
+  const bool leader = lane == 0;
+  // ---- shared memory (offsets from the first 8 KB boundary, so that a warp's chunk buffer and its ring are aligned to
+  //      their own sizes and "base | (offset & mask)" is one LOP3):
+  //      chunk buffers [warps][8 KB] | mbarriers [warps][64 B] | rings [warps][ring] | class tables
+  constexpr uint32_t kBuf = kWideStages * kWideChunkBytes;
+  constexpr int LR = sizeof(Real) == 8 ? 3 : 2;
+  const uint32_t ring_bytes = A.ring << LR;
+  const uint32_t s0base = (smem_u32(smem_wide) + (kBuf - 1)) & ~(kBuf - 1);
+  unsigned char* g0base = smem_wide + (s0base - smem_u32(smem_wide));
+  const uint32_t off_bar = A.warps_per_cta * kBuf;
+  const uint32_t off_ring = (off_bar + A.warps_per_cta * 64u + ring_bytes - 1) & ~(ring_bytes - 1);
+  const uint32_t off_tbl = off_ring + A.warps_per_cta * ring_bytes;
   const Real* aw = (const Real*)A.a_w;
   const uint32_t* asl = A.a_slot;
   const Real* vw = (const Real*)A.v_w;
   const uint32_t* vsl = A.v_slot;
+  uint32_t aw_s = 0;  // shared address of the arc-class weights (TBL)
   if (TBL) {
-    Real* s_aw = (Real*)smem_wide;
+    Real* s_aw = (Real*)(g0base + off_tbl);
     Real* s_vw = s_aw + A.n_a;
     uint32_t* s_asl = (uint32_t*)(s_vw + A.n_v);
     uint32_t* s_vsl = s_asl + A.n_a;
@@ -175,22 +234,35 @@ static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
     vw = s_vw;
     asl = s_asl;
     vsl = s_vsl;
-    tbl_bytes = ((size_t)(A.n_a + A.n_v) * (sizeof(Real) + 4) + 127) & ~(size_t)127;
+    aw_s = s0base + off_tbl;
   }
-  const size_t per_warp = 64 + (size_t)kWideStages * kWideChunkBytes + (size_t)A.ring * sizeof(Real);
-  unsigned char* wbase = smem_wide + tbl_bytes + (size_t)wib * per_warp;
   WidePipe P;
-  P.bar0 = smem_u32(wbase);
-  P.buf0 = P.bar0 + 64;
-  P.seq = 0;
-  Real* ring = (Real*)(wbase + 64 + (size_t)kWideStages * kWideChunkBytes);
+  P.buf0 = s0base + (uint32_t)wib * kBuf;
+  P.bar0 = s0base + off_bar + (uint32_t)wib * 64u;
+  P.wpar = 0;
+  P.pf = (uint32_t)A.l2_prefetch;
+  const uint32_t ring_s = s0base + off_ring + (uint32_t)wib * ring_bytes;
+  Real* ring = (Real*)(g0base + off_ring + (size_t)wib * ring_bytes);
   const uint32_t M = A.ring - 1;
+  const uint32_t M8 = M << LR;
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < kWideStages; ++k) mbar_init(P.bar0 + k * 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();  // tables staged, barriers initialised
+  // keep the address bases in registers (ptxas would otherwise rematerialise them from the kernel parameters inside the
+  // inner loops: ~20 of 60 instructions per 4-row block)
+  uint32_t buf_s = P.buf0, ring_m8 = M8, ring_b = ring_s, aw_b = aw_s;
+  asm volatile("" : "+r"(buf_s), "+r"(ring_m8), "+r"(ring_b), "+r"(aw_b));
+  // record r of the current stream (byte offset o = 8*r): buffer | (o & (8 KB - 1)); ring entry of state x: ring | ((x << LR) & M8)
+  const bool ga = A.generic_addr != 0;
+  const uint2* cbuf = (const uint2*)(g0base + (size_t)wib * kBuf);
+  auto rec_at = [&](uint32_t byte_off) -> uint2 {
+    return ga ? cbuf[(byte_off >> 3) & (kWideStages * kWideChunkRec - 1)] : lds_u2(buf_s | (byte_off & (kBuf - 1)));
+  };
+  auto ring_at = [&](uint32_t x) -> Real { return ga ? ring[x & M] : lds_real<Real>(ring_b | ((x << LR) & ring_m8)); };
+  auto aw_at = [&](uint32_t c) -> Real { return (TBL && !ga) ? lds_real<Real>(aw_b + (c << LR)) : aw[c]; };
 
   const uint32_t gw = blockIdx.x * A.warps_per_cta + wib, nw = gridDim.x * A.warps_per_cta;
   for (uint32_t li = gw; li < A.n_list; li += nw) {
@@ -203,7 +275,7 @@ static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
     const int nl = (int)d.n_levels;
 
     // ================================================================ forward
-    wide_open(P, A.ell_in + d.in_base, d.in_len, false, lane);
+    wide_open<false>(P, A.ell_in + d.in_base, d.in_len, leader);
     if (lane == 0) {
       ring[0] = Real(1);
       ag[0] = Real(1);
@@ -229,26 +301,33 @@ static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
       Real a0 = 0, a1 = 0;
       if (D) {
         if (last_event <= min_src) {
-          uint32_t k = 0;
-          for (; k + 4 <= D; k += 4) {
-            wide_need(P, m.x + k * W, m.x + (k + 4) * W - 1, lane);
-            const uint2 r0 = wide_rec(P, m.x + k * W + lw), r1 = wide_rec(P, m.x + (k + 1) * W + lw);
-            const uint2 r2 = wide_rec(P, m.x + (k + 2) * W + lw), r3 = wide_rec(P, m.x + (k + 3) * W + lw);
-            const Real x0 = ring[r0.x & M], x1 = ring[r1.x & M], x2 = ring[r2.x & M], x3 = ring[r3.x & M];
-            const Real w0 = aw[r0.y], w1 = aw[r1.y], w2 = aw[r2.y], w3 = aw[r3.y];
+          uint32_t k = 0, base = m.x;  // base: first record of row k (warp-uniform)
+          const uint32_t W4 = 4 * W, Wb = W << 3;
+          uint32_t o = (base + lw) << 3;  // byte offset of this lane's record in row k
+          for (; k + 4 <= D; k += 4, base += W4, o += 4 * Wb) {
+            wide_need<false>(P, base, base + W4 - 1, leader);
+            const uint2 r0 = rec_at(o), r1 = rec_at(o + Wb), r2 = rec_at(o + 2 * Wb), r3 = rec_at(o + 3 * Wb);
+            const Real x0 = ring_at(r0.x), x1 = ring_at(r1.x), x2 = ring_at(r2.x), x3 = ring_at(r3.x);
+            const Real w0 = aw_at(r0.y), w1 = aw_at(r1.y), w2 = aw_at(r2.y), w3 = aw_at(r3.y);
             a0 = fma(x0, w0, a0);
             a1 = fma(x1, w1, a1);
             a0 = fma(x2, w2, a0);
             a1 = fma(x3, w3, a1);
           }
-          for (; k < D; ++k) {
-            wide_need(P, m.x + k * W, m.x + (k + 1) * W - 1, lane);
-            const uint2 r0 = wide_rec(P, m.x + k * W + lw);
-            a0 = fma(ring[r0.x & M], aw[r0.y], a0);
+          if (k < D) {  // 1..3 rows left: absent rows read record {state 0, padding class} (weight 0)
+            const uint32_t rem = D - k;
+            wide_need<false>(P, base, base + rem * W - 1, leader);
+            const uint2 pad = make_uint2(0u, 0u);
+            const uint2 r0 = rec_at(o), r1 = rem > 1 ? rec_at(o + Wb) : pad, r2 = rem > 2 ? rec_at(o + 2 * Wb) : pad;
+            const Real x0 = ring_at(r0.x), x1 = ring_at(r1.x), x2 = ring_at(r2.x);
+            const Real w0 = aw_at(r0.y), w1 = aw_at(r1.y), w2 = aw_at(r2.y);
+            a0 = fma(x0, w0, a0);
+            a1 = fma(x1, w1, a1);
+            a0 = fma(x2, w2, a0);
           }
         } else {  // a source level inside the window carries another power-of-two scale (rare)
           for (uint32_t k = 0; k < D; ++k) {
-            wide_need(P, m.x + k * W, m.x + (k + 1) * W - 1, lane);
+            wide_need<false>(P, m.x + k * W, m.x + (k + 1) * W - 1, leader);
             const uint2 r0 = wide_rec(P, m.x + k * W + lw);
             const Real wv = aw[r0.y];
             if (wv != Real(0)) {
@@ -284,7 +363,7 @@ static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
     const double cw = d.weight / (double)afin;
 
     // ================================================================ backward + counts
-    wide_open(P, A.ell_out + d.out_base, d.out_len, true, lane);
+    wide_open<true>(P, A.ell_out + d.out_base, d.out_len, leader);
     int Fnext = 0, last_event_b = 0x7fffffff;
     mnext = __ldg(&meta[nl - 1]);
     vnext = 0;
@@ -318,26 +397,36 @@ static __global__ void __launch_bounds__(512) k_fb_wide(WideArgs A) {
       if (O) {
         if (uniform && !A.any_a_slot) {  // no per-arc count work at all
           // (rows are taken last to first: the outgoing stream is consumed strictly backwards)
-          uint32_t k = O;
+          uint32_t k = O, base = m.y + O * W;  // base: one past the last record of row k-1 (warp-uniform)
+          const uint32_t W4 = 4 * W, Wb = W << 3;
+          uint32_t o = (base + lw) << 3;
           for (; k >= 4; k -= 4) {
-            wide_need(P, m.y + (k - 4) * W, m.y + k * W - 1, lane);
-            const uint2 r0 = wide_rec(P, m.y + (k - 1) * W + lw), r1 = wide_rec(P, m.y + (k - 2) * W + lw);
-            const uint2 r2 = wide_rec(P, m.y + (k - 3) * W + lw), r3 = wide_rec(P, m.y + (k - 4) * W + lw);
-            const Real x0 = ring[r0.x & M], x1 = ring[r1.x & M], x2 = ring[r2.x & M], x3 = ring[r3.x & M];
-            const Real w0 = aw[r0.y], w1 = aw[r1.y], w2 = aw[r2.y], w3 = aw[r3.y];
+            base -= W4;
+            o -= 4 * Wb;
+            wide_need<true>(P, base, base + W4 - 1, leader);
+            const uint2 r0 = rec_at(o + 3 * Wb), r1 = rec_at(o + 2 * Wb), r2 = rec_at(o + Wb), r3 = rec_at(o);
+            const Real x0 = ring_at(r0.x), x1 = ring_at(r1.x), x2 = ring_at(r2.x), x3 = ring_at(r3.x);
+            const Real w0 = aw_at(r0.y), w1 = aw_at(r1.y), w2 = aw_at(r2.y), w3 = aw_at(r3.y);
             b0 = fma(x0, w0, b0);
             b1 = fma(x1, w1, b1);
             b0 = fma(x2, w2, b0);
             b1 = fma(x3, w3, b1);
           }
-          for (; k > 0; --k) {
-            wide_need(P, m.y + (k - 1) * W, m.y + k * W - 1, lane);
-            const uint2 r0 = wide_rec(P, m.y + (k - 1) * W + lw);
-            b0 = fma(ring[r0.x & M], aw[r0.y], b0);
+          if (k > 0) {  // rows k-1 .. 0
+            base -= k * W;
+            o -= k * Wb;
+            wide_need<true>(P, base, base + k * W - 1, leader);
+            const uint2 pad = make_uint2(0u, 0u);
+            const uint2 r0 = rec_at(o), r1 = k > 1 ? rec_at(o + Wb) : pad, r2 = k > 2 ? rec_at(o + 2 * Wb) : pad;
+            const Real x0 = ring_at(r0.x), x1 = ring_at(r1.x), x2 = ring_at(r2.x);
+            const Real w0 = aw_at(r0.y), w1 = aw_at(r1.y), w2 = aw_at(r2.y);
+            b0 = fma(x0, w0, b0);
+            b1 = fma(x1, w1, b1);
+            b0 = fma(x2, w2, b0);
           }
         } else {
           for (uint32_t k = O; k-- > 0;) {
-            wide_need(P, m.y + k * W, m.y + (k + 1) * W - 1, lane);
+            wide_need<true>(P, m.y + k * W, m.y + (k + 1) * W - 1, leader);
             const uint2 r0 = wide_rec(P, m.y + k * W + lw);
             const Real wv = aw[r0.y];
             Real tt = wv * ring[r0.x & M];
