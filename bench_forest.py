@@ -1,7 +1,8 @@
 """bench_forest.py -- forest-em inside-outside EM throughput (hyperedges/s); run as `python bench.py --workload forest`.
 
-Workload = BASELINE.json configs[4]: 100k random AND/OR derivation forests per GPU (about 500
-hyperedges each, 15 % shared sub-forests), rule ids Zipf over 10^6 rules, normalization groups of 2..50 rules.
+Workload = BASELINE.json configs[4]: 100k random AND/OR derivation forests IN TOTAL (strong scaling:
+rank r of N keeps block r), EVERY forest its own random shape (about 500 hyperedges each, 15 % shared sub-forests), rule
+ids Zipf over 10^6 rules, normalization groups of 2..50 rules.
 A step = one EM iteration: inside + outside + expected counts over the resident forests, (all-reduce of the rule
 count table when N>1), NormalizeGroups M-step.  Same JSON contract as bench.py; the unit of work is one hyperedge
 (an AND node with its tail list)."""
@@ -56,20 +57,56 @@ def cpu_forest_oracle(fs, n_sample, procs, precision, budget_s=15.0):
 
 
 def config_of(a, world):
-    return {"workload": "configs[4] forest-em inside-outside: 100k random AND/OR forests per GPU (~500 hyperedges each, "
-                        "15% shared sub-forests), rule ids Zipf(1.0) over 1e6 rules, normgroups of 2..50 rules",
-            "forests_per_gpu": 100000 * a.scale, "l2": "forest topology ~2 GB per GPU > 126 MB L2",
-            "parallelism": f"forests sharded over {world} GPU(s), one NCCL all-reduce of the rule count table per iteration"}
+    return {"workload": f"configs[4] forest-em inside-outside: {100000 * a.scale} random AND/OR forests in total, every forest "
+                        "its own shape (~500 hyperedges each, 15% shared sub-forests), rule ids Zipf(1.0) over 1e6 rules, "
+                        "normgroups of 2..50 rules",
+            "forests_total": 100000 * a.scale, "l2": "forest topology ~2 GB > 126 MB L2",
+            "parallelism": f"forests sharded over {world} GPU(s) (strong scaling), one NCCL all-reduce of the rule count "
+                           "table per iteration, issued by the library on its own stream"}
+
+
+def inside_parity(fs, n, precision, local):
+    """ln inside of the first n forests at uniform initial weights: GPU (a small separate context) against the CPU
+    oracle (forest-em -i 0 -S).  Returns {"n", "max_rel", "tol", "ok"}."""
+    import numpy as np
+    from carmel_b200 import synth
+    from carmel_b200.forest_api import Forests
+    n = min(n, len(fs["node_off"]) - 1)
+    d = tempfile.mkdtemp(prefix="cb200_fpar_")
+    try:
+        files = synth.write_forests(fs, d, n_forests=n)
+        flag = ["-U"] if precision == 64 else []
+        subprocess.run([FOREST_ORACLE, *flag, "-f", files["forests"], "-n", files["norm"], "-i", "0", "-S", f"{d}/s.out"],
+                       capture_output=True, text=True, check=True)
+        want = np.array([float(t[2:]) if t.startswith("e^") else (np.log(float(t)) if float(t) > 0 else -np.inf)
+                         for t in open(f"{d}/s.out").read().split()][:n])
+        G = Forests(device=local, precision=precision)
+        G.set_rules(fs["rulespace"], fs["group_off"], fs["group_members"])
+        w0 = np.full(fs["rulespace"], -np.inf)
+        go, gm = fs["group_off"].astype(np.int64), fs["group_members"].astype(np.int64)
+        w0[gm] = -np.log(np.repeat(np.diff(go), np.diff(go)).astype(np.float64))
+        G.set_params(w0)
+        e = int(fs["node_off"][n])
+        G.add(fs["node_off"][:n + 1], fs["next"][:e], fs["label"][:e], fs["backref"][:e])
+        G.estimate()
+        got = G.inside(n)
+        G.close()
+        rel = float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))))
+        tol = 1e-6 if precision == 64 else 1e-4
+        return {"n": int(n), "max_rel": rel, "tol": tol, "ok": bool(rel <= tol),
+                "what": "ln inside[root] per forest at uniform initial weights, GPU vs CPU oracle (forest-em -i 0 -S)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def reference_arm(a):
     from carmel_b200 import synth
     t0 = time.time()
     procs = max(1, os.cpu_count() or 1)
-    fs = synth.make_forests(n_forests=100 * procs, n_rules=1000000, templates=32)
+    fs = synth.make_forests(n_forests=100 * procs, n_rules=1000000, templates=0)
     cb = cpu_forest_oracle(fs, 100 * procs, procs, a.precision, budget_s=8.0 * max(1, min(a.steps, 4)))
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if a.precision == 64 else "f32", "data": "synthetic", "config": config_of(a, a.gpus),
             "impl": "reference", "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -77,7 +114,9 @@ def reference_arm(a):
     print(json.dumps(line))
 
 
-def run(a, rank, world, local):
+def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
+    """as_leg: called by bench.py for its c5 leg (process group already up; returns the line on rank 0 instead of
+    printing it).  token: NCCL rendezvous token for the library's own all-reduce (world > 1)."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -87,13 +126,20 @@ def run(a, rank, world, local):
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (carmel_b200 has no CPU fallback)"
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not as_leg:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1 and token is None:
+        import carmel_b200 as cb
+        box = [cb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        token = box[0]
     t_build = time.time()
-    fs = synth.make_forests(n_forests=100000 * a.scale, n_rules=1000000, seed=20260105 + 1000 * rank, templates=128)
+    fs = synth.make_forests(n_forests=100000 * a.scale, n_rules=1000000, seed=20260105, templates=0, part=(rank, world))
     stream = torch.cuda.Stream()
     F = Forests(device=local, precision=a.precision)
     F.set_stream(stream.cuda_stream)
+    if world > 1:
+        F.comm_init_rank(world, rank, token)
     F.set_rules(fs["rulespace"], fs["group_off"], fs["group_members"])
     rulespace = fs["rulespace"]
     w0 = np.full(rulespace, -np.inf)
@@ -108,22 +154,9 @@ def run(a, rank, world, local):
     if world > 1:
         dist.all_reduce(tot)
     he_total, nodes_total, links_total, forests_total = (float(x) for x in tot.tolist())
-    reduce_tensor = {}
-
-    def allreduce(ptr, n):
-        t = reduce_tensor.get((ptr, n))
-        if t is None:
-            class _Arr:
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-            t = torch.as_tensor(_Arr(), device=torch.device("cuda", local))
-            reduce_tensor[(ptr, n)] = t
-        with torch.cuda.stream(stream):
-            dist.all_reduce(t)
-
     def step():
         F.estimate_launch()
-        if world > 1:
-            allreduce(*F.reduce_buffer())
+        F.allreduce_counts()  # NCCL on the library's stream (no-op on one GPU)
         r = F.estimate_finish()
         F.maximize(0.0, 0.0, UNIFORM)
         return r
@@ -173,8 +206,7 @@ def run(a, rank, world, local):
     def e2e_step():
         lib.cml_forests_set_params(F.h, C.cast(h_params.data_ptr(), f64p))            # H2D: rule weights
         F.estimate_launch()
-        if world > 1:
-            allreduce(*F.reduce_buffer())
+        F.allreduce_counts()
         F.estimate_finish()                                                           # D2H: likelihood scalars
         lib.cml_forests_get_counts(F.h, C.cast(h_counts.data_ptr(), f64p), rulespace)  # D2H: expected rule counts
         F.maximize(0.0, 0.0, UNIFORM)
@@ -207,21 +239,30 @@ def run(a, rank, world, local):
                     f" (inside + outside + counts, {k_ms[0][1]} launch(es) per iteration)",
                     "kernel_ms": kms, "algorithmic_bytes_per_hyperedge": bytes_step / max(1, tot_local["hyperedges"]),
                     "hyperedges_per_launch_set": tot_local["hyperedges"], "kernel_share_of_step": kms / (ms / a.steps)}
+        cpu = None
+        if with_cpu:
+            try:
+                procs = max(1, os.cpu_count() or 1)
+                cpu = cpu_forest_oracle(fs, 100 * procs, procs, a.precision, budget_s=10.0 if as_leg else 15.0)
+            except Exception as ex:
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         try:
-            procs = max(1, os.cpu_count() or 1)
-            cpu = cpu_forest_oracle(fs, 100 * procs, procs, a.precision, budget_s=15.0)
+            parity = inside_parity(fs, 256, a.precision, local)
         except Exception as ex:
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+            parity = {"n": 0, "max_rel": None, "ok": False, "error": str(ex)[:200]}
+        roofline["padded_steps_over_steps"] = (lay["padded_steps"] / lay["steps"]) if lay.get("steps") else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "parity": parity,
                 "dtype": "f64" if a.precision == 64 else "f32", "data": "synthetic", "config": config_of(a, world),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "totals": {"forests": forests_total, "hyperedges": he_total, "nodes": nodes_total, "links": links_total,
                            "rulespace": rulespace, "avg_ln_p": last[0] / max(1.0, last[2] - last[1])},
-                "layout": lay}
-        print(json.dumps(line))
+                "layout": lay, "templates": "every forest its own shape (csrc/tools/forest_synth.c)"}
+        if not as_leg:
+            print(json.dumps(line))
     if world > 1:
         dist.barrier()
     F.close()
-    if world > 1:
+    if world > 1 and not as_leg:
         dist.destroy_process_group()
+    return line if rank == 0 else None

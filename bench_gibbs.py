@@ -89,7 +89,8 @@ def reference_arm(a):
     print(json.dumps(line))
 
 
-def run(a, rank, world, local):
+def run(a, rank, world, local, as_leg=False, with_cpu=True):
+    """as_leg: called by bench.py for its c4 leg (returns the line instead of printing it; no process-group handling)"""
     import torch
     import torch.distributed as dist
     import carmel_b200 as cb
@@ -98,7 +99,7 @@ def run(a, rank, world, local):
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (carmel_b200 has no CPU fallback)"
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not as_leg:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d = tempfile.mkdtemp(prefix=f"cb200_gibbs_{rank}_")
     w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104 + rank)
@@ -231,11 +232,13 @@ def run(a, rank, world, local):
                         "traffic": None, "peak_source": which,
                         "kernel": "k_gibbs (backward filter + forward sample per block) + k_gibbs_apply",
                         "kernel_ms": ms / a.steps, "algorithmic_bytes_per_sample": bytes_step / max(1, blocks)}
-        try:
-            procs = max(1, os.cpu_count() or 1)
-            cpu = cpu_oracle_gibbs(w["files"], 25 * procs, procs)
-        except Exception as ex:
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        cpu = None
+        if with_cpu:
+            try:
+                procs = max(1, os.cpu_count() or 1)
+                cpu = cpu_oracle_gibbs(w["files"], 25 * procs, procs, sweeps=2 if as_leg else 3)
+            except Exception as ex:
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_of(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
@@ -249,10 +252,12 @@ def run(a, rank, world, local):
         if is_dense:
             line["config"]["l2"] = ("dense-state working set (symbols, beta rows, probability table) fits in L2: L2 flushed "
                                     "(256 MB write) between timed sweeps, each sweep timed with its own CUDA-event pair")
-        print(json.dumps(line))
+        if not as_leg:
+            print(json.dumps(line))
     if world > 1:
         dist.barrier()
     job.close()
     shutil.rmtree(d, ignore_errors=True)
-    if world > 1:
+    if world > 1 and not as_leg:
         dist.destroy_process_group()
+    return line if rank == 0 else None

@@ -121,6 +121,19 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.cml_reduce_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.cml_use_reduce_buffer.argtypes = [vp, vp, C.c_uint64]
     lib.cml_maximize.argtypes = [vp, C.c_double, _f64p]
+    lib.cml_em_step.argtypes = [vp, C.c_double, C.POINTER(CmlEstimateResult), _f64p]
+    lib.cml_snapshot_previous.argtypes = [vp, C.c_int]
+    lib.cml_comm_unique_id.argtypes = [C.c_char_p]
+    lib.cml_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    lib.cml_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    lib.cml_set_comm.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.cml_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cml_allreduce_counts.argtypes = [vp]
+    lib.cml_allreduce_buffer.argtypes = [vp, vp, C.c_uint64]
+    lib.cml_allreduce_host.argtypes = [vp, _f64p, C.c_uint64]
+    lib.cml_collective_count.argtypes = [vp]
+    lib.cml_collective_count.restype = C.c_uint64
+    lib.cml_job_set_comm.argtypes = [vp, C.c_char_p]
     lib.cml_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.cml_layout_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
     lib.cml_lane_stats.argtypes = [vp] + [C.POINTER(C.c_uint64)] * 4
@@ -317,6 +330,27 @@ class Context:
     def estimate_launch(self):
         self._check(self.lib.cml_estimate_launch(self.h))
 
+    def em_step(self, rate: float = 1.0):
+        """one whole EM iteration (E-step, all-reduce when a communicator is set, M-step), one host synchronisation;
+        returns (CmlEstimateResult of the weights the iteration started from, max weight change)"""
+        r = CmlEstimateResult()
+        d = C.c_double()
+        self._check(self.lib.cml_em_step(self.h, rate, C.byref(r), C.cast(C.byref(d), _f64p)))
+        return r, float(d.value)
+
+    def snapshot_previous(self, slot: int = 0):
+        self._check(self.lib.cml_snapshot_previous(self.h, slot))
+
+    def comm_init_rank(self, n_ranks: int, rank: int, token: bytes):
+        assert len(token) == 128
+        self._check(self.lib.cml_comm_init_rank(self.h, n_ranks, rank, token))
+
+    def allreduce_counts(self):
+        self._check(self.lib.cml_allreduce_counts(self.h))
+
+    def collective_count(self) -> int:
+        return int(self.lib.cml_collective_count(self.h))
+
     def estimate_finish(self) -> CmlEstimateResult:
         r = CmlEstimateResult()
         self._check(self.lib.cml_estimate_finish(self.h, C.byref(r)))
@@ -409,11 +443,20 @@ class Context:
         self._check(self.lib.cml_gibbs_get_samples(self.h, C.cast(len_ptr, _u32p), C.cast(arcs_ptr, _u32p), cap))
 
 
+def comm_unique_id() -> bytes:
+    """128-byte NCCL rendezvous token (cml_comm_unique_id): create on rank 0, broadcast to the other ranks"""
+    buf = C.create_string_buffer(128)
+    rc = load_library().cml_comm_unique_id(buf)
+    if rc != 0:
+        raise CarmelB200Error(rc, "cml_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 class Job:
     """One `carmel -t ...` run (cml_job): argv in carmel's grammar.  After prepare() the job's Context
     (borrowed, owned by the job) can be driven step by step; train() runs the reference's EM loop."""
 
-    def __init__(self, argv: list[str], allreduce=None):
+    def __init__(self, argv: list[str], allreduce=None, comm_token: bytes | None = None):
         self.lib = load_library()
         args = ["carmel-b200", *argv]
         arr = (C.c_char_p * len(args))(*[a.encode() for a in args])
@@ -428,6 +471,9 @@ class Job:
         if allreduce is not None:
             self._cb = ALLREDUCE_FN(lambda user, ptr, n: allreduce(int(ptr), int(n)))
             self.lib.cml_job_set_allreduce(self.h, self._cb, None)
+        if comm_token is not None:  # NCCL rendezvous token (comm_unique_id on rank 0, shipped to every rank)
+            assert len(comm_token) == 128
+            self._check(self.lib.cml_job_set_comm(self.h, comm_token))
         self.ctx = None
 
     def _check(self, rc):

@@ -44,12 +44,13 @@ def _sources(dirpath: str) -> list[str]:
     out = []
     for base, _, files in os.walk(dirpath):
         for f in files:
-            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h")):
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".c")):
                 out.append(os.path.join(base, f))
     return out
 
 
 FOREST_CLI = os.path.join(OUT, "forest-em-b200")
+SYNTH_LIB = os.path.join(OUT, "libcb200_synth.so")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -81,7 +82,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(lib_src))) as ex:
         objs = list(ex.map(compile_one, lib_src))
-    subprocess.run([nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *objs, "-lcudart"], check=True)
+    subprocess.run([nvcc, *NVCC_FLAGS, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"], check=True)
+    # bench / test tooling (not part of the product library): the synthetic forest generator
+    tool = os.path.join(CSRC, "tools", "forest_synth.c")
+    if os.path.exists(tool):
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", SYNTH_LIB, tool], check=True)
     for main, exe in ((os.path.join(host, "main.cpp"), CLI), (os.path.join(host, "forest_main.cpp"), FOREST_CLI)):
         if os.path.exists(main):
             subprocess.run(["g++", "-O3", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe, main,

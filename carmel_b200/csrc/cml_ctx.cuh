@@ -166,6 +166,20 @@ struct cml_ctx {
 
   std::vector<std::unique_ptr<Batch>> batches;
   bool estimate_pending = false;
+  int opt_allow_empty = 0;   // CML_OPT_ALLOW_EMPTY: an E-step over no resident examples contributes zeros (empty shard)
+
+  // collective (cml_comm.cu): ncclComm_t of this rank, or null for a single-GPU context
+  void* comm = nullptr;
+  bool own_comm = false;
+  int comm_rank = 0, comm_size = 1;
+  uint64_t collectives = 0;
+  DevArray<double> host_scratch;  // 64 doubles: small host-side all-reduces (corpus statistics)
+  // fused EM step (cml_em_step): pinned result block, CUDA graph of the whole iteration
+  double* h_step = nullptr;       // pinned: sum ln P, sum w ln P, n_zero, max change (bits)
+  cudaGraphExec_t graph = nullptr;
+  bool graph_dirty = true, capturing = false;
+  uint64_t graph_launches = 0, graph_collectives = 0;  // kernels / collectives one replay stands for
+  int opt_no_graph = 0;           // CML_OPT_NO_GRAPH: cml_em_step enqueues its launches one by one
   // host copies of the chains (the dense-state factorisation needs them)
   std::vector<uint32_t> h_chain_off, h_chain_param, h_param_tie;
   std::vector<double> h_arc_prior;

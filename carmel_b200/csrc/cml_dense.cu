@@ -713,7 +713,7 @@ static int launch_dense_tc(cml_ctx* ctx) {
     CML_CUDA(cudaEventCreate(&D.ev0));
     CML_CUDA(cudaEventCreate(&D.ev1));
   }
-  CML_CUDA(cudaEventRecord(D.ev0, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev0, s));
   if (D.tc_groups) {
     A.rows = reinterpret_cast<float*>(D.alpha_g.p);
     A.exps = D.exp_g.p;
@@ -727,7 +727,7 @@ static int launch_dense_tc(cml_ctx* ctx) {
     k_dense_tc_counts<<<std::max(1u, std::min<unsigned>(cdiv(D.n_seq, kDW), 4u * ctx->sm_count)), kDW * 32, csmem, s>>>(A);
     ctx->launches += 3;
   }
-  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev1, s));
   if (D.n_seq) {
     cmlk::k_reduce_lnp<<<std::min<unsigned>(cdiv(D.n_seq, 256), 4 * ctx->sm_count), 256, 0, s>>>(
         D.ex_lnp.p, D.seq_weight.p, D.n_seq, ctx->reduce + ctx->n_slots);
@@ -773,10 +773,10 @@ int launch_dense(cml_ctx* ctx) {
     CML_CUDA(cudaEventCreate(&D.ev0));
     CML_CUDA(cudaEventCreate(&D.ev1));
   }
-  CML_CUDA(cudaEventRecord(D.ev0, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev0, s));
   kern<<<grid, kDW * 32, smem, s>>>(A);
   ++ctx->launches;
-  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev1, s));
   if (D.n_seq) {
     cmlk::k_reduce_lnp<<<std::min<unsigned>(cdiv(D.n_seq, 256), 4 * ctx->sm_count), 256, 0, s>>>(
         D.ex_lnp.p, D.seq_weight.p, D.n_seq, ctx->reduce + ctx->n_slots);
@@ -1120,12 +1120,12 @@ int launch_sparse(cml_ctx* ctx) {
     CML_CUDA(cudaEventCreate(&D.ev0));
     CML_CUDA(cudaEventCreate(&D.ev1));
   }
-  CML_CUDA(cudaEventRecord(D.ev0, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev0, s));
   if (D.n_tiles) {
     kern<<<cdiv(D.n_tiles, kSW), kSW * 32, smem, s>>>(A);
     ++ctx->launches;
   }
-  CML_CUDA(cudaEventRecord(D.ev1, s));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev1, s));
   if (ctx->n_hot) {
     cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, s>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p, ctx->reduce);
     ++ctx->launches;

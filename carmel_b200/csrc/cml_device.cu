@@ -16,6 +16,7 @@
 #include "cml_kernels_model.cuh"
 
 static thread_local std::string g_create_err;
+void cml_comm_release(cml_ctx* ctx);  // cml_comm.cu
 
 // -------------------------------------------------------------------------------------------------
 // context
@@ -77,6 +78,9 @@ extern "C" void cml_destroy(cml_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cml_comm_release(ctx);
+  if (ctx->graph) cudaGraphExecDestroy(ctx->graph);
+  if (ctx->h_step) cudaFreeHost(ctx->h_step);
   ctx->batches.clear();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -91,6 +95,7 @@ extern "C" int cml_set_stream(cml_ctx* ctx, void* s) {
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)s;
   ctx->own_stream = false;
+  ctx->graph_dirty = true;
   return CML_OK;
 }
 
@@ -120,10 +125,18 @@ extern "C" int cml_set_option(cml_ctx* ctx, int option, int value) {
       return CML_OK;
     case CML_OPT_NO_COUNTS:
       ctx->opt_no_counts = value;
+      ctx->graph_dirty = true;
       return CML_OK;
     case CML_OPT_NO_FACTOR:
       CML_REQUIRE(!ctx->have_model, CML_ERR_STATE, "CML_OPT_NO_FACTOR must be set before cml_set_model");
       ctx->opt_no_factor = value;
+      return CML_OK;
+    case CML_OPT_ALLOW_EMPTY:
+      ctx->opt_allow_empty = value;
+      return CML_OK;
+    case CML_OPT_NO_GRAPH:
+      ctx->opt_no_graph = value;
+      ctx->graph_dirty = true;
       return CML_OK;
     case CML_OPT_NO_WIDE:
       CML_REQUIRE(ctx->batches.empty(), CML_ERR_STATE, "CML_OPT_NO_WIDE must be set before cml_add_trellises");
@@ -390,6 +403,7 @@ extern "C" int cml_set_model(cml_ctx* ctx, const cml_model* m) {
   CML_CUDA(cudaStreamSynchronize(s));  // the host staging vectors go out of scope
   ctx->have_model = true;
   ctx->have_params = false;
+  ctx->graph_dirty = true;
   return CML_OK;
 }
 
@@ -1212,6 +1226,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   }
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->batches.push_back(std::move(bt));
+  ctx->graph_dirty = true;
   if (ctx->slot_occ.size() != ctx->n_slots) ctx->slot_occ.assign(ctx->n_slots, 0);
   for (size_t i = 0; i < batch_occ.size(); ++i) ctx->slot_occ[i] += batch_occ[i];
   ctx->hot_dirty = true;
@@ -1223,6 +1238,7 @@ extern "C" int cml_clear_trellises(cml_ctx* ctx) {
   cudaSetDevice(ctx->device);
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->batches.clear();
+  ctx->graph_dirty = true;
   ctx->slot_occ.assign(ctx->n_slots, 0);
   ctx->hot_dirty = true;
   return CML_OK;
@@ -1342,7 +1358,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     CML_CUDA(cudaEventCreate(&bt.ev_fb1));
   }
   bt.n_fb_kernels = 0;
-  CML_CUDA(cudaEventRecord(bt.ev_fb0, ctx->stream));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(bt.ev_fb0, ctx->stream));
   if (SCALED && bt.ell_ex) {
     EllArgs E;
     E.desc = bt.edesc.p;
@@ -1517,7 +1533,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
       }
     }
   }
-  CML_CUDA(cudaEventRecord(bt.ev_fb1, ctx->stream));
+  if (!ctx->capturing) CML_CUDA(cudaEventRecord(bt.ev_fb1, ctx->stream));
   k_reduce_lnp<<<std::min<unsigned>(cdiv(bt.n_ex, 256), 4 * ctx->sm_count), 256, 0, ctx->stream>>>(
       bt.ex_lnp.p, bt.ex_weight.p, bt.n_ex, ctx->reduce + ctx->n_slots);
   ++ctx->launches;
@@ -1603,9 +1619,15 @@ static int rebuild_slot_codes(cml_ctx* ctx) {
 extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   if (!ctx) return CML_ERR_ARG;
   CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
+  cudaSetDevice(ctx->device);
+  if (ctx->batches.empty() && !ctx->dense && ctx->opt_allow_empty) {
+    // an empty shard of a multi-GPU job: zero counts and likelihood terms, the rank still joins the all-reduce
+    CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), ctx->stream));
+    ctx->estimate_pending = true;
+    return CML_OK;
+  }
   CML_REQUIRE(!ctx->batches.empty() || ctx->dense, CML_ERR_NODERIV,
               "no trellises resident (no training example had a derivation)");
-  cudaSetDevice(ctx->device);
   if (ctx->dense) {
     const int rc = cml_dense_estimate_launch(ctx);
     if (rc) return rc;
@@ -1782,6 +1804,7 @@ extern "C" int cml_use_reduce_buffer(cml_ctx* ctx, void* p, uint64_t n) {
   }
   CML_REQUIRE(n >= ctx->reduce_n, CML_ERR_ARG, "reduce buffer too small (need count slots + 3 doubles)");
   ctx->reduce = (double*)p;
+  ctx->graph_dirty = true;
   return CML_OK;
 }
 
@@ -1826,11 +1849,10 @@ extern "C" int cml_normalize_params(cml_ctx* ctx) {
   return run_normalize(ctx);
 }
 
-extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
+// M-step launches on the context's stream; the largest weight change ends up in ctx->maxchg (device).  No host
+// synchronisation: cml_maximize and cml_em_step read it back.
+static int enqueue_maximize(cml_ctx* ctx, double rate) {
   using namespace cmlk;
-  if (!ctx) return CML_ERR_ARG;
-  CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
-  cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   const bool slots_are_params = ctx->trivial && !ctx->dense;  // dense mode: slots are T / E cells with chains
   if (rate <= 1. && ctx->n_ties == 0 && ctx->n_params <= 8192 && ctx->n_slots <= 16384 && ctx->max_group_size <= 256 &&
@@ -1859,10 +1881,6 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
     k_mstep_fused<<<1, 1024, 0, s>>>(M);
     ++ctx->launches;
     CML_CUDA(cudaGetLastError());
-    unsigned long long bits = 0;
-    CML_CUDA(cudaMemcpyAsync(&bits, ctx->maxchg.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
-    CML_CUDA(cudaStreamSynchronize(s));
-    if (max_delta) std::memcpy(max_delta, &bits, sizeof(double));
     return CML_OK;
   }
   if (!slots_are_params) CML_CUDA(cudaMemsetAsync(ctx->acc.p, 0, ctx->n_params * sizeof(double), s));
@@ -1886,10 +1904,122 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
                                                        ctx->maxchg.p);
   ++ctx->launches;
   CML_CUDA(cudaGetLastError());
+  return CML_OK;
+}
+
+extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
+  if (!ctx) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
+  cudaSetDevice(ctx->device);
+  const int r = enqueue_maximize(ctx, rate);
+  if (r) return r;
   unsigned long long bits = 0;
-  CML_CUDA(cudaMemcpyAsync(&bits, ctx->maxchg.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
-  CML_CUDA(cudaStreamSynchronize(s));
+  CML_CUDA(cudaMemcpyAsync(&bits, ctx->maxchg.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
   if (max_delta) std::memcpy(max_delta, &bits, sizeof(double));
+  return CML_OK;
+}
+
+// One EM iteration, one host synchronisation (include/carmel_b200.h).  The sequence
+//   parameters -> snapshot slot 3, arc / class weights, E-step kernels, all-reduce, likelihood scalars -> pinned host,
+//   M-step kernels, max change -> pinned host
+// is the same every iteration, so it is captured into a CUDA graph once and replayed (NCCL all-reduces are
+// capturable); anything that changes the sequence marks the graph dirty.
+static int enqueue_em_step(cml_ctx* ctx, double rate) {
+  cudaStream_t s = ctx->stream;
+  CML_CUDA(cudaMemcpyAsync(ctx->snap[3].p, ctx->ln_w.p, ctx->n_params * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  int r = cml_estimate_launch(ctx);
+  if (r) return r;
+  ctx->estimate_pending = false;
+  if ((r = cml_allreduce_counts(ctx))) return r;
+  CML_CUDA(cudaMemcpyAsync(ctx->h_step, ctx->reduce + ctx->n_slots, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if ((r = enqueue_maximize(ctx, rate))) return r;
+  CML_CUDA(cudaMemcpyAsync(ctx->h_step + 3, ctx->maxchg.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  return CML_OK;
+}
+
+extern "C" int cml_em_step(cml_ctx* ctx, double rate, cml_estimate_result* out, double* max_delta) {
+  if (!ctx) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_model && ctx->have_params, CML_ERR_STATE, "cml_set_model and cml_set_params first");
+  CML_REQUIRE(!ctx->batches.empty() || ctx->dense || ctx->opt_allow_empty, CML_ERR_NODERIV,
+              "no trellises resident (no training example had a derivation)");
+  cudaSetDevice(ctx->device);
+  if (!ctx->h_step) CML_CUDA(cudaMallocHost((void**)&ctx->h_step, 8 * sizeof(double)));
+  if (!ctx->dense && (ctx->hot_dirty || ctx->cls_dirty) && !ctx->batches.empty()) {  // host-side table rebuilds
+    const int rc = rebuild_slot_codes(ctx);
+    if (rc) return rc;
+    ctx->graph_dirty = true;
+  }
+  const bool use_graph = !ctx->opt_no_graph && rate == 1.;
+  if (use_graph) {
+    if (ctx->graph_dirty || !ctx->graph) {
+      if (ctx->graph) {
+        cudaGraphExecDestroy(ctx->graph);
+        ctx->graph = nullptr;
+      }
+      // one plain pass first: kernels set their attributes / lazily created events outside the capture
+      int r = enqueue_em_step(ctx, rate);
+      if (r) return r;
+      CML_CUDA(cudaStreamSynchronize(ctx->stream));
+      CML_CUDA(cudaMemcpyAsync(ctx->ln_w.p, ctx->snap[3].p, ctx->n_params * sizeof(double), cudaMemcpyDeviceToDevice,
+                               ctx->stream));  // undo: the captured pass below is the one that counts
+      cudaGraph_t g = nullptr;
+      const uint64_t launches0 = ctx->launches, coll0 = ctx->collectives;
+      CML_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
+      r = enqueue_em_step(ctx, rate);
+      ctx->capturing = false;
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+      if (r) {
+        if (g) cudaGraphDestroy(g);
+        return r;
+      }
+      CML_CUDA(e);
+      ctx->graph_launches = ctx->launches - launches0;
+      ctx->graph_collectives = ctx->collectives - coll0;
+      ctx->launches = launches0;
+      ctx->collectives = coll0;
+      CML_CUDA(cudaGraphInstantiate(&ctx->graph, g, 0));
+      cudaGraphDestroy(g);
+      ctx->graph_dirty = false;
+    }
+    CML_CUDA(cudaGraphLaunch(ctx->graph, ctx->stream));
+    ctx->launches += ctx->graph_launches;
+    ctx->collectives += ctx->graph_collectives;
+  } else {
+    const int r = enqueue_em_step(ctx, rate);
+    if (r) return r;
+  }
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (out) {
+    out->sum_ln_p = ctx->h_step[0];
+    out->sum_w_ln_p = ctx->h_step[1];
+    out->n_zero = (uint64_t)(ctx->h_step[2] + 0.5);
+  }
+  if (max_delta) *max_delta = ctx->h_step[3];
+  return CML_OK;
+}
+
+extern "C" int cml_snapshot_previous(cml_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 2) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_params, CML_ERR_STATE, "no parameters set");
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaMemcpyAsync(ctx->snap[slot].p, ctx->snap[3].p, ctx->n_params * sizeof(double), cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  return CML_OK;
+}
+
+// small host-side sums over the ranks (corpus totals before training): through a 64-double device scratch
+extern "C" int cml_allreduce_host(cml_ctx* ctx, double* inout, uint64_t n) {
+  if (!ctx || !inout || n > 64) return CML_ERR_ARG;
+  if (!ctx->comm || ctx->comm_size <= 1) return CML_OK;
+  cudaSetDevice(ctx->device);
+  if (!ctx->host_scratch.p) CML_CUDA(ctx->host_scratch.alloc(64));
+  CML_CUDA(cudaMemcpyAsync(ctx->host_scratch.p, inout, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int r = cml_allreduce_buffer(ctx, ctx->host_scratch.p, n);
+  if (r) return r;
+  CML_CUDA(cudaMemcpyAsync(inout, ctx->host_scratch.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
   return CML_OK;
 }
 
@@ -1901,15 +2031,17 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_restore_params", "cml_add_sequences", "cml_dense_stats", "cml_dense_kernel", "cml_add_trellises", "cml_clear_trellises", "cml_trellis_totals", "cml_layout_stats",
       "cml_lane_stats", "cml_wide_stats", "cml_get_example_layout", "cml_estimate", "cml_estimate_launch", "cml_estimate_finish", "cml_last_fb_time_ms",
       "cml_get_example_logprob", "cml_get_arc_counts", "cml_get_counts", "cml_count_slots", "cml_reduce_buffer",
-      "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize",
+      "cml_use_reduce_buffer", "cml_reduce_buffer_write", "cml_reduce_buffer_read", "cml_maximize", "cml_em_step", "cml_snapshot_previous", "cml_comm_unique_id", "cml_comm_init_rank",
+      "cml_comm_init_all", "cml_set_comm", "cml_comm_info", "cml_allreduce_counts", "cml_allreduce_buffer",
+      "cml_allreduce_host", "cml_collective_count",
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",
-      "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_attach_dense", "cml_gibbs_sweep",
+      "cml_job_set_comm", "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_attach_dense", "cml_gibbs_sweep",
       "cml_gibbs_sample_capacity", "cml_gibbs_get_samples", "cml_gibbs_get_state", "cml_forests_create", "cml_forests_destroy",
       "cml_forests_last_error", "cml_forests_set_stream", "cml_forests_set_layout", "cml_forests_layout_stats",
       "cml_forests_launch_count", "cml_forests_set_rules",
       "cml_forests_set_params", "cml_forests_get_params", "cml_forests_add", "cml_forests_totals", "cml_forests_estimate",
       "cml_forests_estimate_launch", "cml_forests_estimate_finish", "cml_forests_last_time_ms", "cml_forests_get_inside",
-      "cml_forests_get_counts", "cml_forests_reduce_buffer", "cml_forests_maximize", "cml_forests_normalize_params",
+      "cml_forests_get_counts", "cml_forests_reduce_buffer", "cml_forests_comm_init_rank", "cml_forests_allreduce_counts", "cml_forests_maximize", "cml_forests_normalize_params",
       "cml_forest_job_open", "cml_forest_job_close", "cml_forest_job_error", "cml_forest_job_set_allreduce",
       "cml_forest_job_prepare", "cml_forest_job_context", "cml_forest_job_train", "cml_forest_job_write",
       "cml_forest_job_stats"};

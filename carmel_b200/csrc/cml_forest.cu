@@ -700,7 +700,14 @@ struct cml_forests {
   DevArray<double> hot;
   uint32_t n_hot = 0;
   std::vector<std::unique_ptr<ForestBatch>> batches;
+  void* comm = nullptr;  // ncclComm_t of this rank (cml_forests_comm_init_rank), null on a single GPU
+  int comm_size = 1;
+  uint64_t collectives = 0;
 };
+// cml_comm.cu
+int cml_nccl_init_rank(void** comm, int n_ranks, int rank, const unsigned char* id, std::string& err);
+int cml_nccl_allreduce(void* comm, double* p, uint64_t count, cudaStream_t s, std::string& err);
+void cml_nccl_destroy(void* comm);
 
 #define ctx f
 #define F_REQUIRE(cond, code, msg) \
@@ -747,8 +754,28 @@ extern "C" void cml_forests_destroy(cml_forests* f) {
   cudaSetDevice(f->device);
   cudaStreamSynchronize(f->stream);
   f->batches.clear();
+  cml_nccl_destroy(f->comm);
   if (f->own_stream) cudaStreamDestroy(f->stream);
   delete f;
+}
+// the per-iteration all-reduce of [rule counts | sum ln inside | n_zero | n_forests] (north_star (4)); same rendezvous
+// token scheme as cml_comm_init_rank
+extern "C" int cml_forests_comm_init_rank(cml_forests* f, int n_ranks, int rank, const unsigned char id[CML_COMM_ID_BYTES]) {
+  if (!f || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return CML_ERR_ARG;
+  cudaSetDevice(f->device);
+  cml_nccl_destroy(f->comm);
+  f->comm = nullptr;
+  const int r = cml_nccl_init_rank(&f->comm, n_ranks, rank, id, f->err);
+  if (r) return r;
+  f->comm_size = n_ranks;
+  return CML_OK;
+}
+extern "C" int cml_forests_allreduce_counts(cml_forests* f) {
+  if (!f) return CML_ERR_ARG;
+  if (!f->comm || f->comm_size <= 1) return CML_OK;
+  cudaSetDevice(f->device);
+  ++f->collectives;
+  return cml_nccl_allreduce(f->comm, f->reduce.p, f->rulespace + 3, f->stream, f->err);
 }
 extern "C" const char* cml_forests_last_error(cml_forests* f) { return f ? f->err.c_str() : g_forest_create_err.c_str(); }
 extern "C" int cml_forests_set_stream(cml_forests* f, void* s) {

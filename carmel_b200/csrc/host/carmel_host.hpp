@@ -211,6 +211,10 @@ struct TrainJob {
   bool train_cascade = false;
   AllReduceFn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  // NCCL rendezvous token of a sharded run (cml_job_set_comm): the context joins the communicator in prepare() and
+  // the per-iteration all-reduce is issued by the library on its own stream (no callback)
+  bool have_comm_id = false;
+  unsigned char comm_id[128] = {0};
   // state
   cml_ctx* ctx = nullptr;
   ModelArrays M;

@@ -285,6 +285,13 @@ extern "C" int cml_job_open(cml_job** out, int argc, const char* const* argv) {
 }
 extern "C" void cml_job_close(cml_job* j) { delete j; }
 extern "C" const char* cml_job_error(cml_job* j) { return j ? j->err.c_str() : "null job"; }
+extern "C" int cml_job_set_comm(cml_job* j, const unsigned char id[128]) {
+  if (!j || !id) return CML_ERR_ARG;
+  std::memcpy(j->job.comm_id, id, 128);
+  j->job.have_comm_id = true;
+  return CML_OK;
+}
+
 extern "C" int cml_job_set_allreduce(cml_job* j, cml_allreduce_fn fn, void* user) {
   if (!j) return CML_ERR_ARG;
   j->job.allreduce = fn;

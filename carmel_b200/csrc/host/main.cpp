@@ -7,8 +7,12 @@
 //   carmel-b200 -t [-HJ] [-M n] [-e w] [-X w] [-f w] [-U] [-o g] [-j|-u] [-d] [-K] [-F out]
 //               [--train-cascade] [--normby=JCN] [--priors=w,w] [--float] [--scaled] [--gpu=n]
 //               [--dump-trellis=file] [--history=file] [--trellis-only] corpus wfst [wfst ...]
+#include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
+#include <sstream>
+#include <thread>
 
 #include "carmel_host.hpp"
 
@@ -28,7 +32,62 @@ static void usage() {
                "  --normby=JCN --priors=w,w   per-transducer normalisation / additive priors\n"
                "  --float  fp32 state scores (default fp64)   --scaled  scaled linear space (default log)\n"
                "  --gpu=n  CUDA device   --history=file  --dump-trellis=file  --write-composed=file\n"
+               "  --gpus=N examples sharded over GPUs 0..N-1 of this box, one host thread per GPU; the count table is\n"
+               "           all-reduced with NCCL every iteration (EM only)\n"
                "  --trellis-only  build (and dump) the derivation lattices on the host, then stop\n";
+}
+
+// carmel-b200 --gpus=N ...: N jobs in one process, job r keeps block r of the corpus on GPU r (--shard=r/N --gpu=r); the
+// contexts share one NCCL communicator and every iteration all-reduces the count table on the GPUs' own streams.  All
+// ranks take the same decisions (the reduced table and likelihood are identical everywhere); rank 0 logs and writes.
+static int run_multi_gpu(int argc, char** argv, int n_gpus) {
+  unsigned char id[CML_COMM_ID_BYTES];
+  if (cml_comm_unique_id(id) != CML_OK) {
+    std::cerr << "ERROR: --gpus needs NCCL (libnccl.so.2 could not be loaded)\n";
+    return -11;
+  }
+  std::vector<std::unique_ptr<TrainJob>> jobs;
+  std::vector<std::vector<std::string>> args(n_gpus);
+  std::ostringstream quiet;
+  for (int r = 0; r < n_gpus; ++r) {  // parse / read / compose once per rank (sequentially: the readers share nothing,
+    for (int i = 0; i < argc; ++i)     //  but their messages should appear once)
+      if (std::strncmp(argv[i], "--gpus", 6) != 0 && std::strncmp(argv[i], "--gpu=", 6) != 0 &&
+          !(r > 0 && (std::strncmp(argv[i], "--history", 9) == 0 || std::strncmp(argv[i], "--dump-trellis", 14) == 0)))
+        args[r].push_back(argv[i]);
+    args[r].push_back("--shard=" + std::to_string(r) + "/" + std::to_string(n_gpus));
+    args[r].push_back("--gpu=" + std::to_string(r));
+    std::vector<const char*> av;
+    for (auto const& a : args[r]) av.push_back(a.c_str());
+    jobs.emplace_back(new TrainJob());
+    const int rc = open_job((int)av.size(), av.data(), *jobs.back(), r == 0 ? (std::ostream&)std::cerr : (std::ostream&)quiet);
+    if (rc != 0) return rc;
+    if (jobs.back()->gopt.enabled) {
+      std::cerr << "ERROR: --gpus shards EM training; --crp sampling is sequential over the corpus (one GPU)\n";
+      return -11;
+    }
+    std::memcpy(jobs.back()->comm_id, id, sizeof(id));
+    jobs.back()->have_comm_id = true;
+  }
+  std::vector<std::string> errs(n_gpus);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n_gpus; ++r)
+    th.emplace_back([&, r]() {
+      try {
+        std::ostringstream sink;
+        jobs[r]->run(r == 0 ? (std::ostream&)std::cerr : (std::ostream&)sink);
+      } catch (std::exception& e) {
+        errs[r] = e.what();
+        if (errs[r].empty()) errs[r] = "failed";
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n_gpus; ++r)
+    if (!errs[r].empty()) {
+      std::cerr << "ERROR (GPU " << r << "): " << errs[r] << std::endl;
+      return -11;
+    }
+  jobs[0]->write_outputs(std::cout);
+  return 0;
 }
 
 int main(int argc, char** argv) {
@@ -37,6 +96,9 @@ int main(int argc, char** argv) {
       usage();
       return 0;
     }
+    for (int i = 1; i < argc; ++i)
+      if (std::strncmp(argv[i], "--gpus=", 7) == 0 && std::atoi(argv[i] + 7) > 1)
+        return run_multi_gpu(argc, argv, std::atoi(argv[i] + 7));
     TrainJob job;
     const int rc = open_job(argc, argv, job, std::cerr);
     if (job.lopt.count("help")) {

@@ -258,6 +258,10 @@ void TrainJob::prepare() {
   if (opt.max_iter == 0) ok(cml_set_option(ctx, CML_OPT_ARC_COUNTS, 1));  // -M 0 writes per-arc fractional counts
   if (opt.no_ell) ok(cml_set_option(ctx, CML_OPT_NO_ELL, 1));
   if (opt.lane_min >= 0) ok(cml_set_option(ctx, CML_OPT_LANE_MIN, opt.lane_min));
+  if (opt.shard_count > 1) {
+    ok(cml_set_option(ctx, CML_OPT_ALLOW_EMPTY, 1));  // a rank whose block has no usable example still joins every collective
+    if (have_comm_id) ok(cml_comm_init_rank(ctx, (int)opt.shard_count, (int)opt.shard_rank, comm_id));
+  }
   if (opt.no_factor) ok(cml_set_option(ctx, CML_OPT_NO_FACTOR, 1));
   if (opt.no_wide) ok(cml_set_option(ctx, CML_OPT_NO_WIDE, 1));
   // locality keys: arcs with the same output symbol, then source state, are laid out together on the GPU,
@@ -355,14 +359,19 @@ void TrainJob::prepare() {
     corpus.examples.swap(keep);
     corpus.count();
     if (opt.shard_count > 1) {  // global corpus statistics: one small all-reduce
-      if (!allreduce) throw std::runtime_error("--shard needs an all-reduce hook (use the multi-GPU driver)");
-      void* buf;
-      uint64_t nbuf;
-      ok(cml_reduce_buffer(ctx, &buf, &nbuf));
       double h[4] = {(double)corpus.n_pairs, corpus.total_weight, corpus.n_input, corpus.n_output};
-      ok(cml_reduce_buffer_write(ctx, h, 4));
-      allreduce(allreduce_user, buf, nbuf);
-      ok(cml_reduce_buffer_read(ctx, h, 4));
+      if (have_comm_id) {
+        ok(cml_allreduce_host(ctx, h, 4));
+      } else {
+        if (!allreduce) throw std::runtime_error("--shard needs a communicator (cml_job_set_comm / --gpus) or an all-reduce hook");
+        void* buf;
+        uint64_t nbuf;
+        ok(cml_reduce_buffer(ctx, &buf, &nbuf));
+        ok(cml_reduce_buffer_write(ctx, h, 4));  // (synchronises the context's stream)
+        // hook contract: the sum is complete in device memory when the hook returns
+        allreduce(allreduce_user, buf, nbuf);
+        ok(cml_reduce_buffer_read(ctx, h, 4));
+      }
       corpus.n_pairs = (uint32_t)(h[0] + .5);
       corpus.total_weight = h[1];
       corpus.n_input = h[2];
@@ -400,11 +409,18 @@ void TrainJob::prepare() {
 double TrainJob::estimate(double& ln_unweighted) {
   cml_estimate_result r;
   ok(cml_estimate_launch(ctx));
-  if (allreduce && opt.shard_count > 1) {
-    void* buf;
-    uint64_t nbuf;
-    ok(cml_reduce_buffer(ctx, &buf, &nbuf));
-    allreduce(allreduce_user, buf, nbuf);
+  if (opt.shard_count > 1) {
+    if (have_comm_id) {
+      ok(cml_allreduce_counts(ctx));  // NCCL, stream-ordered behind the E-step kernels
+    } else if (allreduce) {
+      // hook contract: the E-step has finished before the hook runs (it may use any stream), and the sum is
+      // complete in device memory when it returns
+      void* buf;
+      uint64_t nbuf;
+      ok(cml_reduce_buffer(ctx, &buf, &nbuf));
+      ok(cml_synchronize(ctx));
+      allreduce(allreduce_user, buf, nbuf);
+    }
   }
   ok(cml_estimate_finish(ctx, &r));
   if (r.n_zero) {  // some example has probability zero: the corpus probability is zero
@@ -494,7 +510,7 @@ TrainResult const& TrainJob::run(std::ostream& log) {
   prepare();
   double ln_corpus_p = 0;
   // ---- -M 0 / -M 1: fractional counts only / a single iteration (train.cc:520-538) ----
-  if (opt.max_iter == 0 || opt.max_iter == 1) {
+  if (opt.max_iter == 0 || (opt.max_iter == 1 && opt.ran_restarts == 0)) {  // (train.cc:520)
     const double p = estimate(ln_corpus_p);
     res.history.push_back({1, ln_corpus_p, p, 0});
     log << "Corpus ";
@@ -510,6 +526,22 @@ TrainResult const& TrainJob::run(std::ostream& log) {
           if (a.group != kLocked || using_cascade) a.ln_w = c > 0 ? std::log(c) : kNegInf;
           ++a_id;
         }
+      if (using_cascade) {
+        // cascade.distribute_counts (cascade.h:286-325): unlocked member arcs are zeroed, then every composed arc's
+        // count + prior is added to each unlocked arc of its chain; locked member arcs keep their weights
+        std::vector<double> acc(M.n_params, 0.);
+        for (uint32_t a = 0; a < M.n_arcs; ++a) {
+          const double c = counts[a] + (M.arc_prior.empty() ? 0. : M.arc_prior[a]);
+          for (uint32_t k = M.chain_off[a]; k < M.chain_off[a + 1]; ++k) acc[M.chain_param[k]] += c;
+        }
+        size_t p = 0;
+        for (Wfst* m : members)
+          for (auto& st : m->states)
+            for (Arc& a : st) {
+              if (M.param_tie[p] != kLocked) a.ln_w = acc[p] > 0 ? std::log(acc[p]) : kNegInf;
+              ++p;
+            }
+      }
     } else {
       double d;
       ok(cml_maximize(ctx, 1., &d));

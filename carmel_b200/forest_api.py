@@ -63,6 +63,8 @@ def _lib():
         lib.cml_forests_get_inside.argtypes = [_vp, _f64p, C.c_uint64]
         lib.cml_forests_get_counts.argtypes = [_vp, _f64p, C.c_uint64]
         lib.cml_forests_reduce_buffer.argtypes = [_vp, C.POINTER(_vp), _u64p]
+        lib.cml_forests_comm_init_rank.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
+        lib.cml_forests_allreduce_counts.argtypes = [_vp]
         lib.cml_forests_maximize.argtypes = [_vp, C.POINTER(CmlForestNormOpts), _f64p, _u64p]
         lib.cml_forests_normalize_params.argtypes = [_vp]
         lib.cml_forest_job_open.argtypes = [C.POINTER(_vp), C.c_int, C.POINTER(C.c_char_p)]
@@ -180,6 +182,13 @@ class Forests:
         v = np.empty(self.rulespace, np.float64)
         self._ok(self.lib.cml_forests_get_counts(self.h, v.ctypes.data_as(_f64p), self.rulespace))
         return v
+
+    def comm_init_rank(self, n_ranks: int, rank: int, token: bytes):
+        assert len(token) == 128
+        self._ok(self.lib.cml_forests_comm_init_rank(self.h, n_ranks, rank, token))
+
+    def allreduce_counts(self):
+        self._ok(self.lib.cml_forests_allreduce_counts(self.h))
 
     def reduce_buffer(self):
         p, n = _vp(), C.c_uint64()

@@ -155,12 +155,81 @@ def _forest_template(rng, depth: int, share: float):
     return np.array(nxt, np.uint32), np.array(kind, np.uint8), np.array(target, np.uint32)
 
 
+FOREST_CHUNKS = 64  # the distinct-shape corpus is defined as 64 independently seeded chunks (so that rank r of N can
+                    # generate exactly its block of the same corpus)
+
+
+def _distinct_shapes(n_forests: int, seed: int, target_hyperedges: int, share: float = 0.15, threads: int | None = None,
+                     part: tuple = (0, 1)):
+    """every forest its own random shape: the C generator (csrc/tools/forest_synth.c, same shape law as
+    _forest_template), chunks of forests generated on host threads (ctypes releases the GIL).  part = (r, N): only
+    the chunks of block r of N are generated; returns the arrays of that block and its chunk ids."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from . import build as _b
+    if not os.path.exists(_b.SYNTH_LIB):
+        _b.build()
+    lib = C.CDLL(_b.SYNTH_LIB)
+    lib.cb200_synth_forests.restype = C.c_uint64
+    lib.cb200_synth_forests.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_double, C.c_uint64] + [C.c_void_p] * 4
+    threads = threads or max(1, min(32, (os.cpu_count() or 1) // max(1, part[1])))
+    n_chunks = max(1, min(FOREST_CHUNKS, n_forests // 64 or 1))
+    bounds = np.linspace(0, n_forests, n_chunks + 1).astype(np.int64)
+    c_lo, c_hi = part[0] * n_chunks // part[1], (part[0] + 1) * n_chunks // part[1]
+
+    def gen(c):
+        n = int(bounds[c + 1] - bounds[c])
+        cap = n * (4 * target_hyperedges) + 4096
+        off = np.zeros(n + 1, np.uint64)
+        nx, lab, br = np.empty(cap, np.uint32), np.empty(cap, np.uint32), np.empty(cap, np.uint8)
+        tot = int(lib.cb200_synth_forests(n, seed * 1000003 + c, target_hyperedges, share, cap, off.ctypes.data,
+                                          nx.ctypes.data, lab.ctypes.data, br.ctypes.data))
+        if n and not tot:
+            raise RuntimeError("forest generator: output capacity too small")
+        return off, nx[:tot], lab[:tot], br[:tot]
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(gen, range(c_lo, c_hi)))
+    n_local = int(bounds[c_hi] - bounds[c_lo])
+    node_off = np.zeros(n_local + 1, np.uint64)
+    base = 0
+    for k, (off, _, _, _) in enumerate(parts):
+        c = c_lo + k
+        node_off[bounds[c] - bounds[c_lo] + 1:bounds[c + 1] - bounds[c_lo] + 1] = off[1:] + np.uint64(base)
+        base += int(off[-1])
+    if not parts:
+        return node_off, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint8)
+    return (node_off, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]),
+            np.concatenate([p[3] for p in parts]))
+
+
 def make_forests(n_forests: int = 100000, n_rules: int = 1000000, seed: int = 20260105, templates: int = 512,
-                 target_hyperedges: int = 500, zipf: float = 1.0, group_seed: int = 20260105) -> dict:
+                 target_hyperedges: int = 500, zipf: float = 1.0, group_seed: int = 20260105, part: tuple = (0, 1)) -> dict:
     """Synthetic forest corpus in the C ABI's layout (cml_forest_batch) plus normalization groups of size U[2,50]
     covering every rule.  Shapes come from `templates` random forests (depth 6-12, about `target_hyperedges` AND nodes
     each); every forest draws its own rule ids, Zipf(`zipf`) over `n_rules`."""
     rng = np.random.default_rng(seed)
+    if templates <= 0:  # every forest its own shape (BASELINE configs[4] as written: "100k random forests")
+        node_off, nxt, lab0, backref = _distinct_shapes(n_forests, seed, target_hyperedges, part=part)
+        rng = np.random.default_rng([seed, part[0], part[1]])  # rule ids of this block
+        total = int(node_off[-1])
+        label = lab0.copy()
+        and_pos = np.nonzero((lab0 == 1) & (backref == 0))[0]
+        label[(backref == 0)] = 0
+        ranks = np.arange(1, n_rules + 1, dtype=np.float64) ** -zipf
+        cdf = np.cumsum(ranks / ranks.sum())
+        ids = np.searchsorted(cdf, rng.random(len(and_pos)), side="right").astype(np.uint32)
+        perm = rng.permutation(n_rules).astype(np.uint32)
+        label[and_pos] = 1 + perm[np.minimum(ids, n_rules - 1)]
+        grng = np.random.default_rng(group_seed)
+        order = 1 + grng.permutation(n_rules).astype(np.uint64)
+        gsz = grng.integers(2, 51, size=n_rules // 2 + 1)
+        goff = np.concatenate([[0], np.cumsum(gsz)])
+        goff = goff[goff < n_rules]
+        goff = np.concatenate([goff, [n_rules]]).astype(np.uint64)
+        return {"node_off": node_off, "next": nxt, "label": label, "backref": backref, "n_rules": n_rules,
+                "rulespace": n_rules + 1, "group_off": goff, "group_members": order, "hyperedges": int(len(and_pos)),
+                "nodes": total, "templates": len(node_off) - 1}
     shapes = []
     tries = 0
     while len(shapes) < templates and tries < 40 * templates:

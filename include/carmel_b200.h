@@ -70,8 +70,11 @@ enum cml_option {
   CML_OPT_NO_COUNTS = 4,  /* profiling only: the wide / lane kernels skip their expected-count REDs */
   CML_OPT_NO_FACTOR = 5,  /* keep one weight-table entry per arc: no arc classes / state parts.
                              Set before cml_set_model. */
-  CML_OPT_NO_WIDE = 6     /* lattices with levels of 9..32 states stay on the k_fb_ell classes instead of the
+  CML_OPT_NO_WIDE = 6,    /* lattices with levels of 9..32 states stay on the k_fb_ell classes instead of the
                              warp-per-lattice kernel (tests).  Set before cml_add_trellises. */
+  CML_OPT_ALLOW_EMPTY = 7, /* a rank of a sharded job whose block holds no usable example still takes part in every
+                             collective: its E-step contributes zeros instead of failing with CML_ERR_NODERIV */
+  CML_OPT_NO_GRAPH = 8    /* cml_em_step enqueues its launches one by one instead of replaying a CUDA graph */
 };
 int cml_set_option(cml_ctx* ctx, int option, int value);
 
@@ -293,6 +296,36 @@ uint64_t cml_gibbs_sample_capacity(cml_ctx* ctx);
 int cml_gibbs_get_samples(cml_ctx* ctx, uint32_t* path_len, uint32_t* path_arcs, uint64_t cap);
 int cml_gibbs_get_state(cml_ctx* ctx, double* count, double* cum, double* normsum);
 
+/* ---- collective: the per-iteration all-reduce of the count table (north_star (4)) -------------- *
+ * The reference is single process; the sharded E-step relies on "examples are independent given the weights"
+ * (carmel/src/cached_derivs.h:69-75, forest-em/forest-em.hpp:573-578).  One ncclAllReduce(sum, fp64) of the reduce
+ * buffer [count slots | sum ln P | sum w ln P | n_zero] per iteration, enqueued on the context's stream after the E-step
+ * kernels; the M-step then runs redundantly on every rank (no broadcast).  NCCL is bound at run time (libnccl.so.2).
+ *   one process per GPU:      rank 0 calls cml_comm_unique_id, the launcher ships the 128 bytes to every rank, every
+ *                             rank calls cml_comm_init_rank on its context;
+ *   one process, n contexts:  cml_comm_init_all (ncclCommInitAll), one host thread per context afterwards;
+ *   existing communicator:    cml_set_comm(ctx, ncclComm_t, rank, n_ranks). */
+#define CML_COMM_ID_BYTES 128
+int cml_comm_unique_id(unsigned char out[CML_COMM_ID_BYTES]);
+int cml_comm_init_rank(cml_ctx* ctx, int n_ranks, int rank, const unsigned char id[CML_COMM_ID_BYTES]);
+int cml_comm_init_all(cml_ctx** ctxs, int n);
+int cml_set_comm(cml_ctx* ctx, void* nccl_comm, int rank, int n_ranks);
+int cml_comm_info(cml_ctx* ctx, int* rank, int* n_ranks);
+int cml_allreduce_counts(cml_ctx* ctx);                      /* between cml_estimate_launch and cml_estimate_finish */
+int cml_allreduce_buffer(cml_ctx* ctx, void* device_ptr, uint64_t n_doubles); /* in place, on the context's stream */
+int cml_allreduce_host(cml_ctx* ctx, double* inout, uint64_t n /* <= 64 */);  /* small host-side sums (corpus totals) */
+uint64_t cml_collective_count(cml_ctx* ctx);
+
+/* ---- one whole EM iteration in one call ------------------------------------------------------------------------- *
+ * forward_backward::estimate + maximize (carmel/src/train.cc:763-773,893-923) of one iteration of WFST::train's loop
+ * (train.cc:576-657): arc weights from the parameters, E-step, all-reduce (when a communicator is set), M-step at the
+ * given over-relaxation rate, and ONE host synchronisation that returns the corpus likelihood of the weights the
+ * iteration started from and the largest weight change.  The parameters the iteration started from stay available to
+ * cml_snapshot_previous (save_best, train.cc:592-600, after the fact).  Launches are replayed from a CUDA graph
+ * captured on first use (the iteration of a small model is launch bound: ~10 launches around a 60 us kernel). */
+int cml_em_step(cml_ctx* ctx, double rate, cml_estimate_result* out, double* max_delta);
+int cml_snapshot_previous(cml_ctx* ctx, int slot); /* parameters before the last cml_em_step -> snapshot slot */
+
 /* host access to the first n doubles of the reduce buffer (small control all-reduces) */
 int cml_reduce_buffer_write(cml_ctx* ctx, const double* src, uint64_t n);
 int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n);
@@ -316,6 +349,11 @@ typedef struct cml_job_info {
 int cml_job_open(cml_job** out, int argc, const char* const* argv); /* parse, read, reduce, compose */
 void cml_job_close(cml_job* job);
 const char* cml_job_error(cml_job* job);
+/* sharded runs (--shard=r/N): either the NCCL rendezvous token of cml_comm_unique_id (the job's context joins the
+ * communicator in cml_job_prepare and the library issues the all-reduces itself), or a host hook that sums a device
+ * buffer in place; the hook is called after the context's stream has been synchronised and must have completed the
+ * sum when it returns. */
+int cml_job_set_comm(cml_job* job, const unsigned char id[CML_COMM_ID_BYTES]);
 int cml_job_set_allreduce(cml_job* job, cml_allreduce_fn fn, void* user);
 int cml_job_prepare(cml_job* job); /* model + lattices onto the GPU; no iteration yet */
 cml_ctx* cml_job_context(cml_job* job); /* valid after cml_job_prepare; owned by the job */
@@ -381,6 +419,10 @@ int cml_forests_last_time_ms(cml_forests* f, float* ms, uint32_t* n_kernels);  /
 int cml_forests_get_inside(cml_forests* f, double* ln_inside, uint64_t n);     /* per forest, in the order added */
 int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n);        /* linear, [rulespace] */
 int cml_forests_reduce_buffer(cml_forests* f, void** device_ptr, uint64_t* n_doubles);
+/* multi-GPU: join an NCCL communicator (token from cml_comm_unique_id) and sum the reduce buffer over the ranks on the
+ * context's stream, between cml_forests_estimate_launch and cml_forests_estimate_finish */
+int cml_forests_comm_init_rank(cml_forests* f, int n_ranks, int rank, const unsigned char id[CML_COMM_ID_BYTES]);
+int cml_forests_allreduce_counts(cml_forests* f);
 /* M-step: rule_weights <- normalised (counts + prior_total).  max_delta / max_index as NormalizeGroups
  * reports them (largest absolute change of a probability and the rule it belongs to). */
 int cml_forests_maximize(cml_forests* f, const cml_forest_norm_opts* o, double* max_delta, uint64_t* max_index);
