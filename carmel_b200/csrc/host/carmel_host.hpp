@@ -187,6 +187,9 @@ struct GibbsOpts {
   double high_temp = 1, low_temp = 1;  // --high-temp= --low-temp=
   uint64_t seed = 1;                 // --seed= : key of the counter-based uniforms
   bool batched = false;              // --crp-batched : all blocks in parallel against the previous sweep's counts
+  bool sample_prob = false;          // --sample-prob (carmel.cc:1869): log the proposal probability of each new sample given
+                                     // the counts without its block (gibbs.hpp:866 with cache_prob off) instead of the cache
+                                     // model's -- the quantity in the golden log commands.trace:6976-12996
   std::string dump_samples_file;     // --dump-samples=file : final sample, arc-table ids per block
 };
 // sum-all-reduce of n doubles at device_ptr across the ranks of a multi-GPU run (NCCL, supplied by the driver)

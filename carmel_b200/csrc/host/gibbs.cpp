@@ -178,6 +178,22 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
   auto time_of = [&](uint32_t it) { return it > g.burnin ? (double)it - (double)g.burnin : 0.; };
   std::vector<double> ccount(M.n_params), csum(std::max<uint32_t>(1, n_norms));
   const double n_sym = corpus.n_output;
+  // --sample-prob: host mirror of the sampler's counts (prior + the current sample of every block) and the previous
+  // sweep's sample, to evaluate each new path against the counts without its own block
+  std::vector<double> sp_count, sp_sum;
+  std::vector<uint32_t> prev_len, prev_arcs;
+  if (g.sample_prob) {
+    sp_count.assign(prior.begin(), prior.end());
+    sp_sum.assign(std::max<uint32_t>(1, n_norms), 0.);
+    for (uint32_t p = 0; p < M.n_params; ++p)
+      if (norm[p] != kNoGroup) sp_sum[norm[p]] += prior[p];
+    prev_len.assign(res.examples, 0);
+    prev_arcs.assign(cap, 0);
+  }
+  auto for_params = [&](uint32_t a, auto&& f) {
+    const uint32_t k0 = using_cascade ? M.chain_off[a] : a, k1 = using_cascade ? M.chain_off[a + 1] : a + 1;
+    for (uint32_t c = k0; c < k1; ++c) f(using_cascade ? M.chain_param[c] : c);
+  };
   for (uint32_t it = 0; it <= g.iter; ++it) {
     double temperature = g.high_temp;
     if (g.iter > 0 && g.high_temp != g.low_temp)
@@ -198,6 +214,34 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
       if (norm[p] != kNoGroup) csum[norm[p]] += prior[p];
     }
     double ln_p = 0;
+    if (g.sample_prob) {
+      // gibbs.hpp:851-871 in block order: remove the block's old sample, add the new one, score it
+      for (uint64_t e = 0; e < res.examples; ++e) {
+        const double wt = corpus.examples[e].weight;
+        for (uint32_t k = 0; k < prev_len[e]; ++k)
+          for_params(prev_arcs[base[e] + k], [&](uint32_t p) {
+            if (norm[p] != kNoGroup) {
+              sp_count[p] -= wt;
+              sp_sum[norm[p]] -= wt;
+            }
+          });
+        for (uint32_t k = 0; k < path_len[e]; ++k)
+          for_params(path_arcs[base[e] + k], [&](uint32_t p) {
+            if (norm[p] != kNoGroup) {
+              sp_count[p] += wt;
+              sp_sum[norm[p]] += wt;
+            }
+          });
+        // scored with the new sample's counts back in (gibbs.hpp:866: "do it after to get overestimate"): the only
+        // reading under which the golden log is possible (its i=0 sample, 2^-207028, beats the EM optimum 2^-212071)
+        for (uint32_t k = 0; k < path_len[e]; ++k)
+          for_params(path_arcs[base[e] + k], [&](uint32_t p) {
+            ln_p += norm[p] != kNoGroup ? std::log(sp_count[p] / sp_sum[norm[p]]) : std::log(prior[p]);
+          });
+      }
+      prev_len = path_len;
+      prev_arcs = path_arcs;
+    } else
     for (uint64_t e = 0; e < res.examples; ++e)
       for (uint32_t k = 0; k < path_len[e]; ++k) {
         const uint32_t a = path_arcs[base[e] + k];
@@ -209,7 +253,7 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
       }
     res.history.push_back({it, ln_p, ln_p, 0});
     if (!opt.quiet) {
-      log << "Gibbs i=" << it << " cache-model prob=" << format_base2(ln_p);
+      log << "Gibbs i=" << it << (g.sample_prob ? " sample prob=" : " cache-model prob=") << format_base2(ln_p);
       if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << format_base2(-ln_p / n_sym);
       log << " per-block-ppx(N=" << res.examples << ")=" << format_base2(-ln_p / (double)res.examples) << "\n";
     }

@@ -104,6 +104,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
     if (lopt.count("low-temp")) g.low_temp = std::atof(lopt["low-temp"].c_str());
     if (lopt.count("seed")) g.seed = std::strtoull(lopt["seed"].c_str(), nullptr, 10);
     g.batched = lopt.count("crp-batched") > 0;
+    g.sample_prob = lopt.count("sample-prob") > 0;
     if (lopt.count("dump-samples")) g.dump_samples_file = lopt["dump-samples"];
   }
   if (!flags[(unsigned)'t']) {

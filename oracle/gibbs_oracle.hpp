@@ -65,6 +65,10 @@ struct GibbsOpts {
   uint64_t seed = 1;
   unsigned init_em = 0;
   bool em_p0 = false;
+  // --sample-prob (carmel.cc:1869 "show the sample prob given model, previous sample"): the proposal probability of each
+  // new sample under the current counts, which is what the older binary behind the golden log
+  // carmel-tutorial/commands.trace:6976-12996 printed by default ("sample prob=").
+  bool sample_prob = false;
 };
 
 struct Gibbs {
@@ -252,6 +256,14 @@ struct Gibbs {
       sample_arcs[b].clear();
       resample_block(b, power, iter);
       W bp = W::one();
+      if (gopt.sample_prob) {
+        // scored AFTER the new sample's counts are back in (gibbs.hpp:866 comment: "do it after to get overestimate"):
+        // the only reading under which the golden log is possible -- its i=0 sample has 2^-207028 > the EM optimum 2^-212071
+        addc(sample[b], wt);
+        for (unsigned id : sample[b]) bp *= W(proposal_prob(id));
+        p *= bp;
+        continue;
+      }
       for (unsigned id : sample[b]) {
         GibbsParam const& gp = gps[id];
         bp *= W(gp.has_norm() ? ccount[id]++ / csum[gp.norm]++ : gp.prior);
@@ -260,7 +272,7 @@ struct Gibbs {
       addc(sample[b], wt);
     }
     iter_ln_prob.push_back(p.w);
-    log << "Gibbs i=" << iter << " cache-model prob=" << fmt_base2(p);
+    log << "Gibbs i=" << iter << (gopt.sample_prob ? " sample prob=" : " cache-model prob=") << fmt_base2(p);
     if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << fmt_base2(p.ppxper(n_sym));
     log << " per-block-ppx(N=" << derivs.size() << ")=" << fmt_base2(p.ppxper((double)derivs.size())) << "\n";
   }
@@ -324,6 +336,7 @@ inline int gibbs_main(WFST& result, Cascade& cascade, Corpus& corpus, std::vecto
   if (lopt.count("final-counts")) g.final_counts = true;
   if (lopt.count("crp-exclude-prior")) g.exclude_prior = true;
   if (lopt.count("high-temp")) g.high_temp = atof(lopt["high-temp"].c_str());
+  g.sample_prob = lopt.count("sample-prob") > 0;
   if (lopt.count("low-temp")) g.low_temp = atof(lopt["low-temp"].c_str());
   if (lopt.count("seed")) g.seed = strtoull(lopt["seed"].c_str(), nullptr, 10);
   if (g.final_counts) g.burnin = g.iter;

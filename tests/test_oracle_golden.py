@@ -80,3 +80,29 @@ def test_cat_spellout_cascade_first_start(oracle_bin, tmp_path):
     assert f"({g['composed_states']} states / {g['composed_arcs']} arcs)" in err
     _check_traj(trajectory_log2(err), g["trajectory_log2"])
     assert "Converged - per-example perplexity ratio exceeds 0.999 after 3 iterations." in err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# --crp Gibbs sampling against the reference's golden log.  `carmel --crp -M 6000 tagging.data tagging.fsa tagging.fst`
+# (carmel-tutorial/commands:33, commands.trace:6976-12996) logs a "sample prob" per sweep; the seed was not recorded, so
+# sampled derivations cannot be compared, but with 24,115 points the per-point perplexity of a sweep is a tight
+# statistic.  "sample prob" is the proposal probability of each block's new sample with its own counts already added
+# back (gibbs.hpp:866: "do it after to get overestimate") -- the only reading under which the log is possible: its
+# initial sample has probability 2^-207028, above the EM optimum 2^-212071 of the same model (commands.trace:5889).
+TRACE_CRP_TAGGING = {0: 8.58505, 1: 9.03819, 2: 9.01795, 10: 8.9784, 30: 8.93824, 100: 8.90217, 300: 8.89113}
+
+
+def test_crp_tagging_trajectory_matches_the_golden_log(oracle_bin, tmp_path):
+    import re
+    c, a, b = stage(tmp_path, "tagging.data", "tagging.fsa", "tagging.fst")
+    rc, _, err = run(oracle_bin, ["--crp", "-M", "300", "--seed=11", "--sample-prob", c, a, b], cwd=str(tmp_path), timeout=600)
+    assert rc == 0, err[-2000:]
+    ppx = {int(m.group(1)): float(m.group(2))
+           for m in re.finditer(r"Gibbs i=(\d+) sample prob=\S+ per-point-ppx\(N=24115\)=2\^([0-9.]+)", err)}
+    assert len(ppx) == 301
+    # (seed-to-seed spread of the oracle itself: 0.03 at sweep 0, 0.05 around sweep 10 while the chain burns in, 0.015 later)
+    for i, tol in ((0, 0.10), (1, 0.07), (2, 0.07), (10, 0.07), (30, 0.05), (100, 0.03), (300, 0.025)):
+        assert abs(ppx[i] - TRACE_CRP_TAGGING[i]) <= tol, (i, ppx[i], TRACE_CRP_TAGGING[i])
+    # the chain is stationary from about sweep 100 on: the log's last 5,000 sweeps stay within 2^8.88 .. 2^8.90
+    tail = [ppx[i] for i in range(200, 301)]
+    assert 8.87 <= min(tail) and max(tail) <= 8.92, (min(tail), max(tail))
