@@ -309,6 +309,12 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def trace(msg):  # CB200_BENCH_TRACE=1: where is every rank (multi-GPU debugging)
+        if os.environ.get("CB200_BENCH_TRACE"):
+            print(f"[bench rank {rank} +{time.time() - T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    T0 = time.time()
+
     def new_token():
         """NCCL rendezvous token for one job's communicator (rank 0 makes it, everybody gets it)"""
         if world == 1:
@@ -348,10 +354,13 @@ def main():
         if world > 1 and shard:
             extra.append(f"--shard={rank}/{world}")
         t_build = time.time()
+        trace(f"measure: open job {extra}")
         job = cb.Job(extra + list(w["argv"]), comm_token=new_token() if (world > 1 and shard) else None)
+        trace("prepare")
         ctx = job.prepare()
         ctx.set_stream(stream.cuda_stream)
         t_build = time.time() - t_build
+        trace(f"prepared in {t_build:.1f}s")
         info = job.stats()
         dense = ctx.dense_stats()
         is_dense = dense["sequences"] > 0
@@ -377,7 +386,9 @@ def main():
             except Exception as ex:
                 parity = {"n": 0, "max_rel": None, "ok": False, "error": str(ex)[:300]}
         barrier()
+        trace("first em_step")
         first = ctx.em_step(1.0)  # (first call: plain pass + graph capture)
+        trace("first em_step done")
         first_counts = ctx.counts() if check_n and rank == 0 else None
         # the dense-state path's working set (symbols + alpha rows) fits in L2: flush L2 between its timed steps
         flush = is_dense
@@ -420,7 +431,9 @@ def main():
         if rank == 0:
             sampler.start()
         l0, c0 = ctx.launch_count(), ctx.collective_count()
+        trace("timed region")
         ms = timed(step, steps)
+        trace("timed region done")
         launches, collectives = ctx.launch_count() - l0, ctx.collective_count() - c0
         clocks = sampler.stop() if rank == 0 else None
         value = arcs_total * steps / (ms / 1e3)
@@ -527,7 +540,9 @@ def main():
                                    "timing": "CUDA events around the kernel on the launching stream, un-graphed pass after the "
                                              "timed region (the timed region replays a CUDA graph)"}
                 res["layout"] = lay
+        trace("close job")
         job.close()
+        trace("job closed")
 
         # ---- N > 1: the same total corpus on rank 0 alone; sum ln P and the reduced count table must agree
         if check_n and world > 1:

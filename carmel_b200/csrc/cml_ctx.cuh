@@ -176,7 +176,7 @@ struct cml_ctx {
   DevArray<double> host_scratch;  // 64 doubles: small host-side all-reduces (corpus statistics)
   // fused EM step (cml_em_step): pinned result block, CUDA graph of the whole iteration
   double* h_step = nullptr;       // pinned: sum ln P, sum w ln P, n_zero, max change (bits)
-  cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph = nullptr, graph_b = nullptr;  // graph_b: the part after the all-reduce (multi-GPU)
   bool graph_dirty = true, capturing = false;
   uint64_t graph_launches = 0, graph_collectives = 0;  // kernels / collectives one replay stands for
   int opt_no_graph = 0;           // CML_OPT_NO_GRAPH: cml_em_step enqueues its launches one by one

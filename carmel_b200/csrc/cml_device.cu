@@ -80,6 +80,7 @@ extern "C" void cml_destroy(cml_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cml_comm_release(ctx);
   if (ctx->graph) cudaGraphExecDestroy(ctx->graph);
+  if (ctx->graph_b) cudaGraphExecDestroy(ctx->graph_b);
   if (ctx->h_step) cudaFreeHost(ctx->h_step);
   ctx->batches.clear();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1925,16 +1926,44 @@ extern "C" int cml_maximize(cml_ctx* ctx, double rate, double* max_delta) {
 //   M-step kernels, max change -> pinned host
 // is the same every iteration, so it is captured into a CUDA graph once and replayed (NCCL all-reduces are
 // capturable); anything that changes the sequence marks the graph dirty.
-static int enqueue_em_step(cml_ctx* ctx, double rate) {
+static int enqueue_em_step_a(cml_ctx* ctx) {  // everything before the all-reduce
   cudaStream_t s = ctx->stream;
   CML_CUDA(cudaMemcpyAsync(ctx->snap[3].p, ctx->ln_w.p, ctx->n_params * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  int r = cml_estimate_launch(ctx);
+  const int r = cml_estimate_launch(ctx);
   if (r) return r;
   ctx->estimate_pending = false;
-  if ((r = cml_allreduce_counts(ctx))) return r;
+  return CML_OK;
+}
+static int enqueue_em_step_b(cml_ctx* ctx, double rate) {  // everything after it
+  cudaStream_t s = ctx->stream;
   CML_CUDA(cudaMemcpyAsync(ctx->h_step, ctx->reduce + ctx->n_slots, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if ((r = enqueue_maximize(ctx, rate))) return r;
+  const int r = enqueue_maximize(ctx, rate);
+  if (r) return r;
   CML_CUDA(cudaMemcpyAsync(ctx->h_step + 3, ctx->maxchg.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  return CML_OK;
+}
+static int enqueue_em_step(cml_ctx* ctx, double rate) {
+  int r = enqueue_em_step_a(ctx);
+  if (r) return r;
+  if ((r = cml_allreduce_counts(ctx))) return r;
+  return enqueue_em_step_b(ctx, rate);
+}
+// capture fn() on the context's stream into an executable graph; launches / collectives counted once per replay
+template <class F>
+static int capture_graph(cml_ctx* ctx, cudaGraphExec_t* exec, F&& fn) {
+  cudaGraph_t g = nullptr;
+  CML_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  const int r = fn();
+  ctx->capturing = false;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  if (r) {
+    if (g) cudaGraphDestroy(g);
+    return r;
+  }
+  CML_CUDA(e);
+  CML_CUDA(cudaGraphInstantiate(exec, g, 0));
+  cudaGraphDestroy(g);
   return CML_OK;
 }
 
@@ -1950,40 +1979,40 @@ extern "C" int cml_em_step(cml_ctx* ctx, double rate, cml_estimate_result* out, 
     if (rc) return rc;
     ctx->graph_dirty = true;
   }
-  const bool use_graph = !ctx->opt_no_graph && rate == 1.;
+  const bool use_graph = !ctx->opt_no_graph && rate == 1. && !getenv("CML_NO_GRAPH");
+  // With a communicator the iteration is two graphs around an eagerly enqueued ncclAllReduce (the collective itself
+  // is not captured: one launch, and no dependence on NCCL's graph-capture support across processes).
+  const bool split = ctx->comm && ctx->comm_size > 1;
   if (use_graph) {
     if (ctx->graph_dirty || !ctx->graph) {
-      if (ctx->graph) {
-        cudaGraphExecDestroy(ctx->graph);
-        ctx->graph = nullptr;
-      }
+      if (ctx->graph) cudaGraphExecDestroy(ctx->graph);
+      if (ctx->graph_b) cudaGraphExecDestroy(ctx->graph_b);
+      ctx->graph = ctx->graph_b = nullptr;
       // one plain pass first: kernels set their attributes / lazily created events outside the capture
       int r = enqueue_em_step(ctx, rate);
       if (r) return r;
       CML_CUDA(cudaStreamSynchronize(ctx->stream));
       CML_CUDA(cudaMemcpyAsync(ctx->ln_w.p, ctx->snap[3].p, ctx->n_params * sizeof(double), cudaMemcpyDeviceToDevice,
                                ctx->stream));  // undo: the captured pass below is the one that counts
-      cudaGraph_t g = nullptr;
       const uint64_t launches0 = ctx->launches, coll0 = ctx->collectives;
-      CML_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      ctx->capturing = true;
-      r = enqueue_em_step(ctx, rate);
-      ctx->capturing = false;
-      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-      if (r) {
-        if (g) cudaGraphDestroy(g);
-        return r;
+      if (!split) {
+        if ((r = capture_graph(ctx, &ctx->graph, [&]() { return enqueue_em_step(ctx, rate); }))) return r;
+      } else {
+        if ((r = capture_graph(ctx, &ctx->graph, [&]() { return enqueue_em_step_a(ctx); }))) return r;
+        if ((r = capture_graph(ctx, &ctx->graph_b, [&]() { return enqueue_em_step_b(ctx, rate); }))) return r;
       }
-      CML_CUDA(e);
       ctx->graph_launches = ctx->launches - launches0;
       ctx->graph_collectives = ctx->collectives - coll0;
       ctx->launches = launches0;
       ctx->collectives = coll0;
-      CML_CUDA(cudaGraphInstantiate(&ctx->graph, g, 0));
-      cudaGraphDestroy(g);
       ctx->graph_dirty = false;
     }
     CML_CUDA(cudaGraphLaunch(ctx->graph, ctx->stream));
+    if (split) {
+      const int r = cml_allreduce_counts(ctx);
+      if (r) return r;
+      CML_CUDA(cudaGraphLaunch(ctx->graph_b, ctx->stream));
+    }
     ctx->launches += ctx->graph_launches;
     ctx->collectives += ctx->graph_collectives;
   } else {
