@@ -777,6 +777,12 @@ extern "C" int cml_forests_allreduce_counts(cml_forests* f) {
   ++f->collectives;
   return cml_nccl_allreduce(f->comm, f->reduce.p, f->rulespace + 3, f->stream, f->err);
 }
+extern "C" int cml_forests_synchronize(cml_forests* f) {
+  if (!f) return CML_ERR_ARG;
+  cudaSetDevice(f->device);
+  CML_CUDA(cudaStreamSynchronize(f->stream));
+  return CML_OK;
+}
 extern "C" const char* cml_forests_last_error(cml_forests* f) { return f ? f->err.c_str() : g_forest_create_err.c_str(); }
 extern "C" int cml_forests_set_stream(cml_forests* f, void* s) {
   if (!f) return CML_ERR_ARG;
@@ -1524,6 +1530,113 @@ extern "C" int cml_forests_get_inside(cml_forests* f, double* ln_inside, uint64_
     o += bt->n_forests;
   }
   CML_CUDA(cudaStreamSynchronize(f->stream));
+  return CML_OK;
+}
+// ---------------------------------------------------------------------------------------------------
+// Viterbi (best derivation) over the forests in the reference's own representation: FForest::viterbi_rec
+// (forest-em/forest.hpp:507-574): as inside, with max at the OR nodes; best[i] = the chosen child of OR node i (the
+// first child that attains the maximum).  A decode-side pass that runs once after training (forest-em -v): one thread
+// per forest, the recursion as an explicit stack of open nodes over the pre-order array.
+// ---------------------------------------------------------------------------------------------------
+const int kVitDepth = 96;
+__global__ void k_forest_viterbi(uint64_t n_forests, const uint64_t* __restrict__ node_off, const uint32_t* __restrict__ next,
+                                 const uint32_t* __restrict__ label, const uint8_t* __restrict__ backref,
+                                 const double* __restrict__ ln_w, double* __restrict__ vit, uint32_t* __restrict__ best,
+                                 double* __restrict__ root, int* __restrict__ err) {
+  const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_forests) return;
+  const uint64_t base = node_off[f];
+  const uint32_t n = (uint32_t)(node_off[f + 1] - base);
+  const uint32_t* nx = next + base;
+  const uint32_t* lb = label + base;
+  const uint8_t* br = backref + base;
+  double* v = vit + base;
+  uint32_t* bc = best + base;
+  uint32_t s_node[kVitDepth];
+  double s_acc[kVitDepth];
+  uint32_t s_best[kVitDepth];
+  int sp = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    double val;
+    bool done;
+    if (br[i]) {
+      val = v[lb[i]];  // a shared sub-forest: defined (and finished) earlier in the pre-order
+      v[i] = val;
+      done = true;
+    } else if (nx[i] == i + 1) {
+      val = lb[i] ? ln_w[lb[i]] : -CUDART_INF;  // leaf rule (an OR node without children cannot be written)
+      v[i] = val;
+      done = true;
+    } else {
+      if (sp >= kVitDepth) {
+        *err = 1;
+        return;
+      }
+      s_node[sp] = i;
+      s_acc[sp] = lb[i] ? ln_w[lb[i]] : -CUDART_INF;
+      s_best[sp] = 0xFFFFFFFFu;
+      ++sp;
+      done = false;
+      val = 0;
+    }
+    uint32_t child = i;
+    while (done && sp > 0) {  // hand the finished value to the open parent; close parents that end here
+      const int t = sp - 1;
+      const uint32_t p = s_node[t];
+      if (lb[p]) {
+        s_acc[t] += val;
+      } else if (s_best[t] == 0xFFFFFFFFu || val > s_acc[t]) {
+        s_acc[t] = val;
+        s_best[t] = child;
+      }
+      if (nx[p] == i + 1) {  // the parent's last descendant was node i
+        val = s_acc[t];
+        v[p] = val;
+        bc[p] = s_best[t];
+        child = p;
+        --sp;
+      } else
+        done = false;
+    }
+  }
+  root[f] = n ? v[0] : -CUDART_INF;
+}
+
+// viterbi scores (ln) of every forest's root and, per node of the batch, the chosen child of OR nodes (in-forest
+// pre-order index; 0xFFFFFFFF elsewhere), at the current rule weights.  The batch is the one given to cml_forests_add
+// (the device keeps forests in its own layouts, so the reference arrays are uploaded again for this one-off pass).
+extern "C" int cml_forests_viterbi(cml_forests* f, const cml_forest_batch* b, double* root_ln, uint32_t* best_child) {
+  if (!f || !b || !root_ln || !best_child) return CML_ERR_ARG;
+  F_REQUIRE(f->have_params, CML_ERR_STATE, "cml_forests_viterbi before cml_forests_set_params");
+  CML_CUDA(cudaSetDevice(f->device));
+  if (!b->n_forests) return CML_OK;
+  const uint64_t n_nodes = b->node_off[b->n_forests];
+  DevArray<uint64_t> d_off;
+  DevArray<uint32_t> d_next, d_label, d_best;
+  DevArray<uint8_t> d_br;
+  DevArray<double> d_vit, d_root;
+  DevArray<int> d_err;
+  cudaStream_t s = f->stream;
+  CML_CUDA(d_off.upload(b->node_off, b->n_forests + 1, s));
+  CML_CUDA(d_next.upload(b->next, n_nodes, s));
+  CML_CUDA(d_label.upload(b->label, n_nodes, s));
+  CML_CUDA(d_br.upload(b->backref, n_nodes, s));
+  CML_CUDA(d_best.alloc(std::max<uint64_t>(1, n_nodes)));
+  CML_CUDA(d_vit.alloc(std::max<uint64_t>(1, n_nodes)));
+  CML_CUDA(d_root.alloc(b->n_forests));
+  CML_CUDA(d_err.alloc(1));
+  CML_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), s));
+  CML_CUDA(cudaMemsetAsync(d_best.p, 0xFF, std::max<uint64_t>(1, n_nodes) * sizeof(uint32_t), s));
+  k_forest_viterbi<<<f_cdiv(b->n_forests, 128), 128, 0, s>>>(b->n_forests, d_off.p, d_next.p, d_label.p, d_br.p, f->ln_w.p, d_vit.p,
+                                                             d_best.p, d_root.p, d_err.p);
+  ++f->launches;
+  CML_CUDA(cudaGetLastError());
+  int herr = 0;
+  CML_CUDA(cudaMemcpyAsync(&herr, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaMemcpyAsync(root_ln, d_root.p, b->n_forests * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaMemcpyAsync(best_child, d_best.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  F_REQUIRE(!herr, CML_ERR_ARG, "cml_forests_viterbi: a forest nests deeper than 96 levels");
   return CML_OK;
 }
 extern "C" int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n) {

@@ -226,6 +226,10 @@ struct TrainJob {
   TrainResult res;
 
   ~TrainJob();
+  void build_model();  // parameters, chains, normalisation groups (host only; fem.cpp)
+  void export_fem_tables(std::ostream& log);        // --fem-norm / --fem-param, after training (fem.cpp)
+  void export_fem_forest(TrellisBatch const& tb, std::ostream& log);  // --fem-forest, from prepare()
+  void load_fem_param(std::string const& file);     // --load-fem-param
   void prepare();
   bool try_dense(int tape, Corpus const& local, std::vector<uint32_t>& kept, std::vector<uint32_t>& dropped);
   double estimate(double& ln_unweighted);
@@ -244,6 +248,7 @@ struct TrainJob {
   void finish();
   void ok(int rc) const;
 };
+void add_model_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M);  // train.cpp
 // Parse carmel's argv grammar (carmel.cc:929-1066), read the transducers, reduce / compose them and read the
 // corpus.  Returns carmel's exit code (0 = ready to train); messages go to `err`.
 int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err);

@@ -292,6 +292,7 @@ void ForestJob::prepare() {
   }
   if (cml_forests_create(&ctx, opt.device, opt.double_precision ? 64 : 32) != CML_OK)
     throw std::runtime_error(std::string("GPU library: ") + cml_forests_last_error(nullptr));
+  if (opt.shard_count > 1 && have_comm_id) ok(cml_forests_comm_init_rank(ctx, opt.shard_count, opt.shard_rank, comm_id));
   ok(cml_forests_set_layout(ctx, opt.layout));
   ok(cml_forests_set_rules(ctx, rulespace, groups.size(), groups.off.data(), groups.members.data()));
   ok(cml_forests_set_params(ctx, ln_w.data()));
@@ -316,11 +317,17 @@ void ForestJob::prepare() {
 // forest-em.hpp:556-572 estimate: average log prob over the non-zero forests; counts stay on the GPU
 double ForestJob::estimate(bool first_time, std::ostream& log, uint64_t* n_used) {
   ok(cml_forests_estimate_launch(ctx));
-  if (allreduce && opt.shard_count > 1) {
-    void* p = nullptr;
-    uint64_t n = 0;
-    ok(cml_forests_reduce_buffer(ctx, &p, &n));
-    allreduce(allreduce_user, p, n);
+  if (opt.shard_count > 1) {
+    if (have_comm_id) {
+      ok(cml_forests_allreduce_counts(ctx));  // NCCL, stream-ordered behind the E-step kernels
+    } else if (allreduce) {
+      // hook contract: the E-step has finished before the hook runs, the sum is complete when it returns
+      void* p = nullptr;
+      uint64_t n = 0;
+      ok(cml_forests_reduce_buffer(ctx, &p, &n));
+      ok(cml_forests_synchronize(ctx));
+      allreduce(allreduce_user, p, n);
+    }
   }
   cml_forest_estimate_result r{};
   ok(cml_forests_estimate_finish(ctx, &r));
@@ -340,13 +347,47 @@ double ForestJob::estimate(bool first_time, std::ostream& log, uint64_t* n_used)
 
 // forest-em.hpp:626-655 maximize
 void ForestJob::maximize(std::ostream& log, double& max_delta, uint64_t& max_index) {
-  (void)log;
   firsttime = false;
   cml_forest_norm_opts o{};
   o.prior_total = opt.prior_counts * (double)total_forests;
   o.add_k = opt.add_k_smoothing;
   o.zero_mode = opt.zero_zerocounts ? CML_FOREST_ZERO : CML_FOREST_UNIFORM;
   ok(cml_forests_maximize(ctx, &o, &max_delta, &max_index));
+  // on_watch_iteration (forest-em.hpp:621-624) -> dump_params (:172-189)
+  const bool watch = iteration <= opt.watch_period || (opt.watch_period && iteration % opt.watch_period == 0);
+  if (watch && opt.checkpoint_parameters && opt.shard_rank == 0) {
+    const std::string suffix = ".restart." + std::to_string(restart + 1) + ".iteration." + std::to_string(iteration + 1);
+    const std::string wf = opt.checkpoint_prefix + ".params" + suffix, cf = opt.checkpoint_prefix + ".counts" + suffix;
+    log << '\n';
+    {
+      log << "Writing trained parameters to " << wf << "\n";
+      std::ofstream o(wf);
+      write_params_to(o);
+    }
+    {
+      log << "Writing trained counts to " << cf << "\n";
+      std::ofstream o(cf);
+      write_counts_to(o);
+    }
+  }
+  ++iteration;
+}
+
+// forest-em.hpp:190-201 write_params / write_counts (one weight per line, 1-based rule ids)
+void ForestJob::write_params_to(std::ostream& o) {
+  if (ctx) ok(cml_forests_get_params(ctx, ln_w.data()));
+  for (uint64_t i = 1; i < ln_w.size(); ++i) o << ' ' << fmt_forest_weight(ln_w[i], opt.double_precision, opt.human_probs) << "\n";
+  o << std::endl;
+}
+void ForestJob::write_counts_to(std::ostream& o) {
+  std::vector<double> c(rulespace, 0.);
+  if (ctx && (!history.empty() || iteration)) ok(cml_forests_get_counts(ctx, c.data(), c.size()));
+  const double prior = (history.empty() && !iteration) ? 0. : opt.prior_counts * (double)total_forests;
+  for (uint64_t i = 1; i < count_space; ++i) {
+    const double v = c[i] + prior;
+    o << ' ' << fmt_forest_weight(v > 0 ? std::log(v) : kNegInfD, opt.double_precision, opt.human_probs) << "\n";
+  }
+  o << std::endl;
 }
 
 namespace {
@@ -446,6 +487,8 @@ double ForestJob::run(std::ostream& logs) {
   if (ran_restarts == 0) break;
   --ran_restarts;
   logs << "\nRandom restart - " << ran_restarts << " remaining.\n";
+  ++restart;
+  iteration = 0;
   randomize(rng);
   }
   logs << "\nSetting weights to model with best ";
@@ -465,20 +508,12 @@ void ForestJob::write_outputs(std::ostream& log) {
   if (!opt.outparam_file.empty()) {
     log << "Writing trained parameters to " << opt.outparam_file << "\n";
     std::ofstream o(opt.outparam_file);
-    for (uint64_t i = 1; i < ln_w.size(); ++i) o << ' ' << fmt_forest_weight(ln_w[i], dbl, opt.human_probs) << "\n";
-    o << std::endl;
+    write_params_to(o);
   }
   if (!opt.outcounts_file.empty()) {
     log << "Writing trained counts to " << opt.outcounts_file << "\n";
     std::ofstream o(opt.outcounts_file);
-    std::vector<double> c(rulespace, 0.);
-    if (ctx && !history.empty()) ok(cml_forests_get_counts(ctx, c.data(), c.size()));
-    const double prior = history.empty() ? 0. : opt.prior_counts * (double)total_forests;
-    for (uint64_t i = 1; i < count_space; ++i) {
-      const double v = c[i] + prior;
-      o << ' ' << fmt_forest_weight(v > 0 ? std::log(v) : kNegInfD, dbl, opt.human_probs) << "\n";
-    }
-    o << std::endl;
+    write_counts_to(o);
   }
   if (!opt.outinside_file.empty() && ctx) {  // final_iteration (forest-em.hpp:500-509) with the final weights
     log << "Running final per-forest inside score printing.\n";
@@ -487,6 +522,62 @@ void ForestJob::write_outputs(std::ostream& log) {
     ok(cml_forests_get_inside(ctx, in.data(), in.size()));
     std::ofstream o(opt.outinside_file);
     for (double v : in) o << fmt_forest_weight(v, dbl, opt.human_probs) << "\n";
+  }
+  if (!opt.outviterbi_file.empty() && ctx) {  // forest-em-params.cpp:125-131, forest-em.hpp:490-495,535-550
+    log << "Running final viterbi forests decoding.\n";
+    ok(cml_forests_estimate(ctx, nullptr));
+    const uint64_t nf = shard_end - shard_begin;
+    std::vector<double> sum(nf), best(nf);
+    ok(cml_forests_get_inside(ctx, sum.data(), nf));
+    std::vector<uint64_t> off(forests.node_off.begin() + shard_begin, forests.node_off.begin() + shard_end + 1);
+    const uint64_t o0 = off.empty() ? 0 : off[0];
+    for (auto& v : off) v -= o0;
+    cml_forest_batch b{};
+    b.n_forests = nf;
+    b.node_off = off.data();
+    b.next = forests.next.data() + o0;
+    b.label = forests.label.data() + o0;
+    b.backref = forests.backref.data() + o0;
+    std::vector<uint32_t> choice(nf ? off[nf] : 0);
+    ok(cml_forests_viterbi(ctx, &b, best.data(), choice.data()));
+    std::ofstream o(opt.outviterbi_file);
+    for (uint64_t f = 0; f < nf; ++f) {
+      const uint32_t* nx = b.next + off[f];
+      const uint32_t* lb = b.label + off[f];
+      const uint8_t* br = b.backref + off[f];
+      const uint32_t* ch = choice.data() + off[f];
+      o << fmt_forest_weight(best[f], dbl, opt.human_probs) << '/' << fmt_forest_weight(sum[f], dbl, opt.human_probs) << '='
+        << 100 * std::exp(best[f] - sum[f]) << "% ";
+      // write_viterbi_rec (forest.hpp:590-631) without recursion: a stack of (node, next child) for the AND nodes
+      std::vector<std::pair<uint32_t, uint32_t>> st;
+      uint32_t cur = 0;
+      bool have = true;
+      while (have || !st.empty()) {
+        if (have) {
+          while (br[cur] || lb[cur] == 0) cur = br[cur] ? lb[cur] : ch[cur];  // shared node / OR node: follow
+          if (nx[cur] == cur + 1) {
+            o << lb[cur];
+            have = false;
+          } else {
+            o << '(' << lb[cur];
+            st.emplace_back(cur, cur + 1);
+            have = false;
+          }
+        }
+        if (st.empty()) break;
+        auto& top = st.back();
+        if (top.second == nx[top.first]) {
+          o << ')';
+          st.pop_back();
+          continue;
+        }
+        o << ' ';
+        cur = top.second;
+        top.second = nx[cur];
+        have = true;
+      }
+      o << '\n';
+    }
   }
   if (!opt.history_file.empty()) {
     std::ofstream o(opt.history_file);
@@ -512,7 +603,7 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
       {"normalize-initial", 'N'}, {"use-double-precision", 'U'}, {"human-probs", 'H'},     {"log-level", 'L'},
       {"out-per-forest-inside-sum", 'S'}, {"max-forest-nodes", 'm'}, {"max-normgroup-size", 'M'}, {"prealloc-params", 'P'},
       {"tempfile-prefix", 't'},   {"forest-tick-period", 'T'},   {"watch-period", 'W'},    {"random-seed", 's'},
-      {"random-restarts", 'r'}};
+      {"random-restarts", 'r'},   {"checkpoint-prefix", 'x'},    {"checkpoint-parameters", 'c'}, {"outviterbi-file", 'v'}};
   ForestOpts& a = job.opt;
   try {
     for (int i = 1; i < argc; ++i) {
@@ -567,6 +658,7 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
         case 'o': a.outparam_file = need(); break;
         case 'O': a.outcounts_file = need(); break;
         case 'S': a.outinside_file = need(); break;
+        case 'v': a.outviterbi_file = need(); break;
         case 'i': a.max_iter = (unsigned)std::atol(need().c_str()); break;
         case 'e': a.converge_ratio = std::atof(need().c_str()); break;
         case 'd': a.converge_delta = std::atof(need().c_str()); break;
@@ -575,7 +667,10 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
         case 'L': a.log_level = (unsigned)std::atol(need().c_str()); break;
         case 'r': a.random_restarts = (unsigned)std::atol(need().c_str()); break;
         case 's': a.random_seed = std::strtoull(need().c_str(), nullptr, 10); break;
-        case 'm': case 'M': case 'P': case 't': case 'T': case 'W': need(); break;  // sizing / cosmetic: accepted, unused
+        case 'W': a.watch_period = (unsigned)std::atol(need().c_str()); break;
+        case 'x': a.checkpoint_prefix = need(); break;
+        case 'c': a.checkpoint_parameters = true; break;
+        case 'm': case 'M': case 'P': case 't': case 'T': need(); break;  // sizing / cosmetic: accepted, unused
         case 'z': a.zero_zerocounts = true; break;
         case 'u': a.initial_1_params = true; break;
         case 'N': a.normalize_initial = true; break;
@@ -600,6 +695,7 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
 struct cml_forest_job {
   cb::ForestJob job;
   std::string err;
+  bool quiet = false;
 };
 namespace {
 template <class F>
@@ -630,6 +726,12 @@ extern "C" int cml_forest_job_open(cml_forest_job** out, int argc, const char* c
 }
 extern "C" void cml_forest_job_close(cml_forest_job* j) { delete j; }
 extern "C" const char* cml_forest_job_error(cml_forest_job* j) { return j ? j->err.c_str() : "null job"; }
+extern "C" int cml_forest_job_set_comm(cml_forest_job* j, const unsigned char id[128]) {
+  if (!j || !id) return CML_ERR_ARG;
+  std::memcpy(j->job.comm_id, id, 128);
+  j->job.have_comm_id = true;
+  return CML_OK;
+}
 extern "C" int cml_forest_job_set_allreduce(cml_forest_job* j, cml_allreduce_fn fn, void* user) {
   if (!j) return CML_ERR_ARG;
   j->job.allreduce = fn;
@@ -643,9 +745,15 @@ extern "C" int cml_forest_job_prepare(cml_forest_job* j) {
   });
 }
 extern "C" cml_forests* cml_forest_job_context(cml_forest_job* j) { return j ? j->job.ctx : nullptr; }
+extern "C" int cml_forest_job_set_quiet(cml_forest_job* j, int quiet) {  // ranks > 0 of a multi-GPU run do not log
+  if (!j) return CML_ERR_ARG;
+  j->quiet = quiet != 0;
+  return CML_OK;
+}
 extern "C" int cml_forest_job_train(cml_forest_job* j) {
   return fguarded(j, [&]() {
-    j->job.run(std::cerr);
+    std::ostringstream sink;
+    j->job.run(j->quiet ? (std::ostream&)sink : (std::ostream&)std::cerr);
     return (int)CML_OK;
   });
 }

@@ -41,7 +41,7 @@ struct NormGroupsHost {
 
 struct ForestOpts {
   std::string forests_file, normgroups_file, initparam_file, outparam_file, outcounts_file, outinside_file, history_file,
-      print_forests_file;
+      print_forests_file, outviterbi_file;  // -v : 'best/sum=pct% <viterbi derivation>' per forest (forest-em-params.hpp:115)
   unsigned max_iter = 1000;            // -i  (forest-em-params.hpp:185)
   double converge_ratio = 1. / 65536;  // -e  (:186)
   double converge_delta = 0;           // -d  (:187)
@@ -59,6 +59,12 @@ struct ForestOpts {
   int shard_rank = 0, shard_count = 1;  // --shard=r/N
   int layout = CML_FOREST_LAYOUT_AUTO;  // --layout=auto|group|thread (device layout family, see cml_forests_set_layout)
   bool parse_only = false;            // --parse-only : read (and --print-forests) without touching the GPU
+  // checkpoints (forest-em.hpp:166-201,621-641; forest-em-params.hpp:138-145): on every "watch" iteration (the first
+  // watch_period iterations, then every watch_period-th) write <prefix>.params / <prefix>.counts
+  // .restart.R.iteration.I; a run is resumed by passing a params checkpoint as -I
+  unsigned watch_period = 10;          // -W
+  std::string checkpoint_prefix;       // -x
+  bool checkpoint_parameters = false;  // -c
 };
 
 struct ForestIter {
@@ -80,8 +86,13 @@ struct ForestJob {
   uint64_t shard_begin = 0, shard_end = 0;
   ForestAllReduceFn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  bool have_comm_id = false;          // NCCL rendezvous token (cml_forest_job_set_comm / forest-em-b200 --gpus=N): the
+  unsigned char comm_id[128] = {0};   // library issues the per-iteration all-reduce itself
   cml_forests* ctx = nullptr;
   bool prepared = false, firsttime = true;
+  unsigned iteration = 0, restart = 0;  // maximize() calls so far / current random restart (checkpoint names)
+  void write_params_to(std::ostream& o);
+  void write_counts_to(std::ostream& o);
   std::vector<ForestIter> history;
   double best_alp = 0;
   uint64_t last_n_zero = 0;

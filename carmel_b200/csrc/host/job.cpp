@@ -124,6 +124,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   if (lopt.count("scaled")) topt.space = CML_SPACE_SCALED;
   if (lopt.count("no-ell")) topt.no_ell = true;
   if (lopt.count("no-dense")) topt.dense = -1;
+  if (lopt.count("fem-forest")) topt.dense = -1;  // the forests are the derivation lattices (carmel.cc:764-767 force_cascade_derivs)
   if (lopt.count("lane-min")) topt.lane_min = std::atoi(lopt["lane-min"].c_str());
   if (lopt.count("no-lane")) topt.lane_min = 0;
   if (lopt.count("no-factor")) topt.no_factor = true;

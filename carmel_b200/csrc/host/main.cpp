@@ -34,7 +34,10 @@ static void usage() {
                "  --gpu=n  CUDA device   --history=file  --dump-trellis=file  --write-composed=file\n"
                "  --gpus=N examples sharded over GPUs 0..N-1 of this box, one host thread per GPU; the count table is\n"
                "           all-reduced with NCCL every iteration (EM only)\n"
-               "  --trellis-only  build (and dump) the derivation lattices on the host, then stop\n";
+               "  --trellis-only  build (and dump) the derivation lattices on the host, then stop\n"
+               "  --fem-forest=f --fem-norm=f --fem-param=f   export the cascade for forest-em(-b200): one derivation forest\n"
+               "           per example, normalisation groups, parameters after training (-M -1: the normalised input weights)\n"
+               "  --load-fem-param=f  read cascade weights written by --fem-param\n";
 }
 
 // carmel-b200 --gpus=N ...: N jobs in one process, job r keeps block r of the corpus on GPU r (--shard=r/N --gpu=r); the
@@ -107,6 +110,10 @@ int main(int argc, char** argv) {
     }
     if (rc == -9 && job.fst_files.empty()) usage();
     if (rc != 0) return rc;
+    if (job.lopt.count("load-fem-param")) {  // carmel.cc:792-800
+      std::cerr << "Reading cascade weights from --load-fem-param=" << job.lopt["load-fem-param"] << std::endl;
+      job.load_fem_param(job.lopt["load-fem-param"]);
+    }
     if (job.lopt.count("trellis-only")) {  // host-side lattice construction only (no GPU work): parity tests
       TrellisBatch tb;
       std::vector<uint32_t> dropped;
@@ -135,6 +142,7 @@ int main(int argc, char** argv) {
     else
       job.run(std::cerr);
     job.write_outputs(std::cout);
+    if (job.lopt.count("fem-norm") || job.lopt.count("fem-param")) job.export_fem_tables(std::cerr);  // carmel.cc:1528 fem_out
     return 0;
   } catch (std::exception& e) {
     std::cerr << "ERROR: " << e.what() << std::endl;

@@ -16,9 +16,7 @@ namespace cb {
 
 TrainOpts::TrainOpts() : ln_converge_delta(std::log(1e-4)), ln_converge_ratio(std::log(.999)) {}
 
-namespace {
-
-void add_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
+void add_model_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
   // normalisation groups: all arcs leaving a state (JOINT) or leaving a state with the same input
   // symbol (CONDITIONAL); NONE keeps weights (carmel/src/fst.h:1362-1446, cascade.h:339-350)
   std::unordered_map<uint32_t, uint32_t> tie_ids;  // '!N' ids are local to a transducer
@@ -53,6 +51,8 @@ void add_member(Wfst const& w, NormalizeMethod const& m, ModelArrays& M) {
     }
   }
 }
+
+namespace {
 
 // logweight::root / ppxper keep a zero weight zero (weight.h:435-440, WEIGHT_CORRECT_ZERO): a corpus with a
 // zero-probability example therefore has "perplexity 0", which the reference then treats as the best
@@ -238,21 +238,7 @@ bool TrainJob::try_dense(int tape, Corpus const& local, std::vector<uint32_t>& k
 // lattices (this rank's shard) flattened and resident on the GPU.
 void TrainJob::prepare() {
   if (prepared) return;
-  using_cascade = !cascade.trivial;
-  members = using_cascade ? cascade.members : std::vector<Wfst*>{x};
-  for (size_t i = 0; i < members.size(); ++i)
-    add_member(*members[i], i < methods.size() ? methods[i] : NormalizeMethod(), M);
-  M.n_params = (uint32_t)M.ln_w.size();
-  M.n_arcs = (uint32_t)x->num_arcs();
-  if (using_cascade) {
-    M.chain_off.push_back(0);
-    for (auto const& st : x->states)
-      for (Arc const& a : st) {
-        auto const& ch = cascade.chains.at(a.group);
-        M.chain_param.insert(M.chain_param.end(), ch.begin(), ch.end());
-        M.chain_off.push_back((uint32_t)M.chain_param.size());
-      }
-  }
+  build_model();
   if (cml_create(&ctx, opt.device, opt.precision, opt.space) != CML_OK)
     throw std::runtime_error(std::string("carmel_b200: ") + cml_last_error(nullptr));
   if (opt.max_iter == 0) ok(cml_set_option(ctx, CML_OPT_ARC_COUNTS, 1));  // -M 0 writes per-arc fractional counts
@@ -385,6 +371,7 @@ void TrainJob::prepare() {
       std::ofstream o(opt.dump_trellis_file, std::ios::binary);
       tb.dump(o, M.n_arcs);
     }
+    if (lopt.count("fem-forest") && opt.shard_rank == 0) export_fem_forest(tb, std::cerr);
     if (!dense_done) {
       if (!tb.ex_states.empty()) {
         cml_trellis_batch b{};
@@ -509,6 +496,14 @@ void TrainJob::finish() {
 TrainResult const& TrainJob::run(std::ostream& log) {
   prepare();
   double ln_corpus_p = 0;
+  if (opt.max_iter + 1 == 0) {  // -M -1: the likelihood of the (normalised) input weights, nothing else (train.cc:516-517)
+    const double p = estimate(ln_corpus_p);
+    res.history.push_back({1, ln_corpus_p, p, 0});
+    res.ln_best_ppx = w_root(p, -corpus.total_weight);
+    write_back();
+    finish();
+    return res;
+  }
   // ---- -M 0 / -M 1: fractional counts only / a single iteration (train.cc:520-538) ----
   if (opt.max_iter == 0 || (opt.max_iter == 1 && opt.ran_restarts == 0)) {  // (train.cc:520)
     const double p = estimate(ln_corpus_p);

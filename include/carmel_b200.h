@@ -421,6 +421,11 @@ int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n);        /
 int cml_forests_reduce_buffer(cml_forests* f, void** device_ptr, uint64_t* n_doubles);
 /* multi-GPU: join an NCCL communicator (token from cml_comm_unique_id) and sum the reduce buffer over the ranks on the
  * context's stream, between cml_forests_estimate_launch and cml_forests_estimate_finish */
+/* Viterbi (best derivation, FForest::viterbi_rec, forest-em/forest.hpp:507-574; forest-em -v): ln score of every
+ * forest's best derivation and, per node of `b` (the batch as given to cml_forests_add), the chosen child of OR nodes
+ * (in-forest pre-order index, the first child that attains the maximum; 0xFFFFFFFF elsewhere), at the current weights */
+int cml_forests_viterbi(cml_forests* f, const cml_forest_batch* b, double* root_ln, uint32_t* best_child);
+int cml_forests_synchronize(cml_forests* f);
 int cml_forests_comm_init_rank(cml_forests* f, int n_ranks, int rank, const unsigned char id[CML_COMM_ID_BYTES]);
 int cml_forests_allreduce_counts(cml_forests* f);
 /* M-step: rule_weights <- normalised (counts + prior_total).  max_delta / max_index as NormalizeGroups
@@ -439,6 +444,8 @@ typedef struct cml_forest_job_info {
 int cml_forest_job_open(cml_forest_job** out, int argc, const char* const* argv);
 void cml_forest_job_close(cml_forest_job* job);
 const char* cml_forest_job_error(cml_forest_job* job);
+int cml_forest_job_set_quiet(cml_forest_job* job, int quiet); /* no log lines from this job (ranks > 0 of --gpus=N) */
+int cml_forest_job_set_comm(cml_forest_job* job, const unsigned char id[CML_COMM_ID_BYTES]); /* as cml_job_set_comm */
 int cml_forest_job_set_allreduce(cml_forest_job* job, cml_allreduce_fn fn, void* user);
 int cml_forest_job_prepare(cml_forest_job* job);
 cml_forests* cml_forest_job_context(cml_forest_job* job);

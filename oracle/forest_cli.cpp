@@ -14,7 +14,7 @@
 using namespace forc;
 
 struct Args {
-  std::string forests, norm, initparam, outparam, outcounts, outinside, history, print_forests;
+  std::string forests, norm, initparam, outparam, outcounts, outinside, history, print_forests, outviterbi;
   ForestOpts opt;
   bool dbl = false;
   int time_estimate = 0;
@@ -91,6 +91,11 @@ static int run(Args const& a) {
     for (auto const& f : F.forests) F.visit_forest(f, false, false, sink);
     for (double l : F.last_inside) o << fmt_weight(LW<Real>::ln((Real)l), a.opt.human_probs) << "\n";
   }
+  if (!a.outviterbi.empty()) {  // forest-em-params.cpp:125-131 final viterbi forests decoding (-v)
+    log << "Running final viterbi forests decoding.\n";
+    std::ofstream o(a.outviterbi);
+    for (auto const& f : F.forests) F.write_viterbi(o, f, a.opt.human_probs);
+  }
   if (!a.history.empty()) {
     std::ofstream o(a.history);
     o.precision(17);
@@ -106,7 +111,7 @@ int main(int argc, char** argv) {
       {"outcounts-file", 'O'}, {"max-iter", 'i'},          {"converge", 'e'},           {"deltaparam-epsilon", 'd'},
       {"prior-counts-per", 'p'}, {"add-k-smoothing", 'k'}, {"zero-zerocounts", 'z'},    {"initial-1-params", 'u'},
       {"normalize-initial", 'N'}, {"use-double-precision", 'U'}, {"human-probs", 'H'},  {"log-level", 'L'},
-      {"out-per-forest-inside-sum", 'S'}};
+      {"out-per-forest-inside-sum", 'S'}, {"outviterbi-file", 'v'}};
   try {
     for (int i = 1; i < argc; ++i) {
       std::string s = argv[i];
@@ -146,6 +151,7 @@ int main(int argc, char** argv) {
         case 'o': a.outparam = need(); break;
         case 'O': a.outcounts = need(); break;
         case 'S': a.outinside = need(); break;
+        case 'v': a.outviterbi = need(); break;
         case 'i': a.opt.max_iter = (unsigned)std::atol(need().c_str()); break;
         case 'e': a.opt.converge_ratio = std::atof(need().c_str()); break;
         case 'd': a.opt.converge_delta = std::atof(need().c_str()); break;

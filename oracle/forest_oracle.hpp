@@ -514,6 +514,71 @@ struct Forests {
         b = c.next;
       } while (b != e);
   }
+  // forest.hpp:507-574 viterbi_rec: as inside_rec with max for the OR nodes; best[i] = the chosen child of OR node i
+  // (the first child that attains the maximum: a later child replaces the choice only when strictly better)
+  std::vector<uint32_t> vit_best;
+  void viterbi_rec(Forest const& f, uint32_t b) {
+    const uint32_t e = f.nodes[b].next, i = b;
+    ForestNode const& nd = f.nodes[b];
+    if (nd.backref) {
+      inside[i] = inside[nd.label];
+      return;
+    }
+    if (nd.label == 0) {  // OR
+      ++b;
+      uint32_t n = f.nodes[b].next;
+      viterbi_rec(f, b);
+      inside[i] = inside[i + 1];
+      vit_best[i] = b;
+      for (b = n; b < e; b = n) {
+        n = f.nodes[b].next;
+        viterbi_rec(f, b);
+        if (inside[i] < inside[b]) {
+          inside[i] = inside[b];
+          vit_best[i] = b;
+        }
+      }
+    } else {  // AND
+      inside[i] = rule_weights[nd.label];
+      ++b;
+      uint32_t n;
+      for (; b < e; b = n) {
+        n = f.nodes[b].next;
+        viterbi_rec(f, b);
+        inside[i] *= inside[b];
+      }
+    }
+  }
+  // forest.hpp:590-631 write_viterbi_rec
+  void write_viterbi_rec(std::ostream& o, Forest const& f, uint32_t b) const {
+    ForestNode const& nd = f.nodes[b];
+    if (nd.backref) return write_viterbi_rec(o, f, nd.label);
+    if (nd.label == 0) return write_viterbi_rec(o, f, vit_best[b]);
+    const uint32_t e = nd.next;
+    if (b + 1 == e) {
+      o << nd.label;
+      return;
+    }
+    o << '(' << nd.label;
+    uint32_t n;
+    for (++b; b < e; b = n) {
+      n = f.nodes[b].next;
+      o << ' ';
+      write_viterbi_rec(o, f, b);
+    }
+    o << ')';
+  }
+  // forest-em.hpp:535-550 (final viterbi decoding, -v): "best/sum=pct% tree" per forest (forest.hpp:581-585)
+  void write_viterbi(std::ostream& o, Forest const& f, bool human) {
+    inside_rec(f, 0);
+    outside_order.clear();
+    const W sum = inside[0];
+    vit_best.assign(f.size(), 0);
+    viterbi_rec(f, 0);
+    o << fmt_weight(inside[0], human) << '/' << fmt_weight(sum, human) << '=' << 100 * (inside[0] / sum).getReal() << "% ";
+    write_viterbi_rec(o, f, 0);
+    o << '\n';
+  }
   // forest.hpp:439-491 compute_norm_outside
   bool compute_norm_outside(Forest const& f) {
     if (!(inside[0] > W())) {

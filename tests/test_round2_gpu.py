@@ -297,3 +297,54 @@ def test_cli_two_gpus_equals_one(cli, tmp_path):
         assert abs(x[1] - y[1]) <= 1e-9 * max(1.0, abs(x[1])), (x, y)
     for n in ("tags.fsa.trained", "lexicon.fst.trained"):
         compare_wfst_text(open(os.path.join(d, "two", n)).read(), open(os.path.join(d, "one", n)).read(), 1e-8, ln_floor=-690.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _norm_sets(path):
+    txt = open(path).read()
+    return sorted(tuple(sorted(int(t) for t in g.split())) for g in re.findall(r"\(([0-9 ]+)\)", txt))
+
+
+def test_fem_export_matches_oracle_and_feeds_the_forest_kernels(cli, oracle_bin, tmp_path, native_lib):
+    """carmel -> forest-em bridge in the PRODUCT (cascade.h:85-202, carmel.cc:756-830, to-fem.sh usage `-M -1`):
+    forests byte-identical to the oracle's export, same parameters and normalisation groups; the exported cascade
+    trained by forest-em-b200 follows the reference's golden cipher trajectory; --load-fem-param round trip."""
+    import math
+    from carmel_b200 import FOREST_CLI_PATH
+    from helpers import golden
+    d = str(tmp_path)
+    sub = {}
+    for who in ("o", "p"):
+        os.makedirs(f"{d}/{who}")
+        sub[who] = stage(os.path.join(d, who), "cipher.data", "cipher.wfsa", "cipher.fst")
+    args = ["--train-cascade", "--normby=NC", "-HJ", "-M", "-1"]
+    rc, _, err = run(oracle_bin, [*args, f"--fem-forest={d}/o.forest", f"--fem-norm={d}/o.norm", f"--fem-param={d}/o.param", *sub["o"]])
+    assert rc == 0, err
+    rc, _, err = run(cli, [*args, "--scaled", f"--fem-forest={d}/p.forest", f"--fem-norm={d}/p.norm", f"--fem-param={d}/p.param",
+                           *sub["p"]])
+    assert rc == 0, err
+    assert open(f"{d}/p.forest", "rb").read() == open(f"{d}/o.forest", "rb").read()
+    assert _norm_sets(f"{d}/p.norm") == _norm_sets(f"{d}/o.norm")
+    from forest_helpers import read_weights
+    po, pp = read_weights(f"{d}/o.param"), read_weights(f"{d}/p.param")
+    assert len(po) == len(pp) == 550 + 599  # cipher.wfsa + cipher.fst arcs
+    for x, y in zip(pp, po):
+        assert (x == y) or abs(x - y) <= 1e-9 * max(1.0, abs(y)), (x, y)
+    # the product's own export drives the forest kernels along the golden trajectory (commands.trace:6905-6950)
+    want = golden()["cipher"]["trajectory_log2"]
+    rc, _, err = run(FOREST_CLI_PATH, ["-U", "-f", f"{d}/p.forest", "-n", f"{d}/p.norm", "-I", f"{d}/p.param", "-i", "22", "-e", "0",
+                                       f"--history={d}/h"])
+    assert rc == 0, err
+    hist = [(int(r[0]), float(r[1])) for r in (ln.split() for ln in open(f"{d}/h")) if r]
+    assert len(hist) == len(want) == 22
+    for (it, log2p), h in zip(want, hist):
+        got = h[1] * 10 / math.log(2)
+        assert h[0] == it and abs(got - log2p) <= 1.01e-5 * abs(log2p), (it, got, log2p)
+    # --load-fem-param: the exported weights read back give the same likelihood as the transducers they came from
+    rc, _, e1 = run(cli, ["--train-cascade", "--normby=NC", "-M", "-1", "--scaled", f"--history={d}/h1", *sub["p"]])
+    assert rc == 0, e1
+    rc, _, e2 = run(cli, ["--train-cascade", "--normby=NC", "-M", "-1", "--scaled", f"--load-fem-param={d}/p.param", f"--history={d}/h2",
+                          *sub["p"]])
+    assert rc == 0, e2
+    a, b = read_history(f"{d}/h1"), read_history(f"{d}/h2")
+    assert len(a) == len(b) == 1 and abs(a[0][1] - b[0][1]) <= 1e-9 * abs(a[0][1])
