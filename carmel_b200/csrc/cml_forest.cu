@@ -700,6 +700,16 @@ struct cml_forests {
   DevArray<double> hot;
   uint32_t n_hot = 0;
   std::vector<std::unique_ptr<ForestBatch>> batches;
+  // --crp Gibbs sampling (cml_forests_gibbs_*): the forests in the reference representation, CRP state, samples
+  bool have_gibbs = false;
+  uint64_t g_forests = 0, g_nodes = 0, g_cap = 0;
+  uint32_t g_norms = 0;
+  int g_cur = 0;
+  DevArray<uint64_t> g_node_off, g_samp_base;
+  DevArray<uint32_t> g_next, g_label, g_norm, g_sample[2], g_len[2];
+  DevArray<uint8_t> g_backref;
+  DevArray<double> g_prior, g_count, g_cum, g_normsum, g_ins;
+  DevArray<int> g_err;
   void* comm = nullptr;  // ncclComm_t of this rank (cml_forests_comm_init_rank), null on a single GPU
   int comm_size = 1;
   uint64_t collectives = 0;
@@ -1637,6 +1647,345 @@ extern "C" int cml_forests_viterbi(cml_forests* f, const cml_forest_batch* b, do
   CML_CUDA(cudaMemcpyAsync(best_child, d_best.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CML_CUDA(cudaStreamSynchronize(s));
   F_REQUIRE(!herr, CML_ERR_ARG, "cml_forests_viterbi: a forest nests deeper than 96 levels");
+  return CML_OK;
+}
+// ---------------------------------------------------------------------------------------------------
+// forest-em --crp: Gibbs sampling of one derivation per forest under the CRP cache model.
+// Reference: FForests::resample_block (forest-em/forest-em.hpp:752-764): FForest::compute_inside(W) with the proposal
+// probabilities count/normsum (forest.hpp:769-816), then FForest::choose_random top-down (forest.hpp:726-758): at an OR
+// node one uniform picks the first child whose (inside^power / norm) takes the running choice below zero, an AND node
+// records its rule and descends into all children; a back reference continues with power 1 (reproduced).  Counts:
+// gibbs_base::iteration (graehl/shared/gibbs.hpp:836-877).  Uniforms are counter based, u(seed, sweep, forest, draw),
+// one per OR node visited, in visit order, so SEQUENTIAL mode reproduces the CPU restatement derivation by derivation.
+// The sampler works on the reference's pre-order arrays (the recursion as explicit stacks); arithmetic is the
+// reference's fp64 logweight (pairwise log-add in child order).
+// ---------------------------------------------------------------------------------------------------
+const int kGibbsDepth = 96, kGibbsStack = 384;
+__device__ __forceinline__ uint64_t fg_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double fg_uniform(uint64_t seed, uint32_t sweep, uint32_t block, uint32_t draw) {
+  uint64_t h = fg_mix64(seed ^ fg_mix64(((uint64_t)sweep << 32) | block));
+  h = fg_mix64(h + draw);
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+struct FGibbsArgs {
+  uint64_t n_forests;
+  const uint64_t* node_off;
+  const uint32_t* next;
+  const uint32_t* label;
+  const uint8_t* backref;
+  const uint32_t* norm;     // [rulespace] normalisation group or 0xFFFFFFFF (fixed probability = prior)
+  const double* prior;
+  double* count;            // sequential mode updates these between forests
+  double* normsum;
+  double* ins;              // [nodes] ln inside scratch
+  const uint64_t* samp_base;
+  const uint32_t* old_len;  // previous sample (removed first in sequential mode)
+  const uint32_t* old_ids;
+  uint32_t* new_len;
+  uint32_t* new_ids;
+  double power;
+  uint64_t seed;
+  uint32_t sweep;
+  int sequential;
+  int* err;
+};
+__device__ void forest_gibbs_one(const FGibbsArgs& A, uint64_t f) {
+  const uint64_t base = A.node_off[f];
+  const uint32_t n = (uint32_t)(A.node_off[f + 1] - base);
+  const uint32_t* nx = A.next + base;
+  const uint32_t* lb = A.label + base;
+  const uint8_t* br = A.backref + base;
+  double* in_ = A.ins + base;
+  const uint64_t sb = A.samp_base[f];
+  if (A.sequential) {  // addc(block, -wt): the forest's previous sample leaves the counts (gibbs.hpp:851-852)
+    for (uint32_t k = 0, e = A.old_len[f]; k < e; ++k) {
+      const uint32_t id = A.old_ids[sb + k], g = A.norm[id];
+      if (g != 0xFFFFFFFFu) {
+        A.count[id] -= 1.;
+        A.normsum[g] -= 1.;
+      }
+    }
+  }
+  auto proposal_ln = [&](uint32_t id) -> double {
+    const uint32_t g = A.norm[id];
+    const double p = g != 0xFFFFFFFFu ? A.count[id] / A.normsum[g] : A.prior[id];
+    return p > 0 ? log(p) : -CUDART_INF;
+  };
+  {  // compute_inside(W): post-order with a stack of open nodes
+    uint32_t s_node[kGibbsDepth];
+    double s_acc[kGibbsDepth];
+    bool s_first[kGibbsDepth];
+    int sp = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      double val = 0;
+      bool done;
+      if (br[i]) {
+        val = in_[lb[i]];
+        in_[i] = val;
+        done = true;
+      } else if (nx[i] == i + 1) {
+        val = lb[i] ? proposal_ln(lb[i]) : -CUDART_INF;
+        in_[i] = val;
+        done = true;
+      } else {
+        if (sp >= kGibbsDepth) {
+          *A.err = 1;
+          return;
+        }
+        s_node[sp] = i;
+        s_acc[sp] = lb[i] ? proposal_ln(lb[i]) : -CUDART_INF;
+        s_first[sp] = true;
+        ++sp;
+        done = false;
+      }
+      while (done && sp > 0) {
+        const int t = sp - 1;
+        const uint32_t p = s_node[t];
+        if (lb[p])
+          s_acc[t] += val;  // AND: product
+        else {
+          s_acc[t] = s_first[t] ? val : ln_add<double>(s_acc[t], val);  // OR: first child, then += in order
+          s_first[t] = false;
+        }
+        if (nx[p] == i + 1) {
+          val = s_acc[t];
+          in_[p] = val;
+          --sp;
+        } else
+          done = false;
+      }
+    }
+  }
+  // choose_random: depth-first, children in order; the stack holds the nodes still to visit (bit 31: power 1)
+  uint32_t st[kGibbsStack];
+  int sp = 0;
+  uint32_t len = 0, draw = 0;
+  st[sp++] = 0u;
+  while (sp > 0) {
+    uint32_t b = st[--sp];
+    const bool unit = (b >> 31) != 0;
+    b &= 0x7fffffffu;
+    const double power = unit ? 1. : A.power;
+    if (br[b]) {
+      st[sp++] = lb[b] | 0x80000000u;  // choose_random(l.pointer(), v): default power
+      continue;
+    }
+    const uint32_t e = nx[b];
+    if (lb[b] == 0) {
+      double norm = -CUDART_INF;
+      for (uint32_t i = b + 1; i != e; i = nx[i]) {
+        const double x = in_[i];
+        norm = ln_add<double>(norm, x > -CUDART_INF ? x * power : x);
+      }
+      uint32_t i = b + 1;
+      double choice = fg_uniform(A.seed, A.sweep, (uint32_t)f, draw++);
+      for (;;) {
+        const double x = in_[i];
+        choice -= exp((x > -CUDART_INF ? x * power : x) - norm);
+        if (choice < 0) break;
+        const uint32_t nn = nx[i];
+        if (nn == e) break;
+        i = nn;
+      }
+      st[sp++] = i | (unit ? 0x80000000u : 0u);
+    } else {
+      if (sb + len >= A.samp_base[f + 1]) {  // (a derivation that revisits shared sub-forests more often than budgeted)
+        *A.err = 2;
+        return;
+      }
+      A.new_ids[sb + len++] = lb[b];
+      // children are pushed last to first so that the first child is visited next
+      uint32_t cnt = 0;
+      for (uint32_t c = b + 1; c < e; c = nx[c]) ++cnt;
+      if (sp + (int)cnt > kGibbsStack) {
+        *A.err = 1;
+        return;
+      }
+      uint32_t k = 0;
+      for (uint32_t c = b + 1; c < e; c = nx[c], ++k) st[sp + (cnt - 1 - k)] = c | (unit ? 0x80000000u : 0u);
+      sp += (int)cnt;
+    }
+  }
+  A.new_len[f] = len;
+  if (A.sequential) {  // addc(block, +wt)
+    for (uint32_t k = 0; k < len; ++k) {
+      const uint32_t id = A.new_ids[sb + k], g = A.norm[id];
+      if (g != 0xFFFFFFFFu) {
+        A.count[id] += 1.;
+        A.normsum[g] += 1.;
+      }
+    }
+  }
+}
+__global__ void k_forest_gibbs_sequential(FGibbsArgs A) {  // the exact collapsed sampler: one thread walks the corpus
+  if (blockIdx.x || threadIdx.x) return;
+  for (uint64_t f = 0; f < A.n_forests; ++f) {
+    forest_gibbs_one(A, f);
+    if (*A.err) return;
+  }
+}
+__global__ void k_forest_gibbs_batched(FGibbsArgs A) {  // every forest against the previous sweep's counts
+  const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < A.n_forests) forest_gibbs_one(A, f);
+}
+// batched mode: count deltas of the sweep (old sample out, new sample in)
+__global__ void k_forest_gibbs_apply(uint64_t n_forests, const uint64_t* __restrict__ samp_base, const uint32_t* __restrict__ old_len,
+                                     const uint32_t* __restrict__ old_ids, const uint32_t* __restrict__ new_len,
+                                     const uint32_t* __restrict__ new_ids, const uint32_t* __restrict__ norm, double* count,
+                                     double* normsum) {
+  const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_forests) return;
+  const uint64_t sb = samp_base[f];
+  for (uint32_t k = 0, e = old_len[f]; k < e; ++k) {
+    const uint32_t id = old_ids[sb + k], g = norm[id];
+    if (g != 0xFFFFFFFFu) {
+      atomicAdd(&count[id], -1.);
+      atomicAdd(&normsum[g], -1.);
+    }
+  }
+  for (uint32_t k = 0, e = new_len[f]; k < e; ++k) {
+    const uint32_t id = new_ids[sb + k], g = norm[id];
+    if (g != 0xFFFFFFFFu) {
+      atomicAdd(&count[id], 1.);
+      atomicAdd(&normsum[g], 1.);
+    }
+  }
+}
+__global__ void k_forest_gibbs_accumulate(uint64_t n, const double* __restrict__ count, double dt, double* __restrict__ cum) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cum[i] += dt * count[i];
+}
+
+// counts := priors (restore_p0, gibbs.hpp:618-623); the forests stay on the device in the reference representation
+extern "C" int cml_forests_gibbs_init(cml_forests* f, const cml_forest_batch* b, const cml_forest_gibbs_model* g) {
+  if (!f || !b || !g || !g->param_norm || !g->param_prior) return CML_ERR_ARG;
+  F_REQUIRE(f->have_rules, CML_ERR_STATE, "cml_forests_gibbs_init before cml_forests_set_rules");
+  CML_CUDA(cudaSetDevice(f->device));
+  cudaStream_t s = f->stream;
+  const uint64_t nn = b->n_forests ? b->node_off[b->n_forests] : 0;
+  std::vector<uint64_t> base(b->n_forests + 1, 0);
+  for (uint64_t i = 0; i < b->n_forests; ++i) {
+    uint64_t he = 0;
+    for (uint64_t k = b->node_off[i]; k < b->node_off[i + 1]; ++k) he += (!b->backref[k] && b->label[k] != 0);
+    // a shared sub-forest can be sampled through several references: bound the path by the node count of the forest
+    base[i + 1] = base[i] + std::max<uint64_t>(he, b->node_off[i + 1] - b->node_off[i]) * 4;
+  }
+  for (uint64_t r = 0; r < f->rulespace; ++r)
+    F_REQUIRE(g->param_norm[r] == 0xFFFFFFFFu || g->param_norm[r] < g->n_norms, CML_ERR_ARG, "param_norm out of range");
+  f->g_forests = b->n_forests;
+  f->g_nodes = nn;
+  f->g_cap = base[b->n_forests];
+  f->g_norms = g->n_norms;
+  CML_CUDA(f->g_node_off.upload(b->node_off, b->n_forests + 1, s));
+  CML_CUDA(f->g_next.upload(b->next, nn, s));
+  CML_CUDA(f->g_label.upload(b->label, nn, s));
+  CML_CUDA(f->g_backref.upload(b->backref, nn, s));
+  CML_CUDA(f->g_samp_base.upload(base.data(), base.size(), s));
+  CML_CUDA(f->g_norm.upload(g->param_norm, f->rulespace, s));
+  CML_CUDA(f->g_prior.upload(g->param_prior, f->rulespace, s));
+  CML_CUDA(f->g_count.upload(g->param_prior, f->rulespace, s));
+  CML_CUDA(f->g_cum.alloc(f->rulespace));
+  CML_CUDA(cudaMemsetAsync(f->g_cum.p, 0, f->rulespace * sizeof(double), s));
+  std::vector<double> ns(std::max<uint32_t>(1, g->n_norms), 0.);
+  for (uint64_t r = 0; r < f->rulespace; ++r)
+    if (g->param_norm[r] != 0xFFFFFFFFu) ns[g->param_norm[r]] += g->param_prior[r];
+  CML_CUDA(f->g_normsum.upload(ns.data(), ns.size(), s));
+  CML_CUDA(f->g_ins.alloc(std::max<uint64_t>(1, nn)));
+  for (int k = 0; k < 2; ++k) {
+    CML_CUDA(f->g_sample[k].alloc(std::max<uint64_t>(1, f->g_cap)));
+    CML_CUDA(f->g_len[k].alloc(std::max<uint64_t>(1, b->n_forests)));
+    CML_CUDA(cudaMemsetAsync(f->g_len[k].p, 0, std::max<uint64_t>(1, b->n_forests) * sizeof(uint32_t), s));
+  }
+  CML_CUDA(f->g_err.alloc(1));
+  CML_CUDA(cudaMemsetAsync(f->g_err.p, 0, sizeof(int), s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  f->g_cur = 0;
+  f->have_gibbs = true;
+  return CML_OK;
+}
+
+// one sweep (gibbs_base::iteration): every forest resampled once; afterwards cum += accumulate_dt * count
+extern "C" int cml_forests_gibbs_sweep(cml_forests* f, const cml_gibbs_sweep_opts* o) {
+  if (!f || !o) return CML_ERR_ARG;
+  F_REQUIRE(f->have_gibbs, CML_ERR_STATE, "cml_forests_gibbs_sweep before cml_forests_gibbs_init");
+  CML_CUDA(cudaSetDevice(f->device));
+  cudaStream_t s = f->stream;
+  const int cur = f->g_cur, nxt = cur ^ 1;
+  FGibbsArgs A;
+  A.n_forests = f->g_forests;
+  A.node_off = f->g_node_off.p;
+  A.next = f->g_next.p;
+  A.label = f->g_label.p;
+  A.backref = f->g_backref.p;
+  A.norm = f->g_norm.p;
+  A.prior = f->g_prior.p;
+  A.count = f->g_count.p;
+  A.normsum = f->g_normsum.p;
+  A.ins = f->g_ins.p;
+  A.samp_base = f->g_samp_base.p;
+  A.old_len = f->g_len[cur].p;
+  A.old_ids = f->g_sample[cur].p;
+  A.new_len = f->g_len[nxt].p;
+  A.new_ids = f->g_sample[nxt].p;
+  A.power = o->power;
+  A.seed = o->seed;
+  A.sweep = o->sweep;
+  A.sequential = o->mode == CML_GIBBS_SEQUENTIAL;
+  A.err = f->g_err.p;
+  if (f->g_forests) {
+    if (A.sequential) {
+      k_forest_gibbs_sequential<<<1, 32, 0, s>>>(A);
+      ++f->launches;
+    } else {
+      k_forest_gibbs_batched<<<f_cdiv(f->g_forests, 64), 64, 0, s>>>(A);
+      k_forest_gibbs_apply<<<f_cdiv(f->g_forests, 128), 128, 0, s>>>(f->g_forests, f->g_samp_base.p, f->g_len[cur].p, f->g_sample[cur].p,
+                                                                   f->g_len[nxt].p, f->g_sample[nxt].p, f->g_norm.p, f->g_count.p,
+                                                                   f->g_normsum.p);
+      f->launches += 2;
+    }
+  }
+  if (o->accumulate_dt != 0.) {
+    k_forest_gibbs_accumulate<<<f_cdiv(f->rulespace, 256), 256, 0, s>>>(f->rulespace, f->g_count.p, o->accumulate_dt, f->g_cum.p);
+    ++f->launches;
+  }
+  CML_CUDA(cudaGetLastError());
+  int herr = 0;
+  CML_CUDA(cudaMemcpyAsync(&herr, f->g_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  F_REQUIRE(!herr, CML_ERR_ARG,
+            herr == 2 ? "cml_forests_gibbs_sweep: a sampled derivation is longer than its sample slot"
+                      : "cml_forests_gibbs_sweep: a forest nests deeper than the sampler's stacks (96 levels)");
+  f->g_cur = nxt;
+  return CML_OK;
+}
+extern "C" uint64_t cml_forests_gibbs_sample_capacity(cml_forests* f) { return f ? f->g_cap : 0; }
+// current sample: len[forest] rule ids at ids[base_f ..] in record order (choose_random's v.record), base_f from
+// cml_forests_gibbs_sample_bases
+extern "C" int cml_forests_gibbs_get_samples(cml_forests* f, uint32_t* len, uint32_t* ids, uint64_t cap, uint64_t* bases) {
+  if (!f || !len || !ids) return CML_ERR_ARG;
+  F_REQUIRE(f->have_gibbs && cap >= f->g_cap, CML_ERR_ARG, "cml_forests_gibbs_get_samples: no sampler state or buffer too small");
+  CML_CUDA(cudaSetDevice(f->device));
+  cudaStream_t s = f->stream;
+  CML_CUDA(cudaMemcpyAsync(len, f->g_len[f->g_cur].p, f->g_forests * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaMemcpyAsync(ids, f->g_sample[f->g_cur].p, f->g_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (bases) CML_CUDA(cudaMemcpyAsync(bases, f->g_samp_base.p, (f->g_forests + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
+  return CML_OK;
+}
+extern "C" int cml_forests_gibbs_get_state(cml_forests* f, double* count, double* cum, double* normsum) {
+  if (!f) return CML_ERR_ARG;
+  F_REQUIRE(f->have_gibbs, CML_ERR_STATE, "no sampler state");
+  CML_CUDA(cudaSetDevice(f->device));
+  cudaStream_t s = f->stream;
+  if (count) CML_CUDA(cudaMemcpyAsync(count, f->g_count.p, f->rulespace * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (cum) CML_CUDA(cudaMemcpyAsync(cum, f->g_cum.p, f->rulespace * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (normsum) CML_CUDA(cudaMemcpyAsync(normsum, f->g_normsum.p, std::max<uint32_t>(1, f->g_norms) * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CML_CUDA(cudaStreamSynchronize(s));
   return CML_OK;
 }
 extern "C" int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n) {

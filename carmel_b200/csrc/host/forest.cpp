@@ -501,6 +501,132 @@ double ForestJob::run(std::ostream& logs) {
   return best_alp;
 }
 
+// forest-em --crp (FForests::run_gibbs, forest-em/forest-em.hpp:711-750; gibbs_base::run / iteration,
+// graehl/shared/gibbs.hpp:803-877): parameters from the normalised rule weights, one sweep per iteration on the GPU,
+// the cache-model (or --sample-prob) probability of every sweep's sample on the host, final weights = time-averaged
+// counts normalised per group (finalize_cumulative_counts + from_gibbs).
+void ForestJob::run_gibbs(std::ostream& log) {
+  prepare();
+  if (opt.shard_count > 1) throw std::runtime_error("--crp samples the forests in corpus order: one GPU (no --shard / --gpus)");
+  ok(cml_forests_normalize_params(ctx));  // to_gibbs -> define_gibbs(true): normalize() first
+  ok(cml_forests_get_params(ctx, ln_w.data()));
+  std::vector<uint32_t> norm(rulespace, 0xFFFFFFFFu);
+  std::vector<double> prior(rulespace, 0.);
+  for (uint64_t g = 0; g < groups.size(); ++g) {  // visit_norm_param (normalize.hpp:194-210); group ids 1.. as there
+    const uint64_t n = groups.off[g + 1] - groups.off[g];
+    for (uint64_t k = groups.off[g]; k < groups.off[g + 1]; ++k) {
+      const uint64_t p = groups.members[k];
+      norm[p] = (uint32_t)g + 1;
+      prior[p] = opt.crp_uniform_p0 ? opt.crp_alpha : opt.crp_alpha * std::exp(ln_w[p]) * (double)n;
+    }
+  }
+  for (uint64_t p = 0; p < rulespace; ++p)
+    if (norm[p] == 0xFFFFFFFFu) prior[p] = std::exp(ln_w[p]);  // no group: fixed probability
+  const uint32_t n_norms = (uint32_t)groups.size() + 1;
+  const uint64_t nf = shard_end - shard_begin;
+  std::vector<uint64_t> off(forests.node_off.begin() + shard_begin, forests.node_off.begin() + shard_end + 1);
+  const uint64_t o0 = off.empty() ? 0 : off[0];
+  for (auto& v : off) v -= o0;
+  cml_forest_batch b{};
+  b.n_forests = nf;
+  b.node_off = off.data();
+  b.next = forests.next.data() + o0;
+  b.label = forests.label.data() + o0;
+  b.backref = forests.backref.data() + o0;
+  cml_forest_gibbs_model gm{norm.data(), prior.data(), n_norms};
+  ok(cml_forests_gibbs_init(ctx, &b, &gm));
+  const uint64_t cap = cml_forests_gibbs_sample_capacity(ctx);
+  std::vector<uint32_t> len(nf), ids(cap), prev_len(nf, 0), prev_ids;
+  std::vector<uint64_t> base(nf + 1);
+  const unsigned Ni = opt.crp_iter;
+  unsigned burnin = std::min(opt.crp_burnin, Ni);
+  if (opt.crp_final_counts) burnin = Ni;  // gibbs_opts.hpp:259
+  auto time_of = [&](unsigned it) { return it > burnin ? (double)it - (double)burnin : 0.; };
+  const double n_sym = opt.crp_n_sym ? opt.crp_n_sym : (double)(off.empty() ? 0 : off[nf]);  // forest-em.hpp:733: n_nodes
+  std::vector<double> ccount(rulespace), csum(n_norms), sp_count, sp_sum;
+  if (opt.crp_sample_prob) {
+    sp_count = prior;
+    sp_sum.assign(n_norms, 0.);
+    for (uint64_t p = 0; p < rulespace; ++p)
+      if (norm[p] != 0xFFFFFFFFu) sp_sum[norm[p]] += prior[p];
+    prev_ids.assign(cap, 0);
+  }
+  for (unsigned it = 0; it <= Ni; ++it) {
+    double temperature = opt.crp_high_temp;
+    if (Ni > 0 && opt.crp_high_temp != opt.crp_low_temp)
+      temperature = opt.crp_high_temp + (opt.crp_low_temp - opt.crp_high_temp) * std::min(1.0, (double)it / Ni);
+    cml_gibbs_sweep_opts so{};
+    so.mode = opt.crp_batched ? CML_GIBBS_BATCHED : CML_GIBBS_SEQUENTIAL;
+    so.power = temperature > 0 ? 1. / temperature : 1.;
+    so.seed = opt.crp_seed;
+    so.sweep = it;
+    so.init_from_params = 0;
+    so.accumulate_dt = it == Ni ? 1. : time_of(it + 1) - time_of(it);
+    ok(cml_forests_gibbs_sweep(ctx, &so));
+    ok(cml_forests_gibbs_get_samples(ctx, len.data(), ids.data(), cap, base.data()));
+    double ln_p = 0;
+    if (opt.crp_sample_prob) {  // as carmel-b200 --sample-prob: scored with the new sample's counts back in
+      for (uint64_t f = 0; f < nf; ++f) {
+        for (uint32_t k = 0; k < prev_len[f]; ++k) {
+          const uint32_t p = prev_ids[base[f] + k];
+          if (norm[p] != 0xFFFFFFFFu) sp_count[p] -= 1., sp_sum[norm[p]] -= 1.;
+        }
+        for (uint32_t k = 0; k < len[f]; ++k) {
+          const uint32_t p = ids[base[f] + k];
+          if (norm[p] != 0xFFFFFFFFu) sp_count[p] += 1., sp_sum[norm[p]] += 1.;
+        }
+        for (uint32_t k = 0; k < len[f]; ++k) {
+          const uint32_t p = ids[base[f] + k];
+          ln_p += norm[p] != 0xFFFFFFFFu ? std::log(sp_count[p] / sp_sum[norm[p]]) : std::log(prior[p]);
+        }
+      }
+      prev_len = len;
+      prev_ids = ids;
+    } else {  // cache model (gibbs.hpp:137-140,700-742): reset every sweep
+      std::fill(csum.begin(), csum.end(), 0.);
+      for (uint64_t p = 0; p < rulespace; ++p) {
+        ccount[p] = prior[p];
+        if (norm[p] != 0xFFFFFFFFu) csum[norm[p]] += prior[p];
+      }
+      for (uint64_t f = 0; f < nf; ++f)
+        for (uint32_t k = 0; k < len[f]; ++k) {
+          const uint32_t p = ids[base[f] + k];
+          ln_p += norm[p] != 0xFFFFFFFFu ? std::log(ccount[p]++ / csum[norm[p]]++) : std::log(prior[p]);
+        }
+    }
+    history.push_back({it, ln_p, 0., 0, nf});
+    log << "Gibbs i=" << it << (opt.crp_sample_prob ? " sample prob=" : " cache-model prob=") << format_base2(ln_p);
+    if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << format_base2(-ln_p / n_sym);
+    log << " per-block-ppx(N=" << nf << ")=" << format_base2(-ln_p / (double)nf) << "\n";
+  }
+  if (!opt.outsample_file.empty()) {  // print_sample (forest-em.hpp:775-784)
+    std::ofstream o(opt.outsample_file);
+    for (uint64_t f = 0; f < nf; ++f) {
+      for (uint32_t k = 0; k < len[f]; ++k) o << (k ? " " : "") << ids[base[f] + k];
+      o << "\n";
+    }
+  }
+  // finalize_cumulative_counts (gibbs.hpp:626-644) + from_gibbs (forest-em.hpp:743-750)
+  std::vector<double> count(rulespace), cum(rulespace), normsum(n_norms, 0.), v(rulespace);
+  ok(cml_forests_gibbs_get_state(ctx, count.data(), cum.data(), nullptr));
+  const double tmax1 = ((double)Ni - (double)burnin) + 1;
+  for (uint64_t p = 0; p < rulespace; ++p) {
+    if (opt.crp_final_counts && !opt.crp_exclude_prior)
+      v[p] = count[p];
+    else if (opt.crp_final_counts)
+      v[p] = count[p] - prior[p];
+    else
+      v[p] = cum[p] - (opt.crp_exclude_prior ? prior[p] * tmax1 : 0.);
+    if (norm[p] != 0xFFFFFFFFu) normsum[norm[p]] += v[p];
+  }
+  for (uint64_t p = 0; p < rulespace; ++p) {
+    const double fp = norm[p] != 0xFFFFFFFFu ? (v[p] > 0 ? v[p] / normsum[norm[p]] : 0.) : prior[p];
+    ln_w[p] = fp > 0 ? std::log(fp) : kNegInfD;
+  }
+  ok(cml_forests_set_params(ctx, ln_w.data()));
+  gibbs_done = true;
+}
+
 // forest-em-params.cpp:116-136 outputs; forest-em.hpp:190-201 write_params / write_counts
 void ForestJob::write_outputs(std::ostream& log) {
   const bool dbl = opt.double_precision;
@@ -627,6 +753,22 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
           continue;
         }
         if (key == "gpu") { a.device = std::atoi(val.c_str()); continue; }
+        if (key == "crp") { a.crp_iter = (unsigned)std::atol(val.c_str()); continue; }
+        if (key == "burnin") { a.crp_burnin = (unsigned)std::atol(val.c_str()); continue; }
+        if (key == "const-alpha") { a.crp_alpha = std::atof(val.c_str()); continue; }
+        if (key == "high-temp") { a.crp_high_temp = std::atof(val.c_str()); continue; }
+        if (key == "low-temp") { a.crp_low_temp = std::atof(val.c_str()); continue; }
+        if (key == "n-symbols") { a.crp_n_sym = std::atof(val.c_str()); continue; }
+        if (key == "seed") { a.crp_seed = std::strtoull(val.c_str(), nullptr, 10); continue; }
+        if (key == "outsample-file") { a.outsample_file = val; continue; }
+        if (key == "uniform-p0") { a.crp_uniform_p0 = true; continue; }
+        if (key == "final-counts") { a.crp_final_counts = true; continue; }
+        if (key == "crp-exclude-prior") { a.crp_exclude_prior = true; continue; }
+        if (key == "sample-prob") { a.crp_sample_prob = true; continue; }
+        if (key == "crp-batched") { a.crp_batched = true; continue; }
+        if (key == "alpha" || key == "include-self" || key == "expectation" || key == "crp-restarts" || key == "init-em" ||
+            key == "prior-inference-stddev")  // sampler variants this path does not build: refuse, do not ignore
+          throw std::runtime_error("--" + key + " is not supported by forest-em-b200");
         if (key == "shard") {
           const size_t sl = val.find('/');
           if (sl == std::string::npos) throw std::runtime_error("--shard=r/N needs 0 <= r < N");
@@ -753,7 +895,11 @@ extern "C" int cml_forest_job_set_quiet(cml_forest_job* j, int quiet) {  // rank
 extern "C" int cml_forest_job_train(cml_forest_job* j) {
   return fguarded(j, [&]() {
     std::ostringstream sink;
-    j->job.run(j->quiet ? (std::ostream&)sink : (std::ostream&)std::cerr);
+    std::ostream& lg = j->quiet ? (std::ostream&)sink : (std::ostream&)std::cerr;
+    if (j->job.opt.crp_iter)
+      j->job.run_gibbs(lg);  // forest-em-params.cpp:112-113: gibbs replaces EM
+    else
+      j->job.run(lg);
     return (int)CML_OK;
   });
 }

@@ -62,6 +62,13 @@ struct ForestOpts {
   // checkpoints (forest-em.hpp:166-201,621-641; forest-em-params.hpp:138-145): on every "watch" iteration (the first
   // watch_period iterations, then every watch_period-th) write <prefix>.params / <prefix>.counts
   // .restart.R.iteration.I; a run is resumed by passing a params checkpoint as -I
+  // --crp=n Gibbs sampling instead of EM (gibbs_opts.hpp:34-130 via forest-em-params.hpp:172-175)
+  unsigned crp_iter = 0, crp_burnin = 0;
+  double crp_alpha = .1;               // --const-alpha (gibbs_opts.hpp:229): prior = alpha * p0 * |group|
+  bool crp_uniform_p0 = false, crp_final_counts = false, crp_exclude_prior = false, crp_sample_prob = false, crp_batched = false;
+  double crp_high_temp = 1, crp_low_temp = 1, crp_n_sym = 0;
+  uint64_t crp_seed = 1;               // --seed : key of the counter-based uniforms
+  std::string outsample_file;          // --outsample-file : the final sample, rule ids in record order, one forest per line
   unsigned watch_period = 10;          // -W
   std::string checkpoint_prefix;       // -x
   bool checkpoint_parameters = false;  // -c
@@ -89,7 +96,7 @@ struct ForestJob {
   bool have_comm_id = false;          // NCCL rendezvous token (cml_forest_job_set_comm / forest-em-b200 --gpus=N): the
   unsigned char comm_id[128] = {0};   // library issues the per-iteration all-reduce itself
   cml_forests* ctx = nullptr;
-  bool prepared = false, firsttime = true;
+  bool prepared = false, firsttime = true, gibbs_done = false;
   unsigned iteration = 0, restart = 0;  // maximize() calls so far / current random restart (checkpoint names)
   void write_params_to(std::ostream& o);
   void write_counts_to(std::ostream& o);
@@ -104,6 +111,7 @@ struct ForestJob {
   double estimate(bool first_time, std::ostream& log, uint64_t* n_used = nullptr);
   void maximize(std::ostream& log, double& max_delta, uint64_t& max_index);
   double run(std::ostream& log);  // overrelaxed_em
+  void run_gibbs(std::ostream& log);  // --crp (forest-em.hpp:694-797)
   void randomize(std::mt19937_64& rng);
   void write_outputs(std::ostream& log);
   void ok(int rc) const;

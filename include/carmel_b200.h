@@ -421,6 +421,26 @@ int cml_forests_get_counts(cml_forests* f, double* counts, uint64_t n);        /
 int cml_forests_reduce_buffer(cml_forests* f, void** device_ptr, uint64_t* n_doubles);
 /* multi-GPU: join an NCCL communicator (token from cml_comm_unique_id) and sum the reduce buffer over the ranks on the
  * context's stream, between cml_forests_estimate_launch and cml_forests_estimate_finish */
+/* ---- forest-em --crp: Gibbs sampling over forests ------------------------------------------ *
+ * Replaces FForests::run_gibbs / to_gibbs / resample_block (forest-em/forest-em.hpp:694-797), FForest::compute_inside(W)
+ * and choose_random (forest-em/forest.hpp:726-816) under gibbs_base (graehl/shared/gibbs.hpp:803-877).  One parameter
+ * per rule: param_norm[rule] = normalisation group (or 0xFFFFFFFF: fixed probability = param_prior[rule]),
+ * param_prior[rule] = alpha * p0 * |group| (gibbs.hpp:589-597).  `b` is the batch as given to cml_forests_add.  Sweeps
+ * take the same options as cml_gibbs_sweep; uniforms are u(seed, sweep, forest, draw), one per OR node visited, so
+ * CML_GIBBS_SEQUENTIAL reproduces the CPU restatement derivation by derivation.  CML_GIBBS_BATCHED samples every
+ * forest against the previous sweep's counts, its own previous sample included (gibbs --include-self semantics). */
+typedef struct cml_forest_gibbs_model {
+  const uint32_t* param_norm;  /* [rulespace] */
+  const double* param_prior;   /* [rulespace] */
+  uint32_t n_norms;
+} cml_forest_gibbs_model;
+int cml_forests_gibbs_init(cml_forests* f, const cml_forest_batch* b, const cml_forest_gibbs_model* g);
+int cml_forests_gibbs_sweep(cml_forests* f, const cml_gibbs_sweep_opts* o);
+uint64_t cml_forests_gibbs_sample_capacity(cml_forests* f);
+/* current sample: len[forest] rule ids at ids[bases[forest] ..] in record order; bases has n_forests + 1 entries */
+int cml_forests_gibbs_get_samples(cml_forests* f, uint32_t* len, uint32_t* ids, uint64_t cap, uint64_t* bases);
+int cml_forests_gibbs_get_state(cml_forests* f, double* count, double* cum, double* normsum);
+
 /* Viterbi (best derivation, FForest::viterbi_rec, forest-em/forest.hpp:507-574; forest-em -v): ln score of every
  * forest's best derivation and, per node of `b` (the batch as given to cml_forests_add), the chosen child of OR nodes
  * (in-forest pre-order index, the first child that attains the maximum; 0xFFFFFFFF elsewhere), at the current weights */

@@ -18,6 +18,12 @@ struct Args {
   ForestOpts opt;
   bool dbl = false;
   int time_estimate = 0;
+  // --crp=n Gibbs sampling (gibbs_opts.hpp:34-130 as used by forest-em-params.hpp:172-175)
+  unsigned crp = 0, burnin = 0;
+  double alpha = .1, high_temp = 1, low_temp = 1, n_sym = 0;
+  bool uniformp0 = false, final_counts = false, exclude_prior = false, sample_prob = false;
+  unsigned long long seed = 1;
+  std::string outsample;
 };
 
 template <class Real>
@@ -70,7 +76,35 @@ static int run(Args const& a) {
                   a.time_estimate, sec, he, F.n_nodes, F.forests.size(), alp);
       return 0;
     }
-    if (a.opt.max_iter) F.train(log);
+    if (a.crp) {  // forest-em-params.cpp:112-113: gibbs replaces EM
+      typename Forests<Real>::GibbsOpts g;
+      g.iter = a.crp;
+      g.burnin = std::min(a.burnin, a.crp);
+      if (a.final_counts) g.burnin = a.crp;  // gibbs_opts.hpp:259
+      g.alpha = a.alpha;
+      g.uniformp0 = a.uniformp0;
+      g.final_counts = a.final_counts;
+      g.exclude_prior = a.exclude_prior;
+      g.sample_prob = a.sample_prob;
+      g.high_temp = a.high_temp;
+      g.low_temp = a.low_temp;
+      g.seed = a.seed;
+      g.n_sym = a.n_sym;
+      F.run_gibbs(g, log);
+      if (!a.outsample.empty()) {  // print_sample (forest-em.hpp:775-784): rule ids in record order, one forest per line
+        std::ofstream o(a.outsample);
+        for (auto const& smp : F.g_sample) {
+          for (size_t k = 0; k < smp.size(); ++k) o << (k ? " " : "") << smp[k];
+          o << "\n";
+        }
+      }
+      if (!a.history.empty()) {
+        std::ofstream o(a.history);
+        o.precision(17);
+        for (size_t i = 0; i < F.g_iter_ln_prob.size(); ++i) o << i << ' ' << F.g_iter_ln_prob[i] << "\n";
+      }
+    } else if (a.opt.max_iter)
+      F.train(log);
   }
   if (!a.outparam.empty()) {
     log << "Writing trained parameters to " << a.outparam << "\n";
@@ -96,7 +130,7 @@ static int run(Args const& a) {
     std::ofstream o(a.outviterbi);
     for (auto const& f : F.forests) F.write_viterbi(o, f, a.opt.human_probs);
   }
-  if (!a.history.empty()) {
+  if (!a.history.empty() && !a.crp) {
     std::ofstream o(a.history);
     o.precision(17);
     for (auto const& h : F.history) o << h.i << ' ' << h.alp << ' ' << h.max_delta << ' ' << h.max_index << ' ' << h.n << "\n";
@@ -128,6 +162,18 @@ int main(int argc, char** argv) {
         if (key == "history") { a.history = val; continue; }
         if (key == "print-forests") { a.print_forests = val; continue; }
         if (key == "time-estimate") { a.time_estimate = std::atoi(val.c_str()); continue; }
+        if (key == "crp") { a.crp = (unsigned)std::atol(val.c_str()); continue; }
+        if (key == "burnin") { a.burnin = (unsigned)std::atol(val.c_str()); continue; }
+        if (key == "const-alpha") { a.alpha = std::atof(val.c_str()); continue; }
+        if (key == "high-temp") { a.high_temp = std::atof(val.c_str()); continue; }
+        if (key == "low-temp") { a.low_temp = std::atof(val.c_str()); continue; }
+        if (key == "n-symbols") { a.n_sym = std::atof(val.c_str()); continue; }
+        if (key == "seed") { a.seed = std::strtoull(val.c_str(), nullptr, 10); continue; }
+        if (key == "outsample-file") { a.outsample = val; continue; }
+        if (key == "uniform-p0") { a.uniformp0 = true; continue; }
+        if (key == "final-counts") { a.final_counts = true; continue; }
+        if (key == "crp-exclude-prior") { a.exclude_prior = true; continue; }
+        if (key == "sample-prob") { a.sample_prob = true; continue; }
         auto it = longs.find(key);
         if (it == longs.end()) throw std::runtime_error("unknown option --" + key);
         c = it->second;

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -578,6 +579,210 @@ struct Forests {
     o << fmt_weight(inside[0], human) << '/' << fmt_weight(sum, human) << '=' << 100 * (inside[0] / sum).getReal() << "% ";
     write_viterbi_rec(o, f, 0);
     o << '\n';
+  }
+  // ------------------------------------------------------------------------------------------------------------
+  // Gibbs sampling over forests (forest-em --crp): FForests::run_gibbs / to_gibbs / resample_block / from_gibbs
+  // (forest-em/forest-em.hpp:694-797), FForest::compute_inside(W) + choose_random (forest/forest.hpp:726-816),
+  // gibbs_base (graehl/shared/gibbs.hpp:582-623,712-792,803-877), delta_sum (delta_sum.hpp:49-106).
+  // PARITY UNPINNED by the reference (forest-em ships no expected outputs and draws from boost's generator): sampled
+  // derivations are defined on injected uniforms u(seed, sweep, forest, draw), one per OR node visited, in visit order.
+  // ------------------------------------------------------------------------------------------------------------
+  struct GibbsOpts {
+    unsigned iter = 0, burnin = 0;
+    double alpha = .1;  // --const-alpha (gibbs_opts.hpp:229)
+    bool uniformp0 = false, final_counts = false, exclude_prior = false, sample_prob = false;
+    double high_temp = 1, low_temp = 1;
+    uint64_t seed = 1;
+    double n_sym = 0;  // --n-symbols; default: total forest nodes (forest-em.hpp:733)
+  };
+  struct GDelta {  // delta_sum.hpp:49-106
+    double x = 0, tmax = 0, s = 0;
+    void clear(double x0) { x = x0, s = tmax = 0; }
+    void add_delta(double d, double t) {
+      const double moret = t - tmax;
+      if (moret > 0) {
+        tmax = t;
+        s += moret * x;
+      } else if (moret < 0)
+        s += d * (-moret);
+      x += d;
+    }
+    void extend(double t) {
+      const double moret = t - tmax;
+      tmax = t;
+      s += x * moret;
+    }
+  };
+  static constexpr unsigned G_NONORM = 0xFFFFFFFFu;
+  std::vector<double> g_prior;       // pseudo-count, or the fixed probability of a parameter without a group
+  std::vector<unsigned> g_norm;      // normalisation group (1-based as visit_norm_param numbers them) or G_NONORM
+  std::vector<GDelta> g_count;
+  std::vector<double> g_normsum;
+  std::vector<std::vector<unsigned>> g_sample;  // per forest: rule ids in record order
+  std::vector<double> g_iter_ln_prob;
+  static uint64_t g_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+  }
+  static double g_uniform(uint64_t seed, uint32_t sweep, uint32_t block, uint32_t draw) {  // as gibbs_oracle.hpp
+    uint64_t h = g_mix64(seed ^ g_mix64(((uint64_t)sweep << 32) | block));
+    h = g_mix64(h + draw);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+  }
+  double g_proposal(unsigned id) const {  // gibbs.hpp:154-157
+    return g_norm[id] != G_NONORM ? g_count[id].x / g_normsum[g_norm[id]] : g_prior[id];
+  }
+  // forest.hpp:769-816 compute_inside(W): inside with the proposal probabilities
+  void g_inside_rec(Forest const& f, uint32_t b) {
+    const uint32_t e = f.nodes[b].next, i = b;
+    ForestNode const& nd = f.nodes[b];
+    if (nd.backref) {
+      inside[i] = inside[nd.label];
+      return;
+    }
+    if (nd.label == 0) {
+      ++b;
+      uint32_t n = f.nodes[b].next;
+      g_inside_rec(f, b);
+      inside[i] = inside[i + 1];
+      for (b = n; b < e; b = n) {
+        n = f.nodes[b].next;
+        g_inside_rec(f, b);
+        inside[i] += inside[b];
+      }
+    } else {
+      inside[i] = W((Real)g_proposal(nd.label));
+      ++b;
+      uint32_t n;
+      for (; b < e; b = n) {
+        n = f.nodes[b].next;
+        g_inside_rec(f, b);
+        inside[i] *= inside[b];
+      }
+    }
+  }
+  // forest.hpp:726-758 choose_random.  NB the reference follows a back reference with the default power = 1
+  // (`choose_random(l.pointer(), v)`), so annealing stops below shared sub-forests; reproduced.
+  void g_choose(Forest const& f, uint32_t b, double power, GibbsOpts const& o, uint32_t sweep, uint32_t block, uint32_t& draw,
+                std::vector<unsigned>& out) {
+    ForestNode const& nd = f.nodes[b];
+    const uint32_t e = nd.next;
+    if (nd.backref) return g_choose(f, nd.label, 1., o, sweep, block, draw, out);
+    if (nd.label == 0) {
+      W norm;  // zero
+      for (uint32_t i = b + 1; i != e; i = f.nodes[i].next) norm += inside[i].pow((Real)power);
+      uint32_t i = b + 1;
+      double choice = g_uniform(o.seed, sweep, block, draw++);
+      for (;;) {
+        choice -= (inside[i].pow((Real)power) / norm).getReal();
+        if (choice < 0) break;
+        const uint32_t n = f.nodes[i].next;
+        if (n == e) break;
+        i = n;
+      }
+      g_choose(f, i, power, o, sweep, block, draw, out);
+    } else {
+      out.push_back(nd.label);
+      for (uint32_t c = b + 1; c < e; c = f.nodes[c].next) g_choose(f, c, power, o, sweep, block, draw, out);
+    }
+  }
+  void g_addc(std::vector<unsigned> const& ids, double d, double time) {  // gibbs.hpp:769-792
+    for (unsigned id : ids)
+      if (g_norm[id] != G_NONORM) {
+        g_normsum[g_norm[id]] += d;
+        g_count[id].add_delta(d, time);
+      }
+  }
+  void run_gibbs(GibbsOpts o, std::ostream& log) {
+    // to_gibbs (forest-em.hpp:731-742): normalise, then one parameter per rule (visit_norm_param, normalize.hpp:194-210)
+    normalize_params();
+    g_prior.assign(rulespace, 0.);
+    g_norm.assign(rulespace, G_NONORM);
+    unsigned normi = 0;
+    for (auto const& g : norm_groups.groups) {
+      ++normi;
+      for (size_t p : g) {
+        g_norm[p] = normi;
+        g_prior[p] = o.uniformp0 ? o.alpha : o.alpha * (double)rule_weights[p].getReal() * (double)g.size();
+      }
+    }
+    for (size_t p = 0; p < rulespace; ++p)
+      if (g_norm[p] == G_NONORM) g_prior[p] = (double)rule_weights[p].getReal();
+    const unsigned nnorm = normi + 1;
+    if (!o.n_sym) o.n_sym = (double)n_nodes;
+    // run (gibbs.hpp:803-828)
+    g_count.assign(rulespace, GDelta());
+    g_normsum.assign(nnorm, 0.);
+    for (size_t p = 0; p < rulespace; ++p)
+      if (g_norm[p] != G_NONORM) {
+        g_normsum[g_norm[p]] += g_prior[p];
+        g_count[p].clear(g_prior[p]);
+      }
+    g_sample.assign(forests.size(), {});
+    g_iter_ln_prob.clear();
+    for (unsigned iter = 0; iter <= o.iter; ++iter) {
+      double time = (double)iter - (double)o.burnin;
+      if (time < 0 || iter == 0) time = 0;
+      double temperature = o.high_temp;
+      if (o.iter > 0 && o.high_temp != o.low_temp)
+        temperature = o.high_temp + (o.low_temp - o.high_temp) * std::min(1.0, (double)iter / o.iter);
+      const double power = temperature > 0 ? 1. / temperature : 1;
+      std::vector<double> ccount(rulespace, 0.), csum(nnorm, 0.);  // cache reset (gibbs.hpp:656-667,700-705)
+      for (size_t p = 0; p < rulespace; ++p)
+        if (g_norm[p] != G_NONORM) csum[g_norm[p]] += (ccount[p] = g_prior[p]);
+      double ln_p = 0;
+      for (uint32_t b = 0; b < forests.size(); ++b) {
+        Forest const& f = forests[b];
+        g_addc(g_sample[b], -1., time);
+        g_sample[b].clear();
+        g_inside_rec(f, 0);
+        uint32_t draw = 0;
+        g_choose(f, 0, power, o, iter, b, draw, g_sample[b]);
+        if (o.sample_prob) {  // as the carmel oracle: scored with the new sample's counts back in
+          g_addc(g_sample[b], 1., time);
+          for (unsigned id : g_sample[b]) ln_p += std::log(g_proposal(id));
+          continue;
+        }
+        for (unsigned id : g_sample[b])
+          ln_p += std::log(g_norm[id] != G_NONORM ? ccount[id]++ / csum[g_norm[id]]++ : g_prior[id]);
+        g_addc(g_sample[b], 1., time);
+      }
+      g_iter_ln_prob.push_back(ln_p);
+      const double l2 = 1. / std::log(2.);
+      log << "Gibbs i=" << iter << (o.sample_prob ? " sample prob=" : " cache-model prob=") << "2^" << fmt_g6(ln_p * l2);
+      if (o.n_sym) log << " per-point-ppx(N=" << o.n_sym << ")=2^" << fmt_g6(-ln_p * l2 / o.n_sym);
+      log << " per-block-ppx(N=" << forests.size() << ")=2^" << fmt_g6(-ln_p * l2 / (double)forests.size()) << "\n";
+    }
+    // finalize_cumulative_counts (gibbs.hpp:626-644) + from_gibbs (forest-em.hpp:743-750)
+    if (!(o.final_counts && !o.exclude_prior)) {
+      const double tmax1 = ((double)o.iter - (double)o.burnin) + 1;
+      for (size_t p = 0; p < rulespace; ++p) {
+        if (g_norm[p] == G_NONORM) continue;
+        if (o.exclude_prior) {
+          g_count[p].s += -g_prior[p] * g_count[p].tmax;
+          g_count[p].x += -g_prior[p];
+        }
+        if (!o.final_counts) {
+          g_count[p].extend(tmax1);
+          g_count[p].x = g_count[p].s;
+        }
+      }
+      g_normsum.assign(nnorm, 0.);
+      for (size_t p = 0; p < rulespace; ++p)
+        if (g_norm[p] != G_NONORM) g_normsum[g_norm[p]] += g_count[p].x;
+    }
+    for (size_t p = 0; p < rulespace; ++p) {
+      double fp = g_prior[p];
+      if (g_norm[p] != G_NONORM) fp = g_count[p].x > 0 ? g_count[p].x / g_normsum[g_norm[p]] : 0.;
+      rule_weights[p] = W((Real)fp);
+    }
+  }
+  static std::string fmt_g6(double v) {
+    std::ostringstream o;
+    o << std::setprecision(6) << v;
+    return o.str();
   }
   // forest.hpp:439-491 compute_norm_outside
   bool compute_norm_outside(Forest const& f) {

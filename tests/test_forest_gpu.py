@@ -302,3 +302,75 @@ def test_forest_cli_two_gpus_equals_one(fem, tmp_path):
         assert abs(a[1] - b[1]) <= 1e-9 * max(1.0, abs(a[1])), (a, b)
     for x, y in zip(read_weights(f"{d}/w2"), read_weights(f"{d}/w1")):
         assert _close_ln(x, y, 1e-8), (x, y)
+
+
+# ---- forest-em --crp (row a24): Gibbs sampling over forests ---------------------------------------------------------
+GIBBS_VARIANTS = [
+    ["--crp=6"],
+    ["--crp=8", "--burnin=3"],
+    ["--crp=5", "--final-counts"],
+    ["--crp=6", "--burnin=2", "--crp-exclude-prior"],
+    ["--crp=5", "--uniform-p0", "--const-alpha=0.5"],
+    ["--crp=6", "--high-temp=3", "--low-temp=0.5"],
+    ["--crp=4", "--sample-prob", "--const-alpha=2"],
+]
+
+
+@pytest.mark.parametrize("variant", range(len(GIBBS_VARIANTS)))
+def test_forest_gibbs_sequential_is_sample_identical(fem, forest_oracle_bin, tmp_path, variant):
+    """same uniforms u(seed, sweep, forest, draw) => the same derivation for every forest in every sweep, the same
+    per-sweep probabilities and the same final (time-averaged) weights as the CPU restatement (forest.hpp:726-816,
+    forest-em.hpp:694-797, gibbs.hpp:803-877)"""
+    rng = np.random.default_rng(20262020 + variant)
+    d = str(tmp_path)
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules=40, depth=5, share=0.25) for _ in range(70)) + "\n")
+    # (variant 0 leaves some rules out of every group: fixed zero probabilities, cache-model prob = 2^-inf on both sides)
+    open(f"{d}/n", "w").write(random_normgroups(rng, 40, leave_out=0.1 if variant == 0 else 0.0))
+    args = ["-U", "-f", f"{d}/f", "-n", f"{d}/n", "--seed=5", *GIBBS_VARIANTS[variant]]
+    rc, _, oerr = run(forest_oracle_bin, [*args, f"--outsample-file={d}/o.s", "-o", f"{d}/o.w", f"--history={d}/o.h"])
+    assert rc == 0, oerr
+    rc, _, err = run(fem, [*args, f"--outsample-file={d}/p.s", "-o", f"{d}/p.w", f"--history={d}/p.h"])
+    assert rc == 0, err
+    assert open(f"{d}/p.s").read() == open(f"{d}/o.s").read()
+    ho = [float(ln.split()[1]) for ln in open(f"{d}/o.h") if ln.strip()]
+    hp = [float(ln.split()[1]) for ln in open(f"{d}/p.h") if ln.strip()]
+    assert len(ho) == len(hp) and len(ho) >= 5
+    for a, b in zip(hp, ho):
+        assert a == b or abs(a - b) <= 1e-9 * max(1.0, abs(b)), (a, b)
+    for x, y in zip(read_weights(f"{d}/p.w"), read_weights(f"{d}/o.w")):
+        assert _close_ln(x, y, 1e-8, floor=-600.0), (x, y)
+    assert [ln for ln in err.splitlines() if ln.startswith("Gibbs i=")] == [ln for ln in oerr.splitlines() if ln.startswith("Gibbs i=")]
+
+
+def test_forest_gibbs_converges_to_the_posterior(fem, tmp_path):
+    """one forest with two derivations, rule 1 or rule 2, in one group: the sampler is a Polya urn with prior alpha*p0*N
+    = 0.5 each and 200 copies of the forest; the time-averaged weight of rule 1 must sit near 1/2, and every sampled
+    derivation is one of the two (sanity of the cache / count bookkeeping, no oracle involved)"""
+    d = str(tmp_path)
+    open(f"{d}/f", "w").write("(OR 1 2)\n" * 200)
+    open(f"{d}/n", "w").write("((1 2))\n")
+    rc, _, err = run(fem, ["-U", "-f", f"{d}/f", "-n", f"{d}/n", "--crp=400", "--burnin=100", "--const-alpha=0.5", "--seed=9",
+                           f"--outsample-file={d}/s", "-o", f"{d}/w"], timeout=600)
+    assert rc == 0, err
+    w = read_weights(f"{d}/w")
+    p1 = math.exp(w[0])
+    assert abs(p1 + math.exp(w[1]) - 1) < 1e-9
+    assert 0.2 < p1 < 0.8, p1  # (the urn's limit is Beta(0.5, 0.5)-ish per run; the time average pulls it inside)
+    assert set(open(f"{d}/s").read().split()) <= {"1", "2"}
+
+
+def test_forest_gibbs_batched_level(fem, forest_oracle_bin, tmp_path):
+    """--crp-batched (every forest against the previous sweep's counts): not the oracle's derivations; its cache-model
+    probability settles at the sequential sampler's level"""
+    rng = np.random.default_rng(20262121)
+    d = str(tmp_path)
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules=30, depth=4) for _ in range(400)) + "\n")
+    open(f"{d}/n", "w").write(random_normgroups(rng, 30, leave_out=0.0))
+    args = ["-U", "-f", f"{d}/f", "-n", f"{d}/n", "--seed=5", "--crp=60", "--burnin=30"]
+    out = {}
+    for name, extra in (("seq", []), ("bat", ["--crp-batched"])):
+        rc, _, err = run(fem, [*args, *extra, f"--history={d}/h.{name}"], timeout=600)
+        assert rc == 0, err
+        h = [float(ln.split()[1]) for ln in open(f"{d}/h.{name}") if ln.strip()]
+        out[name] = sum(h[-20:]) / 20
+    assert abs(out["seq"] - out["bat"]) <= 0.03 * abs(out["seq"]), out

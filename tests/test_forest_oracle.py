@@ -95,3 +95,25 @@ def test_cipher_cross_program_identity(oracle_bin, forest_oracle_bin, tmp_path):
     for (it, log2p), h in zip(want, hist):
         got = float(h[1]) * n / math.log(2)
         assert int(h[0]) == it and abs(got - log2p) <= 1.01e-5 * abs(log2p), (it, got, log2p)
+
+
+def test_forest_gibbs_oracle_sanity(forest_oracle_bin, tmp_path):
+    """forest-em --crp restatement (forest.hpp:726-816, forest-em.hpp:694-797): PARITY UNPINNED by the reference (no
+    expected outputs, boost RNG) -- pinned to first principles instead: (i) every sampled derivation is a derivation of
+    its forest, (ii) with a deterministic forest the sample is that derivation and its rules take all the mass,
+    (iii) the counts bookkeeping: after the run the weights of every group sum to one."""
+    import math
+    from forest_helpers import read_weights
+    d = str(tmp_path)
+    open(f"{d}/f", "w").write("(OR (1 3) (2 3))\n" * 50 + "(4 3)\n" * 10)
+    open(f"{d}/n", "w").write("((1 2) (3) (4 5))\n")
+    rc, _, err = run(forest_oracle_bin, ["-U", "-f", f"{d}/f", "-n", f"{d}/n", "--crp=40", "--burnin=10", "--seed=3",
+                                         f"--outsample-file={d}/s", "-o", f"{d}/w"])
+    assert rc == 0, err
+    lines = open(f"{d}/s").read().splitlines()
+    assert len(lines) == 60
+    assert all(ln in ("1 3", "2 3") for ln in lines[:50]) and all(ln == "4 3" for ln in lines[50:])
+    w = [math.exp(x) for x in read_weights(f"{d}/w")]
+    assert abs(w[0] + w[1] - 1) < 1e-9 and abs(w[2] - 1) < 1e-9 and abs(w[3] + w[4] - 1) < 1e-9
+    assert w[3] > 0.95  # rule 4 is used by 10 forests, rule 5 by none: alpha * p0 * N = 0.1 pseudo-counts against 10
+    assert err.count("Gibbs i=") == 41
