@@ -382,6 +382,115 @@ __global__ void __launch_bounds__(kGibbsSeqThreads) k_gibbs_sequential(GibbsArgs
 }
 
 
+// --expectation (gibbs.cc:311-316, derivations.h:381-398 collect_counts_gibbs): a block's "sample" is every arc of its
+// lattice with its posterior under the current proposal probabilities (incremental EM over the CRP counts).  One CTA
+// walks the blocks in corpus order: the block's previous posteriors leave the counts, the lattice arcs get their
+// proposal weights from the counts, forward / backward in log space (online log-sum-exp in stored arc order), the new
+// posteriors enter the counts.  post[] holds one double per lattice arc (out-arc order), old and new generation.
+struct ExpectArgs {
+  const uint32_t* in_off;
+  const uint2* in_arc;      // {src layered index, internal arc id}, destination-major
+  double* alpha;            // scratch: one double per lattice state (same bases as beta)
+  const double* old_post;
+  double* new_post;
+  double* blk_lnp;          // [n_ex] ln P(block) = sum over all derivations
+};
+__global__ void __launch_bounds__(kGibbsSeqThreads) k_gibbs_expectation(GibbsArgs A, ExpectArgs X) {
+  const double NI = -CUDART_INF;
+  const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+  for (uint32_t e = 0; e < A.n_ex; ++e) {
+    const CmlExDesc d = A.desc[e];
+    const uint32_t* __restrict__ lvl = A.lvl_off + d.lvl_base;
+    const uint32_t* __restrict__ ooff = A.out_off + d.row_base;
+    const uint32_t* __restrict__ ioff = X.in_off + d.row_base;
+    const uint2* __restrict__ oarc = A.out_arc + d.arc_base;
+    const uint2* __restrict__ iarc = X.in_arc + d.arc_base;
+    const double* __restrict__ po = X.old_post + d.arc_base;
+    double* __restrict__ pn = X.new_post + d.arc_base;
+    double* be = A.beta + A.beta_base[e];
+    double* al = X.alpha + A.beta_base[e];
+    const uint32_t n_arcs = ooff[d.n_states];
+    const double wt = d.weight;
+    auto for_params = [&](uint32_t internal, double dlt) {  // addc with block_delta weights (gibbs.hpp:779-786)
+      const uint32_t a = A.arc_orig[internal];
+      const uint32_t k0 = A.chain_off ? A.chain_off[a] : a, k1 = A.chain_off ? A.chain_off[a + 1] : a + 1;
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t p = A.chain_off ? A.chain_param[k] : k;
+        const uint32_t g = A.param_norm[p];
+        if (g == CML_NO_GROUP) continue;
+        atomicAdd(&A.count[p], dlt);
+        atomicAdd(&A.normsum[g], dlt);
+      }
+    };
+    // (1) the block's previous posteriors leave the counts
+    for (uint32_t k = tid; k < n_arcs; k += nt) {
+      const double v = po[k];
+      if (v != 0.) for_params(oarc[k].y, -wt * v);
+    }
+    __syncthreads();
+    // (2) proposal weight of every lattice arc from the counts as they are now (fixed for the whole block)
+    for (uint32_t k = tid; k < n_arcs; k += nt) pn[k] = arc_lnprob(A, oarc[k].y);
+    __syncthreads();
+    // (3) backward, levels descending: a thread per state, arcs in stored order
+    for (int L = (int)d.n_levels - 1; L >= 0; --L) {
+      for (uint32_t s = lvl[L] + tid; s < lvl[L + 1]; s += nt) {
+        double m = NI, acc = 0;
+        if (s == d.fin) {
+          m = 0;
+          acc = 1;
+        }
+        for (uint32_t k = ooff[s], ke = ooff[s + 1]; k < ke; ++k) {
+          const double v = pn[k] + be[oarc[k].x];
+          if (v > m) {
+            acc = acc * exp(m - v) + 1.;
+            m = v;
+          } else if (v > NI)
+            acc += exp(v - m);
+        }
+        be[s] = (m > NI) ? m + log(acc) : NI;
+      }
+      __syncthreads();
+    }
+    // (4) forward, levels ascending, over the incoming arcs; the weight of in-arc j is looked up through its arc id
+    for (uint32_t L = 0; L < d.n_levels; ++L) {
+      for (uint32_t s = lvl[L] + tid; s < lvl[L + 1]; s += nt) {
+        double m = NI, acc = 0;
+        if (s == 0) {
+          m = 0;
+          acc = 1;
+        }
+        for (uint32_t k = ioff[s], ke = ioff[s + 1]; k < ke; ++k) {
+          const uint2 r = iarc[k];
+          const double v = arc_lnprob(A, r.y) + al[r.x];
+          if (v > m) {
+            acc = acc * exp(m - v) + 1.;
+            m = v;
+          } else if (v > NI)
+            acc += exp(v - m);
+        }
+        al[s] = (m > NI) ? m + log(acc) : NI;
+      }
+      __syncthreads();
+    }
+    const double lnP = al[d.fin];
+    if (tid == 0) X.blk_lnp[e] = lnP;
+    // (5) posteriors (count updates only after every thread has read the counts it needs: steps 2 and 4 are done)
+    for (uint32_t s = tid; s < d.n_states; s += nt) {
+      const double a_s = al[s];
+      for (uint32_t k = ooff[s], ke = ooff[s + 1]; k < ke; ++k) {
+        const double v = pn[k] + a_s + be[oarc[k].x] - lnP;
+        pn[k] = (lnP > NI && v > NI) ? exp(v) : 0.;
+      }
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < n_arcs; k += nt) {
+      const double v = pn[k];
+      if (v != 0.) for_params(oarc[k].y, wt * v);
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Dense-state batched sampler (cml_gibbs_attach_dense): position-synchronous lattices are never walked.
 // One warp per block, lane = WFST state.  Backward filter in scaled linear space: beta_t[i] = sum_j W[o_t][j][i] *
@@ -641,7 +750,7 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
   A.seed = o->seed;
   A.sweep = o->sweep;
   A.sequential = o->mode == CML_GIBBS_SEQUENTIAL;
-  const bool table = o->init_from_params || !A.sequential;
+  const bool table = (o->init_from_params || !A.sequential) && o->mode != CML_GIBBS_EXPECTATION;
   if (table) {  // per-arc ln probabilities as a table: from the EM weights, or from the frozen counts
     const double* lnp = ctx->ln_w.p;
     if (!o->init_from_params) {
@@ -663,7 +772,28 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
     ++ctx->launches;
     A.arc_lnw = (const double*)ctx->arc_w_real.p;
   }
-  if (A.sequential) {
+  if (o->mode == CML_GIBBS_EXPECTATION) {
+    CML_REQUIRE(!o->init_from_params, CML_ERR_ARG, "--expectation has no separate initial distribution (gibbs.cc:311-313)");
+    const size_t na = std::max<uint64_t>(1, bt.n_arcs), ns = std::max<uint64_t>(1, bt.n_states);
+    if (ctx->g_post[0].n < na) {
+      for (int k = 0; k < 2; ++k) {
+        CML_CUDA(ctx->g_post[k].alloc(na));
+        CML_CUDA(cudaMemsetAsync(ctx->g_post[k].p, 0, na * sizeof(double), s));
+      }
+      CML_CUDA(ctx->g_alpha.alloc(ns));
+      CML_CUDA(ctx->g_blk_lnp.alloc(std::max<uint64_t>(1, bt.n_ex)));
+    }
+    A.arc_lnw = nullptr;  // proposal weights straight from the counts (they change between blocks)
+    ExpectArgs X;
+    X.in_off = bt.in_off.p;
+    X.in_arc = bt.in_arc.p;
+    X.alpha = ctx->g_alpha.p;
+    X.old_post = ctx->g_post[ctx->g_cur].p;
+    X.new_post = ctx->g_post[ctx->g_cur ^ 1].p;
+    X.blk_lnp = ctx->g_blk_lnp.p;
+    k_gibbs_expectation<<<1, kGibbsSeqThreads, 0, s>>>(A, X);
+    ++ctx->launches;
+  } else if (A.sequential) {
     if (ctx->g_tbl.n < (size_t)ctx->n_arcs + 1) CML_CUDA(ctx->g_tbl.alloc((size_t)ctx->n_arcs + 1));
     k_gibbs_sequential<<<1, kGibbsSeqThreads, 0, s>>>(A, ctx->g_tbl.p, ctx->n_arcs);
     ++ctx->launches;
@@ -699,6 +829,16 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
   return CML_OK;
 }
 
+
+// --expectation: ln P(block) (sum over all derivations) of every block in the last sweep
+extern "C" int cml_gibbs_get_block_logprob(cml_ctx* ctx, double* ln_p, uint64_t n) {
+  if (!ctx || !ln_p) return CML_ERR_ARG;
+  CML_REQUIRE(ctx->have_gibbs && ctx->g_blk_lnp.p && n <= ctx->g_blk_lnp.n, CML_ERR_STATE, "no --expectation sweep has run");
+  cudaSetDevice(ctx->device);
+  CML_CUDA(cudaMemcpyAsync(ln_p, ctx->g_blk_lnp.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CML_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CML_OK;
+}
 
 extern "C" int cml_gibbs_attach_dense(cml_ctx* ctx, const cml_dense_view* v, const cml_sequence_batch* b) {
   if (!ctx || !v || !b) return CML_ERR_ARG;

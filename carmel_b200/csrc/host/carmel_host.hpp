@@ -187,6 +187,7 @@ struct GibbsOpts {
   double high_temp = 1, low_temp = 1;  // --high-temp= --low-temp=
   uint64_t seed = 1;                 // --seed= : key of the counter-based uniforms
   bool batched = false;              // --crp-batched : all blocks in parallel against the previous sweep's counts
+  bool expectation = false;          // --expectation (gibbs.cc:311-316): blocks carry posteriors of all their arcs (incremental EM)
   bool sample_prob = false;          // --sample-prob (carmel.cc:1869): log the proposal probability of each new sample given
                                      // the counts without its block (gibbs.hpp:866 with cache_prob off) instead of the cache
                                      // model's -- the quantity in the golden log commands.trace:6976-12996

@@ -199,13 +199,26 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
     if (g.iter > 0 && g.high_temp != g.low_temp)
       temperature = g.high_temp + (g.low_temp - g.high_temp) * std::min(1.0, (double)it / g.iter);
     cml_gibbs_sweep_opts so{};
-    so.mode = g.batched ? CML_GIBBS_BATCHED : CML_GIBBS_SEQUENTIAL;
+    so.mode = g.expectation ? CML_GIBBS_EXPECTATION : g.batched ? CML_GIBBS_BATCHED : CML_GIBBS_SEQUENTIAL;
     so.power = temperature > 0 ? 1. / temperature : 1.;
     so.seed = g.seed;
     so.sweep = it;
     so.init_from_params = 0;
     so.accumulate_dt = it == g.iter ? 1. : time_of(it + 1) - time_of(it);
     ok(cml_gibbs_sweep(ctx, &so));
+    if (g.expectation) {  // record_iteration with probname "sum-all-derivations" (gibbs.hpp:930-945)
+      std::vector<double> blk(res.examples);
+      ok(cml_gibbs_get_block_logprob(ctx, blk.data(), blk.size()));
+      double ln_p = 0;
+      for (double v : blk) ln_p += v;
+      res.history.push_back({it, ln_p, ln_p, 0});
+      if (!opt.quiet) {
+        log << "Gibbs i=" << it << " sum-all-derivations prob=" << format_base2(ln_p);
+        if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << format_base2(-ln_p / n_sym);
+        log << " per-block-ppx(N=" << res.examples << ")=" << format_base2(-ln_p / (double)res.examples) << "\n";
+      }
+      continue;
+    }
     ok(cml_gibbs_get_samples(ctx, path_len.data(), path_arcs.data(), cap));
     // cache-model probability of the sweep's sample (gibbs.hpp:137-140,700-742)
     std::fill(csum.begin(), csum.end(), 0.);

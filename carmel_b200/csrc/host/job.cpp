@@ -83,7 +83,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   if (crp) {
     // Options of carmel's sampler (carmel.cc:268-302) that change what is sampled and that this path does not
     // build: refuse them instead of training something else under the same command line.
-    static const char* const not_built[] = {"expectation", "random-start", "include-self", "crp-restarts",
+    static const char* const not_built[] = {"random-start", "include-self", "crp-restarts",
                                             "crp-argmax-final", "crp-argmax-sum", "init-em", "em-p0",
                                             "init-from-p0", "prior-inference-stddev", "prior-inference-global",
                                             "prior-inference-restart-fresh"};
@@ -105,6 +105,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
     if (lopt.count("seed")) g.seed = std::strtoull(lopt["seed"].c_str(), nullptr, 10);
     g.batched = lopt.count("crp-batched") > 0;
     g.sample_prob = lopt.count("sample-prob") > 0;
+    g.expectation = lopt.count("expectation") > 0;
     if (lopt.count("dump-samples")) g.dump_samples_file = lopt["dump-samples"];
   }
   if (!flags[(unsigned)'t']) {

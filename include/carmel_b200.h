@@ -270,7 +270,9 @@ typedef struct cml_gibbs_model {
 } cml_gibbs_model;
 enum cml_gibbs_mode {
   CML_GIBBS_SEQUENTIAL = 0, /* exact collapsed sampler: blocks in corpus order, counts updated between blocks */
-  CML_GIBBS_BATCHED = 1     /* all blocks in parallel against the previous sweep's counts */
+  CML_GIBBS_BATCHED = 1,    /* all blocks in parallel against the previous sweep's counts */
+  CML_GIBBS_EXPECTATION = 2 /* --expectation (gibbs.cc:311-316, derivations.h:381-398): blocks in corpus order, a block's
+                               "sample" is every arc of its lattice weighted by its posterior under the current counts */
 };
 typedef struct cml_gibbs_sweep_opts {
   int mode;
@@ -295,6 +297,8 @@ uint64_t cml_gibbs_sample_capacity(cml_ctx* ctx);
  * base_e = sum of the lattice level counts of the examples before e */
 int cml_gibbs_get_samples(cml_ctx* ctx, uint32_t* path_len, uint32_t* path_arcs, uint64_t cap);
 int cml_gibbs_get_state(cml_ctx* ctx, double* count, double* cum, double* normsum);
+/* CML_GIBBS_EXPECTATION: ln P(block) (sum over all its derivations, derivations.h:386) of the n first blocks, last sweep */
+int cml_gibbs_get_block_logprob(cml_ctx* ctx, double* ln_p, uint64_t n);
 
 /* ---- collective: the per-iteration all-reduce of the count table (north_star (4)) -------------- *
  * The reference is single process; the sharded E-step relies on "examples are independent given the weights"

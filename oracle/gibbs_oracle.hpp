@@ -69,6 +69,9 @@ struct GibbsOpts {
   // new sample under the current counts, which is what the older binary behind the golden log
   // carmel-tutorial/commands.trace:6976-12996 printed by default ("sample prob=").
   bool sample_prob = false;
+  // --expectation (gibbs_opts.hpp; gibbs.cc:311-316, derivations.h:381-398 collect_counts_gibbs): a block's "sample" is
+  // every lattice arc with its posterior under the current proposal probabilities -- incremental EM over the CRP counts
+  bool expectation = false;
 };
 
 struct Gibbs {
@@ -83,6 +86,7 @@ struct Gibbs {
   std::vector<std::vector<unsigned>> chain_of_arc;  // arc-table id -> param ids (chain order)
   std::vector<std::vector<unsigned>> sample;        // per block: param ids in path order
   std::vector<std::vector<unsigned>> sample_arcs;   // per block: arc-table ids of the sampled path
+  std::vector<std::vector<double>> sample_wt;       // --expectation: weight of every entry of sample[b] (block_delta::wt)
   std::vector<Arc*> arc_of_param;
   std::vector<double> init_arc_weight;  // composed arc weights for the iteration-0 sample (--init-em)
   bool init_prob = false;
@@ -171,10 +175,42 @@ struct Gibbs {
       for (Arc* a : chain_arcs[i]) chain_of_arc[i].push_back(a->group);
     sample.assign(derivs.size(), {});
     sample_arcs.assign(derivs.size(), {});
+    sample_wt.assign(derivs.size(), {});
   }
   double proposal_prob(unsigned id) const {
     GibbsParam const& p = gps[id];
     return p.has_norm() ? p.sumcount.x / normsum[p.norm] : p.prior;
+  }
+  void addc_weighted(std::vector<unsigned> const& b, std::vector<double> const& w, double d) {  // gibbs.hpp:779-786
+    for (size_t i = 0; i < b.size(); ++i) {
+      GibbsParam& p = gps[b[i]];
+      if (p.has_norm()) {
+        normsum[p.norm] += w[i] * d;
+        p.sumcount.add_delta(w[i] * d, time);
+      }
+    }
+  }
+  // derivations.h:381-398 collect_counts_gibbs: forward-backward with the proposal weights; every arc's posterior goes
+  // to every parameter of its chain.  Returns the block probability (sum over all derivations).
+  W expectation_block(unsigned b) {
+    Derivations& d = derivs[b];
+    auto wt = [&](GraphArc const& a) {
+      W prob = W::one();
+      for (unsigned id : chain_of_arc[a.id]) prob *= W(proposal_prob(id));
+      return prob;
+    };
+    std::vector<W> f, bw;
+    W prob = d.compute_fb(f, bw, wt);
+    for (unsigned s = 0; s < d.g.size(); ++s)
+      for (GraphArc const& a : d.g[s]) {
+        W contrib = wt(a) * f[a.src] * bw[a.dest];
+        const double w = (contrib / prob).getReal();
+        for (unsigned id : chain_of_arc[a.id]) {
+          sample[b].push_back(id);
+          sample_wt[b].push_back(w);
+        }
+      }
+    return prob;
   }
   void addc(std::vector<unsigned> const& b, double d) {
     for (unsigned id : b) {
@@ -251,6 +287,14 @@ struct Gibbs {
     if (iter > 0) init_prob = false;
     for (unsigned b = 0; b < derivs.size(); ++b) {
       double wt = derivs[b].weight;
+      if (gopt.expectation) {  // gibbs.hpp:851-871 with block_delta weights
+        addc_weighted(sample[b], sample_wt[b], -wt);
+        sample[b].clear();
+        sample_wt[b].clear();
+        p *= expectation_block(b);
+        addc_weighted(sample[b], sample_wt[b], wt);
+        continue;
+      }
       addc(sample[b], -wt);
       sample[b].clear();
       sample_arcs[b].clear();
@@ -272,7 +316,8 @@ struct Gibbs {
       addc(sample[b], wt);
     }
     iter_ln_prob.push_back(p.w);
-    log << "Gibbs i=" << iter << (gopt.sample_prob ? " sample prob=" : " cache-model prob=") << fmt_base2(p);
+    log << "Gibbs i=" << iter << (gopt.expectation ? " sum-all-derivations prob=" : gopt.sample_prob ? " sample prob=" : " cache-model prob=")
+        << fmt_base2(p);
     if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << fmt_base2(p.ppxper(n_sym));
     log << " per-block-ppx(N=" << derivs.size() << ")=" << fmt_base2(p.ppxper((double)derivs.size())) << "\n";
   }
@@ -337,6 +382,7 @@ inline int gibbs_main(WFST& result, Cascade& cascade, Corpus& corpus, std::vecto
   if (lopt.count("crp-exclude-prior")) g.exclude_prior = true;
   if (lopt.count("high-temp")) g.high_temp = atof(lopt["high-temp"].c_str());
   g.sample_prob = lopt.count("sample-prob") > 0;
+  g.expectation = lopt.count("expectation") > 0;
   if (lopt.count("low-temp")) g.low_temp = atof(lopt["low-temp"].c_str());
   if (lopt.count("seed")) g.seed = strtoull(lopt["seed"].c_str(), nullptr, 10);
   if (g.final_counts) g.burnin = g.iter;

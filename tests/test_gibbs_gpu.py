@@ -190,3 +190,40 @@ def test_dense_state_sampler_draws_from_the_lattice_samplers_distribution(native
     assert chi2 <= len(keys) + 6 * math.sqrt(2 * len(keys)), (chi2, len(keys))
     # and the derivations themselves are the same set (no derivation one sampler can draw and the other cannot)
     assert {k for k in hd if hd[k] >= 40} == {k for k in hl if hl[k] >= 40}
+
+
+# ---- --expectation (row a18): blocks carry the posteriors of all their arcs (incremental EM over the CRP counts) -----
+def _expect_both(cli, oracle_bin, tmp_path, args, files, trained):
+    rc, out, err = run(cli, [*args, "--expectation", f"--history={tmp_path}/h.p", *files])
+    assert rc == 0, err
+    got = [open(f + ".trained").read() for f in trained]
+    rc, oout, oerr = run(oracle_bin, [*args, "--expectation", f"--history={tmp_path}/h.o", *files])
+    assert rc == 0, oerr
+    want = [open(f + ".trained").read() for f in trained]
+    hp, ho = _hist(f"{tmp_path}/h.p"), _hist(f"{tmp_path}/h.o")
+    assert len(hp) == len(ho) >= 4
+    for (i, a), (j, b) in zip(hp, ho):
+        assert i == j and abs(a - b) <= 1e-9 * max(1.0, abs(b)), (i, a, b)
+    assert hp[-1][1] > hp[0][1]  # the likelihood of the corpus improves from sweep to sweep
+    for g, w in zip(got, want):
+        compare_wfst_text(g, w, 1e-6)
+    assert "sum-all-derivations prob=" in err
+    return err
+
+
+@pytest.mark.parametrize("extra", [[], ["--burnin=2"], ["--final-counts"], ["--uniform-p0"]])
+def test_cipher_crp_expectation(cli, oracle_bin, tmp_path, extra):
+    """gibbs.cc:311-316 + derivations.h:381-398 (collect_counts_gibbs): per-sweep sum-all-derivations probability and the
+    final weights against the CPU restatement (no random numbers are involved: the comparison is exact up to rounding)"""
+    data, wfsa, fst = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    _expect_both(cli, oracle_bin, tmp_path, ["--crp", "-M", "6", "--priors=0,1e-2", "-HJ", *extra], [data, wfsa, fst], [wfsa, fst])
+
+
+def test_epron_crp_expectation(cli, oracle_bin, tmp_path):
+    fst, data = stage(tmp_path, "epron-jpron.fst", "epron-jpron.data")
+    _expect_both(cli, oracle_bin, tmp_path, ["--crp", "-M", "6", "--priors=0.05"], [data, fst], [fst])
+
+
+def test_tagging_crp_expectation(cli, oracle_bin, tmp_path):
+    data, fsa, fst = stage(tmp_path, "tagging.data", "tagging.fsa", "tagging.fst")
+    _expect_both(cli, oracle_bin, tmp_path, ["--crp=4", "--burnin=1", "--priors=0.1,0.01", "-HJ"], [data, fsa, fst], [fsa, fst])
