@@ -34,8 +34,14 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   for (int i = 1; i < argc; ++i) {
     const std::string arg = argv[i];
     if (!pending.empty()) {
-      const char p = pending.front();
-      pending.erase(pending.begin());
+      // carmel binds pending value flags by a FIXED priority chain, not in the order they were written
+      // (carmel.cc:930-990: = N X o ! R w z k g M L T e f p F +); 'G' shares -g's argument (carmel.cc:1043)
+      static const char kPriority[] = "=NXo!RwzkgMLTefpF+";
+      size_t best = 0;
+      for (size_t q = 1; q < pending.size(); ++q)
+        if (std::strchr(kPriority, pending[q]) < std::strchr(kPriority, pending[best])) best = q;
+      const char p = pending[best];
+      pending.erase(pending.begin() + best);
       double w = 0;
       switch (p) {
         case 'M': topt.max_iter = (uint32_t)std::atol(arg.c_str()); break;
@@ -68,6 +74,7 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
           const char c = arg[k];
           flags[(unsigned char)c] = true;
           if (std::strchr("MeXfoFR!kTpwzgLN=+", c)) pending.push_back(c);
+          if (c == 'G') pending.push_back('g');
           if (c == 'j') default_group = JOINT;
           if (c == 'u') default_group = NONE;
         }
@@ -75,6 +82,13 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
     } else
       files.push_back(arg);
   }
+  // flags that change WHAT is computed and that this path does not build are refused, not ignored:
+  // -r (right-to-left composition), -a (mediate-state composition: different composed arc ids), -+ (digamma)
+  for (const char c : {'r', 'a', '+'})
+    if (flags[(unsigned char)c]) {
+      err << "carmel-b200: -" << c << " is not implemented on the training path\n";
+      return -11;
+    }
   // --crp forces -t and --train-cascade (carmel.cc:255-304 parse_gibbs_opts)
   const bool crp = lopt.count("crp") > 0;
   const bool trainc = lopt.count("train-cascade") > 0 || crp;

@@ -85,7 +85,7 @@ def test_random_cascades_bit_exact(oracle_bin, cli, tmp_path, seed):
     assert filecmp.cmp(f"{tmp_path}/o", f"{tmp_path}/p", shallow=False)
 
 
-@pytest.mark.parametrize("opt", ["--expectation", "--random-start", "--crp-restarts=2", "--init-em=3",
+@pytest.mark.parametrize("opt", ["--random-start", "--crp-restarts=2", "--init-em=3",
                                  "--crp-argmax-final", "--prior-inference-stddev=0.1"])
 def test_unbuilt_sampler_options_are_refused(cli, tmp_path, opt):
     """Sampler options of the reference (carmel.cc:268-302) that change what is sampled and that this
