@@ -49,11 +49,17 @@ CIPHER_LINES, CIPHER_SAMPLE = 2000, 160
 C3_SENTENCES, C3_SAMPLE = 1000000, 16000
 
 
-def measured_traffic(kernel):
-    """dram bytes per launch of a kernel from the committed ncu captures (profiles/traffic.json), or None"""
+def measured_traffic(kernel, units=None):
+    """dram bytes per launch of a kernel from the committed ncu captures (profiles/traffic.json), or None.  The capture
+    names the units (arcs / positions / hyperedges) its launch processed: a launch over `units` units is charged
+    bytes / captured units x units (same workload family at another size)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
-        return float(t["bytes"]) if t else None  # bytes per launch (source file named in profiles/traffic.json)
+        if not t:
+            return None
+        if units and t.get("units"):
+            return float(t["bytes"]) / float(t["units"]) * float(units)
+        return float(t["bytes"])
     except Exception:
         return None
 
@@ -488,7 +494,7 @@ def main():
                 lattice_bytes = (16.0 + 2.0 * rs * (states_local / max(1, arcs_local))) * arcs_local
                 res["roofline"] = {
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": measured_traffic("k_fb_sparse") if traffic_key else None, "peak_source": which,
+                    "traffic": measured_traffic("k_fb_sparse", dense["positions"]) if traffic_key else None, "peak_source": which,
                     "kernel": "k_fb_sparse (forward + backward + counts, one sequence per lane, lattices never "
                               "materialised; 1 launch per iteration)",
                     "kernel_ms": k_ms, "algorithmic_bytes_per_position": bytes_pos,
@@ -509,7 +515,7 @@ def main():
                 hbm_bytes = dense["positions"] * (2.0 * 32 * rs + 8 + 2 + 2)  # alpha row written + read, exponents, symbol twice
                 res["roofline"] = {
                     "bound": "tensor", "achieved": ach, "peak": tf32["value"], "unit": "TFLOP/s", "frac": ach / tf32["value"],
-                    "traffic": measured_traffic("k_fb_dense") if traffic_key else None,
+                    "traffic": measured_traffic("k_fb_dense", dense["positions"]) if traffic_key else None,
                     "peak_source": "TF32 GEMM rate measured in this run (torch.matmul 8192^3, allow_tf32, best of 5)",
                     "kernel": ("k_dense_tc<fwd> + k_dense_tc<bwd> + k_dense_tc_counts (3xTF32 mma.sync sweeps, 16 sequences per "
                                "warp; 3 launches per iteration)" if dense["kernel"] == "dense_tc" else
@@ -530,7 +536,7 @@ def main():
                 lay = {**ctx.layout_stats(), **ctx.lane_stats(), **ctx.wide_stats()}
                 kname = ("k_fb_wide (warp per lattice, bulk-copy record stream, factored weights in shared memory)"
                          if lay["wide_examples"] else "k_fb_lane (lattice per lane, tiles of 32)" if lay["lane_examples"] else "k_fb_ell / k_fb_warp")
-                traffic = measured_traffic(traffic_key) if traffic_key else None
+                traffic = measured_traffic(traffic_key, arcs_local) if traffic_key else None
                 res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                                    "frac": achieved / hbm_peak, "traffic": traffic,
                                    "traffic_over_algorithmic": (traffic / (bytes_per_arc * arcs_local)) if traffic else None,
