@@ -137,6 +137,8 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
     fs = synth.make_forests(n_forests=100000 * a.scale, n_rules=1000000, seed=20260105, templates=0, part=(rank, world))
     stream = torch.cuda.Stream()
     F = Forests(device=local, precision=a.precision)
+    if os.environ.get("CB200_FOREST_LAYOUT"):  # development runs: 1 group, 2 thread, 3 level (default: the library's choice)
+        F.set_layout(int(os.environ["CB200_FOREST_LAYOUT"]))
     F.set_stream(stream.cuda_stream)
     if world > 1:
         F.comm_init_rank(world, rank, token)
@@ -223,7 +225,7 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
         # algorithmic bytes of one E-step: per node label + child_off (inside) and label + par_off (outside), 4 B each;
         # per child/parent link one u32 in each pass; inside/posterior values stay in shared memory
         bytes_step = 16.0 * tot_local["nodes"] + 8.0 * tot_local["links"]
-        lay = F.layout_stats()
+        lay = {**F.layout_stats(), **F.level_stats()}
         if lay["tile_forests"]:
             # thread-per-forest tiles: one u32 word per node header and per link in each pass (rule ids ride in the
             # headers), inside[] and gamma[] written once (tree children / tree parents are read back from the
@@ -234,13 +236,16 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
         peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
         from bench import measured_traffic
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": measured_traffic("k_forest_thread") if lay["tile_forests"] and a.precision == 32 and a.scale == 1 else None,
-                    "peak_source": which, "kernel": ("k_forest_thread" if lay["tile_forests"] else "k_forest_warp/k_forest_cta") +
+                    "traffic": (measured_traffic("k_forest_level", tot_local["hyperedges"]) if lay["level_forests"] else
+                                measured_traffic("k_forest_thread", tot_local["hyperedges"]) if lay["tile_forests"] else None) if a.precision == 32 else None,
+                    "peak_source": which, "kernel": ("k_forest_level (CTA per run of forests, nodes height-major, values in shared memory, "
+                                                     "16 B/node + 2 B/link streamed per pass)" if lay["level_forests"] else
+                                                     "k_forest_thread" if lay["tile_forests"] else "k_forest_warp/k_forest_cta") +
                     f" (inside + outside + counts, {k_ms[0][1]} launch(es) per iteration)",
                     "kernel_ms": kms, "algorithmic_bytes_per_hyperedge": bytes_step / max(1, tot_local["hyperedges"]),
                     "hyperedges_per_launch_set": tot_local["hyperedges"], "kernel_share_of_step": kms / (ms / a.steps)}
         cpu = None
-        if with_cpu:
+        if with_cpu and not os.environ.get("CB200_NO_CPU"):  # (development runs skip the CPU baseline)
             try:
                 procs = max(1, os.cpu_count() or 1)
                 cpu = cpu_forest_oracle(fs, 100 * procs, procs, a.precision, budget_s=10.0 if as_leg else 15.0)

@@ -63,7 +63,8 @@ class CmlJobInfo(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("examples", "trellis_states", "trellis_arcs", "n_params", "n_arcs",
                                           "corpus_pairs", "iterations")] + [("ln_best_ppx", C.c_double),
                                                                             ("last_ln_prob", C.c_double),
-                                                                            ("dense", C.c_uint64)]
+                                                                            ("dense", C.c_uint64),
+                                                                            ("device_build_s", C.c_double)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)

@@ -474,6 +474,231 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Level-synchronous tiles (the throughput path for corpora of many small forests of ANY shape).
+//
+// A TILE is a run of consecutive forests whose nodes together fit in the CTA's shared memory (<= 32,768, 15-bit
+// local ids).  The nodes of a tile are stored height-major ACROSS its forests: level 0 = the leaves of every
+// forest of the tile, level 1 = ..., so one level is one contiguous slice of the arrays and the CTA's threads walk
+// it with unit stride: label u32 + child/parent CSR offset u32 per node and pass, 16-bit local ids per link.  One
+// value array lives in shared memory: after the inside pass it holds inside[node]; the outside pass visits the
+// levels downwards and REPLACES a node's slot by the message its children need: gamma[node] (linear) for an AND
+// node, ln gamma[node] - inside[node] for an OR node (a child of an OR parent adds exp(inside[child] + message)).
+// Every gather of a child / parent value is a shared-memory read; global memory sees only the coalesced streams,
+// read once per pass (DRAM traffic = the topology, no re-reads), and the rule weight / count tables (L2).
+// Thread 0 requests the slices of the level `pf` steps ahead into L2 with cp.async.bulk.prefetch (TMA unit), so
+// the dependent loads of a level (offsets, then links) pay L2 latency, not HBM latency; the per-thread loop keeps
+// the next node's header loads in flight while the current node is reduced.  No divergence beyond the arity loop:
+// lanes of a warp own consecutive nodes of the same level (k_forest_thread on an all-distinct corpus ran with 16
+// of 32 lanes active and 2.7x the algorithmic DRAM traffic: profiles/round2_A_k_forest_thread.txt).
+// ---------------------------------------------------------------------------------------------------
+const int kLvlThreads = 512;
+const uint32_t kLvlMaxLevels = 255, kLvlMaxNodes = 32768, kLvlOrParent = 0x8000u;
+const int kLvlU = 4, kLvlKids = 4, kLvlPars = 2;  // nodes in flight per thread; child / parent ids fetched ahead per node
+struct __align__(16) LevelTile {
+  uint64_t node_base;   // first entry of the tile in lt_label / lt_coff / lt_poff (n_nodes + 1 entries)
+  uint64_t link_base;   // first link of the tile in lt_child / lt_par
+  uint64_t lvl_base;    // 3 x (n_levels + 1) u32 in lt_lvl: node / child-link / parent-link offsets at the level boundaries
+  uint32_t n_nodes, n_levels, n_forests;
+  uint32_t forest_base; // first entry of the tile in lt_root / lt_forest
+};
+struct LevelArgs {
+  const LevelTile* tiles;
+  const uint32_t* label;
+  const uint32_t* coff;
+  const uint32_t* poff;
+  const uint16_t* child;
+  const uint16_t* par;
+  const uint32_t* lvl;
+  const uint16_t* root;     // local id of each forest's root
+  const uint32_t* forest;   // forest number within the batch (for ln_inside)
+  const void* lnw;
+  const uint32_t* hot_index;
+  double* counts;
+  double* hot;
+  uint32_t n_hot;
+  double* ln_inside;
+  int pf;                   // L2 prefetch distance in levels (0 = off)
+};
+__device__ __forceinline__ void f_prefetch_l2(const void* base, size_t b0, size_t b1) {  // bytes [b0, b1) behind base
+  const uintptr_t s = ((uintptr_t)base + b0) & ~(uintptr_t)15, e = ((uintptr_t)base + b1 + 15) & ~(uintptr_t)15;
+  if (e > s) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"((const void*)s), "r"((uint32_t)(e - s)) : "memory");
+}
+template <typename Real>
+__device__ __forceinline__ Real f_log(Real x);
+template <>
+__device__ __forceinline__ float f_log<float>(float x) { return logf(x); }
+template <>
+__device__ __forceinline__ double f_log<double>(double x) { return log(x); }
+
+template <typename Real>
+__global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_lv[];
+  __shared__ uint32_t s_lvl[3 * (kLvlMaxLevels + 1)];
+  Real* __restrict__ val = reinterpret_cast<Real*>(smem_lv);
+  const LevelTile T = A.tiles[blockIdx.x];
+  const uint32_t tid = threadIdx.x, NT = blockDim.x, nl = T.n_levels;
+  for (uint32_t k = tid; k < 3 * (nl + 1); k += NT) s_lvl[k] = __ldg(A.lvl + T.lvl_base + k);
+  const uint32_t* __restrict__ s_node = s_lvl;
+  const uint32_t* __restrict__ s_cl = s_lvl + (nl + 1);
+  const uint32_t* __restrict__ s_pl = s_lvl + 2 * (nl + 1);
+  const uint32_t* __restrict__ label = A.label + T.node_base;
+  const uint32_t* __restrict__ coff = A.coff + T.node_base;
+  const uint32_t* __restrict__ poff = A.poff + T.node_base;
+  const uint16_t* __restrict__ child = A.child + T.link_base;
+  const uint16_t* __restrict__ par = A.par + T.link_base;
+  const Real* __restrict__ lnw = (const Real*)A.lnw;
+  const Real NI = FNum<Real>::ninf();
+  const uint32_t pf = (uint32_t)A.pf;
+  __syncthreads();
+  auto prefetch_in = [&](uint32_t L) {
+    f_prefetch_l2(label, 4ull * s_node[L], 4ull * s_node[L + 1]);
+    f_prefetch_l2(coff, 4ull * s_node[L], 4ull * s_node[L + 1] + 4);
+    f_prefetch_l2(child, 2ull * s_cl[L], 2ull * s_cl[L + 1]);
+  };
+  auto prefetch_out = [&](uint32_t L) {
+    f_prefetch_l2(label, 4ull * s_node[L], 4ull * s_node[L + 1]);
+    f_prefetch_l2(poff, 4ull * s_node[L], 4ull * s_node[L + 1] + 4);
+    f_prefetch_l2(par, 2ull * s_pl[L], 2ull * s_pl[L + 1]);
+  };
+  // ---- inside: ascending height (forest.hpp:636-697).  A thread keeps kLvlU nodes of the level in flight: all their
+  // headers are loaded, then all their first kLvlKids child ids and rule weights, then they are reduced one by one --
+  // with one node per thread and iteration the kernel ran at the latency of its dependent loads times the resident
+  // threads (profiles/round2_B_k_forest_level.txt: 1.79 ms, DRAM 9 % busy, long-scoreboard + barrier stalls).
+  if (tid == 0 && pf)
+    for (uint32_t L = 0; L < pf && L < nl; ++L) prefetch_in(L);
+  for (uint32_t L = 0; L < nl; ++L) {
+    const uint32_t n1 = s_node[L + 1];
+    if (tid == 0 && pf && L + pf < nl) prefetch_in(L + pf);
+    if (L == 0) {  // height 0: leaves, inside = the rule weight
+      for (uint32_t j0 = s_node[0] + tid; j0 < n1; j0 += 2 * kLvlU * NT) {
+        uint32_t lab[2 * kLvlU];
+#pragma unroll
+        for (int k = 0; k < 2 * kLvlU; ++k) {
+          const uint32_t j = j0 + k * NT;
+          lab[k] = j < n1 ? (__ldg(label + j) & ~kHotBit) : 0u;
+        }
+        Real wv[2 * kLvlU];
+#pragma unroll
+        for (int k = 0; k < 2 * kLvlU; ++k) wv[k] = __ldg(lnw + lab[k]);
+#pragma unroll
+        for (int k = 0; k < 2 * kLvlU; ++k) {
+          const uint32_t j = j0 + k * NT;
+          if (j < n1) val[j] = wv[k];
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += kLvlU * NT) {
+      uint32_t lab[kLvlU], c0[kLvlU], c1[kLvlU];
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+        const uint32_t j = j0 + k * NT;
+        const bool ok = j < n1;
+        lab[k] = ok ? (__ldg(label + j) & ~kHotBit) : 0u;
+        c0[k] = ok ? __ldg(coff + j) : 0u;
+        c1[k] = ok ? __ldg(coff + j + 1) : 0u;
+      }
+      uint32_t ch[kLvlU][kLvlKids];
+      Real wv[kLvlU];
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+#pragma unroll
+        for (int q = 0; q < kLvlKids; ++q) ch[k][q] = (c0[k] + q < c1[k]) ? (uint32_t)__ldg(child + c0[k] + q) : 0u;
+        wv[k] = __ldg(lnw + lab[k]);  // (entry 0 exists: rule ids start at 1)
+      }
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+        const uint32_t j = j0 + k * NT;
+        if (j >= n1) continue;
+        const uint32_t nc = c1[k] - c0[k];
+        Real v;
+        if (lab[k]) {  // AND: rule weight times the children
+          v = wv[k];
+#pragma unroll
+          for (int q = 0; q < kLvlKids; ++q)
+            if ((uint32_t)q < nc) v += val[ch[k][q]];
+          for (uint32_t c = c0[k] + kLvlKids; c < c1[k]; ++c) v += val[__ldg(child + c)];
+        } else {       // OR: the first child, then the others folded in the reference's order
+          v = val[ch[k][0]];
+#pragma unroll
+          for (int q = 1; q < kLvlKids; ++q)
+            if ((uint32_t)q < nc) v = ln_add_fast<Real>(v, val[ch[k][q]]);
+          for (uint32_t c = c0[k] + kLvlKids; c < c1[k]; ++c) v = ln_add_fast<Real>(v, val[__ldg(child + c)]);
+        }
+        val[j] = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (uint32_t k = tid; k < T.n_forests; k += NT)
+    A.ln_inside[__ldg(A.forest + T.forest_base + k)] = (double)val[__ldg(A.root + T.forest_base + k)];
+  if (tid == 0 && pf)
+    for (uint32_t d = 0; d < pf && d < nl; ++d) prefetch_out(nl - 1 - d);
+  __syncthreads();
+  // ---- outside as posteriors, descending height, pull over the parents (forest.hpp:439-491); a root (no parents) of a
+  // zero-probability forest starts at 0, so that forest collects no counts (forest.hpp:447-451)
+  const uint32_t replica = blockIdx.x & (kHotCopies - 1);
+  for (uint32_t L = nl; L-- > 0;) {
+    const uint32_t n1 = s_node[L + 1];
+    if (tid == 0 && pf && L >= pf) prefetch_out(L - pf);
+    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += kLvlU * NT) {
+      uint32_t lab[kLvlU], k0[kLvlU], k1[kLvlU];
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+        const uint32_t j = j0 + k * NT;
+        const bool ok = j < n1;
+        lab[k] = ok ? __ldg(label + j) : 0u;
+        k0[k] = ok ? __ldg(poff + j) : 0u;
+        k1[k] = ok ? __ldg(poff + j + 1) : 0u;
+      }
+      uint32_t pa[kLvlU][kLvlPars], hix[kLvlU];
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+#pragma unroll
+        for (int q = 0; q < kLvlPars; ++q) pa[k][q] = (k0[k] + q < k1[k]) ? (uint32_t)__ldg(par + k0[k] + q) : 0u;
+        hix[k] = (lab[k] & kHotBit) ? __ldg(&A.hot_index[lab[k] & ~kHotBit]) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < kLvlU; ++k) {
+        const uint32_t j = j0 + k * NT;
+        if (j >= n1) continue;
+        const Real in_i = val[j];
+        const uint32_t np = k1[k] - k0[k];
+        Real g;
+        if (np == 0)
+          g = in_i > NI ? Real(1) : Real(0);
+        else {
+          g = 0;
+          auto add = [&](uint32_t e) {
+            const Real m = val[e & (kLvlOrParent - 1)];
+            if (e & kLvlOrParent) {  // OR parent: this alternative's share, m = ln gamma[p] - inside[p]
+              if (in_i > NI) g += FNum<Real>::ex(in_i + m);
+            } else
+              g += m;                // AND parent: every child is used whenever the parent is
+          };
+#pragma unroll
+          for (int q = 0; q < kLvlPars; ++q)
+            if ((uint32_t)q < np) add(pa[k][q]);
+          for (uint32_t kk = k0[k] + kLvlPars; kk < k1[k]; ++kk) add(__ldg(par + kk));
+        }
+        if (lab[k] & ~kHotBit) {
+          if (g > 0) {
+            if (lab[k] & kHotBit)
+              atomicAdd(A.hot + (size_t)replica * A.n_hot + hix[k], (double)g);
+            else
+              atomicAdd(A.counts + lab[k], (double)g);
+          }
+          if (L) val[j] = g;
+        } else if (L)
+          val[j] = (g > 0 && in_i > NI) ? f_log<Real>(g) - in_i : NI;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // mark hot rules in the headers of the outside streams (bit 22); idempotent
 __global__ void k_forest_mark_hot_ops(uint64_t n, uint32_t* __restrict__ ops, const uint32_t* __restrict__ hot_index) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -669,6 +894,12 @@ struct ForestBatch {
   DevArray<uint32_t> t_ops_in, t_ops_out;
   uint32_t t_stack_rows = 2;  // shared-memory rows per lane for the value / path stacks
   DevArray<unsigned char> t_in, t_ga, t_vout;
+  // level-synchronous tiles
+  uint32_t n_ltiles = 0, lt_max_nodes = 0;
+  uint64_t lt_forests = 0, lt_nodes = 0, lt_links = 0;
+  DevArray<LevelTile> ltiles;
+  DevArray<uint32_t> lt_label, lt_coff, lt_poff, lt_lvl, lt_forest;
+  DevArray<uint16_t> lt_child, lt_par, lt_root;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_kernels = 0;
   ~ForestBatch() {
@@ -805,7 +1036,7 @@ extern "C" int cml_forests_set_stream(cml_forests* f, void* s) {
 extern "C" uint64_t cml_forests_launch_count(cml_forests* f) { return f ? f->launches : 0; }
 extern "C" int cml_forests_set_layout(cml_forests* f, int layout) {
   if (!f) return CML_ERR_ARG;
-  F_REQUIRE(layout >= CML_FOREST_LAYOUT_AUTO && layout <= CML_FOREST_LAYOUT_THREAD, CML_ERR_ARG, "cml_forests_set_layout: unknown layout");
+  F_REQUIRE(layout >= CML_FOREST_LAYOUT_AUTO && layout <= CML_FOREST_LAYOUT_LEVEL, CML_ERR_ARG, "cml_forests_set_layout: unknown layout");
   f->layout = layout;
   return CML_OK;
 }
@@ -825,6 +1056,25 @@ extern "C" int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, 
   if (steps) *steps = c;
   if (padded_steps) *padded_steps = d;
   if (padded_rows) *padded_rows = e;
+  return CML_OK;
+}
+
+extern "C" int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
+                                       uint64_t* max_tile_nodes) {
+  if (!f) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0, c = 0, d = 0, e = 0;
+  for (auto const& bt : f->batches) {
+    a += bt->lt_forests;
+    b += bt->n_ltiles;
+    c += bt->lt_nodes;
+    d += bt->lt_links;
+    e = std::max<uint64_t>(e, bt->lt_max_nodes);
+  }
+  if (forests) *forests = a;
+  if (tiles) *tiles = b;
+  if (nodes) *nodes = c;
+  if (links) *links = d;
+  if (max_tile_nodes) *max_tile_nodes = e;
   return CML_OK;
 }
 
@@ -1027,21 +1277,57 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     bt->max_nodes = std::max<uint64_t>(bt->max_nodes, ff[i].n_real);
   }
   // layout family per forest: thread-per-forest tiles for corpora of many small forests, else warp / CTA per forest
-  std::vector<char> in_tile(nf, 0);
+  std::vector<char> in_tile(nf, 0), in_level(nf, 0);
+  const size_t real_bytes = f->precision == 64 ? 8 : 4;
+  // level-synchronous tiles (k_forest_level): runs of consecutive forests whose nodes fit in a CTA's shared memory
+  std::vector<uint32_t> lv_forests;           // forests in level tiles, tile-major (corpus order)
+  std::vector<uint32_t> lv_first;             // per tile: first entry in lv_forests (+ sentinel)
+  {
+    uint64_t min_forests = 256, smem_kb = 100;
+    if (const char* e = getenv("CML_FOREST_LEVEL_MIN_FORESTS")) min_forests = std::strtoull(e, nullptr, 10);
+    if (const char* e = getenv("CML_FOREST_LEVEL_SMEM_KB")) smem_kb = std::strtoull(e, nullptr, 10);
+    smem_kb = std::min<uint64_t>(smem_kb, f->smem_optin ? (f->smem_optin - 4096) / 1024 : 100);
+    const uint64_t cap = std::min<uint64_t>(kLvlMaxNodes, smem_kb * 1024 / real_bytes);
+    uint64_t cand = 0, cand_nodes = 0;
+    for (uint64_t i = 0; i < nf; ++i)
+      if (ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels) {
+        ++cand;
+        cand_nodes += ff[i].n_real;
+      }
+    const bool use = f->layout == CML_FOREST_LAYOUT_LEVEL || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests);
+    if (use && cand) {
+      // small corpora: smaller tiles so that there are a few CTAs per SM
+      uint64_t target = std::max<uint64_t>(2048, cand_nodes / (4ull * (uint64_t)f->sm_count));
+      if (const char* e = getenv("CML_FOREST_LEVEL_TILE_NODES")) target = std::strtoull(e, nullptr, 10);
+      target = std::min(target, cap);
+      uint64_t cur = 0;
+      for (uint64_t i = 0; i < nf; ++i) {
+        if (!(ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels)) continue;
+        in_level[i] = 1;
+        if (lv_first.empty() || cur + ff[i].n_real > target) {
+          lv_first.push_back((uint32_t)lv_forests.size());
+          cur = 0;
+        }
+        cur += ff[i].n_real;
+        lv_forests.push_back((uint32_t)i);
+      }
+      lv_first.push_back((uint32_t)lv_forests.size());
+    }
+  }
   {
     uint64_t min_forests = 8192, max_nodes = 16384;
     if (const char* e = getenv("CML_FOREST_TILE_MIN_FORESTS")) min_forests = std::strtoull(e, nullptr, 10);
     if (const char* e = getenv("CML_FOREST_TILE_MAX_NODES")) max_nodes = std::strtoull(e, nullptr, 10);
     uint64_t cand = 0;
-    for (uint64_t i = 0; i < nf; ++i) cand += ff[i].n_real <= max_nodes;
+    for (uint64_t i = 0; i < nf; ++i) cand += !in_level[i] && ff[i].n_real <= max_nodes;
     const bool labels_fit = f->rulespace <= (uint64_t)kHdrLabel + 1;  // the stream headers carry 22-bit rule ids
     const bool use = labels_fit &&
                      (f->layout == CML_FOREST_LAYOUT_THREAD || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests));
     if (use)
-      for (uint64_t i = 0; i < nf; ++i) in_tile[i] = ff[i].n_real <= max_nodes || f->layout == CML_FOREST_LAYOUT_THREAD;
+      for (uint64_t i = 0; i < nf; ++i) in_tile[i] = !in_level[i] && (ff[i].n_real <= max_nodes || f->layout == CML_FOREST_LAYOUT_THREAD);
   }
   for (uint64_t i = 0; i < nf; ++i) {
-    const bool g = !in_tile[i];
+    const bool g = !in_tile[i] && !in_level[i];
     node_base[i + 1] = node_base[i] + (g ? ff[i].n_real + 1 : 0);
     link_base[i + 1] = link_base[i] + (g ? ff[i].n_links : 0);
     lvl_base[i + 1] = lvl_base[i] + (g ? ff[i].n_levels + 1 : 0);
@@ -1112,6 +1398,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
           const uint32_t* next = b->next + o;
           const uint32_t* label = b->label + o;
           const uint8_t* backref = b->backref + o;
+          if (in_level[fi]) continue;  // (level tiles are laid out tile by tile below)
           FlatForest fx;
           forest_pass1(n, next, label, backref, f->rulespace, S, fx);  // recompute heights (cheap, keeps pass 1 memory small)
           const uint32_t nr = fx.n_real, nl = fx.n_levels;
@@ -1285,13 +1572,166 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     work(0);
     for (auto& t : th) t.join();
   }
+  // ---- level tiles: per tile, the nodes of its forests height-major (level, forest, pre-order), two CSRs of 16-bit local ids
+  const size_t n_lt = lv_first.empty() ? 0 : lv_first.size() - 1;
+  std::vector<LevelTile> ltiles(n_lt);
+  std::vector<uint32_t> lt_label, lt_coff, lt_poff, lt_lvl, lt_forest(lv_forests.size());
+  std::vector<uint16_t> lt_child, lt_par, lt_root(lv_forests.size());
+  if (n_lt) {
+    uint64_t nb = 0, lb = 0, vb = 0;
+    for (size_t t = 0; t < n_lt; ++t) {
+      LevelTile& T = ltiles[t];
+      std::memset(&T, 0, sizeof(T));
+      T.node_base = nb;
+      T.link_base = lb;
+      T.lvl_base = vb;
+      T.forest_base = lv_first[t];
+      T.n_forests = lv_first[t + 1] - lv_first[t];
+      uint32_t nn = 0, nlv = 0;
+      uint64_t nk = 0;
+      for (uint32_t k = lv_first[t]; k < lv_first[t + 1]; ++k) {
+        const uint32_t fi = lv_forests[k];
+        nn += ff[fi].n_real;
+        nk += ff[fi].n_links;
+        nlv = std::max(nlv, ff[fi].n_levels);
+      }
+      T.n_nodes = nn;
+      T.n_levels = nlv;
+      nb += nn + 1;
+      lb += nk;
+      vb += 3ull * (nlv + 1);
+      bt->lt_max_nodes = std::max(bt->lt_max_nodes, nn);
+      bt->lt_nodes += nn;
+      bt->lt_links += nk;
+    }
+    bt->n_ltiles = (uint32_t)n_lt;
+    bt->lt_forests = lv_forests.size();
+    lt_label.assign(nb + 16, 0);
+    lt_coff.assign(nb + 16, 0);
+    lt_poff.assign(nb + 16, 0);
+    lt_lvl.assign(vb, 0);
+    lt_child.assign(lb + 16, 0);
+    lt_par.assign(lb + 16, 0);
+    std::atomic<size_t> next_tile(0);
+    std::atomic<int> tile_err(0);
+    auto work = [&](unsigned tid) {
+      ForestScratch S;
+      std::vector<uint64_t>& occ = occ_parts[tid];
+      if (occ.size() != f->rulespace) occ.assign(f->rulespace, 0);
+      std::vector<uint32_t> H, newid, cnt, pre_off, itp;
+      for (;;) {
+        const size_t t = next_tile.fetch_add(1);
+        if (t >= n_lt) break;
+        const LevelTile& T = ltiles[t];
+        const uint32_t nft = T.n_forests, nlv = T.n_levels, nn = T.n_nodes;
+        uint32_t* lab = lt_label.data() + T.node_base;
+        uint32_t* coff = lt_coff.data() + T.node_base;
+        uint32_t* poff = lt_poff.data() + T.node_base;
+        uint16_t* child = lt_child.data() + T.link_base;
+        uint16_t* par = lt_par.data() + T.link_base;
+        uint32_t* lvl = lt_lvl.data() + T.lvl_base;
+        cnt.assign((size_t)nlv * nft, 0);
+        H.clear();
+        pre_off.assign(nft + 1, 0);
+        for (uint32_t k = 0; k < nft; ++k) {  // heights of every pre-order node of the tile; nodes per (level, forest)
+          const uint32_t fi = lv_forests[T.forest_base + k];
+          const uint64_t o = b->node_off[fi];
+          const uint32_t n = (uint32_t)(b->node_off[fi + 1] - o);
+          FlatForest fx;
+          forest_pass1(n, b->next + o, b->label + o, b->backref + o, f->rulespace, S, fx);
+          if (fx.error) tile_err = 1;
+          pre_off[k + 1] = pre_off[k] + n;
+          H.insert(H.end(), S.height.begin(), S.height.begin() + n);
+          const uint8_t* backref = b->backref + o;
+          for (uint32_t i = 0; i < n; ++i)
+            if (!backref[i]) ++cnt[(size_t)S.height[i] * nft + k];
+        }
+        uint32_t run = 0;
+        for (uint32_t L = 0; L < nlv; ++L) {
+          lvl[L] = run;
+          for (uint32_t k = 0; k < nft; ++k) {
+            const uint32_t c = cnt[(size_t)L * nft + k];
+            cnt[(size_t)L * nft + k] = run;
+            run += c;
+          }
+        }
+        lvl[nlv] = run;
+        newid.assign(pre_off[nft], 0);
+        std::fill(coff, coff + nn + 1, 0u);
+        std::fill(poff, poff + nn + 1, 0u);
+        for (uint32_t k = 0; k < nft; ++k) {  // local ids, stable in pre-order within (level, forest)
+          const uint32_t fi = lv_forests[T.forest_base + k];
+          const uint64_t o = b->node_off[fi];
+          const uint32_t n = pre_off[k + 1] - pre_off[k];
+          const uint8_t* backref = b->backref + o;
+          for (uint32_t i = 0; i < n; ++i)
+            if (!backref[i]) newid[pre_off[k] + i] = cnt[(size_t)H[pre_off[k] + i] * nft + k]++;
+          lt_root[T.forest_base + k] = (uint16_t)newid[pre_off[k]];
+          lt_forest[T.forest_base + k] = fi;
+        }
+        for (uint32_t k = 0; k < nft; ++k) {  // labels, child / parent degrees
+          const uint32_t fi = lv_forests[T.forest_base + k];
+          const uint64_t o = b->node_off[fi];
+          const uint32_t n = pre_off[k + 1] - pre_off[k];
+          const uint32_t* next = b->next + o;
+          const uint32_t* label = b->label + o;
+          const uint8_t* backref = b->backref + o;
+          const uint32_t* nid = newid.data() + pre_off[k];
+          for (uint32_t p = 0; p < n; ++p) {
+            if (backref[p]) continue;
+            const uint32_t id = nid[p];
+            lab[id] = label[p];
+            if (label[p]) ++occ[label[p]];
+            for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+              ++coff[id + 1];
+              ++poff[nid[backref[q] ? label[q] : q] + 1];
+            }
+          }
+        }
+        for (uint32_t id = 0; id < nn; ++id) {
+          coff[id + 1] += coff[id];
+          poff[id + 1] += poff[id];
+        }
+        for (uint32_t L = 0; L <= nlv; ++L) {
+          lvl[(nlv + 1) + L] = coff[lvl[L]];
+          lvl[2 * (nlv + 1) + L] = poff[lvl[L]];
+        }
+        itp.assign(nn, 0);
+        for (uint32_t k = 0; k < nft; ++k) {  // links: children in the reference's order; parents in (forest, pre-order) order
+          const uint32_t fi = lv_forests[T.forest_base + k];
+          const uint64_t o = b->node_off[fi];
+          const uint32_t n = pre_off[k + 1] - pre_off[k];
+          const uint32_t* next = b->next + o;
+          const uint32_t* label = b->label + o;
+          const uint8_t* backref = b->backref + o;
+          const uint32_t* nid = newid.data() + pre_off[k];
+          for (uint32_t p = 0; p < n; ++p) {
+            if (backref[p]) continue;
+            const uint32_t id = nid[p];
+            const uint32_t flag = label[p] ? 0u : kLvlOrParent;
+            uint32_t kk = coff[id];
+            for (uint32_t q = p + 1; q < next[p]; q = next[q]) {
+              const uint32_t c = nid[backref[q] ? label[q] : q];
+              child[kk++] = (uint16_t)c;
+              par[poff[c] + itp[c]++] = (uint16_t)(id | flag);
+            }
+          }
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    F_REQUIRE(!tile_err.load(), CML_ERR_ARG, "cml_forests_add: forest changed between passes");
+  }
   for (auto const& occ : occ_parts)
     for (uint64_t r = 0; r < occ.size(); ++r) f->rule_occ[r] += occ[r];
   // classes: smallest shared-memory capacity that fits, else the CTA class
   const size_t real_b = f->precision == 64 ? 8 : 4;
   std::vector<std::vector<uint32_t>> by_cls(kNWarpCls + 1);
   for (uint64_t i = 0; i < nf; ++i) {
-    if (in_tile[i]) continue;
+    if (in_tile[i] || in_level[i]) continue;
     int c = kNWarpCls;
     for (int k = 0; k < kNWarpCls; ++k)
       if (desc[i].n_nodes <= kWarpCaps[k] && (size_t)kWarpsPerCta * 2 * kWarpCaps[k] * real_b <= f->smem_optin) {
@@ -1331,6 +1771,17 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
     CML_CUDA(bt->t_ga.alloc(bt->t_rows * real_b));
     CML_CUDA(bt->t_vout.alloc(h_ops_out.size() * real_b));  // one value slot per outside stream word
     CML_CUDA(cudaMemsetAsync(bt->t_vout.p, 0, h_ops_out.size() * real_b, f->stream));
+  }
+  if (bt->n_ltiles) {
+    CML_CUDA(bt->ltiles.upload(ltiles.data(), ltiles.size(), f->stream));
+    CML_CUDA(bt->lt_label.upload(lt_label.data(), lt_label.size(), f->stream));
+    CML_CUDA(bt->lt_coff.upload(lt_coff.data(), lt_coff.size(), f->stream));
+    CML_CUDA(bt->lt_poff.upload(lt_poff.data(), lt_poff.size(), f->stream));
+    CML_CUDA(bt->lt_lvl.upload(lt_lvl.data(), lt_lvl.size(), f->stream));
+    CML_CUDA(bt->lt_child.upload(lt_child.data(), lt_child.size(), f->stream));
+    CML_CUDA(bt->lt_par.upload(lt_par.data(), lt_par.size(), f->stream));
+    CML_CUDA(bt->lt_root.upload(lt_root.data(), lt_root.size(), f->stream));
+    CML_CUDA(bt->lt_forest.upload(lt_forest.data(), lt_forest.size(), f->stream));
   }
   CML_CUDA(bt->ln_inside.alloc(nf));
   CML_CUDA(cudaEventCreate(&bt->ev0));
@@ -1379,6 +1830,10 @@ static int forest_rebuild_hot(cml_forests* f) {
   for (auto& bt : f->batches) {
     k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
     ++f->launches;
+    if (bt->n_ltiles) {
+      k_forest_mark_hot<<<f_cdiv(bt->lt_label.n, 256), 256, 0, f->stream>>>(bt->lt_label.n, bt->lt_label.p, f->hot_index.p);
+      ++f->launches;
+    }
     if (bt->n_tiles) {
       k_forest_mark_hot_ops<<<f_cdiv(bt->t_ops_out.n, 256), 256, 0, f->stream>>>(bt->t_ops_out.n, bt->t_ops_out.p,
                                                                                f->hot_index.p);
@@ -1430,6 +1885,34 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     if (tsmem > 48 * 1024)
       CML_CUDA(cudaFuncSetAttribute(k_forest_thread<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     k_forest_thread<Real><<<f_cdiv(bt.n_tiles, kTileWarps), kTileWarps * 32, tsmem, f->stream>>>(T);
+    ++f->launches;
+    ++bt.n_kernels;
+  }
+  if (bt.n_ltiles) {
+    LevelArgs L{};
+    L.tiles = bt.ltiles.p;
+    L.label = bt.lt_label.p;
+    L.coff = bt.lt_coff.p;
+    L.poff = bt.lt_poff.p;
+    L.child = bt.lt_child.p;
+    L.par = bt.lt_par.p;
+    L.lvl = bt.lt_lvl.p;
+    L.root = bt.lt_root.p;
+    L.forest = bt.lt_forest.p;
+    L.lnw = f->w_real.p;
+    L.hot_index = f->hot_index.p;
+    L.counts = f->reduce.p;
+    L.hot = f->hot.p;
+    L.n_hot = f->n_hot;
+    L.ln_inside = bt.ln_inside.p;
+    L.pf = 2;
+    if (const char* e = getenv("CML_FOREST_LEVEL_PREFETCH")) L.pf = std::max(0, atoi(e));
+    int threads = kLvlThreads;
+    if (const char* e = getenv("CML_FOREST_LEVEL_THREADS")) threads = std::min(kLvlThreads, std::max(32, atoi(e) / 32 * 32));
+    const size_t lsmem = ((size_t)bt.lt_max_nodes * sizeof(Real) + 15) & ~(size_t)15;
+    CML_CUDA(cudaFuncSetAttribute(k_forest_level<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)std::max<size_t>(lsmem, 48 * 1024)));  // (3 KB of static tables on top)
+    k_forest_level<Real><<<bt.n_ltiles, threads, lsmem, f->stream>>>(L);
     ++f->launches;
     ++bt.n_kernels;
   }

@@ -124,6 +124,11 @@ struct TrellisBatch {  // the C ABI's cml_trellis_batch, owning its storage; ref
 void build_trellises(Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
                      unsigned n_threads = 0);
 
+// The same, on the GPU (cml_build_trellises): one persistent thread per example walks the reference's DFS.  Chosen by
+// --device-build, or by default for corpora of >= 8,192 examples (--host-build keeps the host builder).
+void build_trellises_device(cml_ctx* ctx, Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
+                            double* seconds = nullptr);
+
 // Multi-GPU sharding of the E-step (examples are independent given the weights: cached_derivs.h:69-75):
 // rank r of n keeps the contiguous block [e0, e1) of the corpus; blocks are balanced by string length
 // (1 + |in| + |out| per example), cover the corpus and do not overlap.
@@ -146,6 +151,7 @@ struct TrainOpts {
   int lane_min = -1;                // --lane-min=n / --no-lane : CML_OPT_LANE_MIN (-1 = library default)
   bool no_factor = false;           // --no-factor : one weight-table entry per arc (CML_OPT_NO_FACTOR)
   bool no_wide = false;             // --no-wide : wide lattices stay on the k_fb_ell classes (CML_OPT_NO_WIDE)
+  int device_build = 0;             // lattice construction: 0 auto (GPU for >= 8,192 examples), --device-build 1, --host-build -1
   int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
   uint32_t ran_restarts = 0;        // -! n : additional random starts (train.cc:553-667)
@@ -170,6 +176,7 @@ struct TrainResult {
   double ln_best_ppx = 0;
   std::vector<IterRecord> history;
   uint64_t trellis_arcs = 0, trellis_states = 0, examples = 0;  // resident on this GPU
+  double device_build_s = 0;  // > 0: lattices built by cml_build_trellises in this many seconds
   bool dense = false;  // the E-step runs on the dense-state view (no lattices materialised)
 };
 // The device model: parameters = all arcs of the cascade members (or of x) in arc-table order.

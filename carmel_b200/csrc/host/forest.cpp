@@ -748,8 +748,8 @@ int open_forest_job(int argc, const char* const* argv, ForestJob& job, std::ostr
         if (key == "print-forests") { a.print_forests_file = val; continue; }
         if (key == "parse-only") { a.parse_only = true; continue; }
         if (key == "layout") {
-          if (val != "auto" && val != "group" && val != "thread") throw std::runtime_error("--layout=auto|group|thread");
-          a.layout = val == "group" ? CML_FOREST_LAYOUT_GROUP : val == "thread" ? CML_FOREST_LAYOUT_THREAD : CML_FOREST_LAYOUT_AUTO;
+          if (val != "auto" && val != "group" && val != "thread" && val != "level") throw std::runtime_error("--layout=auto|group|thread|level");
+          a.layout = val == "group" ? CML_FOREST_LAYOUT_GROUP : val == "thread" ? CML_FOREST_LAYOUT_THREAD : val == "level" ? CML_FOREST_LAYOUT_LEVEL : CML_FOREST_LAYOUT_AUTO;
           continue;
         }
         if (key == "gpu") { a.device = std::atoi(val.c_str()); continue; }

@@ -57,7 +57,7 @@ struct ForestOpts {
   uint64_t random_seed = 1;            // -s  : the restarts' generator (draws differ from the reference's)
   int device = 0;                      // --gpu=n
   int shard_rank = 0, shard_count = 1;  // --shard=r/N
-  int layout = CML_FOREST_LAYOUT_AUTO;  // --layout=auto|group|thread (device layout family, see cml_forests_set_layout)
+  int layout = CML_FOREST_LAYOUT_AUTO;  // --layout=auto|group|thread|level (device layout family, see cml_forests_set_layout)
   bool parse_only = false;            // --parse-only : read (and --print-forests) without touching the GPU
   // checkpoints (forest-em.hpp:166-201,621-641; forest-em-params.hpp:138-145): on every "watch" iteration (the first
   // watch_period iterations, then every watch_period-th) write <prefix>.params / <prefix>.counts

@@ -145,6 +145,8 @@ int open_job(int argc, const char* const* argv, TrainJob& job, std::ostream& err
   if (lopt.count("no-factor")) topt.no_factor = true;
   if (lopt.count("no-wide")) topt.no_wide = true;
   if (lopt.count("dense")) topt.dense = 1;
+  if (lopt.count("device-build")) topt.device_build = 1;
+  if (lopt.count("host-build")) topt.device_build = -1;
   if (lopt.count("gpu")) topt.device = std::atoi(lopt["gpu"].c_str());
   if (lopt.count("history")) topt.history_file = lopt["history"];
   if (lopt.count("dump-trellis")) topt.dump_trellis_file = lopt["dump-trellis"];
@@ -330,6 +332,7 @@ extern "C" int cml_job_stats(cml_job* j, cml_job_info* info) {
   info->examples = j->job.res.examples;
   info->trellis_states = j->job.res.trellis_states;
   info->trellis_arcs = j->job.res.trellis_arcs;
+  info->device_build_s = j->job.res.device_build_s;
   info->n_params = j->job.M.n_params;
   info->n_arcs = j->job.M.n_arcs;
   info->corpus_pairs = j->job.corpus.n_pairs;

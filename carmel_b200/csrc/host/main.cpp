@@ -125,7 +125,21 @@ int main(int argc, char** argv) {
         job.corpus.examples.swap(local.examples);
         std::cerr << "Shard " << job.opt.shard_rank << "/" << job.opt.shard_count << ": examples [" << e0 << ", " << e1 << ")\n";
       }
-      build_trellises(*job.x, job.corpus, tb, dropped);
+      if (job.opt.device_build > 0) {  // --device-build: the same lattices from the GPU builder (cml_build_trellises)
+        cml_ctx* bctx = nullptr;
+        if (cml_create(&bctx, job.opt.device, 64, CML_SPACE_LOG) != CML_OK)
+          throw std::runtime_error(std::string("carmel-b200: ") + cml_last_error(nullptr));
+        double secs = 0;
+        try {
+          build_trellises_device(bctx, *job.x, job.corpus, tb, dropped, &secs);
+        } catch (...) {
+          cml_destroy(bctx);
+          throw;
+        }
+        cml_destroy(bctx);
+        std::cerr << "Device-side lattice construction took " << secs << " s\n";
+      } else
+        build_trellises(*job.x, job.corpus, tb, dropped);
       uint64_t ns = 0;
       for (uint32_t n : tb.ex_states) ns += n;
       std::cerr << "Built " << tb.ex_states.size() << " derivation lattices (" << ns << " states, " << tb.arc_dst.size()

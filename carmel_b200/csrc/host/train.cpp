@@ -334,7 +334,12 @@ void TrainJob::prepare() {
       throw std::runtime_error(std::string("--dense: no dense-state view of this model / corpus") +
                                (ctx ? std::string(": ") + cml_last_error(ctx) : std::string()));
     if (!dense_done) {
-      build_trellises(*x, local, tb, dropped);
+      if (opt.device_build > 0 || (opt.device_build == 0 && local.examples.size() >= 8192)) {
+        double secs = 0;
+        build_trellises_device(ctx, *x, local, tb, dropped, &secs);
+        res.device_build_s = secs;
+      } else
+        build_trellises(*x, local, tb, dropped);
       kept = tb.kept_example;
     }
     for (uint32_t e : dropped)  // cached_derivs.h:53-57,87-93

@@ -377,4 +377,76 @@ void build_trellises(Wfst const& x, Corpus const& corpus, TrellisBatch& out, std
   }
 }
 
+// The same batch built on the GPU (cml_build_trellises, csrc/cml_build.cu): the transducer's arc table and the corpus are
+// handed over as flat arrays, the result comes back in the form build_trellises produces (byte-identical dumps).
+void build_trellises_device(cml_ctx* ctx, Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
+                            double* seconds) {
+  out.clear();
+  dropped.clear();
+  std::vector<uint32_t> soff, ain, aout, adest;
+  x.arc_offsets(soff);
+  const size_t na = x.num_arcs();
+  ain.reserve(na);
+  aout.reserve(na);
+  adest.reserve(na);
+  for (auto const& st : x.states)
+    for (Arc const& a : st) {
+      ain.push_back(a.in);
+      aout.push_back(a.out);
+      adest.push_back(a.dest);
+    }
+  const size_t n = corpus.examples.size();
+  std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0);
+  std::vector<double> weight(n);
+  for (size_t e = 0; e < n; ++e) {
+    in_off[e + 1] = in_off[e] + corpus.examples[e].in.size();
+    out_off[e + 1] = out_off[e] + corpus.examples[e].out.size();
+    weight[e] = corpus.examples[e].weight;
+  }
+  std::vector<uint32_t> in_sym(in_off[n]), out_sym(out_off[n]);
+  for (size_t e = 0; e < n; ++e) {
+    std::copy(corpus.examples[e].in.begin(), corpus.examples[e].in.end(), in_sym.begin() + in_off[e]);
+    std::copy(corpus.examples[e].out.begin(), corpus.examples[e].out.end(), out_sym.begin() + out_off[e]);
+  }
+  cml_wfst_view xv{};
+  xv.n_states = x.num_states();
+  xv.final_state = x.final_state;
+  xv.n_arcs = na;
+  xv.state_arc_off = soff.data();
+  xv.arc_in = ain.data();
+  xv.arc_out = aout.data();
+  xv.arc_dest = adest.data();
+  cml_corpus_view cv{};
+  cv.n_ex = n;
+  cv.in_off = in_off.data();
+  cv.in_sym = in_sym.data();
+  cv.out_off = out_off.data();
+  cv.out_sym = out_sym.data();
+  cv.weight = weight.data();
+  cml_built_trellises* b = nullptr;
+  if (cml_build_trellises(ctx, &xv, &cv, &b) != CML_OK || !b)
+    throw std::runtime_error(std::string("cml_build_trellises: ") + cml_last_error(ctx));
+  const cml_trellis_batch& t = b->batch;
+  uint64_t rows = 0;
+  for (uint64_t e = 0; e < t.n_ex; ++e) rows += (uint64_t)t.ex_states[e] + 1;
+  const uint64_t arcs = rows ? 0 : 0;
+  (void)arcs;
+  out.ex_states.assign(t.ex_states, t.ex_states + t.n_ex);
+  out.ex_fin.assign(t.ex_fin, t.ex_fin + t.n_ex);
+  out.ex_weight.assign(t.ex_weight, t.ex_weight + t.n_ex);
+  out.arc_off.assign(t.arc_off, t.arc_off + rows);
+  uint64_t n_arcs = 0, row = 0;
+  for (uint64_t e = 0; e < t.n_ex; ++e) {
+    n_arcs += t.arc_off[row + t.ex_states[e]];
+    row += (uint64_t)t.ex_states[e] + 1;
+  }
+  out.arc_dst.assign(t.arc_dst, t.arc_dst + n_arcs);
+  out.arc_id.assign(t.arc_id, t.arc_id + n_arcs);
+  out.kept_example.assign(b->kept_example, b->kept_example + t.n_ex);
+  out.pre_arcs = b->pre_arcs;
+  dropped.assign(b->dropped, b->dropped + b->n_dropped);
+  if (seconds) *seconds = b->seconds;
+  cml_free_built_trellises(b);
+}
+
 }  // namespace cb

@@ -148,6 +148,46 @@ typedef struct cml_trellis_batch {
 } cml_trellis_batch;
 int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b);
 int cml_clear_trellises(cml_ctx* ctx);
+
+/* ---- device-side lattice construction ------------------------------------------------------------- *
+ * Replaces derivations::compute (carmel/src/derivations.h:479-513: derive :640-676, add_arcs :678-704, prune
+ * :572-629) for a whole corpus: the intersection  input string x transducer x output string  of every example,
+ * built on the GPU (one persistent thread per example walks the reference's DFS with an explicit stack; cml_build.cu)
+ * and returned in HOST memory in exactly the form cml_add_trellises takes -- reference state ids (DFS pre-order after
+ * pruning), stored arc order, arc-table ids -- so the result is interchangeable with a host-built batch, byte for byte.
+ * Examples without a derivation are left out and listed in `dropped` (cached_derivs.h:87-93).
+ *   transducer: arc table in arc-table order (fst.h:1330-1334), state s owns arcs [state_arc_off[s], state_arc_off[s+1]);
+ *               symbol 0 = *e* on either tape
+ *   corpus:     example e = (in_sym[in_off[e] .. in_off[e+1]), out_sym[out_off[e] .. out_off[e+1])), weight[e] (NULL = 1) */
+typedef struct cml_wfst_view {
+  uint32_t n_states, final_state;
+  uint64_t n_arcs;
+  const uint32_t* state_arc_off; /* [n_states + 1] */
+  const uint32_t* arc_in;        /* [n_arcs] */
+  const uint32_t* arc_out;
+  const uint32_t* arc_dest;
+} cml_wfst_view;
+typedef struct cml_corpus_view {
+  uint64_t n_ex;
+  const uint64_t* in_off;  /* [n_ex + 1] */
+  const uint32_t* in_sym;
+  const uint64_t* out_off; /* [n_ex + 1] */
+  const uint32_t* out_sym;
+  const double* weight;    /* [n_ex] or NULL */
+} cml_corpus_view;
+typedef struct cml_built_trellises {
+  cml_trellis_batch batch;       /* the kept examples, corpus order; pointers owned by this object */
+  const uint32_t* kept_example;  /* [batch.n_ex] corpus index of each kept example */
+  uint64_t n_dropped;
+  const uint32_t* dropped;       /* corpus indices of the examples without a derivation */
+  uint64_t pre_arcs;             /* transducer arcs examined (the reference's "derivations pre-prune" figure) */
+  uint32_t launches;             /* kernel launches (capacity rounds of the sizing pass + the fill pass) */
+  uint32_t peak_states, peak_kept_arcs, peak_depth; /* largest walk: states / kept arcs before pruning, DFS depth */
+  double seconds;                /* wall time of the call (index, upload, both passes, download) */
+  void* owner;
+} cml_built_trellises;
+int cml_build_trellises(cml_ctx* ctx, const cml_wfst_view* x, const cml_corpus_view* c, cml_built_trellises** out);
+void cml_free_built_trellises(cml_built_trellises* b);
 int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs, uint64_t* n_levels);
 /* how the resident lattices are stored: examples / arcs / padded records in the level-sliced ELL layout
  * (throughput kernel) and examples in the layered-CSR layout (general kernels) */
@@ -340,7 +380,8 @@ int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n);
  * value flags taking the next argument, --key[=value]; first file = pair corpus, then the
  * transducers (composed left to right).  Extra long options of this implementation: --float
  * (fp32 scores), --scaled (scaled linear space), --gpu=n, --shard=r/N (this process keeps block r of
- * N of the corpus on its GPU; needs an all-reduce hook), --history=file, --dump-trellis=file.
+ * N of the corpus on its GPU; needs an all-reduce hook), --history=file, --dump-trellis=file,
+ * --device-build / --host-build (where the derivation lattices are constructed; default: GPU for >= 8,192 examples).
  * Log lines go to stderr in the reference's format (train.cc:587-627). */
 typedef struct cml_job cml_job;
 typedef void (*cml_allreduce_fn)(void* user, void* device_ptr, uint64_t n_doubles); /* in-place fp64 sum */
@@ -349,6 +390,7 @@ typedef struct cml_job_info {
   uint64_t n_params, n_arcs, corpus_pairs, iterations;
   double ln_best_ppx, last_ln_prob;
   uint64_t dense; /* 1: the E-step / batched sampler runs on the dense-state view (no lattice walked) */
+  double device_build_s; /* > 0: the lattices were built on the GPU (cml_build_trellises) in this many seconds */
 } cml_job_info;
 int cml_job_open(cml_job** out, int argc, const char* const* argv); /* parse, read, reduce, compose */
 void cml_job_close(cml_job* job);
@@ -398,11 +440,17 @@ int cml_forests_create(cml_forests** out, int device, int precision /* 32 | 64 *
 void cml_forests_destroy(cml_forests* f);
 const char* cml_forests_last_error(cml_forests* f);
 int cml_forests_set_stream(cml_forests* f, void* cuda_stream);
-/* Device layout of the forests added afterwards.  AUTO: corpora of many small forests use one thread per forest
- * (32 forests per warp, transposed streams); few or large forests use one warp / one CTA per forest with
- * height-levelised CSRs.  The other two values force one family (tests, measurements). */
-enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1, CML_FOREST_LAYOUT_THREAD = 2 };
+/* Device layout of the forests added afterwards.  AUTO: corpora of >= 256 forests that fit in a CTA's shared memory
+ * use LEVEL tiles (a CTA owns a run of forests and walks their nodes height-major, all values in shared memory);
+ * few or large forests use one warp / one CTA per forest with height-levelised CSRs (GROUP).  THREAD = one forest per
+ * lane (32 forests per warp, transposed streams; round 1's throughput layout, efficient only when the forests of a
+ * warp share a shape).  The explicit values force one family (tests, measurements). */
+enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1, CML_FOREST_LAYOUT_THREAD = 2, CML_FOREST_LAYOUT_LEVEL = 3 };
 int cml_forests_set_layout(cml_forests* f, int layout);
+/* level-synchronous tiles resident (CML_FOREST_LAYOUT_LEVEL, the AUTO choice for >= 256 forests that fit in shared
+ * memory): forests, tiles (= CTAs per E-step), nodes, links, nodes of the largest tile */
+int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
+                            uint64_t* max_tile_nodes);
 /* thread-per-forest tiles resident: forests in tiles, tiles, real steps, padded steps, padded value rows x 32 */
 int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, uint64_t* tiles, uint64_t* steps, uint64_t* padded_steps,
                              uint64_t* padded_rows);

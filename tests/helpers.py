@@ -26,8 +26,9 @@ def stage(tmp_path, *names):
     return out
 
 
-def run(binary, args, cwd=None, timeout=120):
-    p = subprocess.run([binary, *args], cwd=cwd, capture_output=True, text=True, timeout=timeout)
+def run(binary, args, cwd=None, timeout=120, env=None):
+    p = subprocess.run([binary, *args], cwd=cwd, capture_output=True, text=True, timeout=timeout,
+                       env={**os.environ, **env} if env else None)
     return p.returncode, p.stdout, p.stderr
 
 

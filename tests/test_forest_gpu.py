@@ -35,7 +35,7 @@ def _close_ln(a, b, rel, floor=-60.0):
     return abs(math.expm1(a - b)) <= rel if abs(a - b) < 1 else False
 
 
-def _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel, check_index=True, layouts=("group", "thread")):
+def _compare(fem, forest_oracle_bin, tmp_path, args, mode, rel, check_index=True, layouts=("group", "thread", "level")):
     """product (every device layout family) against the oracle: history, weights, counts, per-forest inside"""
     d = str(tmp_path)
     rc, out, oerr = run(forest_oracle_bin, [*mode, *args, "-o", f"{d}/o.w", "-O", f"{d}/o.c", "-S", f"{d}/o.s", f"--history={d}/o.h"])
@@ -159,7 +159,7 @@ def test_cipher_forests_golden_trajectory(fem, oracle_bin, tmp_path):
                                     f"--fem-param={d}/c.param", data, wfsa, fst])
     assert rc == 0, err
     want = golden()["cipher"]["trajectory_log2"]
-    for layout in ("group", "thread"):
+    for layout in ("group", "thread", "level"):
         rc, out, err = run(fem, ["-U", "-f", f"{d}/c.forest", "-n", f"{d}/c.norm", "-I", f"{d}/c.param", "-i", "22", "-e", "0",
                                  f"--layout={layout}", f"--history={d}/h"])
         assert rc == 0, err
