@@ -22,7 +22,8 @@ struct EllClass {
 // ordered by group size: an example takes the first class it fits
 static const EllClass kEllCls[NELL] = {{4, 1, false},  {8, 1, false},  {4, 4, false}, {8, 4, false},
                                        {16, 2, false}, {32, 1, false}, {32, 8, true}};
-enum ExClass { CLS_WARP0 = 0, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, NCLS = 8 };
+// CLS_CYCLIC: lattices with a cycle, walked in the reference's DFS order by k_fb_cyclic (one thread per lattice)
+enum ExClass { CLS_WARP0 = 0, NWARPCLS = 6, CLS_CTA = 6, CLS_GLOBAL = 7, CLS_CYCLIC = 8, NCLS = 9 };
 static const uint32_t kWarpCaps[NWARPCLS] = {64, 128, 256, 512, 1024, 2048};
 static const uint32_t kPadNone = 0xFFFFFFFFu;
 
@@ -40,6 +41,8 @@ struct Batch {
   uint32_t cta_cap = 0;
   DevArray<unsigned char> scratch;
   DevArray<int> scratch_lvl;
+  DevArray<double> cyc_scratch;  // CLS_CYCLIC: ln alpha / ln beta, 2 per state
+  uint64_t cyc_ex = 0, cyc_back_edges = 0;
   // --- ELL part (v2 kernel)
   uint64_t ell_ex = 0, ell_arcs = 0, ell_pad_records = 0;
   DevArray<cmlk::EllDesc> edesc;

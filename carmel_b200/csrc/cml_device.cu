@@ -452,7 +452,8 @@ namespace {
 
 struct FlatEx {  // per-example facts discovered in pass 1
   uint32_t n_levels = 0;
-  bool cycle = false;
+  bool cycle = false;      // the lattice has a cycle: laid out in the reference's DFS order (CLS_CYCLIC)
+  uint32_t back_edges = 0;
   bool ell = false;        // eligible for the ELL kernel
   uint32_t g_class = 0;    // index into kEllG
   uint32_t ring_need = 0;  // max index distance of an arc + max level width + 1
@@ -502,7 +503,46 @@ void levelize(uint32_t n, const uint32_t* off, const uint32_t* dst, uint32_t* le
     }
   }
   if (queue.size() != n) {
+    // A cycle.  The reference warns and carries on (derivations.h:722-729): forward and backward both walk the states in
+    // the reverse post-order of a DFS from the start over the stored arc lists (graph.h:241-288), so a back edge's
+    // contribution reaches its destination after that state has been propagated.  Same order here: local_of[] = rank in
+    // that order, one state per "level"; k_fb_cyclic walks it sequentially.
     fx.cycle = true;
+    fx.ell = fx.lane_ok = fx.wide_ok = false;
+    auto& begun = S.indeg;   // 0 new, 1 begun, 2 done
+    auto& it = S.icur;       // next arc to follow
+    begun.assign(n, 0);
+    it.assign(n, 0);
+    queue.clear();           // DFS stack
+    uint32_t rank = n, nback = 0;
+    begun[0] = 1;
+    it[0] = off[0];
+    queue.push_back(0);
+    while (!queue.empty()) {
+      const uint32_t s = queue.back();
+      if (it[s] == off[s + 1]) {
+        begun[s] = 2;
+        local_of[s] = --rank;  // post-order position, reversed
+        queue.pop_back();
+        continue;
+      }
+      const uint32_t d = dst[it[s]++];
+      if (begun[d] == 2) continue;
+      if (begun[d] == 1) {
+        ++nback;
+        continue;
+      }
+      begun[d] = 1;
+      it[d] = off[d];
+      queue.push_back(d);
+    }
+    // (every state of a pruned lattice is reachable from the start; anything else keeps the lowest ranks, unreached)
+    for (uint32_t s = 0; s < n; ++s)
+      if (begun[s] != 2) local_of[s] = --rank;
+    for (uint32_t s = 0; s < n; ++s) level_of[s] = local_of[s];
+    fx.n_levels = n;
+    fx.width = 1;
+    fx.back_edges = nback;
     return;
   }
   const uint32_t nl = fx.n_levels = maxl + 1;
@@ -668,8 +708,12 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     bt->h_nlevels[e] = fx[e].n_levels;
   });
   CML_REQUIRE(!bad_range, CML_ERR_ARG, "trellis arc destination or arc id out of range");
-  CML_REQUIRE(!bad_cycle, CML_ERR_CYCLE,
-              "derivation lattice has a cycle (the reference warns 'Forward/backward will miss some paths')");
+  if (bad_cycle)  // cyclic lattices take the reference's sequential order (k_fb_cyclic); the sampler has no such order
+    for (uint64_t e = 0; e < n_ex; ++e)
+      if (fx[e].cycle) {
+        ++bt->cyc_ex;
+        bt->cyc_back_edges += fx[e].back_edges;
+      }
 
   // ---- lane-per-lattice layout for corpora of many narrow lattices (cml_kernels_lane.cuh)
   std::vector<uint32_t> lane_list;
@@ -974,7 +1018,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
   const uint32_t cta_max_states = (uint32_t)((smem_budget - 64) / per_state);
   std::vector<std::vector<uint32_t>> cls(NCLS), ecls(NELL);
   std::vector<uint32_t> wide_list;
-  uint64_t scratch_states = 0;
+  uint64_t scratch_states = 0, cyc_states = 0;
   for (uint64_t e = 0; e < n_ex; ++e) {
     if (fx[e].lane) continue;
     if (fx[e].wide) {
@@ -992,7 +1036,11 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
     }
     const uint32_t n = b->ex_states[e];
     int c = -1;
-    if (fx[e].width <= 96) {
+    if (fx[e].cycle) {
+      c = CLS_CYCLIC;
+      desc[slot_of[e]].scratch_base = cyc_states;
+      cyc_states += n;
+    } else if (fx[e].width <= 96) {
       for (int i = 0; i < NWARPCLS; ++i)
         if (n <= kWarpCaps[i]) {
           c = CLS_WARP0 + i;
@@ -1199,6 +1247,7 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       CML_CUDA(bt->scratch.alloc(scratch_states * 2 * rs));
       if (scaled) CML_CUDA(bt->scratch_lvl.alloc(scratch_states * 2));
     }
+    if (cyc_states) CML_CUDA(bt->cyc_scratch.alloc(cyc_states * 2));
   }
   if (n_e) {
     CML_CUDA(bt->edesc.upload(edesc.data(), n_e, s));
@@ -1245,6 +1294,17 @@ extern "C" int cml_clear_trellises(cml_ctx* ctx) {
   return CML_OK;
 }
 
+extern "C" int cml_cyclic_stats(cml_ctx* ctx, uint64_t* n_examples, uint64_t* n_back_edges) {
+  if (!ctx) return CML_ERR_ARG;
+  uint64_t a = 0, b = 0;
+  for (auto& bt : ctx->batches) {
+    a += bt->cyc_ex;
+    b += bt->cyc_back_edges;
+  }
+  if (n_examples) *n_examples = a;
+  if (n_back_edges) *n_back_edges = b;
+  return CML_OK;
+}
 extern "C" int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs,
                                   uint64_t* n_levels) {
   if (!ctx) return CML_ERR_ARG;
@@ -1471,8 +1531,12 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     const size_t tbl_v = (size_t)L.n_v * (sizeof(Real) + 4);
     const bool ta = tbl_a <= 40 * 1024, tv = tbl_v <= 24 * 1024;
     const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real) + (ta ? tbl_a : 0) + (tv ? tbl_v : 0);
-    auto kern = ta ? (tv ? k_fb_lane<Real, true, true> : k_fb_lane<Real, true, false>)
-                   : (tv ? k_fb_lane<Real, false, true> : k_fb_lane<Real, false, false>);
+    int minb = 2;
+    if (const char* e = getenv("CML_LANE_MINB")) minb = atoi(e);  // tuning knob: 3 = register cap for three resident blocks
+    auto kern = minb >= 3 ? (ta ? (tv ? k_fb_lane<Real, true, true, 3> : k_fb_lane<Real, true, false, 3>)
+                                : (tv ? k_fb_lane<Real, false, true, 3> : k_fb_lane<Real, false, false, 3>))
+                          : (ta ? (tv ? k_fb_lane<Real, true, true, 2> : k_fb_lane<Real, true, false, 2>)
+                                : (tv ? k_fb_lane<Real, false, true, 2> : k_fb_lane<Real, false, false, 2>));
     if (smem > 48 * 1024) CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<cdiv(bt.lane_tiles, kLaneWarps), kLaneWarps * 32, smem, ctx->stream>>>(L);
@@ -1529,6 +1593,16 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
         A.n_list = n;
         A.cap_states = 0;
         k_fb_cta<Real, SCALED, true><<<n, 256, 0, ctx->stream>>>(A);
+        ++ctx->launches;
+        ++bt.n_fb_kernels;
+      }
+    }
+    {
+      const uint32_t n = bt.cls_begin[CLS_CYCLIC + 1] - bt.cls_begin[CLS_CYCLIC];
+      if (n) {  // lattices with a cycle: the reference's sequential walk, one thread per lattice
+        A.ex_list = bt.ex_list.p + bt.cls_begin[CLS_CYCLIC];
+        A.n_list = n;
+        k_fb_cyclic<Real, SCALED><<<cdiv(n, 64), 64, 0, ctx->stream>>>(A, bt.cyc_scratch.p);
         ++ctx->launches;
         ++bt.n_fb_kernels;
       }
@@ -2066,7 +2140,7 @@ extern "C" const char* const* cml_exported_symbols(size_t* n) {
       "cml_normalize_params", "cml_exported_symbols", "cml_job_open", "cml_job_close", "cml_job_error",
       "cml_job_set_comm", "cml_job_set_allreduce", "cml_job_prepare", "cml_job_context", "cml_job_train", "cml_job_write", "cml_job_stats", "cml_gibbs_init", "cml_gibbs_attach_dense", "cml_gibbs_sweep",
       "cml_gibbs_sample_capacity", "cml_gibbs_get_samples", "cml_gibbs_get_state", "cml_gibbs_get_block_logprob", "cml_forests_create", "cml_forests_destroy",
-      "cml_forests_last_error", "cml_forests_set_stream", "cml_forests_set_layout", "cml_forests_layout_stats", "cml_forests_level_stats", "cml_build_trellises", "cml_free_built_trellises",
+      "cml_forests_last_error", "cml_forests_set_stream", "cml_forests_set_layout", "cml_forests_layout_stats", "cml_forests_level_stats", "cml_build_trellises", "cml_free_built_trellises", "cml_cyclic_stats",
       "cml_forests_launch_count", "cml_forests_set_rules",
       "cml_forests_set_params", "cml_forests_get_params", "cml_forests_add", "cml_forests_totals", "cml_forests_estimate",
       "cml_forests_estimate_launch", "cml_forests_estimate_finish", "cml_forests_last_time_ms", "cml_forests_get_inside",

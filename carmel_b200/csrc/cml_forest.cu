@@ -492,9 +492,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) k_forest_thread(TileArgs A) {
 // lanes of a warp own consecutive nodes of the same level (k_forest_thread on an all-distinct corpus ran with 16
 // of 32 lanes active and 2.7x the algorithmic DRAM traffic: profiles/round2_A_k_forest_thread.txt).
 // ---------------------------------------------------------------------------------------------------
-const int kLvlThreads = 512;
 const uint32_t kLvlMaxLevels = 255, kLvlMaxNodes = 32768, kLvlOrParent = 0x8000u;
-const int kLvlU = 4, kLvlKids = 4, kLvlPars = 2;  // nodes in flight per thread; child / parent ids fetched ahead per node
+const int kLvlKids = 4, kLvlPars = 2;  // child / parent ids fetched ahead per node
 struct __align__(16) LevelTile {
   uint64_t node_base;   // first entry of the tile in lt_label / lt_coff / lt_poff (n_nodes + 1 entries)
   uint64_t link_base;   // first link of the tile in lt_child / lt_par
@@ -519,6 +518,8 @@ struct LevelArgs {
   uint32_t n_hot;
   double* ln_inside;
   int pf;                   // L2 prefetch distance in levels (0 = off)
+  uint32_t n_tiles;         // tiles of this launch (tiles points at the first)
+  uint32_t cap;             // G = 32: value slots per warp
 };
 __device__ __forceinline__ void f_prefetch_l2(const void* base, size_t b0, size_t b1) {  // bytes [b0, b1) behind base
   const uintptr_t s = ((uintptr_t)base + b0) & ~(uintptr_t)15, e = ((uintptr_t)base + b1 + 15) & ~(uintptr_t)15;
@@ -531,14 +532,20 @@ __device__ __forceinline__ float f_log<float>(float x) { return logf(x); }
 template <>
 __device__ __forceinline__ double f_log<double>(double x) { return log(x); }
 
-template <typename Real>
-__global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
+// NTHR / MINB: threads per CTA and resident CTAs per SM the registers are capped for; U: nodes in flight per thread.
+// (Measured and dropped: one WARP per small tile instead of a CTA -- no barriers, but levels of a few nodes leave most
+// lanes idle: 13 of 32 lanes active, twice the warp instructions, 1.76 ms against 1.55 ms; profiles/round2_D_*.)
+template <typename Real, int NTHR, int MINB, int U>
+__global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
   extern __shared__ __align__(16) unsigned char smem_lv[];
   __shared__ uint32_t s_lvl[3 * (kLvlMaxLevels + 1)];
+  const uint32_t grp = blockIdx.x;
   Real* __restrict__ val = reinterpret_cast<Real*>(smem_lv);
-  const LevelTile T = A.tiles[blockIdx.x];
+  const LevelTile T = A.tiles[grp];
   const uint32_t tid = threadIdx.x, NT = blockDim.x, nl = T.n_levels;
   for (uint32_t k = tid; k < 3 * (nl + 1); k += NT) s_lvl[k] = __ldg(A.lvl + T.lvl_base + k);
+  __syncthreads();
+  auto sync = [&]() { __syncthreads(); };
   const uint32_t* __restrict__ s_node = s_lvl;
   const uint32_t* __restrict__ s_cl = s_lvl + (nl + 1);
   const uint32_t* __restrict__ s_pl = s_lvl + 2 * (nl + 1);
@@ -550,7 +557,6 @@ __global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
   const Real* __restrict__ lnw = (const Real*)A.lnw;
   const Real NI = FNum<Real>::ninf();
   const uint32_t pf = (uint32_t)A.pf;
-  __syncthreads();
   auto prefetch_in = [&](uint32_t L) {
     f_prefetch_l2(label, 4ull * s_node[L], 4ull * s_node[L + 1]);
     f_prefetch_l2(coff, 4ull * s_node[L], 4ull * s_node[L + 1] + 4);
@@ -561,7 +567,7 @@ __global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
     f_prefetch_l2(poff, 4ull * s_node[L], 4ull * s_node[L + 1] + 4);
     f_prefetch_l2(par, 2ull * s_pl[L], 2ull * s_pl[L + 1]);
   };
-  // ---- inside: ascending height (forest.hpp:636-697).  A thread keeps kLvlU nodes of the level in flight: all their
+  // ---- inside: ascending height (forest.hpp:636-697).  A thread keeps U nodes of the level in flight: all their
   // headers are loaded, then all their first kLvlKids child ids and rule weights, then they are reduced one by one --
   // with one node per thread and iteration the kernel ran at the latency of its dependent loads times the resident
   // threads (profiles/round2_B_k_forest_level.txt: 1.79 ms, DRAM 9 % busy, long-scoreboard + barrier stalls).
@@ -571,45 +577,45 @@ __global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
     const uint32_t n1 = s_node[L + 1];
     if (tid == 0 && pf && L + pf < nl) prefetch_in(L + pf);
     if (L == 0) {  // height 0: leaves, inside = the rule weight
-      for (uint32_t j0 = s_node[0] + tid; j0 < n1; j0 += 2 * kLvlU * NT) {
-        uint32_t lab[2 * kLvlU];
+      for (uint32_t j0 = tid; j0 < n1; j0 += 2 * U * NT) {
+        uint32_t lab[2 * U];
 #pragma unroll
-        for (int k = 0; k < 2 * kLvlU; ++k) {
+        for (int k = 0; k < 2 * U; ++k) {
           const uint32_t j = j0 + k * NT;
           lab[k] = j < n1 ? (__ldg(label + j) & ~kHotBit) : 0u;
         }
-        Real wv[2 * kLvlU];
+        Real wv[2 * U];
 #pragma unroll
-        for (int k = 0; k < 2 * kLvlU; ++k) wv[k] = __ldg(lnw + lab[k]);
+        for (int k = 0; k < 2 * U; ++k) wv[k] = __ldg(lnw + lab[k]);
 #pragma unroll
-        for (int k = 0; k < 2 * kLvlU; ++k) {
+        for (int k = 0; k < 2 * U; ++k) {
           const uint32_t j = j0 + k * NT;
           if (j < n1) val[j] = wv[k];
         }
       }
-      __syncthreads();
+      sync();
       continue;
     }
-    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += kLvlU * NT) {
-      uint32_t lab[kLvlU], c0[kLvlU], c1[kLvlU];
+    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += U * NT) {
+      uint32_t lab[U], c0[U], c1[U];
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
         const uint32_t j = j0 + k * NT;
         const bool ok = j < n1;
         lab[k] = ok ? (__ldg(label + j) & ~kHotBit) : 0u;
         c0[k] = ok ? __ldg(coff + j) : 0u;
         c1[k] = ok ? __ldg(coff + j + 1) : 0u;
       }
-      uint32_t ch[kLvlU][kLvlKids];
-      Real wv[kLvlU];
+      uint32_t ch[U][kLvlKids];
+      Real wv[U];
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
 #pragma unroll
         for (int q = 0; q < kLvlKids; ++q) ch[k][q] = (c0[k] + q < c1[k]) ? (uint32_t)__ldg(child + c0[k] + q) : 0u;
         wv[k] = __ldg(lnw + lab[k]);  // (entry 0 exists: rule ids start at 1)
       }
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
         const uint32_t j = j0 + k * NT;
         if (j >= n1) continue;
         const uint32_t nc = c1[k] - c0[k];
@@ -630,38 +636,38 @@ __global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
         val[j] = v;
       }
     }
-    __syncthreads();
+    sync();
   }
   for (uint32_t k = tid; k < T.n_forests; k += NT)
     A.ln_inside[__ldg(A.forest + T.forest_base + k)] = (double)val[__ldg(A.root + T.forest_base + k)];
   if (tid == 0 && pf)
     for (uint32_t d = 0; d < pf && d < nl; ++d) prefetch_out(nl - 1 - d);
-  __syncthreads();
+  sync();
   // ---- outside as posteriors, descending height, pull over the parents (forest.hpp:439-491); a root (no parents) of a
   // zero-probability forest starts at 0, so that forest collects no counts (forest.hpp:447-451)
-  const uint32_t replica = blockIdx.x & (kHotCopies - 1);
+  const uint32_t replica = grp & (kHotCopies - 1);
   for (uint32_t L = nl; L-- > 0;) {
     const uint32_t n1 = s_node[L + 1];
     if (tid == 0 && pf && L >= pf) prefetch_out(L - pf);
-    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += kLvlU * NT) {
-      uint32_t lab[kLvlU], k0[kLvlU], k1[kLvlU];
+    for (uint32_t j0 = s_node[L] + tid; j0 < n1; j0 += U * NT) {
+      uint32_t lab[U], k0[U], k1[U];
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
         const uint32_t j = j0 + k * NT;
         const bool ok = j < n1;
         lab[k] = ok ? __ldg(label + j) : 0u;
         k0[k] = ok ? __ldg(poff + j) : 0u;
         k1[k] = ok ? __ldg(poff + j + 1) : 0u;
       }
-      uint32_t pa[kLvlU][kLvlPars], hix[kLvlU];
+      uint32_t pa[U][kLvlPars], hix[U];
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
 #pragma unroll
         for (int q = 0; q < kLvlPars; ++q) pa[k][q] = (k0[k] + q < k1[k]) ? (uint32_t)__ldg(par + k0[k] + q) : 0u;
         hix[k] = (lab[k] & kHotBit) ? __ldg(&A.hot_index[lab[k] & ~kHotBit]) : 0u;
       }
 #pragma unroll
-      for (int k = 0; k < kLvlU; ++k) {
+      for (int k = 0; k < U; ++k) {
         const uint32_t j = j0 + k * NT;
         if (j >= n1) continue;
         const Real in_i = val[j];
@@ -695,7 +701,7 @@ __global__ void __launch_bounds__(kLvlThreads, 2) k_forest_level(LevelArgs A) {
           val[j] = (g > 0 && in_i > NI) ? f_log<Real>(g) - in_i : NI;
       }
     }
-    __syncthreads();
+    sync();
   }
 }
 
@@ -895,7 +901,8 @@ struct ForestBatch {
   uint32_t t_stack_rows = 2;  // shared-memory rows per lane for the value / path stacks
   DevArray<unsigned char> t_in, t_ga, t_vout;
   // level-synchronous tiles
-  uint32_t n_ltiles = 0, lt_max_nodes = 0;
+  uint32_t n_ltiles = 0, lt_max_nodes = 0;  // all level tiles; nodes of the largest CTA tile
+  uint32_t n_wtiles = 0, lt_warp_cap = 0;   // the first n_wtiles tiles are WARP tiles of <= lt_warp_cap nodes
   uint64_t lt_forests = 0, lt_nodes = 0, lt_links = 0;
   DevArray<LevelTile> ltiles;
   DevArray<uint32_t> lt_label, lt_coff, lt_poff, lt_lvl, lt_forest;
@@ -1060,16 +1067,18 @@ extern "C" int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, 
 }
 
 extern "C" int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
-                                       uint64_t* max_tile_nodes) {
+                                       uint64_t* max_tile_nodes, uint64_t* warp_tiles) {
   if (!f) return CML_ERR_ARG;
-  uint64_t a = 0, b = 0, c = 0, d = 0, e = 0;
+  uint64_t a = 0, b = 0, c = 0, d = 0, e = 0, w = 0;
   for (auto const& bt : f->batches) {
     a += bt->lt_forests;
     b += bt->n_ltiles;
     c += bt->lt_nodes;
     d += bt->lt_links;
-    e = std::max<uint64_t>(e, bt->lt_max_nodes);
+    e = std::max<uint64_t>(e, std::max(bt->lt_max_nodes, bt->n_wtiles ? bt->lt_warp_cap : 0u));
+    w += bt->n_wtiles;
   }
+  if (warp_tiles) *warp_tiles = w;
   if (forests) *forests = a;
   if (tiles) *tiles = b;
   if (nodes) *nodes = c;
@@ -1282,6 +1291,7 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
   // level-synchronous tiles (k_forest_level): runs of consecutive forests whose nodes fit in a CTA's shared memory
   std::vector<uint32_t> lv_forests;           // forests in level tiles, tile-major (corpus order)
   std::vector<uint32_t> lv_first;             // per tile: first entry in lv_forests (+ sentinel)
+  uint32_t lv_n_warp_tiles = 0, lv_warp_cap = 0;  // the first tiles are WARP tiles (<= lv_warp_cap nodes each)
   {
     uint64_t min_forests = 256, smem_kb = 100;
     if (const char* e = getenv("CML_FOREST_LEVEL_MIN_FORESTS")) min_forests = std::strtoull(e, nullptr, 10);
@@ -1296,17 +1306,24 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
       }
     const bool use = f->layout == CML_FOREST_LAYOUT_LEVEL || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests);
     if (use && cand) {
+      auto eligible = [&](uint64_t i) { return ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels; };
+      uint64_t cur = 0;
       // small corpora: smaller tiles so that there are a few CTAs per SM
-      uint64_t target = std::max<uint64_t>(2048, cand_nodes / (4ull * (uint64_t)f->sm_count));
+      uint64_t rest_nodes = 0;
+      for (uint64_t i = 0; i < nf; ++i)
+        if (eligible(i) && !in_level[i]) rest_nodes += ff[i].n_real;
+      uint64_t target = std::max<uint64_t>(2048, rest_nodes / (4ull * (uint64_t)f->sm_count));
       if (const char* e = getenv("CML_FOREST_LEVEL_TILE_NODES")) target = std::strtoull(e, nullptr, 10);
       target = std::min(target, cap);
-      uint64_t cur = 0;
+      cur = 0;
+      bool first_cta = true;
       for (uint64_t i = 0; i < nf; ++i) {
-        if (!(ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels)) continue;
+        if (!eligible(i) || in_level[i]) continue;
         in_level[i] = 1;
-        if (lv_first.empty() || cur + ff[i].n_real > target) {
+        if (first_cta || cur + ff[i].n_real > target) {
           lv_first.push_back((uint32_t)lv_forests.size());
           cur = 0;
+          first_cta = false;
         }
         cur += ff[i].n_real;
         lv_forests.push_back((uint32_t)i);
@@ -1600,11 +1617,13 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
       nb += nn + 1;
       lb += nk;
       vb += 3ull * (nlv + 1);
-      bt->lt_max_nodes = std::max(bt->lt_max_nodes, nn);
+      if (t >= lv_n_warp_tiles) bt->lt_max_nodes = std::max(bt->lt_max_nodes, nn);
       bt->lt_nodes += nn;
       bt->lt_links += nk;
     }
     bt->n_ltiles = (uint32_t)n_lt;
+    bt->n_wtiles = lv_n_warp_tiles;
+    bt->lt_warp_cap = lv_warp_cap;
     bt->lt_forests = lv_forests.size();
     lt_label.assign(nb + 16, 0);
     lt_coff.assign(nb + 16, 0);
@@ -1907,12 +1926,28 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     L.ln_inside = bt.ln_inside.p;
     L.pf = 2;
     if (const char* e = getenv("CML_FOREST_LEVEL_PREFETCH")) L.pf = std::max(0, atoi(e));
-    int threads = kLvlThreads;
-    if (const char* e = getenv("CML_FOREST_LEVEL_THREADS")) threads = std::min(kLvlThreads, std::max(32, atoi(e) / 32 * 32));
     const size_t lsmem = ((size_t)bt.lt_max_nodes * sizeof(Real) + 15) & ~(size_t)15;
-    CML_CUDA(cudaFuncSetAttribute(k_forest_level<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)std::max<size_t>(lsmem, 48 * 1024)));  // (3 KB of static tables on top)
-    k_forest_level<Real><<<bt.n_ltiles, threads, lsmem, f->stream>>>(L);
+    L.n_tiles = bt.n_ltiles;
+    L.cap = bt.lt_max_nodes;
+    // launch shapes (threads x resident CTAs per SM): the tile capacity (CML_FOREST_LEVEL_SMEM_KB at add time) decides how
+    // many CTAs really fit; 0 = 512 x 2 (default), 1 = 384 x 3, 2 = 256 x 4, 3 = 256 x 6 with 2 nodes in flight
+    int variant = 0;
+    if (const char* e = getenv("CML_FOREST_LEVEL_VARIANT")) variant = atoi(e);
+    auto go = [&](auto kern, int threads) -> int {
+      CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(lsmem, 48 * 1024)));
+      kern<<<bt.n_ltiles, threads, lsmem, f->stream>>>(L);
+      return CML_OK;
+    };
+    int rc;
+    if (variant == 1)
+      rc = go(k_forest_level<Real, 384, 3, 4>, 384);
+    else if (variant == 2)
+      rc = go(k_forest_level<Real, 256, 4, 4>, 256);
+    else if (variant == 3)
+      rc = go(k_forest_level<Real, 256, 6, 2>, 256);
+    else
+      rc = go(k_forest_level<Real, 512, 2, 4>, 512);
+    if (rc) return rc;
     ++f->launches;
     ++bt.n_kernels;
   }

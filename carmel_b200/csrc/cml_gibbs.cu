@@ -637,6 +637,8 @@ extern "C" int cml_gibbs_init(cml_ctx* ctx, const cml_gibbs_model* g) {
   CML_REQUIRE(g->n_params == ctx->n_params && g->param_norm && g->param_prior, CML_ERR_ARG, "gibbs model does not match the model");
   CML_REQUIRE(ctx->batches.size() == 1 && ctx->batches[0]->ell_ex == 0, CML_ERR_STATE,
               "Gibbs sampling needs the lattices in ONE batch in the layered-CSR layout (log space or CML_OPT_NO_ELL)");
+  CML_REQUIRE(ctx->batches[0]->cyc_ex == 0, CML_ERR_CYCLE,
+              "Gibbs sampling over a lattice with a cycle is not built (the backward filter has no level order)");
   cudaSetDevice(ctx->device);
   Batch& bt = *ctx->batches[0];
   cudaStream_t s = ctx->stream;

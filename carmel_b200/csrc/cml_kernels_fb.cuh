@@ -396,6 +396,69 @@ static __global__ void __launch_bounds__(256) k_fb_cta(FbArgs A) {
 
 // Sum of ln P_e, w_e ln P_e and the zero-probability count over a batch (deterministic per block,
 // one atomicAdd triple per block into the reduce buffer's scalar tail).
+// ---------------------------------------------------------------------------------------------
+// Lattices with a cycle (CLS_CYCLIC).  The reference does not solve the cyclic system: it walks the states once in the
+// reverse post-order of its DFS (forward) and once in post-order over the reversed graph (backward), warns that
+// "Forward/backward will miss some paths" (derivations.h:400-417,722-729; graph.h:241-288,391-402), and uses whatever
+// alpha / beta that leaves for the counts.  To give the same numbers the walk must be the same SEQUENCE of updates, so
+// one thread owns a lattice: layered index j = rank in that order (cml_add_trellises), out-lists in stored order.
+// Natural-log fp64 whatever the context's space / precision (these lattices are rare and small).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cyc_lse(double a, double b) {
+  if (!(a > -CUDART_INF)) return b;
+  if (!(b > -CUDART_INF)) return a;
+  const double hi = fmax(a, b), d = -fabs(a - b);
+  return d < -36. ? hi : hi + log1p(exp(d));  // logweight operator+ (weight.h:765-801: 36-nat cutoff)
+}
+template <typename Real, bool SCALED>
+static __global__ void __launch_bounds__(64) k_fb_cyclic(FbArgs A, double* __restrict__ scratch) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_list) return;
+  const CmlExDesc d = A.desc[A.ex_list[t]];
+  const Real* __restrict__ w = (const Real*)A.arc_w;
+  const uint32_t* __restrict__ ioff = A.in_off + d.row_base;
+  const uint32_t* __restrict__ ooff = A.out_off + d.row_base;
+  const uint2* __restrict__ iarc = A.in_arc + d.arc_base;
+  const uint2* __restrict__ oarc = A.out_arc + d.arc_base;
+  double* __restrict__ f = scratch + 2 * d.scratch_base;
+  double* __restrict__ bw = f + d.n_states;
+  const uint32_t n = d.n_states;
+  auto lnw = [&](uint32_t id) -> double { return SCALED ? log((double)w[id]) : (double)w[id]; };
+  for (uint32_t j = 0; j < n; ++j) f[j] = bw[j] = -CUDART_INF;
+  f[0] = 0.;  // the start state is first in the order
+  for (uint32_t j = 0; j < n; ++j) {
+    const double fj = f[j];
+    if (!(fj > -CUDART_INF)) continue;
+    for (uint32_t k = ooff[j]; k < ooff[j + 1]; ++k) {
+      const uint2 a = oarc[k];
+      f[a.x] = cyc_lse(f[a.x], fj + lnw(a.y));
+    }
+  }
+  const double P = f[d.fin];
+  A.ex_lnp[d.ex_index] = P;
+  if (!(P > -CUDART_INF)) return;
+  bw[d.fin] = 0.;
+  for (uint32_t j = n; j-- > 0;) {
+    const double bj = bw[j];
+    if (!(bj > -CUDART_INF)) continue;
+    for (uint32_t k = ioff[j]; k < ioff[j + 1]; ++k) {
+      const uint2 a = iarc[k];
+      bw[a.x] = cyc_lse(bw[a.x], bj + lnw(a.y));
+    }
+  }
+  for (uint32_t j = 0; j < n; ++j) {
+    const double fj = f[j];
+    if (!(fj > -CUDART_INF)) continue;
+    for (uint32_t k = ooff[j]; k < ooff[j + 1]; ++k) {
+      const uint2 a = oarc[k];
+      const uint32_t code = A.arc_slot[a.y];
+      if (code == kSlotNone) continue;
+      const double c = exp(lnw(a.y) + fj + bw[a.x] - P) * d.weight;
+      if (c > 0) count_add(A.sink, code, c);
+    }
+  }
+}
+
 static __global__ void __launch_bounds__(256) k_reduce_lnp(const double* __restrict__ ex_lnp, const double* __restrict__ ex_weight,
                                                     uint64_t n, double* __restrict__ scal) {
   double s0 = 0, s1 = 0, nz = 0;

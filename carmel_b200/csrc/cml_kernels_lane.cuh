@@ -64,8 +64,9 @@ constexpr int kLaneWarps = 8;
 // TA / TV: the arc-class / state-class tables (weight + slot code) are staged in shared memory.  Arc weights are
 // FACTORED (cml_device.cu "arc classes"): w(arc) = U[record's class] * V[class of the destination state]; the state
 // part's expected count is the state posterior, accumulated once per state.
-template <typename Real, bool TA, bool TV>
-static __global__ void __launch_bounds__(kLaneWarps * 32) k_fb_lane(LaneArgs A) {
+// MINB: resident blocks per SM the register allocation is capped for (2 = uncapped, ~86 registers; 3 caps at 80).
+template <typename Real, bool TA, bool TV, int MINB>
+static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneArgs A) {
   extern __shared__ __align__(16) unsigned char smem_lane[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * kLaneWarps + wib;

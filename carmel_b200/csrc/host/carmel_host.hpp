@@ -125,7 +125,7 @@ void build_trellises(Wfst const& x, Corpus const& corpus, TrellisBatch& out, std
                      unsigned n_threads = 0);
 
 // The same, on the GPU (cml_build_trellises): one persistent thread per example walks the reference's DFS.  Chosen by
-// --device-build, or by default for corpora of >= 8,192 examples (--host-build keeps the host builder).
+// --device-build (--host-build, the default, keeps the multi-threaded host builder).
 void build_trellises_device(cml_ctx* ctx, Wfst const& x, Corpus const& corpus, TrellisBatch& out, std::vector<uint32_t>& dropped,
                             double* seconds = nullptr);
 
@@ -151,7 +151,7 @@ struct TrainOpts {
   int lane_min = -1;                // --lane-min=n / --no-lane : CML_OPT_LANE_MIN (-1 = library default)
   bool no_factor = false;           // --no-factor : one weight-table entry per arc (CML_OPT_NO_FACTOR)
   bool no_wide = false;             // --no-wide : wide lattices stay on the k_fb_ell classes (CML_OPT_NO_WIDE)
-  int device_build = 0;             // lattice construction: 0 auto (GPU for >= 8,192 examples), --device-build 1, --host-build -1
+  int device_build = 0;             // lattice construction: 0 / --host-build -1: host threads; --device-build 1: cml_build_trellises
   int dense = 0;                    // dense-state path: 0 auto (when the model has the view), --no-dense -1, --dense 1 (required)
   std::string history_file, dump_trellis_file;
   uint32_t ran_restarts = 0;        // -! n : additional random starts (train.cc:553-667)

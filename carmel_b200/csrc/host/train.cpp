@@ -334,7 +334,7 @@ void TrainJob::prepare() {
       throw std::runtime_error(std::string("--dense: no dense-state view of this model / corpus") +
                                (ctx ? std::string(": ") + cml_last_error(ctx) : std::string()));
     if (!dense_done) {
-      if (opt.device_build > 0 || (opt.device_build == 0 && local.examples.size() >= 8192)) {
+      if (opt.device_build > 0) {  // (measured: not faster than 16 host threads at 1M sentences -- DESIGN.md; opt-in)
         double secs = 0;
         build_trellises_device(ctx, *x, local, tb, dropped, &secs);
         res.device_build_s = secs;
@@ -388,6 +388,11 @@ void TrainJob::prepare() {
         b.arc_dst = tb.arc_dst.data();
         b.arc_id = tb.arc_id.data();
         ok(cml_add_trellises(ctx, &b));
+        uint64_t cyc = 0, back = 0;
+        ok(cml_cyclic_stats(ctx, &cyc, &back));
+        if (cyc)  // derivations.h:726-728 (the reference prints this once per example)
+          std::cerr << "Warning: at least one cycle in derivations for " << cyc << " example(s) (" << back
+                    << " back edges).  Forward/backward will miss some paths.\n";
       }
       res.trellis_arcs = tb.arc_dst.size();
       res.examples = tb.ex_states.size();

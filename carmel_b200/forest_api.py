@@ -49,7 +49,7 @@ def _lib():
         lib.cml_forests_set_stream.argtypes = [_vp, _vp]
         lib.cml_forests_set_layout.argtypes = [_vp, C.c_int]
         lib.cml_forests_layout_stats.argtypes = [_vp] + [_u64p] * 5
-        lib.cml_forests_level_stats.argtypes = [_vp] + [_u64p] * 5
+        lib.cml_forests_level_stats.argtypes = [_vp] + [_u64p] * 6
         lib.cml_forests_launch_count.argtypes = [_vp]
         lib.cml_forests_launch_count.restype = C.c_uint64
         lib.cml_forests_set_rules.argtypes = [_vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
@@ -131,9 +131,10 @@ class Forests:
         return dict(zip(("tile_forests", "tiles", "steps", "padded_steps", "padded_rows"), (x.value for x in v)))
 
     def level_stats(self) -> dict:
-        v = [C.c_uint64() for _ in range(5)]
+        v = [C.c_uint64() for _ in range(6)]
         self._ok(self.lib.cml_forests_level_stats(self.h, *[C.byref(x) for x in v]))
-        return dict(zip(("level_forests", "level_tiles", "level_nodes", "level_links", "max_tile_nodes"), (x.value for x in v)))
+        return dict(zip(("level_forests", "level_tiles", "level_nodes", "level_links", "max_tile_nodes", "warp_tiles"),
+                        (x.value for x in v)))
 
     def set_rules(self, rulespace: int, group_off, group_members):
         go, gm = _arr(group_off, np.uint64), _arr(group_members, np.uint64)

@@ -33,7 +33,7 @@ enum cml_status {
   CML_ERR_ARG = -1,    /* bad argument / inconsistent sizes */
   CML_ERR_CUDA = -2,   /* CUDA runtime error or no usable device */
   CML_ERR_STATE = -3,  /* call order violated (e.g. estimate before set_model) */
-  CML_ERR_CYCLE = -4,  /* derivation lattice has a cycle (reference only warns: derivations.h:726-728) */
+  CML_ERR_CYCLE = -4,  /* a forest's back references form a cycle; Gibbs sampling over a lattice with a cycle */
   CML_ERR_NODERIV = -5, /* no training example had a derivation (train.cc:249-252) */
   CML_ERR_NOT_DENSE = -6 /* cml_add_sequences: the arc table has no transition x emission factorisation
                             (or too many states); nothing was changed, use cml_add_trellises instead */
@@ -136,7 +136,11 @@ int cml_restore_params(cml_ctx* ctx, int slot);
  *   arc_off    [sum(ex_states) + n_ex] per example a CSR row-offset array of ex_states+1 entries,
  *              offsets local to the example's first arc
  *   arc_dst, arc_id [total arcs] destination state id and arc-table id (GraphArc.dest / .data)
- * Returns CML_ERR_CYCLE if a lattice has a cycle. */
+ * A lattice with a cycle (an *e*:*e* loop in the transducer) is accepted like the reference accepts it
+ * (derivations.h:722-729 "Warning: at least one cycle in derivations ... Forward/backward will miss some paths"):
+ * it is walked in the reference's DFS order by a sequential kernel, back-edge contributions arriving after their
+ * destination has been propagated, so likelihood and counts equal the reference's; cml_cyclic_stats reports how many
+ * such lattices / back edges are resident (the caller prints the warning).  Only the Gibbs sampler refuses them. */
 typedef struct cml_trellis_batch {
   uint64_t n_ex;
   const uint32_t* ex_states;
@@ -189,6 +193,7 @@ typedef struct cml_built_trellises {
 int cml_build_trellises(cml_ctx* ctx, const cml_wfst_view* x, const cml_corpus_view* c, cml_built_trellises** out);
 void cml_free_built_trellises(cml_built_trellises* b);
 int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs, uint64_t* n_levels);
+int cml_cyclic_stats(cml_ctx* ctx, uint64_t* n_examples, uint64_t* n_back_edges);
 /* how the resident lattices are stored: examples / arcs / padded records in the level-sliced ELL layout
  * (throughput kernel) and examples in the layered-CSR layout (general kernels) */
 int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,
@@ -381,7 +386,7 @@ int cml_reduce_buffer_read(cml_ctx* ctx, double* dst, uint64_t n);
  * transducers (composed left to right).  Extra long options of this implementation: --float
  * (fp32 scores), --scaled (scaled linear space), --gpu=n, --shard=r/N (this process keeps block r of
  * N of the corpus on its GPU; needs an all-reduce hook), --history=file, --dump-trellis=file,
- * --device-build / --host-build (where the derivation lattices are constructed; default: GPU for >= 8,192 examples).
+ * --device-build / --host-build (where the derivation lattices are constructed; default: host threads).
  * Log lines go to stderr in the reference's format (train.cc:587-627). */
 typedef struct cml_job cml_job;
 typedef void (*cml_allreduce_fn)(void* user, void* device_ptr, uint64_t n_doubles); /* in-place fp64 sum */
@@ -448,9 +453,10 @@ int cml_forests_set_stream(cml_forests* f, void* cuda_stream);
 enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1, CML_FOREST_LAYOUT_THREAD = 2, CML_FOREST_LAYOUT_LEVEL = 3 };
 int cml_forests_set_layout(cml_forests* f, int layout);
 /* level-synchronous tiles resident (CML_FOREST_LAYOUT_LEVEL, the AUTO choice for >= 256 forests that fit in shared
- * memory): forests, tiles (= CTAs per E-step), nodes, links, nodes of the largest tile */
+ * memory): forests, tiles, nodes, links, node capacity of the largest tile, and how many of the tiles are WARP tiles
+ * (one warp walks the tile; the other tiles take a whole CTA) */
 int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
-                            uint64_t* max_tile_nodes);
+                            uint64_t* max_tile_nodes, uint64_t* warp_tiles);
 /* thread-per-forest tiles resident: forests in tiles, tiles, real steps, padded steps, padded value rows x 32 */
 int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, uint64_t* tiles, uint64_t* steps, uint64_t* padded_steps,
                              uint64_t* padded_rows);

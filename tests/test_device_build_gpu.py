@@ -1,8 +1,8 @@
 """Device-side lattice construction (cml_build_trellises / csrc/cml_build.cu): the GPU builder's dump
 must be byte-identical to the CPU oracle's restatement of derivations::compute (derivations.h:479-704) -- state ids in
 DFS pre-order after pruning, stored arc order, arc-table ids -- on the reference's fixtures, random transducers with
-epsilons, random cascades, under tiny first-round capacities (every example overflows and is retried), and at a corpus
-size where the product picks the GPU builder by itself; the host builder is the second implementation beside it."""
+epsilons, random cascades, under tiny first-round capacities (every example overflows and is retried), and through
+the job API at 9,000 sentences; the host builder is the second implementation beside it."""
 import filecmp
 import os
 
@@ -70,9 +70,9 @@ def test_random_transducers_bit_exact(oracle_bin, cli, tmp_path, seed):
 def test_random_cascades_bit_exact(oracle_bin, cli, tmp_path, seed):
     rng = np.random.default_rng(20260201 + seed)
     a, ins, mids, arcs_a = random_wfst(rng, n_states=3, n_in=2, n_out=2, eps_rate=0.2, lock_rate=0.1, tie_rate=0.0,
-                                       out_prefix="m")
+                                       in_prefix="i", out_prefix="m")
     b, _, outs, arcs_b = random_wfst(rng, n_states=3, n_in=2, n_out=2, eps_rate=0.2, lock_rate=0.1, tie_rate=0.0,
-                                     in_syms=mids)
+                                     in_prefix="m", out_prefix="z")
     lines = []
     for _ in range(24):
         li, lo = int(rng.integers(0, 4)), int(rng.integers(0, 4))
@@ -85,24 +85,23 @@ def test_random_cascades_bit_exact(oracle_bin, cli, tmp_path, seed):
     _three_way(oracle_bin, cli, ["--train-cascade", c, fa, fb], str(tmp_path))
 
 
-def test_auto_selection_and_training_at_scale(native_lib, oracle_bin, tmp_path):
-    """>= 8,192 examples: the product builds the lattices on the GPU by itself; per-example ln P of the lattice path
-    equals the oracle's on the first examples and the whole-corpus likelihood equals the host-built run's."""
+def test_training_on_device_built_lattices(native_lib, oracle_bin, tmp_path):
+    """--device-build through the job API: the E-step over GPU-built lattices gives the host-built run's likelihood and
+    counts (9,000 sentences: many walks per persistent worker)."""
     import carmel_b200 as cb
     from carmel_b200 import synth
     w = synth.write_hmm(os.path.join(str(tmp_path), "h"), n_sent=9000, seed=7)
     res = {}
-    for how in ("--host-build", None):
-        argv = ["-q", "--scaled", "--no-dense", *([how] if how else []), *w["argv"]]
+    for how in ("--host-build", "--device-build"):
+        argv = ["-q", "--scaled", "--no-dense", how, *w["argv"]]
         job = cb.Job(argv)
         ctx = job.prepare()
         st = job.stats()
         r = ctx.estimate()
         res[how] = (st, r.sum_ln_p, ctx.counts().copy())
         job.close()
-    assert res["--host-build"][0]["device_build_s"] == 0
-    assert res[None][0]["device_build_s"] > 0
-    assert res[None][0]["trellis_arcs"] == res["--host-build"][0]["trellis_arcs"]
-    assert res[None][0]["trellis_states"] == res["--host-build"][0]["trellis_states"]
-    assert abs(res[None][1] - res["--host-build"][1]) <= 1e-12 * abs(res[None][1])
-    np.testing.assert_allclose(res[None][2], res["--host-build"][2], rtol=1e-9, atol=1e-300)
+    h, g = res["--host-build"], res["--device-build"]
+    assert h[0]["device_build_s"] == 0 and g[0]["device_build_s"] > 0
+    assert g[0]["trellis_arcs"] == h[0]["trellis_arcs"] and g[0]["trellis_states"] == h[0]["trellis_states"]
+    assert abs(g[1] - h[1]) <= 1e-12 * abs(h[1])
+    np.testing.assert_allclose(g[2], h[2], rtol=1e-9, atol=1e-300)

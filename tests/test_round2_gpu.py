@@ -348,3 +348,38 @@ def test_fem_export_matches_oracle_and_feeds_the_forest_kernels(cli, oracle_bin,
     assert rc == 0, e2
     a, b = read_history(f"{d}/h1"), read_history(f"{d}/h2")
     assert len(a) == len(b) == 1 and abs(a[0][1] - b[0][1]) <= 1e-9 * abs(a[0][1])
+
+
+CYCLIC_FST = """qf
+(q0 (q0 "a" "x" 0.5))
+(q0 (q0 "a" "y" 0.2))
+(q0 (q1 *e* *e* 0.3))
+(q1 (q0 *e* *e* 0.4))
+(q1 (q1 "a" "y" 0.3))
+(q1 (qf "b" "z" 0.6))
+"""
+
+
+@pytest.mark.parametrize("mode,rel", [([], 1e-6), (["--scaled"], 1e-6), (["--float", "--scaled"], 1e-4)])
+def test_cyclic_lattices_follow_the_reference_order(native_lib, oracle_bin, tmp_path, mode, rel):
+    """An *e*:*e* loop in the transducer puts a cycle into every derivation lattice.  The reference warns ("Forward/
+    backward will miss some paths", derivations.h:722-729) and walks the states once in its DFS order, back-edge
+    contributions arriving late (graph.h:241-288,391-402); the oracle restates that walk.  The GPU path (k_fb_cyclic)
+    must give the same likelihood trajectory and weights, beside ordinary lattices in the same batch."""
+    from carmel_b200 import CLI_PATH
+    from helpers import compare_wfst_text, read_history, run
+    f, c = os.path.join(str(tmp_path), "c.fst"), os.path.join(str(tmp_path), "c.data")
+    open(f, "w").write(CYCLIC_FST)
+    open(c, "w").write('"a" "a" "b"\n"x" "y" "z"\n"a" "b"\n"y" "z"\n"b"\n"z"\n"a" "a" "a" "b"\n"y" "x" "y" "z"\n')
+    rc, oout, oerr = run(oracle_bin, ["-t", "-M", "6", f"--history={tmp_path}/h.o", c, f])
+    assert rc == 0, oerr
+    rc, out, err = run(CLI_PATH, ["-t", "-M", "6", *mode, f"--history={tmp_path}/h.p", c, f])
+    assert rc == 0, err
+    assert "Warning: at least one cycle in derivations for 4 example(s)" in err
+    assert "Forward/backward will miss some paths." in err
+    ho, hp = read_history(f"{tmp_path}/h.o"), read_history(f"{tmp_path}/h.p")
+    assert len(ho) == len(hp) and len(ho) >= 3
+    for a, b in zip(hp, ho):
+        assert a[0] == b[0]
+        assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (a, b)
+    compare_wfst_text(out, oout, rel * 20)
