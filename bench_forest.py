@@ -238,8 +238,8 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (measured_traffic("k_forest_level", tot_local["hyperedges"]) if lay["level_forests"] else
                                 measured_traffic("k_forest_thread", tot_local["hyperedges"]) if lay["tile_forests"] else None) if a.precision == 32 else None,
-                    "peak_source": which, "kernel": ("k_forest_level (CTA per run of forests, nodes height-major, values in shared memory, "
-                                                     "16 B/node + 2 B/link streamed per pass)" if lay["level_forests"] else
+                    "peak_source": which, "kernel": ("k_forest_level (a 128-thread CTA per run of forests, 16 CTAs per SM, nodes height-major, values in "
+                                                     "shared memory, 8 B/node + 2 B/link streamed per pass)" if lay["level_forests"] else
                                                      "k_forest_thread" if lay["tile_forests"] else "k_forest_warp/k_forest_cta") +
                     f" (inside + outside + counts, {k_ms[0][1]} launch(es) per iteration)",
                     "kernel_ms": kms, "algorithmic_bytes_per_hyperedge": bytes_step / max(1, tot_local["hyperedges"]),

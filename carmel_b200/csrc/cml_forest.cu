@@ -503,7 +503,8 @@ struct __align__(16) LevelTile {
 };
 struct LevelArgs {
   const LevelTile* tiles;
-  const uint32_t* label;
+  const uint32_t* label;      // inside pass: rule id (0 = OR)
+  const uint32_t* label_out;  // outside pass: rule id, or bit 31 | replica row of a hot rule
   const uint32_t* coff;
   const uint32_t* poff;
   const uint16_t* child;
@@ -519,7 +520,8 @@ struct LevelArgs {
   double* ln_inside;
   int pf;                   // L2 prefetch distance in levels (0 = off)
   uint32_t n_tiles;         // tiles of this launch (tiles points at the first)
-  uint32_t cap;             // G = 32: value slots per warp
+  uint32_t cap;             // value slots of the largest tile
+  uint32_t lvl_smem_off;    // byte offset of the level tables in dynamic shared memory (behind the values)
 };
 __device__ __forceinline__ void f_prefetch_l2(const void* base, size_t b0, size_t b1) {  // bytes [b0, b1) behind base
   const uintptr_t s = ((uintptr_t)base + b0) & ~(uintptr_t)15, e = ((uintptr_t)base + b1 + 15) & ~(uintptr_t)15;
@@ -538,9 +540,9 @@ __device__ __forceinline__ double f_log<double>(double x) { return log(x); }
 template <typename Real, int NTHR, int MINB, int U>
 __global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
   extern __shared__ __align__(16) unsigned char smem_lv[];
-  __shared__ uint32_t s_lvl[3 * (kLvlMaxLevels + 1)];
   const uint32_t grp = blockIdx.x;
   Real* __restrict__ val = reinterpret_cast<Real*>(smem_lv);
+  uint32_t* __restrict__ s_lvl = reinterpret_cast<uint32_t*>(smem_lv + A.lvl_smem_off);  // 3 x (levels + 1) words
   const LevelTile T = A.tiles[grp];
   const uint32_t tid = threadIdx.x, NT = blockDim.x, nl = T.n_levels;
   for (uint32_t k = tid; k < 3 * (nl + 1); k += NT) s_lvl[k] = __ldg(A.lvl + T.lvl_base + k);
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
   const uint32_t* __restrict__ s_cl = s_lvl + (nl + 1);
   const uint32_t* __restrict__ s_pl = s_lvl + 2 * (nl + 1);
   const uint32_t* __restrict__ label = A.label + T.node_base;
+  const uint32_t* __restrict__ label_o = A.label_out + T.node_base;
   const uint32_t* __restrict__ coff = A.coff + T.node_base;
   const uint32_t* __restrict__ poff = A.poff + T.node_base;
   const uint16_t* __restrict__ child = A.child + T.link_base;
@@ -563,7 +566,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
     f_prefetch_l2(child, 2ull * s_cl[L], 2ull * s_cl[L + 1]);
   };
   auto prefetch_out = [&](uint32_t L) {
-    f_prefetch_l2(label, 4ull * s_node[L], 4ull * s_node[L + 1]);
+    f_prefetch_l2(label_o, 4ull * s_node[L], 4ull * s_node[L + 1]);
     f_prefetch_l2(poff, 4ull * s_node[L], 4ull * s_node[L + 1] + 4);
     f_prefetch_l2(par, 2ull * s_pl[L], 2ull * s_pl[L + 1]);
   };
@@ -655,16 +658,15 @@ __global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
       for (int k = 0; k < U; ++k) {
         const uint32_t j = j0 + k * NT;
         const bool ok = j < n1;
-        lab[k] = ok ? __ldg(label + j) : 0u;
+        lab[k] = ok ? __ldg(label_o + j) : 0u;
         k0[k] = ok ? __ldg(poff + j) : 0u;
         k1[k] = ok ? __ldg(poff + j + 1) : 0u;
       }
-      uint32_t pa[U][kLvlPars], hix[U];
+      uint32_t pa[U][kLvlPars];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
 #pragma unroll
         for (int q = 0; q < kLvlPars; ++q) pa[k][q] = (k0[k] + q < k1[k]) ? (uint32_t)__ldg(par + k0[k] + q) : 0u;
-        hix[k] = (lab[k] & kHotBit) ? __ldg(&A.hot_index[lab[k] & ~kHotBit]) : 0u;
       }
 #pragma unroll
       for (int k = 0; k < U; ++k) {
@@ -689,10 +691,10 @@ __global__ void __launch_bounds__(NTHR, MINB) k_forest_level(LevelArgs A) {
             if ((uint32_t)q < np) add(pa[k][q]);
           for (uint32_t kk = k0[k] + kLvlPars; kk < k1[k]; ++kk) add(__ldg(par + kk));
         }
-        if (lab[k] & ~kHotBit) {
+        if (lab[k]) {  // an AND node (the label of a hot rule is bit 31 | its replica row, never 0)
           if (g > 0) {
             if (lab[k] & kHotBit)
-              atomicAdd(A.hot + (size_t)replica * A.n_hot + hix[k], (double)g);
+              atomicAdd(A.hot + (size_t)replica * A.n_hot + (lab[k] & ~kHotBit), (double)g);
             else
               atomicAdd(A.counts + lab[k], (double)g);
           }
@@ -721,6 +723,16 @@ __global__ void k_forest_mark_hot(uint64_t n, uint32_t* __restrict__ label, cons
   if (i >= n) return;
   const uint32_t lab = label[i] & ~kHotBit;
   label[i] = (lab && hot_index[lab] != 0xFFFFFFFFu) ? (lab | kHotBit) : lab;
+}
+// level tiles: the outside pass's label stream carries the replica ROW of a hot rule instead of its id (bit 31 set), so
+// the count of a hot rule needs no lookup; derived from the inside pass's labels whenever the hot set changes
+__global__ void k_forest_label_out(uint64_t n, const uint32_t* __restrict__ label, const uint32_t* __restrict__ hot_index,
+                                   uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t lab = label[i] & ~kHotBit;
+  const uint32_t h = lab ? hot_index[lab] : 0xFFFFFFFFu;
+  out[i] = h != 0xFFFFFFFFu ? (h | kHotBit) : lab;
 }
 __global__ void k_forest_fold(uint32_t n_hot, const uint32_t* __restrict__ hot_rule, const double* __restrict__ hot,
                               double* __restrict__ counts) {
@@ -901,11 +913,11 @@ struct ForestBatch {
   uint32_t t_stack_rows = 2;  // shared-memory rows per lane for the value / path stacks
   DevArray<unsigned char> t_in, t_ga, t_vout;
   // level-synchronous tiles
-  uint32_t n_ltiles = 0, lt_max_nodes = 0;  // all level tiles; nodes of the largest CTA tile
-  uint32_t n_wtiles = 0, lt_warp_cap = 0;   // the first n_wtiles tiles are WARP tiles of <= lt_warp_cap nodes
+  uint32_t n_ltiles = 0, lt_max_nodes = 0, lt_max_levels = 0;  // level tiles; nodes / levels of the largest tile
+  uint32_t n_stiles = 0, lt_small_nodes = 0;  // the first n_stiles tiles are SMALL tiles (largest: lt_small_nodes nodes)
   uint64_t lt_forests = 0, lt_nodes = 0, lt_links = 0;
   DevArray<LevelTile> ltiles;
-  DevArray<uint32_t> lt_label, lt_coff, lt_poff, lt_lvl, lt_forest;
+  DevArray<uint32_t> lt_label, lt_label_out, lt_coff, lt_poff, lt_lvl, lt_forest;
   DevArray<uint16_t> lt_child, lt_par, lt_root;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n_kernels = 0;
@@ -1067,7 +1079,7 @@ extern "C" int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, 
 }
 
 extern "C" int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
-                                       uint64_t* max_tile_nodes, uint64_t* warp_tiles) {
+                                       uint64_t* max_tile_nodes, uint64_t* small_tiles) {
   if (!f) return CML_ERR_ARG;
   uint64_t a = 0, b = 0, c = 0, d = 0, e = 0, w = 0;
   for (auto const& bt : f->batches) {
@@ -1075,10 +1087,10 @@ extern "C" int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64
     b += bt->n_ltiles;
     c += bt->lt_nodes;
     d += bt->lt_links;
-    e = std::max<uint64_t>(e, std::max(bt->lt_max_nodes, bt->n_wtiles ? bt->lt_warp_cap : 0u));
-    w += bt->n_wtiles;
+    e = std::max<uint64_t>(e, std::max(bt->lt_max_nodes, bt->lt_small_nodes));
+    w += bt->n_stiles;
   }
-  if (warp_tiles) *warp_tiles = w;
+  if (small_tiles) *small_tiles = w;
   if (forests) *forests = a;
   if (tiles) *tiles = b;
   if (nodes) *nodes = c;
@@ -1291,43 +1303,55 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
   // level-synchronous tiles (k_forest_level): runs of consecutive forests whose nodes fit in a CTA's shared memory
   std::vector<uint32_t> lv_forests;           // forests in level tiles, tile-major (corpus order)
   std::vector<uint32_t> lv_first;             // per tile: first entry in lv_forests (+ sentinel)
-  uint32_t lv_n_warp_tiles = 0, lv_warp_cap = 0;  // the first tiles are WARP tiles (<= lv_warp_cap nodes each)
+  // two tile classes: SMALL tiles for the launch shape 128 threads x 16 CTAs per SM (full occupancy, 16 independent
+  // barrier domains per SM: measured best, profiles/round2_F_*), LARGE tiles (512 x 2) for forests that do not fit a
+  // small tile's shared memory.  Tiles [0, lv_n_small) are small.
+  uint32_t lv_n_small = 0;
   {
-    uint64_t min_forests = 256, smem_kb = 100;
+    uint64_t min_forests = 256, kb_small = 12, kb_large = 100;  // (16 x (12 KB + tables + 1 KB reserved) fit one SM)
     if (const char* e = getenv("CML_FOREST_LEVEL_MIN_FORESTS")) min_forests = std::strtoull(e, nullptr, 10);
-    if (const char* e = getenv("CML_FOREST_LEVEL_SMEM_KB")) smem_kb = std::strtoull(e, nullptr, 10);
-    smem_kb = std::min<uint64_t>(smem_kb, f->smem_optin ? (f->smem_optin - 4096) / 1024 : 100);
-    const uint64_t cap = std::min<uint64_t>(kLvlMaxNodes, smem_kb * 1024 / real_bytes);
-    uint64_t cand = 0, cand_nodes = 0;
+    if (const char* e = getenv("CML_FOREST_LEVEL_SMEM_KB")) kb_small = std::strtoull(e, nullptr, 10);  // (0: no small tiles)
+    if (const char* e = getenv("CML_FOREST_LEVEL_LARGE_KB")) kb_large = std::strtoull(e, nullptr, 10);
+    kb_large = std::min<uint64_t>(kb_large, f->smem_optin ? (f->smem_optin - 4096) / 1024 : 100);
+    kb_small = std::min(kb_small, kb_large);
+    uint32_t max_lev = 1;  // the level tables of a tile (3 x (levels + 1) words) share the CTA's shared memory
     for (uint64_t i = 0; i < nf; ++i)
-      if (ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels) {
-        ++cand;
-        cand_nodes += ff[i].n_real;
-      }
+      if (ff[i].n_levels <= kLvlMaxLevels) max_lev = std::max(max_lev, ff[i].n_levels);
+    const uint64_t lvl_bytes = (12ull * (max_lev + 1) + 15) & ~15ull;
+    auto cap_of = [&](uint64_t kb) {
+      return std::min<uint64_t>(kLvlMaxNodes, (kb * 1024 - std::min<uint64_t>(lvl_bytes, kb * 512)) / real_bytes);
+    };
+    const uint64_t cap_small = kb_small ? cap_of(kb_small) : 0, cap = cap_of(kb_large);
+    uint64_t cand = 0;
+    for (uint64_t i = 0; i < nf; ++i) cand += ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels;
     const bool use = f->layout == CML_FOREST_LAYOUT_LEVEL || (f->layout == CML_FOREST_LAYOUT_AUTO && cand >= min_forests);
     if (use && cand) {
       auto eligible = [&](uint64_t i) { return ff[i].n_real <= cap && ff[i].n_levels <= kLvlMaxLevels; };
-      uint64_t cur = 0;
-      // small corpora: smaller tiles so that there are a few CTAs per SM
-      uint64_t rest_nodes = 0;
-      for (uint64_t i = 0; i < nf; ++i)
-        if (eligible(i) && !in_level[i]) rest_nodes += ff[i].n_real;
-      uint64_t target = std::max<uint64_t>(2048, rest_nodes / (4ull * (uint64_t)f->sm_count));
-      if (const char* e = getenv("CML_FOREST_LEVEL_TILE_NODES")) target = std::strtoull(e, nullptr, 10);
-      target = std::min(target, cap);
-      cur = 0;
-      bool first_cta = true;
-      for (uint64_t i = 0; i < nf; ++i) {
-        if (!eligible(i) || in_level[i]) continue;
-        in_level[i] = 1;
-        if (first_cta || cur + ff[i].n_real > target) {
-          lv_first.push_back((uint32_t)lv_forests.size());
-          cur = 0;
-          first_cta = false;
+      auto pack = [&](uint64_t lo, uint64_t hi, uint64_t tile_cap) {  // forests of lo < n_real <= hi, corpus order
+        uint64_t nodes = 0;
+        for (uint64_t i = 0; i < nf; ++i)
+          if (eligible(i) && ff[i].n_real > lo && ff[i].n_real <= hi) nodes += ff[i].n_real;
+        // small corpora: smaller tiles so that there are a few CTAs per SM
+        uint64_t target = std::max<uint64_t>(1024, nodes / (8ull * (uint64_t)f->sm_count));
+        if (const char* e = getenv("CML_FOREST_LEVEL_TILE_NODES")) target = std::strtoull(e, nullptr, 10);
+        target = std::min(target, tile_cap);
+        uint64_t cur = 0;
+        bool first = true;
+        for (uint64_t i = 0; i < nf; ++i) {
+          if (!eligible(i) || !(ff[i].n_real > lo && ff[i].n_real <= hi)) continue;
+          in_level[i] = 1;
+          if (first || cur + ff[i].n_real > std::max<uint64_t>(target, ff[i].n_real)) {
+            lv_first.push_back((uint32_t)lv_forests.size());
+            cur = 0;
+            first = false;
+          }
+          cur += ff[i].n_real;
+          lv_forests.push_back((uint32_t)i);
         }
-        cur += ff[i].n_real;
-        lv_forests.push_back((uint32_t)i);
-      }
+      };
+      if (cap_small) pack(0, cap_small, cap_small);
+      lv_n_small = (uint32_t)lv_first.size();
+      pack(cap_small, cap, cap);
       lv_first.push_back((uint32_t)lv_forests.size());
     }
   }
@@ -1617,13 +1641,16 @@ extern "C" int cml_forests_add(cml_forests* f, const cml_forest_batch* b) {
       nb += nn + 1;
       lb += nk;
       vb += 3ull * (nlv + 1);
-      if (t >= lv_n_warp_tiles) bt->lt_max_nodes = std::max(bt->lt_max_nodes, nn);
+      if (t < lv_n_small)
+        bt->lt_small_nodes = std::max(bt->lt_small_nodes, nn);
+      else
+        bt->lt_max_nodes = std::max(bt->lt_max_nodes, nn);
+      bt->lt_max_levels = std::max(bt->lt_max_levels, nlv);
       bt->lt_nodes += nn;
       bt->lt_links += nk;
     }
     bt->n_ltiles = (uint32_t)n_lt;
-    bt->n_wtiles = lv_n_warp_tiles;
-    bt->lt_warp_cap = lv_warp_cap;
+    bt->n_stiles = lv_n_small;
     bt->lt_forests = lv_forests.size();
     lt_label.assign(nb + 16, 0);
     lt_coff.assign(nb + 16, 0);
@@ -1850,7 +1877,9 @@ static int forest_rebuild_hot(cml_forests* f) {
     k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
     ++f->launches;
     if (bt->n_ltiles) {
-      k_forest_mark_hot<<<f_cdiv(bt->lt_label.n, 256), 256, 0, f->stream>>>(bt->lt_label.n, bt->lt_label.p, f->hot_index.p);
+      if (!bt->lt_label_out.p) CML_CUDA(bt->lt_label_out.alloc(bt->lt_label.n));
+      k_forest_label_out<<<f_cdiv(bt->lt_label.n, 256), 256, 0, f->stream>>>(bt->lt_label.n, bt->lt_label.p, f->hot_index.p,
+                                                                          bt->lt_label_out.p);
       ++f->launches;
     }
     if (bt->n_tiles) {
@@ -1911,6 +1940,7 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     LevelArgs L{};
     L.tiles = bt.ltiles.p;
     L.label = bt.lt_label.p;
+    L.label_out = bt.lt_label_out.p;
     L.coff = bt.lt_coff.p;
     L.poff = bt.lt_poff.p;
     L.child = bt.lt_child.p;
@@ -1926,30 +1956,44 @@ static int forest_launch(cml_forests* f, ForestBatch& bt) {
     L.ln_inside = bt.ln_inside.p;
     L.pf = 2;
     if (const char* e = getenv("CML_FOREST_LEVEL_PREFETCH")) L.pf = std::max(0, atoi(e));
-    const size_t lsmem = ((size_t)bt.lt_max_nodes * sizeof(Real) + 15) & ~(size_t)15;
-    L.n_tiles = bt.n_ltiles;
-    L.cap = bt.lt_max_nodes;
-    // launch shapes (threads x resident CTAs per SM): the tile capacity (CML_FOREST_LEVEL_SMEM_KB at add time) decides how
-    // many CTAs really fit; 0 = 512 x 2 (default), 1 = 384 x 3, 2 = 256 x 4, 3 = 256 x 6 with 2 nodes in flight
-    int variant = 0;
+    // launch shapes (threads x resident CTAs per SM, nodes in flight per thread).  Small tiles: 128 x 16 x 1 by default
+    // (CML_FOREST_LEVEL_VARIANT picks another shape for measurements; the tile capacity CML_FOREST_LEVEL_SMEM_KB at add
+    // time decides how many CTAs really fit); large tiles: 512 x 2 x 4.
+    int variant = 6;
     if (const char* e = getenv("CML_FOREST_LEVEL_VARIANT")) variant = atoi(e);
-    auto go = [&](auto kern, int threads) -> int {
+    auto go = [&](auto kern, int threads, uint32_t first, uint32_t n, uint32_t max_nodes) -> int {
+      const size_t vsmem = ((size_t)max_nodes * sizeof(Real) + 15) & ~(size_t)15;
+      const size_t lsmem = vsmem + ((12 * ((size_t)bt.lt_max_levels + 1) + 15) & ~(size_t)15);
+      LevelArgs X = L;
+      X.tiles = bt.ltiles.p + first;
+      X.n_tiles = n;
+      X.cap = max_nodes;
+      X.lvl_smem_off = (uint32_t)vsmem;
       CML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(lsmem, 48 * 1024)));
-      kern<<<bt.n_ltiles, threads, lsmem, f->stream>>>(L);
+      kern<<<n, threads, lsmem, f->stream>>>(X);
+      ++f->launches;
+      ++bt.n_kernels;
       return CML_OK;
     };
-    int rc;
-    if (variant == 1)
-      rc = go(k_forest_level<Real, 384, 3, 4>, 384);
-    else if (variant == 2)
-      rc = go(k_forest_level<Real, 256, 4, 4>, 256);
-    else if (variant == 3)
-      rc = go(k_forest_level<Real, 256, 6, 2>, 256);
-    else
-      rc = go(k_forest_level<Real, 512, 2, 4>, 512);
-    if (rc) return rc;
-    ++f->launches;
-    ++bt.n_kernels;
+    if (bt.n_stiles) {
+      const uint32_t n = bt.n_stiles, mx = bt.lt_small_nodes;
+      int rc;
+      switch (variant) {
+        case 0: rc = go(k_forest_level<Real, 512, 2, 4>, 512, 0, n, mx); break;
+        case 1: rc = go(k_forest_level<Real, 384, 3, 4>, 384, 0, n, mx); break;
+        case 2: rc = go(k_forest_level<Real, 256, 4, 4>, 256, 0, n, mx); break;
+        case 3: rc = go(k_forest_level<Real, 256, 6, 2>, 256, 0, n, mx); break;
+        case 4: rc = go(k_forest_level<Real, 128, 12, 2>, 128, 0, n, mx); break;
+        case 5: rc = go(k_forest_level<Real, 256, 8, 1>, 256, 0, n, mx); break;
+        case 7: rc = go(k_forest_level<Real, 64, 24, 2>, 64, 0, n, mx); break;
+        default: rc = go(k_forest_level<Real, 128, 16, 1>, 128, 0, n, mx);
+      }
+      if (rc) return rc;
+    }
+    if (bt.n_ltiles > bt.n_stiles) {
+      const int rc = go(k_forest_level<Real, 512, 2, 4>, 512, bt.n_stiles, bt.n_ltiles - bt.n_stiles, bt.lt_max_nodes);
+      if (rc) return rc;
+    }
   }
   for (int c = 0; c < kNWarpCls; ++c) {
     const uint32_t n = bt.cls_begin[c + 1] - bt.cls_begin[c];

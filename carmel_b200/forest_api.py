@@ -133,7 +133,7 @@ class Forests:
     def level_stats(self) -> dict:
         v = [C.c_uint64() for _ in range(6)]
         self._ok(self.lib.cml_forests_level_stats(self.h, *[C.byref(x) for x in v]))
-        return dict(zip(("level_forests", "level_tiles", "level_nodes", "level_links", "max_tile_nodes", "warp_tiles"),
+        return dict(zip(("level_forests", "level_tiles", "level_nodes", "level_links", "max_tile_nodes", "small_tiles"),
                         (x.value for x in v)))
 
     def set_rules(self, rulespace: int, group_off, group_members):

@@ -453,10 +453,10 @@ int cml_forests_set_stream(cml_forests* f, void* cuda_stream);
 enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1, CML_FOREST_LAYOUT_THREAD = 2, CML_FOREST_LAYOUT_LEVEL = 3 };
 int cml_forests_set_layout(cml_forests* f, int layout);
 /* level-synchronous tiles resident (CML_FOREST_LAYOUT_LEVEL, the AUTO choice for >= 256 forests that fit in shared
- * memory): forests, tiles, nodes, links, node capacity of the largest tile, and how many of the tiles are WARP tiles
- * (one warp walks the tile; the other tiles take a whole CTA) */
+ * memory): forests, tiles (= CTAs per E-step), nodes, links, nodes of the largest tile, and how many of the tiles are
+ * SMALL tiles (<= 13 KB of values: 128-thread CTAs, 16 per SM; the others are 512-thread CTAs with up to 100 KB) */
 int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
-                            uint64_t* max_tile_nodes, uint64_t* warp_tiles);
+                            uint64_t* max_tile_nodes, uint64_t* small_tiles);
 /* thread-per-forest tiles resident: forests in tiles, tiles, real steps, padded steps, padded value rows x 32 */
 int cml_forests_layout_stats(cml_forests* f, uint64_t* tile_forests, uint64_t* tiles, uint64_t* steps, uint64_t* padded_steps,
                              uint64_t* padded_rows);

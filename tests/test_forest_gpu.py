@@ -115,6 +115,22 @@ def test_random_forests_thread_layout_without_stacks(fem, forest_oracle_bin, tmp
 
 
 @pytest.mark.parametrize("mode,rel", MODES)
+@pytest.mark.parametrize("small_kb", ["0", "1"])
+def test_level_layout_large_tiles(fem, forest_oracle_bin, tmp_path, monkeypatch, mode, rel, small_kb):
+    """the level layout has two tile classes (128-thread CTAs for runs of forests that fit 13 KB of values, 512-thread
+    CTAs for larger forests); with the small class switched off (0) or shrunk to 1 KB the same corpus runs on the large
+    tiles, alone or mixed with small ones"""
+    monkeypatch.setenv("CML_FOREST_LEVEL_SMEM_KB", small_kb)
+    rng = np.random.default_rng(913)
+    d = str(tmp_path)
+    n_rules = 80
+    open(f"{d}/f", "w").write("\n".join(random_forest(rng, n_rules, depth=int(rng.integers(2, 9)), share=0.3) for _ in range(96)) + "\n")
+    open(f"{d}/n", "w").write(random_normgroups(rng, n_rules))
+    _compare(fem, forest_oracle_bin, tmp_path, ["-f", f"{d}/f", "-n", f"{d}/n", "-i", "4", "-u"], mode, rel,
+             check_index=False, layouts=("level",))
+
+
+@pytest.mark.parametrize("mode,rel", MODES)
 def test_deep_random_forests_thread_layout(fem, forest_oracle_bin, tmp_path, mode, rel):
     """deeper forests with many shared sub-forests: value stack and path stack several levels deep, back-reference
     links mixed with stack links"""
