@@ -1158,8 +1158,8 @@ extern "C" int cml_add_trellises(cml_ctx* ctx, const cml_trellis_batch* b) {
       lane_levels += T.n_levels;
     }
     const uint2 padrec = make_uint2(0u, 0u);  // arc class 0: the zero-weight padding class
-    h_lfw.assign((size_t)(fo + (cmlk::kLaneStages + 1) * U) * 32, padrec);  // + the prefetch tail
-    h_lbw.assign((size_t)(bo + (cmlk::kLaneStages + 1) * U) * 32, padrec);
+    h_lfw.assign((size_t)(fo + 2 * U) * 32, padrec);  // + the prefetch tail
+    h_lbw.assign((size_t)(bo + 2 * U) * 32, padrec);
     h_lvcls.assign((size_t)(lane_states + 2) * 32, 0u);  // state class 0: no state part (+ the prefetch tail)
     // phase B: fill
     tile_for([&](uint32_t t) {
@@ -1531,9 +1531,8 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     const size_t tbl_v = (size_t)L.n_v * (sizeof(Real) + 4);
     const bool ta = tbl_a <= 40 * 1024, tv = tbl_v <= 24 * 1024;
     int minb = 2;
-    if (const char* e = getenv("CML_LANE_MINB")) minb = atoi(e);  // tuning knob: 3 = register cap + 3-chunk ring for three resident blocks
-    const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real) +
-                        (size_t)kLaneWarps * cmlk::lane_stages(minb) * cmlk::kLaneU * 32 * sizeof(uint2) + (ta ? tbl_a : 0) + (tv ? tbl_v : 0);
+    if (const char* e = getenv("CML_LANE_MINB")) minb = atoi(e);  // tuning knob: 3 = register cap for three resident blocks (measured slower: profiles/round2_D)
+    const size_t smem = (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real) + (ta ? tbl_a : 0) + (tv ? tbl_v : 0);
     auto kern = minb >= 3 ? (ta ? (tv ? k_fb_lane<Real, true, true, 3> : k_fb_lane<Real, true, false, 3>)
                                 : (tv ? k_fb_lane<Real, false, true, 3> : k_fb_lane<Real, false, false, 3>))
                           : (ta ? (tv ? k_fb_lane<Real, true, true, 2> : k_fb_lane<Real, true, false, 2>)

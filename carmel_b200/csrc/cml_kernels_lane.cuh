@@ -14,11 +14,8 @@
 //     fully coalesced;
 //   * state scores of the last two levels live in a per-lane shared-memory ring (column = lane: conflict free,
 //     private to the lane, so there is no synchronisation of any kind in the sweep);
-//   * records run through a per-warp cp.async ring in shared memory, kLaneStages - 1 chunks (20 rows) ahead; a lane copies
-//     and reads only its own 8-byte slots, so cp.async.wait_group is the only synchronisation (the register-staged
-//     prefetch it replaces exposed the load latency: its rotating moves wait for the newest load -- 14 % of the samples
-//     sat on the first use of a record, profiles/round2_A_k_fb_lane.txt); weights are fetched one chunk ahead; per arc:
-//     1 LDS.64 record + 1 LDS weight + 1 LDS score + 1 FMA (forward), plus the count RED (backward);
+//   * records are prefetched two chunks ahead and weights one chunk ahead in registers; the only per-arc work is
+//     1 coalesced LDG.64 + 1 gather + 1 LDS + 1 FMA (forward), plus the count RED (backward);
 //   * power-of-two rescaling is per lane and per level: a level whose maximum leaves the exponent window changes
 //     the scale of the NEXT level (scores already stored are never rewritten).
 #pragma once
@@ -63,9 +60,6 @@ constexpr uint32_t kLaneLast = 0x80000000u, kLaneLevelEnd = 0x40000000u;
 constexpr int kLaneRing = 16;  // ring entries per lane: two levels of width <= 8
 constexpr int kLaneU = 4;      // rows per software-pipeline chunk
 constexpr int kLaneWarps = 8;
-constexpr int kLaneStages = 6;  // chunks of the record stream in the per-warp cp.async ring (kLaneStages - 1 in flight)
-// three resident blocks per SM (MINB = 3) leave room for a 3-chunk ring only
-constexpr int lane_stages(int minb) { return minb >= 3 ? 3 : kLaneStages; }
 
 // TA / TV: the arc-class / state-class tables (weight + slot code) are staged in shared memory.  Arc weights are
 // FACTORED (cml_device.cu "arc classes"): w(arc) = U[record's class] * V[class of the destination state]; the state
@@ -73,7 +67,6 @@ constexpr int lane_stages(int minb) { return minb >= 3 ? 3 : kLaneStages; }
 // MINB: resident blocks per SM the register allocation is capped for (2 = uncapped, ~86 registers; 3 caps at 80).
 template <typename Real, bool TA, bool TV, int MINB>
 static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneArgs A) {
-  constexpr int NST = lane_stages(MINB);
   extern __shared__ __align__(16) unsigned char smem_lane[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * kLaneWarps + wib;
@@ -82,23 +75,6 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
   const Real* __restrict__ vwt = reinterpret_cast<const Real*>(A.v_w);
   const uint32_t* __restrict__ vsl = A.v_slot;
   unsigned char* sp = smem_lane + (size_t)kLaneWarps * kLaneRing * 32 * sizeof(Real);
-  uint2* sring = reinterpret_cast<uint2*>(sp) + (size_t)wib * NST * kLaneU * 32 + lane;  // this lane's stream slots
-  const uint32_t sstr = (uint32_t)__cvta_generic_to_shared(sring);
-  sp += (size_t)kLaneWarps * NST * kLaneU * 32 * sizeof(uint2);
-  auto issue = [&](const uint2* __restrict__ base, uint32_t row) {  // queue chunk row / kLaneU (the arrays have a padded tail)
-    const uint32_t st = (row / kLaneU) % NST;
-#pragma unroll
-    for (int k = 0; k < kLaneU; ++k)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sstr + (uint32_t)((st * kLaneU + k) * 32) * 8u),
-                   "l"(base + (size_t)(row + k) * 32)
-                   : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-  auto fetch = [&](uint32_t row, uint2 (&r)[kLaneU]) {
-    const uint32_t st = (row / kLaneU) % NST;
-#pragma unroll
-    for (int k = 0; k < kLaneU; ++k) r[k] = sring[(st * kLaneU + k) * 32];
-  };
   if (TA) {
     Real* s_w = reinterpret_cast<Real*>(sp);
     uint32_t* s_sl = reinterpret_cast<uint32_t*>(s_w + A.n_a);
@@ -148,21 +124,21 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
     Real w0[kLaneU];
     const uint32_t R = T.rows_f;
 #pragma unroll
-    for (int c = 0; c < NST - 1; ++c) issue(fw, c * kLaneU);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 2) : "memory");  // chunk 0 has landed
-    fetch(0, r0);
+    for (int k = 0; k < kLaneU; ++k) r0[k] = fw[(size_t)k * 32];
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) w0[k] = w[r0[k].y];
+#pragma unroll
+    for (int k = 0; k < kLaneU; ++k) r1[k] = fw[(size_t)(kLaneU + k) * 32];
     // state parts: class of state s+1 two closes ahead, its weight one close ahead (the array has a padded tail)
     uint32_t vc_next = vcl[(size_t)2 * 32];
     Real vw_cur = vwt[vcl[(size_t)1 * 32]];
     for (uint32_t r = 0; r < R; r += kLaneU) {
       Real w1[kLaneU];
-      issue(fw, r + (NST - 1) * kLaneU);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 2) : "memory");  // chunk r / kLaneU + 1 has landed
-      fetch(r + kLaneU, r1);
+      uint2 r2[kLaneU];
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) w1[k] = w[r1[k].y];
+#pragma unroll
+      for (int k = 0; k < kLaneU; ++k) r2[k] = fw[(size_t)(r + 2 * kLaneU + k) * 32];  // (the array has a padded tail)
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) {
         const uint32_t x = r0[k].x;
@@ -195,9 +171,9 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
       for (int k = 0; k < kLaneU; ++k) {
         r0[k] = r1[k];
         w0[k] = w1[k];
+        r1[k] = r2[k];
       }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
   const bool live = ex != 0xFFFFFFFFu;
   if (live) A.ex_lnp[ex] = (afin > 0) ? log((double)afin) - (double)Efin * 0.69314718055994530942 : -CUDART_INF;
@@ -221,14 +197,14 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
     uint32_t q0[kLaneU];
     const uint32_t R = T.rows_b;
 #pragma unroll
-    for (int c = 0; c < NST - 1; ++c) issue(bw, c * kLaneU);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 2) : "memory");
-    fetch(0, r0);
+    for (int k = 0; k < kLaneU; ++k) r0[k] = bw[(size_t)k * 32];
 #pragma unroll
     for (int k = 0; k < kLaneU; ++k) {
       e0[k] = w[r0[k].y];
       q0[k] = wsl[r0[k].y];
     }
+#pragma unroll
+    for (int k = 0; k < kLaneU; ++k) r1[k] = bw[(size_t)(kLaneU + k) * 32];
     // state parts: class of state s-1 two closes ahead, weight / slot of the closing state one close ahead
     uint32_t vc_next = s >= 1 ? vcl[(size_t)(s - 1) * 32] : 0u;
     Real vw_cur;
@@ -241,14 +217,14 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
     for (uint32_t r = 0; r < R; r += kLaneU) {
       Real e1[kLaneU];
       uint32_t q1[kLaneU];
-      issue(bw, r + (NST - 1) * kLaneU);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 2) : "memory");
-      fetch(r + kLaneU, r1);
+      uint2 r2[kLaneU];
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) {
         e1[k] = w[r1[k].y];
         q1[k] = wsl[r1[k].y];
       }
+#pragma unroll
+      for (int k = 0; k < kLaneU; ++k) r2[k] = bw[(size_t)(r + 2 * kLaneU + k) * 32];
 #pragma unroll
       for (int k = 0; k < kLaneU; ++k) {
         const uint32_t x = r0[k].x;
@@ -291,9 +267,9 @@ static __global__ void __launch_bounds__(kLaneWarps * 32, MINB) k_fb_lane(LaneAr
         r0[k] = r1[k];
         e0[k] = e1[k];
         q0[k] = q1[k];
+        r1[k] = r2[k];
       }
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
 }
 

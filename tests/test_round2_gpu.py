@@ -212,7 +212,7 @@ def test_tensor_core_sweeps_selected_by_their_threshold(native_lib, oracle_bin, 
 
 
 def test_forest_tiles_selected_by_their_threshold(native_lib, forest_oracle_bin, tmp_path):
-    """8,300 forests, every one its own shape: the thread-per-forest tiles are chosen without --layout"""
+    """8,300 forests, every one its own shape: the level-synchronous tiles (k_forest_level) are chosen without --layout"""
     import bench_forest
     from carmel_b200 import synth
     from carmel_b200.forest_api import Forests
@@ -224,7 +224,9 @@ def test_forest_tiles_selected_by_their_threshold(native_lib, forest_oracle_bin,
     w0[gm] = -np.log(np.repeat(np.diff(go), np.diff(go)).astype(np.float64))
     F.set_params(w0)
     F.add(fs["node_off"], fs["next"], fs["label"], fs["backref"])
-    assert F.layout_stats()["tile_forests"] == 8300
+    assert F.layout_stats()["tile_forests"] == 0
+    lv = F.level_stats()
+    assert lv["level_forests"] == 8300 and lv["small_tiles"] == lv["level_tiles"] > 100, lv
     F.estimate()
     got = F.inside(8300)[:400]
     F.close()
