@@ -129,6 +129,7 @@ struct cml_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int sm_count = CML_SM_COUNT_FALLBACK;
+  uint32_t hot_copies = cmlk::kHotCopies;  // replicas of a hot count slot (power of two; CML_HOT_COPIES)
   size_t smem_optin = 0;
   std::string err;
   uint64_t launches = 0;

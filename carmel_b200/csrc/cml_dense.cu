@@ -1081,7 +1081,7 @@ int launch_sparse(cml_ctx* ctx) {
   ++ctx->launches;
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
   if (ctx->n_hot)
-    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * cmlk::kHotCopies * sizeof(double), s));
+    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * ctx->hot_copies * sizeof(double), s));
   const size_t rs = sizeof(Real);
   const uint32_t SP = D.SP, K = D.K;
   SparseArgs A;
@@ -1102,7 +1102,7 @@ int launch_sparse(cml_ctx* ctx) {
   A.e_code = D.e_code.p;
   A.t_slot = D.cell_slot.p;
   A.f_slot = D.cell_slot.p + (size_t)D.nT + (size_t)D.n_sym * K;
-  A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+  A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot, ctx->hot_copies - 1};
   A.ex_lnp = D.ex_lnp.p;
   A.alpha = D.alpha_g.p;
   A.exps = D.exp_g.p;
@@ -1127,7 +1127,7 @@ int launch_sparse(cml_ctx* ctx) {
   }
   if (!ctx->capturing) CML_CUDA(cudaEventRecord(D.ev1, s));
   if (ctx->n_hot) {
-    cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, s>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p, ctx->reduce);
+    cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, s>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p, ctx->reduce, ctx->hot_copies);
     ++ctx->launches;
   }
   if (D.n_seq) {
@@ -1456,7 +1456,7 @@ extern "C" int cml_add_sequences(cml_ctx* ctx, const cml_dense_view* v, const cm
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), s));
   ctx->n_hot = (uint32_t)hot.size();
   CML_CUDA(ctx->hot_slot.upload(hot.data(), hot.size(), s));
-  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * cmlk::kHotCopies)));
+  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * ctx->hot_copies)));
   CML_CUDA(cudaStreamSynchronize(s));
   ctx->n_slots = n_slots;
   ctx->slots_are_arcs = false;

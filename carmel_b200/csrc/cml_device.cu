@@ -63,6 +63,11 @@ extern "C" int cml_create(cml_ctx** out, int device, int precision, int space) {
   ctx->precision = precision;
   ctx->space = space;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("CML_HOT_COPIES")) {  // tuning knob: replicas per hot count slot (power of two, 1..1024)
+    uint32_t c = (uint32_t)std::max(1, atoi(e)), p2 = 1;
+    while (p2 * 2 <= c && p2 < 1024) p2 *= 2;
+    ctx->hot_copies = p2;
+  }
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     g_create_err = cudaGetErrorString(e);
@@ -1428,7 +1433,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     E.ell_out = bt.ell_out.p;
     E.arc_w = ctx->arc_w_real.p;
     E.arc_ws = ctx->arc_ws.p;
-    E.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    E.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot, ctx->hot_copies - 1};
     E.ex_lnp = bt.ex_lnp.p;
     E.alpha_g = bt.alpha_g.p;
     E.lvl_exp = bt.lvl_exp.p;
@@ -1457,7 +1462,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     Wd.n_a = (uint32_t)ctx->a_list.size();
     Wd.n_v = (uint32_t)ctx->v_list.size();
     Wd.any_a_slot = ctx->any_a_slot;
-    Wd.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    Wd.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot, ctx->hot_copies - 1};
     Wd.ex_lnp = bt.ex_lnp.p;
     Wd.alpha_g = bt.alpha_g.p;
     Wd.lvl_exp = bt.lvl_exp.p;
@@ -1520,7 +1525,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     L.v_slot = ctx->v_slot.p;
     L.n_a = (uint32_t)ctx->a_list.size();
     L.n_v = (uint32_t)ctx->v_list.size();
-    L.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    L.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot, ctx->hot_copies - 1};
     L.ex_lnp = bt.ex_lnp.p;
     L.alpha = bt.lane_alpha.p;
     L.lvle = bt.lane_lvle.p;
@@ -1553,7 +1558,7 @@ static int launch_fb(cml_ctx* ctx, Batch& bt) {
     A.out_arc = bt.out_arc.p;
     A.arc_w = ctx->arc_w_real.p;
     A.arc_slot = ctx->arc_slot_code.p;
-    A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot};
+    A.sink = cmlk::CountSink{ctx->reduce, ctx->hot_counts.p, ctx->n_hot, ctx->hot_copies - 1};
     A.ex_lnp = bt.ex_lnp.p;
     A.scratch = bt.scratch.p;
     A.scratch_lvl = bt.scratch_lvl.p;
@@ -1685,7 +1690,14 @@ static int rebuild_slot_codes(cml_ctx* ctx) {
   ctx->cls_dirty = false;
   CML_CUDA(ctx->arc_slot_code.upload(code.data(), code.size(), ctx->stream));
   CML_CUDA(ctx->hot_slot.upload(hot.data(), hot.size(), ctx->stream));
-  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * cmlk::kHotCopies)));
+  if (!getenv("CML_HOT_COPIES")) {
+    // many narrow lattices (k_fb_lane) put one fp64 RED per arc on ~1 k arc-class slots: 1,024 replicas instead of 64
+    // are worth 12 % of the kernel there (profiles/round2_J); small corpora keep 64 (the fold and the memset scale with it)
+    uint64_t lane_arcs = 0;
+    for (auto& bt : ctx->batches) lane_arcs += bt->lane_arcs;
+    ctx->hot_copies = lane_arcs >= (16ull << 20) ? 1024u : cmlk::kHotCopies;
+  }
+  CML_CUDA(ctx->hot_counts.alloc(std::max<size_t>(1, (size_t)ctx->n_hot * ctx->hot_copies)));
   CML_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->hot_dirty = false;
   return CML_OK;
@@ -1738,7 +1750,7 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   }
   CML_CUDA(cudaMemsetAsync(ctx->reduce, 0, ctx->reduce_n * sizeof(double), ctx->stream));
   if (ctx->n_hot)
-    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * cmlk::kHotCopies * sizeof(double), ctx->stream));
+    CML_CUDA(cudaMemsetAsync(ctx->hot_counts.p, 0, (size_t)ctx->n_hot * ctx->hot_copies * sizeof(double), ctx->stream));
   for (auto& bt : ctx->batches) {
     if (ctx->precision == 64)
       r = sc ? launch_fb<double, true>(ctx, *bt) : launch_fb<double, false>(ctx, *bt);
@@ -1748,7 +1760,7 @@ extern "C" int cml_estimate_launch(cml_ctx* ctx) {
   }
   if (ctx->n_hot) {
     cmlk::k_fold_hot<<<cdiv(ctx->n_hot, 256), 256, 0, ctx->stream>>>(ctx->n_hot, ctx->hot_slot.p, ctx->hot_counts.p,
-                                                                   ctx->reduce);
+                                                                   ctx->reduce, ctx->hot_copies);
     ++ctx->launches;
     CML_CUDA(cudaGetLastError());
   }

@@ -865,21 +865,32 @@ __global__ void k_forest_norm(uint64_t n_groups, const uint64_t* __restrict__ go
 __global__ void k_forest_maxdiff(uint64_t n_groups, const double* __restrict__ gdiff, const uint64_t* __restrict__ gidx,
                                  const uint64_t* __restrict__ gmem, double* __restrict__ out_diff,
                                  unsigned long long* __restrict__ out_rule) {
-  __shared__ double s_d[256];
-  __shared__ uint64_t s_g[256];
+  __shared__ double s_d[1024];
+  __shared__ uint64_t s_g[1024];
   double best = 0;  // maxdiff starts at zero and needs a strictly larger difference (normalize.hpp:258)
   uint64_t bg = ~0ull;
-  for (uint64_t g = threadIdx.x; g < n_groups; g += blockDim.x) {
-    const double d = gdiff[g];
-    if (d > best || (d == best && d > 0 && g < bg)) {
-      best = d;
-      bg = g;
+  // one block of 1024 threads, 4 loads in flight per thread (a 256-thread block walking 40 k groups one dependent load at
+  // a time was most of the M-step's time)
+  for (uint64_t g0 = threadIdx.x; g0 < n_groups; g0 += 4ull * blockDim.x) {
+    double d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t g = g0 + (uint64_t)k * blockDim.x;
+      d[k] = g < n_groups ? gdiff[g] : 0.;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t g = g0 + (uint64_t)k * blockDim.x;
+      if (g < n_groups && (d[k] > best || (d[k] == best && d[k] > 0 && g < bg))) {
+        best = d[k];
+        bg = g;
+      }
     }
   }
   s_d[threadIdx.x] = best;
   s_g[threadIdx.x] = bg;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = (int)blockDim.x / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
       const double d = s_d[threadIdx.x + o];
       const uint64_t g = s_g[threadIdx.x + o];
@@ -2574,7 +2585,7 @@ static int forest_norm(cml_forests* f, const double* counts, double prior, doubl
                                                                      add_k, zero_mode, f->ln_w.p, f->gdiff.p, f->gidx.p);
     ++f->launches;
   }
-  k_forest_maxdiff<<<1, 256, 0, f->stream>>>(f->n_groups, f->gdiff.p, f->gidx.p, f->group_members.p, f->out_diff.p, f->out_rule.p);
+  k_forest_maxdiff<<<1, 1024, 0, f->stream>>>(f->n_groups, f->gdiff.p, f->gidx.p, f->group_members.p, f->out_diff.p, f->out_rule.p);
   ++f->launches;
   CML_CUDA(cudaGetLastError());
   double d = 0;

@@ -55,29 +55,30 @@ struct Num<float> {
 // into counts[] by k_fold_hot afterwards.
 constexpr uint32_t kSlotNone = 0xFFFFFFFFu;
 constexpr uint32_t kSlotHot = 0x80000000u;
-constexpr uint32_t kHotCopies = 64;
+constexpr uint32_t kHotCopies = 64;  // default; cml_ctx::hot_copies (a power of two, CML_HOT_COPIES) is what the buffers are sized for
 struct CountSink {
   double* counts;   // [n_slots]
-  double* hot;      // [kHotCopies][n_hot]
+  double* hot;      // [copies][n_hot]
   uint32_t n_hot;
+  uint32_t mask;    // copies - 1
 };
 __device__ __forceinline__ void count_add(const CountSink& S, uint32_t code, double v) {
 #ifdef CML_DEBUG_NO_COUNTS  // profiling experiment: how long is the sweep without its REDs?
   if (v < 1e300) return;
 #endif
   if (code & kSlotHot)
-    atomicAdd(S.hot + (size_t)(blockIdx.x & (kHotCopies - 1)) * S.n_hot + (code & 0x7fffffffu), v);
+    atomicAdd(S.hot + (size_t)(blockIdx.x & S.mask) * S.n_hot + (code & 0x7fffffffu), v);
   else
     atomicAdd(S.counts + code, v);
 }
 // fold the hot replicas into the count table (one thread per hot slot)
 static __global__ void k_fold_hot(uint32_t n_hot, const uint32_t* __restrict__ hot_slot, const double* __restrict__ hot,
-                           double* __restrict__ counts) {
+                           double* __restrict__ counts, uint32_t copies) {
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_hot) return;
   double s = 0;
 #pragma unroll 8
-  for (uint32_t k = 0; k < kHotCopies; ++k) s += hot[(size_t)k * n_hot + h];
+  for (uint32_t k = 0; k < copies; ++k) s += hot[(size_t)k * n_hot + h];
   if (s != 0.) atomicAdd(&counts[hot_slot[h]], s);
 }
 
