@@ -657,14 +657,14 @@ def main():
             return bench_forest.run(fa, rank, world, local, as_leg=True, token=new_token(), with_cpu=(world == 1))
         run_leg("c5", c5)
 
-    if "c4" in legs and world == 1:
+    if "c4" in legs:
         def c4():
             import bench_gibbs
             ga = argparse.Namespace(**vars(a))
-            ga.scale = 4  # 20,000 lines x 50 = configs[3]'s 1M letters
+            ga.scale = 4  # 20,000 lines x 50 = configs[3]'s 1M letters (in total: sharded over the ranks)
             ga.steps = max(3, min(a.steps, 10))
             ga.no_dense = False
-            return bench_gibbs.run(ga, rank, world, local, as_leg=True, with_cpu=True)
+            return bench_gibbs.run(ga, rank, world, local, as_leg=True, with_cpu=(world == 1), token=new_token())
         run_leg("c4", c4)
 
     if "cli" in legs and world == 1:

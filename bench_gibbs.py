@@ -22,9 +22,12 @@ METRIC, UNIT = "gibbs_samples_per_sec", "samples/s"
 
 def config_of(a, world):
     return {"workload": "configs[3] --crp Gibbs on the synthetic cipher (27x27 channel o locked bigram LM, alpha=0.01), "
-                        f"{5000 * a.scale} lines x 50 letters per GPU, batched sweeps",
-            "blocks_per_gpu": 5000 * a.scale, "l2": "lattices 2.9 GB per GPU > 126 MB L2",
-            "parallelism": f"{world} independent replica(s): the exact sampler is sequential over the corpus (SURVEY 8e)"}
+                        f"{5000 * a.scale} lines x 50 letters IN TOTAL, batched sweeps",
+            "blocks_total": 5000 * a.scale, "l2": "lattices 2.9 GB per 20,000 lines > 126 MB L2",
+            "parallelism": ("one GPU" if world == 1 else
+                            f"blocks sharded over {world} GPUs (strong scaling); every rank samples its blocks against the counts "
+                            "of the previous sweep, one NCCL all-reduce of the count deltas per sweep (SURVEY 8e); the exact "
+                            "sampler is sequential over the corpus and stays on one GPU")}
 
 
 def cpu_oracle_gibbs(files, n_lines, procs, sweeps=3):
@@ -89,7 +92,7 @@ def reference_arm(a):
     print(json.dumps(line))
 
 
-def run(a, rank, world, local, as_leg=False, with_cpu=True):
+def run(a, rank, world, local, as_leg=False, with_cpu=True, token=None):
     """as_leg: called by bench.py for its c4 leg (returns the line instead of printing it; no process-group handling)"""
     import torch
     import torch.distributed as dist
@@ -101,8 +104,24 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
     torch.cuda.set_device(local)
     if world > 1 and not as_leg:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    d = tempfile.mkdtemp(prefix=f"cb200_gibbs_{rank}_")
-    w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104 + rank)
+    sharded = world > 1
+    if sharded:  # one corpus for all ranks (rank 0 writes it), every rank keeps its block: --shard + the library's communicator
+        d = os.path.join(tempfile.gettempdir(), f"cb200_gibbs_{os.environ.get('MASTER_PORT', 'x')}_{os.getppid()}")
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+            w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104)
+            json.dump(w, open(os.path.join(d, "workload.json"), "w"))
+        dist.barrier()
+        w = json.load(open(os.path.join(d, "workload.json")))
+        if token is None:
+            box = [cb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            token = box[0]
+    else:
+        d = tempfile.mkdtemp(prefix=f"cb200_gibbs_{rank}_")
+        w = synth.write_cipher(d, n_lines=5000 * a.scale, line_len=50, seed=20260104 + rank)
+    shard = [f"--shard={rank}/{world}"] if sharded else []
+    my_seed = 1 + 7919 * rank  # (draws are keyed by the local block number)
     stream = torch.cuda.Stream()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     no_dense = bool(getattr(a, "no_dense", False))
@@ -138,7 +157,7 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
 
     # the same corpus on the lattice sampler (k_gibbs_batched), for the record beside the dense-state sampler
     lattice_leg = None
-    if not no_dense:
+    if not no_dense and not sharded:
         job0 = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", "--no-dense", "--priors=0,1e-2",
                        "--seed=1", *w["argv"][1:]])
         ctx0 = job0.prepare()
@@ -158,19 +177,24 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
         job0.close()
 
     t_build = time.time()
-    job = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", *(["--no-dense"] if no_dense else []),
-                  "--priors=0,1e-2", "--seed=1", *w["argv"][1:]])
+    job = cb.Job(["-q", f"--gpu={local}", "--crp", "-M", "1000", "--crp-batched", *(["--no-dense"] if no_dense else []), *shard,
+                  "--priors=0,1e-2", "--seed=1", *w["argv"][1:]], comm_token=token if sharded else None)
     ctx = job.prepare()
     ctx.set_stream(stream.cuda_stream)
     t_build = time.time() - t_build
     info = job.stats()
     blocks, arcs, states = info["examples"], info["trellis_arcs"], info["trellis_states"]
     is_dense = bool(info.get("dense", 0))
+    tot = torch.tensor([blocks, arcs, states], dtype=torch.float64, device="cuda")
+    if sharded:
+        dist.all_reduce(tot)
+    blocks_total = float(tot[0].item())
+    c0 = ctx.collective_count()
 
     sweep = [0]
 
     def step():
-        ctx.gibbs_sweep(1, sweep[0], seed=1, power=1.0, accumulate_dt=1.0)
+        ctx.gibbs_sweep(1, sweep[0], seed=my_seed, power=1.0, accumulate_dt=1.0)
         sweep[0] += 1
 
     for _ in range(a.warmup):
@@ -182,7 +206,8 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
     ms = timed(step, a.steps, flush=is_dense)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    value = world * blocks * a.steps / (ms / 1e3)
+    value = blocks_total * a.steps / (ms / 1e3)
+    collectives = ctx.collective_count() - c0
 
     # e2e: what the host loop of `carmel --crp` does every sweep: read the sampled derivations back (for the cache-model
     # probability, gibbs.hpp:712-742)
@@ -196,12 +221,12 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
 
     e2e_step()
     ms_e2e = timed(e2e_step, a.steps, flush=is_dense)
-    e2e = {"value": world * blocks * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0,
+    e2e = {"value": blocks_total * a.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": 0,
            "d2h_bytes_per_step": 4 * (blocks + cap), "ms_per_step": ms_e2e / a.steps,
            "lattices": f"resident; one-time host build + upload took {t_build:.2f}s on this rank"}
     # the exact sequential sampler on the same blocks (one CTA walks the corpus)
     n_seq = max(1, min(2, a.steps))
-    ms_seq = timed(lambda: ctx.gibbs_sweep(0, 100000 + sweep[0], seed=1, power=1.0, accumulate_dt=0.0), n_seq)
+    ms_seq = None if sharded else timed(lambda: ctx.gibbs_sweep(0, 100000 + sweep[0], seed=1, power=1.0, accumulate_dt=0.0), n_seq)
     if rank == 0:
         peaks, which = measured_peaks()
         # per sample one backward sweep over the block's lattice (8 B/arc record + the state scores written and
@@ -240,12 +265,13 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
             except Exception as ex:
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_of(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks,
-                "sequential": {"value": blocks * n_seq / (ms_seq / 1e3), "unit": UNIT, "ms_per_sweep": ms_seq / n_seq,
-                               "note": "exact collapsed sampler, identical derivations to the CPU oracle (tests/test_gibbs_gpu.py)"},
-                "totals": {"blocks": blocks, "trellis_arcs": arcs, "trellis_states": states},
+                "gpu_launches": int(launches), "collectives": int(collectives), "clocks": clocks,
+                "sequential": None if ms_seq is None else
+                {"value": blocks * n_seq / (ms_seq / 1e3), "unit": UNIT, "ms_per_sweep": ms_seq / n_seq,
+                 "note": "exact collapsed sampler, identical derivations to the CPU oracle (tests/test_gibbs_gpu.py)"},
+                "totals": {"blocks": blocks_total, "trellis_arcs": float(tot[1].item()), "trellis_states": float(tot[2].item())},
                 "sampler": "dense-state (cml_gibbs_attach_dense)" if is_dense else "lattice"}
         if lattice_leg is not None:
             line["lattice_path"] = lattice_leg
@@ -257,7 +283,8 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True):
     if world > 1:
         dist.barrier()
     job.close()
-    shutil.rmtree(d, ignore_errors=True)
+    if not sharded or rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
     if world > 1 and not as_leg:
         dist.destroy_process_group()
     return line if rank == 0 else None

@@ -209,7 +209,7 @@ struct cml_ctx {
   bool have_gibbs = false;
   uint32_t g_norms = 0;
   DevArray<uint32_t> g_param_norm, g_arc_orig, g_sample[2], g_sample_len[2], g_au_off, g_au_param;
-  DevArray<double> g_prior, g_count, g_cum, g_normsum, g_lnp, g_beta, g_tbl;
+  DevArray<double> g_prior, g_count, g_cum, g_normsum, g_lnp, g_beta, g_tbl, g_delta;
   DevArray<uint64_t> g_sample_base, g_beta_base;
   DevArray<double> g_post[2], g_alpha, g_blk_lnp;  // --expectation: per-lattice-arc posteriors (two generations), alpha, ln P per block
   DevArray<uint2> g_arc_pg;

@@ -614,6 +614,18 @@ __global__ void k_gibbs_apply(GibbsArgs A) {
   add_sample_counts(A, A.new_sample + A.sample_base[e], A.new_len[e], wt, true);
 }
 
+// sharded batched sweeps: a rank applies its blocks' (new - old) sample counts to a zeroed DELTA table
+// [n_params | n_norms], the tables are summed over the ranks (one all-reduce per sweep) and added to the replicated
+// counts, so every rank samples the next sweep against the same global counts
+__global__ void k_gibbs_add_delta(uint32_t n_params, uint32_t n_norms, const double* __restrict__ delta, double* __restrict__ count,
+                                  double* __restrict__ normsum) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_params)
+    count[i] += delta[i];
+  else if (i < n_params + n_norms)
+    normsum[i - n_params] += delta[i];
+}
+
 __global__ void k_gibbs_lnprob(uint32_t n_params, const uint32_t* __restrict__ param_norm, const double* __restrict__ prior,
                                const double* __restrict__ count, const double* __restrict__ normsum,
                                double* __restrict__ lnp) {
@@ -774,6 +786,27 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
     ++ctx->launches;
     A.arc_lnw = (const double*)ctx->arc_w_real.p;
   }
+  // batched modes: the sweep's count update, summed over the ranks when the context has a communicator
+  auto apply_batched = [&](const GibbsArgs& B) -> int {
+    if (!ctx->comm || ctx->comm_size <= 1) {
+      k_gibbs_apply<<<cdiv(B.n_ex, 128), 128, 0, s>>>(B);
+      ++ctx->launches;
+      return CML_OK;
+    }
+    const uint32_t n_norms = (uint32_t)ctx->g_normsum.n;
+    const size_t nd = (size_t)ctx->n_params + n_norms;
+    if (ctx->g_delta.n < nd) CML_CUDA(ctx->g_delta.alloc(nd));
+    CML_CUDA(cudaMemsetAsync(ctx->g_delta.p, 0, nd * sizeof(double), s));
+    GibbsArgs D = B;
+    D.count = ctx->g_delta.p;
+    D.normsum = ctx->g_delta.p + ctx->n_params;
+    if (B.n_ex) k_gibbs_apply<<<cdiv(B.n_ex, 128), 128, 0, s>>>(D);
+    const int rc = cml_allreduce_buffer(ctx, ctx->g_delta.p, nd);
+    if (rc) return rc;
+    k_gibbs_add_delta<<<cdiv(nd, 256), 256, 0, s>>>(ctx->n_params, n_norms, ctx->g_delta.p, ctx->g_count.p, ctx->g_normsum.p);
+    ctx->launches += 2;
+    return CML_OK;
+  };
   if (o->mode == CML_GIBBS_EXPECTATION) {
     CML_REQUIRE(!o->init_from_params, CML_ERR_ARG, "--expectation has no separate initial distribution (gibbs.cc:311-313)");
     const size_t na = std::max<uint64_t>(1, bt.n_arcs), ns = std::max<uint64_t>(1, bt.n_states);
@@ -814,12 +847,14 @@ extern "C" int cml_gibbs_sweep(cml_ctx* ctx, const cml_gibbs_sweep_opts* o) {
     const uint32_t nt = ctx->gd_V * ctx->gd_S * 32;
     k_gibbs_dense_table<<<cdiv(nt, 256), 256, 0, s>>>(nt, ctx->gd_arc.p, A.arc_lnw, ctx->gd_W.p);
     k_gibbs_dense<<<std::max(1u, std::min<unsigned>(cdiv(A.n_ex, kGibbsWarps), (unsigned)ctx->sm_count * 16u)), kGibbsWarps * 32, 0, s>>>(A, G);
-    k_gibbs_apply<<<cdiv(A.n_ex, 128), 128, 0, s>>>(A);
-    ctx->launches += 3;
+    ctx->launches += 2;
+    const int rc = apply_batched(A);
+    if (rc) return rc;
   } else {
     k_gibbs_batched<<<std::max(1u, std::min<unsigned>(cdiv(A.n_ex, kGibbsWarps), (unsigned)ctx->sm_count * 16u)), kGibbsWarps * 32, 0, s>>>(A);
-    k_gibbs_apply<<<cdiv(A.n_ex, 128), 128, 0, s>>>(A);
-    ctx->launches += 2;
+    ++ctx->launches;
+    const int rc = apply_batched(A);
+    if (rc) return rc;
   }
   if (o->accumulate_dt != 0.) {
     k_gibbs_accumulate<<<cdiv(ctx->n_params, 256), 256, 0, s>>>(ctx->n_params, ctx->g_count.p, ctx->g_cum.p, o->accumulate_dt);

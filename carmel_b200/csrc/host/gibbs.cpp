@@ -167,7 +167,17 @@ void TrainJob::attach_dense_sampler() {
 }
 
 TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
+  // Sharded sampling: only batched sweeps shard -- every rank samples its blocks against the counts the
+  // previous sweep left, the ranks' count deltas are summed by one all-reduce per sweep (cml_gibbs_sweep).  The exact
+  // sampler visits the blocks one after another, so it stays on one GPU; results of a sharded run are reported as
+  // perplexity agreement, not sample identity.
+  const bool sharded = opt.shard_count > 1;
+  if (sharded && (!gopt.batched || gopt.expectation || gopt.sample_prob))
+    throw std::runtime_error("--shard / --gpus with --crp needs --crp-batched (and neither --expectation nor --sample-prob): "
+                             "the exact sampler is sequential over the corpus");
   prepare_gibbs();
+  if (sharded && !have_comm_id)
+    throw std::runtime_error("sharded --crp-batched needs the library's communicator (cml_job_set_comm / --gpus)");
   GibbsOpts& g = gopt;
   std::vector<uint32_t> const& norm = g_norm;
   std::vector<double> const& prior = g_prior;
@@ -201,7 +211,7 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
     cml_gibbs_sweep_opts so{};
     so.mode = g.expectation ? CML_GIBBS_EXPECTATION : g.batched ? CML_GIBBS_BATCHED : CML_GIBBS_SEQUENTIAL;
     so.power = temperature > 0 ? 1. / temperature : 1.;
-    so.seed = g.seed;
+    so.seed = g.seed + (sharded ? 0x9E3779B97F4A7C15ull * (uint64_t)(opt.shard_rank + 1) : 0ull);  // (draws are keyed by local block number)
     so.sweep = it;
     so.init_from_params = 0;
     so.accumulate_dt = it == g.iter ? 1. : time_of(it + 1) - time_of(it);
@@ -264,11 +274,13 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
           ln_p += norm[p] != kNoGroup ? std::log(ccount[p]++ / csum[norm[p]]++) : std::log(prior[p]);
         }
       }
+    if (sharded) ok(cml_allreduce_host(ctx, &ln_p, 1));  // (every rank scores its blocks with a cache of its own)
+    const double n_blocks = sharded ? (double)corpus.n_pairs : (double)res.examples;
     res.history.push_back({it, ln_p, ln_p, 0});
     if (!opt.quiet) {
       log << "Gibbs i=" << it << (g.sample_prob ? " sample prob=" : " cache-model prob=") << format_base2(ln_p);
       if (n_sym) log << " per-point-ppx(N=" << n_sym << ")=" << format_base2(-ln_p / n_sym);
-      log << " per-block-ppx(N=" << res.examples << ")=" << format_base2(-ln_p / (double)res.examples) << "\n";
+      log << " per-block-ppx(N=" << n_blocks << ")=" << format_base2(-ln_p / n_blocks) << "\n";
     }
   }
   if (!gopt.dump_samples_file.empty()) {

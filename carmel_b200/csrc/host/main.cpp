@@ -64,8 +64,9 @@ static int run_multi_gpu(int argc, char** argv, int n_gpus) {
     jobs.emplace_back(new TrainJob());
     const int rc = open_job((int)av.size(), av.data(), *jobs.back(), r == 0 ? (std::ostream&)std::cerr : (std::ostream&)quiet);
     if (rc != 0) return rc;
-    if (jobs.back()->gopt.enabled) {
-      std::cerr << "ERROR: --gpus shards EM training; --crp sampling is sequential over the corpus (one GPU)\n";
+    if (jobs.back()->gopt.enabled && !jobs.back()->gopt.batched) {
+      std::cerr << "ERROR: --gpus shards EM training and --crp-batched sweeps; the exact --crp sampler is sequential over the "
+                   "corpus (one GPU)\n";
       return -11;
     }
     std::memcpy(jobs.back()->comm_id, id, sizeof(id));
@@ -77,7 +78,10 @@ static int run_multi_gpu(int argc, char** argv, int n_gpus) {
     th.emplace_back([&, r]() {
       try {
         std::ostringstream sink;
-        jobs[r]->run(r == 0 ? (std::ostream&)std::cerr : (std::ostream&)sink);
+        if (jobs[r]->gopt.enabled)
+          jobs[r]->run_gibbs(r == 0 ? (std::ostream&)std::cerr : (std::ostream&)sink);
+        else
+          jobs[r]->run(r == 0 ? (std::ostream&)std::cerr : (std::ostream&)sink);
       } catch (std::exception& e) {
         errs[r] = e.what();
         if (errs[r].empty()) errs[r] = "failed";

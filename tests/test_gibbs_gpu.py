@@ -227,3 +227,31 @@ def test_epron_crp_expectation(cli, oracle_bin, tmp_path):
 def test_tagging_crp_expectation(cli, oracle_bin, tmp_path):
     data, fsa, fst = stage(tmp_path, "tagging.data", "tagging.fsa", "tagging.fst")
     _expect_both(cli, oracle_bin, tmp_path, ["--crp=4", "--burnin=1", "--priors=0.1,0.01", "-HJ"], [data, fsa, fst], [fsa, fst])
+
+
+def test_batched_sweeps_two_gpus_agree_with_one(cli, tmp_path):
+    """batched sweeps shard the blocks over the GPUs, one all-reduce of the count deltas per sweep; the
+    sharded run must end at the perplexity of the one-GPU run (not the same samples: the ranks draw different uniforms)
+    and write a normalised channel"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from carmel_b200 import synth
+    w = synth.write_cipher(str(tmp_path / "syn"), n_lines=300, line_len=30, seed=7)
+    data, wfsa, fst = w["files"]
+    bits = {}
+    for name, extra in (("one", []), ("two", ["--gpus=2"])):
+        rc, out, err = run(cli, ["--crp", "-M", "150", "--burnin=50", "--crp-batched", "--priors=0,1e-2", "--seed=9", "-q", *extra,
+                                 f"--history={tmp_path}/h.{name}", data, wfsa, fst], timeout=600)
+        assert rc == 0, err
+        h = _hist(f"{tmp_path}/h.{name}")
+        assert len(h) == 151
+        bits[name] = -np.mean([v for _, v in h[-50:]]) / 9000 / math.log(2)
+        rows = {}
+        for m in re.finditer(r'\(0 \(0 ("[^"]*") ("[^"]*") ([^)\s]+)\)\)', open(fst + ".trained").read()):
+            rows[m.group(1)] = rows.get(m.group(1), 0.0) + math.exp(_ln_weight(m.group(3)))
+        assert len(rows) == 27 and all(abs(v - 1) < 1e-6 for v in rows.values()), (name, rows)
+    assert abs(bits["one"] - bits["two"]) <= 0.03 * bits["one"], bits
+    # the exact sampler is sequential over the corpus: refused, not silently replicated
+    rc, _, err = run(cli, ["--crp", "-M", "5", "--gpus=2", data, wfsa, fst])
+    assert rc != 0 and "sequential over the corpus" in err
