@@ -136,6 +136,11 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
     t_build = time.time()
     fs = synth.make_forests(n_forests=100000 * a.scale, n_rules=1000000, seed=20260105, templates=0, part=(rank, world))
     stream = torch.cuda.Stream()
+    if os.environ.get("CB200_DIRTY"):  # debugging aid: the library's cudaMalloc calls then see non-zero memory
+        x = torch.full((int(os.environ["CB200_DIRTY"]) << 30,), 0xAB, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        del x
+        torch.cuda.empty_cache()
     F = Forests(device=local, precision=a.precision)
     if os.environ.get("CB200_FOREST_LAYOUT"):  # development runs: 1 group, 2 thread, 3 level (default: the library's choice)
         F.set_layout(int(os.environ["CB200_FOREST_LAYOUT"]))

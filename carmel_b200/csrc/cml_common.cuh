@@ -46,7 +46,8 @@ struct DevArray {
   // always allocates at least one element so kernels never see a null table
   cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
     cudaError_t e = alloc(count ? count : 1);
-    if (e != cudaSuccess || !count || !h) return e;
+    if (e != cudaSuccess) return e;
+    if (!count || !h) return cudaMemsetAsync(p, 0, sizeof(T), s);  // (kernels that walk `n` elements see a defined value)
     return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
   }
   void release() {

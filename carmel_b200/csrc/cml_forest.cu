@@ -1885,8 +1885,10 @@ static int forest_rebuild_hot(cml_forests* f) {
   CML_CUDA(f->hot_rule.upload(hot_rule.data(), hot_rule.size(), f->stream));
   CML_CUDA(f->hot.alloc(std::max<size_t>(1, (size_t)kHotCopies * f->n_hot)));
   for (auto& bt : f->batches) {
-    k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
-    ++f->launches;
+    if (bt->n_forests > bt->t_forests + bt->lt_forests) {  // (only batches that hold per-forest CSRs)
+      k_forest_mark_hot<<<f_cdiv(bt->label.n, 256), 256, 0, f->stream>>>(bt->label.n, bt->label.p, f->hot_index.p);
+      ++f->launches;
+    }
     if (bt->n_ltiles) {
       if (!bt->lt_label_out.p) CML_CUDA(bt->lt_label_out.alloc(bt->lt_label.n));
       k_forest_label_out<<<f_cdiv(bt->lt_label.n, 256), 256, 0, f->stream>>>(bt->lt_label.n, bt->lt_label.p, f->hot_index.p,

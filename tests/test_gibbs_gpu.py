@@ -241,8 +241,8 @@ def test_batched_sweeps_two_gpus_agree_with_one(cli, tmp_path):
     data, wfsa, fst = w["files"]
     bits = {}
     for name, extra in (("one", []), ("two", ["--gpus=2"])):
-        rc, out, err = run(cli, ["--crp", "-M", "150", "--burnin=50", "--crp-batched", "--priors=0,1e-2", "--seed=9", "-q", *extra,
-                                 f"--history={tmp_path}/h.{name}", data, wfsa, fst], timeout=600)
+        rc, out, err = run(cli, ["--crp", "-M", "150", "--burnin=50", "--crp-batched", "--priors=0,1e-2", "--seed=9", "-q", "-HJ", *extra,
+                                 f"--history={tmp_path}/h.{name}", data, wfsa, fst], timeout=240)
         assert rc == 0, err
         h = _hist(f"{tmp_path}/h.{name}")
         assert len(h) == 151
