@@ -304,8 +304,10 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (carmel_b200 has no CPU fallback)"
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")  # CPU side channel: survives a broken CUDA context on some rank (run_leg)
     shared = os.path.join(tempfile.gettempdir(), f"cb200_bench_{os.environ.get('MASTER_PORT', 'single')}_{os.getppid() if world > 1 else os.getpid()}")
     if rank == 0:
         shutil.rmtree(shared, ignore_errors=True)
@@ -608,6 +610,25 @@ def main():
         if single and other is not None:
             line["sparse_path"] = leg_of(other, "same corpus with --no-dense")
 
+    def finish_line():
+        """rank 0: parity gates, then THE line"""
+        if tf32["value"] is not None:
+            line["tf32_peak_tflops_measured"] = tf32["value"]
+        # parity gates: a line whose GPU results differ from the oracle's is not a measurement
+        bad = []
+        for key in ("parity", "parity_n"):
+            if key in line and line[key] is not None and not line[key].get("ok", False):
+                bad.append(key)
+        for leg in ("dense_path", "c3", "c5"):
+            p = (line.get(leg) or {}).get("parity")
+            if p is not None and not p.get("ok", False):
+                bad.append(f"{leg}.parity")
+        line["parity_ok"] = not bad
+        if bad:  # a line whose results differ from the oracle's is not a measurement: say so in the line itself
+            line["parity_failures"] = bad
+            line["invalid"] = "parity check failed: " + ", ".join(bad)
+        print(json.dumps(line, default=lambda o: str(o)))
+
     # ---------------------------------------------------------------- legs
     def run_leg(name, fn):
         """a leg never takes the line down: failures are recorded in its place"""
@@ -620,6 +641,24 @@ def main():
         except Exception as ex:  # noqa: BLE001
             if rank == 0:
                 line[name] = {"failed": f"{type(ex).__name__}: {ex}"[:400], "wall_s": time.time() - t0}
+        # a CUDA error is sticky: if the device of ANY rank is broken after this leg, nothing later can run (and the
+        # NCCL barrier would hang the other ranks) -- every rank learns it over the CPU group, rank 0 prints the line
+        # with what it has, and all ranks leave
+        broken = 0
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            broken = 1
+        if gloo is not None:
+            flag = torch.tensor([broken], dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=gloo)
+            broken = int(flag.item())
+        if broken:
+            if rank == 0:
+                line["aborted_after_leg"] = name
+                finish_line()
+            sys.stdout.flush()
+            os._exit(0)
         barrier()
 
     if "c2" in legs:
@@ -708,22 +747,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if tf32["value"] is not None:
-            line["tf32_peak_tflops_measured"] = tf32["value"]
-        # parity gates: a line whose GPU results differ from the oracle's is not a measurement
-        bad = []
-        for key in ("parity", "parity_n"):
-            if key in line and line[key] is not None and not line[key].get("ok", False):
-                bad.append(key)
-        for leg in ("dense_path", "c3", "c5"):
-            p = (line.get(leg) or {}).get("parity")
-            if p is not None and not p.get("ok", False):
-                bad.append(f"{leg}.parity")
-        line["parity_ok"] = not bad
-        if bad:  # a line whose results differ from the oracle's is not a measurement: say so in the line itself
-            line["parity_failures"] = bad
-            line["invalid"] = "parity check failed: " + ", ".join(bad)
-        print(json.dumps(line, default=lambda o: str(o)))
+        finish_line()
     barrier()
     if rank == 0 and not a.keep:
         shutil.rmtree(shared, ignore_errors=True)

@@ -270,7 +270,7 @@ def run(a, rank, world, local, as_leg=False, token=None, with_cpu=True):
                 "layout": lay, "templates": "every forest its own shape (csrc/tools/forest_synth.c)"}
         if not as_leg:
             print(json.dumps(line))
-    if world > 1:
+    if world > 1 and not as_leg:  # (as a leg: bench.py's run_leg synchronises the ranks, over a channel that survives a CUDA error)
         dist.barrier()
     F.close()
     if world > 1 and not as_leg:

@@ -280,7 +280,7 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True, token=None):
                                     "(256 MB write) between timed sweeps, each sweep timed with its own CUDA-event pair")
         if not as_leg:
             print(json.dumps(line))
-    if world > 1:
+    if world > 1 and not as_leg:
         dist.barrier()
     job.close()
     if not sharded or rank == 0:
