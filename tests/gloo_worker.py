@@ -102,11 +102,31 @@ def forest_rank(cfg, rank, world):
     return buf
 
 
+def gibbs_rank(cfg, rank, world):
+    """one batched --crp sweep's count update on this rank's blocks (cml_gibbs_sweep with a communicator): the
+    (new - old) sample counts of the rank's blocks go to a zeroed delta table [n_params | n_norms]; the summed deltas
+    are added to the replicated counts.  Blocks are split like the product's contiguous shards."""
+    n_params, n_norms = cfg["n_params"], cfg["n_norms"]
+    norm = cfg["param_norm"]
+    blocks = cfg["blocks"]
+    b0, b1 = rank * len(blocks) // world, (rank + 1) * len(blocks) // world
+    delta = np.zeros(n_params + n_norms + 2)
+    for old, new, wt in blocks[b0:b1]:
+        for arcs, sign in ((old, -wt), (new, wt)):
+            for a in arcs:
+                for p in cfg["chains"][a]:
+                    if norm[p] >= 0:
+                        delta[p] += sign
+                        delta[n_params + norm[p]] += sign
+    delta[-1] = b1 - b0
+    return delta
+
+
 def main():
     cfg = json.load(open(sys.argv[1]))
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)  # MASTER_ADDR=127.0.0.1 from the environment
-    buf = carmel_rank(cfg, rank, world) if cfg["case"] == "carmel" else forest_rank(cfg, rank, world)
+    buf = (carmel_rank if cfg["case"] == "carmel" else gibbs_rank if cfg["case"] == "gibbs" else forest_rank)(cfg, rank, world)
     n_local = buf[-1]
     t = torch.from_numpy(buf)
     dist.all_reduce(t)  # the one collective of an EM iteration: fp64 sum of [counts | sum ln p | n]

@@ -91,6 +91,36 @@ def test_forest_shards_allreduce_to_unsharded(native_lib, forest_oracle_bin, tmp
     np.testing.assert_allclose(red[1:-2], want, rtol=1e-10, atol=1e-14)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_batched_gibbs_count_deltas_allreduce_to_unsharded(tmp_path, world):
+    """sharded batched --crp sweeps: the all-reduced per-rank delta tables, added to the replicated counts,
+    must equal the one-GPU update (remove every block's old sample, add its new one)"""
+    rng = np.random.default_rng(17)
+    n_params, n_norms, n_arcs = 40, 6, 25
+    norm = [int(rng.integers(0, n_norms)) if rng.random() < 0.8 else -1 for _ in range(n_params)]
+    chains = [[int(p) for p in rng.choice(n_params, size=int(rng.integers(1, 4)), replace=False)] for _ in range(n_arcs)]
+    blocks = [([int(a) for a in rng.integers(0, n_arcs, int(rng.integers(0, 9)))],
+               [int(a) for a in rng.integers(0, n_arcs, int(rng.integers(1, 9)))], float(rng.choice([1.0, 2.0, 0.5])))
+              for _ in range(23)]
+    d = str(tmp_path)
+    json.dump({"case": "gibbs", "dir": d, "n_params": n_params, "n_norms": n_norms, "param_norm": norm, "chains": chains,
+               "blocks": blocks}, open(f"{d}/cfg.json", "w"))
+    _launch(f"{d}/cfg.json", world)
+    res = json.load(open(f"{d}/result.json"))
+    red = np.asarray(res["reduced"])
+    assert sum(res["per_rank"]) == len(blocks) == red[-1] and all(n > 0 for n in res["per_rank"])
+    count, normsum = np.zeros(n_params), np.zeros(n_norms)
+    for old, new, wt in blocks:  # the sequentially applied update of one GPU (k_gibbs_apply)
+        for arcs, sign in ((old, -wt), (new, wt)):
+            for a in arcs:
+                for p in chains[a]:
+                    if norm[p] >= 0:
+                        count[p] += sign
+                        normsum[norm[p]] += sign
+    np.testing.assert_allclose(red[:n_params], count, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(red[n_params:n_params + n_norms], normsum, rtol=0, atol=1e-12)
+
+
 def test_shard_partition_covers_corpus(native_lib, tmp_path):
     """blocks of --shard=r/N concatenate to the unsharded lattice dump, for several N"""
     from carmel_b200 import CLI_PATH
