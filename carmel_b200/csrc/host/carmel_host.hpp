@@ -244,6 +244,10 @@ struct TrainJob {
   TrainResult const& run(std::ostream& log);        // EM (WFST::train)
   TrainResult const& run_gibbs(std::ostream& log);  // --crp (WFST::train_gibbs)
   void prepare_gibbs();
+  // --viterbi=FILE: the best derivation of every training pair under the (normalised) model as given, one line per
+  // kept example: ln weight, number of arcs, arc-table ids; then, per arc, the (input:output) labels of the cascade
+  // members' arcs it stands for (decode side: carmel -k 1 on the composed machine, fst.h:769-800)
+  void run_viterbi(std::ostream& log, std::string const& path);
   void attach_dense_sampler();  // batched --crp on position-synchronous lattices: cml_gibbs_attach_dense  // lattices + CRP parameters on the GPU, counts = priors; no sweep yet
   bool gibbs_prepared = false;
   std::vector<uint32_t> g_norm;  // CRP normalisation group of every parameter (kNoGroup = fixed probability)

@@ -317,4 +317,46 @@ TrainResult const& TrainJob::run_gibbs(std::ostream& log) {
   return res;
 }
 
+// Decode: best derivation per training pair (cml_viterbi).  The weights are the model's as read, after the same
+// normalisation a training run starts from (train.cc:509); no training happens.
+void TrainJob::run_viterbi(std::ostream& log, std::string const& path) {
+  opt.precision = 64;
+  opt.space = CML_SPACE_LOG;  // layered-CSR lattices keep the reference's per-state arc order
+  opt.no_ell = true;
+  opt.dense = -1;
+  if (opt.shard_count > 1) throw std::runtime_error("--viterbi decodes on one GPU");
+  prepare();
+  uint64_t n_ex = 0, n_states = 0, n_arcs = 0, n_levels = 0;
+  ok(cml_trellis_totals(ctx, &n_ex, &n_states, &n_arcs, &n_levels));
+  std::vector<uint32_t> len(n_ex), arcs(std::max<uint64_t>(1, n_levels));
+  std::vector<uint64_t> base(n_ex + 1);
+  std::vector<double> lnw(n_ex);
+  if (n_ex) ok(cml_viterbi(ctx, len.data(), base.data(), arcs.data(), arcs.size(), lnw.data()));
+  // labels of every parameter's member arc (parameters are numbered member by member, state by state, arc by arc)
+  std::vector<std::string> plabel;
+  for (Wfst* m : members)
+    for (auto& st : m->states)
+      for (Arc& a : st) plabel.push_back(m->alph[0]->names[a.in] + ":" + m->alph[1]->names[a.out]);
+  std::ofstream o(path);
+  if (!o) throw std::runtime_error("cannot write " + path);
+  o.precision(17);
+  double total = 0;
+  for (uint64_t e = 0; e < n_ex; ++e) {
+    o << lnw[e] << " " << len[e];
+    for (uint32_t k = 0; k < len[e]; ++k) o << " " << arcs[base[e] + k];
+    o << " |";
+    for (uint32_t k = 0; k < len[e]; ++k) {
+      const uint32_t a = arcs[base[e] + k];
+      const uint32_t k0 = using_cascade ? M.chain_off[a] : a, k1 = using_cascade ? M.chain_off[a + 1] : a + 1;
+      o << " (";
+      for (uint32_t c = k0; c < k1; ++c) o << (c > k0 ? " " : "") << plabel[using_cascade ? M.chain_param[c] : c];
+      o << ")";
+    }
+    o << "\n";
+    total += lnw[e];
+  }
+  if (!opt.quiet)
+    log << "Viterbi: best derivations of " << n_ex << " examples, product of their weights=" << format_base2(total) << "\n";
+}
+
 }  // namespace cb

@@ -155,6 +155,10 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
+    if (job.lopt.count("viterbi")) {  // decode only: best derivation of every training pair
+      job.run_viterbi(std::cerr, job.lopt["viterbi"]);
+      return 0;
+    }
     if (job.gopt.enabled)
       job.run_gibbs(std::cerr);
     else

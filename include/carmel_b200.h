@@ -194,6 +194,17 @@ int cml_build_trellises(cml_ctx* ctx, const cml_wfst_view* x, const cml_corpus_v
 void cml_free_built_trellises(cml_built_trellises* b);
 int cml_trellis_totals(cml_ctx* ctx, uint64_t* n_ex, uint64_t* n_states, uint64_t* n_arcs, uint64_t* n_levels);
 int cml_cyclic_stats(cml_ctx* ctx, uint64_t* n_examples, uint64_t* n_back_edges);
+/* Best derivation of every resident lattice at the current parameters -- the decode carmel does with `-k 1` on the
+ * composed  string x transducer x string  machine (fst.h:769-800 bestPaths, graehl/shared/kbest.h): max-plus forward
+ * pass over the layered CSR (states in topological order, out-arcs in the reference's stored order, a destination takes
+ * a new best only on a strict improvement), then the walk back from the goal.  Among derivations of exactly equal
+ * weight (the same arcs in another order) the one found first in that order is reported.  Needs an fp64 CML_SPACE_LOG context
+ * whose lattices are all in the layered-CSR layout (CML_OPT_NO_ELL), like the samplers.
+ *   path_len[n_ex]       arcs of example e's best derivation (0: none)
+ *   path_base[n_ex + 1]  example e's arcs are path_arcs[path_base[e] .. path_base[e] + path_len[e])
+ *   path_arcs[cap]       arc-table ids in path order; cap >= the total number of lattice levels (cml_trellis_totals)
+ *   ln_weight[n_ex]      ln of the derivation's weight (-inf: none) */
+int cml_viterbi(cml_ctx* ctx, uint32_t* path_len, uint64_t* path_base, uint32_t* path_arcs, uint64_t cap, double* ln_weight);
 /* how the resident lattices are stored: examples / arcs / padded records in the level-sliced ELL layout
  * (throughput kernel) and examples in the layered-CSR layout (general kernels) */
 int cml_layout_stats(cml_ctx* ctx, uint64_t* ell_examples, uint64_t* ell_arcs, uint64_t* ell_records,

@@ -338,6 +338,49 @@ int real_main(int argc, char** argv) {
     for (double v : lnp) write_f64(o, v);
     return 0;
   }
+  if (lopt.count("dump-viterbi")) {
+    // best derivation of every training pair at the initial (normalised) weights: what `carmel -k 1` finds on the
+    // composed string x transducer x string machine (fst.h:769-800 bestPaths over makeGraph; graehl/shared/kbest.h).
+    // Restated as a max-plus pass over the derivation lattice in its topological order (reverse of the DFS post-order,
+    // graph.h:241-288), out-arcs in stored order, strict improvement; then the walk back from the goal.
+    std::ofstream o(lopt["dump-viterbi"]);
+    o.precision(17);
+    cascade.update();
+    IOIndex io(*result);
+    for (auto const& e : corpus.examples) {
+      Derivations d;
+      d.in = e.in;
+      d.out = e.out;
+      d.weight = e.weight;
+      if (!d.compute(*result, io, tr.arcs)) continue;
+      const unsigned n = (unsigned)d.g.size();
+      std::vector<unsigned> order;
+      d.make_order(order);
+      const double NI = -std::numeric_limits<double>::infinity();
+      std::vector<double> best(n, NI);
+      std::vector<unsigned> from(n, 0), via(n, 0);
+      best[0] = 0;
+      for (auto t = order.rbegin(); t != order.rend(); ++t) {
+        const unsigned s = *t;
+        if (!(best[s] > NI)) continue;
+        for (auto const& a : d.g[s]) {
+          const double c = best[s] + tr.arcs.t[a.id].arc->weight.w;
+          if (c > best[a.dest]) {
+            best[a.dest] = c;
+            from[a.dest] = s;
+            via[a.dest] = a.id;
+          }
+        }
+      }
+      std::vector<unsigned> path;
+      if (best[d.fin] > NI)
+        for (unsigned s = d.fin; s != 0; s = from[s]) path.push_back(via[s]);
+      o << best[d.fin] << " " << path.size();
+      for (size_t k = path.size(); k-- > 0;) o << " " << path[k];
+      o << "\n";
+    }
+    return 0;
+  }
   if (lopt.count("time-estimate")) {  // CPU baseline: time K E-steps (+M-steps) on this corpus
     unsigned K = (unsigned)atoi(lopt["time-estimate"].c_str());
     cascade.update();

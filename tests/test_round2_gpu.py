@@ -13,6 +13,7 @@
   * carmel-b200 --gpus=2 against one GPU (skipped on a one-GPU box).
 
 Tolerances (north_star): 1e-6 relative in fp64, 1e-4 in fp32."""
+import math
 import os
 import re
 
@@ -385,3 +386,60 @@ def test_cyclic_lattices_follow_the_reference_order(native_lib, oracle_bin, tmp_
         assert a[0] == b[0]
         assert abs(a[1] - b[1]) <= rel * max(1.0, abs(b[1])), (a, b)
     compare_wfst_text(out, oout, rel * 20)
+
+
+def _read_viterbi(path):
+    out = []
+    for ln in open(path):
+        head = ln.split("|")[0].split()
+        out.append((float(head[0]), [int(x) for x in head[2:2 + int(head[1])]]))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_viterbi_random_transducers(native_lib, oracle_bin, tmp_path, seed):
+    """--viterbi (cml_viterbi): the best derivation of every training pair -- weight and arc-table ids --
+    equals the oracle's max-plus pass over the same lattices (random weights: no ties)"""
+    from carmel_b200 import CLI_PATH
+    from helpers import random_wfst, sample_pairs
+    rng = np.random.default_rng(20270101 + seed)
+    ns = int(rng.integers(2, 7))
+    fst, ins, outs, arcs = random_wfst(rng, n_states=ns, eps_rate=float(rng.uniform(0, 0.4)))
+    corpus = sample_pairs(rng, arcs, ns, n_pairs=12, ins=ins, outs=outs)
+    f, c = os.path.join(str(tmp_path), "r.fst"), os.path.join(str(tmp_path), "r.data")
+    open(f, "w").write(fst)
+    open(c, "w").write(corpus)
+    rc, _, err = run(oracle_bin, ["-t", f"--dump-viterbi={tmp_path}/v.o", c, f])
+    assert rc == 0, err
+    rc, _, err = run(CLI_PATH, ["-t", f"--viterbi={tmp_path}/v.p", c, f])
+    assert rc == 0, err
+    want, got = _read_viterbi(f"{tmp_path}/v.o"), _read_viterbi(f"{tmp_path}/v.p")
+    assert len(want) == len(got) >= 5
+    for (wo, po), (wp, pp) in zip(want, got):
+        assert wo == wp or abs(wo - wp) <= 1e-9 * max(1.0, abs(wo)), (wo, wp)  # (-inf on both sides: only zero-weight derivations)
+        if wo == -math.inf:
+            continue
+        # derivations that use the same arcs in another order (an insertion here or there) have the same weight: which
+        # of them is reported depends on the order the states are visited in (layered order here, DFS order in the oracle)
+        assert po == pp or sorted(po) == sorted(pp), (po, pp)
+
+
+def test_viterbi_trained_cipher(native_lib, oracle_bin, tmp_path):
+    """the tutorial's decode step on its own training data: best derivations under the TRAINED cipher channel (the
+    reference's cipher.fst.trained) composed with the letter-bigram LM; also checks the member-arc labels of a path"""
+    from carmel_b200 import CLI_PATH
+    data, wfsa = stage(tmp_path, "cipher.data", "cipher.wfsa")
+    fst = os.path.join(str(tmp_path), "cipher.fst")
+    open(fst, "w").write(open(os.path.join(GOLDEN, "cipher.fst.trained")).read())
+    rc, _, err = run(oracle_bin, ["--train-cascade", f"--dump-viterbi={tmp_path}/v.o", data, wfsa, fst])
+    assert rc == 0, err
+    rc, _, err = run(CLI_PATH, ["--train-cascade", f"--viterbi={tmp_path}/v.p", data, wfsa, fst])
+    assert rc == 0, err
+    assert "Viterbi: best derivations of 10 examples" in err
+    want, got = _read_viterbi(f"{tmp_path}/v.o"), _read_viterbi(f"{tmp_path}/v.p")
+    assert len(want) == len(got) == 10
+    for (wo, po), (wp, pp) in zip(want, got):
+        assert abs(wo - wp) <= 1e-9 * abs(wo), (wo, wp)
+        assert po == pp
+    first = open(f"{tmp_path}/v.p").readline().split("|")[1]
+    assert first.count("(") == len(got[0][1])  # one group of member-arc labels per path arc
