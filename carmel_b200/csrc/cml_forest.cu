@@ -4,7 +4,10 @@
 // visit_inside_norm_outside (forest-em/forest.hpp:326-491,636-697), FForests::estimate / maximize
 // (forest-em/forest-em.hpp:511-572,626-655), NormalizeGroups (graehl/shared/normalize.hpp:123-164).
 //
-// Layout in HBM.  A forest arrives as the reference's pre-order node array.  Here back references are
+// Layout in HBM.  Three families (cml_forests_set_layout): level-synchronous tiles -- a CTA owns a run of forests, nodes
+// height-major across them, all values in shared memory (k_forest_level, the throughput path, described at the kernel);
+// per-forest height-levelised CSRs (k_forest_warp / k_forest_cta, described here); thread-per-forest streams
+// (k_forest_thread).  A forest arrives as the reference's pre-order node array.  Here back references are
 // resolved (a shared node is ONE node with several parents), the real nodes are sorted by height
 // (leaves = 0; a parent is strictly higher than its children), and the hyperedges are stored as two
 // CSRs over that order: children (inside pass, ascending height) and parents (outside pass, descending

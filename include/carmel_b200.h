@@ -465,7 +465,7 @@ enum cml_forest_layout { CML_FOREST_LAYOUT_AUTO = 0, CML_FOREST_LAYOUT_GROUP = 1
 int cml_forests_set_layout(cml_forests* f, int layout);
 /* level-synchronous tiles resident (CML_FOREST_LAYOUT_LEVEL, the AUTO choice for >= 256 forests that fit in shared
  * memory): forests, tiles (= CTAs per E-step), nodes, links, nodes of the largest tile, and how many of the tiles are
- * SMALL tiles (<= 13 KB of values: 128-thread CTAs, 16 per SM; the others are 512-thread CTAs with up to 100 KB) */
+ * SMALL tiles (<= 12 KB of values: 128-thread CTAs, 16 per SM; the others are 512-thread CTAs with up to 100 KB) */
 int cml_forests_level_stats(cml_forests* f, uint64_t* forests, uint64_t* tiles, uint64_t* nodes, uint64_t* links,
                             uint64_t* max_tile_nodes, uint64_t* small_tiles);
 /* thread-per-forest tiles resident: forests in tiles, tiles, real steps, padded steps, padded value rows x 32 */

@@ -117,7 +117,7 @@ def test_random_forests_thread_layout_without_stacks(fem, forest_oracle_bin, tmp
 @pytest.mark.parametrize("mode,rel", MODES)
 @pytest.mark.parametrize("small_kb", ["0", "1"])
 def test_level_layout_large_tiles(fem, forest_oracle_bin, tmp_path, monkeypatch, mode, rel, small_kb):
-    """the level layout has two tile classes (128-thread CTAs for runs of forests that fit 13 KB of values, 512-thread
+    """the level layout has two tile classes (128-thread CTAs for runs of forests that fit 12 KB of values, 512-thread
     CTAs for larger forests); with the small class switched off (0) or shrunk to 1 KB the same corpus runs on the large
     tiles, alone or mixed with small ones"""
     monkeypatch.setenv("CML_FOREST_LEVEL_SMEM_KB", small_kb)
