@@ -309,8 +309,15 @@ extern "C" int cml_build_trellises(cml_ctx* ctx, const cml_wfst_view* x, const c
   const uint32_t Q = x->n_states;
   const uint64_t n_arcs = x->n_arcs;
   const uint64_t n_ex = c->n_ex;
+  CML_REQUIRE(x->state_arc_off[0] == 0 && x->state_arc_off[Q] == n_arcs, CML_ERR_ARG,
+              "cml_build_trellises: state_arc_off must run from 0 to n_arcs");
+  for (uint32_t s = 0; s < Q; ++s)
+    CML_REQUIRE(x->state_arc_off[s] <= x->state_arc_off[s + 1], CML_ERR_ARG, "cml_build_trellises: state_arc_off not monotone");
   for (uint64_t a = 0; a < n_arcs; ++a)
     CML_REQUIRE(x->arc_dest[a] < Q, CML_ERR_ARG, "cml_build_trellises: arc destination out of range");
+  for (uint64_t e = 0; e < n_ex; ++e)
+    CML_REQUIRE(c->in_off[e] <= c->in_off[e + 1] && c->out_off[e] <= c->out_off[e + 1], CML_ERR_ARG,
+                "cml_build_trellises: corpus offsets not monotone");
   // ---- (in,out)-label index of the transducer: per state the arc-table ids grouped by label pair, groups in key order,
   // ids of a group in arc-table order
   std::vector<uint32_t> state_off(Q + 1, 0), range_begin, ids;
