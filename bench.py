@@ -619,7 +619,7 @@ def main():
         for key in ("parity", "parity_n"):
             if key in line and line[key] is not None and not line[key].get("ok", False):
                 bad.append(key)
-        for leg in ("dense_path", "c3", "c5"):
+        for leg in ("dense_path", "c3", "c5", "c4"):
             p = (line.get(leg) or {}).get("parity")
             if p is not None and not p.get("ok", False):
                 bad.append(f"{leg}.parity")

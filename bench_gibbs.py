@@ -30,6 +30,43 @@ def config_of(a, world):
                             "sampler is sequential over the corpus and stays on one GPU")}
 
 
+def sample_parity(files, n_lines=40, sweeps=3, seed=5, gpu=0):
+    """north_star: identical sampled derivations in sequential mode given the same uniform draws.  The exact sampler of
+    the product (carmel-b200 --crp, a separate process) and the CPU oracle run `sweeps` sweeps over the first n_lines of
+    the SAME corpus with the shared counter-based uniforms; the derivations of the last sweep and the per-sweep
+    cache-model probabilities must agree."""
+    from carmel_b200 import CLI_PATH
+    if not os.path.exists(ORACLE):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    d = tempfile.mkdtemp(prefix="cb200_gpar_")
+    try:
+        head = os.path.join(d, "head.data")
+        with open(files[0]) as f, open(head, "w") as g:
+            for _ in range(2 * n_lines):
+                g.write(f.readline())
+        models = [shutil.copy(m, d) for m in files[1:]]
+        common = ["--crp", "-M", str(sweeps), "--priors=0,1e-2", f"--seed={seed}", "-q"]
+        out = {}
+        for name, exe, extra in (("gpu", CLI_PATH, [f"--gpu={gpu}"]), ("cpu", ORACLE, [])):
+            r = subprocess.run([exe, *common, *extra, f"--history={d}/h.{name}", f"--dump-samples={d}/s.{name}", head, *models],
+                               capture_output=True, text=True, cwd=d, timeout=300)
+            if r.returncode != 0:
+                return {"n": 0, "ok": False, "error": f"{name}: rc {r.returncode}: {r.stderr[-200:]}"}
+            out[name] = ([ln.split() for ln in open(f"{d}/s.{name}")],
+                         [float(ln.split()[1]) for ln in open(f"{d}/h.{name}") if ln.strip()])
+        same = out["gpu"][0] == out["cpu"][0]
+        hg, hc = out["gpu"][1], out["cpu"][1]
+        rel = max((abs(a - b) / max(1.0, abs(b)) for a, b in zip(hg, hc)), default=0.0) if len(hg) == len(hc) else float("inf")
+        return {"n": len(out["cpu"][0]), "sweeps": sweeps, "identical_derivations": bool(same), "max_rel": rel, "tol": 1e-9,
+                "ok": bool(same and rel <= 1e-9),
+                "what": "exact sequential sampler, GPU command line vs CPU oracle on the first n lines with shared uniforms: "
+                        "sampled derivations of the last sweep and the per-sweep ln cache-model probabilities"}
+    except Exception as ex:  # noqa: BLE001
+        return {"n": 0, "ok": False, "error": f"{type(ex).__name__}: {ex}"[:300]}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def cpu_oracle_gibbs(files, n_lines, procs, sweeps=3):
     """samples/s of the CPU oracle's sequential sampler on the first n_lines, `procs` independent processes"""
     if not os.path.exists(ORACLE):
@@ -264,7 +301,9 @@ def run(a, rank, world, local, as_leg=False, with_cpu=True, token=None):
                 cpu = cpu_oracle_gibbs(w["files"], 25 * procs, procs, sweeps=2 if as_leg else 3)
             except Exception as ex:
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        parity = sample_parity(w["files"], gpu=local) if not sharded else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "parity": parity,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_of(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "collectives": int(collectives), "clocks": clocks,
