@@ -94,3 +94,22 @@ def test_unbuilt_sampler_options_are_refused(cli, tmp_path, opt):
     rc, _, err = run(cli, ["--crp=2", opt, *paths])
     assert rc != 0
     assert "not implemented on the --crp path" in err
+
+
+def test_multi_gpu_and_decode_options_fail_loudly(cli, tmp_path):
+    """host logic that needs no GPU to be checked: the exact --crp sampler is refused with --gpus (it is sequential over
+    the corpus; only --crp-batched sweeps shard), flags that change what is computed and are not built are refused, and
+    the decode / device-build entry points stop with the no-CPU-fallback error on a machine without a CUDA device rather
+    than computing anything on the host"""
+    import torch
+    paths = stage(tmp_path, "cipher.data", "cipher.wfsa", "cipher.fst")
+    rc, _, err = run(cli, ["--crp", "-M", "3", "--gpus=2", *paths])
+    assert rc != 0 and "sequential over the corpus" in err
+    for flag in ("-r", "-a"):
+        rc, _, err = run(cli, ["--train-cascade", flag, *paths])
+        assert rc != 0 and "not implemented on the training path" in err
+    if not torch.cuda.is_available():
+        for extra in (["--viterbi=" + str(tmp_path / "v")], ["--trellis-only", "--device-build"]):
+            rc, _, err = run(cli, ["--train-cascade", *extra, *paths])
+            assert rc != 0 and ("no CPU fallback" in err or "CUDA" in err), err
+            assert not (tmp_path / "v").exists() or (tmp_path / "v").stat().st_size == 0
